@@ -1,0 +1,309 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end to the two CPU oracle builds.
+
+    kind="ref"  -> oracle/_ref/libbfir_ref.so     the UNMODIFIED reference sources (compiled from
+                   /root/reference/brutefir through oracle/ref_shim; see oracle/Makefile)
+    kind="port" -> oracle/_build/libbfir_oracle.so the restatement in oracle/bfir_oracle.cpp
+
+Both export the same entry points (prefix ``ref_`` / ``orc_``), so every test can be run against
+either.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs
+may import this package; the product (foo-dsp-bfir_b200/) never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libbfir_ref.so")
+PORT_SO = os.path.join(HERE, "_build", "libbfir_oracle.so")
+
+# sample formats, reference brutefir/global.h:24-37
+S8, S16_LE, S16_BE, S24_LE, S24_BE, S32_LE, S32_BE, FLOAT_LE, FLOAT_BE, FLOAT64_LE, FLOAT64_BE = range(1, 12)
+FORMAT_BYTES = {S8: 1, S16_LE: 2, S16_BE: 2, S24_LE: 3, S24_BE: 3, S32_LE: 4, S32_BE: 4,
+                FLOAT_LE: 4, FLOAT_BE: 4, FLOAT64_LE: 8, FLOAT64_BE: 8}
+MIX_INPUT, MIX_INPUT_ADD, MIX_OUTPUT = 1, 2, 3
+
+
+class Overflow(ctypes.Structure):  # bfoverflow_t, global.h:96-102
+    _fields_ = [("n_overflows", ctypes.c_uint), ("intlargest", ctypes.c_int32),
+                ("largest", ctypes.c_double), ("max", ctypes.c_double)]
+
+    def as_tuple(self):
+        return (self.n_overflows, self.intlargest, self.largest, self.max)
+
+
+def build(kind="all", quiet=True):
+    """Compile the oracle libraries (gcc only). `ref` needs /root/reference and is skipped without it."""
+    out = subprocess.run(["make", "-C", HERE, kind], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+def available(kind):
+    return os.path.exists(REF_SO if kind == "ref" else PORT_SO)
+
+
+def best_kind():
+    """'ref' (the real reference sources) when its prebuilt .so is here, else the port."""
+    return "ref" if available("ref") else "port"
+
+
+_libs = {}
+
+
+def lib(kind):
+    if kind in _libs:
+        return _libs[kind]
+    path = REF_SO if kind == "ref" else PORT_SO
+    if not os.path.exists(path):
+        build("ref" if kind == "ref" else "port")
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)
+    L = ctypes.CDLL(path)
+    p = "ref_" if kind == "ref" else "orc_"
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+
+    def sig(name, res, *args):
+        f = getattr(L, p + name)
+        f.restype = res
+        f.argtypes = list(args)
+        return f
+
+    ns = type("OracleNS", (), {})()
+    ns.kind = kind
+    ns.conv_new = sig("conv_new", vp, ci, ci, ci, ci)
+    ns.conv_delete = sig("conv_delete", None, vp)
+    ns.conv_cbufsize = sig("conv_cbufsize", ci, vp)
+    ns.conv_raw2cbuf = sig("conv_raw2cbuf", ci, vp, vp, vp, vp, ci, ci, ci)
+    ns.conv_time2freq = sig("conv_time2freq", None, vp, vp, vp)
+    ns.conv_freq2time = sig("conv_freq2time", None, vp, vp, vp)
+    ns.conv_mixnscale = sig("conv_mixnscale", None, vp, ctypes.POINTER(vp), vp, ctypes.POINTER(cd), ci, ci)
+    ns.conv_convolve_inplace = sig("conv_convolve_inplace", None, vp, vp, vp)
+    ns.conv_convolve = sig("conv_convolve", None, vp, vp, vp, vp)
+    ns.conv_convolve_add = sig("conv_convolve_add", None, vp, vp, vp, vp)
+    ns.conv_crossfade_inplace = sig("conv_crossfade_inplace", None, vp, vp, vp, vp)
+    ns.conv_dirac_convolve = sig("conv_dirac_convolve", None, vp, vp, vp)
+    ns.conv_dirac_convolve_inplace = sig("conv_dirac_convolve_inplace", None, vp, vp)
+    ns.conv_convolve_eval = sig("conv_convolve_eval", None, vp, vp, vp, vp)
+    ns.conv_cbuf2raw = sig("conv_cbuf2raw", ci, vp, vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(Overflow))
+    ns.conv_coeffs2cbuf = sig("conv_coeffs2cbuf", ci, vp, vp, ci, cd, vp)
+    ns.conv_runtime_coeffs2cbuf = sig("conv_runtime_coeffs2cbuf", None, vp, vp, vp)
+    ns.conv_dither_table_size = sig("conv_dither_table_size", ci, vp)
+    ns.conv_dither_table = sig("conv_dither_table", ctypes.POINTER(ctypes.c_int8), vp)
+    ns.conv_dither_ptr = sig("conv_dither_ptr", ci, vp, ci)
+    ns.conv_dither_map = sig("conv_dither_map", None, vp, vp)
+    ns.raw2real = sig("raw2real", None, ci, vp, vp, ci, ci, ci, ci, ci, ci)
+    ns.bfir_new = sig("bfir_new", vp, ci, ci, ci, ci, ci, ci, ci, ci)
+    ns.bfir_delete = sig("bfir_delete", None, vp)
+    ns.bfir_is_initialized = sig("bfir_is_initialized", ci, vp)
+    ns.bfir_set_coeff = sig("bfir_set_coeff", ci, vp, ctypes.POINTER(vp), ci, ci, ci, cd)
+    ns.bfir_run = sig("bfir_run", ci, vp, vp, vp)
+    ns.bfir_reset = sig("bfir_reset", None, vp)
+    ns.bfir_get_overflow = sig("bfir_get_overflow", None, vp, ci, ctypes.POINTER(Overflow))
+    ns.bfir_dither_ptr = sig("bfir_dither_ptr", ci, vp, ci)
+    ns.bfir_blockcounter = sig("bfir_blockcounter", ctypes.c_uint, vp)
+    ns.preprocess_coeff = sig("preprocess_coeff", ci, vp, vp, ci, ci, ci, ci, cd, vp)
+    ns.equalizer_render = sig("equalizer_render", ci, ci, ci, ci, ci, ci, ci,
+                              ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(cd), vp, ci)
+    ns.fft_provider = sig("fft_provider", ctypes.c_char_p)
+    _libs[kind] = ns
+    return ns
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def real_dtype(realsize):
+    return np.float32 if realsize == 4 else np.float64
+
+
+class Convolver:
+    """The reference's `fftw_convolver` (brutefir/fftw_convolver.hpp:28-166) on host numpy cbufs."""
+
+    def __init__(self, length, realsize, kind=None, n_channels=1, sample_rate=44100):
+        self.ns = lib(kind or best_kind())
+        self.L, self.N, self.realsize = length, 2 * length, realsize
+        self.dtype = real_dtype(realsize)
+        self.h = self.ns.conv_new(length, realsize, n_channels, sample_rate)
+        if not self.h:
+            raise ValueError("invalid convolver parameters")
+
+    def close(self):
+        if self.h:
+            self.ns.conv_delete(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def cbuf(self, n=None):
+        return np.zeros(self.N if n is None else n, dtype=self.dtype)
+
+    def cbufsize(self):
+        return self.ns.conv_cbufsize(self.h)
+
+    def raw2cbuf(self, raw, cbuf, next_cbuf, fmt, index, spacing):
+        assert self.ns.conv_raw2cbuf(self.h, _ptr(raw), _ptr(cbuf), _ptr(next_cbuf), fmt, index, spacing) == 0
+
+    def time2freq(self, x, out=None):
+        out = self.cbuf() if out is None else out
+        self.ns.conv_time2freq(self.h, _ptr(x), _ptr(out))
+        return out
+
+    def freq2time(self, x, out=None):
+        out = self.cbuf() if out is None else out
+        self.ns.conv_freq2time(self.h, _ptr(x), _ptr(out))
+        return out
+
+    def mixnscale(self, bufs, scales, mixmode, out=None):
+        out = self.cbuf() if out is None else out
+        n = len(bufs)
+        arr = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sc = (ctypes.c_double * n)(*[float(s) for s in scales])
+        self.ns.conv_mixnscale(self.h, arr, _ptr(out), sc, n, mixmode)
+        return out
+
+    def convolve(self, x, c, out=None):
+        out = self.cbuf() if out is None else out
+        self.ns.conv_convolve(self.h, _ptr(x), _ptr(c), _ptr(out))
+        return out
+
+    def convolve_add(self, x, c, out):
+        self.ns.conv_convolve_add(self.h, _ptr(x), _ptr(c), _ptr(out))
+        return out
+
+    def convolve_inplace(self, x, c):
+        self.ns.conv_convolve_inplace(self.h, _ptr(x), _ptr(c))
+        return x
+
+    def crossfade_inplace(self, x, xfade, buffer):
+        self.ns.conv_crossfade_inplace(self.h, _ptr(x), _ptr(xfade), _ptr(buffer))
+        return x
+
+    def dirac_convolve(self, x, out=None):
+        out = self.cbuf() if out is None else out
+        self.ns.conv_dirac_convolve(self.h, _ptr(x), _ptr(out))
+        return out
+
+    def dirac_convolve_inplace(self, x):
+        self.ns.conv_dirac_convolve_inplace(self.h, _ptr(x))
+        return x
+
+    def convolve_eval(self, x, buffer, out=None):
+        out = self.cbuf() if out is None else out
+        self.ns.conv_convolve_eval(self.h, _ptr(x), _ptr(buffer), _ptr(out))
+        return out
+
+    def cbuf2raw(self, cbuf, out_raw, fmt, index, spacing, apply_dither, dither_channel, overflow):
+        assert self.ns.conv_cbuf2raw(self.h, _ptr(cbuf), _ptr(out_raw), fmt, index, spacing,
+                                     int(apply_dither), dither_channel, ctypes.byref(overflow)) == 0
+
+    def coeffs2cbuf(self, coeffs, scale=1.0, n=None, out=None):
+        out = self.cbuf() if out is None else out
+        coeffs = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        rc = self.ns.conv_coeffs2cbuf(self.h, _ptr(coeffs), len(coeffs) if n is None else n, scale, _ptr(out))
+        return out if rc == 0 else None
+
+    def runtime_coeffs2cbuf(self, src, out=None):
+        out = self.cbuf() if out is None else out
+        src = np.ascontiguousarray(src, dtype=self.dtype)
+        self.ns.conv_runtime_coeffs2cbuf(self.h, _ptr(src), _ptr(out))
+        return out
+
+    def preprocess_coeff(self, coeffs, blocks, scale=1.0):
+        coeffs = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        out = np.zeros((blocks, self.N), dtype=self.dtype)
+        rc = self.ns.preprocess_coeff(self.h, _ptr(coeffs), self.L, blocks, len(coeffs), self.realsize, scale, _ptr(out))
+        return out if rc == 0 else None
+
+    def dither_table(self):
+        n = self.ns.conv_dither_table_size(self.h)
+        p = self.ns.conv_dither_table(self.h)
+        return np.ctypeslib.as_array(p, shape=(n,)).copy()
+
+    def dither_map(self):
+        out = np.zeros(511, dtype=self.dtype)
+        self.ns.conv_dither_map(self.h, _ptr(out))
+        return out
+
+    def dither_ptr(self, ch):
+        return self.ns.conv_dither_ptr(self.h, ch)
+
+
+class Engine:
+    """The reference's `brutefir` class (brutefir/brutefir.hpp:15-52)."""
+
+    def __init__(self, filter_length, filter_blocks, realsize, channels, in_format, out_format,
+                 sampling_rate, apply_dither, kind=None):
+        kind = kind or best_kind()
+        if kind == "ref" and channels > 8:  # BF_MAXCHANNELS, global.h:21
+            kind = "port"
+        self.ns = lib(kind)
+        self.kind = kind
+        self.L, self.P, self.C, self.realsize = filter_length, filter_blocks, channels, realsize
+        self.in_format, self.out_format = in_format, out_format
+        self.dtype = real_dtype(realsize)
+        self.h = self.ns.bfir_new(filter_length, filter_blocks, realsize, channels, in_format, out_format,
+                                  sampling_rate, int(apply_dither))
+        if not self.h:
+            raise ValueError("invalid engine parameters")
+
+    def close(self):
+        if self.h:
+            self.ns.bfir_delete(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def is_initialized(self):
+        return bool(self.ns.bfir_is_initialized(self.h))
+
+    def set_coeff(self, coeffs, coeff_blocks, scale=1.0, length=None):
+        arrs = [np.ascontiguousarray(c, dtype=self.dtype) for c in coeffs]
+        length = len(arrs[0]) if length is None else length
+        ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        return self.ns.bfir_set_coeff(self.h, ptrs, len(arrs), length, coeff_blocks, scale)
+
+    def run(self, inbuf, outbuf=None):
+        if outbuf is None:
+            outbuf = np.zeros(self.L * self.C * FORMAT_BYTES[self.out_format], dtype=np.uint8)
+        rc = self.ns.bfir_run(self.h, _ptr(inbuf), _ptr(outbuf))
+        return rc, outbuf
+
+    def reset(self):
+        self.ns.bfir_reset(self.h)
+
+    def overflow(self, ch):
+        o = Overflow()
+        self.ns.bfir_get_overflow(self.h, ch, ctypes.byref(o))
+        return o
+
+    def dither_ptr(self, ch):
+        return self.ns.bfir_dither_ptr(self.h, ch)
+
+    def blockcounter(self):
+        return self.ns.bfir_blockcounter(self.h)
+
+
+def equalizer_render(block_length, n_blocks, realsize, sampling_rate, freq, mag, phase, kind=None, n_channels=1):
+    ns = lib(kind or best_kind())
+    taps = block_length * n_blocks
+    out = np.zeros(taps // 2, dtype=real_dtype(realsize))
+    n = len(freq)
+    arr = lambda v: (ctypes.c_double * n)(*[float(x) for x in v])
+    rc = ns.equalizer_render(block_length, n_blocks, realsize, n_channels, sampling_rate, n, arr(freq), arr(mag),
+                             arr(phase), _ptr(out), len(out))
+    if rc < 0:
+        raise ValueError("equalizer_render failed")
+    return out
