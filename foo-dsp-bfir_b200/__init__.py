@@ -1,0 +1,425 @@
+"""foo-dsp-bfir_b200 -- B200 (sm_100a) partitioned-convolution engine behind the BruteFIR surface.
+
+This module is the thin Python host mirror of the two reference classes the C ABI replaces
+(``include/bfir_b200.h``):
+
+* :class:`Brutefir`       <-> ``class brutefir``        (reference brutefir/brutefir.hpp:15-52)
+* :class:`FftwConvolver`  <-> ``class fftw_convolver``  (reference brutefir/fftw_convolver.hpp:28-166)
+
+Method names, argument order and return codes follow the reference.  Everything executes in
+``libbfir_b200.so`` (hand-written CUDA); there is no CPU path -- loading fails loudly when the library
+has not been built (``python __graft_entry__.py`` or ``make -C foo-dsp-bfir_b200``), and creating an
+engine fails loudly when no CUDA device is present.
+
+The directory name contains hyphens, so import it with
+``importlib.import_module("foo-dsp-bfir_b200")`` (tests/conftest.py and bench.py do).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbfir_b200.so")
+
+OK, ERR_NONFINITE, ERR_COEFF, ERR_NOT_READY, ERR_INVALID, ERR_CUDA = 0, -1, -2, -3, -4, -5
+
+# sample formats (reference brutefir/global.h:24-37)
+S8, S16_LE, S16_BE, S24_LE, S24_BE, S32_LE, S32_BE, FLOAT_LE, FLOAT_BE, FLOAT64_LE, FLOAT64_BE = range(1, 12)
+FORMAT_BYTES = {S8: 1, S16_LE: 2, S16_BE: 2, S24_LE: 3, S24_BE: 3, S32_LE: 4, S32_BE: 4,
+                FLOAT_LE: 4, FLOAT_BE: 4, FLOAT64_LE: 8, FLOAT64_BE: 8}
+MIXMODE_INPUT, MIXMODE_INPUT_ADD, MIXMODE_OUTPUT = 1, 2, 3
+
+
+class BfirError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("bfir_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Overflow(ctypes.Structure):  # bfir_overflow_t == struct bfoverflow_t (global.h:96-102)
+    _fields_ = [("n_overflows", ctypes.c_uint), ("intlargest", ctypes.c_int32),
+                ("largest", ctypes.c_double), ("max", ctypes.c_double)]
+
+    def as_tuple(self):
+        return (self.n_overflows, self.intlargest, self.largest, self.max)
+
+
+class Config(ctypes.Structure):  # bfir_config_t
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "filter_length", "filter_blocks", "realsize", "channels", "in_format", "out_format",
+        "sampling_rate", "apply_dither", "n_streams", "device", "part_begin", "part_count")]
+
+
+# every symbol include/bfir_b200.h declares: (name, restype, argtypes)
+_vp, _ci, _cd, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+_pp = ctypes.POINTER(ctypes.c_void_p)
+PRINT_CB = ctypes.CFUNCTYPE(None, ctypes.c_char_p)
+API = [
+    ("bfir_create", _ci, [_pp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci]),
+    ("bfir_create_ex", _ci, [_pp, ctypes.POINTER(Config)]),
+    ("bfir_destroy", None, [_vp]),
+    ("bfir_is_initialized", _ci, [_vp]),
+    ("bfir_set_coeff", _ci, [_vp, _pp, _ci, _ci, _ci, _cd]),
+    ("bfir_run", _ci, [_vp, _vp, _vp]),
+    ("bfir_run_device", _ci, [_vp, _vp, _vp]),
+    ("bfir_sync", _ci, [_vp]),
+    ("bfir_reset", _ci, [_vp]),
+    ("bfir_get_overflow", _ci, [_vp, _ci, ctypes.POINTER(Overflow)]),
+    ("bfir_check_overflows", _ci, [_vp]),
+    ("bfir_get_dither_ptr", _ci, [_vp, _ci, ctypes.POINTER(_ci)]),
+    ("bfir_get_blockcounter", _ci, [_vp, ctypes.POINTER(ctypes.c_uint)]),
+    ("bfir_run_partial_device", _ci, [_vp, _vp]),
+    ("bfir_run_finish_device", _ci, [_vp, _vp]),
+    ("bfir_acc_device_ptr", _vp, [_vp, ctypes.POINTER(_sz)]),
+    ("bfir_set_stream", _ci, [_vp, _vp]),
+    ("bfir_set_print_callback", None, [PRINT_CB]),
+    ("bfir_last_error", ctypes.c_char_p, []),
+    ("bfir_kernel_launch_count", ctypes.c_ulonglong, []),
+    ("bfir_conv_create", _ci, [_pp, _ci, _ci, _ci, _ci]),
+    ("bfir_conv_destroy", None, [_vp]),
+    ("bfir_conv_cbufsize", _ci, [_vp]),
+    ("bfir_conv_alloc", _vp, [_vp, _sz]),
+    ("bfir_conv_free", None, [_vp, _vp]),
+    ("bfir_conv_upload", _ci, [_vp, _vp, _vp, _sz]),
+    ("bfir_conv_download", _ci, [_vp, _vp, _vp, _sz]),
+    ("bfir_conv_sync", _ci, [_vp]),
+    ("bfir_conv_raw2cbuf", _ci, [_vp, _vp, _vp, _vp, _ci, _ci, _ci]),
+    ("bfir_conv_time2freq", _ci, [_vp, _vp, _vp]),
+    ("bfir_conv_mixnscale", _ci, [_vp, _pp, _vp, ctypes.POINTER(_cd), _ci, _ci]),
+    ("bfir_conv_convolve_inplace", _ci, [_vp, _vp, _vp]),
+    ("bfir_conv_convolve", _ci, [_vp, _vp, _vp, _vp]),
+    ("bfir_conv_convolve_add", _ci, [_vp, _vp, _vp, _vp]),
+    ("bfir_conv_crossfade_inplace", _ci, [_vp, _vp, _vp, _vp]),
+    ("bfir_conv_dirac_convolve", _ci, [_vp, _vp, _vp]),
+    ("bfir_conv_dirac_convolve_inplace", _ci, [_vp, _vp]),
+    ("bfir_conv_freq2time", _ci, [_vp, _vp, _vp]),
+    ("bfir_conv_convolve_eval", _ci, [_vp, _vp, _vp, _vp]),
+    ("bfir_conv_cbuf2raw", _ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, ctypes.POINTER(Overflow)]),
+    ("bfir_conv_coeffs2cbuf", _ci, [_vp, _vp, _ci, _cd, _vp]),
+    ("bfir_conv_runtime_coeffs2cbuf", _ci, [_vp, _vp, _vp]),
+    ("bfir_conv_dither_table_size", _ci, [_vp]),
+    ("bfir_conv_dither_table", _ci, [_vp, _vp, _ci]),
+    ("bfir_conv_dither_map", _ci, [_vp, _vp]),
+    ("bfir_conv_dither_ptr", _ci, [_vp, _ci]),
+]
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen libbfir_b200.so and bind every exported symbol. Raises if the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise FileNotFoundError(
+            "%s not built: run `python __graft_entry__.py` (or make -C foo-dsp-bfir_b200). "
+            "There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
+    for name, res, args in API:
+        f = getattr(lib, name)  # AttributeError here = header and library out of sync
+        f.restype = res
+        f.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load_library().bfir_last_error().decode("utf-8", "replace")
+
+
+def kernel_launch_count():
+    return int(load_library().bfir_kernel_launch_count())
+
+
+def _check(rc):
+    if rc < 0:
+        raise BfirError(rc, last_error())
+    return rc
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return ctypes.c_void_p(a.data_ptr())
+    if hasattr(a, "ptr"):
+        return ctypes.c_void_p(a.ptr)
+    return a
+
+
+def real_dtype(realsize):
+    return np.float32 if realsize == 4 else np.float64
+
+
+class _CudaArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (int(n),), "typestr": typestr, "version": 2}
+
+
+def as_torch(ptr, n, typestr):
+    """View `n` elements of device memory at `ptr` as a torch tensor (plumbing for NCCL reduces)."""
+    import torch
+    return torch.as_tensor(_CudaArray(ptr, n, typestr), device="cuda")
+
+
+class Brutefir:
+    """``class brutefir`` (reference brutefir/brutefir.hpp:15-52) on the GPU.
+
+    ``run`` takes/returns HOST buffers of ``filter_length * channels`` interleaved samples exactly like
+    the reference; ``run_device`` is the asynchronous device-buffer variant used for throughput.
+    Extra keyword arguments (``n_streams``, ``device``, ``part_begin``, ``part_count``) map to
+    ``bfir_config_t`` and have no reference counterpart.
+    """
+
+    def __init__(self, filter_length, filter_blocks, realsize, channels, in_format, out_format,
+                 sampling_rate, apply_dither, n_streams=1, device=-1, part_begin=0, part_count=0):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        cfg = Config(filter_length, filter_blocks, realsize, channels, in_format, out_format,
+                     sampling_rate, int(bool(apply_dither)), n_streams, device, part_begin, part_count)
+        rc = self.lib.bfir_create_ex(ctypes.byref(self.h), ctypes.byref(cfg))
+        if rc != OK:
+            self.h = ctypes.c_void_p()
+            # the reference constructor cannot fail loudly (is_initialized() stays false); we do
+            raise BfirError(rc, last_error())
+        self.filter_length, self.filter_blocks, self.realsize = filter_length, filter_blocks, realsize
+        self.channels, self.n_streams = channels, n_streams
+        self.in_format, self.out_format = in_format, out_format
+        self.dtype = real_dtype(realsize)
+        self.in_bytes = n_streams * filter_length * channels * FORMAT_BYTES[in_format]
+        self.out_bytes = n_streams * filter_length * channels * FORMAT_BYTES[out_format]
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.bfir_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def is_initialized(self):
+        return bool(self.lib.bfir_is_initialized(self.h))
+
+    def set_coeff(self, coeffs, coeff_blocks, scale=1.0, length=None):
+        """set_coeff(void **coeffs, n_coeffs, length, coeff_blocks, scale): returns 0 or -2."""
+        arrs = [np.ascontiguousarray(c, dtype=self.dtype) for c in coeffs]
+        length = (len(arrs[0]) if arrs else 0) if length is None else length
+        ptrs = (ctypes.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
+        rc = self.lib.bfir_set_coeff(self.h, ptrs, len(arrs), length, coeff_blocks, float(scale))
+        if rc not in (OK, ERR_COEFF):
+            raise BfirError(rc, last_error())
+        return rc
+
+    def run(self, inbuf, outbuf=None):
+        """run(void *inbuf, void *outbuf) -> (rc, outbuf); rc is 0 or -1 like the reference."""
+        if outbuf is None:
+            outbuf = np.empty(self.out_bytes, dtype=np.uint8)
+        rc = self.lib.bfir_run(self.h, _ptr(inbuf), _ptr(outbuf))
+        if rc not in (OK, ERR_NONFINITE):
+            raise BfirError(rc, last_error())
+        return rc, outbuf
+
+    def run_device(self, d_in, d_out):
+        _check(self.lib.bfir_run_device(self.h, _ptr(d_in), _ptr(d_out)))
+
+    def run_partial_device(self, d_in):
+        _check(self.lib.bfir_run_partial_device(self.h, _ptr(d_in)))
+
+    def run_finish_device(self, d_out):
+        _check(self.lib.bfir_run_finish_device(self.h, _ptr(d_out)))
+
+    def acc_device_ptr(self):
+        n = ctypes.c_size_t()
+        p = self.lib.bfir_acc_device_ptr(self.h, ctypes.byref(n))
+        return p, n.value
+
+    def sync(self):
+        rc = self.lib.bfir_sync(self.h)
+        if rc not in (OK, ERR_NONFINITE):
+            raise BfirError(rc, last_error())
+        return rc
+
+    def set_stream(self, cuda_stream):
+        _check(self.lib.bfir_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+
+    def reset(self):
+        _check(self.lib.bfir_reset(self.h))
+
+    def check_overflows(self):
+        return _check(self.lib.bfir_check_overflows(self.h))
+
+    def overflow(self, channel):
+        o = Overflow()
+        _check(self.lib.bfir_get_overflow(self.h, channel, ctypes.byref(o)))
+        return o
+
+    def dither_ptr(self, channel):
+        v = ctypes.c_int()
+        _check(self.lib.bfir_get_dither_ptr(self.h, channel, ctypes.byref(v)))
+        return v.value
+
+    def blockcounter(self):
+        v = ctypes.c_uint()
+        _check(self.lib.bfir_get_blockcounter(self.h, ctypes.byref(v)))
+        return v.value
+
+
+class DeviceBuf:
+    """A device buffer owned by a convolver (the reference's callers own host cbufs instead)."""
+
+    def __init__(self, conv, nbytes):
+        self.conv, self.nbytes = conv, nbytes
+        self.ptr = conv.lib.bfir_conv_alloc(conv.h, nbytes)
+        if not self.ptr:
+            raise BfirError(ERR_CUDA, "bfir_conv_alloc(%d) failed" % nbytes)
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _check(self.conv.lib.bfir_conv_upload(self.conv.h, ctypes.c_void_p(self.ptr), _ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, dtype, count=None):
+        dtype = np.dtype(dtype)
+        count = self.nbytes // dtype.itemsize if count is None else count
+        out = np.empty(count, dtype=dtype)
+        _check(self.conv.lib.bfir_conv_download(self.conv.h, _ptr(out), ctypes.c_void_p(self.ptr), out.nbytes))
+        return out
+
+    def offset(self, nbytes):
+        return self.ptr + nbytes
+
+    def free(self):
+        if self.ptr:
+            self.conv.lib.bfir_conv_free(self.conv.h, ctypes.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class FftwConvolver:
+    """``class fftw_convolver`` (reference brutefir/fftw_convolver.hpp:28-166) on device cbufs."""
+
+    def __init__(self, length, realsize, n_dither_channels=1, sampling_rate=44100):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.bfir_conv_create(ctypes.byref(self.h), length, realsize, n_dither_channels, sampling_rate)
+        if rc != OK:
+            self.h = ctypes.c_void_p()
+            raise BfirError(rc, last_error())
+        self.length, self.n_fft, self.realsize = length, 2 * length, realsize
+        self.dtype = real_dtype(realsize)
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.bfir_conv_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # buffers
+    def cbuf(self, data=None, n_cbufs=1.0):
+        b = DeviceBuf(self, int(self.convolver_cbufsize() * n_cbufs))
+        if data is not None:
+            b.upload(np.ascontiguousarray(data, dtype=self.dtype))
+        return b
+
+    def rawbuf(self, data=None, nbytes=None):
+        b = DeviceBuf(self, nbytes if nbytes is not None else np.asarray(data).nbytes)
+        if data is not None:
+            b.upload(data)
+        return b
+
+    def get(self, buf, count=None):
+        return buf.download(self.dtype, count)
+
+    # entry points, reference names
+    def convolver_cbufsize(self):
+        return self.lib.bfir_conv_cbufsize(self.h)
+
+    def convolver_raw2cbuf(self, rawbuf, cbuf, next_cbuf, fmt, byte_offset, sample_spacing):
+        _check(self.lib.bfir_conv_raw2cbuf(self.h, _ptr(rawbuf), _ptr(cbuf), _ptr(next_cbuf), fmt, byte_offset, sample_spacing))
+
+    def convolver_time2freq(self, input_cbuf, output_cbuf):
+        _check(self.lib.bfir_conv_time2freq(self.h, _ptr(input_cbuf), _ptr(output_cbuf)))
+
+    def convolver_mixnscale(self, input_cbufs, output_cbuf, scales, mixmode):
+        n = len(input_cbufs)
+        arr = (ctypes.c_void_p * n)(*[b.ptr for b in input_cbufs])
+        sc = (ctypes.c_double * n)(*[float(s) for s in scales])
+        return self.lib.bfir_conv_mixnscale(self.h, arr, _ptr(output_cbuf), sc, n, mixmode)
+
+    def convolver_convolve_inplace(self, cbuf, coeffs):
+        _check(self.lib.bfir_conv_convolve_inplace(self.h, _ptr(cbuf), _ptr(coeffs)))
+
+    def convolver_convolve(self, input_cbuf, coeffs, output_cbuf):
+        _check(self.lib.bfir_conv_convolve(self.h, _ptr(input_cbuf), _ptr(coeffs), _ptr(output_cbuf)))
+
+    def convolver_convolve_add(self, input_cbuf, coeffs, output_cbuf):
+        _check(self.lib.bfir_conv_convolve_add(self.h, _ptr(input_cbuf), _ptr(coeffs), _ptr(output_cbuf)))
+
+    def convolver_crossfade_inplace(self, input_cbuf, crossfade_cbuf, buffer_cbuf):
+        _check(self.lib.bfir_conv_crossfade_inplace(self.h, _ptr(input_cbuf), _ptr(crossfade_cbuf), _ptr(buffer_cbuf)))
+
+    def convolver_dirac_convolve(self, input_cbuf, output_cbuf):
+        _check(self.lib.bfir_conv_dirac_convolve(self.h, _ptr(input_cbuf), _ptr(output_cbuf)))
+
+    def convolver_dirac_convolve_inplace(self, cbuf):
+        _check(self.lib.bfir_conv_dirac_convolve_inplace(self.h, _ptr(cbuf)))
+
+    def convolver_freq2time(self, input_cbuf, output_cbuf):
+        _check(self.lib.bfir_conv_freq2time(self.h, _ptr(input_cbuf), _ptr(output_cbuf)))
+
+    def convolver_convolve_eval(self, input_cbuf, buffer_cbuf, output_cbuf):
+        _check(self.lib.bfir_conv_convolve_eval(self.h, _ptr(input_cbuf), _ptr(buffer_cbuf), _ptr(output_cbuf)))
+
+    def convolver_cbuf2raw(self, cbuf, outbuf, fmt, byte_offset, sample_spacing, apply_dither, dither_channel, overflow):
+        _check(self.lib.bfir_conv_cbuf2raw(self.h, _ptr(cbuf), _ptr(outbuf), fmt, byte_offset, sample_spacing,
+                                           int(bool(apply_dither)), dither_channel, ctypes.byref(overflow)))
+
+    def convolver_coeffs2cbuf(self, coeffs, n_coeffs, scale, dest):
+        """Returns 0, or -2 where the reference returns NULL (NaN/Inf among coefficients)."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        rc = self.lib.bfir_conv_coeffs2cbuf(self.h, _ptr(coeffs), n_coeffs, float(scale), _ptr(dest))
+        if rc not in (OK, ERR_COEFF):
+            raise BfirError(rc, last_error())
+        return rc
+
+    def convolver_runtime_coeffs2cbuf(self, src, dest):
+        _check(self.lib.bfir_conv_runtime_coeffs2cbuf(self.h, _ptr(src), _ptr(dest)))
+
+    def sync(self):
+        _check(self.lib.bfir_conv_sync(self.h))
+
+    # dither inspection
+    def dither_table(self):
+        n = _check(self.lib.bfir_conv_dither_table_size(self.h))
+        out = np.empty(n, dtype=np.int8)
+        _check(self.lib.bfir_conv_dither_table(self.h, _ptr(out), n))
+        return out
+
+    def dither_map(self):
+        out = np.empty(512, dtype=self.dtype)
+        _check(self.lib.bfir_conv_dither_map(self.h, _ptr(out)))
+        return out
+
+    def dither_ptr(self, channel):
+        return _check(self.lib.bfir_conv_dither_ptr(self.h, channel))

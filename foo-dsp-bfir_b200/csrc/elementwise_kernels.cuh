@@ -1,0 +1,238 @@
+// Stand-alone kernels behind the reference's per-function convolver entry points (the "inner"
+// surface, brutefir/fftw_convolver.hpp:39-133) and the serial dither requantiser. They operate on
+// device cbufs in the reference's own layouts, so each can be compared with the oracle on identical
+// buffers. Arithmetic uses the reference's operation order with explicitly unfused multiplies and
+// adds (the reference is an SSE2 build without FMA), which makes these entry points bit-exact.
+#pragma once
+#include "rfft_kernels.cuh"
+
+namespace bfir {
+
+enum { MIXMODE_INPUT = 1, MIXMODE_INPUT_ADD = 2, MIXMODE_OUTPUT = 3 }; // fftw_convolver.hpp:14-16
+#define BFIR_MAX_MIX_BUFS 64
+
+struct MixArgs {
+    const void *in[BFIR_MAX_MIX_BUFS];
+    double scales[BFIR_MAX_MIX_BUFS];
+    void *out;
+    int n_bufs, mixmode, N;
+};
+
+struct DitherState {          // device image of dither_state_t (global.h:63-69)
+    int randtab_ptr;
+    int tab0;                 // private copy of dither_randtab[0] (the reference shares one byte, dither.cpp:133)
+    double err[2];            // sf[] / sd[] error feedback, stored widened
+};
+
+struct DitherArgs {
+    const void *real;         // [channels][L] reals
+    void *raw;                // interleaved raw output
+    long long raw_stream_stride; // bytes
+    int fmt, ch_per_stream, L, n_channels;
+    const int8_t *randtab;
+    int randtab_size;
+    const void *randmap;      // 512 entries [-256..255] of T
+    DitherState *dstate;      // [channels]
+    OverflowStats *stats;     // [channels]
+    int single_channel;       // >= 0: inner API call for exactly this dither channel (grid of 1)
+    long long real_stride;    // elements between channels of `real`
+};
+
+#ifdef __CUDACC__
+template <class T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <class T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <class T> __device__ __forceinline__ T sub_rn(T a, T b) { return add_rn<T>(a, -b); }
+
+// convolver_mixnscale, fftw_convolver.cpp:859-1427 (float) / :1559-2123 (double). One thread per ORD slot.
+template <class T>
+__global__ void mixnscale_kernel(const MixArgs a)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x; // index in the ORD buffer
+    if (j >= a.N) return;
+    const int N = a.N, half = N >> 1;
+    const int g = j >> 3, lane = j & 7;
+    int k = 4 * g + (lane & 3);
+    int hc; // matching index in the HC buffer
+    if (lane < 4) hc = k;
+    else hc = (k == 0) ? half : N - k;
+    const int src = a.mixmode == MIXMODE_INPUT ? hc : j;
+    const int dst = a.mixmode == MIXMODE_INPUT ? j : hc;
+    T acc = mul_rn<T>(((const T *)a.in[0])[src], (T)a.scales[0]);
+    for (int b = 1; b < a.n_bufs; b++) acc = add_rn<T>(acc, mul_rn<T>(((const T *)a.in[b])[src], (T)a.scales[b]));
+    // all reads of this thread's sources happen before its write; callers keep out distinct from in
+    ((T *)a.out)[dst] = acc;
+}
+
+// MODE 0: convolve (out = in*c), 1: convolve_add (out += in*c). One thread per group of 8.
+// fftw_convolver.cpp:1430-1525 / :2126-2220
+template <class T, int MODE>
+__global__ void convolve_kernel(const T *b, const T *c, T *d, int N)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g * 8 >= N) return;
+    T bb[8], cc[8], dd[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { bb[j] = b[g * 8 + j]; cc[j] = c[g * 8 + j]; dd[j] = MODE == 1 ? d[g * 8 + j] : (T)0; }
+    T o[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const T re = sub_rn<T>(mul_rn<T>(bb[j], cc[j]), mul_rn<T>(bb[j + 4], cc[j + 4]));
+        const T im = add_rn<T>(mul_rn<T>(bb[j], cc[j + 4]), mul_rn<T>(bb[j + 4], cc[j]));
+        o[j] = MODE == 1 ? add_rn<T>(dd[j], re) : re;
+        o[j + 4] = MODE == 1 ? add_rn<T>(dd[j + 4], im) : im;
+    }
+    if (g == 0) {
+        const T d1 = mul_rn<T>(bb[0], cc[0]), d2 = mul_rn<T>(bb[4], cc[4]);
+        o[0] = MODE == 1 ? add_rn<T>(dd[0], d1) : d1;
+        o[4] = MODE == 1 ? add_rn<T>(dd[4], d2) : d2;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) d[g * 8 + j] = o[j];
+}
+
+// convolver_dirac_convolve[_inplace], fftw_convolver.cpp:1528-1556 / :2223-2251 (HC layout)
+template <class T>
+__global__ void dirac_kernel(const T *in, T *out, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const T fraction = (T)1.0 / (T)N;
+    out[i] = mul_rn<T>(in[i], (i & 1) ? -fraction : fraction);
+}
+
+// linear old->new ramp of convolver_crossfade_inplace, float branch fftw_convolver.cpp:296-305, used
+// for both precisions (the double branch :306-315 reads memory the function never wrote)
+template <class T>
+__global__ void crossfade_ramp_kernel(const T *xfade, T *buffer, int L)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= L) return;
+    if (sizeof(T) == 4) {
+        const float f = (float)(1.0 / (double)(float)(L - 1));
+        const float fn = __fmul_rn(f, (float)n);
+        const double a = __dmul_rn((double)xfade[n], __dadd_rn(1.0, -(double)fn));
+        const float b = __fmul_rn(__fmul_rn((float)buffer[n], f), (float)n);
+        buffer[n] = (T)(float)__dadd_rn(a, (double)b);
+    } else {
+        const double d = 1.0 / (double)(L - 1);
+        const double dn = __dmul_rn(d, (double)n);
+        const double a = __dmul_rn((double)xfade[n], __dadd_rn(1.0, -dn));
+        const double b = __dmul_rn(__dmul_rn((double)buffer[n], d), (double)n);
+        buffer[n] = (T)__dadd_rn(a, b);
+    }
+}
+
+// convolver_raw2cbuf, fftw_convolver.cpp:157-185: L strided raw samples -> next_cbuf[0..L) and cbuf[L..2L)
+template <class T>
+__global__ void raw2cbuf_kernel(const uint8_t *raw, T *cbuf, T *next_cbuf, int fmt, int spacing, int L)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= L) return;
+    const T x = load_raw<T>(raw + (long long)n * spacing * fmt_bytes(fmt), fmt);
+    next_cbuf[n] = x;
+    cbuf[L + n] = x;
+}
+
+// real2raw*_no_dither on a planar real buffer (inner API cbuf2raw without dither), one thread per sample
+template <class T>
+__global__ void real2raw_kernel(const T *real, uint8_t *raw, int fmt, int spacing, int L, double ovf_max, OverflowStats *stats)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    OverflowAcc acc;
+    acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
+    if (n < L) {
+        uint8_t *p = raw + (long long)n * spacing * fmt_bytes(fmt);
+        if (fmt_isfloat(fmt)) {
+            store_raw_float<T>(p, fmt, real[n], (T)ovf_max, acc);
+        } else {
+            int32_t imin, imax;
+            int_limits(fmt, imin, imax);
+            store_raw_quantised<T>(p, fmt, real[n], (T)imin, (T)imax, imin, imax, acc);
+        }
+    }
+    if (acc.n_overflows) atomicAdd(&stats->n_overflows, acc.n_overflows);
+    if (acc.intlargest > 0) atomicMax(&stats->intlargest, acc.intlargest);
+    if (acc.largest > 0.0) atomicMax(&stats->largest_bits, (unsigned long long)__double_as_longlong(acc.largest));
+}
+
+// real2raw*_hp_tpdf -> dither*_real2int_hp_tpdf (real2raw.cpp:39-315 / :645-920, dither.cpp:127-212 /
+// :276-347): first-order high-pass error feedback + TPDF dither. The recurrence is serial in n, so
+// one thread walks one channel; channels run in parallel (one thread per channel).
+template <class T>
+__global__ void dither_kernel(const DitherArgs a)
+{
+    int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.single_channel >= 0) { if (ch != 0) return; ch = a.single_channel; }
+    else if (ch >= a.n_channels) return;
+    const int data_ch = a.single_channel >= 0 ? 0 : ch;
+    DitherState st = a.dstate[ch];
+    // dither_preloop_real2int_hp_tpdf, dither.cpp:127-139
+    if (st.randtab_ptr + a.L >= a.randtab_size) {
+        st.tab0 = a.randtab[st.randtab_ptr - 1];
+        st.randtab_ptr = 1;
+    }
+    const int base = st.randtab_ptr;
+    st.randtab_ptr += a.L;
+
+    const T *real = (const T *)a.real + (long long)data_ch * a.real_stride;
+    const T *map = (const T *)a.randmap + 256;
+    const int stream = data_ch / a.ch_per_stream, c = data_ch - stream * a.ch_per_stream;
+    const int bytes = fmt_bytes(a.fmt);
+    uint8_t *raw = (uint8_t *)a.raw + (long long)stream * a.raw_stream_stride + (long long)c * bytes;
+    const long long step = (long long)a.ch_per_stream * bytes;
+    int32_t imin, imax;
+    int_limits(a.fmt, imin, imax);
+    const T rmin = (T)imin, rmax = (T)imax;
+
+    OverflowStats *os = &a.stats[ch];
+    OverflowAcc acc; // sequential here, so seed with the running values (dither.cpp:170-205 compares against them)
+    acc.n_overflows = 0;
+    acc.intlargest = os->intlargest;
+    acc.largest = __longlong_as_double((long long)os->largest_bits);
+    T e0 = (T)st.err[0], e1 = (T)st.err[1];
+    int prev = base - 1 == 0 ? st.tab0 : (int)a.randtab[base - 1];
+    for (int n = 0; n < a.L; n++) {
+        const int cur = (int)a.randtab[base + n];
+        const T dv = map[cur - prev];
+        prev = cur;
+        T x = add_rn<T>(real[n], sub_rn<T>(e0, e1));          // error feedback {1, -1}
+        e1 = e0;
+        const T d = add_rn<T>(x, dv);
+        const int32_t s = quantise<T>(d, x, rmin, rmax, imin, imax, acc);
+        e0 = sub_rn<T>(x, (T)s);
+        store_raw_int(raw + (long long)n * step, a.fmt, s);
+    }
+    st.err[0] = (double)e0;
+    st.err[1] = (double)e1;
+    a.dstate[ch] = st;
+    os->n_overflows += acc.n_overflows;
+    os->intlargest = acc.intlargest;
+    os->largest_bits = (unsigned long long)__double_as_longlong(acc.largest);
+}
+
+// engine housekeeping
+static __global__ void engine_reset_kernel(EngineState *state, int *procblocks, OverflowStats *stats, int n_channels)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { state->blockcounter = 0; state->first_bad_channel = 0x7fffffff; }
+    if (i < n_channels) { // brutefir.cpp:347-367: counters only, never the buffers
+        procblocks[i] = 0;
+        stats[i].n_overflows = 0; stats[i].intlargest = 0; stats[i].largest_bits = 0ull;
+    }
+}
+
+// undo the bookkeeping of a block that brutefir::run would have aborted at channel `bad`
+// (brutefir.cpp:316-321 returns before :337-340): later channels never ran, the counter did not move
+static __global__ void engine_abort_fixup_kernel(EngineState *state, int *procblocks, const unsigned char *pb_inc, int n_channels, int bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { state->blockcounter -= 1u; state->first_bad_channel = 0x7fffffff; }
+    if (i > bad && i < n_channels && pb_inc[i]) procblocks[i] -= 1;
+}
+#endif
+
+} // namespace bfir

@@ -1,0 +1,467 @@
+// The engine: device-resident counterpart of the reference's `brutefir` class
+// (brutefir/brutefir.hpp:15-130, brutefir/brutefir.cpp). One block step = three kernels on one stream:
+//
+//   rfft_forward_kernel   raw2cbuf + time2freq + mixnscale(INPUT)  -> FDL slot (blockcounter % P)
+//   partition_mac_kernel  convolve + (P-1) x convolve_add          -> accumulated spectrum
+//   rfft_inverse_kernel   mixnscale(OUTPUT) + freq2time + probe + cbuf2raw -> interleaved raw output
+//   (+ dither_kernel when integer output is dithered)
+//
+// All state the reference keeps in host members (blockcounter, procblocks, dither_state, overflow;
+// brutefir.hpp:104-127) lives in device memory, so a block step needs no host-side bookkeeping.
+#include "common.hpp"
+
+namespace bfir {
+
+struct Engine {
+    bfir_config_t cfg;
+    int L = 0, N = 0, P = 0, C = 0, S = 0, Ct = 0, rs = 0, log2m = 0;
+    int part_begin = 0, part_count = 0;
+    SampleFormat in_sf, out_sf;
+    bool dither_on = false, initialized = false, own_stream = true;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    void *fdl = nullptr, *coeffs = nullptr, *acc = nullptr, *prev = nullptr, *ybuf = nullptr, *tw = nullptr;
+    void *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer run()
+    size_t in_bytes = 0, out_bytes = 0;
+    int coeff_alloc = 0;
+    EngineState *state = nullptr;
+    int *procblocks = nullptr, *coeff_blocks = nullptr, *nonfinite = nullptr;
+    unsigned char *pb_inc = nullptr;
+    OverflowStats *stats = nullptr;
+    EngineState *h_state = nullptr; // pinned
+    std::vector<bfir_overflow_t> last_overflow;
+    DitherTables dither;
+    double ovf_max = 1.0;
+    unsigned long long blocks_since_sync = 0;
+
+    ~Engine() { destroy(); }
+    int init(const bfir_config_t &c);
+    void destroy();
+    int set_coeff(const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
+    int enqueue_front(const void *d_inbuf);
+    int enqueue_back(void *d_outbuf);
+    int run_host(const void *inbuf, void *outbuf);
+    int sync_and_probe();
+    int reset();
+    int get_overflow(int ch, bfir_overflow_t *out);
+};
+
+int Engine::init(const bfir_config_t &c)
+{
+    cfg = c;
+    L = c.filter_length; N = 2 * L; P = c.filter_blocks; C = c.channels; S = c.n_streams > 0 ? c.n_streams : 1;
+    rs = c.realsize;
+    if (rs != 4 && rs != 8) { set_error("Invalid real size %d.", rs); return BFIR_ERR_INVALID; }   // fftw_convolver.cpp:64-68
+    log2m = ilog2_exact(L);
+    if (log2m < 0) { set_error("Invalid length %d.", L); return BFIR_ERR_INVALID; }                 // fftw_convolver.cpp:70-74
+    if (!rfft_supported(rs, log2m)) { set_error("block length %d not supported for realsize %d", L, rs); return BFIR_ERR_INVALID; }
+    if (P < 1 || C < 1) { set_error("No channels defined."); return BFIR_ERR_INVALID; }            // brutefir.cpp:745-749
+    if ((long long)C * S > 0x7fffffffLL / 2) return BFIR_ERR_INVALID;
+    Ct = C * S;
+    if (!fill_sample_format(&in_sf, c.in_format, true) || !fill_sample_format(&out_sf, c.out_format, false)) {
+        set_error("invalid sample format %d / %d", c.in_format, c.out_format);
+        return BFIR_ERR_INVALID;
+    }
+    part_begin = c.part_begin;
+    part_count = c.part_count > 0 ? c.part_count : P - part_begin;
+    if (part_begin < 0 || part_begin + part_count > P) { set_error("invalid partition shard"); return BFIR_ERR_INVALID; }
+    dither_on = c.apply_dither && !out_sf.isfloat;                                                   // fftw_convolver.cpp:421,444
+    ovf_max = out_sf.isfloat ? 1.0 : (double)(1 << ((out_sf.bytes << 3) - 1)) - 1.0;                  // brutefir.cpp:672-684
+
+    if (c.device >= 0) BFIR_CUDA(cudaSetDevice(c.device));
+    BFIR_CUDA(cudaGetDevice(&device));
+    BFIR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+
+    const size_t cbuf = (size_t)N * rs;
+    // the delay line only has to hold the slots this engine's partitions read: all P (the slot index
+    // is blockcounter % P like the reference, brutefir.cpp:270,294)
+    BFIR_CUDA(cudaMalloc(&fdl, cbuf * P * Ct));
+    BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * P * Ct, stream));                                      // brutefir.cpp:768-769
+    BFIR_CUDA(cudaMalloc(&acc, cbuf * Ct));
+    BFIR_CUDA(cudaMemsetAsync(acc, 0, cbuf * Ct, stream));
+    BFIR_CUDA(cudaMalloc(&prev, (size_t)L * rs * Ct));
+    BFIR_CUDA(cudaMemsetAsync(prev, 0, (size_t)L * rs * Ct, stream));
+    in_bytes = (size_t)S * L * C * in_sf.bytes;
+    out_bytes = (size_t)S * L * C * out_sf.bytes;
+    BFIR_CUDA(cudaMalloc(&d_in, in_bytes));
+    BFIR_CUDA(cudaMalloc(&d_out, out_bytes));
+    BFIR_CUDA(cudaMalloc((void **)&state, sizeof(EngineState)));
+    BFIR_CUDA(cudaMalloc((void **)&procblocks, sizeof(int) * Ct));
+    BFIR_CUDA(cudaMalloc((void **)&coeff_blocks, sizeof(int) * Ct));
+    BFIR_CUDA(cudaMemsetAsync(coeff_blocks, 0, sizeof(int) * Ct, stream));
+    BFIR_CUDA(cudaMalloc((void **)&pb_inc, (size_t)Ct));
+    BFIR_CUDA(cudaMemsetAsync(pb_inc, 0, (size_t)Ct, stream));
+    BFIR_CUDA(cudaMalloc((void **)&nonfinite, sizeof(int)));
+    BFIR_CUDA(cudaMalloc((void **)&stats, sizeof(OverflowStats) * Ct));
+    BFIR_CUDA(cudaHostAlloc((void **)&h_state, sizeof(EngineState), cudaHostAllocDefault));
+    int rc = make_twiddles(rs, N, &tw);
+    if (rc != BFIR_OK) return rc;
+    if (dither_on) {
+        BFIR_CUDA(cudaMalloc(&ybuf, (size_t)L * rs * Ct));
+        // max_dither_table_size is 0 (memset bfconf, brutefir.cpp:31-32; passed at :712)
+        rc = dither.init(Ct, c.sampling_rate, rs, 0, L);
+        if (rc != BFIR_OK) return rc;
+    }
+    last_overflow.assign(Ct, bfir_overflow_t{0, 0, 0.0, ovf_max});
+    rc = reset();
+    if (rc != BFIR_OK) return rc;
+    BFIR_CUDA(cudaStreamSynchronize(stream));
+    return BFIR_OK;
+}
+
+void Engine::destroy()
+{
+    if (stream && own_stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    stream = nullptr;
+    void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats };
+    for (void *b : bufs) if (b) cudaFree(b);
+    fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = nullptr;
+    state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; pb_inc = nullptr; stats = nullptr;
+    if (h_state) cudaFreeHost(h_state);
+    h_state = nullptr;
+    dither.destroy();
+}
+
+int Engine::reset()
+{
+    // brutefir::reset, brutefir.cpp:347-367
+    const int threads = 256, blocks = (Ct + threads - 1) / threads;
+    engine_reset_kernel<<<blocks, threads, 0, stream>>>(state, procblocks, stats, Ct);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    for (auto &o : last_overflow) { o.n_overflows = 0; o.largest = 0; o.intlargest = 0; }
+    return BFIR_OK;
+}
+
+int Engine::set_coeff(const void *const *h_coeffs, int n_coeffs, int length, int blocks, double scale)
+{
+    // brutefir::set_coeff, brutefir.cpp:180-228 -> coeff::preprocess_coeff, coeff.cpp:293-354
+    //   -> convolver_coeffs2cbuf, fftw_convolver.cpp:475-537, for every (channel, partition) in ONE launch
+    if (h_coeffs == nullptr || blocks < 1 || length < 0) { set_error("invalid coefficient arguments"); return BFIR_ERR_INVALID; }
+    BFIR_CUDA(cudaSetDevice(device));
+    BFIR_CUDA(cudaStreamSynchronize(stream));
+    initialized = false;                                   // free_coeff(), brutefir.cpp:189
+    if (coeffs) { cudaFree(coeffs); coeffs = nullptr; }
+    BFIR_CUDA(cudaMemsetAsync(coeff_blocks, 0, sizeof(int) * Ct, stream));
+    if (n_coeffs > Ct) n_coeffs = Ct;                     // brutefir.cpp:191-194
+    if (n_coeffs < 1) return BFIR_OK;
+    const size_t cbuf = (size_t)N * rs;
+    coeff_alloc = blocks;
+    BFIR_CUDA(cudaMalloc(&coeffs, cbuf * blocks * Ct));
+    BFIR_CUDA(cudaMemsetAsync(coeffs, 0, cbuf * blocks * Ct, stream));
+    // stage the planar host arrays
+    void *d_planar = nullptr;
+    const size_t row = (size_t)(length > 0 ? length : 1) * rs;
+    BFIR_CUDA(cudaMalloc(&d_planar, row * n_coeffs));
+    for (int n = 0; n < n_coeffs; n++) {
+        if (h_coeffs[n] == nullptr) { cudaFree(d_planar); set_error("coefficient array %d is NULL", n); return BFIR_ERR_INVALID; }
+        if (length > 0) BFIR_CUDA(cudaMemcpyAsync((char *)d_planar + row * n, h_coeffs[n], (size_t)length * rs, cudaMemcpyHostToDevice, stream));
+    }
+    BFIR_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int), stream));
+    FwdArgs a = {};
+    a.in_mode = IN_COEFF; a.out_layout = LAYOUT_ORD;
+    a.in = d_planar; a.in_stride_x = (long long)(length > 0 ? length : 1); a.in_stride_y = 0;
+    a.out = coeffs; a.out_stride_x = (long long)blocks * N; a.out_stride_y = N;
+    a.scale_in = scale; a.scale_out = 1.0 / (double)N;     // fftw_convolver.cpp:520
+    a.coeff_len = length; a.nonfinite = nonfinite;
+    cudaError_t e = launch_rfft_forward(rs, log2m, dim3(n_coeffs, blocks), stream, a, tw, 1, 0);
+    count_launch();
+    if (e != cudaSuccess) { cudaFree(d_planar); set_error("coefficient transform launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    std::vector<int> hb(Ct, 0);
+    for (int n = 0; n < n_coeffs; n++) hb[n] = blocks;     // brutefir.cpp:213
+    int bad = 0;
+    BFIR_CUDA(cudaMemcpyAsync(coeff_blocks, hb.data(), sizeof(int) * Ct, cudaMemcpyHostToDevice, stream));
+    BFIR_CUDA(cudaMemcpyAsync(&bad, nonfinite, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BFIR_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_planar);
+    if (bad) {                                             // brutefir.cpp:207-224
+        pinfo("NaN or Inf value among coefficients.\n");
+        cudaFree(coeffs); coeffs = nullptr;
+        cudaMemset(coeff_blocks, 0, sizeof(int) * Ct);
+        set_error("NaN or Inf value among coefficients.");
+        return BFIR_ERR_COEFF;
+    }
+    initialized = true;                                    // brutefir.cpp:226
+    return BFIR_OK;
+}
+
+// input FFT into the delay line + this engine's partition sum
+int Engine::enqueue_front(const void *d_inbuf)
+{
+    FwdArgs f = {};
+    f.in_mode = IN_RAW_PREV; f.out_layout = LAYOUT_ORD;
+    f.in = d_inbuf; f.in_stride_x = (long long)L * C * in_sf.bytes;   // bytes per stream
+    f.out = fdl; f.out_stride_x = (long long)P * N; f.out_stride_y = N;
+    f.scale_in = 1.0; f.scale_out = in_sf.scale;                       // brutefir.cpp:273-277
+    f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = C;
+    f.state = state; f.n_slots = P; f.procblocks = procblocks; f.pb_inc = pb_inc;
+    cudaError_t e = launch_rfft_forward(rs, log2m, dim3(Ct, 1), stream, f, tw, 1, 0);
+    count_launch();
+    if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+
+    MacArgs m = {};
+    m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
+    m.fdl_stride_ch = (long long)P * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = P; m.part_begin = part_begin; m.part_count = part_count;
+    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state; m.block_offset = 0;
+    const int groups = N / 8, threads = groups < 256 ? groups : 256;
+    dim3 grid((groups + threads - 1) / threads, Ct);
+    if (rs == 4) partition_mac_kernel<float, 4><<<grid, threads, 0, stream>>>(m);
+    else partition_mac_kernel<double, 4><<<grid, threads, 0, stream>>>(m);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    return BFIR_OK;
+}
+
+// output stage from the accumulated spectra
+int Engine::enqueue_back(void *d_outbuf)
+{
+    InvArgs v = {};
+    v.in_layout = LAYOUT_ORD; v.in = acc; v.in_stride_x = N;
+    v.scale_in = out_sf.scale;                                         // brutefir.cpp:303-307
+    v.fmt = out_sf.format; v.ch_per_stream = C; v.ovf_max = ovf_max; v.stats = stats; v.state = state;
+    if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }
+    else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * C * out_sf.bytes; }
+    cudaError_t e = launch_rfft_inverse(rs, log2m, dim3(Ct, 1), stream, v, tw, 1, 0);
+    count_launch();
+    if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    if (dither_on) {
+        DitherArgs d = {};
+        d.real = ybuf; d.real_stride = L; d.raw = d_outbuf; d.raw_stream_stride = (long long)L * C * out_sf.bytes;
+        d.fmt = out_sf.format; d.ch_per_stream = C; d.L = L; d.n_channels = Ct;
+        d.randtab = dither.d_tab; d.randtab_size = dither.size; d.randmap = dither.d_map;
+        d.dstate = dither.d_state; d.stats = stats; d.single_channel = -1;
+        const int threads = 32, blocks = (Ct + threads - 1) / threads;
+        if (rs == 4) dither_kernel<float><<<blocks, threads, 0, stream>>>(d);
+        else dither_kernel<double><<<blocks, threads, 0, stream>>>(d);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+    }
+    blocks_since_sync++;
+    return BFIR_OK;
+}
+
+// wait for the stream and apply the reference's NaN/Inf abort (brutefir.cpp:316-321)
+int Engine::sync_and_probe()
+{
+    BFIR_CUDA(cudaMemcpyAsync(h_state, state, sizeof(EngineState), cudaMemcpyDeviceToHost, stream));
+    BFIR_CUDA(cudaStreamSynchronize(stream));
+    const unsigned long long n = blocks_since_sync;
+    blocks_since_sync = 0;
+    if (h_state->first_bad_channel != 0x7fffffff) {
+        pinfo("NaN or Inf values in the system! Invalid input? Aborting.\n");
+        const int bad = h_state->first_bad_channel;
+        if (n == 1) { // exact reference semantics: the aborted block does not advance the counters
+            const int threads = 256, blocks = (Ct + threads - 1) / threads;
+            engine_abort_fixup_kernel<<<blocks, threads, 0, stream>>>(state, procblocks, pb_inc, Ct, bad);
+            count_launch();
+        } else {
+            EngineState s = *h_state;
+            s.first_bad_channel = 0x7fffffff;
+            cudaMemcpyAsync(state, &s, sizeof(s), cudaMemcpyHostToDevice, stream);
+        }
+        BFIR_CUDA(cudaStreamSynchronize(stream));
+        set_error("NaN or Inf values in the system (channel %d)", bad);
+        return BFIR_ERR_NONFINITE;
+    }
+    return BFIR_OK;
+}
+
+int Engine::run_host(const void *inbuf, void *outbuf)
+{
+    BFIR_CUDA(cudaMemcpyAsync(d_in, inbuf, in_bytes, cudaMemcpyHostToDevice, stream));
+    int rc = enqueue_front(d_in);
+    if (rc != BFIR_OK) return rc;
+    rc = enqueue_back(d_out);
+    if (rc != BFIR_OK) return rc;
+    BFIR_CUDA(cudaMemcpyAsync(outbuf, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+    return sync_and_probe();
+}
+
+int Engine::get_overflow(int ch, bfir_overflow_t *out)
+{
+    if (ch < 0 || ch >= Ct || out == nullptr) return BFIR_ERR_INVALID;
+    OverflowStats s;
+    BFIR_CUDA(cudaStreamSynchronize(stream));
+    BFIR_CUDA(cudaMemcpy(&s, stats + ch, sizeof(s), cudaMemcpyDeviceToHost));
+    out->n_overflows = s.n_overflows;
+    out->intlargest = s.intlargest;
+    memcpy(&out->largest, &s.largest_bits, sizeof(double));
+    out->max = ovf_max;
+    return BFIR_OK;
+}
+
+} // namespace bfir
+
+using namespace bfir;
+
+struct bfir_engine { Engine impl; };
+
+extern "C" {
+
+int bfir_create_ex(bfir_engine **out, const bfir_config_t *cfg)
+{
+    if (out == nullptr || cfg == nullptr) return BFIR_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        set_error("no CUDA device: libbfir_b200 has no CPU fallback");
+        return BFIR_ERR_CUDA;
+    }
+    bfir_engine *e = new bfir_engine;
+    const int rc = e->impl.init(*cfg);
+    if (rc != BFIR_OK) { delete e; return rc; }
+    *out = e;
+    return BFIR_OK;
+}
+
+int bfir_create(bfir_engine **out, int filter_length, int filter_blocks, int realsize, int channels,
+                int in_format, int out_format, int sampling_rate, int apply_dither)
+{
+    bfir_config_t c;
+    memset(&c, 0, sizeof(c));
+    c.filter_length = filter_length; c.filter_blocks = filter_blocks; c.realsize = realsize; c.channels = channels;
+    c.in_format = in_format; c.out_format = out_format; c.sampling_rate = sampling_rate; c.apply_dither = apply_dither;
+    c.n_streams = 1; c.device = -1; c.part_begin = 0; c.part_count = 0;
+    return bfir_create_ex(out, &c);
+}
+
+void bfir_destroy(bfir_engine *e) { delete e; }
+int bfir_is_initialized(const bfir_engine *e) { return (e != nullptr && e->impl.initialized) ? 1 : 0; }
+
+int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.set_coeff(coeffs, n_coeffs, length, coeff_blocks, scale);
+}
+
+static int check_ready(bfir_engine *e)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    if (!e->impl.initialized) { set_error("run before set_coeff"); return BFIR_ERR_NOT_READY; }
+    return BFIR_OK;
+}
+
+int bfir_run(bfir_engine *e, const void *inbuf, void *outbuf)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (inbuf == nullptr || outbuf == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.run_host(inbuf, outbuf);
+}
+
+int bfir_run_device(bfir_engine *e, const void *d_inbuf, void *d_outbuf)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    rc = e->impl.enqueue_front(d_inbuf);
+    if (rc != BFIR_OK) return rc;
+    return e->impl.enqueue_back(d_outbuf);
+}
+
+int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    return e->impl.enqueue_front(d_inbuf);
+}
+
+int bfir_run_finish_device(bfir_engine *e, void *d_outbuf)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    return e->impl.enqueue_back(d_outbuf);
+}
+
+void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes)
+{
+    if (e == nullptr) return nullptr;
+    if (bytes) *bytes = (size_t)e->impl.N * e->impl.rs * e->impl.Ct;
+    return e->impl.acc;
+}
+
+int bfir_sync(bfir_engine *e)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.sync_and_probe();
+}
+
+int bfir_reset(bfir_engine *e)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.reset();
+}
+
+int bfir_get_overflow(bfir_engine *e, int channel, bfir_overflow_t *out)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.get_overflow(channel, out);
+}
+
+int bfir_check_overflows(bfir_engine *e)
+{
+    // brutefir::check_overflows + print_overflows, brutefir.cpp:371-388, 585-629
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    Engine &g = e->impl;
+    std::vector<bfir_overflow_t> cur(g.Ct);
+    bool changed = false;
+    for (int n = 0; n < g.Ct; n++) {
+        int rc = g.get_overflow(n, &cur[n]);
+        if (rc != BFIR_OK) return rc;
+        if (memcmp(&cur[n], &g.last_overflow[n], sizeof(bfir_overflow_t)) != 0) changed = true;
+    }
+    if (!changed) return 0;
+    g.last_overflow = cur;
+    bool any = false;
+    for (int n = 0; n < g.Ct; n++) if (cur[n].n_overflows > 0) { any = true; break; }
+    if (!any) return 0;
+    for (int n = 0; n < g.Ct; n++) {
+        double peak = cur[n].largest;
+        if (peak < (double)cur[n].intlargest) peak = (double)cur[n].intlargest;
+        if (peak != 0.0) {
+            if ((peak = 20.0 * log10(peak / cur[n].max)) == 0.0) peak = -0.0;
+            bfir::pinfo("peak: %d/%u/%+.2f ", n, cur[n].n_overflows, peak);
+        } else {
+            bfir::pinfo("peak: %d/%u/-Inf ", n, cur[n].n_overflows);
+        }
+    }
+    return 1;
+}
+
+int bfir_get_dither_ptr(bfir_engine *e, int channel, int *out)
+{
+    if (e == nullptr || out == nullptr || channel < 0 || channel >= e->impl.Ct) return BFIR_ERR_INVALID;
+    if (!e->impl.dither_on) { set_error("engine has no dither state"); return BFIR_ERR_INVALID; }
+    DitherState s;
+    BFIR_CUDA(cudaStreamSynchronize(e->impl.stream));
+    BFIR_CUDA(cudaMemcpy(&s, e->impl.dither.d_state + channel, sizeof(s), cudaMemcpyDeviceToHost));
+    *out = s.randtab_ptr;
+    return BFIR_OK;
+}
+
+int bfir_get_blockcounter(bfir_engine *e, unsigned int *out)
+{
+    if (e == nullptr || out == nullptr) return BFIR_ERR_INVALID;
+    EngineState s;
+    BFIR_CUDA(cudaStreamSynchronize(e->impl.stream));
+    BFIR_CUDA(cudaMemcpy(&s, e->impl.state, sizeof(s), cudaMemcpyDeviceToHost));
+    *out = s.blockcounter;
+    return BFIR_OK;
+}
+
+int bfir_set_stream(bfir_engine *e, void *cuda_stream)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    Engine &g = e->impl;
+    if (g.stream && g.own_stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
+    g.stream = (cudaStream_t)cuda_stream;
+    g.own_stream = false;
+    return BFIR_OK;
+}
+
+void bfir_set_print_callback(void (*cb)(const char *message)) { bfir::g_print_cb = cb; }
+const char *bfir_last_error(void) { return bfir::g_last_error.c_str(); }
+unsigned long long bfir_kernel_launch_count(void) { return bfir::g_launches.load(); }
+
+}

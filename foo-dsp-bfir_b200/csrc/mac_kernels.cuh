@@ -1,0 +1,118 @@
+// Frequency-domain multiply-accumulate over the filter partitions -- THE bandwidth-bound kernel.
+//
+// Reference: brutefir::run's partition loop, brutefir.cpp:288-299, i.e. one convolver_convolve
+// (fftw_convolver.cpp:1465-1493 / 2161-2189) followed by P-1 convolver_convolve_add
+// (:1497-1525 / :2192-2220), each of which re-reads and re-writes the accumulator. Here the
+// accumulator lives in registers for the whole partition loop, so one channel-block moves exactly
+//     B_mac = (2 * P_eff + 1) * N * realsize   bytes
+// (P_eff coefficient spectra + P_eff delay-line spectra in, one accumulated spectrum out).
+//
+// All spectra are in the reference's ORD layout (groups of 8 reals = [Re k..k+3 | Im k..k+3]); the
+// real DC and Nyquist bins share group 0 (slots 0 and 4) and are accumulated separately exactly like
+// the reference's d1s/d2s (fftw_convolver.cpp:1475-1476, 1507-1508).
+#pragma once
+#include "rfft_kernels.cuh"
+
+namespace bfir {
+
+struct MacArgs {
+    const void *fdl;         // [channels][n_slots][N]   frequency-domain delay line, slot = blockcounter % n_slots
+    const void *coeffs;      // [channels][coeff_alloc][N]
+    void *acc;               // [channels][N]
+    long long fdl_stride_ch, coeff_stride_ch; // elements
+    int N;
+    int n_slots;             // filter_blocks of the engine
+    int part_begin, part_count; // partition shard convolved by this launch (whole filter: 0, n_slots)
+    const int *coeff_blocks; // [channels] coefficient partitions actually loaded
+    const int *procblocks;   // [channels] blocks seen so far, already counting the current one
+    const EngineState *state;
+    int block_offset;        // 0: blockcounter is the current block; used by tests
+};
+
+template <class T> struct vec8 { T v[8]; };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void ld8(const float *p, float (&r)[8])
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const double *p, double (&r)[8])
+{
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y; r[4] = c.x; r[5] = c.y; r[6] = d.x; r[7] = d.y;
+}
+__device__ __forceinline__ void st8(float *p, const float (&r)[8])
+{
+    reinterpret_cast<float4 *>(p)[0] = make_float4(r[0], r[1], r[2], r[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+__device__ __forceinline__ void st8(double *p, const double (&r)[8])
+{
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(r[0], r[1]); q[1] = make_double2(r[2], r[3]);
+    q[2] = make_double2(r[4], r[5]); q[3] = make_double2(r[6], r[7]);
+}
+
+template <class T>
+__device__ __forceinline__ void mac8(T (&acc)[8], const T (&b)[8], const T (&c)[8])
+{
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        acc[j] = fma(b[j], c[j], acc[j]);
+        acc[j] = fma(-b[j + 4], c[j + 4], acc[j]);
+        acc[j + 4] = fma(b[j], c[j + 4], acc[j + 4]);
+        acc[j + 4] = fma(b[j + 4], c[j], acc[j + 4]);
+    }
+}
+
+// grid: (ceil(N/8 / blockDim.x), channels). One thread = one ORD group (4 complex bins) of one channel.
+template <class T, int UNROLL>
+__global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (g * 8 >= a.N) return;
+    const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
+    int peff = min(a.coeff_blocks[ch], a.procblocks[ch]);           // brutefir.cpp:292
+    const int i_end = min(peff, a.part_begin + a.part_count);
+    const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
+    const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
+    const unsigned int P = (unsigned int)a.n_slots;
+
+    T acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = (T)0;
+    T dc = (T)0, ny = (T)0;
+
+    int i = a.part_begin;
+    for (; i + UNROLL <= i_end; i += UNROLL) {
+        T b[UNROLL][8], c[UNROLL][8];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const unsigned int slot = (t - (unsigned int)(i + u)) % P; // brutefir.cpp:294
+            ld8(fdl + (long long)slot * a.N, b[u]);
+            ld8(cf + (long long)(i + u) * a.N, c[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            if (g == 0) { dc = fma(b[u][0], c[u][0], dc); ny = fma(b[u][4], c[u][4], ny); }
+            mac8<T>(acc, b[u], c[u]);
+        }
+    }
+    for (; i < i_end; i++) {
+        T b[8], c[8];
+        const unsigned int slot = (t - (unsigned int)i) % P;
+        ld8(fdl + (long long)slot * a.N, b);
+        ld8(cf + (long long)i * a.N, c);
+        if (g == 0) { dc = fma(b[0], c[0], dc); ny = fma(b[4], c[4], ny); }
+        mac8<T>(acc, b, c);
+    }
+    if (g == 0) { acc[0] = dc; acc[4] = ny; }
+    st8((T *)a.acc + (long long)ch * a.N + (long long)g * 8, acc);
+}
+#endif
+
+} // namespace bfir

@@ -1,0 +1,323 @@
+// Real <-> half-complex transforms of one convolver buffer per CTA, with the surrounding stages of
+// the reference's block loop fused into the load and store phases:
+//
+//   forward kernel  = raw2cbuf (raw2real + [prev|cur] framing)         brutefir.cpp:255-260, fftw_convolver.cpp:157-185
+//                   + time2freq (FFTW_R2HC)                            brutefir.cpp:263,     fftw_convolver.cpp:188-212
+//                   + mixnscale(MIXMODE_INPUT, n_bufs=1): scale, HC->ORD brutefir.cpp:273-277, fftw_convolver.cpp:883-907
+//                   also coeffs2cbuf / runtime_coeffs2cbuf             fftw_convolver.cpp:475-567
+//   inverse kernel  = mixnscale(MIXMODE_OUTPUT, n_bufs=1): scale, ORD->HC brutefir.cpp:303-307, fftw_convolver.cpp:1163-1186
+//                   + freq2time (FFTW_HC2R)                            brutefir.cpp:311,     fftw_convolver.cpp:351-375
+//                   + NaN/Inf probe on sample 0                        brutefir.cpp:316-321
+//                   + cbuf2raw (real2raw, no-dither paths + statistics) brutefir.cpp:326-331, fftw_convolver.cpp:406-466
+//
+// Buffer layouts: T = [prev|cur] time, HC = FFTW half-complex, ORD = groups of
+// 8 reals [Re k..k+3 | Im k..k+3] with Re X_{N/2} in slot 4.
+#pragma once
+#include "fft_core.cuh"
+#include "codec.cuh"
+
+namespace bfir {
+
+enum { LAYOUT_ORD = 0, LAYOUT_HC = 1 };
+enum {
+    IN_TIME = 0,     // N reals, T layout (time2freq)
+    IN_RAW_PREV = 1, // engine: interleaved raw block + per-channel previous block
+    IN_COEFF = 2,    // planar coefficients, partition blockIdx.y: [0_L | h[y*L .. ) * scale] (coeffs2cbuf)
+    IN_UPPER = 3     // [0_L | src[0..L)] (runtime_coeffs2cbuf)
+};
+enum {
+    OUT_TIME = 0,    // all N reals (freq2time)
+    OUT_RAW = 1,     // engine: first L samples -> interleaved raw (float formats / integer without dither)
+    OUT_REAL_L = 2   // engine: first L samples -> planar real scratch (consumed by the dither kernel)
+};
+
+// device-resident engine state: lets one CUDA graph be replayed for every block
+struct EngineState {
+    unsigned int blockcounter;  // brutefir.hpp:106
+    int first_bad_channel;      // lowest channel whose output sample 0 was NaN/Inf this block
+};
+
+struct FwdArgs {
+    int in_mode, out_layout;
+    const void *in;          // IN_TIME / IN_UPPER: reals; IN_RAW_PREV: raw bytes; IN_COEFF: planar coefficients
+    long long in_stride_x;   // per blockIdx.x (channel / buffer), in elements (bytes for raw: per stream)
+    long long in_stride_y;   // per blockIdx.y
+    void *out;
+    long long out_stride_x, out_stride_y; // elements
+    double scale_in;         // applied to the samples (coefficient scale)
+    double scale_out;        // applied to the spectrum (input scale, or 1/N for coefficients)
+    // IN_RAW_PREV
+    void *prev;              // [channels][L] previous block
+    int fmt, ch_per_stream;
+    const EngineState *state; // out slot = blockcounter % n_slots when state != NULL
+    int n_slots;
+    int *procblocks;         // [channels], brutefir.cpp:265-268
+    unsigned char *pb_inc;   // [channels], 1 when procblocks was incremented by this launch
+    // IN_COEFF
+    int coeff_len;           // valid coefficients per channel
+    int *nonfinite;          // set to 1 when a scaled coefficient is NaN/Inf (fftw_convolver.cpp:493-497)
+};
+
+struct InvArgs {
+    int in_layout, out_mode;
+    const void *in;
+    long long in_stride_x;   // elements
+    double scale_in;         // applied to the spectrum (output scale)
+    void *out;               // OUT_TIME / OUT_REAL_L: reals; OUT_RAW: raw bytes
+    long long out_stride_x;  // elements (bytes per stream for OUT_RAW)
+    int fmt, ch_per_stream;
+    double ovf_max;          // bfoverflow_t.max
+    OverflowStats *stats;    // [channels]
+    EngineState *state;      // probe + blockcounter++ (engine only)
+};
+
+template <class T> BFIR_HD T tw_re(const cpx<T> &w) { return w.x; }
+
+// ------------------------------------------------------------------------------------------------
+// spectrum access by bin for both layouts. N = 2M. X_0 and X_M are real.
+template <class T> BFIR_HD cpx<T> spec_load(const T *s, int layout, int k, int M)
+{
+    cpx<T> r;
+    if (layout == LAYOUT_ORD) {
+        const int base = ((k >> 2) << 3) + (k & 3);
+        if (k == 0) { r.x = s[0]; r.y = (T)0; }
+        else if (k == M) { r.x = s[4]; r.y = (T)0; }
+        else { r.x = s[base]; r.y = s[base + 4]; }
+    } else {
+        if (k == 0) { r.x = s[0]; r.y = (T)0; }
+        else if (k == M) { r.x = s[M]; r.y = (T)0; }
+        else { r.x = s[k]; r.y = s[2 * M - k]; }
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, phase 0: thread t loads z[n] = x[2n] + i x[2n+1] for n = t + i*NT
+template <class T, int LOG2M>
+BFIR_HD void fwd_load(int t, int bx, int by, cpx<T> (&v)[16], const FwdArgs &a)
+{
+    constexpr int M = 1 << LOG2M, NT = M / 16, L = M; // L = block length = N/2 = M
+    typedef cpx<T> C;
+    if (a.in_mode == IN_TIME) {
+        const C *in = (const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y);
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = in[t + i * NT];
+    } else if (a.in_mode == IN_UPPER) {
+        const C *in = (const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = mk<T>((T)0, (T)0);
+#pragma unroll
+        for (int i = 8; i < 16; i++) v[i] = in[t + (i - 8) * NT];
+    } else if (a.in_mode == IN_COEFF) {
+        const T *in = (const T *)a.in + bx * a.in_stride_x;
+        const T sc = (T)a.scale_in;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = mk<T>((T)0, (T)0);
+#pragma unroll
+        for (int i = 8; i < 16; i++) {
+            const int m = 2 * (t + (i - 8) * NT);            // sample index inside the partition
+            const long long g = (long long)by * L + m;      // index into the channel's coefficients
+            T c0 = (T)0, c1 = (T)0;
+            if (g < a.coeff_len) c0 = in[g] * sc;
+            if (g + 1 < a.coeff_len) c1 = in[g + 1] * sc;
+            bad = bad || !(c0 - c0 == (T)0) || !(c1 - c1 == (T)0); // NaN or Inf
+            v[i] = mk<T>(c0, c1);
+        }
+        if (bad) *a.nonfinite = 1;
+    } else { // IN_RAW_PREV
+        const int stream = bx / a.ch_per_stream, ch = bx - stream * a.ch_per_stream;
+        const int bytes = fmt_bytes(a.fmt);
+        const uint8_t *raw = (const uint8_t *)a.in + (long long)stream * a.in_stride_x + (long long)ch * bytes;
+        const long long step = (long long)a.ch_per_stream * bytes;
+        C *prev = (C *)((T *)a.prev + (long long)bx * L);
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = prev[t + i * NT];
+#pragma unroll
+        for (int i = 8; i < 16; i++) {
+            const int n = t + (i - 8) * NT;                  // complex index inside the current block
+            const uint8_t *p = raw + (long long)(2 * n) * step;
+            v[i] = mk<T>(load_raw<T>(p, a.fmt), load_raw<T>(p + step, a.fmt));
+            prev[n] = v[i];                                  // same thread read prev[n] above: no hazard
+        }
+        if (t == 0 && a.procblocks != NULL) {                // brutefir.cpp:265-268
+            const int pb = a.procblocks[bx];
+            const bool inc = pb < a.n_slots;
+            if (inc) a.procblocks[bx] = pb + 1;
+            a.pb_inc[bx] = inc ? 1 : 0;
+        }
+    }
+}
+
+// forward, phase 2: Z (natural order, padded smem) -> X_k, scaled, stored in ORD or HC layout
+template <class T, int LOG2M>
+BFIR_HD void fwd_split_store(int t, int bx, int by, const cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
+{
+    constexpr int M = 1 << LOG2M, NT = M / 16, N = 2 * M;
+    typedef cpx<T> C;
+    long long off = bx * a.out_stride_x + by * a.out_stride_y;
+    if (a.state != NULL) off += (long long)(a.state->blockcounter % (unsigned int)a.n_slots) * a.out_stride_y;
+    T *out = (T *)a.out + off;
+    const T sc = (T)a.scale_out;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int k = t + i * NT;
+        const C zk = smem[fft_pad(k)];
+        if (k == 0) {
+            const T dc = (zk.x + zk.y) * sc, ny = (zk.x - zk.y) * sc;
+            out[0] = dc;
+            if (a.out_layout == LAYOUT_ORD) out[4] = ny; else out[M] = ny;
+        } else {
+            const C zm = smem[fft_pad(M - k)];
+            // E = (Z_k + conj Z_{M-k})/2, O = (Z_k - conj Z_{M-k})/(2i), X_k = E + W_N^k O
+            const T er = (T)0.5 * (zk.x + zm.x), ei = (T)0.5 * (zk.y - zm.y);
+            const T dr = (T)0.5 * (zk.x - zm.x), di = (T)0.5 * (zk.y + zm.y);
+            const T o_r = di, o_i = -dr;
+            const C w = tw[k << tw_shift_n];
+            const T xr = (er + (w.x * o_r - w.y * o_i)) * sc;
+            const T xi = (ei + (w.x * o_i + w.y * o_r)) * sc;
+            if (a.out_layout == LAYOUT_ORD) {
+                const int base = ((k >> 2) << 3) + (k & 3);
+                out[base] = xr;
+                out[base + 4] = xi;
+            } else {
+                out[k] = xr;
+                out[N - k] = xi;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse, phase 0: Z'_k = (X_k + conj X_{M-k}) + i conj(W_N^k) (X_k - conj X_{M-k}),  k = t + i*NT
+template <class T, int LOG2M>
+BFIR_HD void inv_load(int t, int bx, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
+{
+    constexpr int M = 1 << LOG2M, NT = M / 16;
+    typedef cpx<T> C;
+    const T *in = (const T *)a.in + bx * a.in_stride_x;
+    const T sc = (T)a.scale_in;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int k = t + i * NT;
+        C xk = spec_load<T>(in, a.in_layout, k, M);
+        C xm = spec_load<T>(in, a.in_layout, M - k, M);
+        xk.x *= sc; xk.y *= sc; xm.x *= sc; xm.y *= sc;
+        const T er = xk.x + xm.x, ei = xk.y - xm.y;   // X_k + conj X_{M-k}
+        const T dr = xk.x - xm.x, di = xk.y + xm.y;   // X_k - conj X_{M-k}
+        const C w = tw[k << tw_shift_n];              // W_N^k; need its conjugate
+        const T pr = w.x * dr + w.y * di;             // conj(w) * d
+        const T pi = w.x * di - w.y * dr;
+        v[i] = mk<T>(er - pi, ei + pr);               // e + i p
+    }
+}
+
+// inverse, phase 1: v[i] = z[n], n = t + i*NT, x[2n] = Re, x[2n+1] = Im
+template <class T, int LOG2M>
+BFIR_HD void inv_store(int t, int bx, const cpx<T> (&v)[16], const InvArgs &a, OverflowAcc &acc)
+{
+    constexpr int M = 1 << LOG2M, NT = M / 16, L = M;
+    typedef cpx<T> C;
+    if (a.out_mode == OUT_TIME) {
+        C *out = (C *)((T *)a.out + bx * a.out_stride_x);
+#pragma unroll
+        for (int i = 0; i < 16; i++) out[t + i * NT] = v[i];
+        return;
+    }
+    if (t == 0 && a.state != NULL) {                   // brutefir.cpp:316-321
+        const T y0 = v[0].x;
+        if (!(y0 - y0 == (T)0)) {
+#ifdef __CUDA_ARCH__
+            atomicMin(&a.state->first_bad_channel, bx);
+#else
+            if (bx < a.state->first_bad_channel) a.state->first_bad_channel = bx;
+#endif
+        }
+    }
+    if (a.out_mode == OUT_REAL_L) {
+        C *out = (C *)((T *)a.out + (long long)bx * L);
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[t + i * NT] = v[i];
+        return;
+    }
+    // OUT_RAW
+    const int stream = bx / a.ch_per_stream, ch = bx - stream * a.ch_per_stream;
+    const int bytes = fmt_bytes(a.fmt);
+    uint8_t *raw = (uint8_t *)a.out + (long long)stream * a.out_stride_x + (long long)ch * bytes;
+    const long long step = (long long)a.ch_per_stream * bytes;
+    if (fmt_isfloat(a.fmt)) {
+        const T rmax = (T)a.ovf_max;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint8_t *p = raw + (long long)(2 * (t + i * NT)) * step;
+            store_raw_float<T>(p, a.fmt, v[i].x, rmax, acc);
+            store_raw_float<T>(p + step, a.fmt, v[i].y, rmax, acc);
+        }
+    } else {
+        int32_t imin, imax;
+        int_limits(a.fmt, imin, imax);
+        const T rmin = (T)imin, rmax = (T)imax;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint8_t *p = raw + (long long)(2 * (t + i * NT)) * step;
+            store_raw_quantised<T>(p, a.fmt, v[i].x, rmin, rmax, imin, imax, acc);
+            store_raw_quantised<T>(p + step, a.fmt, v[i].y, rmin, rmax, imin, imax, acc);
+        }
+    }
+}
+
+#ifdef __CUDACC__
+// merge per-thread statistics into the channel's counters: max / sum are order independent, so the
+// result equals the reference's serial update (real2raw.cpp:17-32, dither.cpp:226-271)
+__device__ __forceinline__ void overflow_commit(OverflowStats *dst, OverflowAcc acc)
+{
+    unsigned long long lb = (unsigned long long)__double_as_longlong(acc.largest);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.n_overflows += __shfl_xor_sync(0xffffffffu, acc.n_overflows, o);
+        acc.intlargest = max(acc.intlargest, __shfl_xor_sync(0xffffffffu, acc.intlargest, o));
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, lb, o);
+        lb = lb > other ? lb : other;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (acc.n_overflows) atomicAdd(&dst->n_overflows, acc.n_overflows);
+        if (acc.intlargest > 0) atomicMax(&dst->intlargest, acc.intlargest);
+        if (lb) atomicMax(&dst->largest_bits, lb);
+    }
+}
+
+template <class T, int LOG2M>
+__global__ void __launch_bounds__((1 << LOG2M) / 16) rfft_forward_kernel(const FwdArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
+    const int t = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+    cpx<T> v[16];
+    fwd_load<T, LOG2M>(t, bx, by, v, a);
+    fft_passes<T, LOG2M, false, 0, 0>::run(t, v, smem, tw, tw_shift_m);
+    BlockFFT<T, LOG2M, false>::store_natural(t, v, smem);
+    __syncthreads();
+    fwd_split_store<T, LOG2M>(t, bx, by, smem, tw, tw_shift_n, a);
+}
+
+template <class T, int LOG2M>
+__global__ void __launch_bounds__((1 << LOG2M) / 16) rfft_inverse_kernel(const InvArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
+    const int t = threadIdx.x, bx = blockIdx.x;
+    cpx<T> v[16];
+    inv_load<T, LOG2M>(t, bx, v, tw, tw_shift_n, a);
+    fft_passes<T, LOG2M, true, 0, 0>::run(t, v, smem, tw, tw_shift_m);
+    OverflowAcc acc;
+    acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
+    inv_store<T, LOG2M>(t, bx, v, a, acc);
+    if (a.out_mode == OUT_RAW && a.stats != NULL) {
+        // seed the running maxima with the channel's current values so "x > largest" keeps its meaning
+        overflow_commit(&a.stats[bx], acc);
+    }
+    if (a.state != NULL && bx == 0 && t == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
+}
+#endif
+
+} // namespace bfir

@@ -1,0 +1,210 @@
+/*
+ * bfir_b200.h -- C ABI of libbfir_b200.so, the B200 (sm_100a) drop-in for the BruteFIR convolver path
+ * of vsu/foo-dsp-bfir. Plain pointers and sizes only; no CUDA, C++ or torch types cross this boundary.
+ *
+ * Two nested surfaces are exported, mirroring the reference (citations relative to the reference tree):
+ *
+ *   ENGINE    bfir_*        replaces class `brutefir`            brutefir/brutefir.hpp:15-52
+ *             (what foo_dsp_bfir/foo_dsp_bfir.cpp:279-332 constructs and calls once per block)
+ *   CONVOLVER bfir_conv_*   replaces class `fftw_convolver`      brutefir/fftw_convolver.hpp:28-166
+ *             (per-function entry points on opaque cbufs; here the cbufs are DEVICE buffers obtained
+ *              from bfir_conv_alloc, because the reference's callers own, memset and memcpy them)
+ *
+ * Every function returns BFIR_OK (0) or a negative code; nothing throws across the boundary (the
+ * reference's bare `throw;` paths, brutefir/fftw_convolver.cpp:67,73,92, become BFIR_ERR_INVALID).
+ * There is NO CPU fallback: without a CUDA device every create call fails with BFIR_ERR_CUDA.
+ *
+ * Threading: like the reference, one thread per handle; different handles may be used from different
+ * threads concurrently (each owns a CUDA stream, there is no process-global mutable state).
+ */
+#ifndef BFIR_B200_H
+#define BFIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define BFIR_OK 0
+#define BFIR_ERR_NONFINITE (-1)   /* brutefir::run returned -1 (NaN/Inf in the system), brutefir.cpp:316-321 */
+#define BFIR_ERR_COEFF (-2)       /* set_coeff returned -2 (NaN/Inf among coefficients), brutefir.cpp:219-224 */
+#define BFIR_ERR_NOT_READY (-3)   /* run before set_coeff / channel without coefficients */
+#define BFIR_ERR_INVALID (-4)     /* invalid argument or unsupported size */
+#define BFIR_ERR_CUDA (-5)        /* CUDA runtime failure (see bfir_last_error) */
+
+/* sample formats: brutefir/global.h:24-37 */
+#define BFIR_SAMPLE_FORMAT_S8 1
+#define BFIR_SAMPLE_FORMAT_S16_LE 2
+#define BFIR_SAMPLE_FORMAT_S16_BE 3
+#define BFIR_SAMPLE_FORMAT_S24_LE 4
+#define BFIR_SAMPLE_FORMAT_S24_BE 5
+#define BFIR_SAMPLE_FORMAT_S32_LE 6
+#define BFIR_SAMPLE_FORMAT_S32_BE 7
+#define BFIR_SAMPLE_FORMAT_FLOAT_LE 8
+#define BFIR_SAMPLE_FORMAT_FLOAT_BE 9
+#define BFIR_SAMPLE_FORMAT_FLOAT64_LE 10
+#define BFIR_SAMPLE_FORMAT_FLOAT64_BE 11
+
+/* mix modes: brutefir/fftw_convolver.hpp:14-16 (INPUT_ADD is unimplemented in the reference too) */
+#define BFIR_MIXMODE_INPUT 1
+#define BFIR_MIXMODE_INPUT_ADD 2
+#define BFIR_MIXMODE_OUTPUT 3
+
+/* struct bfoverflow_t, brutefir/global.h:96-102 */
+typedef struct bfir_overflow_t {
+    unsigned int n_overflows;
+    int32_t intlargest;
+    double largest;
+    double max;
+} bfir_overflow_t;
+
+typedef struct bfir_engine bfir_engine;
+typedef struct bfir_conv bfir_conv;
+
+/* ------------------------------------------------------------------------------------------------
+ * ENGINE -- class brutefir
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Extended construction parameters. The first eight fields are the reference constructor's
+ * (brutefir/brutefir.hpp:18-25); the rest have no reference counterpart and default to
+ * {1, -1, 0, 0} through bfir_create. */
+typedef struct bfir_config_t {
+    int filter_length;   /* block length L, power of two, 16..16384 (realsize 4) / 16..8192 (realsize 8) */
+    int filter_blocks;   /* partitions P >= 1 */
+    int realsize;        /* 4 or 8 */
+    int channels;        /* channels per stream; no BF_MAXCHANNELS limit (global.h:21) */
+    int in_format;       /* BFIR_SAMPLE_FORMAT_* */
+    int out_format;
+    int sampling_rate;
+    int apply_dither;    /* integer output formats only (fftw_convolver.cpp:421,444) */
+    int n_streams;       /* independent streams batched in one engine; buffers are [stream][frame][channel] */
+    int device;          /* CUDA device ordinal, -1 = current device */
+    int part_begin;      /* partition shard [part_begin, part_begin+part_count) convolved by this engine; */
+    int part_count;      /* 0 = all. Sharded engines produce PARTIAL spectra, see bfir_run_partial_device */
+} bfir_config_t;
+
+/* brutefir::brutefir (brutefir.cpp:21-44). On failure *out is NULL. */
+int bfir_create(bfir_engine **out, int filter_length, int filter_blocks, int realsize, int channels,
+                int in_format, int out_format, int sampling_rate, int apply_dither);
+int bfir_create_ex(bfir_engine **out, const bfir_config_t *cfg);
+/* brutefir::~brutefir (brutefir.cpp:47-62) */
+void bfir_destroy(bfir_engine *e);
+/* brutefir::is_initialized (brutefir.cpp:68-72): 1 once set_coeff succeeded */
+int bfir_is_initialized(const bfir_engine *e);
+
+/* brutefir::set_coeff(void **coeffs, n_coeffs, length, coeff_blocks, scale) (brutefir.cpp:180-228):
+ * `coeffs[n]` = `length` HOST samples of type float (realsize 4) / double (realsize 8) for channel n;
+ * n_coeffs is clamped to the channel count (all streams x channels); the arrays are copied.
+ * Returns 0 or BFIR_ERR_COEFF (-2) when a scaled coefficient is NaN/Inf. */
+int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
+
+/* brutefir::run (brutefir.cpp:245-343): inbuf/outbuf are HOST buffers holding exactly
+ * n_streams * filter_length * channels interleaved samples in in_format / out_format. Synchronous:
+ * returns when outbuf is filled. Returns 0, or BFIR_ERR_NONFINITE (-1) when output sample 0 of some
+ * channel is NaN/Inf; in that case, as in the reference, the block counter is not advanced. */
+int bfir_run(bfir_engine *e, const void *inbuf, void *outbuf);
+
+/* Same block step on DEVICE buffers, asynchronous on the engine's stream (no error probing until
+ * bfir_sync, which returns BFIR_ERR_NONFINITE if any block since the last sync hit NaN/Inf). */
+int bfir_run_device(bfir_engine *e, const void *d_inbuf, void *d_outbuf);
+int bfir_sync(bfir_engine *e);
+
+/* brutefir::reset (brutefir.cpp:347-367): zeroes counters and overflow statistics, NOT the buffers */
+int bfir_reset(bfir_engine *e);
+/* struct bfoverflow_t overflow[channel] (brutefir.hpp:126) */
+int bfir_get_overflow(bfir_engine *e, int channel, bfir_overflow_t *out);
+/* brutefir::check_overflows (brutefir.cpp:371-388): prints "peak: ch/count/dB" through the print
+ * callback when the statistics changed since the last call; returns 1 if something was printed */
+int bfir_check_overflows(bfir_engine *e);
+/* dither_state_t.randtab_ptr of a channel (global.h:63-69), for parity checks of the table walk */
+int bfir_get_dither_ptr(bfir_engine *e, int channel, int *out);
+/* unsigned int blockcounter (brutefir.hpp:106) */
+int bfir_get_blockcounter(bfir_engine *e, unsigned int *out);
+
+/* Partition-sharded operation (one engine per GPU, no reference counterpart): run_partial_device
+ * executes input FFT + this shard's partition sum and leaves the PARTIAL accumulated spectra
+ * (n_channels * 2L reals, ORD layout) in the buffer returned by bfir_acc_device_ptr; after the caller
+ * has summed the shards' buffers (NCCL reduce / all-reduce), run_finish_device does the output stage. */
+int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf);
+int bfir_run_finish_device(bfir_engine *e, void *d_outbuf);
+void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
+
+/* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the engine's own. */
+int bfir_set_stream(bfir_engine *e, void *cuda_stream);
+
+/* pinfo / set_print_callback (brutefir/pinfo.h:17-18) */
+void bfir_set_print_callback(void (*cb)(const char *message));
+/* last error text of the calling thread */
+const char *bfir_last_error(void);
+/* number of kernels this library has launched in the process so far (all handles) */
+unsigned long long bfir_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * CONVOLVER -- class fftw_convolver. All cbuf / raw arguments are DEVICE pointers (bfir_conv_alloc),
+ * all calls are asynchronous on the convolver's stream; bfir_conv_download / bfir_conv_sync wait.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* fftw_convolver::fftw_convolver(length, realsize, dither) (fftw_convolver.cpp:51-138). The dither
+ * object of the reference (dither.cpp:21-110) is built inside for `n_dither_channels` channels. */
+int bfir_conv_create(bfir_conv **out, int length, int realsize, int n_dither_channels, int sampling_rate);
+void bfir_conv_destroy(bfir_conv *c);
+/* convolver_cbufsize (fftw_convolver.cpp:469-472): 2 * length * realsize bytes */
+int bfir_conv_cbufsize(const bfir_conv *c);
+
+void *bfir_conv_alloc(bfir_conv *c, size_t bytes);   /* zero-filled device memory */
+void bfir_conv_free(bfir_conv *c, void *d_ptr);
+int bfir_conv_upload(bfir_conv *c, void *d_dst, const void *h_src, size_t bytes);
+int bfir_conv_download(bfir_conv *c, void *h_dst, const void *d_src, size_t bytes);
+int bfir_conv_sync(bfir_conv *c);
+
+/* convolver_raw2cbuf (fftw_convolver.cpp:157-185): bf = {format, byte_offset, sample_spacing} */
+int bfir_conv_raw2cbuf(bfir_conv *c, const void *d_rawbuf, void *cbuf, void *next_cbuf, int format,
+                       int byte_offset, int sample_spacing);
+/* convolver_time2freq (fftw_convolver.cpp:188-212): T -> HC, in == out allowed */
+int bfir_conv_time2freq(bfir_conv *c, const void *input_cbuf, void *output_cbuf);
+/* convolver_mixnscale (fftw_convolver.cpp:215-229): input_cbufs = HOST array of n_bufs device cbufs;
+ * output must not alias an input; n_bufs <= 64 */
+int bfir_conv_mixnscale(bfir_conv *c, void *const *input_cbufs, void *output_cbuf, const double *scales,
+                        int n_bufs, int mixmode);
+/* convolver_convolve_inplace / convolve / convolve_add (fftw_convolver.cpp:232-273) on ORD cbufs */
+int bfir_conv_convolve_inplace(bfir_conv *c, void *cbuf, const void *coeffs);
+int bfir_conv_convolve(bfir_conv *c, const void *input_cbuf, const void *coeffs, void *output_cbuf);
+int bfir_conv_convolve_add(bfir_conv *c, const void *input_cbuf, const void *coeffs, void *output_cbuf);
+/* convolver_crossfade_inplace (fftw_convolver.cpp:276-321), float-branch algorithm in both precisions.
+ * input_cbuf (ORD, new filter) becomes the cross-faded spectrum; crossfade_cbuf (ORD, old filter) and
+ * buffer_cbuf are destroyed. */
+int bfir_conv_crossfade_inplace(bfir_conv *c, void *input_cbuf, void *crossfade_cbuf, void *buffer_cbuf);
+/* convolver_dirac_convolve[_inplace] (fftw_convolver.cpp:324-348) on HC cbufs */
+int bfir_conv_dirac_convolve(bfir_conv *c, const void *input_cbuf, void *output_cbuf);
+int bfir_conv_dirac_convolve_inplace(bfir_conv *c, void *cbuf);
+/* convolver_freq2time (fftw_convolver.cpp:351-375): HC -> time, in == out allowed */
+int bfir_conv_freq2time(bfir_conv *c, const void *input_cbuf, void *output_cbuf);
+/* convolver_convolve_eval (fftw_convolver.cpp:378-403): buffer_cbuf is 1.5 cbufs, zeroed before first use */
+int bfir_conv_convolve_eval(bfir_conv *c, const void *input_cbuf, void *buffer_cbuf, void *output_cbuf);
+/* convolver_cbuf2raw (fftw_convolver.cpp:406-466): `overflow` is a HOST struct, read and updated;
+ * synchronous. dither_channel selects the dither_state_t. */
+int bfir_conv_cbuf2raw(bfir_conv *c, const void *cbuf, void *d_outbuf, int format, int byte_offset,
+                       int sample_spacing, int apply_dither, int dither_channel, bfir_overflow_t *overflow);
+/* convolver_coeffs2cbuf (fftw_convolver.cpp:475-537): `coeffs` are n_coeffs HOST samples; d_dest is a
+ * device cbuf (the reference's optional_dest). Synchronous; BFIR_ERR_COEFF on NaN/Inf. */
+int bfir_conv_coeffs2cbuf(bfir_conv *c, const void *coeffs, int n_coeffs, double scale, void *d_dest);
+/* convolver_runtime_coeffs2cbuf (fftw_convolver.cpp:540-567): d_src = length device samples */
+int bfir_conv_runtime_coeffs2cbuf(bfir_conv *c, const void *d_src, void *d_dest);
+/* dither object inspection for parity: table bytes, map [-256..255] (512 entries of realsize), pointers */
+int bfir_conv_dither_table_size(bfir_conv *c);
+int bfir_conv_dither_table(bfir_conv *c, int8_t *h_out, int n);
+int bfir_conv_dither_map(bfir_conv *c, void *h_out);
+int bfir_conv_dither_ptr(bfir_conv *c, int channel);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFIR_B200_H */

@@ -1,0 +1,276 @@
+"""GPU parity of the convolver entry points (class fftw_convolver, reference
+brutefir/fftw_convolver.hpp:28-166): each bfir_conv_* call is compared with the CPU oracle on
+identical buffers, through the C ABI. Tolerances: 1e-5 relative RMS (float) / 1e-12 (double) as the
+north star states; the element-wise entry points are bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import rel_rms, encode_raw, decode_raw
+
+pytestmark = pytest.mark.gpu
+
+TOL = {4: 1e-5, 8: 1e-12}
+SIZES = [(16, 4), (64, 4), (512, 4), (1024, 8), (4096, 4), (8192, 8), (16384, 4), (32, 8), (2048, 8)]
+
+
+def make(pkg, oracle, L, rs):
+    return pkg.FftwConvolver(L, rs), oracle.Convolver(L, rs)
+
+
+@pytest.mark.parametrize("L,rs", SIZES)
+def test_time2freq_freq2time(pkg, oracle, L, rs):
+    g, o = make(pkg, oracle, L, rs)
+    rng = np.random.default_rng(L + rs)
+    x = rng.uniform(-1, 1, 2 * L).astype(g.dtype)
+    bx, bh, bt = g.cbuf(x), g.cbuf(), g.cbuf()
+    g.convolver_time2freq(bx, bh)
+    hc = g.get(bh)
+    ref = o.time2freq(x)
+    assert rel_rms(hc, ref) < TOL[rs]
+    g.convolver_freq2time(bh, bt)
+    assert rel_rms(g.get(bt), o.freq2time(ref.copy())) < TOL[rs]
+    # HC2R(R2HC(x)) = N x  (property 4)
+    assert rel_rms(g.get(bt), 2 * L * x.astype(np.float64)) < TOL[rs]
+    # in place
+    g.convolver_time2freq(bx, bx)
+    assert rel_rms(g.get(bx), ref) < TOL[rs]
+    g.convolver_freq2time(bx, bx)
+    assert rel_rms(g.get(bx), 2 * L * x.astype(np.float64)) < TOL[rs]
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("n_bufs", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("mode", [1, 3])
+def test_mixnscale_bit_exact(pkg, oracle, rs, n_bufs, mode):
+    L = 256
+    g, o = make(pkg, oracle, L, rs)
+    rng = np.random.default_rng(n_bufs * 10 + mode)
+    bufs = [rng.standard_normal(2 * L).astype(g.dtype) for _ in range(n_bufs)]
+    scales = list(rng.uniform(0.1, 2.0, n_bufs))
+    dev = [g.cbuf(b) for b in bufs]
+    out = g.cbuf()
+    assert g.convolver_mixnscale(dev, out, scales, mode) == 0
+    ref = o.mixnscale(bufs, scales, mode)
+    assert np.array_equal(g.get(out), ref)
+
+
+def test_mixnscale_roundtrip_and_invalid_mode(pkg, oracle):
+    L, rs = 128, 8
+    g, o = make(pkg, oracle, L, rs)
+    x = np.random.default_rng(5).standard_normal(2 * L)
+    a, b, c = g.cbuf(x), g.cbuf(), g.cbuf()
+    g.convolver_mixnscale([a], b, [0.25], pkg.MIXMODE_INPUT)
+    g.convolver_mixnscale([b], c, [4.0], pkg.MIXMODE_OUTPUT)
+    assert np.array_equal(g.get(c), x)            # OUTPUT o INPUT = identity x scale (property 2)
+    # MIXMODE_INPUT_ADD is declared but unimplemented in the reference (fftw_convolver.cpp:1423-1425)
+    assert g.convolver_mixnscale([a], b, [1.0], pkg.MIXMODE_INPUT_ADD) == pkg.ERR_INVALID
+
+
+@pytest.mark.parametrize("L,rs", [(16, 4), (512, 4), (512, 8), (4096, 4)])
+def test_convolve_family_bit_exact(pkg, oracle, L, rs):
+    g, o = make(pkg, oracle, L, rs)
+    rng = np.random.default_rng(L)
+    x = rng.standard_normal(2 * L).astype(g.dtype)
+    c = rng.standard_normal(2 * L).astype(g.dtype)
+    d0 = rng.standard_normal(2 * L).astype(g.dtype)
+    bx, bc, bd = g.cbuf(x), g.cbuf(c), g.cbuf(d0)
+    out = g.cbuf()
+    g.convolver_convolve(bx, bc, out)
+    assert np.array_equal(g.get(out), o.convolve(x, c))
+    g.convolver_convolve_add(bx, bc, bd)
+    assert np.array_equal(g.get(bd), o.convolve_add(x, c, d0.copy()))
+    g.convolver_convolve_inplace(bx, bc)
+    assert np.array_equal(g.get(bx), o.convolve_inplace(x.copy(), c))
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_dirac_convolve(pkg, oracle, rs):
+    L = 512
+    g, o = make(pkg, oracle, L, rs)
+    x = np.random.default_rng(9).standard_normal(2 * L).astype(g.dtype)
+    bx, out = g.cbuf(x), g.cbuf()
+    g.convolver_dirac_convolve(bx, out)
+    ref = o.dirac_convolve(x)
+    assert np.array_equal(g.get(out), ref)
+    g.convolver_dirac_convolve_inplace(bx)
+    assert np.array_equal(g.get(bx), ref)
+    # property 3: dirac == ORD->HC(convolve(HC->ORD(x), coeffs2cbuf([1])))
+    one = g.cbuf()
+    assert g.convolver_coeffs2cbuf(np.array([1.0]), 1, 1.0, one) == 0
+    xo, yo, yh = g.cbuf(), g.cbuf(), g.cbuf()
+    bx2 = g.cbuf(x)
+    g.convolver_mixnscale([bx2], xo, [1.0], pkg.MIXMODE_INPUT)
+    g.convolver_convolve(xo, one, yo)
+    g.convolver_mixnscale([yo], yh, [1.0], pkg.MIXMODE_OUTPUT)
+    assert rel_rms(g.get(yh), ref) < TOL[rs] * 10
+
+
+@pytest.mark.parametrize("L,rs", [(64, 4), (1024, 4), (1024, 8), (8192, 8), (16384, 4)])
+def test_coeffs2cbuf(pkg, oracle, L, rs):
+    g, o = make(pkg, oracle, L, rs)
+    rng = np.random.default_rng(L)
+    for n in (L, L - 5, 1, 0, L + 7):
+        h = rng.standard_normal(max(n, 1)).astype(g.dtype)
+        dest = g.cbuf(np.full(2 * L, 7.0))
+        assert g.convolver_coeffs2cbuf(h, n, 0.5, dest) == 0
+        ref = o.coeffs2cbuf(h, 0.5, n=n)
+        got = g.get(dest)
+        if n == 0:
+            assert np.all(got == 0)
+        else:
+            assert rel_rms(got, ref) < TOL[rs]
+    bad = rng.standard_normal(L).astype(g.dtype)
+    bad[L // 2] = np.nan
+    assert g.convolver_coeffs2cbuf(bad, L, 1.0, g.cbuf()) == pkg.ERR_COEFF   # reference returns NULL
+    assert o.coeffs2cbuf(bad) is None
+    bad[L // 2] = np.inf
+    assert g.convolver_coeffs2cbuf(bad, L, 1.0, g.cbuf()) == pkg.ERR_COEFF
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_runtime_coeffs2cbuf(pkg, oracle, rs):
+    L = 2048
+    g, o = make(pkg, oracle, L, rs)
+    h = np.random.default_rng(3).standard_normal(L).astype(g.dtype)
+    src, dest = g.cbuf(h, n_cbufs=0.5), g.cbuf()
+    g.convolver_runtime_coeffs2cbuf(src, dest)
+    got = g.get(dest)
+    assert rel_rms(got, o.runtime_coeffs2cbuf(h)) < TOL[rs]
+    assert rel_rms(got, o.coeffs2cbuf(h)) < TOL[rs]
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_crossfade_inplace(pkg, oracle, rs):
+    L = 1024
+    g = pkg.FftwConvolver(L, rs)
+    o = oracle.Convolver(L, rs, kind="port" if rs == 8 else None)  # double: float-branch algorithm
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, 2 * L).astype(g.dtype)
+    new = o.convolve(o.mixnscale([o.time2freq(x)], [1.0], 1), o.coeffs2cbuf(rng.standard_normal(L)))
+    old = o.convolve(o.mixnscale([o.time2freq(x)], [1.0], 1), o.coeffs2cbuf(rng.standard_normal(L)))
+    bi, bx, bb = g.cbuf(new), g.cbuf(old), g.cbuf()
+    g.convolver_crossfade_inplace(bi, bx, bb)
+    ref = o.crossfade_inplace(new.copy(), old.copy(), o.cbuf())
+    assert rel_rms(g.get(bi), ref) < TOL[rs] * 2
+    # semantic check: IFFT of the result ramps old -> new over the first half
+    y = o.freq2time(o.mixnscale([g.get(bi)], [1.0], 3))[:L]
+    y_old = o.freq2time(o.mixnscale([old], [1.0], 3))[:L]
+    y_new = o.freq2time(o.mixnscale([new], [1.0], 3))[:L]
+    w = np.arange(L) / (L - 1)
+    assert rel_rms(y, y_old * (1 - w) + y_new * w) < 1e-4 if rs == 4 else 1e-10
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_convolve_eval(pkg, oracle, rs):
+    L = 512
+    g, o = make(pkg, oracle, L, rs)
+    rng = np.random.default_rng(21)
+    buf_g = g.cbuf(n_cbufs=1.5)
+    buf_o = np.zeros(3 * L, dtype=g.dtype)
+    for _ in range(3):
+        hc = o.time2freq(rng.uniform(-1, 1, 2 * L).astype(g.dtype))
+        bi, bo = g.cbuf(hc), g.cbuf()
+        g.convolver_convolve_eval(bi, buf_g, bo)
+        ref = o.convolve_eval(hc, buf_o)
+        scale = 2 * L
+        assert rel_rms(g.get(bo) / scale, ref / scale) < TOL[rs] * 2
+        assert rel_rms(buf_g.download(g.dtype)[:L], buf_o[:L]) < TOL[rs] * 2
+
+
+FORMATS = list(range(1, 12))
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_raw2cbuf_all_formats_bit_exact(pkg, oracle, rs, fmt):
+    L, C = 256, 3
+    g, o = make(pkg, oracle, L, rs)
+    x = np.random.default_rng(fmt).uniform(-1, 1, (L, C))
+    raw = encode_raw(x, fmt)
+    nbytes = pkg.FORMAT_BYTES[fmt]
+    draw = g.rawbuf(raw)
+    for ch in range(C):
+        cb, nb = g.cbuf(), g.cbuf()
+        g.convolver_raw2cbuf(draw, cb, nb, fmt, ch * nbytes, C)
+        rc, rn = o.cbuf(), o.cbuf()
+        o.raw2cbuf(raw, rc, rn, fmt, ch, C)
+        assert np.array_equal(g.get(cb), rc)
+        assert np.array_equal(g.get(nb), rn)
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_cbuf2raw_no_dither_bit_exact(pkg, oracle, rs, fmt):
+    L, C = 512, 2
+    g, o = make(pkg, oracle, L, rs)
+    rng = np.random.default_rng(100 + fmt)
+    nbytes = pkg.FORMAT_BYTES[fmt]
+    isfloat = fmt >= 8
+    full = 1.0 if isfloat else float(2 ** (8 * nbytes - 1))
+    y = (rng.uniform(-1.2, 1.2, 2 * L) * full).astype(g.dtype)
+    # quantiser truth table around 0 / +-0.5 / integers / limits (property 6)
+    if not isfloat:
+        y[:12] = np.array([0.0, -0.0, 0.49, 0.5, -0.49, -0.5, -0.51, 3.0, -3.0, full - 1, -full, -full + 0.4], dtype=g.dtype)
+    cb = g.cbuf(y)
+    draw = g.rawbuf(nbytes=L * C * nbytes)
+    for ch in range(C):
+        og, orf = pkg.Overflow(), oracle.Overflow()
+        og.max = orf.max = 1.0 if isfloat else full - 1
+        out_ref = np.zeros(L * C * nbytes, dtype=np.uint8)
+        g.convolver_cbuf2raw(cb, draw, fmt, ch * nbytes, C, False, 0, og)
+        o.cbuf2raw(y, out_ref, fmt, ch, C, False, 0, orf)
+        got = draw.download(np.uint8)
+        step = C * nbytes
+        for b in range(nbytes):
+            assert np.array_equal(got[ch * nbytes + b::step], out_ref[ch * nbytes + b::step])
+        assert og.as_tuple() == orf.as_tuple()
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("fmt", [1, 2, 3, 4, 6])
+def test_cbuf2raw_dither_bit_exact(pkg, oracle, rs, fmt):
+    """dither table, table walk and the serial hp-tpdf requantiser, fed the SAME real buffer"""
+    L, rate, nch = 1024, 4000, 2
+    g = pkg.FftwConvolver(L, rs, nch, rate)
+    o = oracle.Convolver(L, rs, n_channels=nch, sample_rate=rate)
+    assert np.array_equal(g.dither_table(), o.dither_table())
+    assert np.array_equal(g.dither_map()[:511], o.dither_map())
+    nbytes = pkg.FORMAT_BYTES[fmt]
+    full = float(2 ** (8 * nbytes - 1))
+    rng = np.random.default_rng(fmt)
+    draw = g.rawbuf(nbytes=L * nbytes)
+    og, orf = pkg.Overflow(), oracle.Overflow()
+    og.max = orf.max = full - 1
+    # 50 blocks: the walk of channel 1 wraps at block 39 and stops before table index 18310, the first
+    # place where tab[n]-tab[n-1] == +255 (out of bounds in the reference, dither.cpp:77-78,160-161)
+    for blk in range(50):
+        y = (rng.uniform(-1.05, 1.05, 2 * L) * full * (0.01 if blk % 3 == 0 else 1.0)).astype(g.dtype)
+        cb = g.cbuf(y)
+        out_ref = np.zeros(L * nbytes, dtype=np.uint8)
+        g.convolver_cbuf2raw(cb, draw, fmt, 0, 1, True, 1, og)
+        o.cbuf2raw(y, out_ref, fmt, 0, 1, True, 1, orf)
+        assert np.array_equal(draw.download(np.uint8), out_ref), blk
+        assert g.dither_ptr(1) == o.dither_ptr(1)
+        assert og.as_tuple() == orf.as_tuple()
+
+
+def test_dither_map_entry_255_policy(pkg, oracle):
+    """delta +255 indexes one past the reference's 511-entry map (dither.cpp:77-78): the build defines
+    it by continuing the formula; the restatement (port) pins the same value"""
+    L, rate = 1024, 4000
+    g = pkg.FftwConvolver(L, 4, 1, rate)
+    o = oracle.Convolver(L, 4, kind="port", n_channels=1, sample_rate=rate)
+    m = g.dither_map()
+    assert m[511] == np.float32(0.5 + 1.0 / 255.0 + 255.0 / 255.0)
+    tab = g.dither_table().astype(int)
+    assert 255 in np.diff(tab[:30 * L])      # the walk below really crosses such a delta
+    draw = g.rawbuf(nbytes=L * 2)
+    og, orf = pkg.Overflow(), oracle.Overflow()
+    og.max = orf.max = 32767.0
+    rng = np.random.default_rng(1)
+    for blk in range(30):
+        y = (rng.uniform(-1, 1, 2 * L) * 30000).astype(np.float32)
+        out_ref = np.zeros(L * 2, dtype=np.uint8)
+        g.convolver_cbuf2raw(g.cbuf(y), draw, 2, 0, 1, True, 0, og)
+        o.cbuf2raw(y, out_ref, 2, 0, 1, True, 0, orf)
+        assert np.array_equal(draw.download(np.uint8), out_ref), blk

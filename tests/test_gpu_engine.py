@@ -1,0 +1,218 @@
+"""GPU parity of the block loop (class brutefir, reference brutefir/brutefir.cpp:245-343) through
+bfir_run: CUDA path vs the CPU oracle on the same seeded inputs, plus size-independent properties
+(run() == direct linear convolution) at the BASELINE.json sizes."""
+import numpy as np
+import pytest
+
+from conftest import white_noise, decay_filter, rel_rms, encode_raw, decode_raw
+
+pytestmark = pytest.mark.gpu
+
+TOL = {4: 1e-5, 8: 1e-12}
+
+
+def run_both(pkg, oracle, L, P, rs, C, in_fmt, out_fmt, n_blocks, dither=False, rate=44100, taps=None,
+             coeff_blocks=None, scale=1.0, amp=1.0, seed=0):
+    taps = L * P if taps is None else taps
+    coeff_blocks = P if coeff_blocks is None else coeff_blocks
+    g = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, rate, dither)
+    o = oracle.Engine(L, P, rs, C, in_fmt, out_fmt, rate, dither)
+    h = [decay_filter(c, taps) for c in range(C)]
+    assert g.set_coeff(h, coeff_blocks, scale) == 0
+    assert o.set_coeff(h, coeff_blocks, scale) == 0
+    assert g.is_initialized() and o.is_initialized()
+    x = white_noise(seed, n_blocks * L, C) * amp
+    outs_g, outs_o = [], []
+    for b in range(n_blocks):
+        raw = encode_raw(x[b * L:(b + 1) * L], in_fmt)
+        rc_g, out_g = g.run(raw)
+        rc_o, out_o = o.run(raw)
+        assert rc_g == 0 and rc_o == 0
+        outs_g.append(decode_raw(out_g, out_fmt, C))
+        outs_o.append(decode_raw(out_o, out_fmt, C))
+    return g, o, x, h, np.concatenate(outs_g), np.concatenate(outs_o)
+
+
+@pytest.mark.parametrize("L,P,rs,C", [(64, 3, 4, 2), (256, 5, 8, 3), (1024, 4, 4, 8), (16, 2, 8, 1), (512, 1, 4, 2),
+                                      (2048, 7, 8, 2), (128, 16, 4, 11)])
+def test_run_matches_oracle_float_io(pkg, oracle, L, P, rs, C):
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    g, o, x, h, yg, yo = run_both(pkg, oracle, L, P, rs, C, fmt, fmt, 3 * P + 2, taps=L * P - 3)
+    for c in range(C):
+        assert rel_rms(yg[:, c], yo[:, c]) < TOL[rs]
+    assert g.blockcounter() == o.blockcounter() == 3 * P + 2
+    for c in range(C):
+        a, b = g.overflow(c), o.overflow(c)
+        assert a.n_overflows == b.n_overflows and a.max == b.max
+        assert abs(a.largest - b.largest) <= 1e-4 * max(1.0, b.largest)
+
+
+def test_cfg0_stereo_float_vs_oracle_and_direct(pkg, oracle):
+    """BASELINE configs[0]: stereo float, 65536 taps, L=4096, P=16"""
+    from oracle import oracle_np
+    L, P = 4096, 16
+    g, o, x, h, yg, yo = run_both(pkg, oracle, L, P, 4, 2, pkg.FLOAT_LE, pkg.FLOAT_LE, 24)
+    for c in range(2):
+        assert rel_rms(yg[:, c], yo[:, c]) < 1e-5
+        truth = oracle_np.direct_convolution(x[:, c].astype(np.float32), h[c].astype(np.float32), len(x))
+        assert rel_rms(yg[:, c], truth) < 1e-5
+
+
+def test_cfg1_double_vs_oracle_and_direct(pkg, oracle):
+    """BASELINE configs[1]: 7.1 (8 ch) double, 262144 taps, L=8192, P=32"""
+    from oracle import oracle_np
+    L, P, C = 8192, 32, 8
+    g, o, x, h, yg, yo = run_both(pkg, oracle, L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 36)
+    for c in range(C):
+        assert rel_rms(yg[:, c], yo[:, c]) < 1e-12
+        assert rel_rms(yg[:, c], oracle_np.direct_convolution(x[:, c], h[c], len(x))) < 1e-12
+
+
+def test_product_configuration_float_io_double_engine(pkg, oracle):
+    """what foo_dsp_bfir constructs: FILTER_LEN 1024, REALSIZE 8, FLOAT_LE in/out (foo_dsp_bfir.cpp:279-286)"""
+    g, o, x, h, yg, yo = run_both(pkg, oracle, 1024, 8, 8, 2, pkg.FLOAT_LE, pkg.FLOAT_LE, 20)
+    assert rel_rms(yg, yo) < 1e-7     # output is rounded to float32 on both sides
+
+
+@pytest.mark.parametrize("in_fmt", list(range(1, 12)))
+def test_all_input_formats(pkg, oracle, in_fmt):
+    g, o, x, h, yg, yo = run_both(pkg, oracle, 256, 3, 4, 2, in_fmt, pkg.FLOAT_LE, 8)
+    assert rel_rms(yg, yo) < 1e-5
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("out_fmt", [1, 2, 3, 4, 5, 6, 7])
+def test_integer_output_no_dither_within_1lsb(pkg, oracle, rs, out_fmt):
+    in_fmt = pkg.FLOAT_LE
+    g, o, x, h, yg, yo = run_both(pkg, oracle, 512, 4, rs, 2, in_fmt, out_fmt, 10, amp=1.3)
+    assert np.max(np.abs(yg - yo)) <= 1          # within 1 LSB with dither off (north star)
+    frac_equal = np.mean(yg == yo)
+    assert frac_equal > 0.99 if out_fmt in (1, 2, 3) else frac_equal > 0.5
+    for c in range(2):
+        a, b = g.overflow(c), o.overflow(c)
+        assert abs(int(a.n_overflows) - int(b.n_overflows)) <= 2 and b.n_overflows > 0
+        assert abs(a.intlargest - b.intlargest) <= 1
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_dithered_output_table_walk_and_lsb(pkg, oracle, rs):
+    """dither on: the table walk (randtab_ptr per block) is bit-exact; samples stay within 1 LSB of the
+    oracle except where the (different-rounding) convolution output flips a quantiser decision"""
+    L, P, C, rate = 256, 3, 2, 2000
+    g, o, x, h, yg, yo = run_both(pkg, oracle, L, P, rs, C, pkg.FLOAT_LE, pkg.S16_LE, 90, dither=True, rate=rate)
+    for c in range(C):
+        assert g.dither_ptr(c) == o.dither_ptr(c)
+    assert np.mean(np.abs(yg - yo) <= 1) > 0.999
+    assert np.max(np.abs(yg - yo)) <= 2
+
+
+def test_reset_keeps_buffers_and_restarts_counters(pkg, oracle):
+    L, P, C = 128, 4, 2
+    g = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    o = oracle.Engine(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    h = [decay_filter(c, L * P) for c in range(C)]
+    g.set_coeff(h, P); o.set_coeff(h, P)
+    x = white_noise(3, 12 * L, C)
+    for b in range(12):
+        if b == 6:
+            g.reset(); o.reset()     # brutefir.cpp:347-367: counters only; stale time block remains
+            assert g.blockcounter() == 0
+        raw = encode_raw(x[b * L:(b + 1) * L], pkg.FLOAT_LE)
+        _, yg = g.run(raw)
+        _, yo = o.run(raw)
+        assert rel_rms(yg.view(np.float32), yo.view(np.float32)) < 1e-5
+
+
+def test_nonfinite_input_returns_minus_one_and_does_not_advance(pkg, oracle):
+    L, P, C = 64, 2, 3
+    g = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    o = oracle.Engine(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    h = [decay_filter(c, L * P) for c in range(C)]
+    g.set_coeff(h, P); o.set_coeff(h, P)
+    x = white_noise(5, L, C).astype(np.float32)
+    assert g.run(x.view(np.uint8).ravel())[0] == 0 and o.run(x.view(np.uint8).ravel())[0] == 0
+    bad = x.copy(); bad[3, 1] = np.nan
+    assert g.run(bad.view(np.uint8).ravel())[0] == -1       # brutefir.cpp:316-321
+    assert o.run(bad.view(np.uint8).ravel())[0] == -1
+    assert g.blockcounter() == o.blockcounter() == 1        # :337-340 not reached
+
+
+def test_set_coeff_errors_and_replacement(pkg, oracle):
+    L, P, C = 64, 2, 2
+    g = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    assert not g.is_initialized()
+    x = white_noise(1, L, C).astype(np.float32).view(np.uint8).ravel()
+    with pytest.raises(pkg.BfirError):
+        g.run(x)                                            # run before set_coeff
+    h = [decay_filter(c, L * P) for c in range(C)]
+    hbad = [h[0].copy(), h[1].copy()]
+    hbad[1][5] = np.inf
+    assert g.set_coeff(hbad, P) == -2 and not g.is_initialized()   # brutefir.cpp:219-224
+    assert g.set_coeff(h, P) == 0 and g.is_initialized()
+    y1 = g.run(x)[1].copy()
+    assert g.set_coeff([2 * h[0], 2 * h[1]], P) == 0               # replacing filters keeps the delay line
+    g2 = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    g2.set_coeff(h, P, 2.0)
+    assert rel_rms(g2.run(x)[1].view(np.float32), 2 * y1.view(np.float32)) < 1e-6
+
+
+def test_invalid_parameters(pkg):
+    for args in [(100, 2, 4, 2, 8, 8, 44100, False), (64, 2, 5, 2, 8, 8, 44100, False), (64, 0, 4, 2, 8, 8, 44100, False),
+                 (64, 2, 4, 0, 8, 8, 44100, False), (64, 2, 4, 2, 0, 8, 44100, False), (64, 2, 4, 2, 8, 12, 44100, False),
+                 (32768, 2, 4, 2, 8, 8, 44100, False), (16384, 2, 8, 2, 8, 8, 44100, False)]:
+        with pytest.raises(pkg.BfirError) as e:
+            pkg.Brutefir(*args)
+        assert e.value.code == pkg.ERR_INVALID
+
+
+def test_streams_batch_equals_separate_engines(pkg, oracle):
+    """n_streams batching (cfg3 layout [stream][frame][channel]) == independent engines"""
+    L, P, C, S = 256, 3, 2, 5
+    g = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False, n_streams=S)
+    h = [decay_filter(c, L * P) for c in range(C * S)]
+    assert g.set_coeff(h, P) == 0
+    singles = []
+    for s in range(S):
+        e = oracle.Engine(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+        e.set_coeff(h[s * C:(s + 1) * C], P)
+        singles.append(e)
+    x = white_noise(9, 6 * L, C * S).astype(np.float32)
+    for b in range(6):
+        blk = x[b * L:(b + 1) * L]                                  # [L, S*C]
+        batched = np.ascontiguousarray(blk.reshape(L, S, C).transpose(1, 0, 2))   # [S, L, C]
+        _, out = g.run(batched.view(np.uint8).ravel())
+        out = out.view(np.float32).reshape(S, L, C)
+        for s in range(S):
+            _, ref = singles[s].run(np.ascontiguousarray(batched[s]).view(np.uint8).ravel())
+            assert rel_rms(out[s], ref.view(np.float32).reshape(L, C)) < 1e-5
+
+
+def test_partition_shards_sum_to_full_filter(pkg, oracle):
+    """partition sharding: partial spectra of two shards summed == unsharded engine"""
+    import torch
+    L, P, C = 512, 8, 2
+    h = [decay_filter(c, L * P) for c in range(C)]
+    full = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    a = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False, part_begin=0, part_count=3)
+    b = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False, part_begin=3, part_count=5)
+    for e in (full, a, b):
+        assert e.set_coeff(h, P) == 0
+    pa, n = a.acc_device_ptr()
+    pb, _ = b.acc_device_ptr()
+    ta, tb = pkg.as_torch(pa, n // 4, "<f4"), pkg.as_torch(pb, n // 4, "<f4")
+    x = white_noise(2, 12 * L, C).astype(np.float32)
+    d_in = torch.empty(L * C, dtype=torch.float32, device="cuda")
+    outs = [torch.empty(L * C, dtype=torch.float32, device="cuda") for _ in range(3)]
+    for blk in range(12):
+        d_in.copy_(torch.from_numpy(x[blk * L:(blk + 1) * L].ravel()))
+        torch.cuda.synchronize()
+        full.run_device(d_in, outs[0])
+        a.run_partial_device(d_in)
+        b.run_partial_device(d_in)
+        assert full.sync() == 0 and a.sync() == 0 and b.sync() == 0
+        ta += tb                                   # what the NCCL reduce does across GPUs
+        torch.cuda.synchronize()
+        a.run_finish_device(outs[1])
+        b.run_finish_device(outs[2])               # keeps shard b's block counter in step
+        assert a.sync() == 0 and b.sync() == 0
+        assert rel_rms(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 1e-6, blk
