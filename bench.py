@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the partitioned-convolution hot path (BASELINE.json metric:
+"Msamples/s (all channels) at 262144 taps", configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (one "step" = one block of the block loop, brutefir::run, for every stream of the batch):
+  cfg1: 7.1 (8 channels) @ 48 kHz, double precision (realsize 8), FLOAT64_LE in/out, 262144-tap FIR per
+  channel = P 32 partitions of L 8192 samples (FFT 16384 points), distinct filter per channel.
+  S independent 7.1 streams are batched per GPU so that the streamed set (coefficient spectra + delay
+  line = S x 64 MiB) exceeds the 126 MB L2 -- no L2 flush is needed between steps. N GPUs: every rank
+  runs its own S streams (channel/stream sharding, no collective): weak scaling.
+
+Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM; e2e = the
+same metric through bfir_run with pinned HOST buffers (H2D + kernels + D2H + sync per step); roofline
+= partition-MAC kernel, algorithmic bytes (2P+1)*N*realsize per channel-block over its CUDA-event
+time; cpu_baseline = the reference's own sources (oracle/_ref, FFT provider named) on the host cores;
+latency = host-visible bfir_run latency of ONE 7.1 stream (p50/p99).
+`--impl reference` times only the CPU reference (rank 0), same metric/config.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(name="cfg1", channels=8, realsize=8, L=8192, P=32, rate=48000, fmt=10)  # FLOAT64_LE
+METRIC = "Msamples/s (all channels) at 262144 taps"
+
+
+def workload_config(streams, n_gpus):
+    return {
+        "workload": "cfg1: 7.1 room correction 48 kHz, 262144-tap double-precision FIR per channel, "
+                    "8192-sample partitions (P=32, FFT 16384), FLOAT64_LE in/out, distinct filters",
+        "streams_per_gpu": streams, "channels_per_stream": CFG["channels"], "block": CFG["L"], "partitions": CFG["P"],
+        "samples_per_step": streams * CFG["channels"] * CFG["L"] * n_gpus,
+        "parallelism": "stream-sharded x%d (no collective)" % n_gpus,
+        "l2": "streamed set per step (%d MiB coefficient + delay-line spectra per GPU) exceeds the 126 MB L2; no flush"
+              % (streams * CFG["channels"] * 2 * CFG["P"] * 2 * CFG["L"] * CFG["realsize"] // (1 << 20)),
+        "prefill_blocks": CFG["P"],
+    }
+
+
+def make_filters(n_channels, taps, first=0):
+    out = []
+    for ch in range(n_channels):
+        g = np.random.default_rng(1000 + first + ch).standard_normal(taps)
+        h = g * np.exp(-6.9 * np.arange(taps) / taps)
+        out.append(h / np.sqrt(np.sum(h * h)))
+    return out
+
+
+def noise_block(seed, streams, L, C):
+    return np.random.default_rng(0xB200 + seed).uniform(-1.0, 1.0, size=(streams, L, C))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.stop_flag = threading.Event()
+        self.busy = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {}
+            for n in dir(pynvml):
+                if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                    v = getattr(pynvml, n)
+                    if isinstance(v, int) and v not in (0,):
+                        names.setdefault(v, n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            while not self.stop_flag.is_set():
+                if self.busy.is_set():
+                    self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    try:
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, n in names.items():
+                        if r & bit and bit & (bit - 1) == 0:
+                            self.reasons.add(n)
+                time.sleep(0.02)
+        except Exception as e:  # no NVML: report it instead of failing the bench
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        s = sorted(self.samples)
+        reasons = sorted(x for x in self.reasons if x.lower() not in ("gpuidle", "none", "applicationsclockssetting"))
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "samples": len(s), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference
+def cpu_reference(n_threads, blocks, steps, warmup):
+    """The reference's own brutefir::run (oracle/_ref = unmodified sources; else the port) on the host
+    cores: one engine instance (= one 7.1 stream, single-threaded like the reference) per thread."""
+    import oracle
+    kind = oracle.best_kind()
+    C, L, P, rs, fmt, rate = CFG["channels"], CFG["L"], CFG["P"], CFG["realsize"], CFG["fmt"], CFG["rate"]
+    engines, inputs = [], []
+    for t in range(n_threads):
+        e = oracle.Engine(L, P, rs, C, fmt, fmt, rate, False, kind=kind)
+        assert e.set_coeff(make_filters(C, L * P, first=t * C), P) == 0
+        engines.append(e)
+        inputs.append([np.ascontiguousarray(noise_block(100 * t + b, 1, L, C)[0]).view(np.uint8).ravel() for b in range(4)])
+    outs = [np.zeros(L * C * 8, dtype=np.uint8) for _ in range(n_threads)]
+
+    def work(t, n):
+        for b in range(n):
+            rc, _ = engines[t].run(inputs[t][b % 4], outs[t])
+            assert rc == 0
+
+    def parallel(n):
+        th = [threading.Thread(target=work, args=(t, n)) for t in range(n_threads)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t0
+
+    parallel(P)                      # prefill: all P partitions active (procblocks == P)
+    for _ in range(warmup):
+        parallel(blocks)
+    times = [parallel(blocks) for _ in range(steps)]
+    total = sum(times)
+    samples = n_threads * C * L * blocks * steps
+    return {
+        "value": samples / total / 1e6, "unit": "Msamples/s", "cores": n_threads,
+        "kind": "reference" if kind == "ref" else "port",
+        "sample": "%d thread(s) x 1 stream (8 ch) each, %d timed block(s) of 8192 frames per step x %d steps after a %d-block prefill; "
+                  "FFT provider: %s" % (n_threads, blocks, steps, P, oracle.lib(kind).fft_provider().decode()),
+        "ms_per_step": 1e3 * total / steps, "samples_per_step": n_threads * C * L * blocks,
+    }
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--streams", type=int, default=16, help="7.1 streams batched per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = max(args.gpus, world)
+    K, W, S = args.steps, max(args.warmup, 0), args.streams
+    C, L, P, rs, fmt, rate = CFG["channels"], CFG["L"], CFG["P"], CFG["realsize"], CFG["fmt"], CFG["rate"]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = host_cores()
+        r = cpu_reference(cores, blocks=2, steps=max(1, min(K, 8)), warmup=min(W, 1))
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Msamples/s", "n_gpus": n_gpus,
+            "steps": max(1, min(K, 8)), "warmup": min(W, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(S, n_gpus), samples_per_step=r["samples_per_step"],
+                           note="CPU reference: each step is a bounded sample (see cpu_baseline.sample); steps capped at 8"),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("foo-dsp-bfir_b200")
+    pkg.load_library()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    eng = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=S, device=local_rank)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)          # torch events / copies and the engine share one stream
+    eng.set_stream(stream.cuda_stream)
+    Ct = S * C
+    assert eng.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
+    ring = 4
+    host_in = [torch.from_numpy(noise_block(1000 * rank + b, S, L, C)).contiguous().pin_memory() for b in range(ring)]
+    dev_in = [h.cuda(non_blocking=True) for h in host_in]
+    dev_out = torch.empty(S * L * C, dtype=torch.float64, device="cuda")
+    host_out = torch.empty(S * L * C, dtype=torch.float64).pin_memory()
+    torch.cuda.synchronize()
+
+    # prefill the delay line so that every timed step convolves all P partitions, then W warm-up steps
+    for b in range(P + W):
+        eng.run_device(dev_in[b % ring], dev_out)
+    assert eng.sync() == 0
+
+    # ---- device-resident throughput: EXACTLY K steps between barrier+sync, CUDA events on the launch stream
+    eng.set_profiling(K)
+    launches0 = pkg.kernel_launch_count()
+    barrier()
+    sampler.busy.set()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for b in range(K):
+        eng.run_device(dev_in[b % ring], dev_out)
+    ev1.record(stream)
+    assert eng.sync() == 0
+    barrier()
+    sampler.busy.clear()
+    launches = pkg.kernel_launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    prof, nprof = eng.get_profile()
+    value = n_gpus * Ct * L * K / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through bfir_run: pinned host in -> H2D -> kernels -> D2H -> pinned host out, per step
+    e2e_steps = K
+    np_in, np_out = [h.numpy() for h in host_in], host_out.numpy()
+    for b in range(min(W, 3)):
+        rc, _ = eng.run(np_in[b % ring], np_out)
+        assert rc == 0
+    barrier()
+    sampler.busy.set()
+    t0 = time.perf_counter()
+    for b in range(e2e_steps):
+        rc, _ = eng.run(np_in[b % ring], np_out)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    sampler.busy.clear()
+    assert rc == 0
+    t_e2e = max_over_ranks(t_e2e)
+    e2e_value = n_gpus * Ct * L * e2e_steps / t_e2e / 1e6
+    checksum = float(host_out.numpy()[:1024].sum())
+
+    # ---- roofline of the dominant kernel (partition MAC)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    b_mac = (2 * P + 1) * (2 * L) * rs * Ct            # algorithmic bytes per launch
+    mac_ms = prof["mac_ms"] / max(nprof, 1)
+    achieved = b_mac / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "partition_mac_kernel<double,4>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_mac, "avg_launch_ms": mac_ms,
+                "step_share": {k: v / max(nprof, 1) for k, v in prof.items()}}
+
+    # ---- single-stream block latency (p50/p99 of host-visible bfir_run), rank 0
+    latency = None
+    if rank == 0 and not args.no_latency:
+        e1 = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=1, device=local_rank)
+        assert e1.set_coeff(make_filters(C, L * P), P) == 0
+        hin = [np.ascontiguousarray(h.numpy()[0]) for h in host_in]
+        pin = [torch.from_numpy(x).pin_memory() for x in hin]
+        pout = torch.empty(L * C, dtype=torch.float64).pin_memory()
+        for b in range(P + 20):
+            e1.run(pin[b % ring].numpy(), pout.numpy())
+        lat = []
+        for b in range(2000):
+            t0 = time.perf_counter()
+            e1.run(pin[b % ring].numpy(), pout.numpy())
+            lat.append(time.perf_counter() - t0)
+        lat = np.sort(np.array(lat)) * 1e3
+        latency = {"streams": 1, "calls": len(lat), "p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]),
+                   "block_period_ms": 1e3 * L / rate}
+        e1.close()
+
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        r = cpu_reference(host_cores(), blocks=2, steps=3, warmup=0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(S, n_gpus),
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * L * C * 8,
+                    "d2h_bytes_per_step": S * L * C * 8, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
+                    "api": "bfir_run(host in, host out): pinned H2D + 3 kernels + D2H + sync per step", "checksum": checksum},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -73,6 +73,8 @@ API = [
     ("bfir_run_finish_device", _ci, [_vp, _vp]),
     ("bfir_acc_device_ptr", _vp, [_vp, ctypes.POINTER(_sz)]),
     ("bfir_set_stream", _ci, [_vp, _vp]),
+    ("bfir_set_profiling", _ci, [_vp, _ci]),
+    ("bfir_get_profile", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(ctypes.c_ulonglong), _ci]),
     ("bfir_set_print_callback", None, [PRINT_CB]),
     ("bfir_last_error", ctypes.c_char_p, []),
     ("bfir_kernel_launch_count", ctypes.c_ulonglong, []),
@@ -254,6 +256,16 @@ class Brutefir:
 
     def reset(self):
         _check(self.lib.bfir_reset(self.h))
+
+    def set_profiling(self, max_blocks):
+        _check(self.lib.bfir_set_profiling(self.h, int(max_blocks)))
+
+    def get_profile(self, reset=True):
+        """-> ({'fwd_ms','mac_ms','inv_ms'} summed over `blocks` profiled block steps, blocks)"""
+        ms = (ctypes.c_double * 3)()
+        n = ctypes.c_ulonglong()
+        _check(self.lib.bfir_get_profile(self.h, ms, ctypes.byref(n), int(reset)))
+        return {"fwd_ms": ms[0], "mac_ms": ms[1], "inv_ms": ms[2]}, int(n.value)
 
     def check_overflows(self):
         return _check(self.lib.bfir_check_overflows(self.h))

@@ -33,6 +33,14 @@ struct Engine {
     DitherTables dither;
     double ovf_max = 1.0;
     unsigned long long blocks_since_sync = 0;
+    // optional per-kernel timing (bfir_set_profiling)
+    std::vector<cudaEvent_t> pev;
+    size_t pcap = 0, pidx = 0;
+    double pms[3] = {0, 0, 0};
+    unsigned long long pblocks = 0;
+    void prof(int k) { if (pidx < pcap) cudaEventRecord(pev[4 * pidx + k], stream); }
+    void prof_collect();
+    void prof_free() { for (auto ev : pev) cudaEventDestroy(ev); pev.clear(); pcap = pidx = 0; }
 
     ~Engine() { destroy(); }
     int init(const bfir_config_t &c);
@@ -110,8 +118,22 @@ int Engine::init(const bfir_config_t &c)
     return BFIR_OK;
 }
 
+void Engine::prof_collect()
+{
+    for (size_t i = 0; i < pidx; i++) {
+        for (int k = 0; k < 3; k++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, pev[4 * i + k], pev[4 * i + k + 1]) == cudaSuccess) pms[k] += ms;
+        }
+        pblocks++;
+    }
+    if (pidx > 0) { pcap -= pidx; pev.erase(pev.begin(), pev.begin() + 4 * pidx); }
+    pidx = 0;
+}
+
 void Engine::destroy()
 {
+    prof_free();
     if (stream && own_stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     stream = nullptr;
     void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats };
@@ -196,7 +218,9 @@ int Engine::enqueue_front(const void *d_inbuf)
     f.scale_in = 1.0; f.scale_out = in_sf.scale;                       // brutefir.cpp:273-277
     f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = C;
     f.state = state; f.n_slots = P; f.procblocks = procblocks; f.pb_inc = pb_inc;
+    prof(0);
     cudaError_t e = launch_rfft_forward(rs, log2m, dim3(Ct, 1), stream, f, tw, 1, 0);
+    prof(1);
     count_launch();
     if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
 
@@ -209,6 +233,7 @@ int Engine::enqueue_front(const void *d_inbuf)
     dim3 grid((groups + threads - 1) / threads, Ct);
     if (rs == 4) partition_mac_kernel<float, 4><<<grid, threads, 0, stream>>>(m);
     else partition_mac_kernel<double, 4><<<grid, threads, 0, stream>>>(m);
+    prof(2);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     return BFIR_OK;
@@ -238,6 +263,8 @@ int Engine::enqueue_back(void *d_outbuf)
         count_launch();
         BFIR_CUDA(cudaGetLastError());
     }
+    prof(3);
+    if (pidx < pcap) pidx++;
     blocks_since_sync++;
     return BFIR_OK;
 }
@@ -247,6 +274,7 @@ int Engine::sync_and_probe()
 {
     BFIR_CUDA(cudaMemcpyAsync(h_state, state, sizeof(EngineState), cudaMemcpyDeviceToHost, stream));
     BFIR_CUDA(cudaStreamSynchronize(stream));
+    prof_collect();
     const unsigned long long n = blocks_since_sync;
     blocks_since_sync = 0;
     if (h_state->first_bad_channel != 0x7fffffff) {
@@ -457,6 +485,28 @@ int bfir_set_stream(bfir_engine *e, void *cuda_stream)
     if (g.stream && g.own_stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
     g.stream = (cudaStream_t)cuda_stream;
     g.own_stream = false;
+    return BFIR_OK;
+}
+
+int bfir_set_profiling(bfir_engine *e, int max_blocks)
+{
+    if (e == nullptr || max_blocks < 0) return BFIR_ERR_INVALID;
+    Engine &g = e->impl;
+    BFIR_CUDA(cudaStreamSynchronize(g.stream));
+    g.prof_free();
+    g.pev.resize((size_t)max_blocks * 4);
+    for (auto &ev : g.pev) BFIR_CUDA(cudaEventCreate(&ev));
+    g.pcap = (size_t)max_blocks;
+    return BFIR_OK;
+}
+
+int bfir_get_profile(bfir_engine *e, double ms_out[3], unsigned long long *blocks, int reset)
+{
+    if (e == nullptr || ms_out == nullptr || blocks == nullptr) return BFIR_ERR_INVALID;
+    Engine &g = e->impl;
+    for (int k = 0; k < 3; k++) ms_out[k] = g.pms[k];
+    *blocks = g.pblocks;
+    if (reset) { g.pms[0] = g.pms[1] = g.pms[2] = 0.0; g.pblocks = 0; }
     return BFIR_OK;
 }
 

@@ -272,18 +272,19 @@ BFIR_HD void inv_store(int t, int bx, const cpx<T> (&v)[16], const InvArgs &a, O
 __device__ __forceinline__ void overflow_commit(OverflowStats *dst, OverflowAcc acc)
 {
     unsigned long long lb = (unsigned long long)__double_as_longlong(acc.largest);
+    if (blockDim.x >= 32) { // whole warps only (blocks below 32 threads exist for L < 512)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc.n_overflows += __shfl_xor_sync(0xffffffffu, acc.n_overflows, o);
-        acc.intlargest = max(acc.intlargest, __shfl_xor_sync(0xffffffffu, acc.intlargest, o));
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, lb, o);
-        lb = lb > other ? lb : other;
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.n_overflows += __shfl_xor_sync(0xffffffffu, acc.n_overflows, o);
+            acc.intlargest = max(acc.intlargest, __shfl_xor_sync(0xffffffffu, acc.intlargest, o));
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, lb, o);
+            lb = lb > other ? lb : other;
+        }
+        if ((threadIdx.x & 31) != 0) return;
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (acc.n_overflows) atomicAdd(&dst->n_overflows, acc.n_overflows);
-        if (acc.intlargest > 0) atomicMax(&dst->intlargest, acc.intlargest);
-        if (lb) atomicMax(&dst->largest_bits, lb);
-    }
+    if (acc.n_overflows) atomicAdd(&dst->n_overflows, acc.n_overflows);
+    if (acc.intlargest > 0) atomicMax(&dst->intlargest, acc.intlargest);
+    if (lb) atomicMax(&dst->largest_bits, lb);
 }
 
 template <class T, int LOG2M>
@@ -312,10 +313,7 @@ __global__ void __launch_bounds__((1 << LOG2M) / 16) rfft_inverse_kernel(const I
     OverflowAcc acc;
     acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
     inv_store<T, LOG2M>(t, bx, v, a, acc);
-    if (a.out_mode == OUT_RAW && a.stats != NULL) {
-        // seed the running maxima with the channel's current values so "x > largest" keeps its meaning
-        overflow_commit(&a.stats[bx], acc);
-    }
+    if (a.out_mode == OUT_RAW && a.stats != NULL) overflow_commit(&a.stats[bx], acc);
     if (a.state != NULL && bx == 0 && t == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
 }
 #endif

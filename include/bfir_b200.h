@@ -137,6 +137,13 @@ void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
 /* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the engine's own. */
 int bfir_set_stream(bfir_engine *e, void *cuda_stream);
 
+/* Per-kernel timing with CUDA events on the engine's stream (measurement only): after
+ * bfir_set_profiling(e, n) the next n block steps are bracketed by events; bfir_get_profile returns
+ * the accumulated milliseconds of {input FFT, partition MAC, output stage} and the number of blocks,
+ * as of the last bfir_sync / bfir_run, optionally clearing the sums. */
+int bfir_set_profiling(bfir_engine *e, int max_blocks);
+int bfir_get_profile(bfir_engine *e, double ms_out[3], unsigned long long *blocks, int reset);
+
 /* pinfo / set_print_callback (brutefir/pinfo.h:17-18) */
 void bfir_set_print_callback(void (*cb)(const char *message));
 /* last error text of the calling thread */

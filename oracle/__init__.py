@@ -54,6 +54,10 @@ def best_kind():
 _libs = {}
 
 
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
 def lib(kind):
     if kind in _libs:
         return _libs[kind]
@@ -110,11 +114,16 @@ def lib(kind):
                               ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(cd), vp, ci)
     ns.fft_provider = sig("fft_provider", ctypes.c_char_p)
     _libs[kind] = ns
+    if kind == "ref":
+        # Reference quirk (fftw_convolver.cpp:543-549): convolver_runtime_coeffs2cbuf keeps a
+        # function-static scratch sized by its FIRST caller and shared by every later instance, so a
+        # larger convolver overruns it. Prime it once with the largest cbuf any caller here uses.
+        h = ns.conv_new(65536, 8, 1, 44100)
+        src = np.zeros(65536, dtype=np.float64)
+        dst = np.zeros(131072, dtype=np.float64)
+        ns.conv_runtime_coeffs2cbuf(h, _ptr(src), _ptr(dst))
+        ns.conv_delete(h)
     return ns
-
-
-def _ptr(a):
-    return a.ctypes.data_as(ctypes.c_void_p)
 
 
 def real_dtype(realsize):

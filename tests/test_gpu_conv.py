@@ -210,7 +210,12 @@ def test_cbuf2raw_no_dither_bit_exact(pkg, oracle, rs, fmt):
     y = (rng.uniform(-1.2, 1.2, 2 * L) * full).astype(g.dtype)
     # quantiser truth table around 0 / +-0.5 / integers / limits (property 6)
     if not isfloat:
-        y[:12] = np.array([0.0, -0.0, 0.49, 0.5, -0.49, -0.5, -0.51, 3.0, -3.0, full - 1, -full, -full + 0.4], dtype=g.dtype)
+        # (for 32-bit output from a float engine full-1 is not representable: (float)(2^31-1) = 2^31 and
+        #  (int32_t)2^31 is undefined behaviour in the reference, dither.cpp:252-264 -- use 2^31-128 there)
+        top = full - 128 if (nbytes == 4 and rs == 4) else full - 1
+        y[:12] = np.array([0.0, -0.0, 0.49, 0.5, -0.49, -0.5, -0.51, 3.0, -3.0, top, -full, -full + 0.4], dtype=g.dtype)
+        if nbytes == 4 and rs == 4:
+            y[np.abs(y.astype(np.float64) + 0.5 - 2.0 ** 31) < 1] = 1.0
     cb = g.cbuf(y)
     draw = g.rawbuf(nbytes=L * C * nbytes)
     for ch in range(C):
