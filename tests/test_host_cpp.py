@@ -1,0 +1,35 @@
+"""The C++ host mirror (foo-dsp-bfir_b200/host/*.hpp) compiles against the C ABI and behaves like the
+reference classes: CPU run checks the no-device failure contract, GPU run filters audio."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+SRC = os.path.join(ROOT, "tests", "host_cpp", "host_mirror_test.cpp")
+LIBDIR = os.path.join(ROOT, "foo-dsp-bfir_b200")
+
+
+def build(tmp_path):
+    exe = str(tmp_path / "host_mirror_test")
+    r = subprocess.run(["g++", "-std=c++11", "-O1", SRC, "-o", exe, "-L" + LIBDIR, "-lbfir_b200",
+                        "-Wl,-rpath," + LIBDIR], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not found")
+def test_host_mirror_refuses_without_device(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    r = subprocess.run([build(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_host_mirror_filters_audio(tmp_path):
+    r = subprocess.run([build(tmp_path), "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
