@@ -33,6 +33,7 @@ struct Engine {
     DitherTables dither;
     double ovf_max = 1.0;
     unsigned long long blocks_since_sync = 0;
+    int mac_split = 1;              // partition slices per CTA of the MAC kernel (choose_mac_split)
     // optional per-kernel timing (bfir_set_profiling)
     std::vector<cudaEvent_t> pev;
     size_t pcap = 0, pidx = 0;
@@ -110,6 +111,17 @@ int Engine::init(const bfir_config_t &c)
         // max_dither_table_size is 0 (memset bfconf, brutefir.cpp:31-32; passed at :712)
         rc = dither.init(Ct, c.sampling_rate, rs, 0, L);
         if (rc != BFIR_OK) return rc;
+    }
+    // MAC decomposition: enough CTAs for >= ~8 waves of 148 SMs x 3 resident CTAs, never more slices
+    // than partitions; BFIR_MAC_SPLIT overrides (measurement only)
+    {
+        const long long group_threads = (long long)Ct * (N / 8);
+        mac_split = 1;
+        while (mac_split < 16 && mac_split * 2 <= P && group_threads * mac_split / 256 < 8LL * 148 * 3) mac_split *= 2;
+        if (const char *env = getenv("BFIR_MAC_SPLIT")) {
+            const int v = atoi(env);
+            if ((v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) && v <= P) mac_split = v;
+        }
     }
     last_overflow.assign(Ct, bfir_overflow_t{0, 0, 0.0, ovf_max});
     rc = reset();
@@ -229,10 +241,9 @@ int Engine::enqueue_front(const void *d_inbuf)
     m.fdl_stride_ch = (long long)P * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = P; m.part_begin = part_begin; m.part_count = part_count;
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state; m.block_offset = 0;
-    const int groups = N / 8, threads = groups < 256 ? groups : 256;
-    dim3 grid((groups + threads - 1) / threads, Ct);
-    if (rs == 4) partition_mac_kernel<float, 4><<<grid, threads, 0, stream>>>(m);
-    else partition_mac_kernel<double, 4><<<grid, threads, 0, stream>>>(m);
+    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), Ct);
+    mac_kernel_t mk = rs == 4 ? mac_kernel_for_split<float>(mac_split) : mac_kernel_for_split<double>(mac_split);
+    mk<<<grid, 256, 0, stream>>>(m);
     prof(2);
     count_launch();
     BFIR_CUDA(cudaGetLastError());

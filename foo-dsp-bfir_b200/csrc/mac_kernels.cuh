@@ -68,15 +68,22 @@ __device__ __forceinline__ void mac8(T (&acc)[8], const T (&b)[8], const T (&c)[
     }
 }
 
-// grid: (ceil(N/8 / blockDim.x), channels). One thread = one ORD group (4 complex bins) of one channel.
-template <class T, int UNROLL>
+// grid: (ceil(N/8 / GPC), channels), 256 threads. The CTA covers GPC = 256/SPLIT consecutive ORD groups
+// (4 complex bins each); its threads form SPLIT slices, slice s accumulating partitions i = s (mod SPLIT)
+// of its group in registers, UNROLL partitions in flight at a time. The slices are then summed through
+// shared memory in slice order (deterministic). SPLIT trades per-thread work for CTA count: SPLIT 1 is
+// one thread per group over all partitions; larger SPLIT gives few-channel configurations enough CTAs
+// to fill 148 SMs and shortens the tail wave of large ones.
+template <class T, int SPLIT, int UNROLL>
 __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
 {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int GPC = 256 / SPLIT;
+    const int slice = threadIdx.x / GPC, gl = threadIdx.x - slice * GPC;
+    const int g = blockIdx.x * GPC + gl;
     const int ch = blockIdx.y;
-    if (g * 8 >= a.N) return;
+    const bool active = g * 8 < a.N;
     const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
-    int peff = min(a.coeff_blocks[ch], a.procblocks[ch]);           // brutefir.cpp:292
+    const int peff = min(a.coeff_blocks[ch], a.procblocks[ch]);           // brutefir.cpp:292
     const int i_end = min(peff, a.part_begin + a.part_count);
     const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
     const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
@@ -87,31 +94,59 @@ __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
     for (int j = 0; j < 8; j++) acc[j] = (T)0;
     T dc = (T)0, ny = (T)0;
 
-    int i = a.part_begin;
-    for (; i + UNROLL <= i_end; i += UNROLL) {
-        T b[UNROLL][8], c[UNROLL][8];
+    if (active) {
+        int i = a.part_begin + slice;
+        for (; i + (UNROLL - 1) * SPLIT < i_end; i += UNROLL * SPLIT) {
+            T b[UNROLL][8], c[UNROLL][8];
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const unsigned int slot = (t - (unsigned int)(i + u)) % P; // brutefir.cpp:294
-            ld8(fdl + (long long)slot * a.N, b[u]);
-            ld8(cf + (long long)(i + u) * a.N, c[u]);
-        }
+            for (int u = 0; u < UNROLL; u++) {
+                const unsigned int slot = (t - (unsigned int)(i + u * SPLIT)) % P; // brutefir.cpp:294
+                ld8(fdl + (long long)slot * a.N, b[u]);
+                ld8(cf + (long long)(i + u * SPLIT) * a.N, c[u]);
+            }
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            if (g == 0) { dc = fma(b[u][0], c[u][0], dc); ny = fma(b[u][4], c[u][4], ny); }
-            mac8<T>(acc, b[u], c[u]);
+            for (int u = 0; u < UNROLL; u++) {
+                if (g == 0) { dc = fma(b[u][0], c[u][0], dc); ny = fma(b[u][4], c[u][4], ny); }
+                mac8<T>(acc, b[u], c[u]);
+            }
         }
+        for (; i < i_end; i += SPLIT) {
+            T b[8], c[8];
+            const unsigned int slot = (t - (unsigned int)i) % P;
+            ld8(fdl + (long long)slot * a.N, b);
+            ld8(cf + (long long)i * a.N, c);
+            if (g == 0) { dc = fma(b[0], c[0], dc); ny = fma(b[4], c[4], ny); }
+            mac8<T>(acc, b, c);
+        }
+        if (g == 0) { acc[0] = dc; acc[4] = ny; }
     }
-    for (; i < i_end; i++) {
-        T b[8], c[8];
-        const unsigned int slot = (t - (unsigned int)i) % P;
-        ld8(fdl + (long long)slot * a.N, b);
-        ld8(cf + (long long)i * a.N, c);
-        if (g == 0) { dc = fma(b[0], c[0], dc); ny = fma(b[4], c[4], ny); }
-        mac8<T>(acc, b, c);
+    if (SPLIT > 1) {
+        __shared__ T red[SPLIT > 1 ? (SPLIT - 1) * GPC * 8 : 1];
+        if (slice > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) red[((slice - 1) * 8 + j) * GPC + gl] = acc[j];
+        }
+        __syncthreads();
+        if (slice > 0) return;
+#pragma unroll
+        for (int s = 1; s < SPLIT; s++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += red[((s - 1) * 8 + j) * GPC + gl];
     }
-    if (g == 0) { acc[0] = dc; acc[4] = ny; }
-    st8((T *)a.acc + (long long)ch * a.N + (long long)g * 8, acc);
+    if (active) st8((T *)a.acc + (long long)ch * a.N + (long long)g * 8, acc);
+}
+
+typedef void (*mac_kernel_t)(const MacArgs);
+template <class T> inline mac_kernel_t mac_kernel_for_split(int split)
+{
+    switch (split) {
+    case 1: return partition_mac_kernel<T, 1, 4>;
+    case 2: return partition_mac_kernel<T, 2, 4>;
+    case 4: return partition_mac_kernel<T, 4, 4>;
+    case 8: return partition_mac_kernel<T, 8, 4>;
+    case 16: return partition_mac_kernel<T, 16, 2>;
+    default: return partition_mac_kernel<T, 32, 1>;
+    }
 }
 #endif
 

@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Per-kernel CUDA-event times of the engine's block step for an arbitrary configuration (tuning aid).
+
+    python tools/kernel_times.py --channels 8 --realsize 8 --L 8192 --P 32 --streams 16 [--steps 200]
+Prints one JSON line: ms per step for {fwd, mac, inv}, MAC GB/s against B_mac, Msamples/s.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--channels", type=int, default=8)
+    ap.add_argument("--realsize", type=int, default=8)
+    ap.add_argument("--L", type=int, default=8192)
+    ap.add_argument("--P", type=int, default=32)
+    ap.add_argument("--streams", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--tag", default="")
+    a = ap.parse_args()
+    import torch
+    pkg = importlib.import_module("foo-dsp-bfir_b200")
+    fmt = pkg.FLOAT_LE if a.realsize == 4 else pkg.FLOAT64_LE
+    dt = torch.float32 if a.realsize == 4 else torch.float64
+    eng = pkg.Brutefir(a.L, a.P, a.realsize, a.channels, fmt, fmt, 48000, False, n_streams=a.streams)
+    Ct = a.streams * a.channels
+    rng = np.random.default_rng(0)
+    taps = a.L * a.P
+    env = np.exp(-6.9 * np.arange(taps) / taps)
+    base = rng.standard_normal(taps) * env
+    base /= np.sqrt(np.sum(base * base))
+    # distinct filters per channel without generating Ct x taps random numbers
+    hs = [np.roll(base, c % 97) * (1.0 + 0.001 * (c % 13)) for c in range(Ct)]
+    assert eng.set_coeff(hs, a.P) == 0
+    d_in = [torch.rand(a.streams * a.L * a.channels, dtype=dt, device="cuda") * 2 - 1 for _ in range(4)]
+    d_out = torch.empty(a.streams * a.L * a.channels, dtype=dt, device="cuda")
+    torch.cuda.synchronize()
+    for b in range(a.P + 5):
+        eng.run_device(d_in[b % 4], d_out)
+    assert eng.sync() == 0
+    eng.set_profiling(a.steps)
+    for b in range(a.steps):
+        eng.run_device(d_in[b % 4], d_out)
+    assert eng.sync() == 0
+    prof, n = eng.get_profile()
+    ms = {k: v / n for k, v in prof.items()}
+    step = sum(ms.values())
+    b_mac = (2 * a.P + 1) * 2 * a.L * a.realsize * Ct
+    print(json.dumps({"tag": a.tag, "split_env": os.environ.get("BFIR_MAC_SPLIT"), "cfg": vars(a), "ms": ms,
+                      "step_ms": step, "mac_GBs": b_mac / (ms["mac_ms"] * 1e-3) / 1e9,
+                      "mac_frac_of_6545": b_mac / (ms["mac_ms"] * 1e-3) / 1e9 / 6545.3,
+                      "Msamples_s": Ct * a.L / (step * 1e-3) / 1e6}))
+
+
+if __name__ == "__main__":
+    main()
