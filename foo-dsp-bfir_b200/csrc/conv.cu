@@ -6,10 +6,11 @@
 namespace bfir {
 
 struct Conv {
-    int L = 0, N = 0, rs = 0, log2m = 0, device = 0, n_dither = 0;
+    int L = 0, N = 0, rs = 0, log2m = 0, device = 0, n_dither = 0, fft_r0 = 1;
     cudaStream_t stream = nullptr;
     void *tw = nullptr;
-    void *scratch = nullptr;       // one cbuf (runtime_coeffs2cbuf / coeffs2cbuf staging), per instance
+    void *scratch = nullptr;       // one cbuf: in-place staging for two-CTA transforms, per instance
+    void *stage = nullptr;         // half a cbuf: host coefficients on their way into coeffs2cbuf
     OverflowStats *d_stats = nullptr;
     int *d_flag = nullptr;
     DitherTables dither;
@@ -17,8 +18,42 @@ struct Conv {
     ~Conv() { destroy(); }
     int init(int length, int realsize, int n_dither_channels, int sampling_rate);
     void destroy();
-    int fwd(const FwdArgs &a) { cudaError_t e = launch_rfft_forward(rs, log2m, dim3(1, 1), stream, a, tw, 1, 0); count_launch(); if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; } return BFIR_OK; }
-    int inv(const InvArgs &a) { cudaError_t e = launch_rfft_inverse(rs, log2m, dim3(1, 1), stream, a, tw, 1, 0); count_launch(); if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; } return BFIR_OK; }
+    // With two CTAs per transform an in-place call would let one CTA overwrite what the other still
+    // has to read: use one CTA when the size allows, else go through the per-instance scratch cbuf.
+    bool overlaps(const void *in, const void *out) const
+    {
+        const char *a = (const char *)in, *b = (const char *)out;
+        const size_t n = (size_t)N * rs;
+        return a < b + n && b < a + n;
+    }
+    int fwd(FwdArgs a)
+    {
+        int r0 = fft_r0;
+        void *final_out = nullptr;
+        if (r0 == 2 && overlaps(a.in, a.out)) {
+            if (rfft_choose_r0(rs, log2m, 1LL << 40) == 1) r0 = 1;
+            else { final_out = a.out; a.out = scratch; }
+        }
+        cudaError_t e = launch_rfft_forward(rs, log2m, r0, dim3(1, 1), stream, a, tw);
+        count_launch();
+        if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+        if (final_out) BFIR_CUDA(cudaMemcpyAsync(final_out, scratch, (size_t)N * rs, cudaMemcpyDeviceToDevice, stream));
+        return BFIR_OK;
+    }
+    int inv(InvArgs a)
+    {
+        int r0 = fft_r0;
+        void *final_out = nullptr;
+        if (r0 == 2 && overlaps(a.in, a.out)) {
+            if (rfft_choose_r0(rs, log2m, 1LL << 40) == 1) r0 = 1;
+            else { final_out = a.out; a.out = scratch; }
+        }
+        cudaError_t e = launch_rfft_inverse(rs, log2m, r0, dim3(1, 1), stream, a, tw);
+        count_launch();
+        if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+        if (final_out) BFIR_CUDA(cudaMemcpyAsync(final_out, scratch, (size_t)N * rs, cudaMemcpyDeviceToDevice, stream));
+        return BFIR_OK;
+    }
 };
 
 int Conv::init(int length, int realsize, int n_dither_channels, int sampling_rate)
@@ -28,11 +63,13 @@ int Conv::init(int length, int realsize, int n_dither_channels, int sampling_rat
     log2m = ilog2_exact(L);
     if (log2m < 0) { set_error("Invalid length %d.", L); return BFIR_ERR_INVALID; }
     if (!rfft_supported(rs, log2m)) { set_error("block length %d not supported for realsize %d", L, rs); return BFIR_ERR_INVALID; }
+    fft_r0 = rfft_choose_r0(rs, log2m, 1);
     BFIR_CUDA(cudaGetDevice(&device));
     BFIR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = make_twiddles(rs, N, &tw);
     if (rc != BFIR_OK) return rc;
     BFIR_CUDA(cudaMalloc(&scratch, (size_t)N * rs));
+    BFIR_CUDA(cudaMalloc(&stage, (size_t)L * rs));
     BFIR_CUDA(cudaMalloc((void **)&d_stats, sizeof(OverflowStats)));
     BFIR_CUDA(cudaMalloc((void **)&d_flag, sizeof(int)));
     n_dither = n_dither_channels > 0 ? n_dither_channels : 1;
@@ -44,9 +81,10 @@ void Conv::destroy()
     if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); stream = nullptr; }
     if (tw) cudaFree(tw);
     if (scratch) cudaFree(scratch);
+    if (stage) cudaFree(stage);
     if (d_stats) cudaFree(d_stats);
     if (d_flag) cudaFree(d_flag);
-    tw = scratch = nullptr; d_stats = nullptr; d_flag = nullptr;
+    tw = scratch = stage = nullptr; d_stats = nullptr; d_flag = nullptr;
     dither.destroy();
 }
 
@@ -292,10 +330,10 @@ int bfir_conv_coeffs2cbuf(bfir_conv *c, const void *coeffs, int n_coeffs, double
     Conv &g = c->impl;
     if (coeffs == nullptr || d_dest == nullptr || n_coeffs < 0) return BFIR_ERR_INVALID;
     const int len = n_coeffs > g.L ? g.L : n_coeffs;                                 // fftw_convolver.cpp:483
-    if (len > 0) BFIR_CUDA(cudaMemcpyAsync(g.scratch, coeffs, (size_t)len * g.rs, cudaMemcpyHostToDevice, g.stream));
+    if (len > 0) BFIR_CUDA(cudaMemcpyAsync(g.stage, coeffs, (size_t)len * g.rs, cudaMemcpyHostToDevice, g.stream));
     BFIR_CUDA(cudaMemsetAsync(g.d_flag, 0, sizeof(int), g.stream));
     FwdArgs a = {};
-    a.in_mode = IN_COEFF; a.out_layout = LAYOUT_ORD; a.in = g.scratch; a.out = d_dest;
+    a.in_mode = IN_COEFF; a.out_layout = LAYOUT_ORD; a.in = g.stage; a.out = d_dest;
     a.scale_in = scale; a.scale_out = 1.0 / (double)g.N; a.coeff_len = len; a.nonfinite = g.d_flag;
     int rc = g.fwd(a);
     if (rc != BFIR_OK) return rc;

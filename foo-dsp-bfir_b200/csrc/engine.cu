@@ -33,7 +33,8 @@ struct Engine {
     DitherTables dither;
     double ovf_max = 1.0;
     unsigned long long blocks_since_sync = 0;
-    int mac_split = 1;              // partition slices per CTA of the MAC kernel (choose_mac_split)
+    int mac_split = 1;              // partition slices per CTA of the MAC kernel
+    int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
     // optional per-kernel timing (bfir_set_profiling)
     std::vector<cudaEvent_t> pev;
     size_t pcap = 0, pidx = 0;
@@ -89,8 +90,9 @@ int Engine::init(const bfir_config_t &c)
     BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * P * Ct, stream));                                      // brutefir.cpp:768-769
     BFIR_CUDA(cudaMalloc(&acc, cbuf * Ct));
     BFIR_CUDA(cudaMemsetAsync(acc, 0, cbuf * Ct, stream));
-    BFIR_CUDA(cudaMalloc(&prev, (size_t)L * rs * Ct));
-    BFIR_CUDA(cudaMemsetAsync(prev, 0, (size_t)L * rs * Ct, stream));
+    BFIR_CUDA(cudaMalloc(&prev, (size_t)2 * L * rs * Ct));                                          // input_timecbuf[n][2]
+    BFIR_CUDA(cudaMemsetAsync(prev, 0, (size_t)2 * L * rs * Ct, stream));
+    fft_r0 = rfft_choose_r0(rs, log2m, Ct);
     in_bytes = (size_t)S * L * C * in_sf.bytes;
     out_bytes = (size_t)S * L * C * out_sf.bytes;
     BFIR_CUDA(cudaMalloc(&d_in, in_bytes));
@@ -199,7 +201,7 @@ int Engine::set_coeff(const void *const *h_coeffs, int n_coeffs, int length, int
     a.out = coeffs; a.out_stride_x = (long long)blocks * N; a.out_stride_y = N;
     a.scale_in = scale; a.scale_out = 1.0 / (double)N;     // fftw_convolver.cpp:520
     a.coeff_len = length; a.nonfinite = nonfinite;
-    cudaError_t e = launch_rfft_forward(rs, log2m, dim3(n_coeffs, blocks), stream, a, tw, 1, 0);
+    cudaError_t e = launch_rfft_forward(rs, log2m, rfft_choose_r0(rs, log2m, (long long)n_coeffs * blocks), dim3(n_coeffs, blocks), stream, a, tw);
     count_launch();
     if (e != cudaSuccess) { cudaFree(d_planar); set_error("coefficient transform launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
     std::vector<int> hb(Ct, 0);
@@ -228,10 +230,10 @@ int Engine::enqueue_front(const void *d_inbuf)
     f.in = d_inbuf; f.in_stride_x = (long long)L * C * in_sf.bytes;   // bytes per stream
     f.out = fdl; f.out_stride_x = (long long)P * N; f.out_stride_y = N;
     f.scale_in = 1.0; f.scale_out = in_sf.scale;                       // brutefir.cpp:273-277
-    f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = C;
+    f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = C; f.n_channels = Ct;
     f.state = state; f.n_slots = P; f.procblocks = procblocks; f.pb_inc = pb_inc;
     prof(0);
-    cudaError_t e = launch_rfft_forward(rs, log2m, dim3(Ct, 1), stream, f, tw, 1, 0);
+    cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(Ct, 1), stream, f, tw);
     prof(1);
     count_launch();
     if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
@@ -259,7 +261,7 @@ int Engine::enqueue_back(void *d_outbuf)
     v.fmt = out_sf.format; v.ch_per_stream = C; v.ovf_max = ovf_max; v.stats = stats; v.state = state;
     if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }
     else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * C * out_sf.bytes; }
-    cudaError_t e = launch_rfft_inverse(rs, log2m, dim3(Ct, 1), stream, v, tw, 1, 0);
+    cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(Ct, 1), stream, v, tw);
     count_launch();
     if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
     if (dither_on) {

@@ -1,11 +1,12 @@
 // Dispatch table over the per-size FFT translation units (fft_inst.cu).
 #include "fft_dispatch.hpp"
+#include <cstdlib>
 
 namespace bfir {
 
 #define BFIR_DECL(tag, m)                                                                                      \
-    cudaError_t launch_fwd_##tag##_m##m(dim3, cudaStream_t, const FwdArgs &, const void *, int, int);          \
-    cudaError_t launch_inv_##tag##_m##m(dim3, cudaStream_t, const InvArgs &, const void *, int, int);
+    cudaError_t launch_fwd_##tag##_m##m(int, dim3, cudaStream_t, const FwdArgs &, const void *, int, int);     \
+    cudaError_t launch_inv_##tag##_m##m(int, dim3, cudaStream_t, const InvArgs &, const void *, int, int);
 #define BFIR_FOR_F32(X) X(f32, 4) X(f32, 5) X(f32, 6) X(f32, 7) X(f32, 8) X(f32, 9) X(f32, 10) X(f32, 11) X(f32, 12) X(f32, 13) X(f32, 14)
 #define BFIR_FOR_F64(X) X(f64, 4) X(f64, 5) X(f64, 6) X(f64, 7) X(f64, 8) X(f64, 9) X(f64, 10) X(f64, 11) X(f64, 12) X(f64, 13)
 BFIR_FOR_F32(BFIR_DECL)
@@ -20,31 +21,44 @@ static const inv_launcher_t kInvF32[] = { BFIR_FOR_F32(BFIR_INV_ENTRY) };
 static const fwd_launcher_t kFwdF64[] = { BFIR_FOR_F64(BFIR_FWD_ENTRY) };
 static const inv_launcher_t kInvF64[] = { BFIR_FOR_F64(BFIR_INV_ENTRY) };
 
+static int max_sub(int realsize) { return realsize == 4 ? kMaxLog2M_f32 : kMaxLog2M_f64; }
+
 bool rfft_supported(int realsize, int log2m)
 {
-    if (realsize == 4) return log2m >= kMinLog2M && log2m <= kMaxLog2M_f32;
-    if (realsize == 8) return log2m >= kMinLog2M && log2m <= kMaxLog2M_f64;
-    return false;
+    if (realsize != 4 && realsize != 8) return false;
+    return log2m >= kMinLog2M && log2m <= max_sub(realsize) + 1;
 }
 
-size_t rfft_smem_bytes(int realsize, int log2m)
+int rfft_choose_r0(int realsize, int log2m, long long n_buffers)
 {
-    const size_t m = (size_t)1 << log2m;
-    return (m + (m >> 4)) * 2 * (size_t)realsize;
+    if (log2m > max_sub(realsize)) return 2;
+    if (log2m - 1 < kMinLog2M) return 1;
+    if (const char *env = getenv("BFIR_FFT_R0")) {
+        const int v = atoi(env);
+        if (v == 1 || v == 2) return v;
+    }
+    // big transforms leave one CTA per SM (registers / shared memory): two half-size CTAs per buffer
+    // halve the latency as long as the grid still fits the machine in about one wave
+    const int big = realsize == 4 ? 13 : 12;
+    if (log2m >= big && n_buffers <= 2 * 148) return 2;
+    return 1;
 }
 
-cudaError_t launch_rfft_forward(int realsize, int log2m, dim3 grid, cudaStream_t stream, const FwdArgs &a,
-                                const void *tw, int sm, int sn)
+cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw)
 {
-    if (!rfft_supported(realsize, log2m)) return cudaErrorInvalidValue;
-    return (realsize == 4 ? kFwdF32 : kFwdF64)[log2m - kMinLog2M](grid, stream, a, tw, sm, sn);
+    if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
+    const int sub = log2m - (r0 == 2 ? 1 : 0);
+    if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
+    // table length N = 2 * 2^log2m: shift for the sub-transform twiddles, 0 for the W_N^k of the split step
+    return (realsize == 4 ? kFwdF32 : kFwdF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }
 
-cudaError_t launch_rfft_inverse(int realsize, int log2m, dim3 grid, cudaStream_t stream, const InvArgs &a,
-                                const void *tw, int sm, int sn)
+cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw)
 {
-    if (!rfft_supported(realsize, log2m)) return cudaErrorInvalidValue;
-    return (realsize == 4 ? kInvF32 : kInvF64)[log2m - kMinLog2M](grid, stream, a, tw, sm, sn);
+    if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
+    const int sub = log2m - (r0 == 2 ? 1 : 0);
+    if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
+    return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }
 
 } // namespace bfir

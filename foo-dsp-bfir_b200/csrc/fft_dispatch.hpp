@@ -6,18 +6,19 @@
 
 namespace bfir {
 
-// block length L = M = 2^log2m. Supported: 16 <= L <= 16384 (float), 16 <= L <= 8192 (double):
-// the CTA-resident transform needs M complex values (+1/16 padding) in shared memory (<= 227 KB).
+// block length L = M = 2^log2m. One transform is computed by r0 = 1 or 2 CTAs (rfft_kernels.cuh); each
+// CTA holds M/r0 complex values (+1/16 padding) in shared memory (<= 227 KB), which bounds the
+// per-CTA size at 2^14 (float) / 2^13 (double). Supported: 16 <= L <= 32768 (float), 16 <= L <= 16384 (double).
 bool rfft_supported(int realsize, int log2m);
-size_t rfft_smem_bytes(int realsize, int log2m);
+// 1 or 2 CTAs per transform: 2 when the size needs it, or when there are too few buffers to fill the GPU
+int rfft_choose_r0(int realsize, int log2m, long long n_buffers);
 
-// grid = (buffers/channels, partitions); block size and shared memory are implied by the size
-cudaError_t launch_rfft_forward(int realsize, int log2m, dim3 grid, cudaStream_t stream, const FwdArgs &a,
-                                const void *tw, int tw_shift_m, int tw_shift_n);
-cudaError_t launch_rfft_inverse(int realsize, int log2m, dim3 grid, cudaStream_t stream, const InvArgs &a,
-                                const void *tw, int tw_shift_m, int tw_shift_n);
+// grid = (buffers/channels, partitions); block size, grid.z and shared memory are implied by size and r0.
+// tw = table exp(-2 pi i j / N), N = 2 * 2^log2m.
+cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw);
+cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw);
 
-typedef cudaError_t (*fwd_launcher_t)(dim3, cudaStream_t, const FwdArgs &, const void *, int, int);
-typedef cudaError_t (*inv_launcher_t)(dim3, cudaStream_t, const InvArgs &, const void *, int, int);
+typedef cudaError_t (*fwd_launcher_t)(int, dim3, cudaStream_t, const FwdArgs &, const void *, int, int);
+typedef cudaError_t (*inv_launcher_t)(int, dim3, cudaStream_t, const InvArgs &, const void *, int, int);
 
 } // namespace bfir

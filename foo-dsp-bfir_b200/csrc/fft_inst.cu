@@ -12,30 +12,45 @@ static constexpr int kLog2M = BFIR_FFT_LOG2M;
 static constexpr int kM = 1 << kLog2M;
 static constexpr size_t kSmem = (size_t)fft_smem_elems<kM>::value * sizeof(cpx<real_t>);
 
-cudaError_t BFIR_CAT(launch_fwd_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw, int sm, int sn)
+template <int R0>
+static cudaError_t launch_fwd(dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw, int sm, int sn)
 {
     static bool configured = false;
-    auto kernel = rfft_forward_kernel<real_t, kLog2M>;
+    auto kernel = rfft_forward_kernel<real_t, kLog2M, R0>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    grid.z = R0;
     kernel<<<grid, kM / 16, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
     return cudaGetLastError();
 }
 
-cudaError_t BFIR_CAT(launch_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw, int sm, int sn)
+template <int R0>
+static cudaError_t launch_inv(dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw, int sm, int sn)
 {
     static bool configured = false;
-    auto kernel = rfft_inverse_kernel<real_t, kLog2M>;
+    auto kernel = rfft_inverse_kernel<real_t, kLog2M, R0>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    grid.z = R0;
     kernel<<<grid, kM / 16, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
     return cudaGetLastError();
+}
+
+// kLog2M is the per-CTA sub-transform size; r0 CTAs cooperate on one buffer of 2^kLog2M * r0 points
+cudaError_t BFIR_CAT(launch_fwd_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw, int sm, int sn)
+{
+    return r0 == 2 ? launch_fwd<2>(grid, stream, a, tw, sm, sn) : launch_fwd<1>(grid, stream, a, tw, sm, sn);
+}
+
+cudaError_t BFIR_CAT(launch_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int r0, dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw, int sm, int sn)
+{
+    return r0 == 2 ? launch_inv<2>(grid, stream, a, tw, sm, sn) : launch_inv<1>(grid, stream, a, tw, sm, sn);
 }
 
 } // namespace bfir

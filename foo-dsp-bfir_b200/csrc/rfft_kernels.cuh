@@ -47,8 +47,8 @@ struct FwdArgs {
     double scale_in;         // applied to the samples (coefficient scale)
     double scale_out;        // applied to the spectrum (input scale, or 1/N for coefficients)
     // IN_RAW_PREV
-    void *prev;              // [channels][L] previous block
-    int fmt, ch_per_stream;
+    void *prev;              // [2][n_channels][L] previous block, ping-pong by blockcounter parity
+    int fmt, ch_per_stream, n_channels;
     const EngineState *state; // out slot = blockcounter % n_slots when state != NULL
     int n_slots;
     int *procblocks;         // [channels], brutefir.cpp:265-268
@@ -92,68 +92,88 @@ template <class T> BFIR_HD cpx<T> spec_load(const T *s, int layout, int k, int M
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, phase 0: thread t loads z[n] = x[2n] + i x[2n+1] for n = t + i*NT
-template <class T, int LOG2M>
-BFIR_HD void fwd_load(int t, int bx, int by, cpx<T> (&v)[16], const FwdArgs &a)
+// CTA-level split of one transform (R0 = 1 or 2 CTAs per buffer, blockIdx.z = r):
+// a radix-R0 decimation-in-frequency pre-pass is folded into the load phase, after which CTA r owns an
+// independent Ms = M/R0 point transform:
+//     forward:  s_r[n] = W_M^(n r) * sum_j z[n + j Ms] W_R0^(j r)      ->  Z[R0 k + r] = FFT_Ms(s_r)[k]
+//     inverse:  s_r[k] = W_M^(-k r) * sum_j Z'[k + j Ms] W_R0^(-j r)   ->  z[R0 n + r] = IFFT_Ms(s_r)[n]
+// For R0 = 2 the real-FFT split partner of bin k = 2k'+r is M-k = 2(Ms-k')  (r = 0) or 2(Ms-1-k')+1
+// (r = 1): the same CTA, so no exchange between the two CTAs is ever needed. R0 = 2 doubles the
+// largest block length (L = 32768 float, 16384 double) and halves the per-CTA latency of big transforms.
+
+// element z[m] of the packed input, m in [0, M); UPPER tells at compile time that m >= M/2
+template <class T, int LOG2M, bool UPPER>
+BFIR_HD cpx<T> fwd_elem(int m, int bx, int by, int r, const FwdArgs &a, bool &bad)
 {
-    constexpr int M = 1 << LOG2M, NT = M / 16, L = M; // L = block length = N/2 = M
+    constexpr int M = 1 << LOG2M, L = M;
     typedef cpx<T> C;
     if (a.in_mode == IN_TIME) {
-        const C *in = (const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y);
-#pragma unroll
-        for (int i = 0; i < 16; i++) v[i] = in[t + i * NT];
+        return ((const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y))[m];
     } else if (a.in_mode == IN_UPPER) {
-        const C *in = (const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y);
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = mk<T>((T)0, (T)0);
-#pragma unroll
-        for (int i = 8; i < 16; i++) v[i] = in[t + (i - 8) * NT];
+        if (!UPPER) return mk<T>((T)0, (T)0);
+        return ((const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y))[m - M / 2];
     } else if (a.in_mode == IN_COEFF) {
+        if (!UPPER) return mk<T>((T)0, (T)0);
         const T *in = (const T *)a.in + bx * a.in_stride_x;
         const T sc = (T)a.scale_in;
-        bool bad = false;
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = mk<T>((T)0, (T)0);
-#pragma unroll
-        for (int i = 8; i < 16; i++) {
-            const int m = 2 * (t + (i - 8) * NT);            // sample index inside the partition
-            const long long g = (long long)by * L + m;      // index into the channel's coefficients
-            T c0 = (T)0, c1 = (T)0;
-            if (g < a.coeff_len) c0 = in[g] * sc;
-            if (g + 1 < a.coeff_len) c1 = in[g + 1] * sc;
-            bad = bad || !(c0 - c0 == (T)0) || !(c1 - c1 == (T)0); // NaN or Inf
-            v[i] = mk<T>(c0, c1);
-        }
-        if (bad) *a.nonfinite = 1;
-    } else { // IN_RAW_PREV
+        const long long g = (long long)by * L + 2 * (m - M / 2);   // index into the channel's coefficients
+        T c0 = (T)0, c1 = (T)0;
+        if (g < a.coeff_len) c0 = in[g] * sc;
+        if (g + 1 < a.coeff_len) c1 = in[g + 1] * sc;
+        bad = bad || !(c0 - c0 == (T)0) || !(c1 - c1 == (T)0);     // NaN or Inf
+        return mk<T>(c0, c1);
+    } else { // IN_RAW_PREV: [previous block | current block], previous kept in a ping-pong pair that
+             // follows the reference's input_timecbuf[n][curbuf] (brutefir.cpp:255-260, 337)
+        const unsigned int par = a.state->blockcounter & 1u;
+        if (!UPPER) return ((const C *)((const T *)a.prev + ((long long)par * a.n_channels + bx) * L))[m];
         const int stream = bx / a.ch_per_stream, ch = bx - stream * a.ch_per_stream;
         const int bytes = fmt_bytes(a.fmt);
-        const uint8_t *raw = (const uint8_t *)a.in + (long long)stream * a.in_stride_x + (long long)ch * bytes;
         const long long step = (long long)a.ch_per_stream * bytes;
-        C *prev = (C *)((T *)a.prev + (long long)bx * L);
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = prev[t + i * NT];
-#pragma unroll
-        for (int i = 8; i < 16; i++) {
-            const int n = t + (i - 8) * NT;                  // complex index inside the current block
-            const uint8_t *p = raw + (long long)(2 * n) * step;
-            v[i] = mk<T>(load_raw<T>(p, a.fmt), load_raw<T>(p + step, a.fmt));
-            prev[n] = v[i];                                  // same thread read prev[n] above: no hazard
-        }
-        if (t == 0 && a.procblocks != NULL) {                // brutefir.cpp:265-268
-            const int pb = a.procblocks[bx];
-            const bool inc = pb < a.n_slots;
-            if (inc) a.procblocks[bx] = pb + 1;
-            a.pb_inc[bx] = inc ? 1 : 0;
-        }
+        const int n = m - M / 2;                                   // complex index inside the current block
+        const uint8_t *p = (const uint8_t *)a.in + (long long)stream * a.in_stride_x + (long long)ch * bytes + (long long)(2 * n) * step;
+        const C z = mk<T>(load_raw<T>(p, a.fmt), load_raw<T>(p + step, a.fmt));
+        if (r == 0) ((C *)((T *)a.prev + ((long long)(par ^ 1u) * a.n_channels + bx) * L))[n] = z;
+        return z;
     }
 }
 
-// forward, phase 2: Z (natural order, padded smem) -> X_k, scaled, stored in ORD or HC layout
-template <class T, int LOG2M>
-BFIR_HD void fwd_split_store(int t, int bx, int by, const cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
+// forward, phase 0: thread t builds s_r[n], n = t + i*NTs
+template <class T, int LOG2MS, int R0>
+BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
 {
-    constexpr int M = 1 << LOG2M, NT = M / 16, N = 2 * M;
+    constexpr int MS = 1 << LOG2MS, NT = MS / 16, LOG2M = LOG2MS + (R0 == 2 ? 1 : 0);
+    typedef cpx<T> C;
+    bool bad = false;
+    if (R0 == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, bx, by, r, a, bad);
+#pragma unroll
+        for (int i = 8; i < 16; i++) v[i] = fwd_elem<T, LOG2M, true>(t + i * NT, bx, by, r, a, bad);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int n = t + i * NT;
+            const C lo = fwd_elem<T, LOG2M, false>(n, bx, by, r, a, bad);
+            const C hi = fwd_elem<T, LOG2M, true>(n + MS, bx, by, r, a, bad);
+            if (r == 0) v[i] = cadd(lo, hi);
+            else v[i] = cmul(csub(lo, hi), tw[n << (tw_shift_n + 1)]);   // W_M^n = W_N^(2n)
+        }
+    }
+    if (a.in_mode == IN_COEFF && bad) *a.nonfinite = 1;
+    if (a.in_mode == IN_RAW_PREV && t == 0 && r == 0 && a.procblocks != NULL) { // brutefir.cpp:265-268
+        const int pb = a.procblocks[bx];
+        const bool inc = pb < a.n_slots;
+        if (inc) a.procblocks[bx] = pb + 1;
+        a.pb_inc[bx] = inc ? 1 : 0;
+    }
+}
+
+// forward, phase 2: sub-transform result (natural order, padded smem) -> X_k, k = R0 k' + r, scaled,
+// stored in ORD or HC layout
+template <class T, int LOG2MS, int R0>
+BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
+{
+    constexpr int MS = 1 << LOG2MS, NT = MS / 16, M = MS * R0, N = 2 * M;
     typedef cpx<T> C;
     long long off = bx * a.out_stride_x + by * a.out_stride_y;
     if (a.state != NULL) off += (long long)(a.state->blockcounter % (unsigned int)a.n_slots) * a.out_stride_y;
@@ -161,14 +181,15 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, const cpx<T> *smem, const cp
     const T sc = (T)a.scale_out;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const int k = t + i * NT;
-        const C zk = smem[fft_pad(k)];
+        const int kp = t + i * NT;
+        const int k = R0 * kp + r;
+        const C zk = smem[fft_pad(kp)];
         if (k == 0) {
             const T dc = (zk.x + zk.y) * sc, ny = (zk.x - zk.y) * sc;
             out[0] = dc;
             if (a.out_layout == LAYOUT_ORD) out[4] = ny; else out[M] = ny;
         } else {
-            const C zm = smem[fft_pad(M - k)];
+            const C zm = smem[fft_pad(r == 0 ? MS - kp : MS - 1 - kp)];   // Z_{M-k}
             // E = (Z_k + conj Z_{M-k})/2, O = (Z_k - conj Z_{M-k})/(2i), X_k = E + W_N^k O
             const T er = (T)0.5 * (zk.x + zm.x), ei = (T)0.5 * (zk.y - zm.y);
             const T dr = (T)0.5 * (zk.x - zm.x), di = (T)0.5 * (zk.y + zm.y);
@@ -189,42 +210,58 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, const cpx<T> *smem, const cp
 }
 
 // ------------------------------------------------------------------------------------------------
-// inverse, phase 0: Z'_k = (X_k + conj X_{M-k}) + i conj(W_N^k) (X_k - conj X_{M-k}),  k = t + i*NT
-template <class T, int LOG2M>
-BFIR_HD void inv_load(int t, int bx, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
+// Z'_k = (X_k + conj X_{M-k}) + i conj(W_N^k) (X_k - conj X_{M-k}), the packed spectrum whose inverse
+// complex transform is z[n] = x[2n] + i x[2n+1]
+template <class T>
+BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T> *__restrict__ tw, int tw_shift_n)
 {
-    constexpr int M = 1 << LOG2M, NT = M / 16;
+    typedef cpx<T> C;
+    C xk = spec_load<T>(in, layout, k, M);
+    C xm = spec_load<T>(in, layout, M - k, M);
+    xk.x *= sc; xk.y *= sc; xm.x *= sc; xm.y *= sc;
+    const T er = xk.x + xm.x, ei = xk.y - xm.y;   // X_k + conj X_{M-k}
+    const T dr = xk.x - xm.x, di = xk.y + xm.y;   // X_k - conj X_{M-k}
+    const C w = tw[k << tw_shift_n];              // W_N^k; need its conjugate
+    const T pr = w.x * dr + w.y * di;             // conj(w) * d
+    const T pi = w.x * di - w.y * dr;
+    return mk<T>(er - pi, ei + pr);               // e + i p
+}
+
+// inverse, phase 0: thread t builds s_r[k], k = t + i*NTs
+template <class T, int LOG2MS, int R0>
+BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
+{
+    constexpr int MS = 1 << LOG2MS, NT = MS / 16, M = MS * R0;
     typedef cpx<T> C;
     const T *in = (const T *)a.in + bx * a.in_stride_x;
     const T sc = (T)a.scale_in;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int k = t + i * NT;
-        C xk = spec_load<T>(in, a.in_layout, k, M);
-        C xm = spec_load<T>(in, a.in_layout, M - k, M);
-        xk.x *= sc; xk.y *= sc; xm.x *= sc; xm.y *= sc;
-        const T er = xk.x + xm.x, ei = xk.y - xm.y;   // X_k + conj X_{M-k}
-        const T dr = xk.x - xm.x, di = xk.y + xm.y;   // X_k - conj X_{M-k}
-        const C w = tw[k << tw_shift_n];              // W_N^k; need its conjugate
-        const T pr = w.x * dr + w.y * di;             // conj(w) * d
-        const T pi = w.x * di - w.y * dr;
-        v[i] = mk<T>(er - pi, ei + pr);               // e + i p
+        const C lo = inv_elem<T>(in, a.in_layout, k, M, sc, tw, tw_shift_n);
+        if (R0 == 1) {
+            v[i] = lo;
+        } else {
+            const C hi = inv_elem<T>(in, a.in_layout, k + MS, M, sc, tw, tw_shift_n);
+            if (r == 0) v[i] = cadd(lo, hi);
+            else v[i] = cmul(csub(lo, hi), cconj(tw[k << (tw_shift_n + 1)]));   // W_M^(-k)
+        }
     }
 }
 
-// inverse, phase 1: v[i] = z[n], n = t + i*NT, x[2n] = Re, x[2n+1] = Im
-template <class T, int LOG2M>
-BFIR_HD void inv_store(int t, int bx, const cpx<T> (&v)[16], const InvArgs &a, OverflowAcc &acc)
+// inverse, phase 1: v[i] = z[R0 n + r], n = t + i*NTs;  x[2m] = Re z[m], x[2m+1] = Im z[m]
+template <class T, int LOG2MS, int R0>
+BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[16], const InvArgs &a, OverflowAcc &acc)
 {
-    constexpr int M = 1 << LOG2M, NT = M / 16, L = M;
+    constexpr int MS = 1 << LOG2MS, NT = MS / 16, M = MS * R0, L = M;
     typedef cpx<T> C;
     if (a.out_mode == OUT_TIME) {
         C *out = (C *)((T *)a.out + bx * a.out_stride_x);
 #pragma unroll
-        for (int i = 0; i < 16; i++) out[t + i * NT] = v[i];
+        for (int i = 0; i < 16; i++) out[R0 * (t + i * NT) + r] = v[i];
         return;
     }
-    if (t == 0 && a.state != NULL) {                   // brutefir.cpp:316-321
+    if (t == 0 && r == 0 && a.state != NULL) {         // brutefir.cpp:316-321
         const T y0 = v[0].x;
         if (!(y0 - y0 == (T)0)) {
 #ifdef __CUDA_ARCH__
@@ -234,10 +271,11 @@ BFIR_HD void inv_store(int t, int bx, const cpx<T> (&v)[16], const InvArgs &a, O
 #endif
         }
     }
+    // only the first L samples are consumed (fftw_convolver.cpp:425-430): z index < M/2 <=> i < 8
     if (a.out_mode == OUT_REAL_L) {
         C *out = (C *)((T *)a.out + (long long)bx * L);
 #pragma unroll
-        for (int i = 0; i < 8; i++) out[t + i * NT] = v[i];
+        for (int i = 0; i < 8; i++) out[R0 * (t + i * NT) + r] = v[i];
         return;
     }
     // OUT_RAW
@@ -249,7 +287,7 @@ BFIR_HD void inv_store(int t, int bx, const cpx<T> (&v)[16], const InvArgs &a, O
         const T rmax = (T)a.ovf_max;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            uint8_t *p = raw + (long long)(2 * (t + i * NT)) * step;
+            uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
             store_raw_float<T>(p, a.fmt, v[i].x, rmax, acc);
             store_raw_float<T>(p + step, a.fmt, v[i].y, rmax, acc);
         }
@@ -259,7 +297,7 @@ BFIR_HD void inv_store(int t, int bx, const cpx<T> (&v)[16], const InvArgs &a, O
         const T rmin = (T)imin, rmax = (T)imax;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            uint8_t *p = raw + (long long)(2 * (t + i * NT)) * step;
+            uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
             store_raw_quantised<T>(p, a.fmt, v[i].x, rmin, rmax, imin, imax, acc);
             store_raw_quantised<T>(p + step, a.fmt, v[i].y, rmin, rmax, imin, imax, acc);
         }
@@ -287,34 +325,35 @@ __device__ __forceinline__ void overflow_commit(OverflowStats *dst, OverflowAcc 
     if (lb) atomicMax(&dst->largest_bits, lb);
 }
 
-template <class T, int LOG2M>
-__global__ void __launch_bounds__((1 << LOG2M) / 16) rfft_forward_kernel(const FwdArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
+// grid = (buffers, partitions, R0); tw_shift_m = log2(table length / Ms), tw_shift_n = log2(table length / N)
+template <class T, int LOG2MS, int R0>
+__global__ void __launch_bounds__((1 << LOG2MS) / 16) rfft_forward_kernel(const FwdArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
-    const int t = threadIdx.x, bx = blockIdx.x, by = blockIdx.y;
+    const int t = threadIdx.x, bx = blockIdx.x, by = blockIdx.y, r = blockIdx.z;
     cpx<T> v[16];
-    fwd_load<T, LOG2M>(t, bx, by, v, a);
-    fft_passes<T, LOG2M, false, 0, 0>::run(t, v, smem, tw, tw_shift_m);
-    BlockFFT<T, LOG2M, false>::store_natural(t, v, smem);
+    fwd_load<T, LOG2MS, R0>(t, bx, by, r, v, tw, tw_shift_n, a);
+    fft_passes<T, LOG2MS, false, 0, 0>::run(t, v, smem, tw, tw_shift_m);
+    BlockFFT<T, LOG2MS, false>::store_natural(t, v, smem);
     __syncthreads();
-    fwd_split_store<T, LOG2M>(t, bx, by, smem, tw, tw_shift_n, a);
+    fwd_split_store<T, LOG2MS, R0>(t, bx, by, r, smem, tw, tw_shift_n, a);
 }
 
-template <class T, int LOG2M>
-__global__ void __launch_bounds__((1 << LOG2M) / 16) rfft_inverse_kernel(const InvArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
+template <class T, int LOG2MS, int R0>
+__global__ void __launch_bounds__((1 << LOG2MS) / 16) rfft_inverse_kernel(const InvArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
-    const int t = threadIdx.x, bx = blockIdx.x;
+    const int t = threadIdx.x, bx = blockIdx.x, r = blockIdx.z;
     cpx<T> v[16];
-    inv_load<T, LOG2M>(t, bx, v, tw, tw_shift_n, a);
-    fft_passes<T, LOG2M, true, 0, 0>::run(t, v, smem, tw, tw_shift_m);
+    inv_load<T, LOG2MS, R0>(t, bx, r, v, tw, tw_shift_n, a);
+    fft_passes<T, LOG2MS, true, 0, 0>::run(t, v, smem, tw, tw_shift_m);
     OverflowAcc acc;
     acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
-    inv_store<T, LOG2M>(t, bx, v, a, acc);
+    inv_store<T, LOG2MS, R0>(t, bx, r, v, a, acc);
     if (a.out_mode == OUT_RAW && a.stats != NULL) overflow_commit(&a.stats[bx], acc);
-    if (a.state != NULL && bx == 0 && t == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
+    if (a.state != NULL && bx == 0 && t == 0 && r == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
 }
 #endif
 

@@ -1,0 +1,88 @@
+"""Multi-GPU host logic: one process per GPU, `torch.distributed` for the plumbing.
+
+Two ways the path shards, and nothing else:
+
+* **streams / channels** -- channels never interact in ``brutefir::run`` (filter n <-> channel n only,
+  reference brutefir/brutefir.cpp:213-216, 252-334), so whole streams are dealt to ranks with
+  :func:`stream_shard` and there is NO data-path collective.
+* **partitions of one long filter** -- the partition sum ``sum_i X[t-i] * H[i]`` (brutefir.cpp:288-299)
+  is associative across ``i``: rank g convolves partitions :func:`partition_shard` of every channel,
+  every rank transforms the (small) input block redundantly, and ONE sum-reduction of the partial
+  output spectra (``channels * 2L`` reals) per block joins them (:class:`PartitionShardedEngine`).
+
+The engine object only has to provide ``run_partial_device``, ``run_finish_device``, ``sync`` and a
+tensor view of its partial spectra, so the same driver runs on CPU tensors with the ``gloo`` backend in
+the tests (tests/test_sharding_gloo.py) and on the CUDA engine with ``nccl`` on the GPUs.
+"""
+
+
+def stream_shard(n_streams, world_size, rank):
+    """Contiguous split of `n_streams` independent streams: returns (first_stream, count) of `rank`.
+    The first ``n_streams % world_size`` ranks get one stream more."""
+    if world_size < 1 or not 0 <= rank < world_size or n_streams < 0:
+        raise ValueError("invalid shard request")
+    base, extra = divmod(n_streams, world_size)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def partition_shard(n_partitions, world_size, rank):
+    """Contiguous split of the filter partitions [0, P): returns (part_begin, part_count) of `rank`.
+    Ranks beyond the partition count get an empty shard (count 0) and contribute zeros to the reduce."""
+    return stream_shard(n_partitions, world_size, rank)
+
+
+class PartitionShardedEngine:
+    """Drives one partition shard per rank and joins the shards with a sum all-reduce.
+
+    engine      object with run_partial_device(d_in), run_finish_device(d_out), sync()
+    acc         tensor view (torch) of the engine's partial accumulated spectra, reduced in place
+    group       torch.distributed process group (None = default)
+    """
+
+    def __init__(self, engine, acc, group=None):
+        import torch.distributed as dist
+        self.dist, self.engine, self.acc, self.group = dist, engine, acc, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.blocks = 0
+
+    def run_device(self, d_in, d_out, pre_reduce=None):
+        """One block: partial partition sum on every rank -> all-reduce(sum) -> output stage.
+        `pre_reduce` is called between the partial step and the collective (the CUDA engine makes the
+        communication stream wait for the compute stream there)."""
+        self.engine.run_partial_device(d_in)
+        if pre_reduce is not None:
+            pre_reduce()
+        if self.world > 1:
+            self.dist.all_reduce(self.acc, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.engine.run_finish_device(d_out)
+        self.blocks += 1
+
+    def sync(self):
+        return self.engine.sync()
+
+
+def make_partition_sharded(pkg, filter_length, filter_blocks, realsize, channels, in_format, out_format,
+                           sampling_rate, apply_dither, coeffs, coeff_blocks=None, scale=1.0, n_streams=1,
+                           device=-1, group=None):
+    """Build this rank's shard of a partition-sharded CUDA engine and its driver (NCCL).
+
+    Every rank passes the FULL coefficient arrays; the shard convolves only its partitions. The engine
+    runs on torch's current CUDA stream so the NCCL all-reduce is ordered with the kernels."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    begin, count = partition_shard(filter_blocks, world, rank)
+    if count == 0:
+        raise ValueError("more ranks than partitions: %d > %d" % (world, filter_blocks))
+    eng = pkg.Brutefir(filter_length, filter_blocks, realsize, channels, in_format, out_format, sampling_rate,
+                       apply_dither, n_streams=n_streams, device=device, part_begin=begin, part_count=count)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    rc = eng.set_coeff(coeffs, filter_blocks if coeff_blocks is None else coeff_blocks, scale)
+    if rc != 0:
+        raise RuntimeError("set_coeff failed: %d" % rc)
+    ptr, nbytes = eng.acc_device_ptr()
+    acc = pkg.as_torch(ptr, nbytes // realsize, "<f4" if realsize == 4 else "<f8")
+    return PartitionShardedEngine(eng, acc, group), eng

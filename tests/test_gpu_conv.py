@@ -10,7 +10,7 @@ from conftest import rel_rms, encode_raw, decode_raw
 pytestmark = pytest.mark.gpu
 
 TOL = {4: 1e-5, 8: 1e-12}
-SIZES = [(16, 4), (64, 4), (512, 4), (1024, 8), (4096, 4), (8192, 8), (16384, 4), (32, 8), (2048, 8)]
+SIZES = [(16, 4), (64, 4), (512, 4), (1024, 8), (4096, 4), (8192, 8), (16384, 4), (32, 8), (2048, 8), (32768, 4), (16384, 8)]
 
 
 def make(pkg, oracle, L, rs):
@@ -105,7 +105,7 @@ def test_dirac_convolve(pkg, oracle, rs):
     assert rel_rms(g.get(yh), ref) < TOL[rs] * 10
 
 
-@pytest.mark.parametrize("L,rs", [(64, 4), (1024, 4), (1024, 8), (8192, 8), (16384, 4)])
+@pytest.mark.parametrize("L,rs", [(64, 4), (1024, 4), (1024, 8), (8192, 8), (16384, 4), (32768, 4), (16384, 8)])
 def test_coeffs2cbuf(pkg, oracle, L, rs):
     g, o = make(pkg, oracle, L, rs)
     rng = np.random.default_rng(L)
@@ -127,9 +127,8 @@ def test_coeffs2cbuf(pkg, oracle, L, rs):
     assert g.convolver_coeffs2cbuf(bad, L, 1.0, g.cbuf()) == pkg.ERR_COEFF
 
 
-@pytest.mark.parametrize("rs", [4, 8])
-def test_runtime_coeffs2cbuf(pkg, oracle, rs):
-    L = 2048
+@pytest.mark.parametrize("rs,L", [(4, 2048), (8, 2048), (4, 32768), (8, 8192)])
+def test_runtime_coeffs2cbuf(pkg, oracle, rs, L):
     g, o = make(pkg, oracle, L, rs)
     h = np.random.default_rng(3).standard_normal(L).astype(g.dtype)
     src, dest = g.cbuf(h, n_cbufs=0.5), g.cbuf()
@@ -139,9 +138,8 @@ def test_runtime_coeffs2cbuf(pkg, oracle, rs):
     assert rel_rms(got, o.coeffs2cbuf(h)) < TOL[rs]
 
 
-@pytest.mark.parametrize("rs", [4, 8])
-def test_crossfade_inplace(pkg, oracle, rs):
-    L = 1024
+@pytest.mark.parametrize("rs,L", [(4, 1024), (8, 1024), (4, 32768), (8, 4096)])
+def test_crossfade_inplace(pkg, oracle, rs, L):
     g = pkg.FftwConvolver(L, rs)
     o = oracle.Convolver(L, rs, kind="port" if rs == 8 else None)  # double: float-branch algorithm
     rng = np.random.default_rng(11)

@@ -69,6 +69,14 @@ def test_cfg1_double_vs_oracle_and_direct(pkg, oracle):
         assert rel_rms(yg[:, c], oracle_np.direct_convolution(x[:, c], h[c], len(x))) < 1e-12
 
 
+@pytest.mark.parametrize("L,rs", [(32768, 4), (16384, 8), (16384, 4), (8192, 8)])
+def test_largest_block_lengths_two_cta_transform(pkg, oracle, L, rs):
+    """L = 32768 (float) / 16384 (double) only exist as two-CTA transforms; cfg4 uses L = 32768"""
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    g, o, x, h, yg, yo = run_both(pkg, oracle, L, 3, rs, 2, fmt, fmt, 5)
+    assert rel_rms(yg, yo) < TOL[rs]
+
+
 def test_product_configuration_float_io_double_engine(pkg, oracle):
     """what foo_dsp_bfir constructs: FILTER_LEN 1024, REALSIZE 8, FLOAT_LE in/out (foo_dsp_bfir.cpp:279-286)"""
     g, o, x, h, yg, yo = run_both(pkg, oracle, 1024, 8, 8, 2, pkg.FLOAT_LE, pkg.FLOAT_LE, 20)
@@ -171,7 +179,7 @@ def test_set_coeff_errors_and_replacement(pkg, oracle):
 def test_invalid_parameters(pkg):
     for args in [(100, 2, 4, 2, 8, 8, 44100, False), (64, 2, 5, 2, 8, 8, 44100, False), (64, 0, 4, 2, 8, 8, 44100, False),
                  (64, 2, 4, 0, 8, 8, 44100, False), (64, 2, 4, 2, 0, 8, 44100, False), (64, 2, 4, 2, 8, 12, 44100, False),
-                 (32768, 2, 4, 2, 8, 8, 44100, False), (16384, 2, 8, 2, 8, 8, 44100, False)]:
+                 (65536, 2, 4, 2, 8, 8, 44100, False), (32768, 2, 8, 2, 8, 8, 44100, False)]:
         with pytest.raises(pkg.BfirError) as e:
             pkg.Brutefir(*args)
         assert e.value.code == pkg.ERR_INVALID
