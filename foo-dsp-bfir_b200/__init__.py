@@ -48,7 +48,8 @@ class Overflow(ctypes.Structure):  # bfir_overflow_t == struct bfoverflow_t (glo
 class Config(ctypes.Structure):  # bfir_config_t
     _fields_ = [(n, ctypes.c_int) for n in (
         "filter_length", "filter_blocks", "realsize", "channels", "in_format", "out_format",
-        "sampling_rate", "apply_dither", "n_streams", "device", "part_begin", "part_count")]
+        "sampling_rate", "apply_dither", "n_streams", "device", "part_begin", "part_count", "n_groups",
+        "xbar_inputs", "xbar_outputs")]
 
 
 # every symbol include/bfir_b200.h declares: (name, restype, argtypes)
@@ -61,6 +62,7 @@ API = [
     ("bfir_destroy", None, [_vp]),
     ("bfir_is_initialized", _ci, [_vp]),
     ("bfir_set_coeff", _ci, [_vp, _pp, _ci, _ci, _ci, _cd]),
+    ("bfir_set_crossbar", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(_cd)]),
     ("bfir_run", _ci, [_vp, _vp, _vp]),
     ("bfir_run_device", _ci, [_vp, _vp, _vp]),
     ("bfir_sync", _ci, [_vp]),
@@ -72,6 +74,8 @@ API = [
     ("bfir_run_partial_device", _ci, [_vp, _vp]),
     ("bfir_run_finish_device", _ci, [_vp, _vp]),
     ("bfir_acc_device_ptr", _vp, [_vp, ctypes.POINTER(_sz)]),
+    ("bfir_set_groups", _ci, [_vp, _ci]),
+    ("bfir_get_groups", _ci, [_vp]),
     ("bfir_set_stream", _ci, [_vp, _vp]),
     ("bfir_set_profiling", _ci, [_vp, _ci]),
     ("bfir_get_profile", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(ctypes.c_ulonglong), _ci]),
@@ -181,11 +185,13 @@ class Brutefir:
     """
 
     def __init__(self, filter_length, filter_blocks, realsize, channels, in_format, out_format,
-                 sampling_rate, apply_dither, n_streams=1, device=-1, part_begin=0, part_count=0):
+                 sampling_rate, apply_dither, n_streams=1, device=-1, part_begin=0, part_count=0, n_groups=0,
+                 xbar_inputs=0, xbar_outputs=0):
         self.lib = load_library()
         self.h = ctypes.c_void_p()
         cfg = Config(filter_length, filter_blocks, realsize, channels, in_format, out_format,
-                     sampling_rate, int(bool(apply_dither)), n_streams, device, part_begin, part_count)
+                     sampling_rate, int(bool(apply_dither)), n_streams, device, part_begin, part_count, n_groups,
+                     xbar_inputs, xbar_outputs)
         rc = self.lib.bfir_create_ex(ctypes.byref(self.h), ctypes.byref(cfg))
         if rc != OK:
             self.h = ctypes.c_void_p()
@@ -195,8 +201,10 @@ class Brutefir:
         self.channels, self.n_streams = channels, n_streams
         self.in_format, self.out_format = in_format, out_format
         self.dtype = real_dtype(realsize)
-        self.in_bytes = n_streams * filter_length * channels * FORMAT_BYTES[in_format]
-        self.out_bytes = n_streams * filter_length * channels * FORMAT_BYTES[out_format]
+        self.n_inputs = xbar_inputs if xbar_inputs > 0 else channels
+        self.n_outputs = xbar_outputs if xbar_outputs > 0 else channels
+        self.in_bytes = n_streams * filter_length * self.n_inputs * FORMAT_BYTES[in_format]
+        self.out_bytes = n_streams * filter_length * self.n_outputs * FORMAT_BYTES[out_format]
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -221,6 +229,14 @@ class Brutefir:
         if rc not in (OK, ERR_COEFF):
             raise BfirError(rc, last_error())
         return rc
+
+    def set_crossbar(self, in_gains, out_gains):
+        """in_gains [filters][inputs], out_gains [outputs][filters] (mixnscale scales, n_bufs > 1)"""
+        a = np.ascontiguousarray(in_gains, dtype=np.float64)
+        b = np.ascontiguousarray(out_gains, dtype=np.float64)
+        assert a.shape == (self.channels, self.n_inputs) and b.shape == (self.n_outputs, self.channels)
+        _check(self.lib.bfir_set_crossbar(self.h, a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                          b.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
 
     def run(self, inbuf, outbuf=None):
         """run(void *inbuf, void *outbuf) -> (rc, outbuf); rc is 0 or -1 like the reference."""
@@ -250,6 +266,12 @@ class Brutefir:
         if rc not in (OK, ERR_NONFINITE):
             raise BfirError(rc, last_error())
         return rc
+
+    def set_groups(self, n):
+        _check(self.lib.bfir_set_groups(self.h, int(n)))
+
+    def get_groups(self):
+        return _check(self.lib.bfir_get_groups(self.h))
 
     def set_stream(self, cuda_stream):
         _check(self.lib.bfir_set_stream(self.h, ctypes.c_void_p(cuda_stream)))

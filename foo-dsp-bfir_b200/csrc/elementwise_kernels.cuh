@@ -36,6 +36,7 @@ struct DitherArgs {
     OverflowStats *stats;     // [channels]
     int single_channel;       // >= 0: inner API call for exactly this dither channel (grid of 1)
     long long real_stride;    // elements between channels of `real`
+    int ch_base;              // first channel of this launch; n_channels counts from it
 };
 
 #ifdef __CUDACC__
@@ -167,7 +168,7 @@ __global__ void dither_kernel(const DitherArgs a)
 {
     int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (a.single_channel >= 0) { if (ch != 0) return; ch = a.single_channel; }
-    else if (ch >= a.n_channels) return;
+    else { if (ch >= a.n_channels) return; ch += a.ch_base; }
     const int data_ch = a.single_channel >= 0 ? 0 : ch;
     DitherState st = a.dstate[ch];
     // dither_preloop_real2int_hp_tpdf, dither.cpp:127-139
@@ -215,22 +216,22 @@ __global__ void dither_kernel(const DitherArgs a)
 }
 
 // engine housekeeping
-static __global__ void engine_reset_kernel(EngineState *state, int *procblocks, OverflowStats *stats, int n_channels)
+#define BFIR_MAX_GROUPS 8
+static __global__ void engine_reset_kernel(EngineState *state, int *procblocks, OverflowStats *stats, int n_filters, int n_stats)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { state->blockcounter = 0; state->first_bad_channel = 0x7fffffff; }
-    if (i < n_channels) { // brutefir.cpp:347-367: counters only, never the buffers
-        procblocks[i] = 0;
-        stats[i].n_overflows = 0; stats[i].intlargest = 0; stats[i].largest_bits = 0ull;
-    }
+    if (i < BFIR_MAX_GROUPS) { state[i].blockcounter = 0; state[i].first_bad_channel = 0x7fffffff; }
+    // brutefir.cpp:347-367: counters only, never the buffers
+    if (i < n_filters) procblocks[i] = 0;
+    if (i < n_stats) { stats[i].n_overflows = 0; stats[i].intlargest = 0; stats[i].largest_bits = 0ull; }
 }
 
 // undo the bookkeeping of a block that brutefir::run would have aborted at channel `bad`
 // (brutefir.cpp:316-321 returns before :337-340): later channels never ran, the counter did not move
-static __global__ void engine_abort_fixup_kernel(EngineState *state, int *procblocks, const unsigned char *pb_inc, int n_channels, int bad)
+static __global__ void engine_abort_fixup_kernel(EngineState *state, int n_groups, int *procblocks, const unsigned char *pb_inc, int n_channels, int bad)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { state->blockcounter -= 1u; state->first_bad_channel = 0x7fffffff; }
+    if (i < n_groups) { state[i].blockcounter -= 1u; state[i].first_bad_channel = 0x7fffffff; }
     if (i > bad && i < n_channels && pb_inc[i]) procblocks[i] -= 1;
 }
 #endif

@@ -9,12 +9,18 @@
 // All state the reference keeps in host members (blockcounter, procblocks, dither_state, overflow;
 // brutefir.hpp:104-127) lives in device memory, so a block step needs no host-side bookkeeping.
 #include "common.hpp"
+#include "xbar_kernels.cuh"
+#include <time.h>
 
 namespace bfir {
 
 struct Engine {
     bfir_config_t cfg;
     int L = 0, N = 0, P = 0, C = 0, S = 0, Ct = 0, rs = 0, log2m = 0;
+    // crossbar: Ci inputs and Co outputs per stream around the C filters (== C without a crossbar)
+    int Ci = 0, Co = 0, Cit = 0, Cot = 0;
+    bool xbar = false, xbar_set = false;
+    void *xin = nullptr, *yacc = nullptr, *gains_in = nullptr, *gains_out = nullptr;
     int part_begin = 0, part_count = 0;
     SampleFormat in_sf, out_sf;
     bool dither_on = false, initialized = false, own_stream = true;
@@ -24,11 +30,17 @@ struct Engine {
     void *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer run()
     size_t in_bytes = 0, out_bytes = 0;
     int coeff_alloc = 0;
-    EngineState *state = nullptr;
+    EngineState *state = nullptr;   // [BFIR_MAX_GROUPS], one per channel group, kept in lockstep
+    // channel-group pipelining: whole streams are dealt to n_groups groups, each with its own CUDA
+    // stream, so that H2D / kernels / D2H of different groups overlap (and FFT with MAC kernels)
+    struct Group { int s0, s1, c0, c1; cudaStream_t stream; cudaEvent_t done; };
+    Group groups[BFIR_MAX_GROUPS] = {};
+    int n_groups = 1;
+    cudaEvent_t fork_ev = nullptr;
     int *procblocks = nullptr, *coeff_blocks = nullptr, *nonfinite = nullptr;
     unsigned char *pb_inc = nullptr;
     OverflowStats *stats = nullptr;
-    EngineState *h_state = nullptr; // pinned
+    EngineState *h_state = nullptr; // pinned, [BFIR_MAX_GROUPS]
     std::vector<bfir_overflow_t> last_overflow;
     DitherTables dither;
     double ovf_max = 1.0;
@@ -48,8 +60,16 @@ struct Engine {
     int init(const bfir_config_t &c);
     void destroy();
     int set_coeff(const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
+    int set_crossbar(const double *in_gains, const double *out_gains);
+    int set_groups(int n);
+    cudaStream_t gstream(int g) const { return n_groups == 1 ? stream : groups[g].stream; }
+    int fork();
+    int join();
+    int front_group(int g, const void *d_inbuf);
+    int back_group(int g, void *d_outbuf);
     int enqueue_front(const void *d_inbuf);
     int enqueue_back(void *d_outbuf);
+    int enqueue_block(const void *d_inbuf, void *d_outbuf);
     int run_host(const void *inbuf, void *outbuf);
     int sync_and_probe();
     int reset();
@@ -68,6 +88,11 @@ int Engine::init(const bfir_config_t &c)
     if (P < 1 || C < 1) { set_error("No channels defined."); return BFIR_ERR_INVALID; }            // brutefir.cpp:745-749
     if ((long long)C * S > 0x7fffffffLL / 2) return BFIR_ERR_INVALID;
     Ct = C * S;
+    xbar = c.xbar_inputs > 0 || c.xbar_outputs > 0;
+    Ci = c.xbar_inputs > 0 ? c.xbar_inputs : C;
+    Co = c.xbar_outputs > 0 ? c.xbar_outputs : C;
+    if (xbar && (Ci > BFIR_MAX_XBAR || Co > BFIR_MAX_XBAR || C > BFIR_MAX_XBAR)) { set_error("crossbar larger than %d", BFIR_MAX_XBAR); return BFIR_ERR_INVALID; }
+    Cit = Ci * S; Cot = Co * S;
     if (!fill_sample_format(&in_sf, c.in_format, true) || !fill_sample_format(&out_sf, c.out_format, false)) {
         set_error("invalid sample format %d / %d", c.in_format, c.out_format);
         return BFIR_ERR_INVALID;
@@ -90,28 +115,39 @@ int Engine::init(const bfir_config_t &c)
     BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * P * Ct, stream));                                      // brutefir.cpp:768-769
     BFIR_CUDA(cudaMalloc(&acc, cbuf * Ct));
     BFIR_CUDA(cudaMemsetAsync(acc, 0, cbuf * Ct, stream));
-    BFIR_CUDA(cudaMalloc(&prev, (size_t)2 * L * rs * Ct));                                          // input_timecbuf[n][2]
-    BFIR_CUDA(cudaMemsetAsync(prev, 0, (size_t)2 * L * rs * Ct, stream));
+    BFIR_CUDA(cudaMalloc(&prev, (size_t)2 * L * rs * Cit));                                         // input_timecbuf[n][2]
+    BFIR_CUDA(cudaMemsetAsync(prev, 0, (size_t)2 * L * rs * Cit, stream));
+    if (xbar) {
+        BFIR_CUDA(cudaMalloc(&xin, cbuf * Cit));
+        BFIR_CUDA(cudaMalloc(&yacc, cbuf * Cot));
+        BFIR_CUDA(cudaMalloc(&gains_in, (size_t)C * Ci * rs));
+        BFIR_CUDA(cudaMalloc(&gains_out, (size_t)Co * C * rs));
+    }
     fft_r0 = rfft_choose_r0(rs, log2m, Ct);
-    in_bytes = (size_t)S * L * C * in_sf.bytes;
-    out_bytes = (size_t)S * L * C * out_sf.bytes;
+    in_bytes = (size_t)S * L * Ci * in_sf.bytes;
+    out_bytes = (size_t)S * L * Co * out_sf.bytes;
     BFIR_CUDA(cudaMalloc(&d_in, in_bytes));
     BFIR_CUDA(cudaMalloc(&d_out, out_bytes));
-    BFIR_CUDA(cudaMalloc((void **)&state, sizeof(EngineState)));
+    BFIR_CUDA(cudaMalloc((void **)&state, sizeof(EngineState) * BFIR_MAX_GROUPS));
     BFIR_CUDA(cudaMalloc((void **)&procblocks, sizeof(int) * Ct));
     BFIR_CUDA(cudaMalloc((void **)&coeff_blocks, sizeof(int) * Ct));
     BFIR_CUDA(cudaMemsetAsync(coeff_blocks, 0, sizeof(int) * Ct, stream));
     BFIR_CUDA(cudaMalloc((void **)&pb_inc, (size_t)Ct));
     BFIR_CUDA(cudaMemsetAsync(pb_inc, 0, (size_t)Ct, stream));
     BFIR_CUDA(cudaMalloc((void **)&nonfinite, sizeof(int)));
-    BFIR_CUDA(cudaMalloc((void **)&stats, sizeof(OverflowStats) * Ct));
-    BFIR_CUDA(cudaHostAlloc((void **)&h_state, sizeof(EngineState), cudaHostAllocDefault));
+    BFIR_CUDA(cudaMalloc((void **)&stats, sizeof(OverflowStats) * (Cot > Ct ? Cot : Ct)));
+    BFIR_CUDA(cudaHostAlloc((void **)&h_state, sizeof(EngineState) * BFIR_MAX_GROUPS, cudaHostAllocDefault));
+    for (int g = 0; g < BFIR_MAX_GROUPS; g++) {
+        BFIR_CUDA(cudaStreamCreateWithFlags(&groups[g].stream, cudaStreamNonBlocking));
+        BFIR_CUDA(cudaEventCreateWithFlags(&groups[g].done, cudaEventDisableTiming));
+    }
+    BFIR_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
     int rc = make_twiddles(rs, N, &tw);
     if (rc != BFIR_OK) return rc;
     if (dither_on) {
-        BFIR_CUDA(cudaMalloc(&ybuf, (size_t)L * rs * Ct));
+        BFIR_CUDA(cudaMalloc(&ybuf, (size_t)L * rs * Cot));
         // max_dither_table_size is 0 (memset bfconf, brutefir.cpp:31-32; passed at :712)
-        rc = dither.init(Ct, c.sampling_rate, rs, 0, L);
+        rc = dither.init(Cot, c.sampling_rate, rs, 0, L);
         if (rc != BFIR_OK) return rc;
     }
     // MAC decomposition: enough CTAs for >= ~8 waves of 148 SMs x 3 resident CTAs, never more slices
@@ -125,7 +161,20 @@ int Engine::init(const bfir_config_t &c)
             if ((v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) && v <= P) mac_split = v;
         }
     }
-    last_overflow.assign(Ct, bfir_overflow_t{0, 0, 0.0, ovf_max});
+    last_overflow.assign(Cot, bfir_overflow_t{0, 0, 0.0, ovf_max});
+    {
+        // groups: only whole streams can be split (the raw buffers interleave the channels of a stream);
+        // worth it once a group still fills the machine. BFIR_GROUPS overrides (measurement).
+        int want = c.n_groups > 0 ? c.n_groups : 1;
+        if (c.n_groups <= 0) {
+            const double step_bytes = (double)Ct * (2.0 * P + 1) * N * rs;
+            if (S >= 4 && step_bytes >= 256e6) want = 4;
+            else if (S >= 2 && step_bytes >= 64e6) want = 2;
+        }
+        if (const char *env = getenv("BFIR_GROUPS")) { const int v = atoi(env); if (v >= 1) want = v; }
+        rc = set_groups(want);
+        if (rc != BFIR_OK) return rc;
+    }
     rc = reset();
     if (rc != BFIR_OK) return rc;
     BFIR_CUDA(cudaStreamSynchronize(stream));
@@ -148,11 +197,17 @@ void Engine::prof_collect()
 void Engine::destroy()
 {
     prof_free();
-    if (stream && own_stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    if (stream) cudaStreamSynchronize(stream);
+    for (int g = 0; g < BFIR_MAX_GROUPS; g++) {
+        if (groups[g].stream) { cudaStreamSynchronize(groups[g].stream); cudaStreamDestroy(groups[g].stream); groups[g].stream = nullptr; }
+        if (groups[g].done) { cudaEventDestroy(groups[g].done); groups[g].done = nullptr; }
+    }
+    if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
+    if (stream && own_stream) cudaStreamDestroy(stream);
     stream = nullptr;
-    void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats };
+    void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out };
     for (void *b : bufs) if (b) cudaFree(b);
-    fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = nullptr;
+    fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = nullptr;
     state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
     h_state = nullptr;
@@ -162,8 +217,9 @@ void Engine::destroy()
 int Engine::reset()
 {
     // brutefir::reset, brutefir.cpp:347-367
-    const int threads = 256, blocks = (Ct + threads - 1) / threads;
-    engine_reset_kernel<<<blocks, threads, 0, stream>>>(state, procblocks, stats, Ct);
+    const int nmax = Cot > Ct ? Cot : Ct;
+    const int threads = 256, blocks = (nmax + threads - 1) / threads;
+    engine_reset_kernel<<<blocks, threads, 0, stream>>>(state, procblocks, stats, Ct, nmax);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     for (auto &o : last_overflow) { o.n_overflows = 0; o.largest = 0; o.intlargest = 0; }
@@ -222,85 +278,204 @@ int Engine::set_coeff(const void *const *h_coeffs, int n_coeffs, int length, int
     return BFIR_OK;
 }
 
-// input FFT into the delay line + this engine's partition sum
-int Engine::enqueue_front(const void *d_inbuf)
+int Engine::set_crossbar(const double *in_gains, const double *out_gains)
 {
+    if (!xbar) { set_error("engine was created without a crossbar"); return BFIR_ERR_INVALID; }
+    if (in_gains == nullptr || out_gains == nullptr) return BFIR_ERR_INVALID;
+    BFIR_CUDA(cudaStreamSynchronize(stream));
+    for (int g = 0; g < n_groups; g++) BFIR_CUDA(cudaStreamSynchronize(groups[g].stream));
+    // like mixnscalef (fftw_convolver.cpp:871-876) the float engine narrows the gains to float first
+    std::vector<unsigned char> a((size_t)C * Ci * rs), b((size_t)Co * C * rs);
+    for (int k = 0; k < C * Ci; k++) { if (rs == 4) ((float *)a.data())[k] = (float)in_gains[k]; else ((double *)a.data())[k] = in_gains[k]; }
+    for (int k = 0; k < Co * C; k++) { if (rs == 4) ((float *)b.data())[k] = (float)out_gains[k]; else ((double *)b.data())[k] = out_gains[k]; }
+    BFIR_CUDA(cudaMemcpy(gains_in, a.data(), a.size(), cudaMemcpyHostToDevice));
+    BFIR_CUDA(cudaMemcpy(gains_out, b.data(), b.size(), cudaMemcpyHostToDevice));
+    xbar_set = true;
+    return BFIR_OK;
+}
+
+int Engine::set_groups(int n)
+{
+    if (n < 1) n = 1;
+    if (n > BFIR_MAX_GROUPS) n = BFIR_MAX_GROUPS;
+    if (n > S) n = S;
+    if (stream) BFIR_CUDA(cudaStreamSynchronize(stream));
+    for (int g = 0; g < n_groups && g < BFIR_MAX_GROUPS; g++)
+        if (groups[g].stream) BFIR_CUDA(cudaStreamSynchronize(groups[g].stream));
+    n_groups = n;
+    const int base = S / n, extra = S % n;
+    int s = 0;
+    for (int g = 0; g < n; g++) {
+        const int cnt = base + (g < extra ? 1 : 0);
+        groups[g].s0 = s; groups[g].s1 = s + cnt;
+        groups[g].c0 = s * C; groups[g].c1 = (s + cnt) * C;
+        s += cnt;
+    }
+    // all group counters continue from group 0's value
+    EngineState st;
+    BFIR_CUDA(cudaMemcpy(&st, state, sizeof(st), cudaMemcpyDeviceToHost));
+    EngineState all[BFIR_MAX_GROUPS];
+    for (int g = 0; g < BFIR_MAX_GROUPS; g++) all[g] = st;
+    BFIR_CUDA(cudaMemcpy(state, all, sizeof(all), cudaMemcpyHostToDevice));
+    return BFIR_OK;
+}
+
+// group streams start after everything queued on the engine's stream ...
+int Engine::fork()
+{
+    if (n_groups == 1) return BFIR_OK;
+    BFIR_CUDA(cudaEventRecord(fork_ev, stream));
+    for (int g = 0; g < n_groups; g++) BFIR_CUDA(cudaStreamWaitEvent(groups[g].stream, fork_ev, 0));
+    return BFIR_OK;
+}
+
+// ... and the engine's stream continues after every group is done
+int Engine::join()
+{
+    if (n_groups == 1) return BFIR_OK;
+    for (int g = 0; g < n_groups; g++) {
+        BFIR_CUDA(cudaEventRecord(groups[g].done, groups[g].stream));
+        BFIR_CUDA(cudaStreamWaitEvent(stream, groups[g].done, 0));
+    }
+    return BFIR_OK;
+}
+
+// input FFT into the delay line + this engine's partition sum, for the channels of one group
+int Engine::front_group(int g, const void *d_inbuf)
+{
+    const Group &grp = groups[g];
+    const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
+    const int nch = ns * C, c0 = s0 * C;
+    cudaStream_t st = gstream(g);
     FwdArgs f = {};
     f.in_mode = IN_RAW_PREV; f.out_layout = LAYOUT_ORD;
-    f.in = d_inbuf; f.in_stride_x = (long long)L * C * in_sf.bytes;   // bytes per stream
-    f.out = fdl; f.out_stride_x = (long long)P * N; f.out_stride_y = N;
+    f.in = d_inbuf; f.in_stride_x = (long long)L * Ci * in_sf.bytes;  // bytes per stream
     f.scale_in = 1.0; f.scale_out = in_sf.scale;                       // brutefir.cpp:273-277
-    f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = C; f.n_channels = Ct;
-    f.state = state; f.n_slots = P; f.procblocks = procblocks; f.pb_inc = pb_inc;
-    prof(0);
-    cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(Ct, 1), stream, f, tw);
-    prof(1);
+    f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = Ci; f.n_channels = Cit; f.ch_base = s0 * Ci;
+    f.state = state + g; f.n_slots = P;
+    if (!xbar) { f.out = fdl; f.out_stride_x = (long long)P * N; f.out_stride_y = N; f.procblocks = procblocks; f.pb_inc = pb_inc; }
+    else { f.out = xin; f.out_stride_x = N; f.out_stride_y = 0; f.procblocks = nullptr; f.pb_inc = nullptr; }
+    if (g == 0) prof(0);
+    cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(ns * Ci, 1), st, f, tw);
     count_launch();
     if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    if (xbar) { // inputs -> filter inputs, straight into the delay-line slot (mixnscale INPUT, n_bufs = Ci)
+        XbarArgs x = {};
+        x.in = xin; x.in_stride = N; x.out = fdl; x.out_stride = (long long)P * N; x.slot_stride = N;
+        x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = ns; x.stream_base = s0;
+        x.state = state + g; x.n_slots = P; x.procblocks = procblocks; x.pb_inc = pb_inc;
+        xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
+        xk<<<dim3((N + 255) / 256, ns), 256, (size_t)C * Ci * rs, st>>>(x);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+    }
+    if (g == 0) prof(1);
 
     MacArgs m = {};
     m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
     m.fdl_stride_ch = (long long)P * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = P; m.part_begin = part_begin; m.part_count = part_count;
-    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state; m.block_offset = 0;
-    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), Ct);
+    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = c0;
+    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), nch);
     mac_kernel_t mk = rs == 4 ? mac_kernel_for_split<float>(mac_split) : mac_kernel_for_split<double>(mac_split);
-    mk<<<grid, 256, 0, stream>>>(m);
-    prof(2);
+    mk<<<grid, 256, 0, st>>>(m);
+    if (g == 0) prof(2);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     return BFIR_OK;
 }
 
-// output stage from the accumulated spectra
-int Engine::enqueue_back(void *d_outbuf)
+// output stage from the accumulated spectra, for the channels of one group
+int Engine::back_group(int g, void *d_outbuf)
 {
+    const Group &grp = groups[g];
+    const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
+    const int nch = ns * Co, c0 = s0 * Co;
+    cudaStream_t st = gstream(g);
+    if (xbar) { // filter outputs -> outputs (mixnscale OUTPUT, n_bufs = C)
+        XbarArgs x = {};
+        x.in = acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
+        x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = ns; x.stream_base = s0;
+        x.state = nullptr; x.n_slots = P; x.procblocks = nullptr; x.pb_inc = nullptr;
+        xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
+        xk<<<dim3((N + 255) / 256, ns), 256, (size_t)Co * C * rs, st>>>(x);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+    }
     InvArgs v = {};
-    v.in_layout = LAYOUT_ORD; v.in = acc; v.in_stride_x = N;
+    v.in_layout = LAYOUT_ORD; v.in = xbar ? yacc : acc; v.in_stride_x = N;
     v.scale_in = out_sf.scale;                                         // brutefir.cpp:303-307
-    v.fmt = out_sf.format; v.ch_per_stream = C; v.ovf_max = ovf_max; v.stats = stats; v.state = state;
+    v.fmt = out_sf.format; v.ch_per_stream = Co; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.ch_base = c0;
     if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }
-    else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * C * out_sf.bytes; }
-    cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(Ct, 1), stream, v, tw);
+    else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * Co * out_sf.bytes; }
+    cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(nch, 1), st, v, tw);
     count_launch();
     if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
     if (dither_on) {
         DitherArgs d = {};
-        d.real = ybuf; d.real_stride = L; d.raw = d_outbuf; d.raw_stream_stride = (long long)L * C * out_sf.bytes;
-        d.fmt = out_sf.format; d.ch_per_stream = C; d.L = L; d.n_channels = Ct;
+        d.real = ybuf; d.real_stride = L; d.raw = d_outbuf; d.raw_stream_stride = (long long)L * Co * out_sf.bytes;
+        d.fmt = out_sf.format; d.ch_per_stream = Co; d.L = L; d.n_channels = nch; d.ch_base = c0;
         d.randtab = dither.d_tab; d.randtab_size = dither.size; d.randmap = dither.d_map;
         d.dstate = dither.d_state; d.stats = stats; d.single_channel = -1;
-        const int threads = 32, blocks = (Ct + threads - 1) / threads;
-        if (rs == 4) dither_kernel<float><<<blocks, threads, 0, stream>>>(d);
-        else dither_kernel<double><<<blocks, threads, 0, stream>>>(d);
+        const int threads = 32, blocks = (nch + threads - 1) / threads;
+        if (rs == 4) dither_kernel<float><<<blocks, threads, 0, st>>>(d);
+        else dither_kernel<double><<<blocks, threads, 0, st>>>(d);
         count_launch();
         BFIR_CUDA(cudaGetLastError());
     }
-    prof(3);
-    if (pidx < pcap) pidx++;
-    blocks_since_sync++;
+    if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
     return BFIR_OK;
+}
+
+int Engine::enqueue_front(const void *d_inbuf)
+{
+    int rc = fork();
+    for (int g = 0; g < n_groups && rc == BFIR_OK; g++) rc = front_group(g, d_inbuf);
+    if (rc == BFIR_OK) rc = join();
+    return rc;
+}
+
+int Engine::enqueue_back(void *d_outbuf)
+{
+    int rc = fork();
+    for (int g = 0; g < n_groups && rc == BFIR_OK; g++) rc = back_group(g, d_outbuf);
+    if (rc == BFIR_OK) rc = join();
+    blocks_since_sync++;
+    return rc;
+}
+
+// one whole block step on device buffers: every group runs front and back on its own stream
+int Engine::enqueue_block(const void *d_inbuf, void *d_outbuf)
+{
+    int rc = fork();
+    for (int g = 0; g < n_groups && rc == BFIR_OK; g++) {
+        rc = front_group(g, d_inbuf);
+        if (rc == BFIR_OK) rc = back_group(g, d_outbuf);
+    }
+    if (rc == BFIR_OK) rc = join();
+    blocks_since_sync++;
+    return rc;
 }
 
 // wait for the stream and apply the reference's NaN/Inf abort (brutefir.cpp:316-321)
 int Engine::sync_and_probe()
 {
-    BFIR_CUDA(cudaMemcpyAsync(h_state, state, sizeof(EngineState), cudaMemcpyDeviceToHost, stream));
+    BFIR_CUDA(cudaMemcpyAsync(h_state, state, sizeof(EngineState) * n_groups, cudaMemcpyDeviceToHost, stream));
     BFIR_CUDA(cudaStreamSynchronize(stream));
     prof_collect();
     const unsigned long long n = blocks_since_sync;
     blocks_since_sync = 0;
-    if (h_state->first_bad_channel != 0x7fffffff) {
+    int bad = 0x7fffffff;
+    for (int g = 0; g < n_groups; g++) if (h_state[g].first_bad_channel < bad) bad = h_state[g].first_bad_channel;
+    if (bad != 0x7fffffff) {
         pinfo("NaN or Inf values in the system! Invalid input? Aborting.\n");
-        const int bad = h_state->first_bad_channel;
+        const int threads = 256, blocks = (Ct + threads - 1) / threads;
         if (n == 1) { // exact reference semantics: the aborted block does not advance the counters
-            const int threads = 256, blocks = (Ct + threads - 1) / threads;
-            engine_abort_fixup_kernel<<<blocks, threads, 0, stream>>>(state, procblocks, pb_inc, Ct, bad);
+            engine_abort_fixup_kernel<<<blocks, threads, 0, stream>>>(state, n_groups, procblocks, pb_inc, Ct, bad);
             count_launch();
         } else {
-            EngineState s = *h_state;
-            s.first_bad_channel = 0x7fffffff;
-            cudaMemcpyAsync(state, &s, sizeof(s), cudaMemcpyHostToDevice, stream);
+            for (int g = 0; g < n_groups; g++) h_state[g].first_bad_channel = 0x7fffffff;
+            cudaMemcpyAsync(state, h_state, sizeof(EngineState) * n_groups, cudaMemcpyHostToDevice, stream);
         }
         BFIR_CUDA(cudaStreamSynchronize(stream));
         set_error("NaN or Inf values in the system (channel %d)", bad);
@@ -309,20 +484,47 @@ int Engine::sync_and_probe()
     return BFIR_OK;
 }
 
+// brutefir::run on host buffers: per group H2D -> kernels -> D2H on the group's stream, so the copies
+// of one group overlap the kernels of another; returns when outbuf is complete
+static double now_us() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+static double g_dbg_enqueue_us = 0, g_dbg_wait_us = 0; static long g_dbg_calls = 0;
+
 int Engine::run_host(const void *inbuf, void *outbuf)
 {
-    BFIR_CUDA(cudaMemcpyAsync(d_in, inbuf, in_bytes, cudaMemcpyHostToDevice, stream));
-    int rc = enqueue_front(d_in);
+    const double t_begin = now_us();
+    int rc = fork();
     if (rc != BFIR_OK) return rc;
-    rc = enqueue_back(d_out);
+    for (int g = 0; g < n_groups; g++) {
+        const Group &grp = groups[g];
+        const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
+        const size_t ioff = s0 * L * Ci * in_sf.bytes, ibytes = ns * L * Ci * in_sf.bytes;
+        BFIR_CUDA(cudaMemcpyAsync((char *)d_in + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, gstream(g)));
+        rc = front_group(g, d_in);
+        if (rc != BFIR_OK) return rc;
+    }
+    for (int g = 0; g < n_groups; g++) {
+        const Group &grp = groups[g];
+        const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
+        const size_t ooff = s0 * L * Co * out_sf.bytes, obytes = ns * L * Co * out_sf.bytes;
+        rc = back_group(g, d_out);
+        if (rc != BFIR_OK) return rc;
+        BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, gstream(g)));
+    }
+    blocks_since_sync++;
+    rc = join();
     if (rc != BFIR_OK) return rc;
-    BFIR_CUDA(cudaMemcpyAsync(outbuf, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
-    return sync_and_probe();
+    const double t_mid = now_us();
+    rc = sync_and_probe();
+    if (getenv("BFIR_DEBUG_TIMING")) {
+        g_dbg_enqueue_us += t_mid - t_begin; g_dbg_wait_us += now_us() - t_mid; g_dbg_calls++;
+        if (g_dbg_calls % 200 == 0) fprintf(stderr, "[bfir] run_host: enqueue %.1f us, wait %.1f us per call (groups %d)\n", g_dbg_enqueue_us / g_dbg_calls, g_dbg_wait_us / g_dbg_calls, n_groups);
+    }
+    return rc;
 }
 
 int Engine::get_overflow(int ch, bfir_overflow_t *out)
 {
-    if (ch < 0 || ch >= Ct || out == nullptr) return BFIR_ERR_INVALID;
+    if (ch < 0 || ch >= Cot || out == nullptr) return BFIR_ERR_INVALID;
     OverflowStats s;
     BFIR_CUDA(cudaStreamSynchronize(stream));
     BFIR_CUDA(cudaMemcpy(&s, stats + ch, sizeof(s), cudaMemcpyDeviceToHost));
@@ -364,7 +566,7 @@ int bfir_create(bfir_engine **out, int filter_length, int filter_blocks, int rea
     memset(&c, 0, sizeof(c));
     c.filter_length = filter_length; c.filter_blocks = filter_blocks; c.realsize = realsize; c.channels = channels;
     c.in_format = in_format; c.out_format = out_format; c.sampling_rate = sampling_rate; c.apply_dither = apply_dither;
-    c.n_streams = 1; c.device = -1; c.part_begin = 0; c.part_count = 0;
+    c.n_streams = 1; c.device = -1; c.part_begin = 0; c.part_count = 0; c.n_groups = 0; c.xbar_inputs = 0; c.xbar_outputs = 0;
     return bfir_create_ex(out, &c);
 }
 
@@ -381,6 +583,7 @@ static int check_ready(bfir_engine *e)
 {
     if (e == nullptr) return BFIR_ERR_INVALID;
     if (!e->impl.initialized) { set_error("run before set_coeff"); return BFIR_ERR_NOT_READY; }
+    if (e->impl.xbar && !e->impl.xbar_set) { set_error("run before set_crossbar"); return BFIR_ERR_NOT_READY; }
     return BFIR_OK;
 }
 
@@ -396,9 +599,7 @@ int bfir_run_device(bfir_engine *e, const void *d_inbuf, void *d_outbuf)
 {
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
-    rc = e->impl.enqueue_front(d_inbuf);
-    if (rc != BFIR_OK) return rc;
-    return e->impl.enqueue_back(d_outbuf);
+    return e->impl.enqueue_block(d_inbuf, d_outbuf);
 }
 
 int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf)
@@ -445,9 +646,9 @@ int bfir_check_overflows(bfir_engine *e)
     // brutefir::check_overflows + print_overflows, brutefir.cpp:371-388, 585-629
     if (e == nullptr) return BFIR_ERR_INVALID;
     Engine &g = e->impl;
-    std::vector<bfir_overflow_t> cur(g.Ct);
+    std::vector<bfir_overflow_t> cur(g.Cot);
     bool changed = false;
-    for (int n = 0; n < g.Ct; n++) {
+    for (int n = 0; n < g.Cot; n++) {
         int rc = g.get_overflow(n, &cur[n]);
         if (rc != BFIR_OK) return rc;
         if (memcmp(&cur[n], &g.last_overflow[n], sizeof(bfir_overflow_t)) != 0) changed = true;
@@ -455,9 +656,9 @@ int bfir_check_overflows(bfir_engine *e)
     if (!changed) return 0;
     g.last_overflow = cur;
     bool any = false;
-    for (int n = 0; n < g.Ct; n++) if (cur[n].n_overflows > 0) { any = true; break; }
+    for (int n = 0; n < g.Cot; n++) if (cur[n].n_overflows > 0) { any = true; break; }
     if (!any) return 0;
-    for (int n = 0; n < g.Ct; n++) {
+    for (int n = 0; n < g.Cot; n++) {
         double peak = cur[n].largest;
         if (peak < (double)cur[n].intlargest) peak = (double)cur[n].intlargest;
         if (peak != 0.0) {
@@ -472,7 +673,7 @@ int bfir_check_overflows(bfir_engine *e)
 
 int bfir_get_dither_ptr(bfir_engine *e, int channel, int *out)
 {
-    if (e == nullptr || out == nullptr || channel < 0 || channel >= e->impl.Ct) return BFIR_ERR_INVALID;
+    if (e == nullptr || out == nullptr || channel < 0 || channel >= e->impl.Cot) return BFIR_ERR_INVALID;
     if (!e->impl.dither_on) { set_error("engine has no dither state"); return BFIR_ERR_INVALID; }
     DitherState s;
     BFIR_CUDA(cudaStreamSynchronize(e->impl.stream));
@@ -490,6 +691,20 @@ int bfir_get_blockcounter(bfir_engine *e, unsigned int *out)
     *out = s.blockcounter;
     return BFIR_OK;
 }
+
+int bfir_set_crossbar(bfir_engine *e, const double *in_gains, const double *out_gains)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.set_crossbar(in_gains, out_gains);
+}
+
+int bfir_set_groups(bfir_engine *e, int n_groups)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.set_groups(n_groups);
+}
+
+int bfir_get_groups(bfir_engine *e) { return e ? e->impl.n_groups : BFIR_ERR_INVALID; }
 
 int bfir_set_stream(bfir_engine *e, void *cuda_stream)
 {

@@ -37,10 +37,9 @@ int rfft_choose_r0(int realsize, int log2m, long long n_buffers)
         const int v = atoi(env);
         if (v == 1 || v == 2) return v;
     }
-    // big transforms leave one CTA per SM (registers / shared memory): two half-size CTAs per buffer
-    // halve the latency as long as the grid still fits the machine in about one wave
-    const int big = realsize == 4 ? 13 : 12;
-    if (log2m >= big && n_buffers <= 2 * 148) return 2;
+    // (measured on B200: the two-CTA split pays off only for the inverse transform of very few large
+    //  double-precision buffers; the forward side reads every input twice and is slower, so the
+    //  automatic choice stays at one CTA unless the size requires two)
     return 1;
 }
 

@@ -27,6 +27,7 @@ struct MacArgs {
     const int *procblocks;   // [channels] blocks seen so far, already counting the current one
     const EngineState *state;
     int block_offset;        // 0: blockcounter is the current block; used by tests
+    int ch_base;             // first channel of this launch (channel-group pipelining)
 };
 
 template <class T> struct vec8 { T v[8]; };
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
     constexpr int GPC = 256 / SPLIT;
     const int slice = threadIdx.x / GPC, gl = threadIdx.x - slice * GPC;
     const int g = blockIdx.x * GPC + gl;
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.y + a.ch_base;
     const bool active = g * 8 < a.N;
     const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
     const int peff = min(a.coeff_blocks[ch], a.procblocks[ch]);           // brutefir.cpp:292

@@ -49,6 +49,7 @@ struct FwdArgs {
     // IN_RAW_PREV
     void *prev;              // [2][n_channels][L] previous block, ping-pong by blockcounter parity
     int fmt, ch_per_stream, n_channels;
+    int ch_base;             // first channel of this launch (channel-group pipelining): bx = blockIdx.x + ch_base
     const EngineState *state; // out slot = blockcounter % n_slots when state != NULL
     int n_slots;
     int *procblocks;         // [channels], brutefir.cpp:265-268
@@ -66,6 +67,7 @@ struct InvArgs {
     void *out;               // OUT_TIME / OUT_REAL_L: reals; OUT_RAW: raw bytes
     long long out_stride_x;  // elements (bytes per stream for OUT_RAW)
     int fmt, ch_per_stream;
+    int ch_base;             // first channel of this launch
     double ovf_max;          // bfoverflow_t.max
     OverflowStats *stats;    // [channels]
     EngineState *state;      // probe + blockcounter++ (engine only)
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__((1 << LOG2MS) / 16) rfft_forward_kernel(const 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
-    const int t = threadIdx.x, bx = blockIdx.x, by = blockIdx.y, r = blockIdx.z;
+    const int t = threadIdx.x, bx = blockIdx.x + a.ch_base, by = blockIdx.y, r = blockIdx.z;
     cpx<T> v[16];
     fwd_load<T, LOG2MS, R0>(t, bx, by, r, v, tw, tw_shift_n, a);
     fft_passes<T, LOG2MS, false, 0, 0>::run(t, v, smem, tw, tw_shift_m);
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__((1 << LOG2MS) / 16) rfft_inverse_kernel(const 
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
-    const int t = threadIdx.x, bx = blockIdx.x, r = blockIdx.z;
+    const int t = threadIdx.x, bx = blockIdx.x + a.ch_base, r = blockIdx.z;
     cpx<T> v[16];
     inv_load<T, LOG2MS, R0>(t, bx, r, v, tw, tw_shift_n, a);
     fft_passes<T, LOG2MS, true, 0, 0>::run(t, v, smem, tw, tw_shift_m);
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__((1 << LOG2MS) / 16) rfft_inverse_kernel(const 
     acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
     inv_store<T, LOG2MS, R0>(t, bx, r, v, a, acc);
     if (a.out_mode == OUT_RAW && a.stats != NULL) overflow_commit(&a.stats[bx], acc);
-    if (a.state != NULL && bx == 0 && t == 0 && r == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
+    if (a.state != NULL && blockIdx.x == 0 && t == 0 && r == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
 }
 #endif
 

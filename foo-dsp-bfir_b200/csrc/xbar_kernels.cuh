@@ -1,0 +1,77 @@
+// Crossbar mixing in the frequency domain: convolver_mixnscale with n_bufs > 1
+// (reference brutefir/fftw_convolver.cpp:215-229, 908-1158, 1187-1421), i.e. a small dense real gain
+// matrix applied to whole spectra:   out[o][j] = sum_i gain[o][i] * in[i][j],  j = 0..N-1.
+//
+// The engine uses it twice per block when a crossbar is configured (BASELINE configs[4], "32x32
+// mixnscale crossbar"): inputs -> filter inputs (into the delay-line slot) and filter outputs ->
+// outputs. Both sides are in ORD layout, so unlike the stand-alone entry point no reordering is
+// involved. The gains are real scalars, so this is n_out*n_in FFMAs per real -- a bandwidth-trivial
+// pass (reads n_in*N, writes n_out*N); tensor cores would need the gains split into several TF32
+// terms to stay inside the 1e-5 budget and buy nothing at these sizes.
+#pragma once
+#include "rfft_kernels.cuh"
+
+namespace bfir {
+
+#define BFIR_MAX_XBAR 64
+
+struct XbarArgs {
+    const void *in;            // [streams * n_in][in_stride] reals
+    void *out;                 // [streams * n_out][out_stride] reals (+ slot * slot_stride when state != NULL)
+    long long in_stride, out_stride, slot_stride;
+    const void *gains;         // device, [n_out][n_in] of T, row-major
+    int n_in, n_out, N, n_streams;
+    const EngineState *state;  // slot = blockcounter % n_slots
+    int n_slots;
+    int *procblocks;           // [streams * n_out]: incremented here for the filter channels (brutefir.cpp:265-268)
+    unsigned char *pb_inc;
+    int stream_base;           // first stream of this launch (channel groups)
+};
+
+#ifdef __CUDACC__
+// grid: (ceil(N / 256), streams), 256 threads; one thread = one real index j of one stream
+template <class T, int MAXI>
+__global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
+{
+    extern __shared__ __align__(16) unsigned char xbar_smem[];
+    T *g = reinterpret_cast<T *>(xbar_smem);
+    for (int k = threadIdx.x; k < a.n_in * a.n_out; k += blockDim.x) g[k] = ((const T *)a.gains)[k];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y + a.stream_base;
+    if (a.procblocks != NULL && blockIdx.x == 0 && threadIdx.x < a.n_out) {
+        const int ch = s * a.n_out + threadIdx.x;
+        const int pb = a.procblocks[ch];
+        const bool inc = pb < a.n_slots;
+        if (inc) a.procblocks[ch] = pb + 1;
+        a.pb_inc[ch] = inc ? 1 : 0;
+    }
+    if (j >= a.N) return;
+    const T *in = (const T *)a.in + (long long)s * a.n_in * a.in_stride + j;
+    T x[MAXI];
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) x[i] = i < a.n_in ? in[(long long)i * a.in_stride] : (T)0;
+    long long off = (long long)s * a.n_out * a.out_stride + j;
+    if (a.state != NULL) off += (long long)(a.state->blockcounter % (unsigned int)a.n_slots) * a.slot_stride;
+    T *out = (T *)a.out + off;
+    for (int o = 0; o < a.n_out; o++) {
+        const T *row = g + o * a.n_in;
+        T acc = (T)0;
+#pragma unroll
+        for (int i = 0; i < MAXI; i++) if (i < a.n_in) acc = fma(row[i], x[i], acc);
+        out[(long long)o * a.out_stride] = acc;
+    }
+}
+
+typedef void (*xbar_kernel_t)(const XbarArgs);
+template <class T> inline xbar_kernel_t xbar_kernel_for(int n_in)
+{
+    if (n_in <= 4) return xbar_mix_kernel<T, 4>;
+    if (n_in <= 8) return xbar_mix_kernel<T, 8>;
+    if (n_in <= 16) return xbar_mix_kernel<T, 16>;
+    if (n_in <= 32) return xbar_mix_kernel<T, 32>;
+    return xbar_mix_kernel<T, 64>;
+}
+#endif
+
+} // namespace bfir

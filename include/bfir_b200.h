@@ -72,7 +72,7 @@ typedef struct bfir_conv bfir_conv;
 
 /* Extended construction parameters. The first eight fields are the reference constructor's
  * (brutefir/brutefir.hpp:18-25); the rest have no reference counterpart and default to
- * {1, -1, 0, 0} through bfir_create. */
+ * {1, -1, 0, 0, 0, 0, 0} through bfir_create. */
 typedef struct bfir_config_t {
     int filter_length;   /* block length L, power of two, 16..16384 (realsize 4) / 16..8192 (realsize 8) */
     int filter_blocks;   /* partitions P >= 1 */
@@ -86,6 +86,12 @@ typedef struct bfir_config_t {
     int device;          /* CUDA device ordinal, -1 = current device */
     int part_begin;      /* partition shard [part_begin, part_begin+part_count) convolved by this engine; */
     int part_count;      /* 0 = all. Sharded engines produce PARTIAL spectra, see bfir_run_partial_device */
+    int n_groups;        /* channel-group pipelining: whole streams are dealt to this many CUDA streams so that
+                            H2D / kernels / D2H of different groups overlap; 0 = choose, 1 = off, max 8 */
+    int xbar_inputs;     /* crossbar (BASELINE configs[4]): > 0 makes `channels` the number of FILTERS per stream; */
+    int xbar_outputs;    /* the raw input has xbar_inputs channels, the raw output xbar_outputs channels, joined
+                            to the filters by the gain matrices of bfir_set_crossbar. 0 / 0 = the reference's
+                            diagonal routing (input n -> filter n -> output n, brutefir.cpp:213-216) */
 } bfir_config_t;
 
 /* brutefir::brutefir (brutefir.cpp:21-44). On failure *out is NULL. */
@@ -102,6 +108,12 @@ int bfir_is_initialized(const bfir_engine *e);
  * n_coeffs is clamped to the channel count (all streams x channels); the arrays are copied.
  * Returns 0 or BFIR_ERR_COEFF (-2) when a scaled coefficient is NaN/Inf. */
 int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
+
+/* Crossbar gains = the `scales[]` of convolver_mixnscale with n_bufs > 1 (fftw_convolver.cpp:215-229):
+ * filter input f = sum_i in_gains[f * xbar_inputs + i] * input i          (MIXMODE_INPUT, n_bufs = inputs)
+ * output o       = sum_f out_gains[o * channels + f] * filter output f    (MIXMODE_OUTPUT, n_bufs = filters)
+ * HOST arrays of doubles, copied. The sample-format scales are applied on top, as in brutefir::run. */
+int bfir_set_crossbar(bfir_engine *e, const double *in_gains, const double *out_gains);
 
 /* brutefir::run (brutefir.cpp:245-343): inbuf/outbuf are HOST buffers holding exactly
  * n_streams * filter_length * channels interleaved samples in in_format / out_format. Synchronous:
@@ -133,6 +145,10 @@ int bfir_get_blockcounter(bfir_engine *e, unsigned int *out);
 int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf);
 int bfir_run_finish_device(bfir_engine *e, void *d_outbuf);
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
+
+/* Change the number of channel groups (see bfir_config_t.n_groups); synchronises the engine. */
+int bfir_set_groups(bfir_engine *e, int n_groups);
+int bfir_get_groups(bfir_engine *e);
 
 /* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the engine's own. */
 int bfir_set_stream(bfir_engine *e, void *cuda_stream);

@@ -207,6 +207,41 @@ def test_streams_batch_equals_separate_engines(pkg, oracle):
             assert rel_rms(out[s], ref.view(np.float32).reshape(L, C)) < 1e-5
 
 
+@pytest.mark.parametrize("out_fmt,dither", [(8, False), (2, True)])
+def test_channel_groups_do_not_change_results(pkg, oracle, out_fmt, dither):
+    """group pipelining (n_groups CUDA streams) is a scheduling choice only: bit-identical output"""
+    import torch
+    L, P, C, S = 256, 4, 2, 7
+    h = [decay_filter(c, L * P) for c in range(C * S)]
+    engines = [pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, out_fmt, 2000, dither, n_streams=S, n_groups=g) for g in (1, 3, 8)]
+    assert [e.get_groups() for e in engines] == [1, 3, 7]
+    for e in engines:
+        assert e.set_coeff(h, P) == 0
+    x = white_noise(11, 9 * L, C * S).astype(np.float32)
+    nb = pkg.FORMAT_BYTES[out_fmt]
+    d_in = torch.empty(S * L * C, dtype=torch.float32, device="cuda")
+    for b in range(9):
+        blk = np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2))
+        outs = []
+        for i, e in enumerate(engines):
+            if b % 2 == 0:
+                rc, out = e.run(blk.view(np.uint8).ravel())
+                assert rc == 0
+            else:                                   # asynchronous device-buffer path
+                d_in.copy_(torch.from_numpy(blk.ravel()))
+                d_out = torch.zeros(S * L * C * nb, dtype=torch.uint8, device="cuda")
+                torch.cuda.synchronize()
+                e.run_device(d_in, d_out)
+                assert e.sync() == 0
+                out = d_out.cpu().numpy()
+            outs.append(out.copy())
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), b
+        if b == 4:                                  # switching the group count mid-stream keeps the state
+            engines[1].set_groups(2)
+    for e in engines:
+        assert e.blockcounter() == 9
+
+
 def test_partition_shards_sum_to_full_filter(pkg, oracle):
     """partition sharding: partial spectra of two shards summed == unsharded engine"""
     import torch

@@ -1,0 +1,107 @@
+"""GPU parity of the crossbar engine (BASELINE configs[4]: "32x32 mixnscale crossbar"): the input
+and output gain matrices are convolver_mixnscale with n_bufs > 1 (reference
+brutefir/fftw_convolver.cpp:215-229) around the per-filter partition sums. The oracle side composes
+the reference's own entry points in the order of brutefir::run."""
+import numpy as np
+import pytest
+
+from conftest import white_noise, decay_filter, rel_rms
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_xbar_run(oracle, L, P, rs, n_in, n_f, n_out, h, gin, gout, x):
+    """x: [blocks*L, n_in] -> y: [blocks*L, n_out] using fftw_convolver entry points only"""
+    cv = oracle.Convolver(L, rs)
+    dt = cv.dtype
+    H = [cv.preprocess_coeff(np.asarray(h[f], dtype=dt), P) for f in range(n_f)]
+    fdl = np.zeros((n_f, P, 2 * L), dtype=dt)
+    prev = np.zeros((n_in, L), dtype=dt)
+    nb = x.shape[0] // L
+    y = np.zeros((nb * L, n_out))
+    for t in range(nb):
+        hcs = []
+        for i in range(n_in):
+            cur = x[t * L:(t + 1) * L, i].astype(dt)
+            hcs.append(cv.time2freq(np.concatenate([prev[i], cur])))
+            prev[i] = cur
+        accs = []
+        for f in range(n_f):
+            fdl[f, t % P] = cv.mixnscale(hcs, list(gin[f]), 1)                  # MIXMODE_INPUT, n_bufs = n_in
+            acc = cv.convolve(fdl[f, t % P].copy(), H[f][0].copy())
+            for i in range(1, min(P, t + 1)):
+                cv.convolve_add(fdl[f, (t - i) % P].copy(), H[f][i].copy(), acc)
+            accs.append(acc)
+        for o in range(n_out):
+            hc = cv.mixnscale(accs, list(gout[o]), 3)                           # MIXMODE_OUTPUT, n_bufs = n_f
+            y[t * L:(t + 1) * L, o] = cv.freq2time(hc)[:L]
+    return y
+
+
+@pytest.mark.parametrize("rs,L,P,n_in,n_f,n_out", [(4, 256, 3, 2, 3, 2), (8, 128, 4, 5, 4, 3), (4, 1024, 2, 32, 32, 32), (8, 64, 2, 1, 6, 2)])
+def test_crossbar_matches_mixnscale_composition(pkg, oracle, rs, L, P, n_in, n_f, n_out):
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt = np.float32 if rs == 4 else np.float64
+    rng = np.random.default_rng(n_in * 100 + n_f)
+    gin = rng.standard_normal((n_f, n_in)) / np.sqrt(n_in)
+    gout = rng.standard_normal((n_out, n_f)) / np.sqrt(n_f)
+    h = [decay_filter(f, L * P) for f in range(n_f)]
+    g = pkg.Brutefir(L, P, rs, n_f, fmt, fmt, 48000, False, xbar_inputs=n_in, xbar_outputs=n_out)
+    assert g.set_coeff(h, P) == 0
+    x = white_noise(21, (2 * P + 1) * L, n_in).astype(dt)
+    with pytest.raises(pkg.BfirError):
+        g.run(np.ascontiguousarray(x[:L]).view(np.uint8).ravel())          # crossbar gains not set yet
+    g.set_crossbar(gin, gout)
+    ys = []
+    for b in range(2 * P + 1):
+        rc, out = g.run(np.ascontiguousarray(x[b * L:(b + 1) * L]).view(np.uint8).ravel())
+        assert rc == 0
+        ys.append(out.view(dt).reshape(L, n_out).copy())
+    y = np.concatenate(ys)
+    ref = oracle_xbar_run(oracle, L, P, rs, n_in, n_f, n_out, h, gin if rs == 8 else gin.astype(np.float32), gout if rs == 8 else gout.astype(np.float32), x)
+    for o in range(n_out):
+        assert rel_rms(y[:, o], ref[:, o]) < (1e-5 if rs == 4 else 1e-12)
+
+
+def test_identity_crossbar_equals_diagonal_engine(pkg):
+    L, P, C = 512, 3, 4
+    h = [decay_filter(c, L * P) for c in range(C)]
+    a = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False)
+    b = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, xbar_inputs=C, xbar_outputs=C)
+    a.set_coeff(h, P); b.set_coeff(h, P)
+    b.set_crossbar(np.eye(C), np.eye(C))
+    x = white_noise(3, 7 * L, C).astype(np.float32)
+    for blk in range(7):
+        raw = np.ascontiguousarray(x[blk * L:(blk + 1) * L]).view(np.uint8).ravel()
+        ya, yb = a.run(raw)[1].view(np.float32), b.run(raw)[1].view(np.float32)
+        assert np.array_equal(ya, yb)          # gain 1.0 / 0.0 FMAs are exact
+
+
+def test_cfg4_shape_impulse_filters_exact(pkg):
+    """BASELINE configs[4] geometry on one GPU at reduced depth: 32 inputs x 32 filters x 32 outputs,
+    L = 32768 (FFT 65536, two-CTA transform), P = 4. Filters are unit impulses at known delays, so the
+    output is a delayed gain-matrix mix of the inputs -- checked without any oracle."""
+    L, P, n = 32768, 4, 32
+    rng = np.random.default_rng(4)
+    delays = rng.integers(0, L * P - 1, n)
+    h = []
+    for f in range(n):
+        v = np.zeros(L * P, dtype=np.float32)
+        v[delays[f]] = 1.0
+        h.append(v)
+    gin = rng.standard_normal((n, n)) / np.sqrt(n)
+    gout = rng.standard_normal((n, n)) / np.sqrt(n)
+    g = pkg.Brutefir(L, P, 4, n, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, xbar_inputs=n, xbar_outputs=n)
+    assert g.set_coeff(h, P) == 0
+    g.set_crossbar(gin, gout)
+    nb = P + 2
+    x = white_noise(8, nb * L, n).astype(np.float32)
+    y = np.concatenate([g.run(np.ascontiguousarray(x[b * L:(b + 1) * L]).view(np.uint8).ravel())[1].view(np.float32).reshape(L, n).copy()
+                        for b in range(nb)])
+    fin = x.astype(np.float64) @ gin.astype(np.float32).astype(np.float64).T          # filter inputs [t, f]
+    fout = np.zeros_like(fin)
+    for f in range(n):
+        d = delays[f]
+        fout[d:, f] = fin[: nb * L - d, f]
+    ref = fout @ gout.astype(np.float32).astype(np.float64).T
+    assert rel_rms(y, ref) < 1e-5
