@@ -62,6 +62,8 @@ API = [
     ("bfir_destroy", None, [_vp]),
     ("bfir_is_initialized", _ci, [_vp]),
     ("bfir_set_coeff", _ci, [_vp, _pp, _ci, _ci, _ci, _cd]),
+    ("bfir_set_coeff_crossfade", _ci, [_vp, _pp, _ci, _ci, _ci, _cd]),
+    ("bfir_set_coeff_device", _ci, [_vp, _vp, ctypes.c_longlong, _ci, _ci, _ci, _cd, _ci]),
     ("bfir_set_crossbar", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(_cd)]),
     ("bfir_run", _ci, [_vp, _vp, _vp]),
     ("bfir_run_device", _ci, [_vp, _vp, _vp]),
@@ -226,6 +228,23 @@ class Brutefir:
         length = (len(arrs[0]) if arrs else 0) if length is None else length
         ptrs = (ctypes.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
         rc = self.lib.bfir_set_coeff(self.h, ptrs, len(arrs), length, coeff_blocks, float(scale))
+        if rc not in (OK, ERR_COEFF):
+            raise BfirError(rc, last_error())
+        return rc
+
+    def set_coeff_crossfade(self, coeffs, coeff_blocks, scale=1.0, length=None):
+        """stage a new coefficient set; the next run() cross-fades old -> new (crossfade_inplace ramp)"""
+        arrs = [np.ascontiguousarray(c, dtype=self.dtype) for c in coeffs]
+        length = len(arrs[0]) if length is None else length
+        ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        rc = self.lib.bfir_set_coeff_crossfade(self.h, ptrs, len(arrs), length, coeff_blocks, float(scale))
+        if rc not in (OK, ERR_COEFF):
+            raise BfirError(rc, last_error())
+        return rc
+
+    def set_coeff_device(self, d_coeffs, channel_stride, n_coeffs, length, coeff_blocks, scale=1.0, crossfade=False):
+        rc = self.lib.bfir_set_coeff_device(self.h, _ptr(d_coeffs), int(channel_stride), n_coeffs, length, coeff_blocks,
+                                            float(scale), int(bool(crossfade)))
         if rc not in (OK, ERR_COEFF):
             raise BfirError(rc, last_error())
         return rc

@@ -108,23 +108,72 @@ __global__ void dirac_kernel(const T *in, T *out, int N)
 // linear old->new ramp of convolver_crossfade_inplace, float branch fftw_convolver.cpp:296-305, used
 // for both precisions (the double branch :306-315 reads memory the function never wrote)
 template <class T>
+__device__ __forceinline__ T crossfade_ramp(T old_v, T new_v, int n, int L)
+{
+    if (sizeof(T) == 4) {
+        const float f = (float)(1.0 / (double)(float)(L - 1));
+        const float fn = __fmul_rn(f, (float)n);
+        const double a = __dmul_rn((double)old_v, __dadd_rn(1.0, -(double)fn));
+        const float b = __fmul_rn(__fmul_rn((float)new_v, f), (float)n);
+        return (T)(float)__dadd_rn(a, (double)b);
+    } else {
+        const double d = 1.0 / (double)(L - 1);
+        const double dn = __dmul_rn(d, (double)n);
+        const double a = __dmul_rn((double)old_v, __dadd_rn(1.0, -dn));
+        const double b = __dmul_rn(__dmul_rn((double)new_v, d), (double)n);
+        return (T)__dadd_rn(a, b);
+    }
+}
+
+template <class T>
 __global__ void crossfade_ramp_kernel(const T *xfade, T *buffer, int L)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= L) return;
-    if (sizeof(T) == 4) {
-        const float f = (float)(1.0 / (double)(float)(L - 1));
-        const float fn = __fmul_rn(f, (float)n);
-        const double a = __dmul_rn((double)xfade[n], __dadd_rn(1.0, -(double)fn));
-        const float b = __fmul_rn(__fmul_rn((float)buffer[n], f), (float)n);
-        buffer[n] = (T)(float)__dadd_rn(a, (double)b);
-    } else {
-        const double d = 1.0 / (double)(L - 1);
-        const double dn = __dmul_rn(d, (double)n);
-        const double a = __dmul_rn((double)xfade[n], __dadd_rn(1.0, -dn));
-        const double b = __dmul_rn(__dmul_rn((double)buffer[n], d), (double)n);
-        buffer[n] = (T)__dadd_rn(a, b);
+    buffer[n] = crossfade_ramp<T>(xfade[n], buffer[n], n, L);
+}
+
+// Engine-side filter swap (BASELINE configs[2]): the block is computed with the old and the new
+// coefficient set, both accumulated spectra are brought to the time domain, and the first L samples are
+// the linear old->new ramp of convolver_crossfade_inplace (fftw_convolver.cpp:296-305). This kernel is
+// the ramp fused with the output stage (probe + cbuf2raw); the re-FFT of crossfade_inplace (:317-320)
+// is skipped because the consumer is the output stage.
+struct XfadeArgs {
+    const void *t_old, *t_new;   // [channels][N] time-domain outputs of the old / new filter
+    void *out;                   // raw interleaved output, or planar reals [channels][L] for the dither kernel
+    long long out_stream_stride; // bytes
+    int N, L, fmt, ch_per_stream, ch_base, to_real;
+    double ovf_max;
+    OverflowStats *stats;
+    EngineState *state;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) xfade_emit_kernel(const XfadeArgs a)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y + a.ch_base;
+    OverflowAcc acc;
+    acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
+    if (n < a.L) {
+        const T y = crossfade_ramp<T>(((const T *)a.t_old)[(long long)ch * a.N + n], ((const T *)a.t_new)[(long long)ch * a.N + n], n, a.L);
+        if (n == 0 && !(y - y == (T)0)) atomicMin(&a.state->first_bad_channel, ch);     // brutefir.cpp:316-321
+        if (a.to_real) {
+            ((T *)a.out)[(long long)ch * a.L + n] = y;
+        } else {
+            const int stream = ch / a.ch_per_stream, c = ch - stream * a.ch_per_stream;
+            const int bytes = fmt_bytes(a.fmt);
+            uint8_t *p = (uint8_t *)a.out + (long long)stream * a.out_stream_stride + ((long long)n * a.ch_per_stream + c) * bytes;
+            if (fmt_isfloat(a.fmt)) store_raw_float<T>(p, a.fmt, y, (T)a.ovf_max, acc);
+            else {
+                int32_t imin, imax;
+                int_limits(a.fmt, imin, imax);
+                store_raw_quantised<T>(p, a.fmt, y, (T)imin, (T)imax, imin, imax, acc);
+            }
+        }
     }
+    if (!a.to_real) overflow_commit(&a.stats[ch], acc);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.state->blockcounter += 1u;
 }
 
 // convolver_raw2cbuf, fftw_convolver.cpp:157-185: L strided raw samples -> next_cbuf[0..L) and cbuf[L..2L)

@@ -21,6 +21,9 @@ struct Engine {
     int Ci = 0, Co = 0, Cit = 0, Cot = 0;
     bool xbar = false, xbar_set = false;
     void *xin = nullptr, *yacc = nullptr, *gains_in = nullptr, *gains_out = nullptr;
+    // filter swap with crossfade (configs[2]): staged coefficient set, second accumulator, two time buffers
+    void *coeffs_next = nullptr, *acc2 = nullptr, *tbuf = nullptr;
+    bool xfade_pending = false;
     int part_begin = 0, part_count = 0;
     SampleFormat in_sf, out_sf;
     bool dither_on = false, initialized = false, own_stream = true;
@@ -60,6 +63,8 @@ struct Engine {
     int init(const bfir_config_t &c);
     void destroy();
     int set_coeff(const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
+    int load_coeff(const void *const *h_coeffs, const void *d_src, long long d_stride, int n_coeffs, int length, int blocks, double scale, bool next);
+    void finish_block();
     int set_crossbar(const double *in_gains, const double *out_gains);
     int set_groups(int n);
     cudaStream_t gstream(int g) const { return n_groups == 1 ? stream : groups[g].stream; }
@@ -205,9 +210,9 @@ void Engine::destroy()
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
     if (stream && own_stream) cudaStreamDestroy(stream);
     stream = nullptr;
-    void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out };
+    void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
-    fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = nullptr;
+    fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
     state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
     h_state = nullptr;
@@ -228,54 +233,87 @@ int Engine::reset()
 
 int Engine::set_coeff(const void *const *h_coeffs, int n_coeffs, int length, int blocks, double scale)
 {
-    // brutefir::set_coeff, brutefir.cpp:180-228 -> coeff::preprocess_coeff, coeff.cpp:293-354
-    //   -> convolver_coeffs2cbuf, fftw_convolver.cpp:475-537, for every (channel, partition) in ONE launch
-    if (h_coeffs == nullptr || blocks < 1 || length < 0) { set_error("invalid coefficient arguments"); return BFIR_ERR_INVALID; }
+    return load_coeff(h_coeffs, nullptr, 0, n_coeffs, length, blocks, scale, false);
+}
+
+// brutefir::set_coeff, brutefir.cpp:180-228 -> coeff::preprocess_coeff, coeff.cpp:293-354
+//   -> convolver_coeffs2cbuf, fftw_convolver.cpp:475-537, for every (channel, partition) in ONE launch.
+// Source: planar HOST arrays (h_coeffs[n]) or one planar DEVICE array (d_src + n * d_stride elements;
+// stride 0 = the same filter for every channel, as the equalizer produces). next = true stages the set
+// for a cross-faded swap on the following block instead of replacing the current one.
+int Engine::load_coeff(const void *const *h_coeffs, const void *d_src, long long d_stride, int n_coeffs, int length, int blocks, double scale, bool next)
+{
+    if ((h_coeffs == nullptr && d_src == nullptr) || blocks < 1 || length < 0) { set_error("invalid coefficient arguments"); return BFIR_ERR_INVALID; }
     BFIR_CUDA(cudaSetDevice(device));
     BFIR_CUDA(cudaStreamSynchronize(stream));
-    initialized = false;                                   // free_coeff(), brutefir.cpp:189
-    if (coeffs) { cudaFree(coeffs); coeffs = nullptr; }
-    BFIR_CUDA(cudaMemsetAsync(coeff_blocks, 0, sizeof(int) * Ct, stream));
     if (n_coeffs > Ct) n_coeffs = Ct;                     // brutefir.cpp:191-194
-    if (n_coeffs < 1) return BFIR_OK;
     const size_t cbuf = (size_t)N * rs;
-    coeff_alloc = blocks;
-    BFIR_CUDA(cudaMalloc(&coeffs, cbuf * blocks * Ct));
-    BFIR_CUDA(cudaMemsetAsync(coeffs, 0, cbuf * blocks * Ct, stream));
-    // stage the planar host arrays
+    void *target = nullptr;
+    if (next) {
+        if (!initialized || blocks != coeff_alloc || n_coeffs != Ct) { set_error("crossfade swap needs an initialised engine and the same filter geometry"); return BFIR_ERR_INVALID; }
+        if (xbar || part_count != P) { set_error("crossfade swap is not available with a crossbar or a partition shard"); return BFIR_ERR_INVALID; }
+        if (!coeffs_next) BFIR_CUDA(cudaMalloc(&coeffs_next, cbuf * blocks * Ct));
+        if (!acc2) BFIR_CUDA(cudaMalloc(&acc2, cbuf * Ct));
+        if (!tbuf) BFIR_CUDA(cudaMalloc(&tbuf, 2 * cbuf * Ct));
+        target = coeffs_next;
+    } else {
+        initialized = false;                               // free_coeff(), brutefir.cpp:189
+        xfade_pending = false;
+        if (coeffs) { cudaFree(coeffs); coeffs = nullptr; }
+        if (coeffs_next) { cudaFree(coeffs_next); coeffs_next = nullptr; }
+        BFIR_CUDA(cudaMemsetAsync(coeff_blocks, 0, sizeof(int) * Ct, stream));
+        if (n_coeffs < 1) return BFIR_OK;
+        coeff_alloc = blocks;
+        BFIR_CUDA(cudaMalloc(&coeffs, cbuf * blocks * Ct));
+        target = coeffs;
+    }
+    BFIR_CUDA(cudaMemsetAsync(target, 0, cbuf * blocks * Ct, stream));
     void *d_planar = nullptr;
-    const size_t row = (size_t)(length > 0 ? length : 1) * rs;
-    BFIR_CUDA(cudaMalloc(&d_planar, row * n_coeffs));
-    for (int n = 0; n < n_coeffs; n++) {
-        if (h_coeffs[n] == nullptr) { cudaFree(d_planar); set_error("coefficient array %d is NULL", n); return BFIR_ERR_INVALID; }
-        if (length > 0) BFIR_CUDA(cudaMemcpyAsync((char *)d_planar + row * n, h_coeffs[n], (size_t)length * rs, cudaMemcpyHostToDevice, stream));
+    long long stride = d_stride;
+    if (d_src == nullptr) {                                // stage the planar host arrays
+        const size_t row = (size_t)(length > 0 ? length : 1) * rs;
+        BFIR_CUDA(cudaMalloc(&d_planar, row * n_coeffs));
+        for (int n = 0; n < n_coeffs; n++) {
+            if (h_coeffs[n] == nullptr) { cudaFree(d_planar); set_error("coefficient array %d is NULL", n); return BFIR_ERR_INVALID; }
+            if (length > 0) BFIR_CUDA(cudaMemcpyAsync((char *)d_planar + row * n, h_coeffs[n], (size_t)length * rs, cudaMemcpyHostToDevice, stream));
+        }
+        stride = (long long)(length > 0 ? length : 1);
     }
     BFIR_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int), stream));
     FwdArgs a = {};
     a.in_mode = IN_COEFF; a.out_layout = LAYOUT_ORD;
-    a.in = d_planar; a.in_stride_x = (long long)(length > 0 ? length : 1); a.in_stride_y = 0;
-    a.out = coeffs; a.out_stride_x = (long long)blocks * N; a.out_stride_y = N;
+    a.in = d_src ? d_src : d_planar; a.in_stride_x = stride; a.in_stride_y = 0;
+    a.out = target; a.out_stride_x = (long long)blocks * N; a.out_stride_y = N;
     a.scale_in = scale; a.scale_out = 1.0 / (double)N;     // fftw_convolver.cpp:520
     a.coeff_len = length; a.nonfinite = nonfinite;
     cudaError_t e = launch_rfft_forward(rs, log2m, rfft_choose_r0(rs, log2m, (long long)n_coeffs * blocks), dim3(n_coeffs, blocks), stream, a, tw);
     count_launch();
-    if (e != cudaSuccess) { cudaFree(d_planar); set_error("coefficient transform launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
-    std::vector<int> hb(Ct, 0);
-    for (int n = 0; n < n_coeffs; n++) hb[n] = blocks;     // brutefir.cpp:213
+    if (e != cudaSuccess) { if (d_planar) cudaFree(d_planar); set_error("coefficient transform launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
     int bad = 0;
-    BFIR_CUDA(cudaMemcpyAsync(coeff_blocks, hb.data(), sizeof(int) * Ct, cudaMemcpyHostToDevice, stream));
+    if (!next) {
+        std::vector<int> hb(Ct, 0);
+        for (int n = 0; n < n_coeffs; n++) hb[n] = blocks; // brutefir.cpp:213
+        BFIR_CUDA(cudaMemcpyAsync(coeff_blocks, hb.data(), sizeof(int) * Ct, cudaMemcpyHostToDevice, stream));
+    }
     BFIR_CUDA(cudaMemcpyAsync(&bad, nonfinite, sizeof(int), cudaMemcpyDeviceToHost, stream));
     BFIR_CUDA(cudaStreamSynchronize(stream));
-    cudaFree(d_planar);
+    if (d_planar) cudaFree(d_planar);
     if (bad) {                                             // brutefir.cpp:207-224
         pinfo("NaN or Inf value among coefficients.\n");
-        cudaFree(coeffs); coeffs = nullptr;
-        cudaMemset(coeff_blocks, 0, sizeof(int) * Ct);
         set_error("NaN or Inf value among coefficients.");
+        if (!next) { cudaFree(coeffs); coeffs = nullptr; cudaMemset(coeff_blocks, 0, sizeof(int) * Ct); }
         return BFIR_ERR_COEFF;
     }
-    initialized = true;                                    // brutefir.cpp:226
+    if (next) xfade_pending = true;
+    else initialized = true;                               // brutefir.cpp:226
     return BFIR_OK;
+}
+
+// after a block has been enqueued: a staged coefficient set becomes the current one
+void Engine::finish_block()
+{
+    if (xfade_pending) { void *t = coeffs; coeffs = coeffs_next; coeffs_next = t; xfade_pending = false; }
+    blocks_since_sync++;
 }
 
 int Engine::set_crossbar(const double *in_gains, const double *out_gains)
@@ -379,6 +417,11 @@ int Engine::front_group(int g, const void *d_inbuf)
     dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), nch);
     mac_kernel_t mk = rs == 4 ? mac_kernel_for_split<float>(mac_split) : mac_kernel_for_split<double>(mac_split);
     mk<<<grid, 256, 0, st>>>(m);
+    if (xfade_pending) {                                                // same block through the staged filters
+        m.coeffs = coeffs_next; m.acc = acc2;
+        mk<<<grid, 256, 0, st>>>(m);
+        count_launch();
+    }
     if (g == 0) prof(2);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
@@ -402,15 +445,37 @@ int Engine::back_group(int g, void *d_outbuf)
         count_launch();
         BFIR_CUDA(cudaGetLastError());
     }
+    if (xfade_pending) { // old and new filter outputs -> time domain -> linear ramp fused with the output stage
+        InvArgs t = {};
+        t.in_layout = LAYOUT_ORD; t.in_stride_x = N; t.scale_in = out_sf.scale; t.out_mode = OUT_TIME; t.out_stride_x = N; t.ch_base = c0;
+        for (int k = 0; k < 2; k++) {
+            t.in = k == 0 ? acc : acc2;
+            t.out = (char *)tbuf + (size_t)k * N * rs * Ct;
+            cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(nch, 1), st, t, tw);
+            count_launch();
+            if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+        }
+        XfadeArgs x = {};
+        x.t_old = tbuf; x.t_new = (char *)tbuf + (size_t)N * rs * Ct;
+        x.out = dither_on ? ybuf : d_outbuf; x.out_stream_stride = (long long)L * Co * out_sf.bytes;
+        x.N = N; x.L = L; x.fmt = out_sf.format; x.ch_per_stream = Co; x.ch_base = c0; x.to_real = dither_on ? 1 : 0;
+        x.ovf_max = ovf_max; x.stats = stats; x.state = state + g;
+        if (rs == 4) xfade_emit_kernel<float><<<dim3((L + 255) / 256, nch), 256, 0, st>>>(x);
+        else xfade_emit_kernel<double><<<dim3((L + 255) / 256, nch), 256, 0, st>>>(x);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+    }
     InvArgs v = {};
     v.in_layout = LAYOUT_ORD; v.in = xbar ? yacc : acc; v.in_stride_x = N;
     v.scale_in = out_sf.scale;                                         // brutefir.cpp:303-307
     v.fmt = out_sf.format; v.ch_per_stream = Co; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.ch_base = c0;
     if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }
     else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * Co * out_sf.bytes; }
-    cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(nch, 1), st, v, tw);
-    count_launch();
-    if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    if (!xfade_pending) {
+        cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(nch, 1), st, v, tw);
+        count_launch();
+        if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    }
     if (dither_on) {
         DitherArgs d = {};
         d.real = ybuf; d.real_stride = L; d.raw = d_outbuf; d.raw_stream_stride = (long long)L * Co * out_sf.bytes;
@@ -440,7 +505,7 @@ int Engine::enqueue_back(void *d_outbuf)
     int rc = fork();
     for (int g = 0; g < n_groups && rc == BFIR_OK; g++) rc = back_group(g, d_outbuf);
     if (rc == BFIR_OK) rc = join();
-    blocks_since_sync++;
+    finish_block();
     return rc;
 }
 
@@ -453,7 +518,7 @@ int Engine::enqueue_block(const void *d_inbuf, void *d_outbuf)
         if (rc == BFIR_OK) rc = back_group(g, d_outbuf);
     }
     if (rc == BFIR_OK) rc = join();
-    blocks_since_sync++;
+    finish_block();
     return rc;
 }
 
@@ -510,7 +575,7 @@ int Engine::run_host(const void *inbuf, void *outbuf)
         if (rc != BFIR_OK) return rc;
         BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, gstream(g)));
     }
-    blocks_since_sync++;
+    finish_block();
     rc = join();
     if (rc != BFIR_OK) return rc;
     const double t_mid = now_us();
@@ -577,6 +642,19 @@ int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int 
 {
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.set_coeff(coeffs, n_coeffs, length, coeff_blocks, scale);
+}
+
+int bfir_set_coeff_crossfade(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.load_coeff(coeffs, nullptr, 0, n_coeffs, length, coeff_blocks, scale, true);
+}
+
+int bfir_set_coeff_device(bfir_engine *e, const void *d_coeffs, long long channel_stride, int n_coeffs, int length,
+                          int coeff_blocks, double scale, int crossfade)
+{
+    if (e == nullptr || d_coeffs == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.load_coeff(nullptr, d_coeffs, channel_stride, n_coeffs, length, coeff_blocks, scale, crossfade != 0);
 }
 
 static int check_ready(bfir_engine *e)

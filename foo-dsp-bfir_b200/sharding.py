@@ -65,7 +65,7 @@ class PartitionShardedEngine:
 
 def make_partition_sharded(pkg, filter_length, filter_blocks, realsize, channels, in_format, out_format,
                            sampling_rate, apply_dither, coeffs, coeff_blocks=None, scale=1.0, n_streams=1,
-                           device=-1, group=None):
+                           device=-1, group=None, xbar_inputs=0, xbar_outputs=0, in_gains=None, out_gains=None):
     """Build this rank's shard of a partition-sharded CUDA engine and its driver (NCCL).
 
     Every rank passes the FULL coefficient arrays; the shard convolves only its partitions. The engine
@@ -78,7 +78,10 @@ def make_partition_sharded(pkg, filter_length, filter_blocks, realsize, channels
     if count == 0:
         raise ValueError("more ranks than partitions: %d > %d" % (world, filter_blocks))
     eng = pkg.Brutefir(filter_length, filter_blocks, realsize, channels, in_format, out_format, sampling_rate,
-                       apply_dither, n_streams=n_streams, device=device, part_begin=begin, part_count=count)
+                       apply_dither, n_streams=n_streams, device=device, part_begin=begin, part_count=count,
+                       n_groups=1, xbar_inputs=xbar_inputs, xbar_outputs=xbar_outputs)
+    if xbar_inputs or xbar_outputs:
+        eng.set_crossbar(in_gains, out_gains)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     rc = eng.set_coeff(coeffs, filter_blocks if coeff_blocks is None else coeff_blocks, scale)
     if rc != 0:

@@ -109,6 +109,16 @@ int bfir_is_initialized(const bfir_engine *e);
  * Returns 0 or BFIR_ERR_COEFF (-2) when a scaled coefficient is NaN/Inf. */
 int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
 
+/* Runtime filter swap (BASELINE configs[2]; the reference has convolver_crossfade_inplace,
+ * fftw_convolver.cpp:276-321, but no caller): stages a new coefficient set of the SAME geometry; the
+ * next block is computed with the old and the new set and cross-faded old->new with the linear ramp of
+ * crossfade_inplace (:296-305), after which the new set is current. */
+int bfir_set_coeff_crossfade(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
+/* Coefficients already on the device (e.g. rendered by bfir_equalizer_render_device): planar, channel n at
+ * d_coeffs + n * channel_stride elements (stride 0 = one filter shared by all channels). */
+int bfir_set_coeff_device(bfir_engine *e, const void *d_coeffs, long long channel_stride, int n_coeffs, int length,
+                          int coeff_blocks, double scale, int crossfade);
+
 /* Crossbar gains = the `scales[]` of convolver_mixnscale with n_bufs > 1 (fftw_convolver.cpp:215-229):
  * filter input f = sum_i in_gains[f * xbar_inputs + i] * input i          (MIXMODE_INPUT, n_bufs = inputs)
  * output o       = sum_f out_gains[o * channels + f] * filter output f    (MIXMODE_OUTPUT, n_bufs = filters)

@@ -271,3 +271,49 @@ def test_partition_shards_sum_to_full_filter(pkg, oracle):
         b.run_finish_device(outs[2])               # keeps shard b's block counter in step
         assert a.sync() == 0 and b.sync() == 0
         assert rel_rms(outs[1].cpu().numpy(), outs[0].cpu().numpy()) < 1e-6, blk
+
+
+@pytest.mark.parametrize("rs,L,P,C", [(4, 256, 4, 2), (8, 128, 3, 2), (4, 4096, 2, 2)])
+def test_crossfade_filter_swap_every_block(pkg, oracle, rs, L, P, C):
+    """BASELINE configs[2]: a new coefficient set every block, output = crossfade_inplace(old, new).
+    Oracle = the reference's entry points composed in run() order, with convolver_crossfade_inplace
+    (fftw_convolver.cpp:276-321; float-branch algorithm for double) between the
+    partition sums and the output stage."""
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt = np.float32 if rs == 4 else np.float64
+    cv = oracle.Convolver(L, rs, kind="port" if rs == 8 else None)
+    nb = 2 * P + 3
+    filters = [[decay_filter(100 * b + c, L * P) for c in range(C)] for b in range(nb + 1)]
+    g = pkg.Brutefir(L, P, rs, C, fmt, fmt, 96000, False)
+    assert g.set_coeff(filters[0], P) == 0
+    H = [[cv.preprocess_coeff(np.asarray(f, dtype=dt), P) for f in fs] for fs in filters]
+    fdl = np.zeros((C, P, 2 * L), dtype=dt)
+    prev = np.zeros((C, L), dtype=dt)
+    x = white_noise(33, nb * L, C).astype(dt)
+
+    def psum(c, t, Hc):
+        acc = cv.convolve(fdl[c, t % P].copy(), Hc[0].copy())
+        for i in range(1, min(P, t + 1)):
+            cv.convolve_add(fdl[c, (t - i) % P].copy(), Hc[i].copy(), acc)
+        return acc
+
+    for t in range(nb):
+        swap = t >= 1                                  # first block plain, then a swap on every block
+        if swap:
+            assert g.set_coeff_crossfade(filters[t], P) == 0
+        blk = np.ascontiguousarray(x[t * L:(t + 1) * L])
+        rc, out = g.run(blk.view(np.uint8).ravel())
+        assert rc == 0
+        y = out.view(dt).reshape(L, C)
+        for c in range(C):
+            fdl[c, t % P] = cv.mixnscale([cv.time2freq(np.concatenate([prev[c], blk[:, c]]))], [1.0], 1)
+            prev[c] = blk[:, c]
+            if swap:
+                spec = cv.crossfade_inplace(psum(c, t, H[t][c]), psum(c, t, H[t - 1][c]), cv.cbuf())
+            else:
+                spec = psum(c, t, H[0][c])
+            ref = cv.freq2time(cv.mixnscale([spec], [1.0], 3))[:L]
+            assert rel_rms(y[:, c], ref) < (2e-5 if rs == 4 else 1e-12), (t, c)
+    # a swap needs the same geometry and an initialised engine
+    with pytest.raises(pkg.BfirError):
+        g.set_coeff_crossfade(filters[0], P + 1)

@@ -9,12 +9,13 @@ import pytest
 from conftest import ROOT
 
 SRC = os.path.join(ROOT, "tests", "host_cpp", "host_mirror_test.cpp")
+SRC_TOOLS = os.path.join(ROOT, "tests", "host_cpp", "host_tools_test.cpp")
 LIBDIR = os.path.join(ROOT, "foo-dsp-bfir_b200")
 
 
-def build(tmp_path):
-    exe = str(tmp_path / "host_mirror_test")
-    r = subprocess.run(["g++", "-std=c++11", "-O1", SRC, "-o", exe, "-L" + LIBDIR, "-lbfir_b200",
+def build(tmp_path, src=SRC):
+    exe = str(tmp_path / os.path.basename(src).replace(".cpp", ""))
+    r = subprocess.run(["g++", "-std=c++11", "-O1", src, "-o", exe, "-L" + LIBDIR, "-lbfir_b200",
                         "-Wl,-rpath," + LIBDIR], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return exe
@@ -32,4 +33,18 @@ def test_host_mirror_refuses_without_device(tmp_path):
 @pytest.mark.gpu
 def test_host_mirror_filters_audio(tmp_path):
     r = subprocess.run([build(tmp_path), "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not found")
+def test_plugin_adapter_pass_through_without_filter(tmp_path):
+    """dsp_bfir::on_chunk contract (foo_dsp_bfir.cpp:352-357): no filter -> chunk passes through"""
+    r = subprocess.run([build(tmp_path, SRC_TOOLS)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_plugin_adapter_and_offline_tools(tmp_path):
+    """next rows N2 (dsp_impl_base framing) and N3 (convolve_impulses, calculate_attenuation) on the GPU engine"""
+    r = subprocess.run([build(tmp_path, SRC_TOOLS), "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
