@@ -110,6 +110,11 @@ API = [
     ("bfir_conv_dither_table", _ci, [_vp, _vp, _ci]),
     ("bfir_conv_dither_map", _ci, [_vp, _vp]),
     ("bfir_conv_dither_ptr", _ci, [_vp, _ci]),
+    ("bfir_eq_create", _ci, [_pp, _ci, _ci, _ci, _ci]),
+    ("bfir_eq_destroy", None, [_vp]),
+    ("bfir_eq_taps", _ci, [_vp]),
+    ("bfir_eq_render", _ci, [_vp, _ci, ctypes.POINTER(_cd), ctypes.POINTER(_cd), ctypes.POINTER(_cd), _vp]),
+    ("bfir_eq_render_device", _vp, [_vp, _ci, ctypes.POINTER(_cd), ctypes.POINTER(_cd), ctypes.POINTER(_cd)]),
 ]
 
 _lib = None
@@ -476,3 +481,45 @@ class FftwConvolver:
 
     def dither_ptr(self, channel):
         return _check(self.lib.bfir_conv_dither_ptr(self.h, channel))
+
+
+class Equalizer:
+    """``class equalizer`` (reference brutefir/equalizer.hpp:66-115) on the GPU, without the WAV cache."""
+
+    def __init__(self, block_length, n_blocks, realsize, sampling_rate):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p()
+        rc = self.lib.bfir_eq_create(ctypes.byref(self.h), block_length, n_blocks, realsize, sampling_rate)
+        if rc != OK:
+            self.h = ctypes.c_void_p()
+            raise BfirError(rc, last_error())
+        self.taps = self.lib.bfir_eq_taps(self.h)
+        self.realsize, self.dtype = realsize, real_dtype(realsize)
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.bfir_eq_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _arr(v):
+        return (ctypes.c_double * len(v))(*[float(x) for x in v])
+
+    def generate(self, freq, mag, phase):
+        """equalizer::generate: returns the taps/2-sample filter (host array)."""
+        out = np.empty(self.taps // 2, dtype=self.dtype)
+        _check(self.lib.bfir_eq_render(self.h, len(freq), self._arr(freq), self._arr(mag), self._arr(phase), _ptr(out)))
+        return out
+
+    def generate_device(self, freq, mag, phase):
+        """same, but returns the device pointer of the rendered filter (for Brutefir.set_coeff_device)"""
+        p = self.lib.bfir_eq_render_device(self.h, len(freq), self._arr(freq), self._arr(mag), self._arr(phase))
+        if not p:
+            raise BfirError(ERR_CUDA, last_error())
+        return p

@@ -6,7 +6,8 @@ namespace bfir {
 
 #define BFIR_DECL(tag, m)                                                                                      \
     cudaError_t launch_fwd_##tag##_m##m(int, dim3, cudaStream_t, const FwdArgs &, const void *, int, int);     \
-    cudaError_t launch_inv_##tag##_m##m(int, dim3, cudaStream_t, const InvArgs &, const void *, int, int);
+    cudaError_t launch_inv_##tag##_m##m(int, dim3, cudaStream_t, const InvArgs &, const void *, int, int);     \
+    cudaError_t launch_cfft_inv_##tag##_m##m(int, cudaStream_t, const CfftArgs &);
 #define BFIR_FOR_F32(X) X(f32, 4) X(f32, 5) X(f32, 6) X(f32, 7) X(f32, 8) X(f32, 9) X(f32, 10) X(f32, 11) X(f32, 12) X(f32, 13) X(f32, 14)
 #define BFIR_FOR_F64(X) X(f64, 4) X(f64, 5) X(f64, 6) X(f64, 7) X(f64, 8) X(f64, 9) X(f64, 10) X(f64, 11) X(f64, 12) X(f64, 13)
 BFIR_FOR_F32(BFIR_DECL)
@@ -19,6 +20,9 @@ static const int kMinLog2M = 4, kMaxLog2M_f32 = 14, kMaxLog2M_f64 = 13;
 static const fwd_launcher_t kFwdF32[] = { BFIR_FOR_F32(BFIR_FWD_ENTRY) };
 static const inv_launcher_t kInvF32[] = { BFIR_FOR_F32(BFIR_INV_ENTRY) };
 static const fwd_launcher_t kFwdF64[] = { BFIR_FOR_F64(BFIR_FWD_ENTRY) };
+#define BFIR_CFFT_ENTRY(tag, m) launch_cfft_inv_##tag##_m##m,
+static const cfft_launcher_t kCfftF32[] = { BFIR_FOR_F32(BFIR_CFFT_ENTRY) };
+static const cfft_launcher_t kCfftF64[] = { BFIR_FOR_F64(BFIR_CFFT_ENTRY) };
 static const inv_launcher_t kInvF64[] = { BFIR_FOR_F64(BFIR_INV_ENTRY) };
 
 static int max_sub(int realsize) { return realsize == 4 ? kMaxLog2M_f32 : kMaxLog2M_f64; }
@@ -41,6 +45,14 @@ int rfft_choose_r0(int realsize, int log2m, long long n_buffers)
     //  double-precision buffers; the forward side reads every input twice and is slower, so the
     //  automatic choice stays at one CTA unless the size requires two)
     return 1;
+}
+
+int cfft_max_log2m(int realsize) { return max_sub(realsize); }
+
+cudaError_t launch_cfft_inverse(int realsize, int log2m, int batch, cudaStream_t stream, const CfftArgs &a)
+{
+    if ((realsize != 4 && realsize != 8) || log2m < kMinLog2M || log2m > max_sub(realsize) || batch < 1) return cudaErrorInvalidValue;
+    return (realsize == 4 ? kCfftF32 : kCfftF64)[log2m - kMinLog2M](batch, stream, a);
 }
 
 cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw)

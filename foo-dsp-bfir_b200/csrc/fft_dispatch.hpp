@@ -3,6 +3,7 @@
 // -DBFIR_FFT_LOG2M) so the build parallelises.
 #pragma once
 #include "rfft_kernels.cuh"
+#include "eq_kernels.cuh"
 
 namespace bfir {
 
@@ -17,6 +18,11 @@ int rfft_choose_r0(int realsize, int log2m, long long n_buffers);
 // tw = table exp(-2 pi i j / N), N = 2 * 2^log2m.
 cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw);
 cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw);
+
+// batched inverse complex transform of 2^log2m points (4 <= log2m <= 14 float / 13 double), grid = batch
+cudaError_t launch_cfft_inverse(int realsize, int log2m, int batch, cudaStream_t stream, const CfftArgs &a);
+int cfft_max_log2m(int realsize);
+typedef cudaError_t (*cfft_launcher_t)(int, cudaStream_t, const CfftArgs &);
 
 typedef cudaError_t (*fwd_launcher_t)(int, dim3, cudaStream_t, const FwdArgs &, const void *, int, int);
 typedef cudaError_t (*inv_launcher_t)(int, dim3, cudaStream_t, const InvArgs &, const void *, int, int);

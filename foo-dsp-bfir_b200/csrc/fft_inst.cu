@@ -1,6 +1,7 @@
 // One (precision, size) instantiation of the real-FFT kernels; see fft_dispatch.hpp.
 // Compile with -DBFIR_FFT_REAL=float|double -DBFIR_FFT_TAG=f32|f64 -DBFIR_FFT_LOG2M=<4..14>.
 #include "fft_dispatch.hpp"
+#include "eq_kernels.cuh"
 
 #define BFIR_CAT_(a, b, c, d) a##b##_##c##d
 #define BFIR_CAT(a, b, c, d) BFIR_CAT_(a, b, c, d)
@@ -51,6 +52,20 @@ cudaError_t BFIR_CAT(launch_fwd_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int r0, dim3 
 cudaError_t BFIR_CAT(launch_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int r0, dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw, int sm, int sn)
 {
     return r0 == 2 ? launch_inv<2>(grid, stream, a, tw, sm, sn) : launch_inv<1>(grid, stream, a, tw, sm, sn);
+}
+
+// inverse complex transform of 2^kLog2M points with strided access (four-step building block)
+cudaError_t BFIR_CAT(launch_cfft_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int batch, cudaStream_t stream, const CfftArgs &a)
+{
+    static bool configured = false;
+    auto kernel = cfft_strided_kernel<real_t, kLog2M, true>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kernel<<<batch, kM / 16, kSmem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 } // namespace bfir

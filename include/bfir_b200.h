@@ -65,6 +65,7 @@ typedef struct bfir_overflow_t {
 
 typedef struct bfir_engine bfir_engine;
 typedef struct bfir_conv bfir_conv;
+typedef struct bfir_eq bfir_eq;
 
 /* ------------------------------------------------------------------------------------------------
  * ENGINE -- class brutefir
@@ -233,6 +234,21 @@ int bfir_conv_dither_table_size(bfir_conv *c);
 int bfir_conv_dither_table(bfir_conv *c, int8_t *h_out, int n);
 int bfir_conv_dither_map(bfir_conv *c, void *h_out);
 int bfir_conv_dither_ptr(bfir_conv *c, int channel);
+
+/* ------------------------------------------------------------------------------------------------
+ * EQUALIZER -- class equalizer (brutefir/equalizer.hpp:66-115): 31-band ISO 1/3-octave magnitude/phase
+ * -> linear-phase FIR of taps/2 samples, taps = block_length * n_blocks (a power of two, 32 .. 2^28),
+ * identical for every channel. generate() (equalizer.cpp:87-140) + render_f/d (:212-394) run on the
+ * device; the reference's WAV cache is out of scope.
+ * ---------------------------------------------------------------------------------------------- */
+int bfir_eq_create(bfir_eq **out, int block_length, int n_blocks, int realsize, int sampling_rate);
+void bfir_eq_destroy(bfir_eq *q);
+int bfir_eq_taps(const bfir_eq *q);
+/* n_bands <= 31 (freq ascending, mag in dB, phase as the reference takes it); h_out = taps/2 samples of realsize */
+int bfir_eq_render(bfir_eq *q, int n_bands, const double *freq, const double *mag, const double *phase, void *h_out);
+/* same, result left on the device: returns a device pointer to taps/2 samples (valid until the next render /
+ * destroy) for bfir_set_coeff_device(..., channel_stride 0, ...), or NULL on error */
+const void *bfir_eq_render_device(bfir_eq *q, int n_bands, const double *freq, const double *mag, const double *phase);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
