@@ -76,6 +76,12 @@ API = [
     ("bfir_run_partial_device", _ci, [_vp, _vp]),
     ("bfir_run_finish_device", _ci, [_vp, _vp]),
     ("bfir_acc_device_ptr", _vp, [_vp, ctypes.POINTER(_sz)]),
+    ("bfir_peer_setup", _ci, [_vp, _ci, _ci]),
+    ("bfir_peer_export", _ci, [_vp, _vp]),
+    ("bfir_peer_import", _ci, [_vp, _ci, _vp]),
+    ("bfir_peer_set_ptr", _ci, [_vp, _ci, _vp]),
+    ("bfir_peer_recv_ptr", _vp, [_vp]),
+    ("bfir_peer_own_channels", _ci, [_vp, ctypes.POINTER(_ci), ctypes.POINTER(_ci)]),
     ("bfir_set_groups", _ci, [_vp, _ci]),
     ("bfir_get_groups", _ci, [_vp]),
     ("bfir_set_stream", _ci, [_vp, _vp]),
@@ -290,6 +296,29 @@ class Brutefir:
         if rc not in (OK, ERR_NONFINITE):
             raise BfirError(rc, last_error())
         return rc
+
+    # fused partition-shard reduce (peer stores over NVLink instead of an NCCL reduce)
+    def peer_setup(self, rank, world):
+        _check(self.lib.bfir_peer_setup(self.h, rank, world))
+
+    def peer_export(self):
+        buf = ctypes.create_string_buffer(64)
+        _check(self.lib.bfir_peer_export(self.h, buf))
+        return bytes(buf.raw)
+
+    def peer_import(self, peer_rank, handle):
+        _check(self.lib.bfir_peer_import(self.h, peer_rank, ctypes.create_string_buffer(handle, 64)))
+
+    def peer_set_ptr(self, peer_rank, ptr):
+        _check(self.lib.bfir_peer_set_ptr(self.h, peer_rank, ctypes.c_void_p(ptr)))
+
+    def peer_recv_ptr(self):
+        return self.lib.bfir_peer_recv_ptr(self.h)
+
+    def peer_own_channels(self):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        _check(self.lib.bfir_peer_own_channels(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def set_groups(self, n):
         _check(self.lib.bfir_set_groups(self.h, int(n)))

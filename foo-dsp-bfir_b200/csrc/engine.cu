@@ -24,6 +24,13 @@ struct Engine {
     // filter swap with crossfade (configs[2]): staged coefficient set, second accumulator, two time buffers
     void *coeffs_next = nullptr, *acc2 = nullptr, *tbuf = nullptr;
     bool xfade_pending = false;
+    // fused partition-shard reduce: peer-mapped receive buffers (PeerPush), this rank's own channel range
+    PeerPush peer = {};
+    void *recv = nullptr;
+    void *peer_opened[BFIR_MAX_PEERS] = {};
+    int own_first = 0, own_count = 0;
+    int peer_setup(int rank, int world);
+    int peer_ready() const { if (!peer.enabled) return 1; for (int q = 0; q < peer.world; q++) if (!peer.recv[q]) return 0; return 1; }
     int part_begin = 0, part_count = 0;
     SampleFormat in_sf, out_sf;
     bool dither_on = false, initialized = false, own_stream = true;
@@ -210,6 +217,8 @@ void Engine::destroy()
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
     if (stream && own_stream) cudaStreamDestroy(stream);
     stream = nullptr;
+    for (int q = 0; q < BFIR_MAX_PEERS; q++) if (peer_opened[q]) { cudaIpcCloseMemHandle(peer_opened[q]); peer_opened[q] = nullptr; }
+    if (recv) { cudaFree(recv); recv = nullptr; }
     void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
     fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
@@ -332,6 +341,29 @@ int Engine::set_crossbar(const double *in_gains, const double *out_gains)
     return BFIR_OK;
 }
 
+// fused reduce set-up: reduced channels (outputs with a crossbar, else filters) are dealt to the ranks
+// in contiguous ranges of cpr = ceil(n / world); allocates this rank's receive buffer
+int Engine::peer_setup(int rank, int world)
+{
+    const int n_red = xbar ? Cot : Ct;
+    if (world < 2 || world > BFIR_MAX_PEERS || rank < 0 || rank >= world) { set_error("invalid peer geometry"); return BFIR_ERR_INVALID; }
+    if (S != 1 || dither_on || world > n_red) { set_error("fused reduce needs one stream, no dither and world <= channels"); return BFIR_ERR_INVALID; }
+    BFIR_CUDA(cudaStreamSynchronize(stream));
+    memset(&peer, 0, sizeof(peer));
+    peer.world = world; peer.self = rank; peer.cpr = (n_red + world - 1) / world;
+    own_first = rank * peer.cpr;
+    own_count = own_first >= n_red ? 0 : (n_red - own_first < peer.cpr ? n_red - own_first : peer.cpr);
+    if (own_count < 1) { set_error("rank %d owns no channel", rank); return BFIR_ERR_INVALID; }
+    if (recv) { cudaFree(recv); recv = nullptr; }
+    const size_t bytes = (size_t)2 * world * peer.cpr * N * rs;
+    BFIR_CUDA(cudaMalloc(&recv, bytes));
+    BFIR_CUDA(cudaMemset(recv, 0, bytes));
+    peer.recv[rank] = recv;
+    peer.enabled = 1;
+    set_groups(1);
+    return BFIR_OK;
+}
+
 int Engine::set_groups(int n)
 {
     if (n < 1) n = 1;
@@ -414,6 +446,7 @@ int Engine::front_group(int g, const void *d_inbuf)
     m.fdl_stride_ch = (long long)P * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = P; m.part_begin = part_begin; m.part_count = part_count;
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = c0;
+    if (peer.enabled && !xbar) m.push = peer;
     dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), nch);
     mac_kernel_t mk = rs == 4 ? mac_kernel_for_split<float>(mac_split) : mac_kernel_for_split<double>(mac_split);
     mk<<<grid, 256, 0, st>>>(m);
@@ -425,6 +458,16 @@ int Engine::front_group(int g, const void *d_inbuf)
     if (g == 0) prof(2);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
+    if (peer.enabled && xbar) { // partial out-mix on this rank's partition shard, rows pushed to their owners
+        XbarArgs x = {};
+        x.in = acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
+        x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = ns; x.stream_base = s0;
+        x.state = nullptr; x.n_slots = P; x.push = peer; x.push_state = state + g;
+        xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
+        xk<<<dim3((N + 255) / 256, ns), 256, (size_t)Co * C * rs, st>>>(x);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+    }
     return BFIR_OK;
 }
 
@@ -435,6 +478,24 @@ int Engine::back_group(int g, void *d_outbuf)
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
     const int nch = ns * Co, c0 = s0 * Co;
     cudaStream_t st = gstream(g);
+    if (peer.enabled) { // owner side: sum the source slots of the own channels, then the normal output stage on them
+        void *dst = xbar ? yacc : acc;
+        dim3 grid((N + 255) / 256, own_count);
+        if (rs == 4) peer_sum_kernel<float><<<grid, 256, 0, st>>>((const float *)recv, (float *)dst, state + g, peer.world, peer.cpr, N, own_first, own_count);
+        else peer_sum_kernel<double><<<grid, 256, 0, st>>>((const double *)recv, (double *)dst, state + g, peer.world, peer.cpr, N, own_first, own_count);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+        InvArgs v = {};
+        v.in_layout = LAYOUT_ORD; v.in = dst; v.in_stride_x = N; v.scale_in = out_sf.scale;
+        v.fmt = out_sf.format; v.ch_per_stream = own_count; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g;
+        v.ch_base = own_first; v.raw_ch_base = own_first;
+        v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * own_count * out_sf.bytes;
+        cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(own_count, 1), st, v, tw);
+        count_launch();
+        if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+        if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+        return BFIR_OK;
+    }
     if (xbar) { // filter outputs -> outputs (mixnscale OUTPUT, n_bufs = C)
         XbarArgs x = {};
         x.in = acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
@@ -662,6 +723,7 @@ static int check_ready(bfir_engine *e)
     if (e == nullptr) return BFIR_ERR_INVALID;
     if (!e->impl.initialized) { set_error("run before set_coeff"); return BFIR_ERR_NOT_READY; }
     if (e->impl.xbar && !e->impl.xbar_set) { set_error("run before set_crossbar"); return BFIR_ERR_NOT_READY; }
+    if (!e->impl.peer_ready()) { set_error("fused reduce: not every peer receive buffer is connected"); return BFIR_ERR_NOT_READY; }
     return BFIR_OK;
 }
 
@@ -692,6 +754,52 @@ int bfir_run_finish_device(bfir_engine *e, void *d_outbuf)
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     return e->impl.enqueue_back(d_outbuf);
+}
+
+int bfir_peer_setup(bfir_engine *e, int rank, int world)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.peer_setup(rank, world);
+}
+
+int bfir_peer_export(bfir_engine *e, void *handle64)
+{
+    if (e == nullptr || handle64 == nullptr || e->impl.recv == nullptr) return BFIR_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    BFIR_CUDA(cudaIpcGetMemHandle(&h, e->impl.recv));
+    memcpy(handle64, &h, 64);
+    return BFIR_OK;
+}
+
+int bfir_peer_import(bfir_engine *e, int peer_rank, const void *handle64)
+{
+    if (e == nullptr || handle64 == nullptr || !e->impl.peer.enabled || peer_rank < 0 || peer_rank >= e->impl.peer.world) return BFIR_ERR_INVALID;
+    if (peer_rank == e->impl.peer.self) return BFIR_OK;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    BFIR_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    e->impl.peer_opened[peer_rank] = p;
+    e->impl.peer.recv[peer_rank] = p;
+    return BFIR_OK;
+}
+
+int bfir_peer_set_ptr(bfir_engine *e, int peer_rank, void *d_recv)
+{
+    if (e == nullptr || d_recv == nullptr || !e->impl.peer.enabled || peer_rank < 0 || peer_rank >= e->impl.peer.world) return BFIR_ERR_INVALID;
+    e->impl.peer.recv[peer_rank] = d_recv;
+    return BFIR_OK;
+}
+
+void *bfir_peer_recv_ptr(bfir_engine *e) { return e ? e->impl.recv : nullptr; }
+
+int bfir_peer_own_channels(bfir_engine *e, int *first, int *count)
+{
+    if (e == nullptr || !e->impl.peer.enabled) return BFIR_ERR_INVALID;
+    if (first) *first = e->impl.own_first;
+    if (count) *count = e->impl.own_count;
+    return BFIR_OK;
 }
 
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes)

@@ -28,6 +28,7 @@ struct MacArgs {
     const EngineState *state;
     int block_offset;        // 0: blockcounter is the current block; used by tests
     int ch_base;             // first channel of this launch (channel-group pipelining)
+    PeerPush push;           // enabled: partial sums go to the owner rank's receive buffer (fused reduce)
 };
 
 template <class T> struct vec8 { T v[8]; };
@@ -134,7 +135,10 @@ __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
 #pragma unroll
             for (int j = 0; j < 8; j++) acc[j] += red[((s - 1) * 8 + j) * GPC + gl];
     }
-    if (active) st8((T *)a.acc + (long long)ch * a.N + (long long)g * 8, acc);
+    if (active) {
+        T *dst = a.push.enabled ? peer_dst<T>(a.push, ch, a.N, t & 1u) : (T *)a.acc + (long long)ch * a.N;
+        st8(dst + (long long)g * 8, acc);
+    }
 }
 
 typedef void (*mac_kernel_t)(const MacArgs);

@@ -31,6 +31,22 @@ enum {
     OUT_REAL_L = 2   // engine: first L samples -> planar real scratch (consumed by the dither kernel)
 };
 
+// Fused partition-shard reduce ("fused variant"): instead of writing its PARTIAL spectrum
+// of reduced channel `ch` to local memory for a later NCCL reduce, the producing kernel stores it
+// straight into the receive buffer of the rank that owns `ch` -- a peer-mapped pointer, i.e. plain
+// st.global over NVLink -- so the transfer overlaps the partition sum tile by tile. Receive buffer
+// of rank q: [2 (block parity)][world (source rank)][cpr (owned channels)][N].
+#define BFIR_MAX_PEERS 8
+struct PeerPush {
+    void *recv[BFIR_MAX_PEERS];
+    int world, self, cpr, enabled;
+};
+template <class T> BFIR_HD T *peer_dst(const PeerPush &p, int ch, int N, unsigned int parity)
+{
+    const int q = ch / p.cpr, local = ch - q * p.cpr;
+    return (T *)p.recv[q] + (((long long)parity * p.world + p.self) * p.cpr + local) * N;
+}
+
 // device-resident engine state: lets one CUDA graph be replayed for every block
 struct EngineState {
     unsigned int blockcounter;  // brutefir.hpp:106
@@ -68,6 +84,7 @@ struct InvArgs {
     long long out_stride_x;  // elements (bytes per stream for OUT_RAW)
     int fmt, ch_per_stream;
     int ch_base;             // first channel of this launch
+    int raw_ch_base;         // subtracted from the channel for raw addressing (compact own-channel output)
     double ovf_max;          // bfoverflow_t.max
     OverflowStats *stats;    // [channels]
     EngineState *state;      // probe + blockcounter++ (engine only)
@@ -281,7 +298,8 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[16], const InvArg
         return;
     }
     // OUT_RAW
-    const int stream = bx / a.ch_per_stream, ch = bx - stream * a.ch_per_stream;
+    const int rb = bx - a.raw_ch_base;
+    const int stream = rb / a.ch_per_stream, ch = rb - stream * a.ch_per_stream;
     const int bytes = fmt_bytes(a.fmt);
     uint8_t *raw = (uint8_t *)a.out + (long long)stream * a.out_stride_x + (long long)ch * bytes;
     const long long step = (long long)a.ch_per_stream * bytes;

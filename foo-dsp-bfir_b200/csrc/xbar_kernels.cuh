@@ -26,6 +26,8 @@ struct XbarArgs {
     int *procblocks;           // [streams * n_out]: incremented here for the filter channels (brutefir.cpp:265-268)
     unsigned char *pb_inc;
     int stream_base;           // first stream of this launch (channel groups)
+    PeerPush push;             // enabled: output rows go to the owner rank's receive buffer (fused reduce)
+    const EngineState *push_state; // block parity of the receive buffer
 };
 
 #ifdef __CUDACC__
@@ -59,8 +61,23 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
         T acc = (T)0;
 #pragma unroll
         for (int i = 0; i < MAXI; i++) if (i < a.n_in) acc = fma(row[i], x[i], acc);
-        out[(long long)o * a.out_stride] = acc;
+        if (a.push.enabled) peer_dst<T>(a.push, s * a.n_out + o, a.N, a.push_state->blockcounter & 1u)[j] = acc;
+        else out[(long long)o * a.out_stride] = acc;
     }
+}
+
+// owner side of the fused reduce: sum the `world` source slots of each owned channel in rank order
+// (deterministic) into the local spectrum buffer at the channel's absolute position
+template <class T>
+__global__ void __launch_bounds__(256) peer_sum_kernel(const T *recv, T *dst, const EngineState *state, int world, int cpr, int N, int ch_first, int n_own)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int local = blockIdx.y;
+    if (j >= N || local >= n_own) return;
+    const unsigned int parity = state->blockcounter & 1u;
+    T acc = (T)0;
+    for (int s = 0; s < world; s++) acc += recv[(((long long)parity * world + s) * cpr + local) * N + j];
+    dst[(long long)(ch_first + local) * N + j] = acc;
 }
 
 typedef void (*xbar_kernel_t)(const XbarArgs);

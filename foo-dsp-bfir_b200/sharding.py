@@ -89,3 +89,38 @@ def make_partition_sharded(pkg, filter_length, filter_blocks, realsize, channels
     ptr, nbytes = eng.acc_device_ptr()
     acc = pkg.as_torch(ptr, nbytes // realsize, "<f4" if realsize == 4 else "<f8")
     return PartitionShardedEngine(eng, acc, group), eng
+
+
+class FusedPartitionShardedEngine:
+    """Partition sharding with the reduce fused into the producing kernel: every rank's partition-sum
+    (or, with a crossbar, output-mix) kernel stores its partial spectra straight into the receive buffer
+    of the rank that owns the channel (peer-mapped memory, NVLink stores), a one-element all-reduce on
+    the same stream is the only collective (it orders "all peers have pushed" before "owners sum"), and
+    every rank then emits its own channels as a compact interleaved block [L][own_count]."""
+
+    def __init__(self, engine, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.engine, self.group = torch, dist, engine, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        engine.peer_setup(self.rank, self.world)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, engine.peer_export(), group=group)
+        for q, h in enumerate(handles):
+            engine.peer_import(q, h)
+        self.own_first, self.own_count = engine.peer_own_channels()
+        self.flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        dist.barrier(group=group)
+
+    def run_device(self, d_in, d_out_own):
+        self.engine.run_partial_device(d_in)                                  # pushes partials to the owners
+        self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.SUM, group=self.group)   # cross-rank barrier on the stream
+        self.engine.run_finish_device(d_out_own)                              # sum own slots + output stage
+
+    def gather(self, d_out_own, d_all):
+        """d_all [world][L * cpr] <- every rank's own block (only needed when one rank wants all channels)"""
+        self.dist.all_gather_into_tensor(d_all, d_out_own, group=self.group)
+
+    def sync(self):
+        return self.engine.sync()

@@ -157,6 +157,22 @@ int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf);
 int bfir_run_finish_device(bfir_engine *e, void *d_outbuf);
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
 
+/* Fused partition-shard reduce (no reference counterpart; SURVEY 8e "fused variant"). After
+ * bfir_peer_setup(rank, world) + connecting every peer's receive buffer, bfir_run_partial_device stores the
+ * partial spectra of each reduced channel (outputs with a crossbar, else filters) DIRECTLY into the
+ * receive buffer of the rank that owns the channel (peer-mapped pointers: NVLink stores issued by the
+ * producing kernel, tile by tile), and bfir_run_finish_device -- after a cross-rank barrier the caller
+ * provides -- sums the `world` slots of its own channels and emits ONLY those channels, as a compact
+ * interleaved block [L][own_count]. Ownership: contiguous ranges of ceil(n / world) channels.
+ * Connect peers with bfir_peer_export / bfir_peer_import (CUDA IPC handle, 64 bytes, one process per GPU)
+ * or bfir_peer_set_ptr (same process). One stream, no dither, world <= 8. */
+int bfir_peer_setup(bfir_engine *e, int rank, int world);
+int bfir_peer_export(bfir_engine *e, void *handle64);
+int bfir_peer_import(bfir_engine *e, int peer_rank, const void *handle64);
+int bfir_peer_set_ptr(bfir_engine *e, int peer_rank, void *d_recv);
+void *bfir_peer_recv_ptr(bfir_engine *e);
+int bfir_peer_own_channels(bfir_engine *e, int *first, int *count);
+
 /* Change the number of channel groups (see bfir_config_t.n_groups); synchronises the engine. */
 int bfir_set_groups(bfir_engine *e, int n_groups);
 int bfir_get_groups(bfir_engine *e);

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=32, help="inputs = filters = outputs")
     ap.add_argument("--blocks", type=int, default=20)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="peer-store fused reduce instead of the NCCL all-reduce")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -48,6 +49,11 @@ def main():
     torch.cuda.set_stream(stream)
     drv, eng = sh.make_partition_sharded(pkg, L, P, 4, n, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, h, device=local,
                                          xbar_inputs=n, xbar_outputs=n, in_gains=gin, out_gains=gout)
+    own_first, own_count = 0, n
+    if a.fused:
+        assert world > 1, "--fused needs at least two ranks"
+        drv = sh.FusedPartitionShardedEngine(eng)
+        own_first, own_count = drv.own_first, drv.own_count
     full = None
     if a.check and rank == 0:
         full = pkg.Brutefir(L, P, 4, n, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, device=local, n_groups=1, xbar_inputs=n, xbar_outputs=n)
@@ -55,7 +61,7 @@ def main():
         full.set_crossbar(gin, gout)
         full.set_stream(stream.cuda_stream)
     d_in = [torch.from_numpy(np.random.default_rng(0xB200 + b).uniform(-1, 1, L * n).astype(np.float32)).cuda() for b in range(4)]
-    d_out = torch.empty(L * n, dtype=torch.float32, device="cuda")
+    d_out = torch.empty(L * own_count, dtype=torch.float32, device="cuda")
     d_ref = torch.empty(L * n, dtype=torch.float32, device="cuda")
     worst = 0.0
     warm = P          # every timed block convolves all partitions
@@ -80,7 +86,7 @@ def main():
             full.run_device(d_in[(warm + b) % 4], d_ref)
         assert full.sync() == 0
         torch.cuda.synchronize()
-        y, r = d_out.double(), d_ref.double()
+        y, r = d_out.double().reshape(L, own_count), d_ref.double().reshape(L, n)[:, own_first:own_first + own_count]
         worst = float(torch.sqrt(torch.mean((y - r) ** 2) / torch.mean(r ** 2)))
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -89,7 +95,7 @@ def main():
     if rank == 0:
         part = (P + world - 1) // world
         print(json.dumps({"workload": "cfg4-geometry: %dx%d crossbar, L %d, P %d (%d taps), float" % (n, n, L, P, taps),
-                          "world": world, "partitions_per_rank": part, "ms_per_block": ms,
+                          "world": world, "reduce": "fused peer stores + 1-element barrier" if a.fused else "NCCL all-reduce", "partitions_per_rank": part, "ms_per_block": ms,
                           "Msamples_s": n * L / (ms * 1e-3) / 1e6, "reduce_bytes": n * 2 * L * 4,
                           "rel_rms_vs_unsharded": worst if a.check else None,
                           "prefill": "timed after a %d-block prefill (all partitions active)" % warm}))
