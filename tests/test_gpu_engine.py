@@ -320,3 +320,51 @@ def test_crossfade_filter_swap_every_block(pkg, oracle, rs, L, P, C):
     # a swap needs the same geometry and an initialised engine
     with pytest.raises(pkg.BfirError):
         g.set_coeff_crossfade(filters[0], P + 1)
+
+
+def test_cfg3_full_size_properties(pkg):
+    """BASELINE configs[3] at full size on one GPU: 4096 independent stereo streams x 65536 taps
+    (L 4096, P 16, float, distinct filter per channel; 8 GiB of spectra). No oracle at this size:
+    size-independent properties instead -- every channel's filter is a distinct gain * delay, so the
+    output must be the delayed, scaled input (exact overlap-save), streams must not leak into each
+    other, and the 4-group pipelined run must equal the serialised one."""
+    import torch
+    L, P, C, S = 4096, 16, 2, 4096
+    Ct = C * S
+    rng = np.random.default_rng(3)
+    delays = rng.integers(0, L * P - 1, Ct)
+    gains = rng.uniform(0.25, 1.0, Ct).astype(np.float32)
+
+    def sparse_filters():
+        out = []
+        for c in range(Ct):
+            v = np.zeros(L * P, dtype=np.float32)
+            v[delays[c]] = gains[c]
+            out.append(v)
+        return out
+
+    g = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False, n_streams=S, n_groups=1)
+    assert g.set_coeff(sparse_filters(), P) == 0
+    nb = 20
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    x = [torch.rand(S, L, C, dtype=torch.float32, device="cuda", generator=gen) * 2 - 1 for _ in range(nb)]
+    y = [torch.empty(S, L, C, dtype=torch.float32, device="cuda") for _ in range(nb)]
+    for b in range(nb):
+        g.run_device(x[b], y[b])
+    assert g.sync() == 0
+    X = torch.cat(x, dim=1)                             # [S, nb*L, C]
+    Y = torch.cat(y, dim=1)
+    for c in rng.choice(Ct, 64, replace=False):
+        s, k, d = int(c) // C, int(c) % C, int(delays[c])
+        want = torch.zeros(nb * L, device="cuda")
+        want[d:] = X[s, : nb * L - d, k] * float(gains[c])
+        err = torch.sqrt(torch.mean((Y[s, :, k] - want) ** 2) / torch.mean(want ** 2)).item()
+        assert err < 1e-5, (c, err)
+    # pipelined (4 channel groups) == serialised, bit for bit, at full size
+    g2 = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False, n_streams=S, n_groups=4)
+    assert g2.set_coeff(sparse_filters(), P) == 0
+    y2 = torch.empty(S, L, C, dtype=torch.float32, device="cuda")
+    for b in range(nb):
+        g2.run_device(x[b], y2)
+        assert g2.sync() == 0
+        assert torch.equal(y2, y[b]), b

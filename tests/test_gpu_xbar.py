@@ -105,3 +105,47 @@ def test_cfg4_shape_impulse_filters_exact(pkg):
         fout[d:, f] = fin[: nb * L - d, f]
     ref = fout @ gout.astype(np.float32).astype(np.float64).T
     assert rel_rms(y, ref) < 1e-5
+
+
+def test_cfg4_full_depth_one_gpu(pkg):
+    """BASELINE configs[4] at FULL size on one GPU: 16 Mi taps (L 32768 x P 512) per filter, 32x32x32
+    crossbar: 4 GiB of coefficient spectra + 4 GiB delay line. Filters are a few scaled impulses spread
+    over the observable part of the 16 Mi taps, so the exact output is a sum of delayed crossbar mixes."""
+    import torch
+    L, P, n = 32768, 512, 32
+    rng = np.random.default_rng(12)
+    taps = L * P
+    nb = 24                                            # 786432 frames: delays below that are observable
+    delays = rng.integers(0, nb * L - 1, (n, 3))
+    amps = rng.uniform(0.3, 1.0, (n, 3)).astype(np.float32)
+    coeffs = []
+    for f in range(n):
+        v = np.zeros(taps, dtype=np.float32)
+        for d, a in zip(delays[f], amps[f]):
+            v[d] += a
+        coeffs.append(v)
+    gin = rng.standard_normal((n, n)) / np.sqrt(n)
+    gout = rng.standard_normal((n, n)) / np.sqrt(n)
+    g = pkg.Brutefir(L, P, 4, n, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, xbar_inputs=n, xbar_outputs=n)
+    assert g.set_coeff(coeffs, P) == 0
+    del coeffs
+    g.set_crossbar(gin, gout)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    x = [torch.rand(L, n, dtype=torch.float32, device="cuda", generator=gen) * 2 - 1 for _ in range(nb)]
+    y = [torch.empty(L, n, dtype=torch.float32, device="cuda") for _ in range(nb)]
+    for b in range(nb):
+        g.run_device(x[b], y[b])
+    assert g.sync() == 0
+    X = torch.cat(x, dim=0).double()                                   # [T, n]
+    Gi = torch.from_numpy(gin.astype(np.float32)).double().cuda()
+    Go = torch.from_numpy(gout.astype(np.float32)).double().cuda()
+    fin = X @ Gi.T                                                     # filter inputs [T, f]
+    fout = torch.zeros_like(fin)
+    for f in range(n):
+        for d, a in zip(delays[f], amps[f]):
+            d = int(d)
+            fout[d:, f] += fin[: nb * L - d, f] * float(a)
+    ref = fout @ Go.T
+    Y = torch.cat(y, dim=0).double()
+    err = torch.sqrt(torch.mean((Y - ref) ** 2) / torch.mean(ref ** 2)).item()
+    assert err < 1e-5, err
