@@ -10,7 +10,6 @@
 // brutefir.hpp:104-127) lives in device memory, so a block step needs no host-side bookkeeping.
 #include "common.hpp"
 #include "xbar_kernels.cuh"
-#include <time.h>
 
 namespace bfir {
 
@@ -612,12 +611,8 @@ int Engine::sync_and_probe()
 
 // brutefir::run on host buffers: per group H2D -> kernels -> D2H on the group's stream, so the copies
 // of one group overlap the kernels of another; returns when outbuf is complete
-static double now_us() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
-static double g_dbg_enqueue_us = 0, g_dbg_wait_us = 0; static long g_dbg_calls = 0;
-
 int Engine::run_host(const void *inbuf, void *outbuf)
 {
-    const double t_begin = now_us();
     int rc = fork();
     if (rc != BFIR_OK) return rc;
     for (int g = 0; g < n_groups; g++) {
@@ -639,13 +634,7 @@ int Engine::run_host(const void *inbuf, void *outbuf)
     finish_block();
     rc = join();
     if (rc != BFIR_OK) return rc;
-    const double t_mid = now_us();
-    rc = sync_and_probe();
-    if (getenv("BFIR_DEBUG_TIMING")) {
-        g_dbg_enqueue_us += t_mid - t_begin; g_dbg_wait_us += now_us() - t_mid; g_dbg_calls++;
-        if (g_dbg_calls % 200 == 0) fprintf(stderr, "[bfir] run_host: enqueue %.1f us, wait %.1f us per call (groups %d)\n", g_dbg_enqueue_us / g_dbg_calls, g_dbg_wait_us / g_dbg_calls, n_groups);
-    }
-    return rc;
+    return sync_and_probe();
 }
 
 int Engine::get_overflow(int ch, bfir_overflow_t *out)
