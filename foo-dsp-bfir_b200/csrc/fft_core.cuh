@@ -138,6 +138,30 @@ template <bool INV, class T> struct small_dft<4, INV, T> { static BFIR_HD void r
 template <bool INV, class T> struct small_dft<8, INV, T> { static BFIR_HD void run(cpx<T> (&a)[8]) { dft8<INV, T>(a); } };
 template <bool INV, class T> struct small_dft<16, INV, T> { static BFIR_HD void run(cpx<T> (&a)[16]) { dft16<INV, T>(a); } };
 
+// exp(-2 pi i j / D) for j = 0..15 and D = 32 or 64, as compile-time constants: the 16 points a thread
+// owns are N/32 (or N/64) bins apart, so W_N^(k0 + j N/D) = W_N^k0 * root<D>(j) needs ONE table look-up
+// per thread instead of 16
+template <class T, int D> BFIR_HD cpx<T> unit_root(int j)
+{
+    constexpr double c32[16] = { 1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+        0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785,
+        0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474,
+        -0.70710678118654752440, -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913 };
+    constexpr double s32[16] = { 0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+        0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913,
+        1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+        0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785 };
+    constexpr double c64[16] = { 1.0, 0.99518472667219688624, 0.98078528040323044913, 0.95694033573220886494,
+        0.92387953251128675613, 0.88192126434835502971, 0.83146961230254523708, 0.77301045336273696081,
+        0.70710678118654752440, 0.63439328416364549822, 0.55557023301960222474, 0.47139673682599764856,
+        0.38268343236508977173, 0.29028467725446236764, 0.19509032201612826785, 0.09801714032956060199 };
+    constexpr double s64[16] = { 0.0, 0.09801714032956060199, 0.19509032201612826785, 0.29028467725446236764,
+        0.38268343236508977173, 0.47139673682599764856, 0.55557023301960222474, 0.63439328416364549822,
+        0.70710678118654752440, 0.77301045336273696081, 0.83146961230254523708, 0.88192126434835502971,
+        0.92387953251128675613, 0.95694033573220886494, 0.98078528040323044913, 0.99518472667219688624 };
+    return D == 32 ? mk<T>((T)c32[j], (T)-s32[j]) : mk<T>((T)c64[j], (T)-s64[j]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // pass plan: radices whose product is 2^LOG2M, 16s first (so strides are >= 16 from pass 2 on)
 template <int LOG2M> struct fft_plan {
@@ -165,13 +189,32 @@ struct BlockFFT {
     typedef fft_plan<LOG2M> plan;
     typedef cpx<T> C;
 
-    // Butterflies + twiddles of one pass on the thread's registers.
+    // table look-ups of one pass for thread t: per butterfly w^1, and w^4 for radix 8/16 (the other powers
+    // follow by at most 3 multiplications). Kept apart from the butterflies so that the loads can be issued
+    // one pass ahead, before the shared-memory exchange, and their latency stays off the critical path.
     //   tw: table of exp(-2 pi i j / NTW), tw_shift = log2(NTW / M)
+    template <int LOG2R> static constexpr int tw_regs() { return (E >> LOG2R) * (LOG2R >= 3 ? 2 : 1); }
+
+    template <int LOG2R, int LOG2S>
+    static BFIR_HD void load_twiddles(int t, C (&w)[tw_regs<LOG2R>()], const C *__restrict__ tw, int tw_shift)
+    {
+        constexpr int NB = E >> LOG2R, PER = LOG2R >= 3 ? 2 : 1;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const int b = t + j * NT;
+            const int ps = (b >> LOG2S) << LOG2S; // p * s
+            w[PER * j] = tw[ps << tw_shift];
+            if constexpr (PER == 2) w[PER * j + 1] = tw[(ps * 4) << tw_shift];
+        }
+    }
+
+    // Butterflies + twiddles of one pass on the thread's registers.
     template <int LOG2R, int LOG2S, bool LAST>
-    static BFIR_HD void butterflies(int t, C (&v)[E], const C *__restrict__ tw, int tw_shift)
+    static BFIR_HD void butterflies(int t, C (&v)[E], const C (&w)[tw_regs<LOG2R>()])
     {
         constexpr int R = 1 << LOG2R;
         constexpr int NB = E / R; // butterflies per thread
+        constexpr int PER = LOG2R >= 3 ? 2 : 1;
 #pragma unroll
         for (int j = 0; j < NB; j++) {
             C a[R];
@@ -179,9 +222,7 @@ struct BlockFFT {
             for (int k = 0; k < R; k++) a[k] = v[j + k * NB];
             small_dft<R, INV, T>::run(a);
             if constexpr (!LAST) {
-                const int b = t + j * NT;
-                const int ps = (b >> LOG2S) << LOG2S; // p * s
-                C w1 = tw[ps << tw_shift];
+                C w1 = w[PER * j];
                 if (INV) w1 = cconj(w1);
                 if constexpr (R == 2) {
                     a[1] = cmul(a[1], w1);
@@ -189,8 +230,7 @@ struct BlockFFT {
                     C w2 = cmul(w1, w1);
                     a[1] = cmul(a[1], w1); a[2] = cmul(a[2], w2); a[3] = cmul(a[3], cmul(w2, w1));
                 } else {
-                    // two table look-ups (w1, w4) keep the power chain at most 3 multiplications deep
-                    C w4 = tw[(ps * 4) << tw_shift];
+                    C w4 = w[PER * j + 1];
                     if (INV) w4 = cconj(w4);
                     C w2 = cmul(w1, w1), w3 = cmul(w2, w1);
                     a[1] = cmul(a[1], w1); a[2] = cmul(a[2], w2); a[3] = cmul(a[3], w3);
@@ -250,17 +290,30 @@ struct fft_passes {
     static constexpr int LOG2R = plan::log2_radix(PASS);
     static constexpr bool LAST = (PASS == plan::npass - 1);
 
+    static constexpr int NW = F::template tw_regs<LOG2R>();
+
 #ifdef __CUDACC__
-    // device: all threads of the CTA call this; on return v[i] = X[t + i*NT] (natural order)
+    // device: all threads of the CTA call run(); on return v[i] = X[t + i*NT] (natural order)
     static __device__ __forceinline__ void run(int t, cpx<T> (&v)[F::E], cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift)
     {
-        F::template butterflies<LOG2R, LOG2S, LAST>(t, v, tw, tw_shift);
+        static_assert(PASS == 0, "enter at the first pass");
+        cpx<T> w[NW];
+        if constexpr (!LAST) F::template load_twiddles<LOG2R, LOG2S>(t, w, tw, tw_shift);
+        pass(t, v, smem, tw, tw_shift, w);
+    }
+
+    static __device__ __forceinline__ void pass(int t, cpx<T> (&v)[F::E], cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift, const cpx<T> (&w)[NW])
+    {
+        F::template butterflies<LOG2R, LOG2S, LAST>(t, v, w);
         if constexpr (!LAST) {
+            typedef fft_passes<T, LOG2M, INV, PASS + 1, LOG2S + LOG2R> next;
+            cpx<T> wn[next::NW];
+            if constexpr (!next::LAST) F::template load_twiddles<next::LOG2R, LOG2S + LOG2R>(t, wn, tw, tw_shift); // one pass ahead
             F::template store_pass<LOG2R, LOG2S>(t, v, smem);
             __syncthreads();
             F::load_natural(t, v, smem);
             __syncthreads();
-            fft_passes<T, LOG2M, INV, PASS + 1, LOG2S + LOG2R>::run(t, v, smem, tw, tw_shift);
+            next::pass(t, v, smem, tw, tw_shift, wn);
         }
     }
 #endif
@@ -268,7 +321,11 @@ struct fft_passes {
     // host emulation: vs[t] are the registers of thread t
     static void run_host(cpx<T> (*vs)[F::E], cpx<T> *smem, const cpx<T> *tw, int tw_shift)
     {
-        for (int t = 0; t < F::NT; t++) F::template butterflies<LOG2R, LOG2S, LAST>(t, vs[t], tw, tw_shift);
+        for (int t = 0; t < F::NT; t++) {
+            cpx<T> w[NW];
+            if constexpr (!LAST) F::template load_twiddles<LOG2R, LOG2S>(t, w, tw, tw_shift);
+            F::template butterflies<LOG2R, LOG2S, LAST>(t, vs[t], w);
+        }
         if constexpr (!LAST) {
             for (int t = 0; t < F::NT; t++) F::template store_pass<LOG2R, LOG2S>(t, vs[t], smem);
             for (int t = 0; t < F::NT; t++) F::load_natural(t, vs[t], smem);

@@ -163,6 +163,8 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T
     constexpr int MS = 1 << LOG2MS, NT = MS / 16, LOG2M = LOG2MS + (R0 == 2 ? 1 : 0);
     typedef cpx<T> C;
     bool bad = false;
+    cpx<T> wpre = mk<T>((T)1, (T)0);
+    if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];     // W_M^t = W_N^(2t); W_M^(t + i NTs) = W_M^t * root32(i)
     if (R0 == 1) {
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, bx, by, r, a, bad);
@@ -175,7 +177,7 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T
             const C lo = fwd_elem<T, LOG2M, false>(n, bx, by, r, a, bad);
             const C hi = fwd_elem<T, LOG2M, true>(n + MS, bx, by, r, a, bad);
             if (r == 0) v[i] = cadd(lo, hi);
-            else v[i] = cmul(csub(lo, hi), tw[n << (tw_shift_n + 1)]);   // W_M^n = W_N^(2n)
+            else v[i] = cmul(csub(lo, hi), cmul(wpre, unit_root<T, 32>(i)));   // W_M^n = W_N^(2n)
         }
     }
     if (a.in_mode == IN_COEFF && bad) *a.nonfinite = 1;
@@ -198,6 +200,7 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
     if (a.state != NULL) off += (long long)(a.state->blockcounter % (unsigned int)a.n_slots) * a.out_stride_y;
     T *out = (T *)a.out + off;
     const T sc = (T)a.scale_out;
+    const C wbase = tw[(R0 * t + r) << tw_shift_n];   // W_N^k of i = 0; the thread's bins are N/32 apart
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int kp = t + i * NT;
@@ -213,7 +216,7 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
             const T er = (T)0.5 * (zk.x + zm.x), ei = (T)0.5 * (zk.y - zm.y);
             const T dr = (T)0.5 * (zk.x - zm.x), di = (T)0.5 * (zk.y + zm.y);
             const T o_r = di, o_i = -dr;
-            const C w = tw[k << tw_shift_n];
+            const C w = cmul(wbase, unit_root<T, 32>(i));
             const T xr = (er + (w.x * o_r - w.y * o_i)) * sc;
             const T xi = (ei + (w.x * o_i + w.y * o_r)) * sc;
             if (a.out_layout == LAYOUT_ORD) {
@@ -232,7 +235,7 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
 // Z'_k = (X_k + conj X_{M-k}) + i conj(W_N^k) (X_k - conj X_{M-k}), the packed spectrum whose inverse
 // complex transform is z[n] = x[2n] + i x[2n+1]
 template <class T>
-BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T> *__restrict__ tw, int tw_shift_n)
+BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T> w)
 {
     typedef cpx<T> C;
     C xk = spec_load<T>(in, layout, k, M);
@@ -240,8 +243,7 @@ BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T
     xk.x *= sc; xk.y *= sc; xm.x *= sc; xm.y *= sc;
     const T er = xk.x + xm.x, ei = xk.y - xm.y;   // X_k + conj X_{M-k}
     const T dr = xk.x - xm.x, di = xk.y + xm.y;   // X_k - conj X_{M-k}
-    const C w = tw[k << tw_shift_n];              // W_N^k; need its conjugate
-    const T pr = w.x * dr + w.y * di;             // conj(w) * d
+    const T pr = w.x * dr + w.y * di;             // conj(w) * d, w = W_N^k
     const T pi = w.x * di - w.y * dr;
     return mk<T>(er - pi, ei + pr);               // e + i p
 }
@@ -254,16 +256,21 @@ BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[16], const cpx<T> *__res
     typedef cpx<T> C;
     const T *in = (const T *)a.in + bx * a.in_stride_x;
     const T sc = (T)a.scale_in;
+    // one table look-up per thread: the thread's bins k = t + i NT are N/32 (one CTA) or N/64 (two CTAs) apart
+    const C wbase = tw[t << tw_shift_n];                                   // W_N^t
+    C wpre = mk<T>((T)1, (T)0);
+    if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];               // W_M^t
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int k = t + i * NT;
-        const C lo = inv_elem<T>(in, a.in_layout, k, M, sc, tw, tw_shift_n);
+        const C wk = cmul(wbase, R0 == 1 ? unit_root<T, 32>(i) : unit_root<T, 64>(i));   // W_N^k
+        const C lo = inv_elem<T>(in, a.in_layout, k, M, sc, wk);
         if (R0 == 1) {
             v[i] = lo;
         } else {
-            const C hi = inv_elem<T>(in, a.in_layout, k + MS, M, sc, tw, tw_shift_n);
+            const C hi = inv_elem<T>(in, a.in_layout, k + MS, M, sc, mk<T>(wk.y, -wk.x));   // W_N^(k + N/4) = -i W_N^k
             if (r == 0) v[i] = cadd(lo, hi);
-            else v[i] = cmul(csub(lo, hi), cconj(tw[k << (tw_shift_n + 1)]));   // W_M^(-k)
+            else v[i] = cmul(csub(lo, hi), cconj(cmul(wpre, unit_root<T, 32>(i))));       // W_M^(-k)
         }
     }
 }

@@ -30,7 +30,7 @@ def main():
     pkg = importlib.import_module("foo-dsp-bfir_b200")
     fmt = pkg.FLOAT_LE if a.realsize == 4 else pkg.FLOAT64_LE
     dt = torch.float32 if a.realsize == 4 else torch.float64
-    eng = pkg.Brutefir(a.L, a.P, a.realsize, a.channels, fmt, fmt, 48000, False, n_streams=a.streams)
+    eng = pkg.Brutefir(a.L, a.P, a.realsize, a.channels, fmt, fmt, 48000, False, n_streams=a.streams, n_groups=1)
     Ct = a.streams * a.channels
     rng = np.random.default_rng(0)
     taps = a.L * a.P
