@@ -54,6 +54,7 @@ struct Engine {
     DitherTables dither;
     double ovf_max = 1.0;
     unsigned long long blocks_since_sync = 0;
+    unsigned int host_blockcounter = 0;   // mirror of the device block counter (its parity selects the prev buffer)
     int mac_split = 1;              // partition slices per CTA of the MAC kernel
     int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
     // optional per-kernel timing (bfir_set_profiling)
@@ -236,6 +237,7 @@ int Engine::reset()
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     for (auto &o : last_overflow) { o.n_overflows = 0; o.largest = 0; o.intlargest = 0; }
+    host_blockcounter = 0;
     return BFIR_OK;
 }
 
@@ -322,6 +324,7 @@ void Engine::finish_block()
 {
     if (xfade_pending) { void *t = coeffs; coeffs = coeffs_next; coeffs_next = t; xfade_pending = false; }
     blocks_since_sync++;
+    host_blockcounter++;
 }
 
 int Engine::set_crossbar(const double *in_gains, const double *out_gains)
@@ -421,7 +424,7 @@ int Engine::front_group(int g, const void *d_inbuf)
     f.in = d_inbuf; f.in_stride_x = (long long)L * Ci * in_sf.bytes;  // bytes per stream
     f.scale_in = 1.0; f.scale_out = in_sf.scale;                       // brutefir.cpp:273-277
     f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = Ci; f.n_channels = Cit; f.ch_base = s0 * Ci;
-    f.state = state + g; f.n_slots = P;
+    f.state = state + g; f.n_slots = P; f.prev_parity = host_blockcounter & 1u;
     if (!xbar) { f.out = fdl; f.out_stride_x = (long long)P * N; f.out_stride_y = N; f.procblocks = procblocks; f.pb_inc = pb_inc; }
     else { f.out = xin; f.out_stride_x = N; f.out_stride_y = 0; f.procblocks = nullptr; f.pb_inc = nullptr; }
     if (g == 0) prof(0);
@@ -596,6 +599,7 @@ int Engine::sync_and_probe()
         pinfo("NaN or Inf values in the system! Invalid input? Aborting.\n");
         const int threads = 256, blocks = (Ct + threads - 1) / threads;
         if (n == 1) { // exact reference semantics: the aborted block does not advance the counters
+            host_blockcounter--;
             engine_abort_fixup_kernel<<<blocks, threads, 0, stream>>>(state, n_groups, procblocks, pb_inc, Ct, bad);
             count_launch();
         } else {

@@ -66,6 +66,7 @@ struct FwdArgs {
     void *prev;              // [2][n_channels][L] previous block, ping-pong by blockcounter parity
     int fmt, ch_per_stream, n_channels;
     int ch_base;             // first channel of this launch (channel-group pipelining): bx = blockIdx.x + ch_base
+    unsigned int prev_parity; // blockcounter & 1, tracked by the host so that no load depends on the state word
     const EngineState *state; // out slot = blockcounter % n_slots when state != NULL
     int n_slots;
     int *procblocks;         // [channels], brutefir.cpp:265-268
@@ -120,38 +121,67 @@ template <class T> BFIR_HD cpx<T> spec_load(const T *s, int layout, int k, int M
 // (r = 1): the same CTA, so no exchange between the two CTAs is ever needed. R0 = 2 doubles the
 // largest block length (L = 32768 float, 16384 double) and halves the per-CTA latency of big transforms.
 
+// per-thread constants of the input access, computed once (the state word must not be re-read per element:
+// the stores into the previous-block buffer would force the compiler to reload it every time)
+template <class T> struct FwdCtx {
+    const cpx<T> *plain;     // IN_TIME / IN_UPPER
+    const T *coeff;          // IN_COEFF
+    const cpx<T> *prev_rd;   // IN_RAW_PREV: previous block (read), current block (write)
+    cpx<T> *prev_wr;
+    const uint8_t *raw;
+    long long step;
+    T sc;
+};
+
+template <class T, int LOG2M>
+BFIR_HD FwdCtx<T> fwd_ctx(int bx, int by, const FwdArgs &a)
+{
+    constexpr int L = 1 << LOG2M;
+    typedef cpx<T> C;
+    FwdCtx<T> c;
+    c.plain = (const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y);
+    c.coeff = (const T *)a.in + bx * a.in_stride_x;
+    c.sc = (T)a.scale_in;
+    c.prev_rd = NULL; c.prev_wr = NULL; c.raw = NULL; c.step = 0;
+    if (a.in_mode == IN_RAW_PREV) {
+        // [previous block | current block], previous kept in a ping-pong pair that follows the reference's
+        // input_timecbuf[n][curbuf] (brutefir.cpp:255-260, 337)
+        const unsigned int par = a.prev_parity & 1u;
+        c.prev_rd = (const C *)((const T *)a.prev + ((long long)par * a.n_channels + bx) * L);
+        c.prev_wr = (C *)((T *)a.prev + ((long long)(par ^ 1u) * a.n_channels + bx) * L);
+        const int stream = bx / a.ch_per_stream, ch = bx - stream * a.ch_per_stream;
+        const int bytes = fmt_bytes(a.fmt);
+        c.step = (long long)a.ch_per_stream * bytes;
+        c.raw = (const uint8_t *)a.in + (long long)stream * a.in_stride_x + (long long)ch * bytes;
+    }
+    return c;
+}
+
 // element z[m] of the packed input, m in [0, M); UPPER tells at compile time that m >= M/2
 template <class T, int LOG2M, bool UPPER>
-BFIR_HD cpx<T> fwd_elem(int m, int bx, int by, int r, const FwdArgs &a, bool &bad)
+BFIR_HD cpx<T> fwd_elem(int m, int by, int r, const FwdArgs &a, const FwdCtx<T> &c, bool &bad)
 {
     constexpr int M = 1 << LOG2M, L = M;
     typedef cpx<T> C;
     if (a.in_mode == IN_TIME) {
-        return ((const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y))[m];
+        return c.plain[m];
     } else if (a.in_mode == IN_UPPER) {
         if (!UPPER) return mk<T>((T)0, (T)0);
-        return ((const C *)((const T *)a.in + bx * a.in_stride_x + by * a.in_stride_y))[m - M / 2];
+        return c.plain[m - M / 2];
     } else if (a.in_mode == IN_COEFF) {
         if (!UPPER) return mk<T>((T)0, (T)0);
-        const T *in = (const T *)a.in + bx * a.in_stride_x;
-        const T sc = (T)a.scale_in;
         const long long g = (long long)by * L + 2 * (m - M / 2);   // index into the channel's coefficients
         T c0 = (T)0, c1 = (T)0;
-        if (g < a.coeff_len) c0 = in[g] * sc;
-        if (g + 1 < a.coeff_len) c1 = in[g + 1] * sc;
+        if (g < a.coeff_len) c0 = c.coeff[g] * c.sc;
+        if (g + 1 < a.coeff_len) c1 = c.coeff[g + 1] * c.sc;
         bad = bad || !(c0 - c0 == (T)0) || !(c1 - c1 == (T)0);     // NaN or Inf
         return mk<T>(c0, c1);
-    } else { // IN_RAW_PREV: [previous block | current block], previous kept in a ping-pong pair that
-             // follows the reference's input_timecbuf[n][curbuf] (brutefir.cpp:255-260, 337)
-        const unsigned int par = a.state->blockcounter & 1u;
-        if (!UPPER) return ((const C *)((const T *)a.prev + ((long long)par * a.n_channels + bx) * L))[m];
-        const int stream = bx / a.ch_per_stream, ch = bx - stream * a.ch_per_stream;
-        const int bytes = fmt_bytes(a.fmt);
-        const long long step = (long long)a.ch_per_stream * bytes;
+    } else { // IN_RAW_PREV
+        if (!UPPER) return c.prev_rd[m];
         const int n = m - M / 2;                                   // complex index inside the current block
-        const uint8_t *p = (const uint8_t *)a.in + (long long)stream * a.in_stride_x + (long long)ch * bytes + (long long)(2 * n) * step;
-        const C z = mk<T>(load_raw<T>(p, a.fmt), load_raw<T>(p + step, a.fmt));
-        if (r == 0) ((C *)((T *)a.prev + ((long long)(par ^ 1u) * a.n_channels + bx) * L))[n] = z;
+        const uint8_t *p = c.raw + (long long)(2 * n) * c.step;
+        const C z = mk<T>(load_raw<T>(p, a.fmt), load_raw<T>(p + c.step, a.fmt));
+        if (r == 0) c.prev_wr[n] = z;
         return z;
     }
 }
@@ -165,17 +195,18 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T
     bool bad = false;
     cpx<T> wpre = mk<T>((T)1, (T)0);
     if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];     // W_M^t = W_N^(2t); W_M^(t + i NTs) = W_M^t * root32(i)
+    const FwdCtx<T> ctx = fwd_ctx<T, LOG2M>(bx, by, a);
     if (R0 == 1) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, bx, by, r, a, bad);
+        for (int i = 0; i < 8; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, by, r, a, ctx, bad);
 #pragma unroll
-        for (int i = 8; i < 16; i++) v[i] = fwd_elem<T, LOG2M, true>(t + i * NT, bx, by, r, a, bad);
+        for (int i = 8; i < 16; i++) v[i] = fwd_elem<T, LOG2M, true>(t + i * NT, by, r, a, ctx, bad);
     } else {
 #pragma unroll
         for (int i = 0; i < 16; i++) {
             const int n = t + i * NT;
-            const C lo = fwd_elem<T, LOG2M, false>(n, bx, by, r, a, bad);
-            const C hi = fwd_elem<T, LOG2M, true>(n + MS, bx, by, r, a, bad);
+            const C lo = fwd_elem<T, LOG2M, false>(n, by, r, a, ctx, bad);
+            const C hi = fwd_elem<T, LOG2M, true>(n + MS, by, r, a, ctx, bad);
             if (r == 0) v[i] = cadd(lo, hi);
             else v[i] = cmul(csub(lo, hi), cmul(wpre, unit_root<T, 32>(i)));   // W_M^n = W_N^(2n)
         }
