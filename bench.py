@@ -284,8 +284,13 @@ def main():
     b_mac = (2 * P + 1) * (2 * L) * rs * Ct            # algorithmic bytes per launch
     mac_ms = prof["mac_ms"] / max(nprof, 1)
     achieved = b_mac / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    traffic, traffic_src = None, None       # DRAM read+write bytes per launch from the committed ncu --set full capture
+    tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
+    if os.path.exists(tpath) and S == 16:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "partition_mac_kernel<double,4>", "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "partition_mac_kernel<double,SPLIT=4,UNROLL=4>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_mac, "avg_launch_ms": mac_ms,
                 "step_share": {k: v / max(nprof, 1) for k, v in prof.items()}}
 
