@@ -368,3 +368,57 @@ def test_cfg3_full_size_properties(pkg):
         g2.run_device(x[b], y2)
         assert g2.sync() == 0
         assert torch.equal(y2, y[b]), b
+
+
+@pytest.mark.parametrize("P,cb,taps", [(6, 3, 3 * 128), (6, 6, 200), (4, 4, 1), (5, 2, 2 * 128 - 1)])
+def test_ragged_coefficient_geometry(pkg, oracle, P, cb, taps):
+    """coefficient sets shorter than the engine (coeff_blocks < filter_blocks, brutefir.cpp:292) and filters
+    that end inside a partition (coeff::preprocess_coeff zero-padding, coeff.cpp:317-341)"""
+    L, C = 128, 2
+    g = pkg.Brutefir(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 44100, False)
+    o = oracle.Engine(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 44100, False)
+    h = [decay_filter(c, taps) for c in range(C)]
+    assert g.set_coeff(h, cb, 0.7) == 0 and o.set_coeff(h, cb, 0.7) == 0
+    x = white_noise(17, 3 * P * L, C)
+    for b in range(3 * P):
+        raw = np.ascontiguousarray(x[b * L:(b + 1) * L]).view(np.uint8).ravel()
+        yg, yo = g.run(raw)[1].view(np.float64), o.run(raw)[1].view(np.float64)
+        assert rel_rms(yg, yo) < 1e-12, b
+
+
+def test_fewer_coefficient_sets_than_channels(pkg, oracle):
+    """set_coeff with n_coeffs < channels: the reference leaves coeffs[n].data NULL and run() would crash
+    (brutefir.cpp:213-216, 283-297); the build convolves the channels that have a filter and emits silence
+    for the others. n_coeffs > channels is clamped like the reference (:191-194)."""
+    L, P, C = 256, 3, 4
+    g = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    o = oracle.Engine(L, P, 4, 2, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False)
+    h = [decay_filter(c, L * P) for c in range(6)]
+    assert g.set_coeff(h[:2], P) == 0 and o.set_coeff(h[:2], P) == 0
+    x = white_noise(2, 5 * L, C).astype(np.float32)
+    for b in range(5):
+        blk = np.ascontiguousarray(x[b * L:(b + 1) * L])
+        y = g.run(blk.view(np.uint8).ravel())[1].view(np.float32).reshape(L, C)
+        ref = o.run(np.ascontiguousarray(blk[:, :2]).view(np.uint8).ravel())[1].view(np.float32).reshape(L, 2)
+        assert rel_rms(y[:, :2], ref) < 1e-5 and np.all(y[:, 2:] == 0)
+    assert g.set_coeff(h, P) == 0          # six arrays for four channels: clamped
+    assert g.run(np.ascontiguousarray(x[:L]).view(np.uint8).ravel())[0] == 0
+
+
+def test_check_overflows_prints_peaks(pkg):
+    """brutefir::check_overflows / print_overflows (brutefir.cpp:371-388, 585-629) through the print callback"""
+    msgs = []
+    cb = pkg.PRINT_CB(lambda m: msgs.append(m.decode()))
+    pkg.load_library().bfir_set_print_callback(cb)
+    try:
+        L, P, C = 128, 2, 2
+        g = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.S16_LE, 44100, False)
+        g.set_coeff([np.array([4.0]), np.array([0.25])], P)
+        x = (white_noise(1, L, C) * 0.9).astype(np.float32)
+        g.run(x.view(np.uint8).ravel())
+        assert g.check_overflows() == 1              # channel 0 clips (gain 4), channel 1 does not
+        assert len(msgs) == 2 and msgs[0].startswith("peak: 0/") and msgs[1].startswith("peak: 1/0/")
+        assert g.overflow(0).n_overflows > 0 and g.overflow(1).n_overflows == 0
+        assert g.check_overflows() == 0              # unchanged since the last call: silent
+    finally:
+        pkg.load_library().bfir_set_print_callback(pkg.PRINT_CB(0))
