@@ -146,6 +146,7 @@ struct XfadeArgs {
     double ovf_max;
     OverflowStats *stats;
     EngineState *state;
+    int *host_flag;
 };
 
 template <class T>
@@ -157,7 +158,10 @@ __global__ void __launch_bounds__(256) xfade_emit_kernel(const XfadeArgs a)
     acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
     if (n < a.L) {
         const T y = crossfade_ramp<T>(((const T *)a.t_old)[(long long)ch * a.N + n], ((const T *)a.t_new)[(long long)ch * a.N + n], n, a.L);
-        if (n == 0 && !(y - y == (T)0)) atomicMin(&a.state->first_bad_channel, ch);     // brutefir.cpp:316-321
+        if (n == 0 && !(y - y == (T)0)) {                                               // brutefir.cpp:316-321
+            atomicMin(&a.state->first_bad_channel, ch);
+            if (a.host_flag != NULL) *(volatile int *)a.host_flag = 1;
+        }
         if (a.to_real) {
             ((T *)a.out)[(long long)ch * a.L + n] = y;
         } else {

@@ -50,6 +50,7 @@ struct Engine {
     unsigned char *pb_inc = nullptr;
     OverflowStats *stats = nullptr;
     EngineState *h_state = nullptr; // pinned, [BFIR_MAX_GROUPS]
+    int *h_flag = nullptr, *d_flag = nullptr; // mapped pinned word the kernels raise on a non-finite probe
     std::vector<bfir_overflow_t> last_overflow;
     DitherTables dither;
     double ovf_max = 1.0;
@@ -149,6 +150,9 @@ int Engine::init(const bfir_config_t &c)
     BFIR_CUDA(cudaMalloc((void **)&nonfinite, sizeof(int)));
     BFIR_CUDA(cudaMalloc((void **)&stats, sizeof(OverflowStats) * (Cot > Ct ? Cot : Ct)));
     BFIR_CUDA(cudaHostAlloc((void **)&h_state, sizeof(EngineState) * BFIR_MAX_GROUPS, cudaHostAllocDefault));
+    BFIR_CUDA(cudaHostAlloc((void **)&h_flag, sizeof(int), cudaHostAllocMapped));
+    *h_flag = 0;
+    BFIR_CUDA(cudaHostGetDevicePointer((void **)&d_flag, h_flag, 0));
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) {
         BFIR_CUDA(cudaStreamCreateWithFlags(&groups[g].stream, cudaStreamNonBlocking));
         BFIR_CUDA(cudaEventCreateWithFlags(&groups[g].done, cudaEventDisableTiming));
@@ -225,6 +229,8 @@ void Engine::destroy()
     state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
     h_state = nullptr;
+    if (h_flag) cudaFreeHost(h_flag);
+    h_flag = nullptr; d_flag = nullptr;
     dither.destroy();
 }
 
@@ -489,7 +495,7 @@ int Engine::back_group(int g, void *d_outbuf)
         BFIR_CUDA(cudaGetLastError());
         InvArgs v = {};
         v.in_layout = LAYOUT_ORD; v.in = dst; v.in_stride_x = N; v.scale_in = out_sf.scale;
-        v.fmt = out_sf.format; v.ch_per_stream = own_count; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g;
+        v.fmt = out_sf.format; v.ch_per_stream = own_count; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.host_flag = d_flag;
         v.ch_base = own_first; v.raw_ch_base = own_first;
         v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * own_count * out_sf.bytes;
         cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(own_count, 1), st, v, tw);
@@ -522,7 +528,7 @@ int Engine::back_group(int g, void *d_outbuf)
         x.t_old = tbuf; x.t_new = (char *)tbuf + (size_t)N * rs * Ct;
         x.out = dither_on ? ybuf : d_outbuf; x.out_stream_stride = (long long)L * Co * out_sf.bytes;
         x.N = N; x.L = L; x.fmt = out_sf.format; x.ch_per_stream = Co; x.ch_base = c0; x.to_real = dither_on ? 1 : 0;
-        x.ovf_max = ovf_max; x.stats = stats; x.state = state + g;
+        x.ovf_max = ovf_max; x.stats = stats; x.state = state + g; x.host_flag = d_flag;
         if (rs == 4) xfade_emit_kernel<float><<<dim3((L + 255) / 256, nch), 256, 0, st>>>(x);
         else xfade_emit_kernel<double><<<dim3((L + 255) / 256, nch), 256, 0, st>>>(x);
         count_launch();
@@ -531,7 +537,7 @@ int Engine::back_group(int g, void *d_outbuf)
     InvArgs v = {};
     v.in_layout = LAYOUT_ORD; v.in = xbar ? yacc : acc; v.in_stride_x = N;
     v.scale_in = out_sf.scale;                                         // brutefir.cpp:303-307
-    v.fmt = out_sf.format; v.ch_per_stream = Co; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.ch_base = c0;
+    v.fmt = out_sf.format; v.ch_per_stream = Co; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.ch_base = c0; v.host_flag = d_flag;
     if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }
     else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * Co * out_sf.bytes; }
     if (!xfade_pending) {
@@ -588,11 +594,14 @@ int Engine::enqueue_block(const void *d_inbuf, void *d_outbuf)
 // wait for the stream and apply the reference's NaN/Inf abort (brutefir.cpp:316-321)
 int Engine::sync_and_probe()
 {
-    BFIR_CUDA(cudaMemcpyAsync(h_state, state, sizeof(EngineState) * n_groups, cudaMemcpyDeviceToHost, stream));
     BFIR_CUDA(cudaStreamSynchronize(stream));
     prof_collect();
     const unsigned long long n = blocks_since_sync;
     blocks_since_sync = 0;
+    if (*(volatile int *)h_flag == 0) return BFIR_OK;          // nothing raised the flag: no copy needed
+    *h_flag = 0;
+    BFIR_CUDA(cudaMemcpyAsync(h_state, state, sizeof(EngineState) * n_groups, cudaMemcpyDeviceToHost, stream));
+    BFIR_CUDA(cudaStreamSynchronize(stream));
     int bad = 0x7fffffff;
     for (int g = 0; g < n_groups; g++) if (h_state[g].first_bad_channel < bad) bad = h_state[g].first_bad_channel;
     if (bad != 0x7fffffff) {

@@ -41,9 +41,11 @@ int rfft_choose_r0(int realsize, int log2m, long long n_buffers)
         const int v = atoi(env);
         if (v == 1 || v == 2) return v;
     }
-    // (measured on B200: the two-CTA split pays off only for the inverse transform of very few large
-    //  double-precision buffers; the forward side reads every input twice and is slower, so the
-    //  automatic choice stays at one CTA unless the size requires two)
+    // measured on B200 (tools/kernel_times.py): with at most a few dozen buffers an 8192-point double
+    // transform is latency-bound on one CTA per SM and two half-size CTAs are faster (cfg1 single stream:
+    // forward 22.9 -> 21.7 us, inverse 22.6 -> 17.3 us); smaller or float transforms get slower (the
+    // forward side reads every input twice), so they stay on one CTA unless the size requires two
+    if (realsize == 8 && log2m >= 13 && n_buffers <= 64) return 2;
     return 1;
 }
 

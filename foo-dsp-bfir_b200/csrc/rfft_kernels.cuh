@@ -89,6 +89,7 @@ struct InvArgs {
     double ovf_max;          // bfoverflow_t.max
     OverflowStats *stats;    // [channels]
     EngineState *state;      // probe + blockcounter++ (engine only)
+    int *host_flag;          // mapped pinned host word, set to 1 on a non-finite probe (lets the host skip a D2H)
 };
 
 template <class T> BFIR_HD T tw_re(const cpx<T> &w) { return w.x; }
@@ -323,6 +324,7 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[16], const InvArg
         if (!(y0 - y0 == (T)0)) {
 #ifdef __CUDA_ARCH__
             atomicMin(&a.state->first_bad_channel, bx);
+            if (a.host_flag != NULL) *(volatile int *)a.host_flag = 1;
 #else
             if (bx < a.state->first_bad_channel) a.state->first_bad_channel = bx;
 #endif
