@@ -275,6 +275,30 @@ def main():
     e2e_value = n_gpus * Ct * L * e2e_steps / t_e2e / 1e6
     checksum = float(host_out.numpy()[:1024].sum())
 
+    # ---- the same end-to-end step with the product's I/O format: foo_dsp_bfir constructs the engine with REALSIZE 8
+    # and FLOAT_LE in/out (foo_dsp_bfir.cpp:279-286), which halves the PCIe bytes of the FLOAT64_LE headline run
+    e2e_f32 = None
+    if rank == 0 and not args.no_latency:
+        eng.close()
+        e32 = pkg.Brutefir(L, P, rs, C, 8, 8, rate, False, n_streams=S, device=local_rank, n_groups=min(4, S))
+        e32.set_stream(stream.cuda_stream)
+        assert e32.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
+        h32 = [h.float().pin_memory() for h in host_in]
+        o32 = torch.empty(S * L * C, dtype=torch.float32).pin_memory()
+        n32, no32 = [h.numpy() for h in h32], o32.numpy()
+        for b in range(P + 3):
+            e32.run(n32[b % ring], no32)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for b in range(e2e_steps):
+            rc, _ = e32.run(n32[b % ring], no32)
+        t32 = time.perf_counter() - t0
+        assert rc == 0
+        e2e_f32 = {"value": Ct * L * e2e_steps / t32 / 1e6, "unit": "Msamples/s (this rank only)", "ms_per_step": 1e3 * t32 / e2e_steps,
+                   "h2d_bytes_per_step": S * L * C * 4, "d2h_bytes_per_step": S * L * C * 4,
+                   "note": "FLOAT_LE in/out around the double-precision engine, as the plug-in runs it"}
+        e32.close()
+
     # ---- roofline of the dominant kernel (partition MAC)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -332,6 +356,7 @@ def main():
                     "api": "bfir_run(host in, host out): pinned H2D + kernels + D2H + sync per step, %d stream groups pipelined" % e2e_groups,
                     "checksum": checksum},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
+            "e2e_product_io": e2e_f32,
             "clocks": sampler.summary(),
         }
         print(json.dumps(line))
