@@ -56,6 +56,12 @@ struct Engine {
     double ovf_max = 1.0;
     unsigned long long blocks_since_sync = 0;
     unsigned int host_blockcounter = 0;   // mirror of the device block counter (its parity selects the prev buffer)
+    // the kernels of one block step, captured once per block parity and replayed (bfir_run, one group)
+    cudaGraphExec_t step_graph[2] = { nullptr, nullptr };
+    unsigned long long step_graph_launches[2] = { 0, 0 };
+    bool graphs_enabled = true;
+    void invalidate_graphs() { for (int k = 0; k < 2; k++) if (step_graph[k]) { cudaGraphExecDestroy(step_graph[k]); step_graph[k] = nullptr; } }
+    int run_step_graph();
     int mac_split = 1;              // partition slices per CTA of the MAC kernel
     int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
     // optional per-kernel timing (bfir_set_profiling)
@@ -137,6 +143,7 @@ int Engine::init(const bfir_config_t &c)
         BFIR_CUDA(cudaMalloc(&gains_out, (size_t)Co * C * rs));
     }
     fft_r0 = rfft_choose_r0(rs, log2m, Ct);
+    if (const char *env = getenv("BFIR_GRAPHS")) graphs_enabled = atoi(env) != 0;
     in_bytes = (size_t)S * L * Ci * in_sf.bytes;
     out_bytes = (size_t)S * L * Co * out_sf.bytes;
     BFIR_CUDA(cudaMalloc(&d_in, in_bytes));
@@ -214,6 +221,7 @@ void Engine::destroy()
 {
     prof_free();
     if (stream) cudaStreamSynchronize(stream);
+    invalidate_graphs();
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) {
         if (groups[g].stream) { cudaStreamSynchronize(groups[g].stream); cudaStreamDestroy(groups[g].stream); groups[g].stream = nullptr; }
         if (groups[g].done) { cudaEventDestroy(groups[g].done); groups[g].done = nullptr; }
@@ -262,6 +270,7 @@ int Engine::load_coeff(const void *const *h_coeffs, const void *d_src, long long
     if ((h_coeffs == nullptr && d_src == nullptr) || blocks < 1 || length < 0) { set_error("invalid coefficient arguments"); return BFIR_ERR_INVALID; }
     BFIR_CUDA(cudaSetDevice(device));
     BFIR_CUDA(cudaStreamSynchronize(stream));
+    invalidate_graphs();
     if (n_coeffs > Ct) n_coeffs = Ct;                     // brutefir.cpp:191-194
     const size_t cbuf = (size_t)N * rs;
     void *target = nullptr;
@@ -328,7 +337,7 @@ int Engine::load_coeff(const void *const *h_coeffs, const void *d_src, long long
 // after a block has been enqueued: a staged coefficient set becomes the current one
 void Engine::finish_block()
 {
-    if (xfade_pending) { void *t = coeffs; coeffs = coeffs_next; coeffs_next = t; xfade_pending = false; }
+    if (xfade_pending) { void *t = coeffs; coeffs = coeffs_next; coeffs_next = t; xfade_pending = false; invalidate_graphs(); }
     blocks_since_sync++;
     host_blockcounter++;
 }
@@ -368,6 +377,7 @@ int Engine::peer_setup(int rank, int world)
     BFIR_CUDA(cudaMemset(recv, 0, bytes));
     peer.recv[rank] = recv;
     peer.enabled = 1;
+    invalidate_graphs();
     set_groups(1);
     return BFIR_OK;
 }
@@ -381,6 +391,7 @@ int Engine::set_groups(int n)
     for (int g = 0; g < n_groups && g < BFIR_MAX_GROUPS; g++)
         if (groups[g].stream) BFIR_CUDA(cudaStreamSynchronize(groups[g].stream));
     n_groups = n;
+    invalidate_graphs();
     const int base = S / n, extra = S % n;
     int s = 0;
     for (int g = 0; g < n; g++) {
@@ -624,8 +635,46 @@ int Engine::sync_and_probe()
 
 // brutefir::run on host buffers: per group H2D -> kernels -> D2H on the group's stream, so the copies
 // of one group overlap the kernels of another; returns when outbuf is complete
+// capture (first use per block parity) and replay the kernels of one block step: saves the per-kernel
+// launch cost on the latency path. Only pointers fixed for the engine's lifetime are baked in (the staging
+// buffers, the state words); whatever can change them invalidates the graphs.
+int Engine::run_step_graph()
+{
+    const int par = (int)(host_blockcounter & 1u);
+    if (step_graph[par] == nullptr) {
+        const unsigned long long before = g_launches.load();
+        cudaGraph_t graph = nullptr;
+        BFIR_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+        int rc = front_group(0, d_in);
+        if (rc == BFIR_OK) rc = back_group(0, d_out);
+        cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+        if (rc != BFIR_OK || ce != cudaSuccess || graph == nullptr) {
+            if (graph) cudaGraphDestroy(graph);
+            set_error("graph capture of the block step failed");
+            return rc != BFIR_OK ? rc : BFIR_ERR_CUDA;
+        }
+        ce = cudaGraphInstantiate(&step_graph[par], graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { step_graph[par] = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return BFIR_ERR_CUDA; }
+        step_graph_launches[par] = g_launches.load() - before;
+        g_launches.fetch_sub(step_graph_launches[par]);   // nothing ran during capture
+    }
+    BFIR_CUDA(cudaGraphLaunch(step_graph[par], stream));
+    count_launch(step_graph_launches[par]);
+    return BFIR_OK;
+}
+
 int Engine::run_host(const void *inbuf, void *outbuf)
 {
+    // latency path: one group, kernels replayed from a graph (after two plain blocks have configured them)
+    if (graphs_enabled && n_groups == 1 && !xfade_pending && pcap == 0 && !peer.enabled && host_blockcounter >= 2) {
+        BFIR_CUDA(cudaMemcpyAsync(d_in, inbuf, in_bytes, cudaMemcpyHostToDevice, stream));
+        int rc = run_step_graph();
+        if (rc != BFIR_OK) return rc;
+        BFIR_CUDA(cudaMemcpyAsync(outbuf, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
+        finish_block();
+        return sync_and_probe();
+    }
     int rc = fork();
     if (rc != BFIR_OK) return rc;
     for (int g = 0; g < n_groups; g++) {
@@ -901,6 +950,7 @@ int bfir_set_stream(bfir_engine *e, void *cuda_stream)
     if (g.stream && g.own_stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
     g.stream = (cudaStream_t)cuda_stream;
     g.own_stream = false;
+    g.invalidate_graphs();
     return BFIR_OK;
 }
 
