@@ -13,7 +13,9 @@ Workload (one "step" = one block of the block loop, brutefir::run, for every str
   runs its own S streams (channel/stream sharding, no collective): weak scaling.
 
 Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM; e2e = the
-same metric through bfir_run with pinned HOST buffers (H2D + kernels + D2H + sync per step); roofline
+same metric on pinned HOST buffers, the H2D of every input block and the D2H of every output block inside
+the timed region: e2e.value through bfir_run_async/bfir_wait (two blocks in flight), e2e.sync_run through the
+reference's synchronous run() = bfir_run (H2D + kernels + D2H + sync per call); roofline
 = partition-MAC kernel, algorithmic bytes (2P+1)*N*realsize per channel-block over its CUDA-event
 time; cpu_baseline = the reference's own sources (oracle/_ref, FFT provider named) on the host cores;
 latency = host-visible bfir_run latency of ONE 7.1 stream (p50/p99).
@@ -253,48 +255,84 @@ def main():
     prof, nprof = eng.get_profile()
     value = n_gpus * Ct * L * K / (ms_total * 1e-3) / 1e6
 
-    # ---- end to end through bfir_run: pinned host in -> H2D -> kernels -> D2H -> pinned host out, per step
-    e2e_steps = K
-    eng.set_groups(min(4, S))             # overlap H2D / kernels / D2H of stream groups inside bfir_run
-    e2e_groups = eng.get_groups()
-    np_in, np_out = [h.numpy() for h in host_in], host_out.numpy()
-    for b in range(min(W, 3)):
-        rc, _ = eng.run(np_in[b % ring], np_out)
+    # the same device-resident step with 8 stream groups (the transforms of one group run under the partition
+    # sum of another): faster, but per-kernel event times overlap, so the roofline above stays on the serial pass
+    eng.set_groups(min(8, S))
+    for b in range(3):
+        eng.run_device(dev_in[b % ring], dev_out)
+    barrier()
+    ev0g, ev1g = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0g.record(stream)
+    for b in range(K):
+        eng.run_device(dev_in[b % ring], dev_out)
+    ev1g.record(stream)
+    assert eng.sync() == 0
+    barrier()
+    ms_grouped = max_over_ranks(ev0g.elapsed_time(ev1g))
+    value_grouped = {"value": n_gpus * Ct * L * K / (ms_grouped * 1e-3) / 1e6, "ms_per_step": ms_grouped / K,
+                     "stream_groups": eng.get_groups()}
+
+    # ---- end to end on pinned host buffers, every step: H2D of the step's input block, the kernels, D2H of its
+    # output block. Two ways of calling: bfir_run (the reference's synchronous run(), stream groups overlap inside
+    # one call) and bfir_run_async/bfir_wait (batch callers: DEPTH blocks in flight, so the copies and kernels of
+    # consecutive blocks overlap too). The pipelined number is e2e.value, the synchronous one rides beside it.
+    DEPTH = 2
+
+    def e2e_pass(engine, ins, outs, steps, sync_groups, async_groups):
+        engine.set_groups(min(sync_groups, S))
+        for b in range(3):
+            rc, _ = engine.run(ins[b % len(ins)], outs[0])
+            assert rc == 0
+        barrier()
+        t0 = time.perf_counter()
+        for b in range(steps):
+            rc, _ = engine.run(ins[b % len(ins)], outs[0])
+        torch.cuda.synchronize()
+        t_sync = time.perf_counter() - t0
         assert rc == 0
-    barrier()
+        engine.set_groups(min(async_groups, S))
+        groups = engine.get_groups()
+        tickets = [engine.run_async(ins[b % len(ins)], outs[b % len(outs)]) for b in range(3)]
+        assert engine.wait(tickets[-1]) == 0
+        barrier()
+        tickets = []
+        t0 = time.perf_counter()
+        for b in range(steps):
+            tickets.append(engine.run_async(ins[b % len(ins)], outs[b % len(outs)]))
+            if b >= DEPTH:
+                rc = engine.wait(tickets[b - DEPTH])     # block b-DEPTH is now in outs[(b-DEPTH) % len(outs)]
+        rc |= engine.wait(tickets[-1])
+        torch.cuda.synchronize()
+        t_async = time.perf_counter() - t0
+        assert rc == 0
+        barrier()
+        return max_over_ranks(t_sync), max_over_ranks(t_async), groups
+
+    e2e_steps = K
+    host_outs = [host_out] + [torch.empty(S * L * C, dtype=torch.float64).pin_memory() for _ in range(DEPTH)]
+    np_in, np_outs = [h.numpy() for h in host_in], [h.numpy() for h in host_outs]
     sampler.busy.set()
-    t0 = time.perf_counter()
-    for b in range(e2e_steps):
-        rc, _ = eng.run(np_in[b % ring], np_out)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    barrier()
+    t_sync, t_e2e, e2e_groups = e2e_pass(eng, np_in, np_outs, e2e_steps, 4, 8)
     sampler.busy.clear()
-    assert rc == 0
-    t_e2e = max_over_ranks(t_e2e)
     e2e_value = n_gpus * Ct * L * e2e_steps / t_e2e / 1e6
+    e2e_sync_value = n_gpus * Ct * L * e2e_steps / t_sync / 1e6
     checksum = float(host_out.numpy()[:1024].sum())
 
     # ---- the same end-to-end step with the product's I/O format: foo_dsp_bfir constructs the engine with REALSIZE 8
     # and FLOAT_LE in/out (foo_dsp_bfir.cpp:279-286), which halves the PCIe bytes of the FLOAT64_LE headline run
     e2e_f32 = None
-    if rank == 0 and not args.no_latency:
+    if rank == 0 and not args.no_latency and world == 1:
         eng.close()
         e32 = pkg.Brutefir(L, P, rs, C, 8, 8, rate, False, n_streams=S, device=local_rank, n_groups=min(4, S))
         e32.set_stream(stream.cuda_stream)
         assert e32.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
-        h32 = [h.float().pin_memory() for h in host_in]
-        o32 = torch.empty(S * L * C, dtype=torch.float32).pin_memory()
-        n32, no32 = [h.numpy() for h in h32], o32.numpy()
-        for b in range(P + 3):
-            e32.run(n32[b % ring], no32)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for b in range(e2e_steps):
-            rc, _ = e32.run(n32[b % ring], no32)
-        t32 = time.perf_counter() - t0
-        assert rc == 0
-        e2e_f32 = {"value": Ct * L * e2e_steps / t32 / 1e6, "unit": "Msamples/s (this rank only)", "ms_per_step": 1e3 * t32 / e2e_steps,
+        n32 = [h.float().pin_memory().numpy() for h in host_in]
+        no32 = [torch.empty(S * L * C, dtype=torch.float32).pin_memory().numpy() for _ in range(DEPTH + 1)]
+        for b in range(P):
+            e32.run(n32[b % ring], no32[0])
+        ts32, ta32, _ = e2e_pass(e32, n32, no32, e2e_steps, 4, 8)
+        e2e_f32 = {"value": Ct * L * e2e_steps / ta32 / 1e6, "unit": "Msamples/s (this rank only)", "ms_per_step": 1e3 * ta32 / e2e_steps,
+                   "sync_run": {"value": Ct * L * e2e_steps / ts32 / 1e6, "ms_per_step": 1e3 * ts32 / e2e_steps},
                    "h2d_bytes_per_step": S * L * C * 4, "d2h_bytes_per_step": S * L * C * 4,
                    "note": "FLOAT_LE in/out around the double-precision engine, as the plug-in runs it"}
         e32.close()
@@ -329,12 +367,18 @@ def main():
         for b in range(P + 20):
             e1.run(pin[b % ring].numpy(), pout.numpy())
         lat = []
-        for b in range(2000):
+        pin_np, pout_np = [x.numpy() for x in pin], pout.numpy()
+        for b in range(10000):                      # p99 over >= 10 000 timed bfir_run calls
             t0 = time.perf_counter()
-            e1.run(pin[b % ring].numpy(), pout.numpy())
+            e1.run(pin_np[b % ring], pout_np)
             lat.append(time.perf_counter() - t0)
         lat = np.sort(np.array(lat)) * 1e3
+        e1.set_profiling(1000)                      # device-only time of the three kernels, CUDA events
+        for b in range(1000):
+            e1.run(pin_np[b % ring], pout_np)
+        dprof, dn = e1.get_profile()
         latency = {"streams": 1, "calls": len(lat), "p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]),
+                   "max_ms": float(lat[-1]), "device_kernels_ms": sum(dprof.values()) / max(dn, 1),
                    "block_period_ms": 1e3 * L / rate}
         e1.close()
 
@@ -353,10 +397,13 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(S, n_gpus),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * L * C * 8,
                     "d2h_bytes_per_step": S * L * C * 8, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "bfir_run(host in, host out): pinned H2D + kernels + D2H + sync per step, %d stream groups pipelined" % e2e_groups,
+                    "api": "bfir_run_async(pinned host in, pinned host out) + bfir_wait: H2D + kernels + D2H of every block, "
+                           "%d blocks in flight, %d stream groups" % (DEPTH, e2e_groups),
+                    "sync_run": {"value": e2e_sync_value, "ms_per_step": 1e3 * t_sync / e2e_steps,
+                                 "api": "bfir_run(host in, host out): the reference's synchronous run(), 4 stream groups"},
                     "checksum": checksum},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
-            "e2e_product_io": e2e_f32,
+            "e2e_product_io": e2e_f32, "value_grouped": value_grouped,
             "clocks": sampler.summary(),
         }
         print(json.dumps(line))

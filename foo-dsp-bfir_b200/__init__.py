@@ -67,6 +67,8 @@ API = [
     ("bfir_set_crossbar", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(_cd)]),
     ("bfir_run", _ci, [_vp, _vp, _vp]),
     ("bfir_run_device", _ci, [_vp, _vp, _vp]),
+    ("bfir_run_async", ctypes.c_longlong, [_vp, _vp, _vp]),
+    ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
     ("bfir_get_overflow", _ci, [_vp, _ci, ctypes.POINTER(Overflow)]),
@@ -109,6 +111,12 @@ API = [
     ("bfir_conv_dirac_convolve_inplace", _ci, [_vp, _vp]),
     ("bfir_conv_freq2time", _ci, [_vp, _vp, _vp]),
     ("bfir_conv_convolve_eval", _ci, [_vp, _vp, _vp, _vp]),
+    ("bfir_conv_td_block_length", _ci, [_ci]),
+    ("bfir_conv_td_new", _ci, [_vp, ctypes.POINTER(_vp), _vp, _ci]),
+    ("bfir_conv_td_blocklen", _ci, [_vp]),
+    ("bfir_conv_td_coeffs", _vp, [_vp]),
+    ("bfir_conv_td_convolve", _ci, [_vp, _vp, _vp]),
+    ("bfir_conv_td_free", None, [_vp]),
     ("bfir_conv_cbuf2raw", _ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, ctypes.POINTER(Overflow)]),
     ("bfir_conv_coeffs2cbuf", _ci, [_vp, _vp, _ci, _cd, _vp]),
     ("bfir_conv_runtime_coeffs2cbuf", _ci, [_vp, _vp, _vp]),
@@ -279,6 +287,20 @@ class Brutefir:
 
     def run_device(self, d_in, d_out):
         _check(self.lib.bfir_run_device(self.h, _ptr(d_in), _ptr(d_out)))
+
+    def run_async(self, inbuf, outbuf):
+        """Queue one block on PINNED host buffers; returns a ticket for wait(). Buffers stay untouched until then."""
+        t = self.lib.bfir_run_async(self.h, _ptr(inbuf), _ptr(outbuf))
+        if t < 0:
+            raise BfirError(int(t), last_error())
+        return t
+
+    def wait(self, ticket):
+        """-> 0, or -1 when a NaN/Inf probe fired in a block since the last wait/sync."""
+        rc = self.lib.bfir_wait(self.h, ticket)
+        if rc not in (OK, ERR_NONFINITE):
+            raise BfirError(rc, last_error())
+        return rc
 
     def run_partial_device(self, d_in):
         _check(self.lib.bfir_run_partial_device(self.h, _ptr(d_in)))
@@ -477,6 +499,33 @@ class FftwConvolver:
 
     def convolver_convolve_eval(self, input_cbuf, buffer_cbuf, output_cbuf):
         _check(self.lib.bfir_conv_convolve_eval(self.h, _ptr(input_cbuf), _ptr(buffer_cbuf), _ptr(output_cbuf)))
+
+    # td_conv_t (fftw_convolver.cpp:698-777): the handle is an opaque pointer, freed with convolver_td_free
+    def convolver_td_block_length(self, n_coeffs):
+        return self.lib.bfir_conv_td_block_length(n_coeffs)
+
+    def convolver_td_new(self, coeffs, n_coeffs=None):
+        """Returns the td handle, or None where the reference returns NULL / has no defined result."""
+        coeffs = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        n = len(coeffs) if n_coeffs is None else n_coeffs
+        h = _vp()
+        rc = self.lib.bfir_conv_td_new(self.h, ctypes.byref(h), _ptr(coeffs), n)
+        if rc == ERR_INVALID:
+            return None
+        _check(rc)
+        return h
+
+    def convolver_td_coeffs(self, tdc):
+        bl = self.lib.bfir_conv_td_blocklen(tdc)
+        out = np.zeros(2 * bl, dtype=self.dtype)
+        _check(self.lib.bfir_conv_download(self.h, _ptr(out), ctypes.c_void_p(self.lib.bfir_conv_td_coeffs(tdc)), out.nbytes))
+        return out
+
+    def convolver_td_convolve(self, tdc, overlap_block):
+        _check(self.lib.bfir_conv_td_convolve(self.h, tdc, _ptr(overlap_block)))
+
+    def convolver_td_free(self, tdc):
+        self.lib.bfir_conv_td_free(tdc)
 
     def convolver_cbuf2raw(self, cbuf, outbuf, fmt, byte_offset, sample_spacing, apply_dither, dither_channel, overflow):
         _check(self.lib.bfir_conv_cbuf2raw(self.h, _ptr(cbuf), _ptr(outbuf), fmt, byte_offset, sample_spacing,

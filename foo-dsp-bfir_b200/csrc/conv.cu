@@ -14,9 +14,11 @@ struct Conv {
     OverflowStats *d_stats = nullptr;
     int *d_flag = nullptr;
     DitherTables dither;
+    bool own_stream = true;
 
     ~Conv() { destroy(); }
-    int init(int length, int realsize, int n_dither_channels, int sampling_rate);
+    // shared != nullptr: a helper instance (the td convolver's transforms) on its owner's stream, no dither tables
+    int init(int length, int realsize, int n_dither_channels, int sampling_rate, const Conv *shared = nullptr);
     void destroy();
     // With two CTAs per transform an in-place call would let one CTA overwrite what the other still
     // has to read: use one CTA when the size allows, else go through the per-instance scratch cbuf.
@@ -56,7 +58,7 @@ struct Conv {
     }
 };
 
-int Conv::init(int length, int realsize, int n_dither_channels, int sampling_rate)
+int Conv::init(int length, int realsize, int n_dither_channels, int sampling_rate, const Conv *shared)
 {
     rs = realsize; L = length; N = 2 * length;
     if (rs != 4 && rs != 8) { set_error("Invalid real size %d.", rs); return BFIR_ERR_INVALID; }
@@ -65,20 +67,22 @@ int Conv::init(int length, int realsize, int n_dither_channels, int sampling_rat
     if (!rfft_supported(rs, log2m)) { set_error("block length %d not supported for realsize %d", L, rs); return BFIR_ERR_INVALID; }
     fft_r0 = rfft_choose_r0(rs, log2m, 1);
     BFIR_CUDA(cudaGetDevice(&device));
-    BFIR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (shared) { stream = shared->stream; own_stream = false; }
+    else BFIR_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = make_twiddles(rs, N, &tw);
     if (rc != BFIR_OK) return rc;
     BFIR_CUDA(cudaMalloc(&scratch, (size_t)N * rs));
     BFIR_CUDA(cudaMalloc(&stage, (size_t)L * rs));
     BFIR_CUDA(cudaMalloc((void **)&d_stats, sizeof(OverflowStats)));
     BFIR_CUDA(cudaMalloc((void **)&d_flag, sizeof(int)));
+    if (shared) return BFIR_OK;
     n_dither = n_dither_channels > 0 ? n_dither_channels : 1;
     return dither.init(n_dither, sampling_rate, rs, 0, L);
 }
 
 void Conv::destroy()
 {
-    if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); stream = nullptr; }
+    if (stream) { cudaStreamSynchronize(stream); if (own_stream) cudaStreamDestroy(stream); stream = nullptr; }
     if (tw) cudaFree(tw);
     if (scratch) cudaFree(scratch);
     if (stage) cudaFree(stage);
@@ -93,6 +97,11 @@ void Conv::destroy()
 using namespace bfir;
 
 struct bfir_conv { Conv impl; };
+struct bfir_td_conv {
+    Conv fft;                 // transforms of 2 * blocklen points on the owner's stream
+    void *d_coeffs = nullptr; // spectrum of [0 | h | 0] / (2 blocklen), plain HC layout
+    int blocklen = 0;
+};
 
 #define CONV_CHECK(c) do { if ((c) == nullptr) return BFIR_ERR_INVALID; } while (0)
 #define LAUNCH_1D(kernel, n, ...)                                                   \
@@ -289,6 +298,73 @@ int bfir_conv_convolve_eval(bfir_conv *c, const void *input_cbuf, void *buffer_c
     // buffer[0 .. L) = buffer[L .. 2L)                                             :401-402
     BFIR_CUDA(cudaMemcpyAsync(buffer_cbuf, (char *)buffer_cbuf + (size_t)g.L * g.rs, (size_t)g.L * g.rs, cudaMemcpyDeviceToDevice, g.stream));
     return BFIR_OK;
+}
+
+// log2_roof of the reference (log2.h:34-51) for n >= 2; n == 1 shifts by -1 there and is refused here
+int bfir_conv_td_block_length(int n_coeffs)
+{
+    if (n_coeffs < 2 || n_coeffs > (1 << 30)) return -1;
+    int lg = 0;
+    while ((1 << lg) < n_coeffs) lg++;
+    return 1 << lg;
+}
+
+int bfir_conv_td_new(bfir_conv *c, bfir_td_conv **out, const void *h_coeffs, int n_coeffs)
+{
+    CONV_CHECK(c);
+    if (out == nullptr || h_coeffs == nullptr) return BFIR_ERR_INVALID;
+    *out = nullptr;
+    Conv &g = c->impl;
+    const int bl = bfir_conv_td_block_length(n_coeffs);
+    if (bl < 0) { set_error("td_new: invalid coefficient count %d", n_coeffs); return BFIR_ERR_INVALID; }
+    bfir_td_conv *t = new bfir_td_conv;
+    int rc = t->fft.init(bl, g.rs, 0, 0, &g);
+    if (rc != BFIR_OK) { delete t; return rc; }
+    t->blocklen = bl;
+    const size_t rs = (size_t)g.rs;
+    if (cudaMalloc(&t->d_coeffs, 2 * (size_t)bl * rs) != cudaSuccess) { delete t; set_error("td_new: out of device memory"); return BFIR_ERR_CUDA; }
+    // [0_blocklen | coeffs | 0]                                                     fftw_convolver.cpp:731-736
+    cudaError_t e = cudaMemsetAsync(t->d_coeffs, 0, 2 * (size_t)bl * rs, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync((char *)t->d_coeffs + (size_t)bl * rs, h_coeffs, (size_t)n_coeffs * rs, cudaMemcpyHostToDevice, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream); // h_coeffs is the caller's, pageable
+    if (e != cudaSuccess) { bfir_conv_td_free(t); set_error("td_new: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    // in-place R2HC, then every element times 1 / (2 blocklen)                       :738-757
+    FwdArgs a = {};
+    a.in_mode = IN_TIME; a.out_layout = LAYOUT_HC; a.in = t->d_coeffs; a.out = t->d_coeffs;
+    a.scale_in = 1.0; a.scale_out = 1.0 / (double)(bl << 1);
+    rc = t->fft.fwd(a);
+    if (rc != BFIR_OK) { bfir_conv_td_free(t); return rc; }
+    *out = t;
+    return BFIR_OK;
+}
+
+int bfir_conv_td_blocklen(const bfir_td_conv *tdc) { return tdc ? tdc->blocklen : BFIR_ERR_INVALID; }
+const void *bfir_conv_td_coeffs(const bfir_td_conv *tdc) { return tdc ? tdc->d_coeffs : nullptr; }
+
+int bfir_conv_td_convolve(bfir_conv *c, bfir_td_conv *tdc, void *d_overlap_block)
+{
+    CONV_CHECK(c);
+    if (tdc == nullptr || d_overlap_block == nullptr) return BFIR_ERR_INVALID;
+    Conv &g = c->impl;
+    if (tdc->fft.stream != g.stream || tdc->fft.rs != g.rs) { set_error("td_convolve: td_conv_t belongs to another convolver"); return BFIR_ERR_INVALID; }
+    const int size = tdc->blocklen << 1;
+    FwdArgs f = {};                                                                // :763-777
+    f.in_mode = IN_TIME; f.out_layout = LAYOUT_HC; f.in = d_overlap_block; f.out = d_overlap_block; f.scale_in = 1.0; f.scale_out = 1.0;
+    int rc = tdc->fft.fwd(f);
+    if (rc != BFIR_OK) return rc;
+    if (g.rs == 4) LAUNCH_1D(hc_convolve_inplace_kernel<float>, size / 2 + 1, (float *)d_overlap_block, (const float *)tdc->d_coeffs, size);
+    else LAUNCH_1D(hc_convolve_inplace_kernel<double>, size / 2 + 1, (double *)d_overlap_block, (const double *)tdc->d_coeffs, size);
+    InvArgs a = {};
+    a.in_layout = LAYOUT_HC; a.out_mode = OUT_TIME; a.in = d_overlap_block; a.out = d_overlap_block; a.scale_in = 1.0;
+    return tdc->fft.inv(a);
+}
+
+void bfir_conv_td_free(bfir_td_conv *tdc)
+{
+    if (tdc == nullptr) return;
+    if (tdc->fft.stream) cudaStreamSynchronize(tdc->fft.stream);
+    if (tdc->d_coeffs) cudaFree(tdc->d_coeffs);
+    delete tdc;
 }
 
 int bfir_conv_cbuf2raw(bfir_conv *c, const void *cbuf, void *d_outbuf, int format, int byte_offset, int sample_spacing,

@@ -105,6 +105,19 @@ __global__ void dirac_kernel(const T *in, T *out, int N)
     out[i] = mul_rn<T>(in[i], (i & 1) ? -fraction : fraction);
 }
 
+// convolve_inplace_ordered, fftw_convolver.cpp:820-856: complex product on the plain HC layout
+// (Re at n, Im at size - n); one thread per bin, both halves of a bin are read before either is written
+template <class T>
+__global__ void hc_convolve_inplace_kernel(T *b, const T *c, int size)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, size2 = size >> 1;
+    if (n > size2) return;
+    if (n == 0 || n == size2) { b[n] = mul_rn<T>(b[n], c[n]); return; }
+    const T br = b[n], bi = b[size - n], cr = c[n], ci = c[size - n];
+    b[n] = sub_rn<T>(mul_rn<T>(br, cr), mul_rn<T>(bi, ci));
+    b[size - n] = add_rn<T>(mul_rn<T>(br, ci), mul_rn<T>(bi, cr));
+}
+
 // linear old->new ramp of convolver_crossfade_inplace, float branch fftw_convolver.cpp:296-305, used
 // for both precisions (the double branch :306-315 reads memory the function never wrote)
 template <class T>

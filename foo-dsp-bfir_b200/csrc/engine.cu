@@ -62,6 +62,16 @@ struct Engine {
     bool graphs_enabled = true;
     void invalidate_graphs() { for (int k = 0; k < 2; k++) if (step_graph[k]) { cudaGraphExecDestroy(step_graph[k]); step_graph[k] = nullptr; } }
     int run_step_graph();
+    // throughput variant of run (bfir_run_async / bfir_wait): block steps are queued on the group streams
+    // without joining them, so the copies and kernels of consecutive blocks overlap; a ring of events
+    // (one per group) marks the completion of each queued step
+    static const int kMaxInflight = 8;
+    cudaEvent_t ticket_ev[kMaxInflight][BFIR_MAX_GROUPS] = {};
+    long long next_ticket = 0, done_ticket = 0;    // tickets < done_ticket are known to be complete
+    bool async_open = false;                        // group streams hold work the engine's stream has not joined
+    int close_async();
+    long long run_host_async(const void *inbuf, void *outbuf);
+    int wait_ticket(long long t);
     int mac_split = 1;              // partition slices per CTA of the MAC kernel
     int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
     // optional per-kernel timing (bfir_set_profiling)
@@ -90,7 +100,7 @@ struct Engine {
     int enqueue_back(void *d_outbuf);
     int enqueue_block(const void *d_inbuf, void *d_outbuf);
     int run_host(const void *inbuf, void *outbuf);
-    int sync_and_probe();
+    int sync_and_probe(bool allow_rollback = true);
     int reset();
     int get_overflow(int ch, bfir_overflow_t *out);
 };
@@ -227,6 +237,8 @@ void Engine::destroy()
         if (groups[g].done) { cudaEventDestroy(groups[g].done); groups[g].done = nullptr; }
     }
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
+    for (int k = 0; k < kMaxInflight; k++)
+        for (int g = 0; g < BFIR_MAX_GROUPS; g++) if (ticket_ev[k][g]) { cudaEventDestroy(ticket_ev[k][g]); ticket_ev[k][g] = nullptr; }
     if (stream && own_stream) cudaStreamDestroy(stream);
     stream = nullptr;
     for (int q = 0; q < BFIR_MAX_PEERS; q++) if (peer_opened[q]) { cudaIpcCloseMemHandle(peer_opened[q]); peer_opened[q] = nullptr; }
@@ -592,7 +604,8 @@ int Engine::enqueue_back(void *d_outbuf)
 // one whole block step on device buffers: every group runs front and back on its own stream
 int Engine::enqueue_block(const void *d_inbuf, void *d_outbuf)
 {
-    int rc = fork();
+    int rc = close_async();
+    if (rc == BFIR_OK) rc = fork();
     for (int g = 0; g < n_groups && rc == BFIR_OK; g++) {
         rc = front_group(g, d_inbuf);
         if (rc == BFIR_OK) rc = back_group(g, d_outbuf);
@@ -603,9 +616,12 @@ int Engine::enqueue_block(const void *d_inbuf, void *d_outbuf)
 }
 
 // wait for the stream and apply the reference's NaN/Inf abort (brutefir.cpp:316-321)
-int Engine::sync_and_probe()
+int Engine::sync_and_probe(bool allow_rollback)
 {
+    int arc = close_async();
+    if (arc != BFIR_OK) return arc;
     BFIR_CUDA(cudaStreamSynchronize(stream));
+    done_ticket = next_ticket;
     prof_collect();
     const unsigned long long n = blocks_since_sync;
     blocks_since_sync = 0;
@@ -618,7 +634,7 @@ int Engine::sync_and_probe()
     if (bad != 0x7fffffff) {
         pinfo("NaN or Inf values in the system! Invalid input? Aborting.\n");
         const int threads = 256, blocks = (Ct + threads - 1) / threads;
-        if (n == 1) { // exact reference semantics: the aborted block does not advance the counters
+        if (n == 1 && allow_rollback) { // exact reference semantics: the aborted block does not advance the counters
             host_blockcounter--;
             engine_abort_fixup_kernel<<<blocks, threads, 0, stream>>>(state, n_groups, procblocks, pb_inc, Ct, bad);
             count_launch();
@@ -664,8 +680,55 @@ int Engine::run_step_graph()
     return BFIR_OK;
 }
 
+// the engine's stream catches up with whatever bfir_run_async left on the group streams
+int Engine::close_async()
+{
+    if (!async_open) return BFIR_OK;
+    async_open = false;
+    return join();
+}
+
+// queue H2D -> block step -> D2H of one block, group by group, and return its ticket (or an error code < 0)
+long long Engine::run_host_async(const void *inbuf, void *outbuf)
+{
+    int rc;
+    if (!async_open) { // the groups start after everything queued on the engine's stream so far
+        if ((rc = fork()) != BFIR_OK) return rc;
+        async_open = true;
+    }
+    if (next_ticket - done_ticket >= kMaxInflight && (rc = wait_ticket(next_ticket - kMaxInflight)) != BFIR_OK) return rc;
+    const int slot = (int)(next_ticket % kMaxInflight);
+    for (int g = 0; g < n_groups; g++) {
+        const Group &grp = groups[g];
+        const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
+        const size_t ioff = s0 * L * Ci * in_sf.bytes, ibytes = ns * L * Ci * in_sf.bytes;
+        const size_t ooff = s0 * L * Co * out_sf.bytes, obytes = ns * L * Co * out_sf.bytes;
+        BFIR_CUDA(cudaMemcpyAsync((char *)d_in + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, gstream(g)));
+        if ((rc = front_group(g, d_in)) != BFIR_OK) return rc;
+        if ((rc = back_group(g, d_out)) != BFIR_OK) return rc;
+        BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, gstream(g)));
+        if (ticket_ev[slot][g] == nullptr) BFIR_CUDA(cudaEventCreateWithFlags(&ticket_ev[slot][g], cudaEventDisableTiming));
+        BFIR_CUDA(cudaEventRecord(ticket_ev[slot][g], gstream(g)));
+    }
+    finish_block();
+    return next_ticket++;
+}
+
+// returns when the step with ticket t (and every earlier one) has delivered its output block
+int Engine::wait_ticket(long long t)
+{
+    if (t < 0 || t >= next_ticket) { set_error("bfir_wait: unknown ticket %lld", t); return BFIR_ERR_INVALID; }
+    for (; done_ticket <= t; done_ticket++) {
+        const int slot = (int)(done_ticket % kMaxInflight);
+        for (int g = 0; g < n_groups; g++) BFIR_CUDA(cudaEventSynchronize(ticket_ev[slot][g]));
+    }
+    if (*(volatile int *)h_flag != 0) return sync_and_probe(false);   // a probe fired: drain everything and report
+    return BFIR_OK;
+}
+
 int Engine::run_host(const void *inbuf, void *outbuf)
 {
+    if (async_open) { const int arc = close_async(); if (arc != BFIR_OK) return arc; }
     // latency path: one group, kernels replayed from a graph (after two plain blocks have configured them)
     if (graphs_enabled && n_groups == 1 && !xfade_pending && pcap == 0 && !peer.enabled && host_blockcounter >= 2) {
         BFIR_CUDA(cudaMemcpyAsync(d_in, inbuf, in_bytes, cudaMemcpyHostToDevice, stream));
@@ -752,12 +815,14 @@ int bfir_is_initialized(const bfir_engine *e) { return (e != nullptr && e->impl.
 
 int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.set_coeff(coeffs, n_coeffs, length, coeff_blocks, scale);
 }
 
 int bfir_set_coeff_crossfade(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.load_coeff(coeffs, nullptr, 0, n_coeffs, length, coeff_blocks, scale, true);
 }
@@ -765,6 +830,7 @@ int bfir_set_coeff_crossfade(bfir_engine *e, const void *const *coeffs, int n_co
 int bfir_set_coeff_device(bfir_engine *e, const void *d_coeffs, long long channel_stride, int n_coeffs, int length,
                           int coeff_blocks, double scale, int crossfade)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr || d_coeffs == nullptr) return BFIR_ERR_INVALID;
     return e->impl.load_coeff(nullptr, d_coeffs, channel_stride, n_coeffs, length, coeff_blocks, scale, crossfade != 0);
 }
@@ -788,13 +854,30 @@ int bfir_run(bfir_engine *e, const void *inbuf, void *outbuf)
 
 int bfir_run_device(bfir_engine *e, const void *d_inbuf, void *d_outbuf)
 {
+    if (e != nullptr) e->impl.close_async();
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     return e->impl.enqueue_block(d_inbuf, d_outbuf);
 }
 
+long long bfir_run_async(bfir_engine *e, const void *inbuf, void *outbuf)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (inbuf == nullptr || outbuf == nullptr) return BFIR_ERR_INVALID;
+    if (e->impl.peer.enabled) { bfir::set_error("bfir_run_async is not available on a partition shard"); return BFIR_ERR_INVALID; }
+    return e->impl.run_host_async(inbuf, outbuf);
+}
+
+int bfir_wait(bfir_engine *e, long long ticket)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.wait_ticket(ticket);
+}
+
 int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf)
 {
+    if (e != nullptr) e->impl.close_async();
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     return e->impl.enqueue_front(d_inbuf);
@@ -802,6 +885,7 @@ int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf)
 
 int bfir_run_finish_device(bfir_engine *e, void *d_outbuf)
 {
+    if (e != nullptr) e->impl.close_async();
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     return e->impl.enqueue_back(d_outbuf);
@@ -809,6 +893,7 @@ int bfir_run_finish_device(bfir_engine *e, void *d_outbuf)
 
 int bfir_peer_setup(bfir_engine *e, int rank, int world)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.peer_setup(rank, world);
 }
@@ -868,18 +953,21 @@ int bfir_sync(bfir_engine *e)
 
 int bfir_reset(bfir_engine *e)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.reset();
 }
 
 int bfir_get_overflow(bfir_engine *e, int channel, bfir_overflow_t *out)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.get_overflow(channel, out);
 }
 
 int bfir_check_overflows(bfir_engine *e)
 {
+    if (e != nullptr) e->impl.close_async();
     // brutefir::check_overflows + print_overflows, brutefir.cpp:371-388, 585-629
     if (e == nullptr) return BFIR_ERR_INVALID;
     Engine &g = e->impl;
@@ -910,6 +998,7 @@ int bfir_check_overflows(bfir_engine *e)
 
 int bfir_get_dither_ptr(bfir_engine *e, int channel, int *out)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr || out == nullptr || channel < 0 || channel >= e->impl.Cot) return BFIR_ERR_INVALID;
     if (!e->impl.dither_on) { set_error("engine has no dither state"); return BFIR_ERR_INVALID; }
     DitherState s;
@@ -921,6 +1010,7 @@ int bfir_get_dither_ptr(bfir_engine *e, int channel, int *out)
 
 int bfir_get_blockcounter(bfir_engine *e, unsigned int *out)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr || out == nullptr) return BFIR_ERR_INVALID;
     EngineState s;
     BFIR_CUDA(cudaStreamSynchronize(e->impl.stream));
@@ -931,12 +1021,14 @@ int bfir_get_blockcounter(bfir_engine *e, unsigned int *out)
 
 int bfir_set_crossbar(bfir_engine *e, const double *in_gains, const double *out_gains)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.set_crossbar(in_gains, out_gains);
 }
 
 int bfir_set_groups(bfir_engine *e, int n_groups)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.set_groups(n_groups);
 }
@@ -945,6 +1037,7 @@ int bfir_get_groups(bfir_engine *e) { return e ? e->impl.n_groups : BFIR_ERR_INV
 
 int bfir_set_stream(bfir_engine *e, void *cuda_stream)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     Engine &g = e->impl;
     if (g.stream && g.own_stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
@@ -956,6 +1049,7 @@ int bfir_set_stream(bfir_engine *e, void *cuda_stream)
 
 int bfir_set_profiling(bfir_engine *e, int max_blocks)
 {
+    if (e != nullptr) e->impl.close_async();
     if (e == nullptr || max_blocks < 0) return BFIR_ERR_INVALID;
     Engine &g = e->impl;
     BFIR_CUDA(cudaStreamSynchronize(g.stream));

@@ -39,6 +39,10 @@ public:
         return bfir_run(m_engine, inbuf, outbuf) == BFIR_OK ? 0 : -1;
     }
 
+    // throughput variant for batch callers (no reference counterpart): pinned buffers, see bfir_run_async
+    long long run_async(void *inbuf, void *outbuf) { return m_engine == NULL ? -1 : bfir_run_async(m_engine, inbuf, outbuf); }
+    int wait(long long ticket) { return (m_engine != NULL && bfir_wait(m_engine, ticket) == BFIR_OK) ? 0 : -1; }
+
     void reset() { if (m_engine != NULL) bfir_reset(m_engine); }
     void check_overflows() { if (m_engine != NULL) bfir_check_overflows(m_engine); }
 

@@ -42,6 +42,14 @@ public:
     void convolver_freq2time(void *input_cbuf, void *output_cbuf) { bfir_conv_freq2time(m_c, input_cbuf, output_cbuf); }
     void convolver_convolve_eval(void *input_cbuf, void *buffer_cbuf, void *output_cbuf)
     { bfir_conv_convolve_eval(m_c, input_cbuf, buffer_cbuf, output_cbuf); }
+    // td_conv_t (fftw_convolver.hpp:18-26, :158-166): opaque here; `coeffs` host samples, `overlap_block` device
+    int convolver_td_block_length(int n_coeffs) { return bfir_conv_td_block_length(n_coeffs); }
+    bfir_td_conv *convolver_td_new(void *coeffs, int n_coeffs)
+    {
+        bfir_td_conv *t = nullptr;
+        return bfir_conv_td_new(m_c, &t, coeffs, n_coeffs) == BFIR_OK ? t : nullptr;
+    }
+    void convolver_td_convolve(bfir_td_conv *tdc, void *overlap_block) { bfir_conv_td_convolve(m_c, tdc, overlap_block); }
     void convolver_cbuf2raw(void *cbuf, void *outbuf, struct bfir_buffer_format_t *bf, bool apply_dither,
                             int dither_channel, bfir_overflow_t *overflow)
     { bfir_conv_cbuf2raw(m_c, cbuf, outbuf, bf->format, bf->byte_offset, bf->sample_spacing, apply_dither ? 1 : 0, dither_channel, overflow); }

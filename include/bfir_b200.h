@@ -137,6 +137,19 @@ int bfir_run(bfir_engine *e, const void *inbuf, void *outbuf);
 int bfir_run_device(bfir_engine *e, const void *d_inbuf, void *d_outbuf);
 int bfir_sync(bfir_engine *e);
 
+/* Throughput variant of bfir_run for offline / batch callers (no reference counterpart: brutefir::run is
+ * synchronous, brutefir.cpp:245-343). Queues H2D -> block step -> D2H of one block on the stream groups and
+ * returns a ticket (>= 0) without waiting, so the copies and kernels of consecutive blocks overlap.
+ * inbuf/outbuf are PINNED host buffers laid out as for bfir_run; they must stay untouched until
+ * bfir_wait(ticket) (or bfir_sync) has returned. At most 8 steps are in flight: a ninth call first waits
+ * for the oldest. bfir_wait returns when the step with that ticket and all earlier ones have delivered
+ * their output; BFIR_ERR_NONFINITE if a NaN/Inf probe fired in any block since the last wait/sync (all
+ * queued work is drained first; unlike bfir_run the block counter is not rolled back). Any other call
+ * on the engine joins the queued steps before it does its own work. Returns an error code < 0 instead
+ * of a ticket on failure. */
+long long bfir_run_async(bfir_engine *e, const void *inbuf, void *outbuf);
+int bfir_wait(bfir_engine *e, long long ticket);
+
 /* brutefir::reset (brutefir.cpp:347-367): zeroes counters and overflow statistics, NOT the buffers */
 int bfir_reset(bfir_engine *e);
 /* struct bfoverflow_t overflow[channel] (brutefir.hpp:126) */
@@ -236,6 +249,20 @@ int bfir_conv_dirac_convolve_inplace(bfir_conv *c, void *cbuf);
 int bfir_conv_freq2time(bfir_conv *c, const void *input_cbuf, void *output_cbuf);
 /* convolver_convolve_eval (fftw_convolver.cpp:378-403): buffer_cbuf is 1.5 cbufs, zeroed before first use */
 int bfir_conv_convolve_eval(bfir_conv *c, const void *input_cbuf, void *buffer_cbuf, void *output_cbuf);
+/* Small one-shot convolver, td_conv_t (fftw_convolver.hpp:18-26): convolver_td_block_length / _td_new /
+ * _td_convolve (fftw_convolver.cpp:698-777) with convolve_inplace_ordered (:820-856). `h_coeffs` are
+ * n_coeffs HOST samples of the convolver's precision; the overlap block is a DEVICE buffer of
+ * 2 * blocklen reals, transformed in place: R2HC, complex product with the spectrum of
+ * [0_blocklen | coeffs | 0] / (2 blocklen) on the plain half-complex layout, HC2R. n_coeffs == 1, where
+ * the reference shifts by -1 (log2.h:38-43), is refused; blocklen must be a supported transform size
+ * (>= 16). The reference never frees a td_conv_t; bfir_conv_td_free does. */
+typedef struct bfir_td_conv bfir_td_conv;
+int bfir_conv_td_block_length(int n_coeffs);
+int bfir_conv_td_new(bfir_conv *c, bfir_td_conv **out, const void *h_coeffs, int n_coeffs);
+int bfir_conv_td_blocklen(const bfir_td_conv *tdc);
+const void *bfir_conv_td_coeffs(const bfir_td_conv *tdc); /* device pointer, 2 * blocklen reals (HC) */
+int bfir_conv_td_convolve(bfir_conv *c, bfir_td_conv *tdc, void *d_overlap_block);
+void bfir_conv_td_free(bfir_td_conv *tdc);
 /* convolver_cbuf2raw (fftw_convolver.cpp:406-466): `overflow` is a HOST struct, read and updated;
  * synchronous. dither_channel selects the dither_state_t. */
 int bfir_conv_cbuf2raw(bfir_conv *c, const void *cbuf, void *d_outbuf, int format, int byte_offset,

@@ -92,6 +92,11 @@ def lib(kind):
     ns.conv_dirac_convolve = sig("conv_dirac_convolve", None, vp, vp, vp)
     ns.conv_dirac_convolve_inplace = sig("conv_dirac_convolve_inplace", None, vp, vp)
     ns.conv_convolve_eval = sig("conv_convolve_eval", None, vp, vp, vp, vp)
+    ns.conv_td_block_length = sig("conv_td_block_length", ci, vp, ci)
+    ns.conv_td_new = sig("conv_td_new", vp, vp, vp, ci)
+    ns.conv_td_coeffs = sig("conv_td_coeffs", None, vp, vp, ci)
+    ns.conv_td_convolve = sig("conv_td_convolve", None, vp, vp, vp)
+    ns.conv_td_free = sig("conv_td_free", None, vp)
     ns.conv_cbuf2raw = sig("conv_cbuf2raw", ci, vp, vp, vp, ci, ci, ci, ci, ci, ctypes.POINTER(Overflow))
     ns.conv_coeffs2cbuf = sig("conv_coeffs2cbuf", ci, vp, vp, ci, cd, vp)
     ns.conv_runtime_coeffs2cbuf = sig("conv_runtime_coeffs2cbuf", None, vp, vp, vp)
@@ -209,6 +214,29 @@ class Convolver:
         out = self.cbuf() if out is None else out
         self.ns.conv_convolve_eval(self.h, _ptr(x), _ptr(buffer), _ptr(out))
         return out
+
+    # small one-shot convolver (fftw_convolver.cpp:698-777): returns (blocklen, handle)
+    def td_block_length(self, n_coeffs):
+        return self.ns.conv_td_block_length(self.h, n_coeffs)
+
+    def td_new(self, coeffs):
+        coeffs = np.ascontiguousarray(coeffs, dtype=self.dtype)
+        bl = self.td_block_length(len(coeffs))
+        if bl < 0:
+            return -1, None
+        return bl, self.ns.conv_td_new(self.h, _ptr(coeffs), len(coeffs))
+
+    def td_coeffs(self, tdc, blocklen):
+        out = np.zeros(2 * blocklen, dtype=self.dtype)
+        self.ns.conv_td_coeffs(tdc, _ptr(out), out.nbytes)
+        return out
+
+    def td_convolve(self, tdc, overlap_block):
+        self.ns.conv_td_convolve(self.h, tdc, _ptr(overlap_block))
+        return overlap_block
+
+    def td_free(self, tdc):
+        self.ns.conv_td_free(tdc)
 
     def cbuf2raw(self, cbuf, out_raw, fmt, index, spacing, apply_dither, dither_channel, overflow):
         assert self.ns.conv_cbuf2raw(self.h, _ptr(cbuf), _ptr(out_raw), fmt, index, spacing,

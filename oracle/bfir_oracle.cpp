@@ -512,6 +512,44 @@ struct Engine {
     }
 };
 
+// ---- small one-shot convolver on plain half-complex buffers (fftw_convolver.cpp:698-777, 820-856)
+template <class T>
+struct TdConv {
+    int blocklen;
+    oracle_fft::RealFFT<T> fft;
+    std::vector<T> coeffs; // spectrum of [0_blocklen | h | 0], scaled by 1/(2 blocklen), HC layout
+    TdConv(const T *h, int n, int bl) : blocklen(bl), fft(2 * bl), coeffs(2 * (size_t)bl, (T)0)
+    {
+        memcpy(&coeffs[bl], h, sizeof(T) * n);             // :731-736
+        fft.r2hc(coeffs.data(), coeffs.data());            // :740 / :750
+        const T s = (T)(1.0 / (T)(bl << 1));               // :741 / :751
+        for (int i = 0; i < 2 * bl; i++) coeffs[i] *= s;
+    }
+    void convolve(T *b) // :763-777 with convolve_inplace_ordered :820-856
+    {
+        const int size = 2 * blocklen, size2 = blocklen;
+        const T *c = coeffs.data();
+        fft.r2hc(b, b);
+        b[0] *= c[0];
+        for (int n = 1; n < size2; n++) {
+            const T a = b[n];
+            b[n] = a * c[n] - b[size - n] * c[size - n];
+            b[size - n] = a * c[size - n] + b[size - n] * c[n];
+        }
+        b[size2] *= c[size2];
+        fft.hc2r(b, b);
+    }
+};
+struct td_handle { int realsize; TdConv<float> *f; TdConv<double> *d; };
+
+static int td_block_length(int n_coeffs) // :698-706 with log2_roof (log2.h:34-51); n == 1 is refused (shift by -1 there)
+{
+    if (n_coeffs < 2) return -1;
+    int lg = 31;
+    while (((unsigned)n_coeffs & (1u << lg)) == 0 && lg > 0) lg--;
+    if (((unsigned)n_coeffs & ~(1u << lg)) != 0) lg++;
+    return 1 << lg;
+}
 struct conv_handle {
     int realsize;
     Conv<float> *cf;
@@ -647,6 +685,35 @@ void orc_conv_convolve_eval(void *p, void *in, void *buffer, void *out)
     conv_handle *h = (conv_handle *)p;
     if (h->realsize == 4) h->cf->convolve_eval((float *)in, (float *)buffer, (float *)out);
     else h->cd->convolve_eval((double *)in, (double *)buffer, (double *)out);
+}
+
+int orc_conv_td_block_length(void *, int n_coeffs) { return td_block_length(n_coeffs); }
+void *orc_conv_td_new(void *p, void *coeffs, int n_coeffs)
+{
+    conv_handle *h = (conv_handle *)p;
+    const int bl = td_block_length(n_coeffs);
+    if (bl < 0) return NULL;
+    td_handle *t = new td_handle();
+    t->realsize = h->realsize;
+    if (h->realsize == 4) t->f = new TdConv<float>((const float *)coeffs, n_coeffs, bl);
+    else t->d = new TdConv<double>((const double *)coeffs, n_coeffs, bl);
+    return t;
+}
+void orc_conv_td_coeffs(void *tdc, void *dst, int nbytes)
+{
+    td_handle *t = (td_handle *)tdc;
+    memcpy(dst, t->realsize == 4 ? (const void *)t->f->coeffs.data() : (const void *)t->d->coeffs.data(), nbytes);
+}
+void orc_conv_td_convolve(void *, void *tdc, void *overlap_block)
+{
+    td_handle *t = (td_handle *)tdc;
+    if (t->realsize == 4) t->f->convolve((float *)overlap_block); else t->d->convolve((double *)overlap_block);
+}
+void orc_conv_td_free(void *tdc)
+{
+    td_handle *t = (td_handle *)tdc;
+    if (t == NULL) return;
+    delete t->f; delete t->d; delete t;
 }
 
 int orc_conv_cbuf2raw(void *p, void *cbuf, void *outbuf, int format, int index, int spacing,

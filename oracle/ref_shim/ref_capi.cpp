@@ -111,6 +111,30 @@ void ref_conv_dirac_convolve(void *p, void *in, void *out) { ((conv_handle *)p)-
 void ref_conv_dirac_convolve_inplace(void *p, void *cbuf) { ((conv_handle *)p)->conv->convolver_dirac_convolve_inplace(cbuf); }
 void ref_conv_convolve_eval(void *p, void *in, void *buffer, void *out) { ((conv_handle *)p)->conv->convolver_convolve_eval(in, buffer, out); }
 
+// small one-shot convolver (fftw_convolver.cpp:698-777). n_coeffs = 1 makes the reference shift by -1
+// (log2_roof(1) == -1, log2.h:38-43), so the wrappers refuse it instead of calling into that.
+int ref_conv_td_block_length(void *p, int n_coeffs)
+{
+    if (n_coeffs == 1) return -1;
+    return ((conv_handle *)p)->conv->convolver_td_block_length(n_coeffs);
+}
+void *ref_conv_td_new(void *p, void *coeffs, int n_coeffs)
+{
+    if (n_coeffs < 2) return NULL;
+    return ((conv_handle *)p)->conv->convolver_td_new(coeffs, n_coeffs);
+}
+void ref_conv_td_coeffs(void *tdc, void *dst, int nbytes) { memcpy(dst, ((td_conv_t *)tdc)->coeffs, nbytes); }
+void ref_conv_td_convolve(void *p, void *tdc, void *overlap_block)
+{
+    ((conv_handle *)p)->conv->convolver_td_convolve((td_conv_t *)tdc, overlap_block);
+}
+void ref_conv_td_free(void *tdc) // the reference never frees a td_conv_t
+{
+    if (tdc == NULL) return;
+    _aligned_free(((td_conv_t *)tdc)->coeffs);
+    free(tdc);
+}
+
 // overflow: {n_overflows, intlargest, largest, max} passed as a caller-owned bfoverflow_t image
 int ref_conv_cbuf2raw(void *p, void *cbuf, void *outbuf, int format, int index, int spacing,
                       int apply_dither, int dither_channel, struct bfoverflow_t *overflow)

@@ -78,6 +78,16 @@ def main():
         G[k + "preprocess_coeff_in"] = pc_in
         G[k + "preprocess_coeff"] = cv.preprocess_coeff(pc_in, 4, 0.5)
 
+        # td_conv_t: small one-shot convolver on the plain HC layout (fftw_convolver.cpp:698-777)
+        td_rng = np.random.default_rng(31 + rs)  # own generator: the vectors above and below keep their draws
+        td_h = (td_rng.standard_normal(31) * np.exp(-np.arange(31) / 8.0)).astype(dt)
+        bl, tdc = cv.td_new(td_h)
+        td_x = td_rng.uniform(-1, 1, 2 * bl).astype(dt)
+        G[k + "td_h"], G[k + "td_x"] = td_h, td_x
+        G[k + "td_coeffs"] = cv.td_coeffs(tdc, bl)
+        G[k + "td_convolve"] = cv.td_convolve(tdc, td_x.copy())
+        cv.td_free(tdc)
+
         # codecs
         C = 3
         xr = rng.uniform(-1, 1, (L, C))

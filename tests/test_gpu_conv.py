@@ -277,3 +277,39 @@ def test_dither_map_entry_255_policy(pkg, oracle):
         g.convolver_cbuf2raw(g.cbuf(y), draw, 2, 0, 1, True, 0, og)
         o.cbuf2raw(y, out_ref, 2, 0, 1, True, 0, orf)
         assert np.array_equal(draw.download(np.uint8), out_ref), blk
+
+
+# ---- td_conv_t: the small one-shot convolver (fftw_convolver.cpp:698-777, 820-856)
+@pytest.mark.parametrize("rs", [4, 8])
+@pytest.mark.parametrize("n_coeffs", [9, 16, 31, 33, 200, 1024])
+def test_td_convolver(pkg, oracle, rs, n_coeffs):
+    g, o = make(pkg, oracle, 256, rs)
+    rng = np.random.default_rng(n_coeffs)
+    h = (rng.standard_normal(n_coeffs) * np.exp(-np.arange(n_coeffs) / 12.0)).astype(g.dtype)
+    bl, ot = o.td_new(h)
+    assert g.convolver_td_block_length(n_coeffs) == bl == o.td_block_length(n_coeffs)
+    gt = g.convolver_td_new(h)
+    assert gt is not None
+    assert rel_rms(g.convolver_td_coeffs(gt), o.td_coeffs(ot, bl)) < TOL[rs]
+    for _ in range(3):
+        x = rng.uniform(-1, 1, 2 * bl).astype(g.dtype)
+        d = g.rawbuf(x)
+        g.convolver_td_convolve(gt, d)
+        ref = o.td_convolve(ot, x.copy())
+        assert rel_rms(d.download(g.dtype), ref) < TOL[rs] * 2
+        # and it is what it says: circular convolution of the block with the coefficients placed at blocklen
+        hp = np.zeros(2 * bl)
+        hp[bl:bl + n_coeffs] = h
+        want = np.real(np.fft.ifft(np.fft.fft(x.astype(np.float64)) * np.fft.fft(hp)))
+        assert rel_rms(d.download(g.dtype), want) < TOL[rs] * 4
+    g.convolver_td_free(gt)
+    o.td_free(ot)
+
+
+def test_td_convolver_limits(pkg):
+    g = pkg.FftwConvolver(64, 4)
+    assert g.convolver_td_block_length(0) == -1          # fftw_convolver.cpp:700-703
+    assert g.convolver_td_block_length(1) == -1          # reference: 1 << log2_roof(1) == 1 << -1, refused
+    assert [g.convolver_td_block_length(n) for n in (2, 3, 4, 5, 31, 32, 33)] == [2, 4, 4, 8, 32, 32, 64]
+    assert g.convolver_td_new(np.ones(1, dtype=np.float32)) is None
+    assert g.convolver_td_new(np.ones(5, dtype=np.float32)) is None   # blocklen 8 < smallest transform (16)

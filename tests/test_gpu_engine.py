@@ -422,3 +422,64 @@ def test_check_overflows_prints_peaks(pkg):
         assert g.check_overflows() == 0              # unchanged since the last call: silent
     finally:
         pkg.load_library().bfir_set_print_callback(pkg.PRINT_CB(0))
+
+
+@pytest.mark.parametrize("groups", [1, 2, 4])
+@pytest.mark.parametrize("out_fmt,dither", [(8, False), (2, True)])
+def test_run_async_equals_run(pkg, groups, out_fmt, dither):
+    """bfir_run_async / bfir_wait: the pipelined variant is a scheduling choice only -- bit-identical
+    output to the synchronous bfir_run, with several blocks in flight and the ticket ring wrapping"""
+    import torch
+    L, P, C, S = 256, 4, 2, 5
+    h = [decay_filter(c, L * P) for c in range(C * S)]
+    sync_e = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, out_fmt, 2000, dither, n_streams=S, n_groups=1)
+    async_e = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, out_fmt, 2000, dither, n_streams=S, n_groups=groups)
+    assert sync_e.set_coeff(h, P) == 0 and async_e.set_coeff(h, P) == 0
+    nblk, nb = 27, pkg.FORMAT_BYTES[out_fmt]
+    x = white_noise(5, nblk * L, C * S).astype(np.float32)
+    blocks = [np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2)).ravel() for b in range(nblk)]
+    want = []
+    for b in range(nblk):
+        rc, out = sync_e.run(blocks[b].view(np.uint8))
+        assert rc == 0
+        want.append(out.copy())
+    pin_in = [torch.from_numpy(blk).pin_memory() for blk in blocks]
+    pin_out = [torch.zeros(S * L * C * nb, dtype=torch.uint8).pin_memory() for _ in range(nblk)]
+    tickets = []
+    for b in range(nblk):
+        if b == 13:                                # a synchronous call in between joins the queued steps first
+            rc, out = async_e.run(blocks[b].view(np.uint8))
+            assert rc == 0 and np.array_equal(out, want[b])
+            tickets.append(None)
+            continue
+        tickets.append(async_e.run_async(pin_in[b].numpy(), pin_out[b].numpy()))
+        if b >= 3 and b % 3 == 0 and tickets[b - 3] is not None:   # wait with three steps still queued behind
+            assert async_e.wait(tickets[b - 3]) == 0
+            assert np.array_equal(pin_out[b - 3].numpy(), want[b - 3])
+    assert async_e.wait(tickets[-1]) == 0
+    for b in range(nblk):
+        if tickets[b] is not None:
+            assert np.array_equal(pin_out[b].numpy(), want[b]), b
+    assert async_e.blockcounter() == sync_e.blockcounter() == nblk
+    for c in range(C * S):
+        a, w = async_e.overflow(c), sync_e.overflow(c)
+        assert (a.n_overflows, a.largest) == (w.n_overflows, w.largest)
+    with pytest.raises(pkg.BfirError):
+        async_e.wait(10 ** 6)                      # a ticket that was never handed out
+
+
+def test_run_async_reports_nonfinite_at_wait(pkg):
+    import torch
+    L, P, C = 128, 2, 2
+    e = pkg.Brutefir(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 2000, False, n_streams=4, n_groups=2)
+    assert e.set_coeff([decay_filter(c, L * P) for c in range(4 * C)], P) == 0
+    good = torch.from_numpy(white_noise(1, L, 4 * C).ravel().copy()).pin_memory()
+    bad = good.clone().pin_memory()
+    bad[5] = float("nan")
+    outs = [torch.zeros(4 * L * C, dtype=torch.float64).pin_memory() for _ in range(3)]
+    t0 = e.run_async(good.numpy(), outs[0].numpy())
+    assert e.wait(t0) == 0
+    t1 = e.run_async(bad.numpy(), outs[1].numpy())
+    t2 = e.run_async(good.numpy(), outs[2].numpy())
+    assert e.wait(t2) == -1                         # raised by the block behind t1, reported at the wait
+    assert e.wait(t1) == 0 and e.sync() == 0        # reported once

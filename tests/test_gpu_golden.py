@@ -62,6 +62,18 @@ def test_convolver_entry_points(pkg, G, rs):
 
 
 @pytest.mark.parametrize("rs", [4, 8])
+def test_td_convolver(pkg, G, rs):
+    k = "conv/%s/" % TAGS[rs]
+    g = pkg.FftwConvolver(64, rs, 2, 2000)
+    t = g.convolver_td_new(G[k + "td_h"])
+    assert rel_rms(g.convolver_td_coeffs(t), G[k + "td_coeffs"]) < TOL[rs]
+    d = g.rawbuf(G[k + "td_x"])
+    g.convolver_td_convolve(t, d)
+    assert rel_rms(d.download(g.dtype), G[k + "td_convolve"]) < TOL[rs] * 2
+    g.convolver_td_free(t)
+
+
+@pytest.mark.parametrize("rs", [4, 8])
 def test_codecs_and_dither(pkg, G, rs):
     L, C, tag = 64, 3, TAGS[rs]
     g = pkg.FftwConvolver(L, rs, 2, 2000)

@@ -55,6 +55,11 @@ def test_convolver_entry_points_match_golden(oracle, G, kind, rs):
         assert exact(cv.convolve_eval(h_, buf), G[k + "convolve_eval"][i])
     assert exact(buf, G[k + "convolve_eval_buffer"])
     assert exact(cv.preprocess_coeff(G[k + "preprocess_coeff_in"], 4, 0.5), G[k + "preprocess_coeff"])
+    bl, tdc = cv.td_new(G[k + "td_h"])                  # td_conv_t, fftw_convolver.cpp:698-777
+    assert bl == 32 == len(G[k + "td_x"]) // 2
+    assert exact(cv.td_coeffs(tdc, bl), G[k + "td_coeffs"])
+    assert exact(cv.td_convolve(tdc, G[k + "td_x"].copy()), G[k + "td_convolve"])
+    cv.td_free(tdc)
 
 
 @pytest.mark.parametrize("kind", oracle_kinds())
@@ -258,3 +263,21 @@ def test_nonfinite_and_edge_cases(oracle):
         x = np.zeros((64, 2), dtype=np.float32)
         x[5, 0] = np.nan
         assert e.run(x.view(np.uint8).ravel())[0] == -1 and e.blockcounter() == 0
+
+
+@pytest.mark.parametrize("kind", oracle_kinds())
+@pytest.mark.parametrize("rs", [4, 8])
+def test_td_convolver_is_a_circular_convolution(oracle, kind, rs):
+    """td_conv_t (fftw_convolver.cpp:698-777): block (x) [0_blocklen | h | 0], circular over 2 * blocklen."""
+    cv = oracle.Convolver(64, rs, kind)
+    assert [cv.td_block_length(n) for n in (0, 1, 2, 3, 4, 5, 31, 32, 33)] == [-1, -1, 2, 4, 4, 8, 32, 32, 64]
+    rng = np.random.default_rng(5)
+    for n in (2, 7, 31, 64, 100):
+        h = rng.standard_normal(n).astype(cv.dtype)
+        bl, tdc = cv.td_new(h)
+        x = rng.uniform(-1, 1, 2 * bl).astype(cv.dtype)
+        hp = np.zeros(2 * bl)
+        hp[bl:bl + n] = h
+        want = np.real(np.fft.ifft(np.fft.fft(x.astype(np.float64)) * np.fft.fft(hp)))
+        assert rel_rms(cv.td_convolve(tdc, x.copy()), want) < (2e-6 if rs == 4 else 1e-14)
+        cv.td_free(tdc)
