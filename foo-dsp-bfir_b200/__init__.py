@@ -68,6 +68,8 @@ API = [
     ("bfir_run", _ci, [_vp, _vp, _vp]),
     ("bfir_run_device", _ci, [_vp, _vp, _vp]),
     ("bfir_run_async", ctypes.c_longlong, [_vp, _vp, _vp]),
+    ("bfir_run_device_pipelined", _ci, [_vp, _vp, _vp]),
+    ("bfir_join", _ci, [_vp]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -287,6 +289,12 @@ class Brutefir:
 
     def run_device(self, d_in, d_out):
         _check(self.lib.bfir_run_device(self.h, _ptr(d_in), _ptr(d_out)))
+
+    def run_device_pipelined(self, d_in, d_out):
+        _check(self.lib.bfir_run_device_pipelined(self.h, _ptr(d_in), _ptr(d_out)))
+
+    def join(self):
+        _check(self.lib.bfir_join(self.h))
 
     def run_async(self, inbuf, outbuf):
         """Queue one block on PINNED host buffers; returns a ticket for wait(). Buffers stay untouched until then."""

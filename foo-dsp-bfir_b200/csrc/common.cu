@@ -5,6 +5,7 @@ namespace bfir {
 
 thread_local std::string g_last_error;
 std::atomic<unsigned long long> g_launches(0);
+thread_local unsigned long long t_launches = 0;
 void (*g_print_cb)(const char *) = nullptr;
 
 void set_error(const char *fmt, ...)

@@ -23,7 +23,8 @@ extern void (*g_print_cb)(const char *);
 void set_error(const char *fmt, ...);
 void pinfo(const char *fmt, ...); // reference brutefir/pinfo.c:26-39
 
-inline void count_launch(unsigned long long n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern thread_local unsigned long long t_launches;   // this thread's share (graph capture counts its own launches with it)
+inline void count_launch(unsigned long long n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); t_launches += n; }
 
 #define BFIR_CUDA(call)                                                                          \
     do {                                                                                         \

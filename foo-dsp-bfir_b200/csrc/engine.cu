@@ -99,6 +99,7 @@ struct Engine {
     int enqueue_front(const void *d_inbuf);
     int enqueue_back(void *d_outbuf);
     int enqueue_block(const void *d_inbuf, void *d_outbuf);
+    int enqueue_block_pipelined(const void *d_inbuf, void *d_outbuf);
     int run_host(const void *inbuf, void *outbuf);
     int sync_and_probe(bool allow_rollback = true);
     int reset();
@@ -615,6 +616,23 @@ int Engine::enqueue_block(const void *d_inbuf, void *d_outbuf)
     return rc;
 }
 
+// the same without the join: the groups of consecutive blocks run into each other (a group that is done with
+// block t starts block t+1 while others still work on t); close_async() joins
+int Engine::enqueue_block_pipelined(const void *d_inbuf, void *d_outbuf)
+{
+    int rc = BFIR_OK;
+    if (!async_open) {
+        if ((rc = fork()) != BFIR_OK) return rc;
+        async_open = n_groups > 1;
+    }
+    for (int g = 0; g < n_groups && rc == BFIR_OK; g++) {
+        rc = front_group(g, d_inbuf);
+        if (rc == BFIR_OK) rc = back_group(g, d_outbuf);
+    }
+    finish_block();
+    return rc;
+}
+
 // wait for the stream and apply the reference's NaN/Inf abort (brutefir.cpp:316-321)
 int Engine::sync_and_probe(bool allow_rollback)
 {
@@ -658,7 +676,7 @@ int Engine::run_step_graph()
 {
     const int par = (int)(host_blockcounter & 1u);
     if (step_graph[par] == nullptr) {
-        const unsigned long long before = g_launches.load();
+        const unsigned long long before = t_launches;
         cudaGraph_t graph = nullptr;
         BFIR_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
         int rc = front_group(0, d_in);
@@ -672,7 +690,7 @@ int Engine::run_step_graph()
         ce = cudaGraphInstantiate(&step_graph[par], graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { step_graph[par] = nullptr; set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); return BFIR_ERR_CUDA; }
-        step_graph_launches[par] = g_launches.load() - before;
+        step_graph_launches[par] = t_launches - before;
         g_launches.fetch_sub(step_graph_launches[par]);   // nothing ran during capture
     }
     BFIR_CUDA(cudaGraphLaunch(step_graph[par], stream));
@@ -838,6 +856,8 @@ int bfir_set_coeff_device(bfir_engine *e, const void *d_coeffs, long long channe
 static int check_ready(bfir_engine *e)
 {
     if (e == nullptr) return BFIR_ERR_INVALID;
+    int cur = -1; // a host thread that has not touched CUDA yet sits on device 0: follow the engine
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != e->impl.device) BFIR_CUDA(cudaSetDevice(e->impl.device));
     if (!e->impl.initialized) { set_error("run before set_coeff"); return BFIR_ERR_NOT_READY; }
     if (e->impl.xbar && !e->impl.xbar_set) { set_error("run before set_crossbar"); return BFIR_ERR_NOT_READY; }
     if (!e->impl.peer_ready()) { set_error("fused reduce: not every peer receive buffer is connected"); return BFIR_ERR_NOT_READY; }
@@ -858,6 +878,20 @@ int bfir_run_device(bfir_engine *e, const void *d_inbuf, void *d_outbuf)
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     return e->impl.enqueue_block(d_inbuf, d_outbuf);
+}
+
+int bfir_run_device_pipelined(bfir_engine *e, const void *d_inbuf, void *d_outbuf)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (e->impl.peer.enabled) { bfir::set_error("bfir_run_device_pipelined is not available on a partition shard"); return BFIR_ERR_INVALID; }
+    return e->impl.enqueue_block_pipelined(d_inbuf, d_outbuf);
+}
+
+int bfir_join(bfir_engine *e)
+{
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.close_async();
 }
 
 long long bfir_run_async(bfir_engine *e, const void *inbuf, void *outbuf)

@@ -149,6 +149,12 @@ int bfir_sync(bfir_engine *e);
  * of a ticket on failure. */
 long long bfir_run_async(bfir_engine *e, const void *inbuf, void *outbuf);
 int bfir_wait(bfir_engine *e, long long ticket);
+/* bfir_run_device without the join at the end of the call: the stream groups of consecutive blocks run into
+ * each other, and the engine's stream does NOT see the result until bfir_join (stream-ordered, no host wait),
+ * bfir_sync or any other call on the engine. A group reads only its own streams' slice of d_inbuf / writes
+ * its slice of d_outbuf, in call order; the caller must not rewrite a buffer that a queued block still uses. */
+int bfir_run_device_pipelined(bfir_engine *e, const void *d_inbuf, void *d_outbuf);
+int bfir_join(bfir_engine *e);
 
 /* brutefir::reset (brutefir.cpp:347-367): zeroes counters and overflow statistics, NOT the buffers */
 int bfir_reset(bfir_engine *e);

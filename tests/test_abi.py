@@ -64,3 +64,16 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 for needle in ("import oracle", "from oracle", "libbfir_ref", "libbfir_oracle", "oracle/_", "fft_r2r"):
                     assert needle not in text, (dirpath, f, needle)
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/bfir_b200.h must compile as C99 (a cgo / JNI / P-Invoke binding parses it as C)"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not found")
+    src = tmp_path / "h.c"
+    src.write_text('#include "bfir_b200.h"\nint main(void) { bfir_config_t c; (void)c; return BFIR_OK; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -483,3 +483,31 @@ def test_run_async_reports_nonfinite_at_wait(pkg):
     t2 = e.run_async(good.numpy(), outs[2].numpy())
     assert e.wait(t2) == -1                         # raised by the block behind t1, reported at the wait
     assert e.wait(t1) == 0 and e.sync() == 0        # reported once
+
+
+def test_run_device_pipelined_equals_run_device(pkg):
+    """bfir_run_device_pipelined + bfir_join: no join between blocks, same bits as bfir_run_device"""
+    import torch
+    L, P, C, S = 512, 3, 2, 6
+    h = [decay_filter(c, L * P) for c in range(C * S)]
+    a = pkg.Brutefir(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 2000, False, n_streams=S, n_groups=1)
+    b = pkg.Brutefir(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 2000, False, n_streams=S, n_groups=3)
+    assert a.set_coeff(h, P) == 0 and b.set_coeff(h, P) == 0
+    st = torch.cuda.Stream()
+    b.set_stream(st.cuda_stream)
+    nblk = 11
+    d_in = [torch.from_numpy(white_noise(40 + k, L, C * S).ravel().copy()).cuda() for k in range(nblk)]
+    out_a = [torch.zeros(S * L * C, dtype=torch.float64, device="cuda") for _ in range(nblk)]
+    out_b = [torch.zeros(S * L * C, dtype=torch.float64, device="cuda") for _ in range(nblk)]
+    torch.cuda.synchronize()
+    for k in range(nblk):
+        a.run_device(d_in[k], out_a[k])
+        b.run_device_pipelined(d_in[k], out_b[k])
+    b.join()                                          # stream-ordered: work queued on `st` after this sees every block
+    with torch.cuda.stream(st):
+        total = torch.stack(out_b).sum()
+    assert a.sync() == 0 and b.sync() == 0
+    for k in range(nblk):
+        assert torch.equal(out_a[k], out_b[k]), k
+    assert float(total) == float(torch.stack(out_a).sum())
+    assert b.blockcounter() == nblk
