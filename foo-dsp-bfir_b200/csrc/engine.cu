@@ -42,7 +42,13 @@ struct Engine {
     EngineState *state = nullptr;   // [BFIR_MAX_GROUPS], one per channel group, kept in lockstep
     // channel-group pipelining: whole streams are dealt to n_groups groups, each with its own CUDA
     // stream, so that H2D / kernels / D2H of different groups overlap (and FFT with MAC kernels)
-    struct Group { int s0, s1, c0, c1; cudaStream_t stream; cudaEvent_t done; };
+    struct Group {
+        int s0, s1, c0, c1;
+        cudaStream_t stream; cudaEvent_t done;
+        // bfir_run_async: the group's copies ride on their own streams so that they overlap its kernels too
+        cudaStream_t h2d, d2h;
+        cudaEvent_t in_ready, in_free, out_ready, out_free, copies_done;
+    };
     Group groups[BFIR_MAX_GROUPS] = {};
     int n_groups = 1;
     cudaEvent_t fork_ev = nullptr;
@@ -69,6 +75,7 @@ struct Engine {
     cudaEvent_t ticket_ev[kMaxInflight][BFIR_MAX_GROUPS] = {};
     long long next_ticket = 0, done_ticket = 0;    // tickets < done_ticket are known to be complete
     bool async_open = false;                        // group streams hold work the engine's stream has not joined
+    bool async_copies = false;                      // ... and so do the groups' copy streams (bfir_run_async)
     int close_async();
     long long run_host_async(const void *inbuf, void *outbuf);
     int wait_ticket(long long t);
@@ -94,7 +101,7 @@ struct Engine {
     cudaStream_t gstream(int g) const { return n_groups == 1 ? stream : groups[g].stream; }
     int fork();
     int join();
-    int front_group(int g, const void *d_inbuf);
+    int front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed = nullptr);
     int back_group(int g, void *d_outbuf);
     int enqueue_front(const void *d_inbuf);
     int enqueue_back(void *d_outbuf);
@@ -174,6 +181,10 @@ int Engine::init(const bfir_config_t &c)
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) {
         BFIR_CUDA(cudaStreamCreateWithFlags(&groups[g].stream, cudaStreamNonBlocking));
         BFIR_CUDA(cudaEventCreateWithFlags(&groups[g].done, cudaEventDisableTiming));
+        BFIR_CUDA(cudaStreamCreateWithFlags(&groups[g].h2d, cudaStreamNonBlocking));
+        BFIR_CUDA(cudaStreamCreateWithFlags(&groups[g].d2h, cudaStreamNonBlocking));
+        for (cudaEvent_t *ev : { &groups[g].in_ready, &groups[g].in_free, &groups[g].out_ready, &groups[g].out_free, &groups[g].copies_done })
+            BFIR_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
     BFIR_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
     int rc = make_twiddles(rs, N, &tw);
@@ -236,6 +247,9 @@ void Engine::destroy()
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) {
         if (groups[g].stream) { cudaStreamSynchronize(groups[g].stream); cudaStreamDestroy(groups[g].stream); groups[g].stream = nullptr; }
         if (groups[g].done) { cudaEventDestroy(groups[g].done); groups[g].done = nullptr; }
+        for (cudaStream_t *st : { &groups[g].h2d, &groups[g].d2h }) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
+        for (cudaEvent_t *ev : { &groups[g].in_ready, &groups[g].in_free, &groups[g].out_ready, &groups[g].out_free, &groups[g].copies_done })
+            if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
     }
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
     for (int k = 0; k < kMaxInflight; k++)
@@ -443,7 +457,7 @@ int Engine::join()
 }
 
 // input FFT into the delay line + this engine's partition sum, for the channels of one group
-int Engine::front_group(int g, const void *d_inbuf)
+int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed)
 {
     const Group &grp = groups[g];
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
@@ -461,6 +475,7 @@ int Engine::front_group(int g, const void *d_inbuf)
     cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(ns * Ci, 1), st, f, tw);
     count_launch();
     if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    if (input_consumed) BFIR_CUDA(cudaEventRecord(*input_consumed, st));   // the raw input block has been read
     if (xbar) { // inputs -> filter inputs, straight into the delay-line slot (mixnscale INPUT, n_bufs = Ci)
         XbarArgs x = {};
         x.in = xin; x.in_stride = N; x.out = fdl; x.out_stride = (long long)P * N; x.slot_stride = N;
@@ -698,35 +713,65 @@ int Engine::run_step_graph()
     return BFIR_OK;
 }
 
-// the engine's stream catches up with whatever bfir_run_async left on the group streams
+// the engine's stream catches up with whatever the pipelined calls left on the group streams
 int Engine::close_async()
 {
     if (!async_open) return BFIR_OK;
     async_open = false;
+    if (async_copies) { // the output copies are the last link of every group's chain
+        async_copies = false;
+        for (int g = 0; g < n_groups; g++) {
+            BFIR_CUDA(cudaEventRecord(groups[g].copies_done, groups[g].d2h));
+            BFIR_CUDA(cudaStreamWaitEvent(stream, groups[g].copies_done, 0));
+            BFIR_CUDA(cudaEventRecord(groups[g].copies_done, groups[g].h2d));
+            BFIR_CUDA(cudaStreamWaitEvent(stream, groups[g].copies_done, 0));
+        }
+    }
+    if (n_groups == 1) return BFIR_OK;
     return join();
 }
 
-// queue H2D -> block step -> D2H of one block, group by group, and return its ticket (or an error code < 0)
+// queue H2D -> block step -> D2H of one block and return its ticket (or an error code < 0). Per group three
+// streams: input copies, kernels, output copies, chained by events --
+//   H2D(t) after fwd(t-1) has consumed the staging slice;  fwd(t) after H2D(t);
+//   inv(t) after D2H(t-1) has drained the output slice;     D2H(t) after inv(t)
+// so a group's copies overlap its own kernels as well as everybody else's.
 long long Engine::run_host_async(const void *inbuf, void *outbuf)
 {
     int rc;
-    if (!async_open) { // the groups start after everything queued on the engine's stream so far
-        if ((rc = fork()) != BFIR_OK) return rc;
-        async_open = true;
+    if (!async_open || !async_copies) { // all streams start after everything queued on the engine's stream so far
+        if ((rc = close_async()) != BFIR_OK) return rc;
+        BFIR_CUDA(cudaEventRecord(fork_ev, stream));
+        for (int g = 0; g < n_groups; g++) {
+            if (n_groups > 1) BFIR_CUDA(cudaStreamWaitEvent(groups[g].stream, fork_ev, 0));
+            BFIR_CUDA(cudaStreamWaitEvent(groups[g].h2d, fork_ev, 0));
+            BFIR_CUDA(cudaStreamWaitEvent(groups[g].d2h, fork_ev, 0));
+            BFIR_CUDA(cudaEventRecord(groups[g].in_free, gstream(g)));
+            BFIR_CUDA(cudaEventRecord(groups[g].out_free, groups[g].d2h));
+        }
+        async_open = async_copies = true;
     }
     if (next_ticket - done_ticket >= kMaxInflight && (rc = wait_ticket(next_ticket - kMaxInflight)) != BFIR_OK) return rc;
     const int slot = (int)(next_ticket % kMaxInflight);
     for (int g = 0; g < n_groups; g++) {
-        const Group &grp = groups[g];
+        Group &grp = groups[g];
         const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
         const size_t ioff = s0 * L * Ci * in_sf.bytes, ibytes = ns * L * Ci * in_sf.bytes;
         const size_t ooff = s0 * L * Co * out_sf.bytes, obytes = ns * L * Co * out_sf.bytes;
-        BFIR_CUDA(cudaMemcpyAsync((char *)d_in + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, gstream(g)));
-        if ((rc = front_group(g, d_in)) != BFIR_OK) return rc;
+        cudaStream_t st = gstream(g);
+        BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, grp.in_free, 0));
+        BFIR_CUDA(cudaMemcpyAsync((char *)d_in + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, grp.h2d));
+        BFIR_CUDA(cudaEventRecord(grp.in_ready, grp.h2d));
+        BFIR_CUDA(cudaStreamWaitEvent(st, grp.in_ready, 0));
+        if ((rc = front_group(g, d_in, &grp.in_free)) != BFIR_OK) return rc;
+        BFIR_CUDA(cudaStreamWaitEvent(st, grp.out_free, 0));
         if ((rc = back_group(g, d_out)) != BFIR_OK) return rc;
-        BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, gstream(g)));
+        BFIR_CUDA(cudaEventRecord(grp.out_ready, st));
+        BFIR_CUDA(cudaStreamWaitEvent(grp.d2h, grp.out_ready, 0));
+        BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, grp.d2h));
+        BFIR_CUDA(cudaEventRecord(grp.out_free, grp.d2h));
         if (ticket_ev[slot][g] == nullptr) BFIR_CUDA(cudaEventCreateWithFlags(&ticket_ev[slot][g], cudaEventDisableTiming));
-        BFIR_CUDA(cudaEventRecord(ticket_ev[slot][g], gstream(g)));
+        BFIR_CUDA(cudaEventRecord(ticket_ev[slot][g], grp.d2h));
     }
     finish_block();
     return next_ticket++;
