@@ -66,8 +66,27 @@ struct Engine {
     cudaGraphExec_t step_graph[2] = { nullptr, nullptr };
     unsigned long long step_graph_launches[2] = { 0, 0 };
     bool graphs_enabled = true;
+    int graph_flavor = 0;           // 0: forward + full partition sum + inverse; 1: forward + inverse with the head term
+    // look-ahead partition sum on the synchronous bfir_run path: once a block is out, sum_{i>=1} X[t+1-i] H[i] of
+    // the NEXT block is computed in the background (only old delay-line slots feed it); the next call then
+    // runs forward transform -> inverse transform with the head term X[t+1] H[0] folded into its load phase
+    bool lookahead_enabled = true, tail_ready = false;
+    cudaEvent_t out_done = nullptr; // the output block of the current bfir_run is on the host
+    // with several stream groups the look-ahead launches run one after the other on their own stream, so that
+    // group 0 can start the next block while the sums of the later groups are still streaming (and the output
+    // copies of the groups come out staggered instead of all at once)
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t tail_done[BFIR_MAX_GROUPS] = {};
+    cudaEvent_t tail_join_ev = nullptr;
+    bool tail_inflight = false;     // tail_stream holds launches the engine's stream has not been ordered after
+    int join_tail();
+    bool lookahead_ok() const
+    {
+        return lookahead_enabled && !xbar && !peer.enabled && part_begin == 0 && part_count == P && P >= 2 && !xfade_pending && pcap == 0;
+    }
+    int tail_group(int g, cudaStream_t st);
     void invalidate_graphs() { for (int k = 0; k < 2; k++) if (step_graph[k]) { cudaGraphExecDestroy(step_graph[k]); step_graph[k] = nullptr; } }
-    int run_step_graph();
+    int run_step_graph(bool use_tail);
     // throughput variant of run (bfir_run_async / bfir_wait): block steps are queued on the group streams
     // without joining them, so the copies and kernels of consecutive blocks overlap; a ring of events
     // (one per group) marks the completion of each queued step
@@ -101,14 +120,14 @@ struct Engine {
     cudaStream_t gstream(int g) const { return n_groups == 1 ? stream : groups[g].stream; }
     int fork();
     int join();
-    int front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed = nullptr);
-    int back_group(int g, void *d_outbuf);
+    int front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed = nullptr, bool skip_mac = false);
+    int back_group(int g, void *d_outbuf, bool head = false);
     int enqueue_front(const void *d_inbuf);
     int enqueue_back(void *d_outbuf);
     int enqueue_block(const void *d_inbuf, void *d_outbuf);
     int enqueue_block_pipelined(const void *d_inbuf, void *d_outbuf);
     int run_host(const void *inbuf, void *outbuf);
-    int sync_and_probe(bool allow_rollback = true);
+    int sync_and_probe(bool allow_rollback = true, cudaEvent_t wait_for = nullptr);
     int reset();
     int get_overflow(int ch, bfir_overflow_t *out);
 };
@@ -162,6 +181,11 @@ int Engine::init(const bfir_config_t &c)
     }
     fft_r0 = rfft_choose_r0(rs, log2m, Ct);
     if (const char *env = getenv("BFIR_GRAPHS")) graphs_enabled = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_LOOKAHEAD")) lookahead_enabled = atoi(env) != 0;
+    BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
+    BFIR_CUDA(cudaStreamCreateWithFlags(&tail_stream, cudaStreamNonBlocking));
+    for (int g = 0; g < BFIR_MAX_GROUPS; g++) BFIR_CUDA(cudaEventCreateWithFlags(&tail_done[g], cudaEventDisableTiming));
+    BFIR_CUDA(cudaEventCreateWithFlags(&tail_join_ev, cudaEventDisableTiming));
     in_bytes = (size_t)S * L * Ci * in_sf.bytes;
     out_bytes = (size_t)S * L * Co * out_sf.bytes;
     BFIR_CUDA(cudaMalloc(&d_in, in_bytes));
@@ -252,6 +276,10 @@ void Engine::destroy()
             if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
     }
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
+    if (out_done) { cudaEventDestroy(out_done); out_done = nullptr; }
+    if (tail_stream) { cudaStreamSynchronize(tail_stream); cudaStreamDestroy(tail_stream); tail_stream = nullptr; }
+    for (int g = 0; g < BFIR_MAX_GROUPS; g++) if (tail_done[g]) { cudaEventDestroy(tail_done[g]); tail_done[g] = nullptr; }
+    if (tail_join_ev) { cudaEventDestroy(tail_join_ev); tail_join_ev = nullptr; }
     for (int k = 0; k < kMaxInflight; k++)
         for (int g = 0; g < BFIR_MAX_GROUPS; g++) if (ticket_ev[k][g]) { cudaEventDestroy(ticket_ev[k][g]); ticket_ev[k][g] = nullptr; }
     if (stream && own_stream) cudaStreamDestroy(stream);
@@ -279,6 +307,7 @@ int Engine::reset()
     BFIR_CUDA(cudaGetLastError());
     for (auto &o : last_overflow) { o.n_overflows = 0; o.largest = 0; o.intlargest = 0; }
     host_blockcounter = 0;
+    tail_ready = false;
     return BFIR_OK;
 }
 
@@ -298,6 +327,7 @@ int Engine::load_coeff(const void *const *h_coeffs, const void *d_src, long long
     BFIR_CUDA(cudaSetDevice(device));
     BFIR_CUDA(cudaStreamSynchronize(stream));
     invalidate_graphs();
+    tail_ready = false;
     if (n_coeffs > Ct) n_coeffs = Ct;                     // brutefir.cpp:191-194
     const size_t cbuf = (size_t)N * rs;
     void *target = nullptr;
@@ -418,6 +448,7 @@ int Engine::set_groups(int n)
     for (int g = 0; g < n_groups && g < BFIR_MAX_GROUPS; g++)
         if (groups[g].stream) BFIR_CUDA(cudaStreamSynchronize(groups[g].stream));
     n_groups = n;
+    tail_ready = false;
     invalidate_graphs();
     const int base = S / n, extra = S % n;
     int s = 0;
@@ -457,7 +488,7 @@ int Engine::join()
 }
 
 // input FFT into the delay line + this engine's partition sum, for the channels of one group
-int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed)
+int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed, bool skip_mac)
 {
     const Group &grp = groups[g];
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
@@ -487,6 +518,8 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed)
         BFIR_CUDA(cudaGetLastError());
     }
     if (g == 0) prof(1);
+    if (skip_mac) return BFIR_OK;   // the look-ahead launch has left sum_{i>=1} in acc; back_group adds the head term
+    tail_ready = false;             // a full partition sum overwrites whatever a look-ahead launch left in acc
 
     MacArgs m = {};
     m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
@@ -519,7 +552,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed)
 }
 
 // output stage from the accumulated spectra, for the channels of one group
-int Engine::back_group(int g, void *d_outbuf)
+int Engine::back_group(int g, void *d_outbuf, bool head)
 {
     const Group &grp = groups[g];
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
@@ -579,6 +612,11 @@ int Engine::back_group(int g, void *d_outbuf)
     v.fmt = out_sf.format; v.ch_per_stream = Co; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.ch_base = c0; v.host_flag = d_flag;
     if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }
     else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * Co * out_sf.bytes; }
+    if (head) {
+        v.head_x = fdl; v.head_x_stride = (long long)P * N;
+        v.head_h = coeffs; v.head_h_stride = (long long)coeff_alloc * N;
+        v.head_blocks = coeff_blocks;
+    }
     if (!xfade_pending) {
         cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(nch, 1), st, v, tw);
         count_launch();
@@ -597,6 +635,26 @@ int Engine::back_group(int g, void *d_outbuf)
         BFIR_CUDA(cudaGetLastError());
     }
     if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+    return BFIR_OK;
+}
+
+// look-ahead: partitions 1 .. P-1 of the NEXT block for the channels of one group (blockcounter has been advanced
+// by the inverse kernel of the block that just went out; the next forward transform has not counted itself yet)
+int Engine::tail_group(int g, cudaStream_t st)
+{
+    const Group &grp = groups[g];
+    const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
+    MacArgs m = {};
+    m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
+    m.fdl_stride_ch = (long long)P * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = P; m.part_begin = 1; m.part_count = P - 1;
+    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
+    m.procblocks_bias = 1;
+    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), ns * C);
+    mac_kernel_t mk = rs == 4 ? mac_kernel_for_split<float>(mac_split) : mac_kernel_for_split<double>(mac_split);
+    mk<<<grid, 256, 0, st>>>(m);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
     return BFIR_OK;
 }
 
@@ -637,7 +695,7 @@ int Engine::enqueue_block_pipelined(const void *d_inbuf, void *d_outbuf)
 {
     int rc = BFIR_OK;
     if (!async_open) {
-        if ((rc = fork()) != BFIR_OK) return rc;
+        if ((rc = join_tail()) != BFIR_OK || (rc = fork()) != BFIR_OK) return rc;
         async_open = n_groups > 1;
     }
     for (int g = 0; g < n_groups && rc == BFIR_OK; g++) {
@@ -649,22 +707,28 @@ int Engine::enqueue_block_pipelined(const void *d_inbuf, void *d_outbuf)
 }
 
 // wait for the stream and apply the reference's NaN/Inf abort (brutefir.cpp:316-321)
-int Engine::sync_and_probe(bool allow_rollback)
+int Engine::sync_and_probe(bool allow_rollback, cudaEvent_t wait_for)
 {
-    int arc = close_async();
-    if (arc != BFIR_OK) return arc;
-    BFIR_CUDA(cudaStreamSynchronize(stream));
+    if (wait_for) {   // bfir_run: the output is home, look-ahead work may still run (and stays un-joined)
+        BFIR_CUDA(cudaEventSynchronize(wait_for));
+    } else {
+        int arc = close_async();
+        if (arc != BFIR_OK) return arc;
+        BFIR_CUDA(cudaStreamSynchronize(stream));
+    }
     done_ticket = next_ticket;
     prof_collect();
     const unsigned long long n = blocks_since_sync;
     blocks_since_sync = 0;
     if (*(volatile int *)h_flag == 0) return BFIR_OK;          // nothing raised the flag: no copy needed
     *h_flag = 0;
+    { int trc = join_tail(); if (trc != BFIR_OK) return trc; }
     BFIR_CUDA(cudaMemcpyAsync(h_state, state, sizeof(EngineState) * n_groups, cudaMemcpyDeviceToHost, stream));
     BFIR_CUDA(cudaStreamSynchronize(stream));
     int bad = 0x7fffffff;
     for (int g = 0; g < n_groups; g++) if (h_state[g].first_bad_channel < bad) bad = h_state[g].first_bad_channel;
     if (bad != 0x7fffffff) {
+        tail_ready = false;
         pinfo("NaN or Inf values in the system! Invalid input? Aborting.\n");
         const int threads = 256, blocks = (Ct + threads - 1) / threads;
         if (n == 1 && allow_rollback) { // exact reference semantics: the aborted block does not advance the counters
@@ -687,15 +751,16 @@ int Engine::sync_and_probe(bool allow_rollback)
 // capture (first use per block parity) and replay the kernels of one block step: saves the per-kernel
 // launch cost on the latency path. Only pointers fixed for the engine's lifetime are baked in (the staging
 // buffers, the state words); whatever can change them invalidates the graphs.
-int Engine::run_step_graph()
+int Engine::run_step_graph(bool use_tail)
 {
+    if (graph_flavor != (use_tail ? 1 : 0)) { invalidate_graphs(); graph_flavor = use_tail ? 1 : 0; }
     const int par = (int)(host_blockcounter & 1u);
     if (step_graph[par] == nullptr) {
         const unsigned long long before = t_launches;
         cudaGraph_t graph = nullptr;
         BFIR_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
-        int rc = front_group(0, d_in);
-        if (rc == BFIR_OK) rc = back_group(0, d_out);
+        int rc = front_group(0, d_in, nullptr, use_tail);
+        if (rc == BFIR_OK) rc = back_group(0, d_out, use_tail);
         cudaError_t ce = cudaStreamEndCapture(stream, &graph);
         if (rc != BFIR_OK || ce != cudaSuccess || graph == nullptr) {
             if (graph) cudaGraphDestroy(graph);
@@ -714,8 +779,20 @@ int Engine::run_step_graph()
 }
 
 // the engine's stream catches up with whatever the pipelined calls left on the group streams
+// the engine's stream is ordered after the look-ahead launches that are still on their own stream
+int Engine::join_tail()
+{
+    if (!tail_inflight) return BFIR_OK;
+    tail_inflight = false;
+    BFIR_CUDA(cudaEventRecord(tail_join_ev, tail_stream));
+    BFIR_CUDA(cudaStreamWaitEvent(stream, tail_join_ev, 0));
+    return BFIR_OK;
+}
+
 int Engine::close_async()
 {
+    int trc = join_tail();
+    if (trc != BFIR_OK) return trc;
     if (!async_open) return BFIR_OK;
     async_open = false;
     if (async_copies) { // the output copies are the last link of every group's chain
@@ -792,37 +869,53 @@ int Engine::wait_ticket(long long t)
 int Engine::run_host(const void *inbuf, void *outbuf)
 {
     if (async_open) { const int arc = close_async(); if (arc != BFIR_OK) return arc; }
+    const bool use_tail = tail_ready && lookahead_ok();   // acc already holds partitions 1 .. P-1 of this block
+    const bool swap_block = xfade_pending;                // filters are being swapped: more swaps may follow, no look-ahead
+    tail_ready = false;
+    int rc;
+    if (!use_tail && (rc = join_tail()) != BFIR_OK) return rc;   // a dropped look-ahead result must not race the full sum
     // latency path: one group, kernels replayed from a graph (after two plain blocks have configured them)
     if (graphs_enabled && n_groups == 1 && !xfade_pending && pcap == 0 && !peer.enabled && host_blockcounter >= 2) {
         BFIR_CUDA(cudaMemcpyAsync(d_in, inbuf, in_bytes, cudaMemcpyHostToDevice, stream));
-        int rc = run_step_graph();
-        if (rc != BFIR_OK) return rc;
+        if ((rc = run_step_graph(use_tail)) != BFIR_OK) return rc;
         BFIR_CUDA(cudaMemcpyAsync(outbuf, d_out, out_bytes, cudaMemcpyDeviceToHost, stream));
         finish_block();
-        return sync_and_probe();
+    } else {
+        if ((rc = fork()) != BFIR_OK) return rc;
+        for (int g = 0; g < n_groups; g++) {
+            const Group &grp = groups[g];
+            const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
+            const size_t ioff = s0 * L * Ci * in_sf.bytes, ibytes = ns * L * Ci * in_sf.bytes;
+            BFIR_CUDA(cudaMemcpyAsync((char *)d_in + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, gstream(g)));
+            if (use_tail && n_groups > 1) BFIR_CUDA(cudaStreamWaitEvent(gstream(g), tail_done[g], 0));   // this group's look-ahead sum is in
+            if ((rc = front_group(g, d_in, nullptr, use_tail)) != BFIR_OK) return rc;
+        }
+        for (int g = 0; g < n_groups; g++) {
+            const Group &grp = groups[g];
+            const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
+            const size_t ooff = s0 * L * Co * out_sf.bytes, obytes = ns * L * Co * out_sf.bytes;
+            if ((rc = back_group(g, d_out, use_tail)) != BFIR_OK) return rc;
+            BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, gstream(g)));
+        }
+        finish_block();
+        if ((rc = join()) != BFIR_OK) return rc;
     }
-    int rc = fork();
-    if (rc != BFIR_OK) return rc;
-    for (int g = 0; g < n_groups; g++) {
-        const Group &grp = groups[g];
-        const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
-        const size_t ioff = s0 * L * Ci * in_sf.bytes, ibytes = ns * L * Ci * in_sf.bytes;
-        BFIR_CUDA(cudaMemcpyAsync((char *)d_in + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, gstream(g)));
-        rc = front_group(g, d_in);
-        if (rc != BFIR_OK) return rc;
+    BFIR_CUDA(cudaEventRecord(out_done, stream));
+    if (lookahead_ok() && !swap_block) { // behind the output copies: the next block's partitions 1 .. P-1, while the host is away
+        if (n_groups == 1) {
+            if ((rc = tail_group(0, stream)) != BFIR_OK) return rc;
+        } else {
+            BFIR_CUDA(cudaStreamWaitEvent(tail_stream, out_done, 0));
+            for (int g = 0; g < n_groups; g++) {
+                if ((rc = tail_group(g, tail_stream)) != BFIR_OK) return rc;
+                BFIR_CUDA(cudaEventRecord(tail_done[g], tail_stream));
+            }
+            tail_inflight = true;
+        }
+        tail_ready = true;
     }
-    for (int g = 0; g < n_groups; g++) {
-        const Group &grp = groups[g];
-        const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
-        const size_t ooff = s0 * L * Co * out_sf.bytes, obytes = ns * L * Co * out_sf.bytes;
-        rc = back_group(g, d_out);
-        if (rc != BFIR_OK) return rc;
-        BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, gstream(g)));
-    }
-    finish_block();
-    rc = join();
-    if (rc != BFIR_OK) return rc;
-    return sync_and_probe();
+    rc = sync_and_probe(true, out_done);
+    return rc;
 }
 
 int Engine::get_overflow(int ch, bfir_overflow_t *out)

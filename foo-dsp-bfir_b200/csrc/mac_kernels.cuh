@@ -28,6 +28,7 @@ struct MacArgs {
     const EngineState *state;
     int block_offset;        // 0: blockcounter is the current block; used by tests
     int ch_base;             // first channel of this launch (channel-group pipelining)
+    int procblocks_bias;     // 1: look-ahead launch for the NEXT block, whose forward transform has not counted itself yet
     PeerPush push;           // enabled: partial sums go to the owner rank's receive buffer (fused reduce)
 };
 
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
     const int ch = blockIdx.y + a.ch_base;
     const bool active = g * 8 < a.N;
     const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
-    const int peff = min(a.coeff_blocks[ch], a.procblocks[ch]);           // brutefir.cpp:292
+    const int peff = min(a.coeff_blocks[ch], min(a.procblocks[ch] + a.procblocks_bias, a.n_slots)); // brutefir.cpp:292, 265-268
     const int i_end = min(peff, a.part_begin + a.part_count);
     const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
     const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;

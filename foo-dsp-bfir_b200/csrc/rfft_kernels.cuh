@@ -51,6 +51,7 @@ template <class T> BFIR_HD T *peer_dst(const PeerPush &p, int ch, int N, unsigne
 struct EngineState {
     unsigned int blockcounter;  // brutefir.hpp:106
     int first_bad_channel;      // lowest channel whose output sample 0 was NaN/Inf this block
+    unsigned int cur_slot;      // delay-line slot of the block in flight, left by the forward kernel for a fused head term
 };
 
 struct FwdArgs {
@@ -90,6 +91,12 @@ struct InvArgs {
     OverflowStats *stats;    // [channels]
     EngineState *state;      // probe + blockcounter++ (engine only)
     int *host_flag;          // mapped pinned host word, set to 1 on a non-finite probe (lets the host skip a D2H)
+    // look-ahead partition sum: `in` holds sum_{i>=1} X[t-i] H[i], computed before the block arrived; the load
+    // phase adds the head term X[t] H[0] (both ORD, slot state->cur_slot of the delay line) on the fly
+    const void *head_x;      // delay line [channels][head_slots][N]; NULL = no head term
+    const void *head_h;      // coefficients [channels][..][N], partition 0 at the start of each channel
+    long long head_x_stride, head_h_stride; // elements per channel
+    const int *head_blocks;  // [channels] coefficient partitions loaded (0: the channel has no filter)
 };
 
 template <class T> BFIR_HD T tw_re(const cpx<T> &w) { return w.x; }
@@ -213,6 +220,8 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T
         }
     }
     if (a.in_mode == IN_COEFF && bad) *a.nonfinite = 1;
+    if (a.in_mode == IN_RAW_PREV && a.state != NULL && t == 0 && r == 0 && by == 0 && bx == a.ch_base)
+        const_cast<EngineState *>(a.state)->cur_slot = a.state->blockcounter % (unsigned int)a.n_slots;
     if (a.in_mode == IN_RAW_PREV && t == 0 && r == 0 && a.procblocks != NULL) { // brutefir.cpp:265-268
         const int pb = a.procblocks[bx];
         const bool inc = pb < a.n_slots;
@@ -266,12 +275,26 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
 // ------------------------------------------------------------------------------------------------
 // Z'_k = (X_k + conj X_{M-k}) + i conj(W_N^k) (X_k - conj X_{M-k}), the packed spectrum whose inverse
 // complex transform is z[n] = x[2n] + i x[2n+1]
+// bin k of `in`, plus the head term X_k H_k when hx != NULL (the real bins 0 and M come back with a zero
+// imaginary part from spec_load, so the complex product is the reference's d1s/d2s real product there)
 template <class T>
-BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T> w)
+BFIR_HD cpx<T> spec_load_head(const T *in, int layout, int k, int M, const T *hx, const T *hh)
+{
+    cpx<T> s = spec_load<T>(in, layout, k, M);
+    if (hx != NULL) {
+        const cpx<T> x = spec_load<T>(hx, LAYOUT_ORD, k, M), h = spec_load<T>(hh, LAYOUT_ORD, k, M);
+        s.x += x.x * h.x - x.y * h.y;
+        s.y += x.x * h.y + x.y * h.x;
+    }
+    return s;
+}
+
+template <class T>
+BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T> w, const T *hx = NULL, const T *hh = NULL)
 {
     typedef cpx<T> C;
-    C xk = spec_load<T>(in, layout, k, M);
-    C xm = spec_load<T>(in, layout, M - k, M);
+    C xk = spec_load_head<T>(in, layout, k, M, hx, hh);
+    C xm = spec_load_head<T>(in, layout, M - k, M, hx, hh);
     xk.x *= sc; xk.y *= sc; xm.x *= sc; xm.y *= sc;
     const T er = xk.x + xm.x, ei = xk.y - xm.y;   // X_k + conj X_{M-k}
     const T dr = xk.x - xm.x, di = xk.y + xm.y;   // X_k - conj X_{M-k}
@@ -281,13 +304,12 @@ BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T
 }
 
 // inverse, phase 0: thread t builds s_r[k], k = t + i*NTs
-template <class T, int LOG2MS, int R0>
-BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
+template <class T, int LOG2MS, int R0, bool HEAD>
+BFIR_HD void inv_load_impl(int t, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const T *in, int layout, T sc,
+                           const T *hx, const T *hh)
 {
     constexpr int MS = 1 << LOG2MS, NT = MS / 16, M = MS * R0;
     typedef cpx<T> C;
-    const T *in = (const T *)a.in + bx * a.in_stride_x;
-    const T sc = (T)a.scale_in;
     // one table look-up per thread: the thread's bins k = t + i NT are N/32 (one CTA) or N/64 (two CTAs) apart
     const C wbase = tw[t << tw_shift_n];                                   // W_N^t
     C wpre = mk<T>((T)1, (T)0);
@@ -296,14 +318,30 @@ BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[16], const cpx<T> *__res
     for (int i = 0; i < 16; i++) {
         const int k = t + i * NT;
         const C wk = cmul(wbase, R0 == 1 ? unit_root<T, 32>(i) : unit_root<T, 64>(i));   // W_N^k
-        const C lo = inv_elem<T>(in, a.in_layout, k, M, sc, wk);
+        const C lo = HEAD ? inv_elem<T>(in, layout, k, M, sc, wk, hx, hh) : inv_elem<T>(in, layout, k, M, sc, wk);
         if (R0 == 1) {
             v[i] = lo;
         } else {
-            const C hi = inv_elem<T>(in, a.in_layout, k + MS, M, sc, mk<T>(wk.y, -wk.x));   // W_N^(k + N/4) = -i W_N^k
+            const C wq = mk<T>(wk.y, -wk.x);                                              // W_N^(k + N/4) = -i W_N^k
+            const C hi = HEAD ? inv_elem<T>(in, layout, k + MS, M, sc, wq, hx, hh) : inv_elem<T>(in, layout, k + MS, M, sc, wq);
             if (r == 0) v[i] = cadd(lo, hi);
             else v[i] = cmul(csub(lo, hi), cconj(cmul(wpre, unit_root<T, 32>(i))));       // W_M^(-k)
         }
+    }
+}
+
+template <class T, int LOG2MS, int R0>
+BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
+{
+    constexpr int M = (1 << LOG2MS) * R0;
+    const T *in = (const T *)a.in + bx * a.in_stride_x;
+    const T sc = (T)a.scale_in;
+    if (a.head_x != NULL && a.head_blocks[bx] > 0) {   // uniform per CTA
+        const T *hx = (const T *)a.head_x + bx * a.head_x_stride + (long long)a.state->cur_slot * (2 * M);
+        const T *hh = (const T *)a.head_h + bx * a.head_h_stride;
+        inv_load_impl<T, LOG2MS, R0, true>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, hx, hh);
+    } else {
+        inv_load_impl<T, LOG2MS, R0, false>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, NULL, NULL);
     }
 }
 

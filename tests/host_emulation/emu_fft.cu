@@ -178,6 +178,43 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
     }
     const double amp = fmt_in == FMT_FLOAT_LE ? 1.0 : 8388608.0;   // integer input is not normalised in this check
     if (worst > (fmt_out == FMT_FLOAT_LE ? 1e-5 * amp : 2.0 / 32768)) { printf("engine inverse: expected silence, got %g\n", worst); fails++; }
+    {   // look-ahead mode: `in` = partitions 1..P-1 (zeros here), head term X[slot] * H[0] added in the load phase.
+        // H[0] = 1 + 0i for every bin (ORD: real parts 1, imaginary parts 0, Nyquist in slot 4 = 1) must reproduce
+        // the plain inverse of the slot; a channel without coefficients (head_blocks 0) must stay silent.
+        std::vector<T> zacc((size_t)Ct * N, (T)0), hone((size_t)Ct * P * N, (T)0);
+        for (int c = 0; c < Ct; c++) for (int g8 = 0; g8 < N / 8; g8++) for (int j = 0; j < 4; j++) hone[((size_t)c * P) * N + g8 * 8 + j] = (T)1;
+        for (int c = 0; c < Ct; c++) hone[((size_t)c * P) * N + 4] = (T)1;
+        std::vector<int> hb(Ct, 1);
+        hb[Ct - 1] = 0;
+        std::vector<uint8_t> raw_head((size_t)S * L * CH * ob, 0xee);
+        if (st.cur_slot != 1u) { printf("cur_slot %u\n", st.cur_slot); fails++; }
+        for (int bx = 0; bx < Ct; bx++) {
+            InvArgs v = {};
+            v.in_layout = LAYOUT_ORD; v.in = zacc.data(); v.in_stride_x = N; v.scale_in = 2.0 / N;
+            v.out_mode = OUT_RAW; v.out = raw_head.data(); v.out_stride_x = (long long)L * CH * ob; v.fmt = fmt_out; v.ch_per_stream = CH;
+            v.ovf_max = fmt_isfloat(fmt_out) ? 1.0 : 32767.0; v.stats = stats.data(); v.state = &st;
+            if (!fmt_isfloat(fmt_out)) v.scale_in *= 32768.0 / (fmt_in == FMT_FLOAT_LE ? 1.0 : 8388608.0);
+            v.head_x = fdl.data(); v.head_x_stride = (long long)P * N; v.head_h = hone.data(); v.head_h_stride = (long long)P * N;
+            v.head_blocks = hb.data();
+            OverflowAcc acc = {};
+            for (int r = 0; r < R0; r++) {
+                for (int t = 0; t < NT; t++) inv_load<T, LOG2MS, R0>(t, bx, r, vs[t], tw.data(), 0, v);
+                fft_passes<T, LOG2MS, true, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
+                for (int t = 0; t < NT; t++) inv_store<T, LOG2MS, R0>(t, bx, r, vs[t], v, acc);
+            }
+        }
+        for (int s_ = 0; s_ < S; s_++) for (int n = 0; n < L; n++) for (int c = 0; c < CH; c++) {
+            const size_t o = (((size_t)s_ * L + n) * CH + c) * ob;
+            const bool silent = s_ * CH + c == Ct - 1;
+            for (int k = 0; k < ob; k++) {
+                const uint8_t want = silent ? 0 : raw_out[o + k];
+                if (raw_head[o + k] != want && !(silent && fmt_isfloat(fmt_out) && k == ob - 1 && raw_head[o + k] == 0x80)) { // -0.0f
+                    if (fails < 5) printf("head mode mismatch s %d n %d c %d\n", s_, n, c);
+                    fails++; break;
+                }
+            }
+        }
+    }
     // coefficient partitions (IN_COEFF) and the upper-half mode (IN_UPPER)
     std::vector<T> h(2 * L + 5), hs((size_t)P * N, (T)7), up(N);
     for (auto &x : h) x = (T)u(rng);

