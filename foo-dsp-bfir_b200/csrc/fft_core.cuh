@@ -162,15 +162,24 @@ template <class T, int D> BFIR_HD cpx<T> unit_root(int j)
     return D == 32 ? mk<T>((T)c32[j], (T)-s32[j]) : mk<T>((T)c64[j], (T)-s64[j]);
 }
 
+// root of unity between consecutive points of one thread: D = 2E (or 4E with two CTAs per transform)
+template <class T, int D> BFIR_HD cpx<T> thread_root(int j)
+{
+    static_assert(D == 16 || D == 32 || D == 64, "8 or 16 points per thread");
+    if (D == 16) return unit_root<T, 32>(2 * j);      // j < 8
+    return unit_root<T, D == 16 ? 32 : D>(j);
+}
+
 // ---------------------------------------------------------------------------------------------
-// pass plan: radices whose product is 2^LOG2M, 16s first (so strides are >= 16 from pass 2 on)
-template <int LOG2M> struct fft_plan {
-    static constexpr int n16 = (LOG2M % 4 == 1 && LOG2M >= 5) ? LOG2M / 4 - 1 : LOG2M / 4;
-    static constexpr int rem = LOG2M - 4 * n16;             // 0,1,2,3 or 5 (-> 8*4)
+// pass plan: radices whose product is 2^LOG2M, none above the E = 2^LOG2E points a thread owns, largest first
+// (E = 16: 16s first, so strides are >= 16 from pass 2 on; a remainder of 2^5 is split 8 x 4 rather than 16 x 2)
+template <int LOG2M, int LOG2E = 4> struct fft_plan {
+    static constexpr int n16 = LOG2E == 4 ? ((LOG2M % 4 == 1 && LOG2M >= 5) ? LOG2M / 4 - 1 : LOG2M / 4) : LOG2M / LOG2E;
+    static constexpr int rem = LOG2M - LOG2E * n16;         // E = 16: 0,1,2,3 or 5 (-> 8*4); E = 8: 0,1,2
     static constexpr int npass = n16 + (rem == 0 ? 0 : (rem == 5 ? 2 : 1));
     static constexpr BFIR_HD int log2_radix(int pass)
     {
-        return pass < n16 ? 4 : (rem == 5 ? (pass == n16 ? 3 : 2) : rem);
+        return pass < n16 ? LOG2E : (rem == 5 ? (pass == n16 ? 3 : 2) : rem);
     }
 };
 
@@ -179,14 +188,18 @@ template <int LOG2M> struct fft_plan {
 BFIR_HD int fft_pad(int i) { return i + (i >> 4); }
 template <int M> struct fft_smem_elems { static constexpr int value = M + (M >> 4); };
 
-template <class T, int LOG2M, bool INV>
+// LOG2E = 4: 16 points per thread (the default everywhere); LOG2E = 3: 8 points per thread on twice the threads,
+// i.e. half the dependent work per thread and twice the warps per transform (double precision, where 16 points
+// cost 128 registers and leave two warps per scheduler)
+template <class T, int LOG2M, bool INV, int LOG2E = 4>
 struct BlockFFT {
     static constexpr int M = 1 << LOG2M;
     static_assert(LOG2M >= 4, "block length below 16 is not supported");
-    static constexpr int E = 16;                       // points per thread
+    static_assert(LOG2E == 3 || LOG2E == 4, "8 or 16 points per thread");
+    static constexpr int E = 1 << LOG2E;               // points per thread
     static constexpr int NT = M / E;                   // threads
-    static constexpr int LOG2NT = LOG2M - 4;
-    typedef fft_plan<LOG2M> plan;
+    static constexpr int LOG2NT = LOG2M - LOG2E;
+    typedef fft_plan<LOG2M, LOG2E> plan;
     typedef cpx<T> C;
 
     // table look-ups of one pass for thread t: per butterfly w^1, and w^4 for radix 8/16 (the other powers
@@ -283,10 +296,10 @@ struct BlockFFT {
 // The pass loop, written once with a SYNC functor so the device kernel passes __syncthreads and the
 // host emulation runs each phase for all threads in turn. PASS is unrolled by recursion because the
 // radix and stride of every pass are compile-time constants.
-template <class T, int LOG2M, bool INV, int PASS, int LOG2S>
+template <class T, int LOG2M, bool INV, int PASS, int LOG2S, int LOG2E = 4>
 struct fft_passes {
-    typedef BlockFFT<T, LOG2M, INV> F;
-    typedef fft_plan<LOG2M> plan;
+    typedef BlockFFT<T, LOG2M, INV, LOG2E> F;
+    typedef fft_plan<LOG2M, LOG2E> plan;
     static constexpr int LOG2R = plan::log2_radix(PASS);
     static constexpr bool LAST = (PASS == plan::npass - 1);
 
@@ -306,7 +319,7 @@ struct fft_passes {
     {
         F::template butterflies<LOG2R, LOG2S, LAST>(t, v, w);
         if constexpr (!LAST) {
-            typedef fft_passes<T, LOG2M, INV, PASS + 1, LOG2S + LOG2R> next;
+            typedef fft_passes<T, LOG2M, INV, PASS + 1, LOG2S + LOG2R, LOG2E> next;
             cpx<T> wn[next::NW];
             if constexpr (!next::LAST) F::template load_twiddles<next::LOG2R, LOG2S + LOG2R>(t, wn, tw, tw_shift); // one pass ahead
             F::template store_pass<LOG2R, LOG2S>(t, v, smem);
@@ -329,7 +342,7 @@ struct fft_passes {
         if constexpr (!LAST) {
             for (int t = 0; t < F::NT; t++) F::template store_pass<LOG2R, LOG2S>(t, vs[t], smem);
             for (int t = 0; t < F::NT; t++) F::load_natural(t, vs[t], smem);
-            fft_passes<T, LOG2M, INV, PASS + 1, LOG2S + LOG2R>::run_host(vs, smem, tw, tw_shift);
+            fft_passes<T, LOG2M, INV, PASS + 1, LOG2S + LOG2R, LOG2E>::run_host(vs, smem, tw, tw_shift);
         }
     }
 };

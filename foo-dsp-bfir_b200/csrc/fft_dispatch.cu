@@ -12,6 +12,13 @@ namespace bfir {
 #define BFIR_FOR_F64(X) X(f64, 4) X(f64, 5) X(f64, 6) X(f64, 7) X(f64, 8) X(f64, 9) X(f64, 10) X(f64, 11) X(f64, 12) X(f64, 13)
 BFIR_FOR_F32(BFIR_DECL)
 BFIR_FOR_F64(BFIR_DECL)
+// 8 points per thread (double, per-CTA sizes 2^6 .. 2^12): no complex-FFT launcher in these units
+#define BFIR_DECL_E8(tag, m)                                                                                   \
+    cudaError_t launch_fwd_##tag##_m##m(int, dim3, cudaStream_t, const FwdArgs &, const void *, int, int);     \
+    cudaError_t launch_inv_##tag##_m##m(int, dim3, cudaStream_t, const InvArgs &, const void *, int, int);
+#define BFIR_FOR_F64E8(X) X(f64e8, 6) X(f64e8, 7) X(f64e8, 8) X(f64e8, 9) X(f64e8, 10) X(f64e8, 11) X(f64e8, 12)
+BFIR_FOR_F64E8(BFIR_DECL_E8)
+static const int kMinLog2M_e8 = 6, kMaxLog2M_e8 = 12;
 
 static const int kMinLog2M = 4, kMaxLog2M_f32 = 14, kMaxLog2M_f64 = 13;
 
@@ -24,6 +31,26 @@ static const fwd_launcher_t kFwdF64[] = { BFIR_FOR_F64(BFIR_FWD_ENTRY) };
 static const cfft_launcher_t kCfftF32[] = { BFIR_FOR_F32(BFIR_CFFT_ENTRY) };
 static const cfft_launcher_t kCfftF64[] = { BFIR_FOR_F64(BFIR_CFFT_ENTRY) };
 static const inv_launcher_t kInvF64[] = { BFIR_FOR_F64(BFIR_INV_ENTRY) };
+static const fwd_launcher_t kFwdF64E8[] = { BFIR_FOR_F64E8(BFIR_FWD_ENTRY) };
+static const inv_launcher_t kInvF64E8[] = { BFIR_FOR_F64E8(BFIR_INV_ENTRY) };
+
+// 8 instead of 16 points per thread for a double-precision transform whose per-CTA size is 2^sub?
+// Measured on B200 (tools/kernel_times.py, profiles/r01_fft_e8_vs_e16.jsonl): 16 double-complex points per thread
+// cost 128 registers and leave two warps per scheduler, so with few transforms in flight (the latency path) the
+// 8-point variant wins everywhere (cfg1 single stream: forward 22.6 -> 19.0 us, inverse 18.2 -> 16.7; 4 streams:
+// 30.3 -> 20.1 / 22.4 -> 18.2; product configuration 12.6 -> 10.2 / 10.8 -> 9.8). With more than 64 transforms
+// per launch the forward side still gains up to 4096 points per CTA (18.4 -> 16.6 us at 128 buffers), the inverse
+// side does not (15.0 -> 16.7), and 8192-point transforms are best on one 16-point CTA each (25.1 vs 29.3 us).
+// BFIR_FFT_E = 8 | 16 forces the answer where both exist.
+static bool use_e8(int realsize, int sub, int r0, long long n_buffers, bool forward)
+{
+    if (realsize != 8 || sub < kMinLog2M_e8 || sub > kMaxLog2M_e8) return false;
+    static const int forced = [] { const char *env = getenv("BFIR_FFT_E"); return env ? atoi(env) : 0; }();
+    if (forced == 8) return true;
+    if (forced == 16) return false;
+    if (n_buffers <= 64) return true;
+    return forward && r0 == 1;
+}
 
 static int max_sub(int realsize) { return realsize == 4 ? kMaxLog2M_f32 : kMaxLog2M_f64; }
 
@@ -63,6 +90,7 @@ cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cuda
     const int sub = log2m - (r0 == 2 ? 1 : 0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
     // table length N = 2 * 2^log2m: shift for the sub-transform twiddles, 0 for the W_N^k of the split step
+    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, true)) return kFwdF64E8[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
     return (realsize == 4 ? kFwdF32 : kFwdF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }
 
@@ -71,6 +99,7 @@ cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cuda
     if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
     const int sub = log2m - (r0 == 2 ? 1 : 0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
+    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return kInvF64E8[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
     return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }
 

@@ -1,5 +1,6 @@
 // One (precision, size) instantiation of the real-FFT kernels; see fft_dispatch.hpp.
-// Compile with -DBFIR_FFT_REAL=float|double -DBFIR_FFT_TAG=f32|f64 -DBFIR_FFT_LOG2M=<4..14>.
+// Compile with -DBFIR_FFT_REAL=float|double -DBFIR_FFT_TAG=f32|f64 -DBFIR_FFT_LOG2M=<4..14>; the variants with
+// 8 points per thread add -DBFIR_FFT_LOG2E=3 and their own tag (f64e8).
 #include "fft_dispatch.hpp"
 #include "eq_kernels.cuh"
 
@@ -8,7 +9,11 @@
 
 namespace bfir {
 
+#ifndef BFIR_FFT_LOG2E
+#define BFIR_FFT_LOG2E 4
+#endif
 typedef BFIR_FFT_REAL real_t;
+static constexpr int kLog2E = BFIR_FFT_LOG2E;
 static constexpr int kLog2M = BFIR_FFT_LOG2M;
 static constexpr int kM = 1 << kLog2M;
 static constexpr size_t kSmem = (size_t)fft_smem_elems<kM>::value * sizeof(cpx<real_t>);
@@ -17,14 +22,14 @@ template <int R0>
 static cudaError_t launch_fwd(dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw, int sm, int sn)
 {
     static bool configured = false;
-    auto kernel = rfft_forward_kernel<real_t, kLog2M, R0>;
+    auto kernel = rfft_forward_kernel<real_t, kLog2M, R0, kLog2E>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     grid.z = R0;
-    kernel<<<grid, kM / 16, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
+    kernel<<<grid, kM >> kLog2E, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
     return cudaGetLastError();
 }
 
@@ -32,14 +37,14 @@ template <int R0>
 static cudaError_t launch_inv(dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw, int sm, int sn)
 {
     static bool configured = false;
-    auto kernel = rfft_inverse_kernel<real_t, kLog2M, R0>;
+    auto kernel = rfft_inverse_kernel<real_t, kLog2M, R0, kLog2E>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     grid.z = R0;
-    kernel<<<grid, kM / 16, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
+    kernel<<<grid, kM >> kLog2E, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
     return cudaGetLastError();
 }
 
@@ -54,6 +59,7 @@ cudaError_t BFIR_CAT(launch_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int r0, dim3 
     return r0 == 2 ? launch_inv<2>(grid, stream, a, tw, sm, sn) : launch_inv<1>(grid, stream, a, tw, sm, sn);
 }
 
+#if BFIR_FFT_LOG2E == 4
 // inverse complex transform of 2^kLog2M points with strided access (four-step building block)
 cudaError_t BFIR_CAT(launch_cfft_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int batch, cudaStream_t stream, const CfftArgs &a)
 {
@@ -67,5 +73,6 @@ cudaError_t BFIR_CAT(launch_cfft_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int batc
     kernel<<<batch, kM / 16, kSmem, stream>>>(a);
     return cudaGetLastError();
 }
+#endif
 
 } // namespace bfir

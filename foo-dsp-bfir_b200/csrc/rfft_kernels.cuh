@@ -195,10 +195,10 @@ BFIR_HD cpx<T> fwd_elem(int m, int by, int r, const FwdArgs &a, const FwdCtx<T> 
 }
 
 // forward, phase 0: thread t builds s_r[n], n = t + i*NTs
-template <class T, int LOG2MS, int R0>
-BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
+template <class T, int LOG2MS, int R0, int LOG2E = 4>
+BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
 {
-    constexpr int MS = 1 << LOG2MS, NT = MS / 16, LOG2M = LOG2MS + (R0 == 2 ? 1 : 0);
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, LOG2M = LOG2MS + (R0 == 2 ? 1 : 0);
     typedef cpx<T> C;
     bool bad = false;
     cpx<T> wpre = mk<T>((T)1, (T)0);
@@ -206,17 +206,17 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T
     const FwdCtx<T> ctx = fwd_ctx<T, LOG2M>(bx, by, a);
     if (R0 == 1) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, by, r, a, ctx, bad);
+        for (int i = 0; i < E / 2; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, by, r, a, ctx, bad);
 #pragma unroll
-        for (int i = 8; i < 16; i++) v[i] = fwd_elem<T, LOG2M, true>(t + i * NT, by, r, a, ctx, bad);
+        for (int i = E / 2; i < E; i++) v[i] = fwd_elem<T, LOG2M, true>(t + i * NT, by, r, a, ctx, bad);
     } else {
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < E; i++) {
             const int n = t + i * NT;
             const C lo = fwd_elem<T, LOG2M, false>(n, by, r, a, ctx, bad);
             const C hi = fwd_elem<T, LOG2M, true>(n + MS, by, r, a, ctx, bad);
             if (r == 0) v[i] = cadd(lo, hi);
-            else v[i] = cmul(csub(lo, hi), cmul(wpre, unit_root<T, 32>(i)));   // W_M^n = W_N^(2n)
+            else v[i] = cmul(csub(lo, hi), cmul(wpre, thread_root<T, 2 * E>(i)));   // W_M^n = W_N^(2n)
         }
     }
     if (a.in_mode == IN_COEFF && bad) *a.nonfinite = 1;
@@ -232,18 +232,18 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[16], const cpx<T
 
 // forward, phase 2: sub-transform result (natural order, padded smem) -> X_k, k = R0 k' + r, scaled,
 // stored in ORD or HC layout
-template <class T, int LOG2MS, int R0>
+template <class T, int LOG2MS, int R0, int LOG2E = 4>
 BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
 {
-    constexpr int MS = 1 << LOG2MS, NT = MS / 16, M = MS * R0, N = 2 * M;
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, M = MS * R0, N = 2 * M;
     typedef cpx<T> C;
     long long off = bx * a.out_stride_x + by * a.out_stride_y;
     if (a.state != NULL) off += (long long)(a.state->blockcounter % (unsigned int)a.n_slots) * a.out_stride_y;
     T *out = (T *)a.out + off;
     const T sc = (T)a.scale_out;
-    const C wbase = tw[(R0 * t + r) << tw_shift_n];   // W_N^k of i = 0; the thread's bins are N/32 apart
+    const C wbase = tw[(R0 * t + r) << tw_shift_n];   // W_N^k of i = 0; the thread's bins are N/(2E) apart
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
+    for (int i = 0; i < E; i++) {
         const int kp = t + i * NT;
         const int k = R0 * kp + r;
         const C zk = smem[fft_pad(kp)];
@@ -257,7 +257,7 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
             const T er = (T)0.5 * (zk.x + zm.x), ei = (T)0.5 * (zk.y - zm.y);
             const T dr = (T)0.5 * (zk.x - zm.x), di = (T)0.5 * (zk.y + zm.y);
             const T o_r = di, o_i = -dr;
-            const C w = cmul(wbase, unit_root<T, 32>(i));
+            const C w = cmul(wbase, thread_root<T, 2 * E>(i));
             const T xr = (er + (w.x * o_r - w.y * o_i)) * sc;
             const T xi = (ei + (w.x * o_i + w.y * o_r)) * sc;
             if (a.out_layout == LAYOUT_ORD) {
@@ -304,20 +304,20 @@ BFIR_HD cpx<T> inv_elem(const T *in, int layout, int k, int M, T sc, const cpx<T
 }
 
 // inverse, phase 0: thread t builds s_r[k], k = t + i*NTs
-template <class T, int LOG2MS, int R0, bool HEAD>
-BFIR_HD void inv_load_impl(int t, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const T *in, int layout, T sc,
+template <class T, int LOG2MS, int R0, bool HEAD, int LOG2E = 4>
+BFIR_HD void inv_load_impl(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const T *in, int layout, T sc,
                            const T *hx, const T *hh)
 {
-    constexpr int MS = 1 << LOG2MS, NT = MS / 16, M = MS * R0;
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, M = MS * R0;
     typedef cpx<T> C;
-    // one table look-up per thread: the thread's bins k = t + i NT are N/32 (one CTA) or N/64 (two CTAs) apart
+    // one table look-up per thread: the thread's bins k = t + i NT are N/(2E) (one CTA) or N/(4E) (two CTAs) apart
     const C wbase = tw[t << tw_shift_n];                                   // W_N^t
     C wpre = mk<T>((T)1, (T)0);
     if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];               // W_M^t
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
+    for (int i = 0; i < E; i++) {
         const int k = t + i * NT;
-        const C wk = cmul(wbase, R0 == 1 ? unit_root<T, 32>(i) : unit_root<T, 64>(i));   // W_N^k
+        const C wk = cmul(wbase, thread_root<T, (R0 == 1 ? 2 : 4) * E>(i));   // W_N^k
         const C lo = HEAD ? inv_elem<T>(in, layout, k, M, sc, wk, hx, hh) : inv_elem<T>(in, layout, k, M, sc, wk);
         if (R0 == 1) {
             v[i] = lo;
@@ -325,13 +325,13 @@ BFIR_HD void inv_load_impl(int t, int r, cpx<T> (&v)[16], const cpx<T> *__restri
             const C wq = mk<T>(wk.y, -wk.x);                                              // W_N^(k + N/4) = -i W_N^k
             const C hi = HEAD ? inv_elem<T>(in, layout, k + MS, M, sc, wq, hx, hh) : inv_elem<T>(in, layout, k + MS, M, sc, wq);
             if (r == 0) v[i] = cadd(lo, hi);
-            else v[i] = cmul(csub(lo, hi), cconj(cmul(wpre, unit_root<T, 32>(i))));       // W_M^(-k)
+            else v[i] = cmul(csub(lo, hi), cconj(cmul(wpre, thread_root<T, 2 * E>(i))));   // W_M^(-k)
         }
     }
 }
 
-template <class T, int LOG2MS, int R0>
-BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[16], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
+template <class T, int LOG2MS, int R0, int LOG2E = 4>
+BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
 {
     constexpr int M = (1 << LOG2MS) * R0;
     const T *in = (const T *)a.in + bx * a.in_stride_x;
@@ -339,22 +339,22 @@ BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[16], const cpx<T> *__res
     if (a.head_x != NULL && a.head_blocks[bx] > 0) {   // uniform per CTA
         const T *hx = (const T *)a.head_x + bx * a.head_x_stride + (long long)a.state->cur_slot * (2 * M);
         const T *hh = (const T *)a.head_h + bx * a.head_h_stride;
-        inv_load_impl<T, LOG2MS, R0, true>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, hx, hh);
+        inv_load_impl<T, LOG2MS, R0, true, LOG2E>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, hx, hh);
     } else {
-        inv_load_impl<T, LOG2MS, R0, false>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, NULL, NULL);
+        inv_load_impl<T, LOG2MS, R0, false, LOG2E>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, NULL, NULL);
     }
 }
 
 // inverse, phase 1: v[i] = z[R0 n + r], n = t + i*NTs;  x[2m] = Re z[m], x[2m+1] = Im z[m]
-template <class T, int LOG2MS, int R0>
-BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[16], const InvArgs &a, OverflowAcc &acc)
+template <class T, int LOG2MS, int R0, int LOG2E = 4>
+BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[1 << LOG2E], const InvArgs &a, OverflowAcc &acc)
 {
-    constexpr int MS = 1 << LOG2MS, NT = MS / 16, M = MS * R0, L = M;
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, M = MS * R0, L = M;
     typedef cpx<T> C;
     if (a.out_mode == OUT_TIME) {
         C *out = (C *)((T *)a.out + bx * a.out_stride_x);
 #pragma unroll
-        for (int i = 0; i < 16; i++) out[R0 * (t + i * NT) + r] = v[i];
+        for (int i = 0; i < E; i++) out[R0 * (t + i * NT) + r] = v[i];
         return;
     }
     if (t == 0 && r == 0 && a.state != NULL) {         // brutefir.cpp:316-321
@@ -368,11 +368,11 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[16], const InvArg
 #endif
         }
     }
-    // only the first L samples are consumed (fftw_convolver.cpp:425-430): z index < M/2 <=> i < 8
+    // only the first L samples are consumed (fftw_convolver.cpp:425-430): z index < M/2 <=> i < E/2
     if (a.out_mode == OUT_REAL_L) {
         C *out = (C *)((T *)a.out + (long long)bx * L);
 #pragma unroll
-        for (int i = 0; i < 8; i++) out[R0 * (t + i * NT) + r] = v[i];
+        for (int i = 0; i < E / 2; i++) out[R0 * (t + i * NT) + r] = v[i];
         return;
     }
     // OUT_RAW
@@ -384,7 +384,7 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[16], const InvArg
     if (fmt_isfloat(a.fmt)) {
         const T rmax = (T)a.ovf_max;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < E / 2; i++) {
             uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
             store_raw_float<T>(p, a.fmt, v[i].x, rmax, acc);
             store_raw_float<T>(p + step, a.fmt, v[i].y, rmax, acc);
@@ -394,7 +394,7 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[16], const InvArg
         int_limits(a.fmt, imin, imax);
         const T rmin = (T)imin, rmax = (T)imax;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < E / 2; i++) {
             uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
             store_raw_quantised<T>(p, a.fmt, v[i].x, rmin, rmax, imin, imax, acc);
             store_raw_quantised<T>(p + step, a.fmt, v[i].y, rmin, rmax, imin, imax, acc);
@@ -423,33 +423,37 @@ __device__ __forceinline__ void overflow_commit(OverflowStats *dst, OverflowAcc 
     if (lb) atomicMax(&dst->largest_bits, lb);
 }
 
+// 8 points per thread at 4096 points per CTA: two CTAs of 512 threads per SM (64 registers each)
+#ifndef BFIR_E8_MINB
+#define BFIR_E8_MINB(log2e, log2ms) (((log2e) == 3 && (log2ms) == 12) ? 2 : 1)
+#endif
 // grid = (buffers, partitions, R0); tw_shift_m = log2(table length / Ms), tw_shift_n = log2(table length / N)
-template <class T, int LOG2MS, int R0>
-__global__ void __launch_bounds__((1 << LOG2MS) / 16) rfft_forward_kernel(const FwdArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
+template <class T, int LOG2MS, int R0, int LOG2E = 4>
+__global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LOG2MS)) rfft_forward_kernel(const FwdArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
     const int t = threadIdx.x, bx = blockIdx.x + a.ch_base, by = blockIdx.y, r = blockIdx.z;
-    cpx<T> v[16];
-    fwd_load<T, LOG2MS, R0>(t, bx, by, r, v, tw, tw_shift_n, a);
-    fft_passes<T, LOG2MS, false, 0, 0>::run(t, v, smem, tw, tw_shift_m);
-    BlockFFT<T, LOG2MS, false>::store_natural(t, v, smem);
+    cpx<T> v[1 << LOG2E];
+    fwd_load<T, LOG2MS, R0, LOG2E>(t, bx, by, r, v, tw, tw_shift_n, a);
+    fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run(t, v, smem, tw, tw_shift_m);
+    BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, v, smem);
     __syncthreads();
-    fwd_split_store<T, LOG2MS, R0>(t, bx, by, r, smem, tw, tw_shift_n, a);
+    fwd_split_store<T, LOG2MS, R0, LOG2E>(t, bx, by, r, smem, tw, tw_shift_n, a);
 }
 
-template <class T, int LOG2MS, int R0>
-__global__ void __launch_bounds__((1 << LOG2MS) / 16) rfft_inverse_kernel(const InvArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
+template <class T, int LOG2MS, int R0, int LOG2E = 4>
+__global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LOG2MS)) rfft_inverse_kernel(const InvArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
     const int t = threadIdx.x, bx = blockIdx.x + a.ch_base, r = blockIdx.z;
-    cpx<T> v[16];
-    inv_load<T, LOG2MS, R0>(t, bx, r, v, tw, tw_shift_n, a);
-    fft_passes<T, LOG2MS, true, 0, 0>::run(t, v, smem, tw, tw_shift_m);
+    cpx<T> v[1 << LOG2E];
+    inv_load<T, LOG2MS, R0, LOG2E>(t, bx, r, v, tw, tw_shift_n, a);
+    fft_passes<T, LOG2MS, true, 0, 0, LOG2E>::run(t, v, smem, tw, tw_shift_m);
     OverflowAcc acc;
     acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
-    inv_store<T, LOG2MS, R0>(t, bx, r, v, a, acc);
+    inv_store<T, LOG2MS, R0, LOG2E>(t, bx, r, v, a, acc);
     if (a.out_mode == OUT_RAW && a.stats != NULL) overflow_commit(&a.stats[bx], acc);
     if (a.state != NULL && blockIdx.x == 0 && t == 0 && r == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
 }

@@ -32,9 +32,9 @@ template <class T> static double rel_rms(const std::vector<T> &a, const std::vec
 }
 
 // LOG2MS = sub-transform size per CTA, R0 = CTAs per buffer; total M = MS * R0
-template <class T, int LOG2MS, int R0> static int check(double tol)
+template <class T, int LOG2MS, int R0, int LOG2E = 4> static int check(double tol)
 {
-    constexpr int MS = 1 << LOG2MS, M = MS * R0, N = 2 * M, NT = MS / 16;
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, M = MS * R0, N = 2 * M, NT = MS / E;
     typedef cpx<T> C;
     std::mt19937 rng(1234 + LOG2MS + 100 * R0);
     std::uniform_real_distribution<double> u(-1, 1);
@@ -43,8 +43,8 @@ template <class T, int LOG2MS, int R0> static int check(double tol)
     auto tw = make_tw<T>(N);
     const int sm = R0 == 2 ? 2 : 1; // log2(N / MS)
     std::vector<C> smem(fft_smem_elems<MS>::value);
-    std::vector<C> regs((size_t)NT * 16);
-    C (*vs)[16] = reinterpret_cast<C (*)[16]>(regs.data());
+    std::vector<C> regs((size_t)NT * E);
+    C (*vs)[E] = reinterpret_cast<C (*)[E]>(regs.data());
     int fails = 0;
 
     for (int layout = 0; layout < 2; layout++) {
@@ -52,10 +52,10 @@ template <class T, int LOG2MS, int R0> static int check(double tol)
         a.in_mode = IN_TIME; a.out_layout = layout; a.in = x.data(); a.out = layout == LAYOUT_HC ? hc.data() : ord.data();
         a.scale_in = 1.0; a.scale_out = layout == LAYOUT_ORD ? 0.5 : 1.0;
         for (int r = 0; r < R0; r++) {
-            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0>(t, 0, 0, r, vs[t], tw.data(), 0, a);
-            fft_passes<T, LOG2MS, false, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
-            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false>::store_natural(t, vs[t], smem.data());
-            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0>(t, 0, 0, r, smem.data(), tw.data(), 0, a);
+            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0, LOG2E>(t, 0, 0, r, vs[t], tw.data(), 0, a);
+            fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
+            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, vs[t], smem.data());
+            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0, LOG2E>(t, 0, 0, r, smem.data(), tw.data(), 0, a);
         }
     }
     oracle_fft::RealFFT<T> of(N);
@@ -77,18 +77,18 @@ template <class T, int LOG2MS, int R0> static int check(double tol)
         b.in_layout = layout; b.out_mode = OUT_TIME; b.in = layout == LAYOUT_HC ? ref.data() : ord_ref.data();
         b.scale_in = layout == LAYOUT_ORD ? 2.0 : 1.0; b.out = back.data();
         for (int r = 0; r < R0; r++) {
-            for (int t = 0; t < NT; t++) inv_load<T, LOG2MS, R0>(t, 0, r, vs[t], tw.data(), 0, b);
-            fft_passes<T, LOG2MS, true, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
+            for (int t = 0; t < NT; t++) inv_load<T, LOG2MS, R0, LOG2E>(t, 0, r, vs[t], tw.data(), 0, b);
+            fft_passes<T, LOG2MS, true, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
             OverflowAcc acc = {};
-            for (int t = 0; t < NT; t++) inv_store<T, LOG2MS, R0>(t, 0, r, vs[t], b, acc);
+            for (int t = 0; t < NT; t++) inv_store<T, LOG2MS, R0, LOG2E>(t, 0, r, vs[t], b, acc);
         }
         std::vector<T> want(N);
         for (int i = 0; i < N; i++) want[i] = x[i] * (T)N;
         e3[layout] = rel_rms(back, want);
     }
     bool ok = e1 < tol && e2 < tol && e3[0] < tol && e3[1] < tol;
-    printf("%s log2ms=%2d R0=%d  r2hc %.3e  ord %.3e  hc2r(ord) %.3e  hc2r(hc) %.3e  %s\n", sizeof(T) == 4 ? "f32" : "f64",
-           LOG2MS, R0, e1, e2, e3[0], e3[1], ok ? "ok" : "FAIL");
+    printf("%s log2ms=%2d R0=%d E=%2d  r2hc %.3e  ord %.3e  hc2r(ord) %.3e  hc2r(hc) %.3e  %s\n", sizeof(T) == 4 ? "f32" : "f64",
+           LOG2MS, R0, E, e1, e2, e3[0], e3[1], ok ? "ok" : "FAIL");
     if (!ok) fails++;
     return fails;
 }
@@ -97,9 +97,9 @@ template <class T, int LOG2MS, int R0> static int check(double tol)
 // slot addressing, coefficient partitions, raw / planar output) on exactly-sized host buffers, so that an
 // out-of-bounds index shows up under AddressSanitizer. Values are checked against the IN_TIME/OUT_TIME
 // path verified above.
-template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in, int fmt_out)
+template <class T, int LOG2MS, int R0, int LOG2E = 4> static int check_engine_modes(int fmt_in, int fmt_out)
 {
-    constexpr int MS = 1 << LOG2MS, M = MS * R0, N = 2 * M, L = M, NT = MS / 16;
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, M = MS * R0, N = 2 * M, L = M, NT = MS / E;
     typedef cpx<T> C;
     const int S = 2, CH = 3, Ct = S * CH, P = 3;
     const int sm = R0 == 2 ? 2 : 1;
@@ -107,8 +107,8 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
     std::uniform_real_distribution<double> u(-1, 1);
     auto tw = make_tw<T>(N);
     std::vector<C> smem(fft_smem_elems<MS>::value);
-    std::vector<C> regs((size_t)NT * 16);
-    C (*vs)[16] = reinterpret_cast<C (*)[16]>(regs.data());
+    std::vector<C> regs((size_t)NT * E);
+    C (*vs)[E] = reinterpret_cast<C (*)[E]>(regs.data());
     const int ib = fmt_bytes(fmt_in), ob = fmt_bytes(fmt_out);
     std::vector<uint8_t> raw_in((size_t)S * L * CH * ib), raw_out((size_t)S * L * CH * ob, 0);
     std::vector<T> planar((size_t)Ct * L);
@@ -131,10 +131,10 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
         a.prev = prev.data(); a.fmt = fmt_in; a.ch_per_stream = CH; a.n_channels = Ct; a.ch_base = 0; a.prev_parity = 0;
         a.state = &st; a.n_slots = P; a.procblocks = procblocks.data(); a.pb_inc = pb_inc.data();
         for (int r = 0; r < R0; r++) {
-            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0>(t, bx, 0, r, vs[t], tw.data(), 0, a);
-            fft_passes<T, LOG2MS, false, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
-            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false>::store_natural(t, vs[t], smem.data());
-            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0>(t, bx, 0, r, smem.data(), tw.data(), 0, a);
+            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0, LOG2E>(t, bx, 0, r, vs[t], tw.data(), 0, a);
+            fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
+            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, vs[t], smem.data());
+            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0, LOG2E>(t, bx, 0, r, smem.data(), tw.data(), 0, a);
         }
         // reference: [0 | cur] through the plain path
         std::fill(tbuf.begin(), tbuf.end(), (T)0);
@@ -142,10 +142,10 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
         FwdArgs b = {};
         b.in_mode = IN_TIME; b.out_layout = LAYOUT_ORD; b.in = tbuf.data(); b.out = ref.data(); b.scale_in = 1.0; b.scale_out = 0.5;
         for (int r = 0; r < R0; r++) {
-            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0>(t, 0, 0, r, vs[t], tw.data(), 0, b);
-            fft_passes<T, LOG2MS, false, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
-            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false>::store_natural(t, vs[t], smem.data());
-            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0>(t, 0, 0, r, smem.data(), tw.data(), 0, b);
+            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0, LOG2E>(t, 0, 0, r, vs[t], tw.data(), 0, b);
+            fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
+            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, vs[t], smem.data());
+            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0, LOG2E>(t, 0, 0, r, smem.data(), tw.data(), 0, b);
         }
         std::vector<T> got(fdl.begin() + ((size_t)bx * P + 1) * N, fdl.begin() + ((size_t)bx * P + 2) * N);
         if (rel_rms(got, ref) > 1e-6) { printf("engine fwd mismatch ch %d\n", bx); fails++; }
@@ -163,9 +163,9 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
         if (!fmt_isfloat(fmt_out)) v.scale_in *= 32768.0 / (fmt_in == FMT_FLOAT_LE ? 1.0 : 8388608.0);
         OverflowAcc acc = {};
         for (int r = 0; r < R0; r++) {
-            for (int t = 0; t < NT; t++) inv_load<T, LOG2MS, R0>(t, bx, r, vs[t], tw.data(), 0, v);
-            fft_passes<T, LOG2MS, true, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
-            for (int t = 0; t < NT; t++) inv_store<T, LOG2MS, R0>(t, bx, r, vs[t], v, acc);
+            for (int t = 0; t < NT; t++) inv_load<T, LOG2MS, R0, LOG2E>(t, bx, r, vs[t], tw.data(), 0, v);
+            fft_passes<T, LOG2MS, true, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
+            for (int t = 0; t < NT; t++) inv_store<T, LOG2MS, R0, LOG2E>(t, bx, r, vs[t], v, acc);
         }
     }
     // [0 | cur] -> first half of the inverse is zero (the previous block was silence)
@@ -198,9 +198,9 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
             v.head_blocks = hb.data();
             OverflowAcc acc = {};
             for (int r = 0; r < R0; r++) {
-                for (int t = 0; t < NT; t++) inv_load<T, LOG2MS, R0>(t, bx, r, vs[t], tw.data(), 0, v);
-                fft_passes<T, LOG2MS, true, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
-                for (int t = 0; t < NT; t++) inv_store<T, LOG2MS, R0>(t, bx, r, vs[t], v, acc);
+                for (int t = 0; t < NT; t++) inv_load<T, LOG2MS, R0, LOG2E>(t, bx, r, vs[t], tw.data(), 0, v);
+                fft_passes<T, LOG2MS, true, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
+                for (int t = 0; t < NT; t++) inv_store<T, LOG2MS, R0, LOG2E>(t, bx, r, vs[t], v, acc);
             }
         }
         for (int s_ = 0; s_ < S; s_++) for (int n = 0; n < L; n++) for (int c = 0; c < CH; c++) {
@@ -225,10 +225,10 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
         a.out = hs.data(); a.out_stride_x = (long long)P * N; a.out_stride_y = N; a.scale_in = 0.5; a.scale_out = 1.0 / N;
         a.coeff_len = (int)h.size(); a.nonfinite = &flag;
         for (int r = 0; r < R0; r++) {
-            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0>(t, 0, by, r, vs[t], tw.data(), 0, a);
-            fft_passes<T, LOG2MS, false, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
-            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false>::store_natural(t, vs[t], smem.data());
-            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0>(t, 0, by, r, smem.data(), tw.data(), 0, a);
+            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0, LOG2E>(t, 0, by, r, vs[t], tw.data(), 0, a);
+            fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
+            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, vs[t], smem.data());
+            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0, LOG2E>(t, 0, by, r, smem.data(), tw.data(), 0, a);
         }
     }
     if (flag != 0) fails++;
@@ -238,15 +238,15 @@ template <class T, int LOG2MS, int R0> static int check_engine_modes(int fmt_in,
         FwdArgs a = {};
         a.in_mode = IN_UPPER; a.out_layout = LAYOUT_ORD; a.in = src.data(); a.out = up.data(); a.scale_in = 1.0; a.scale_out = 1.0 / N;
         for (int r = 0; r < R0; r++) {
-            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0>(t, 0, 0, r, vs[t], tw.data(), 0, a);
-            fft_passes<T, LOG2MS, false, 0, 0>::run_host(vs, smem.data(), tw.data(), sm);
-            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false>::store_natural(t, vs[t], smem.data());
-            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0>(t, 0, 0, r, smem.data(), tw.data(), 0, a);
+            for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0, LOG2E>(t, 0, 0, r, vs[t], tw.data(), 0, a);
+            fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
+            for (int t = 0; t < NT; t++) BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, vs[t], smem.data());
+            for (int t = 0; t < NT; t++) fwd_split_store<T, LOG2MS, R0, LOG2E>(t, 0, 0, r, smem.data(), tw.data(), 0, a);
         }
         std::vector<T> got(hs.begin() + (size_t)2 * N, hs.end());
         if (rel_rms(got, up) > 1e-6) { printf("coefficient partition mismatch\n"); fails++; }
     }
-    printf("%s engine modes log2ms=%d R0=%d fmt %d->%d  %s\n", sizeof(T) == 4 ? "f32" : "f64", LOG2MS, R0, fmt_in, fmt_out, fails ? "FAIL" : "ok");
+    printf("%s engine modes log2ms=%d R0=%d E=%d fmt %d->%d  %s\n", sizeof(T) == 4 ? "f32" : "f64", LOG2MS, R0, E, fmt_in, fmt_out, fails ? "FAIL" : "ok");
     return fails;
 }
 
@@ -262,6 +262,11 @@ int main(int argc, char **argv)
     f += check<float, 4, 1>(2e-6); f += check<double, 5, 1>(4e-15); f += check<float, 6, 1>(2e-6); f += check<double, 7, 1>(4e-15);
     f += check<float, 8, 1>(2e-6); f += check<double, 9, 1>(4e-15);
     f += check<float, 7, 2>(2e-6); f += check<double, 5, 2>(4e-15);
+    // 8 points per thread (the double-precision variants): pass plans [8,8], [8,8,2], [8,8,4], one and two CTAs, engine modes
+    f += check<double, 6, 1, 3>(4e-15); f += check<double, 7, 1, 3>(4e-15); f += check<double, 8, 1, 3>(4e-15);
+    f += check<double, 6, 2, 3>(4e-15); f += check<double, 7, 2, 3>(4e-15);
+    f += check_engine_modes<double, 6, 1, 3>(FMT_S24_LE, FMT_S16_LE);
+    f += check_engine_modes<double, 7, 2, 3>(FMT_FLOAT_LE, FMT_FLOAT_LE);
 #ifndef EMU_QUICK
     if (!quick) {
         f += check<float, 5, 1>(2e-6); f += check<float, 7, 1>(2e-6); f += check<float, 9, 1>(2e-6); f += check<float, 10, 1>(2e-6);
@@ -271,6 +276,8 @@ int main(int argc, char **argv)
         f += check<double, 11, 1>(4e-15); f += check<double, 12, 1>(4e-15); f += check<double, 13, 1>(4e-15);
         f += check<float, 12, 2>(2e-6); f += check<float, 14, 2>(2e-6);
         f += check<double, 12, 2>(4e-15); f += check<double, 13, 2>(4e-15);
+        f += check<double, 9, 1, 3>(4e-15); f += check<double, 10, 1, 3>(4e-15); f += check<double, 11, 1, 3>(4e-15); f += check<double, 12, 1, 3>(4e-15);
+        f += check<double, 9, 2, 3>(4e-15); f += check<double, 10, 2, 3>(4e-15); f += check<double, 11, 2, 3>(4e-15); f += check<double, 12, 2, 3>(4e-15);
     }
 #endif
     printf(f ? "FAILED %d\n" : "ALL OK\n", f);

@@ -571,3 +571,29 @@ def test_lookahead_partition_sum_equals_plain_path(pkg, oracle, rs, groups, monk
             m = ~np.isnan(yp)
             assert rel_rms(ya[m], yp[m]) < tol if m.any() else True
     assert plain.blockcounter() == ahead.blockcounter()
+
+
+@pytest.mark.parametrize("L,S", [(256, 40), (4096, 36), (64, 70)])
+def test_double_precision_batches_above_64_buffers(pkg, oracle, L, S):
+    """More than 64 double-precision transforms per launch take the other kernel variants (16 points per thread on the
+    inverse side, 8 on the forward side up to 4096 points per CTA; below that count both sides use 8): every variant
+    against the oracle, a few streams of the batch each."""
+    P, C = 3, 2
+    g = pkg.Brutefir(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 48000, False, n_streams=S)
+    h = [decay_filter(c % 7, L * P) * (1.0 + 0.01 * c) for c in range(C * S)]
+    assert g.set_coeff(h, P) == 0
+    probe = [0, S // 2, S - 1]
+    singles = {}
+    for s in probe:
+        e = oracle.Engine(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 48000, False)
+        assert e.set_coeff(h[s * C:(s + 1) * C], P) == 0
+        singles[s] = e
+    x = white_noise(19, 5 * L, C * S)
+    for b in range(5):
+        batched = np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2))
+        rc, out = g.run(batched.view(np.uint8).ravel())
+        assert rc == 0
+        out = out.view(np.float64).reshape(S, L, C)
+        for s in probe:
+            _, ref = singles[s].run(np.ascontiguousarray(batched[s]).view(np.uint8).ravel())
+            assert rel_rms(out[s], ref.view(np.float64).reshape(L, C)) < 1e-12, (b, s)
