@@ -18,7 +18,9 @@ BFIR_FOR_F64(BFIR_DECL)
     cudaError_t launch_inv_##tag##_m##m(int, dim3, cudaStream_t, const InvArgs &, const void *, int, int);
 #define BFIR_FOR_F64E8(X) X(f64e8, 6) X(f64e8, 7) X(f64e8, 8) X(f64e8, 9) X(f64e8, 10) X(f64e8, 11) X(f64e8, 12)
 BFIR_FOR_F64E8(BFIR_DECL_E8)
-static const int kMinLog2M_e8 = 6, kMaxLog2M_e8 = 12;
+#define BFIR_FOR_F32E8(X) X(f32e8, 6) X(f32e8, 7) X(f32e8, 8) X(f32e8, 9) X(f32e8, 10) X(f32e8, 11) X(f32e8, 12) X(f32e8, 13)
+BFIR_FOR_F32E8(BFIR_DECL_E8)
+static const int kMinLog2M_e8 = 6, kMaxLog2M_e8 = 12, kMaxLog2M_e8_f32 = 13;
 
 static const int kMinLog2M = 4, kMaxLog2M_f32 = 14, kMaxLog2M_f64 = 13;
 
@@ -33,23 +35,31 @@ static const cfft_launcher_t kCfftF64[] = { BFIR_FOR_F64(BFIR_CFFT_ENTRY) };
 static const inv_launcher_t kInvF64[] = { BFIR_FOR_F64(BFIR_INV_ENTRY) };
 static const fwd_launcher_t kFwdF64E8[] = { BFIR_FOR_F64E8(BFIR_FWD_ENTRY) };
 static const inv_launcher_t kInvF64E8[] = { BFIR_FOR_F64E8(BFIR_INV_ENTRY) };
+static const fwd_launcher_t kFwdF32E8[] = { BFIR_FOR_F32E8(BFIR_FWD_ENTRY) };
+static const inv_launcher_t kInvF32E8[] = { BFIR_FOR_F32E8(BFIR_INV_ENTRY) };
 
-// 8 instead of 16 points per thread for a double-precision transform whose per-CTA size is 2^sub?
-// Measured on B200 (tools/kernel_times.py, profiles/r01_fft_e8_vs_e16.jsonl): 16 double-complex points per thread
-// cost 128 registers and leave two warps per scheduler, so with few transforms in flight (the latency path) the
-// 8-point variant wins everywhere (cfg1 single stream: forward 22.6 -> 19.0 us, inverse 18.2 -> 16.7; 4 streams:
-// 30.3 -> 20.1 / 22.4 -> 18.2; product configuration 12.6 -> 10.2 / 10.8 -> 9.8). With more than 64 transforms
-// per launch the forward side still gains up to 4096 points per CTA (18.4 -> 16.6 us at 128 buffers), the inverse
-// side does not (15.0 -> 16.7), and 8192-point transforms are best on one 16-point CTA each (25.1 vs 29.3 us).
+// 8 instead of 16 points per thread for a transform whose per-CTA size is 2^sub?
+// Measured on B200 (tools/kernel_times.py, profiles/r01_fft_e8_vs_e16.jsonl). While a launch has at most one CTA
+// per SM the kernels are a dependent-latency chain, and half the work per thread on twice the warps wins in both
+// precisions (double cfg1 single stream: forward 22.6 -> 19.0 us, inverse 18.2 -> 16.7; 4 streams 30.3 -> 20.1 /
+// 22.4 -> 18.2; product configuration 12.6 -> 10.2 / 10.8 -> 9.8; float cfg0 12.8 -> 11.1 / 11.4 -> 10.5; 128 float
+// buffers of 1024 points 12.7 -> 10.3 / 11.6 -> 8.8). Larger launches are throughput-bound: 16 points per thread are
+// as fast or faster (float cfg3 shape, 2048 buffers: 61.9 / 55.0 us against 71.5 / 59.9; double 4096 x 256:
+// 22.8 / 21.6 against 23.1 / 24.0), except the double forward side up to 2048 points per CTA (16.9 -> 15.2 us).
 // BFIR_FFT_E = 8 | 16 forces the answer where both exist.
 static bool use_e8(int realsize, int sub, int r0, long long n_buffers, bool forward)
 {
-    if (realsize != 8 || sub < kMinLog2M_e8 || sub > kMaxLog2M_e8) return false;
+    if (sub < kMinLog2M_e8 || sub > (realsize == 8 ? kMaxLog2M_e8 : kMaxLog2M_e8_f32)) return false;
     static const int forced = [] { const char *env = getenv("BFIR_FFT_E"); return env ? atoi(env) : 0; }();
     if (forced == 8) return true;
     if (forced == 16) return false;
-    if (n_buffers <= 64) return true;
-    return forward && r0 == 1;
+    static const int n_sm = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        return n;
+    }();
+    if (n_buffers * r0 <= n_sm) return true;
+    return realsize == 8 && forward && sub <= 11;
 }
 
 static int max_sub(int realsize) { return realsize == 4 ? kMaxLog2M_f32 : kMaxLog2M_f64; }
@@ -90,7 +100,7 @@ cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cuda
     const int sub = log2m - (r0 == 2 ? 1 : 0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
     // table length N = 2 * 2^log2m: shift for the sub-transform twiddles, 0 for the W_N^k of the split step
-    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, true)) return kFwdF64E8[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
+    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, true)) return (realsize == 4 ? kFwdF32E8 : kFwdF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
     return (realsize == 4 ? kFwdF32 : kFwdF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }
 
@@ -99,7 +109,7 @@ cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cuda
     if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
     const int sub = log2m - (r0 == 2 ? 1 : 0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
-    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return kInvF64E8[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
+    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return (realsize == 4 ? kInvF32E8 : kInvF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
     return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }
 

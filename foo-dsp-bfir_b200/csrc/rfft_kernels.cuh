@@ -425,7 +425,7 @@ __device__ __forceinline__ void overflow_commit(OverflowStats *dst, OverflowAcc 
 
 // 8 points per thread at 4096 points per CTA: two CTAs of 512 threads per SM (64 registers each)
 #ifndef BFIR_E8_MINB
-#define BFIR_E8_MINB(log2e, log2ms) (((log2e) == 3 && (log2ms) == 12) ? 2 : 1)
+#define BFIR_E8_MINB(log2e, log2ms) (((log2e) == 3 && (log2ms) == 12) ? 2 : 0)
 #endif
 // grid = (buffers, partitions, R0); tw_shift_m = log2(table length / Ms), tw_shift_n = log2(table length / N)
 template <class T, int LOG2MS, int R0, int LOG2E = 4>
