@@ -448,6 +448,7 @@ int Engine::set_groups(int n)
     for (int g = 0; g < n_groups && g < BFIR_MAX_GROUPS; g++)
         if (groups[g].stream) BFIR_CUDA(cudaStreamSynchronize(groups[g].stream));
     n_groups = n;
+    done_ticket = next_ticket;      // everything queued so far has completed (streams synchronised above)
     tail_ready = false;
     invalidate_graphs();
     const int base = S / n, extra = S % n;
@@ -860,7 +861,7 @@ int Engine::wait_ticket(long long t)
     if (t < 0 || t >= next_ticket) { set_error("bfir_wait: unknown ticket %lld", t); return BFIR_ERR_INVALID; }
     for (; done_ticket <= t; done_ticket++) {
         const int slot = (int)(done_ticket % kMaxInflight);
-        for (int g = 0; g < n_groups; g++) BFIR_CUDA(cudaEventSynchronize(ticket_ev[slot][g]));
+        for (int g = 0; g < n_groups; g++) if (ticket_ev[slot][g]) BFIR_CUDA(cudaEventSynchronize(ticket_ev[slot][g]));
     }
     if (*(volatile int *)h_flag != 0) return sync_and_probe(false);   // a probe fired: drain everything and report
     return BFIR_OK;
