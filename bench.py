@@ -12,11 +12,12 @@ Workload (one "step" = one block of the block loop, brutefir::run, for every str
   line = S x 64 MiB) exceeds the 126 MB L2 -- no L2 flush is needed between steps. N GPUs: every rank
   runs its own S streams (channel/stream sharding, no collective): weak scaling.
 
-Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM; e2e = the
+Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM, two blocks per call
+(bfir_run_device_pair: one partition-sum launch for both, every coefficient spectrum read once); e2e = the
 same metric on pinned HOST buffers, the H2D of every input block and the D2H of every output block inside
-the timed region: e2e.value through bfir_run_async/bfir_wait (three blocks in flight), e2e.sync_run through the
-reference's synchronous run() = bfir_run (H2D + kernels + D2H + sync per call); roofline
-= partition-MAC kernel, algorithmic bytes (2P+1)*N*realsize per channel-block over its CUDA-event
+the timed region: e2e.value through bfir_run_async_pair/bfir_wait (two calls in flight), e2e.one_block_per_call
+through bfir_run_async, e2e.sync_run through the reference's synchronous run() = bfir_run (H2D + kernels + D2H +
+sync per call); roofline = partition-sum kernel, algorithmic bytes (2P+1)*N*realsize per channel-block over its CUDA-event
 time; cpu_baseline = the reference's own sources (oracle/_ref, FFT provider named) on the host cores;
 latency = host-visible bfir_run latency of ONE 7.1 stream (p50/p99).
 `--impl reference` times only the CPU reference (rank 0), same metric/config.
@@ -49,6 +50,8 @@ def workload_config(streams, n_gpus):
         "l2": "streamed set per step (%d MiB coefficient + delay-line spectra per GPU) exceeds the 126 MB L2; no flush"
               % (streams * CFG["channels"] * 2 * CFG["P"] * 2 * CFG["L"] * CFG["realsize"] // (1 << 20)),
         "prefill_blocks": CFG["P"],
+        "step": "one block (8192 frames) of every stream; throughput passes call the two-block entry points (bfir_run_device_pair / "
+                "bfir_run_async_pair), i.e. two steps per call with one partition-sum launch; the one-block-per-call numbers ride beside them",
     }
 
 
@@ -233,53 +236,75 @@ def main():
     torch.cuda.synchronize()
 
     # prefill the delay line so that every timed step convolves all P partitions, then W warm-up steps
-    for b in range(P + W):
+    for b in range(P):
         eng.run_device(dev_in[b % ring], dev_out)
+    warm_out2 = torch.empty_like(dev_out)
+    for b in range(0, max(W, 2), 2):       # warm-up through the two-block entry point (its buffers are allocated here)
+        eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, warm_out2)
     assert eng.sync() == 0
 
-    # ---- device-resident throughput: EXACTLY K steps between barrier+sync, CUDA events on the launch stream
-    eng.set_profiling(K)
-    launches0 = pkg.kernel_launch_count()
-    barrier()
+    # ---- device-resident throughput: EXACTLY K steps between barrier+sync, CUDA events on the launch stream.
+    # A throughput caller has the next block at hand, so the steps go through the two-block entry point: both forward
+    # transforms, ONE partition-sum launch that reads every coefficient spectrum once for both blocks, both inverse
+    # transforms (one stream, kernels back to back, so each kernel's CUDA-event time is its own: the roofline's).
+    dev_out2 = torch.empty_like(dev_out)
+
+    def device_pass(single):
+        eng.set_profiling(K if single else K // 2)
+        n0 = pkg.kernel_launch_count()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        if single:
+            for b in range(K):
+                eng.run_device(dev_in[b % ring], dev_out)
+        else:
+            for b in range(0, K - 1, 2):
+                eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2)
+            if K % 2:
+                eng.run_device(dev_in[(K - 1) % ring], dev_out)
+        e1.record(stream)
+        assert eng.sync() == 0
+        barrier()
+        n = pkg.kernel_launch_count() - n0
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        pr, npr = eng.get_profile()
+        return ms, n, pr, npr
+
     sampler.busy.set()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for b in range(K):
-        eng.run_device(dev_in[b % ring], dev_out)
-    ev1.record(stream)
-    assert eng.sync() == 0
-    barrier()
+    ms_total, launches, prof, nprof = device_pass(single=False)
     sampler.busy.clear()
-    launches = pkg.kernel_launch_count() - launches0
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    prof, nprof = eng.get_profile()
     value = n_gpus * Ct * L * K / (ms_total * 1e-3) / 1e6
+    # the same K steps one block per call (what a real-time caller gets; the per-block partition sum of SURVEY 8d)
+    ms_single, _, prof_single, nprof_single = device_pass(single=True)
+    mac_split = eng.get_mac_split()
 
-    # the same device-resident work the way the end-to-end path runs it: 8 stream groups, no join between blocks
-    # (a group that is done with block t starts block t+1 while others still convolve t, so transforms run under
-    # the partition sums). Per-kernel event times overlap there, so the roofline above stays on the serial pass.
+    # the same device-resident work the way the end-to-end path runs it: 8 stream groups, no join between calls
+    # (a group that is done with its blocks starts the next ones while others still convolve, so transforms run under
+    # the partition sums). Per-kernel event times overlap there, so the roofline stays on the serial pass above.
     eng.set_groups(min(8, S))
-    for b in range(3):
-        eng.run_device_pipelined(dev_in[b % ring], dev_out)
+    for b in range(0, 4, 2):
+        eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2, pipelined=True)
     assert eng.sync() == 0
     barrier()
     ev0g, ev1g = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0g.record(stream)
-    for b in range(K):
-        eng.run_device_pipelined(dev_in[b % ring], dev_out)
+    for b in range(0, K - 1, 2):
+        eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2, pipelined=True)
     eng.join()
     ev1g.record(stream)
     assert eng.sync() == 0
     barrier()
     ms_grouped = max_over_ranks(ev0g.elapsed_time(ev1g))
-    value_grouped = {"value": n_gpus * Ct * L * K / (ms_grouped * 1e-3) / 1e6, "ms_per_step": ms_grouped / K,
-                     "stream_groups": eng.get_groups(), "api": "bfir_run_device_pipelined + bfir_join"}
+    kp = K - K % 2
+    value_grouped = {"value": n_gpus * Ct * L * kp / (ms_grouped * 1e-3) / 1e6, "ms_per_step": ms_grouped / kp,
+                     "stream_groups": eng.get_groups(), "api": "bfir_run_device_pair(pipelined) + bfir_join"}
 
     # ---- end to end on pinned host buffers, every step: H2D of the step's input block, the kernels, D2H of its
-    # output block. Two ways of calling: bfir_run (the reference's synchronous run(), stream groups overlap inside
-    # one call) and bfir_run_async/bfir_wait (batch callers: DEPTH blocks in flight, so the copies and kernels of
-    # consecutive blocks overlap too). The pipelined number is e2e.value, the synchronous one rides beside it.
-    DEPTH = 3
+    # output block. e2e.value: bfir_run_async_pair / bfir_wait (two blocks per call, DEPTH calls in flight, stream
+    # groups with their own copy streams), median of 3 passes of K steps (the pass is half host work, and the hosts
+    # of this pool are noisy). Beside it: one block per call (bfir_run_async) and the reference's synchronous run().
+    DEPTH = 2
 
     def e2e_pass(engine, ins, outs, steps, sync_groups, async_groups):
         engine.set_groups(min(sync_groups, S))
@@ -295,30 +320,47 @@ def main():
         assert rc == 0
         engine.set_groups(min(async_groups, S))
         groups = engine.get_groups()
-        tickets = [engine.run_async(ins[b % len(ins)], outs[b % len(outs)]) for b in range(3)]
-        assert engine.wait(tickets[-1]) == 0
-        barrier()
-        tickets = []
-        t0 = time.perf_counter()
-        for b in range(steps):
-            tickets.append(engine.run_async(ins[b % len(ins)], outs[b % len(outs)]))
-            if b >= DEPTH:
-                rc = engine.wait(tickets[b - DEPTH])     # block b-DEPTH is now in outs[(b-DEPTH) % len(outs)]
-        rc |= engine.wait(tickets[-1])
-        torch.cuda.synchronize()
-        t_async = time.perf_counter() - t0
-        assert rc == 0
-        barrier()
-        return max_over_ranks(t_sync), max_over_ranks(t_async), groups
+        ni, no = len(ins), len(outs)
+
+        def async_pass(pairs):
+            barrier()
+            tickets = []
+            t0 = time.perf_counter()
+            if pairs:
+                for k in range(steps // 2):
+                    b = 2 * k
+                    tickets.append(engine.run_async_pair(ins[b % ni], ins[(b + 1) % ni], outs[b % no], outs[(b + 1) % no]))
+                    if k >= DEPTH:
+                        assert engine.wait(tickets[k - DEPTH]) == 0   # blocks 2(k-DEPTH), +1 are now in their host buffers
+                if steps % 2:
+                    tickets.append(engine.run_async(ins[(steps - 1) % ni], outs[(steps - 1) % no]))
+            else:
+                for b in range(steps):
+                    tickets.append(engine.run_async(ins[b % ni], outs[b % no]))
+                    if b >= 2 * DEPTH:
+                        assert engine.wait(tickets[b - 2 * DEPTH]) == 0
+            assert engine.wait(tickets[-1]) == 0
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            return max_over_ranks(dt)
+        async_pass(True)                                             # warm-up (allocates the staging ring)
+        t_pairs = sorted(async_pass(True) for _ in range(3))
+        t_single = async_pass(False)
+        return max_over_ranks(t_sync), t_pairs, t_single, groups
 
     e2e_steps = K
-    host_outs = [host_out] + [torch.empty(S * L * C, dtype=torch.float64).pin_memory() for _ in range(DEPTH)]
-    np_in, np_outs = [h.numpy() for h in host_in], [h.numpy() for h in host_outs]
+    n_host = 2 * (DEPTH + 1)
+    host_ins = host_in + [torch.from_numpy(noise_block(1000 * rank + 50 + b, S, L, C)).contiguous().pin_memory() for b in range(n_host - ring)]
+    host_outs = [host_out] + [torch.empty(S * L * C, dtype=torch.float64).pin_memory() for _ in range(n_host - 1)]
+    np_in, np_outs = [h.numpy() for h in host_ins], [h.numpy() for h in host_outs]
     sampler.busy.set()
-    t_sync, t_e2e, e2e_groups = e2e_pass(eng, np_in, np_outs, e2e_steps, 4, 4)
+    t_sync, t_pairs, t_single, e2e_groups = e2e_pass(eng, np_in, np_outs, e2e_steps, 4, 4)
     sampler.busy.clear()
+    t_e2e = t_pairs[1]
     e2e_value = n_gpus * Ct * L * e2e_steps / t_e2e / 1e6
     e2e_sync_value = n_gpus * Ct * L * e2e_steps / t_sync / 1e6
+    e2e_single_value = n_gpus * Ct * L * e2e_steps / t_single / 1e6
     checksum = float(host_out.numpy()[:1024].sum())
 
     # ---- the same end-to-end step with the product's I/O format: foo_dsp_bfir constructs the engine with REALSIZE 8
@@ -329,12 +371,13 @@ def main():
         e32 = pkg.Brutefir(L, P, rs, C, 8, 8, rate, False, n_streams=S, device=local_rank, n_groups=min(4, S))
         e32.set_stream(stream.cuda_stream)
         assert e32.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
-        n32 = [h.float().pin_memory().numpy() for h in host_in]
-        no32 = [torch.empty(S * L * C, dtype=torch.float32).pin_memory().numpy() for _ in range(DEPTH + 1)]
+        n32 = [h.float().pin_memory().numpy() for h in host_ins]
+        no32 = [torch.empty(S * L * C, dtype=torch.float32).pin_memory().numpy() for _ in range(n_host)]
         for b in range(P):
             e32.run(n32[b % ring], no32[0])
-        ts32, ta32, _ = e2e_pass(e32, n32, no32, e2e_steps, 4, 4)
-        e2e_f32 = {"value": Ct * L * e2e_steps / ta32 / 1e6, "unit": "Msamples/s (this rank only)", "ms_per_step": 1e3 * ta32 / e2e_steps,
+        ts32, tp32, t1_32, _ = e2e_pass(e32, n32, no32, e2e_steps, 4, 4)
+        e2e_f32 = {"value": Ct * L * e2e_steps / tp32[1] / 1e6, "unit": "Msamples/s (this rank only)", "ms_per_step": 1e3 * tp32[1] / e2e_steps,
+                   "one_block_per_call": {"value": Ct * L * e2e_steps / t1_32 / 1e6, "ms_per_step": 1e3 * t1_32 / e2e_steps},
                    "sync_run": {"value": Ct * L * e2e_steps / ts32 / 1e6, "ms_per_step": 1e3 * ts32 / e2e_steps},
                    "h2d_bytes_per_step": S * L * C * 4, "d2h_bytes_per_step": S * L * C * 4,
                    "note": "FLOAT_LE in/out around the double-precision engine, as the plug-in runs it"}
@@ -346,18 +389,32 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    b_mac = (2 * P + 1) * (2 * L) * rs * Ct            # algorithmic bytes per launch
-    mac_ms = prof["mac_ms"] / max(nprof, 1)
-    achieved = b_mac / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    b_mac = (2 * P + 1) * (2 * L) * rs * Ct            # algorithmic bytes per channel-block x channels
+    npairs = max(nprof, 1)
+    mac_ms = prof["mac_ms"] / npairs                    # one pair launch = two blocks of every channel
+    algorithmic = 2 * b_mac
+    actual = (2 * P + mac_split + 2) * (2 * L) * rs * Ct   # what the pair kernel has to move: H once, X once per slice run, two outputs
+    achieved = algorithmic / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
     traffic, traffic_src = None, None       # DRAM read+write bytes per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
     if os.path.exists(tpath) and S == 16:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+    mac1_ms = prof_single["mac_ms"] / max(nprof_single, 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "partition_mac_kernel<double,SPLIT=4,UNROLL=4>", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_mac, "avg_launch_ms": mac_ms,
-                "step_share": {k: v / max(nprof, 1) for k, v in prof.items()}}
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "partition_mac_pair_kernel<double,SPLIT=%d,UNROLL=2>" % mac_split, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algorithmic, "avg_launch_ms": mac_ms,
+                "note": "algorithmic bytes = SURVEY 8d's (2P+1)*N*realsize per channel-block x 2 blocks x %d channels per launch; the pair kernel "
+                        "reads each coefficient spectrum once for both blocks, so it needs to move only bytes_needed_per_launch: frac > 1 is that reuse, "
+                        "frac_of_bytes_needed is the kernel against the HBM roofline" % Ct,
+                "bytes_needed_per_launch": actual, "frac_of_bytes_needed": actual / (mac_ms * 1e-3) / 1e9 / peak if mac_ms > 0 else 0.0,
+                "step_share": {k: v / npairs / 2 for k, v in prof.items()},
+                "one_block_per_launch": {"kernel": "partition_mac_kernel<double,SPLIT=%d,UNROLL=4>" % mac_split, "avg_launch_ms": mac1_ms,
+                                         "algorithmic_bytes_per_launch": b_mac,
+                                         "frac": b_mac / (mac1_ms * 1e-3) / 1e9 / peak if mac1_ms > 0 else 0.0,
+                                         "value": n_gpus * Ct * L * K / (ms_single * 1e-3) / 1e6, "ms_per_step": ms_single / K,
+                                         "step_share": {k: v / max(nprof_single, 1) for k, v in prof_single.items()}}}
 
     # ---- single-stream block latency (p50/p99 of host-visible bfir_run), rank 0
     latency = None
@@ -410,8 +467,10 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(S, n_gpus),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * L * C * 8,
                     "d2h_bytes_per_step": S * L * C * 8, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "bfir_run_async(pinned host in, pinned host out) + bfir_wait: H2D + kernels + D2H of every block, "
-                           "%d blocks in flight, %d stream groups with their own copy streams" % (DEPTH, e2e_groups),
+                    "api": "bfir_run_async_pair(pinned host in x2, pinned host out x2) + bfir_wait: H2D + kernels + D2H of every block, "
+                           "%d calls in flight, %d stream groups with their own copy streams; median of 3 passes" % (DEPTH, e2e_groups),
+                    "passes_ms_per_step": [1e3 * t / e2e_steps for t in t_pairs],
+                    "one_block_per_call": {"value": e2e_single_value, "ms_per_step": 1e3 * t_single / e2e_steps, "api": "bfir_run_async + bfir_wait"},
                     "sync_run": {"value": e2e_sync_value, "ms_per_step": 1e3 * t_sync / e2e_steps,
                                  "api": "bfir_run(host in, host out): the reference's synchronous run(), 4 stream groups"},
                     "checksum": checksum},

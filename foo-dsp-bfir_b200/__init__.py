@@ -70,6 +70,8 @@ API = [
     ("bfir_run_async", ctypes.c_longlong, [_vp, _vp, _vp]),
     ("bfir_run_device_pipelined", _ci, [_vp, _vp, _vp]),
     ("bfir_join", _ci, [_vp]),
+    ("bfir_run_device_pair", _ci, [_vp, _vp, _vp, _vp, _vp, _ci]),
+    ("bfir_run_async_pair", ctypes.c_longlong, [_vp, _vp, _vp, _vp, _vp]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -88,6 +90,7 @@ API = [
     ("bfir_peer_own_channels", _ci, [_vp, ctypes.POINTER(_ci), ctypes.POINTER(_ci)]),
     ("bfir_set_groups", _ci, [_vp, _ci]),
     ("bfir_get_groups", _ci, [_vp]),
+    ("bfir_get_mac_split", _ci, [_vp]),
     ("bfir_set_stream", _ci, [_vp, _vp]),
     ("bfir_set_profiling", _ci, [_vp, _ci]),
     ("bfir_get_profile", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(ctypes.c_ulonglong), _ci]),
@@ -296,6 +299,17 @@ class Brutefir:
     def join(self):
         _check(self.lib.bfir_join(self.h))
 
+    def run_device_pair(self, d_in0, d_in1, d_out0, d_out1, pipelined=False):
+        """Two consecutive blocks with one partition-sum launch (offline / pipelined callers)."""
+        _check(self.lib.bfir_run_device_pair(self.h, _ptr(d_in0), _ptr(d_in1), _ptr(d_out0), _ptr(d_out1), int(bool(pipelined))))
+
+    def run_async_pair(self, in0, in1, out0, out1):
+        """Two consecutive blocks of PINNED host buffers; returns the ticket of the second block."""
+        t = self.lib.bfir_run_async_pair(self.h, _ptr(in0), _ptr(in1), _ptr(out0), _ptr(out1))
+        if t < 0:
+            raise BfirError(int(t), last_error())
+        return t
+
     def run_async(self, inbuf, outbuf):
         """Queue one block on PINNED host buffers; returns a ticket for wait(). Buffers stay untouched until then."""
         t = self.lib.bfir_run_async(self.h, _ptr(inbuf), _ptr(outbuf))
@@ -355,6 +369,9 @@ class Brutefir:
 
     def get_groups(self):
         return _check(self.lib.bfir_get_groups(self.h))
+
+    def get_mac_split(self):
+        return _check(self.lib.bfir_get_mac_split(self.h))
 
     def set_stream(self, cuda_stream):
         _check(self.lib.bfir_set_stream(self.h, ctypes.c_void_p(cuda_stream)))

@@ -16,6 +16,7 @@ namespace bfir {
 struct Engine {
     bfir_config_t cfg;
     int L = 0, N = 0, P = 0, C = 0, S = 0, Ct = 0, rs = 0, log2m = 0;
+    int Pslots = 0;                 // delay-line slots per channel, P + 1 (see init)
     // crossbar: Ci inputs and Co outputs per stream around the C filters (== C without a crossbar)
     int Ci = 0, Co = 0, Cit = 0, Cot = 0;
     bool xbar = false, xbar_set = false;
@@ -47,7 +48,8 @@ struct Engine {
         cudaStream_t stream; cudaEvent_t done;
         // bfir_run_async: the group's copies ride on their own streams so that they overlap its kernels too
         cudaStream_t h2d, d2h;
-        cudaEvent_t in_ready, in_free, out_ready, out_free, copies_done;
+        cudaEvent_t in_ready, out_ready, copies_done;
+        cudaEvent_t in_free[4], out_free[4];   // per staging slot (kStage)
     };
     Group groups[BFIR_MAX_GROUPS] = {};
     int n_groups = 1;
@@ -98,6 +100,27 @@ struct Engine {
     int close_async();
     long long run_host_async(const void *inbuf, void *outbuf);
     int wait_ticket(long long t);
+    // two blocks per call (bfir_run_device_pair / bfir_run_async_pair): both forward transforms, ONE partition-sum
+    // launch that reads every coefficient spectrum once for both blocks, both inverse transforms
+    void *acc_pair = nullptr;       // accumulated spectra of the second block, [Ct][N]
+    // bfir_run_async: ring of staging buffers for the raw blocks (slot 0 = d_in / d_out), so that the input copies can
+    // run up to kStage - 1 blocks ahead of the transforms and the output copies behind them
+    static const int kStage = 4;
+    void *stage_in[kStage] = {}, *stage_out[kStage] = {};
+    unsigned long long stage_next = 0;
+    int stage_count = kStage;       // slots in use (BFIR_STAGE = 1 .. 4, measurement)
+    int open_async_copies();
+    int stage_alloc(int k);
+    int fwd_block_offset = 0;       // front_group: 1 while the second block of a pair is transformed
+    const void *acc_override = nullptr; // back_group: accumulated spectra to emit instead of acc
+    bool pair_ok() const
+    {
+        return !xbar && !peer.enabled && part_begin == 0 && part_count == P && P >= 2 && !xfade_pending &&
+               host_blockcounter >= (unsigned int)P;
+    }
+    int pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, cudaEvent_t *input_consumed, cudaEvent_t *output_free);
+    int enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined);
+    long long run_host_async_pair(const void *in0, const void *in1, void *out0, void *out1);
     int mac_split = 1;              // partition slices per CTA of the MAC kernel
     int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
     // optional per-kernel timing (bfir_set_profiling)
@@ -105,7 +128,8 @@ struct Engine {
     size_t pcap = 0, pidx = 0;
     double pms[3] = {0, 0, 0};
     unsigned long long pblocks = 0;
-    void prof(int k) { if (pidx < pcap) cudaEventRecord(pev[4 * pidx + k], stream); }
+    bool prof_suppress = false;     // pair_group times the pair as a whole and silences the per-block marks inside it
+    void prof(int k) { if (pidx < pcap && !prof_suppress) cudaEventRecord(pev[4 * pidx + k], stream); }
     void prof_collect();
     void prof_free() { for (auto ev : pev) cudaEventDestroy(ev); pev.clear(); pcap = pidx = 0; }
 
@@ -144,6 +168,7 @@ int Engine::init(const bfir_config_t &c)
     if (P < 1 || C < 1) { set_error("No channels defined."); return BFIR_ERR_INVALID; }            // brutefir.cpp:745-749
     if ((long long)C * S > 0x7fffffffLL / 2) return BFIR_ERR_INVALID;
     Ct = C * S;
+    Pslots = P + 1;
     xbar = c.xbar_inputs > 0 || c.xbar_outputs > 0;
     Ci = c.xbar_inputs > 0 ? c.xbar_inputs : C;
     Co = c.xbar_outputs > 0 ? c.xbar_outputs : C;
@@ -165,10 +190,12 @@ int Engine::init(const bfir_config_t &c)
     own_stream = true;
 
     const size_t cbuf = (size_t)N * rs;
-    // the delay line only has to hold the slots this engine's partitions read: all P (the slot index
-    // is blockcounter % P like the reference, brutefir.cpp:270,294)
-    BFIR_CUDA(cudaMalloc(&fdl, cbuf * P * Ct));
-    BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * P * Ct, stream));                                      // brutefir.cpp:768-769
+    // The reference's delay line has P slots, slot = blockcounter % P (brutefir.cpp:270,294). Here it has P + 1:
+    // the spectrum of block t+1 may then be written while block t's partition sum still needs X[t-P+1] (block
+    // pairs, look-ahead across blocks). Which slot a block lands in is not observable -- partition i is only
+    // read once procblocks says the slot has been written since the last reset.
+    BFIR_CUDA(cudaMalloc(&fdl, cbuf * Pslots * Ct));
+    BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * Pslots * Ct, stream));                                      // brutefir.cpp:768-769
     BFIR_CUDA(cudaMalloc(&acc, cbuf * Ct));
     BFIR_CUDA(cudaMemsetAsync(acc, 0, cbuf * Ct, stream));
     BFIR_CUDA(cudaMalloc(&prev, (size_t)2 * L * rs * Cit));                                         // input_timecbuf[n][2]
@@ -182,6 +209,7 @@ int Engine::init(const bfir_config_t &c)
     fft_r0 = rfft_choose_r0(rs, log2m, Ct);
     if (const char *env = getenv("BFIR_GRAPHS")) graphs_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_LOOKAHEAD")) lookahead_enabled = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
     BFIR_CUDA(cudaStreamCreateWithFlags(&tail_stream, cudaStreamNonBlocking));
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) BFIR_CUDA(cudaEventCreateWithFlags(&tail_done[g], cudaEventDisableTiming));
@@ -207,8 +235,12 @@ int Engine::init(const bfir_config_t &c)
         BFIR_CUDA(cudaEventCreateWithFlags(&groups[g].done, cudaEventDisableTiming));
         BFIR_CUDA(cudaStreamCreateWithFlags(&groups[g].h2d, cudaStreamNonBlocking));
         BFIR_CUDA(cudaStreamCreateWithFlags(&groups[g].d2h, cudaStreamNonBlocking));
-        for (cudaEvent_t *ev : { &groups[g].in_ready, &groups[g].in_free, &groups[g].out_ready, &groups[g].out_free, &groups[g].copies_done })
+        for (cudaEvent_t *ev : { &groups[g].in_ready, &groups[g].out_ready, &groups[g].copies_done })
             BFIR_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        for (int k = 0; k < kStage; k++) {
+            BFIR_CUDA(cudaEventCreateWithFlags(&groups[g].in_free[k], cudaEventDisableTiming));
+            BFIR_CUDA(cudaEventCreateWithFlags(&groups[g].out_free[k], cudaEventDisableTiming));
+        }
     }
     BFIR_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
     int rc = make_twiddles(rs, N, &tw);
@@ -272,8 +304,10 @@ void Engine::destroy()
         if (groups[g].stream) { cudaStreamSynchronize(groups[g].stream); cudaStreamDestroy(groups[g].stream); groups[g].stream = nullptr; }
         if (groups[g].done) { cudaEventDestroy(groups[g].done); groups[g].done = nullptr; }
         for (cudaStream_t *st : { &groups[g].h2d, &groups[g].d2h }) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
-        for (cudaEvent_t *ev : { &groups[g].in_ready, &groups[g].in_free, &groups[g].out_ready, &groups[g].out_free, &groups[g].copies_done })
+        for (cudaEvent_t *ev : { &groups[g].in_ready, &groups[g].out_ready, &groups[g].copies_done })
             if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
+        for (int k = 0; k < kStage; k++)
+            for (cudaEvent_t *ev : { &groups[g].in_free[k], &groups[g].out_free[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
     }
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
     if (out_done) { cudaEventDestroy(out_done); out_done = nullptr; }
@@ -286,8 +320,11 @@ void Engine::destroy()
     stream = nullptr;
     for (int q = 0; q < BFIR_MAX_PEERS; q++) if (peer_opened[q]) { cudaIpcCloseMemHandle(peer_opened[q]); peer_opened[q] = nullptr; }
     if (recv) { cudaFree(recv); recv = nullptr; }
-    void *bufs[] = { fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
+    for (int k = 1; k < kStage; k++) { if (stage_in[k]) cudaFree(stage_in[k]); if (stage_out[k]) cudaFree(stage_out[k]); stage_in[k] = stage_out[k] = nullptr; }
+    stage_in[0] = stage_out[0] = nullptr;
+    void *bufs[] = { acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
+    acc_pair = nullptr;
     fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
     state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
@@ -500,8 +537,8 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
     f.in = d_inbuf; f.in_stride_x = (long long)L * Ci * in_sf.bytes;  // bytes per stream
     f.scale_in = 1.0; f.scale_out = in_sf.scale;                       // brutefir.cpp:273-277
     f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = Ci; f.n_channels = Cit; f.ch_base = s0 * Ci;
-    f.state = state + g; f.n_slots = P; f.prev_parity = host_blockcounter & 1u;
-    if (!xbar) { f.out = fdl; f.out_stride_x = (long long)P * N; f.out_stride_y = N; f.procblocks = procblocks; f.pb_inc = pb_inc; }
+    f.state = state + g; f.n_slots = Pslots; f.n_parts = P; f.prev_parity = (host_blockcounter + (unsigned int)fwd_block_offset) & 1u; f.slot_offset = fwd_block_offset;
+    if (!xbar) { f.out = fdl; f.out_stride_x = (long long)Pslots * N; f.out_stride_y = N; f.procblocks = procblocks; f.pb_inc = pb_inc; }
     else { f.out = xin; f.out_stride_x = N; f.out_stride_y = 0; f.procblocks = nullptr; f.pb_inc = nullptr; }
     if (g == 0) prof(0);
     cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(ns * Ci, 1), st, f, tw);
@@ -510,9 +547,9 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
     if (input_consumed) BFIR_CUDA(cudaEventRecord(*input_consumed, st));   // the raw input block has been read
     if (xbar) { // inputs -> filter inputs, straight into the delay-line slot (mixnscale INPUT, n_bufs = Ci)
         XbarArgs x = {};
-        x.in = xin; x.in_stride = N; x.out = fdl; x.out_stride = (long long)P * N; x.slot_stride = N;
+        x.in = xin; x.in_stride = N; x.out = fdl; x.out_stride = (long long)Pslots * N; x.slot_stride = N;
         x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = ns; x.stream_base = s0;
-        x.state = state + g; x.n_slots = P; x.procblocks = procblocks; x.pb_inc = pb_inc;
+        x.state = state + g; x.n_slots = Pslots; x.n_parts = P; x.procblocks = procblocks; x.pb_inc = pb_inc;
         xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
         xk<<<dim3((N + 255) / 256, ns), 256, (size_t)C * Ci * rs, st>>>(x);
         count_launch();
@@ -524,8 +561,8 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
 
     MacArgs m = {};
     m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
-    m.fdl_stride_ch = (long long)P * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
-    m.N = N; m.n_slots = P; m.part_begin = part_begin; m.part_count = part_count;
+    m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = part_begin; m.part_count = part_count;
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = c0;
     if (peer.enabled && !xbar) m.push = peer;
     dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), nch);
@@ -543,7 +580,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
         XbarArgs x = {};
         x.in = acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
         x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = ns; x.stream_base = s0;
-        x.state = nullptr; x.n_slots = P; x.push = peer; x.push_state = state + g;
+        x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.push = peer; x.push_state = state + g;
         xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
         xk<<<dim3((N + 255) / 256, ns), 256, (size_t)Co * C * rs, st>>>(x);
         count_launch();
@@ -581,7 +618,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
         XbarArgs x = {};
         x.in = acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
         x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = ns; x.stream_base = s0;
-        x.state = nullptr; x.n_slots = P; x.procblocks = nullptr; x.pb_inc = nullptr;
+        x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.procblocks = nullptr; x.pb_inc = nullptr;
         xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
         xk<<<dim3((N + 255) / 256, ns), 256, (size_t)Co * C * rs, st>>>(x);
         count_launch();
@@ -608,13 +645,13 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
         BFIR_CUDA(cudaGetLastError());
     }
     InvArgs v = {};
-    v.in_layout = LAYOUT_ORD; v.in = xbar ? yacc : acc; v.in_stride_x = N;
+    v.in_layout = LAYOUT_ORD; v.in = acc_override ? acc_override : (xbar ? yacc : acc); v.in_stride_x = N;
     v.scale_in = out_sf.scale;                                         // brutefir.cpp:303-307
     v.fmt = out_sf.format; v.ch_per_stream = Co; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.ch_base = c0; v.host_flag = d_flag;
     if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }
     else { v.out_mode = OUT_RAW; v.out = d_outbuf; v.out_stride_x = (long long)L * Co * out_sf.bytes; }
     if (head) {
-        v.head_x = fdl; v.head_x_stride = (long long)P * N;
+        v.head_x = fdl; v.head_x_stride = (long long)Pslots * N;
         v.head_h = coeffs; v.head_h_stride = (long long)coeff_alloc * N;
         v.head_blocks = coeff_blocks;
     }
@@ -635,7 +672,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
         count_launch();
         BFIR_CUDA(cudaGetLastError());
     }
-    if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+    if (g == 0 && !prof_suppress) { prof(3); if (pidx < pcap) pidx++; }
     return BFIR_OK;
 }
 
@@ -647,8 +684,8 @@ int Engine::tail_group(int g, cudaStream_t st)
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
     MacArgs m = {};
     m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
-    m.fdl_stride_ch = (long long)P * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
-    m.N = N; m.n_slots = P; m.part_begin = 1; m.part_count = P - 1;
+    m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 1; m.part_count = P - 1;
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
     m.procblocks_bias = 1;
     dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), ns * C);
@@ -657,6 +694,69 @@ int Engine::tail_group(int g, cudaStream_t st)
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     return BFIR_OK;
+}
+
+// both blocks of a pair for the channels of one group: forward t, forward t+1, ONE partition sum for both,
+// inverse t, inverse t+1 (each inverse advances the block counter)
+int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, cudaEvent_t *input_consumed, cudaEvent_t *output_free)
+{
+    const Group &grp = groups[g];
+    const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
+    // profiling (bfir_set_profiling): one entry per PAIR -- both forward transforms, the pair sum, both inverse transforms
+    if (g == 0) prof(0);
+    prof_suppress = true;
+    int rc = front_group(g, d_in0, nullptr, true);
+    fwd_block_offset = 1;
+    if (rc == BFIR_OK) rc = front_group(g, d_in1, input_consumed, true);
+    fwd_block_offset = 0;
+    prof_suppress = false;
+    if (rc != BFIR_OK) return rc;
+    if (g == 0) prof(1);
+    tail_ready = false;
+    MacArgs m = {};
+    m.fdl = fdl; m.coeffs = coeffs; m.acc = acc; m.acc_next = acc_pair;
+    m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
+    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
+    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), ns * C);
+    mac_kernel_t mk = rs == 4 ? mac_pair_kernel_for_split<float>(mac_split) : mac_pair_kernel_for_split<double>(mac_split);
+    mk<<<grid, 256, 0, gstream(g)>>>(m);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    if (g == 0) prof(2);
+    if (output_free) BFIR_CUDA(cudaStreamWaitEvent(gstream(g), *output_free, 0));   // the staging slices have been copied out
+    prof_suppress = true;
+    rc = back_group(g, d_out0);
+    acc_override = acc_pair;
+    if (rc == BFIR_OK) rc = back_group(g, d_out1);
+    acc_override = nullptr;
+    prof_suppress = false;
+    if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+    return rc;
+}
+
+// two consecutive blocks on device buffers. Falls back to two single-block steps while the delay line is still
+// filling, with a crossbar / partition shard / pending filter swap / dither / profiling.
+int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined)
+{
+    int rc;
+    if (!pair_ok()) {
+        rc = pipelined ? enqueue_block_pipelined(d_in0, d_out0) : enqueue_block(d_in0, d_out0);
+        if (rc == BFIR_OK) rc = pipelined ? enqueue_block_pipelined(d_in1, d_out1) : enqueue_block(d_in1, d_out1);
+        return rc;
+    }
+    if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, (size_t)N * rs * Ct));
+    if (!pipelined) { if ((rc = close_async()) != BFIR_OK) return rc; }
+    if (!async_open) {
+        if ((rc = join_tail()) != BFIR_OK || (rc = fork()) != BFIR_OK) return rc;
+        if (pipelined) async_open = n_groups > 1;
+    }
+    rc = BFIR_OK;
+    for (int g = 0; g < n_groups && rc == BFIR_OK; g++) rc = pair_group(g, d_in0, d_in1, d_out0, d_out1, nullptr, nullptr);
+    finish_block();
+    finish_block();
+    if (rc == BFIR_OK && !pipelined) rc = join();
+    return rc;
 }
 
 int Engine::enqueue_front(const void *d_inbuf)
@@ -809,50 +909,117 @@ int Engine::close_async()
     return join();
 }
 
+int Engine::stage_alloc(int k)
+{
+    if (k == 0) { stage_in[0] = d_in; stage_out[0] = d_out; return BFIR_OK; }
+    if (!stage_in[k]) BFIR_CUDA(cudaMalloc(&stage_in[k], in_bytes));
+    if (!stage_out[k]) BFIR_CUDA(cudaMalloc(&stage_out[k], out_bytes));
+    return BFIR_OK;
+}
+
+// all streams of the pipelined host path start after everything queued on the engine's stream so far
+int Engine::open_async_copies()
+{
+    if (async_open && async_copies) return BFIR_OK;
+    int rc = close_async();
+    if (rc != BFIR_OK) return rc;
+    for (int k = 0; k < kStage; k++) if ((rc = stage_alloc(k)) != BFIR_OK) return rc;
+    BFIR_CUDA(cudaEventRecord(fork_ev, stream));
+    for (int g = 0; g < n_groups; g++) {
+        if (n_groups > 1) BFIR_CUDA(cudaStreamWaitEvent(groups[g].stream, fork_ev, 0));
+        BFIR_CUDA(cudaStreamWaitEvent(groups[g].h2d, fork_ev, 0));
+        BFIR_CUDA(cudaStreamWaitEvent(groups[g].d2h, fork_ev, 0));
+        for (int k = 0; k < kStage; k++) {
+            BFIR_CUDA(cudaEventRecord(groups[g].in_free[k], gstream(g)));
+            BFIR_CUDA(cudaEventRecord(groups[g].out_free[k], groups[g].d2h));
+        }
+    }
+    async_open = async_copies = true;
+    return BFIR_OK;
+}
+
 // queue H2D -> block step -> D2H of one block and return its ticket (or an error code < 0). Per group three
-// streams: input copies, kernels, output copies, chained by events --
-//   H2D(t) after fwd(t-1) has consumed the staging slice;  fwd(t) after H2D(t);
-//   inv(t) after D2H(t-1) has drained the output slice;     D2H(t) after inv(t)
-// so a group's copies overlap its own kernels as well as everybody else's.
+// streams: input copies, kernels, output copies, chained by events over a ring of kStage staging slots --
+//   H2D(t) after the forward transform that last read slot t % kStage;  forward(t) after H2D(t);
+//   inverse(t) after the D2H that last drained slot t % kStage;         D2H(t) after inverse(t)
+// so a group's copies overlap its own kernels as well as everybody else's, and run ahead of / behind them.
 long long Engine::run_host_async(const void *inbuf, void *outbuf)
 {
     int rc;
-    if (!async_open || !async_copies) { // all streams start after everything queued on the engine's stream so far
-        if ((rc = close_async()) != BFIR_OK) return rc;
-        BFIR_CUDA(cudaEventRecord(fork_ev, stream));
-        for (int g = 0; g < n_groups; g++) {
-            if (n_groups > 1) BFIR_CUDA(cudaStreamWaitEvent(groups[g].stream, fork_ev, 0));
-            BFIR_CUDA(cudaStreamWaitEvent(groups[g].h2d, fork_ev, 0));
-            BFIR_CUDA(cudaStreamWaitEvent(groups[g].d2h, fork_ev, 0));
-            BFIR_CUDA(cudaEventRecord(groups[g].in_free, gstream(g)));
-            BFIR_CUDA(cudaEventRecord(groups[g].out_free, groups[g].d2h));
-        }
-        async_open = async_copies = true;
-    }
+    if ((rc = open_async_copies()) != BFIR_OK) return rc;
     if (next_ticket - done_ticket >= kMaxInflight && (rc = wait_ticket(next_ticket - kMaxInflight)) != BFIR_OK) return rc;
     const int slot = (int)(next_ticket % kMaxInflight);
+    const int k = (int)(stage_next++ % (unsigned long long)stage_count);
     for (int g = 0; g < n_groups; g++) {
         Group &grp = groups[g];
         const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
         const size_t ioff = s0 * L * Ci * in_sf.bytes, ibytes = ns * L * Ci * in_sf.bytes;
         const size_t ooff = s0 * L * Co * out_sf.bytes, obytes = ns * L * Co * out_sf.bytes;
         cudaStream_t st = gstream(g);
-        BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, grp.in_free, 0));
-        BFIR_CUDA(cudaMemcpyAsync((char *)d_in + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, grp.h2d));
+        BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, grp.in_free[k], 0));
+        BFIR_CUDA(cudaMemcpyAsync((char *)stage_in[k] + ioff, (const char *)inbuf + ioff, ibytes, cudaMemcpyHostToDevice, grp.h2d));
         BFIR_CUDA(cudaEventRecord(grp.in_ready, grp.h2d));
         BFIR_CUDA(cudaStreamWaitEvent(st, grp.in_ready, 0));
-        if ((rc = front_group(g, d_in, &grp.in_free)) != BFIR_OK) return rc;
-        BFIR_CUDA(cudaStreamWaitEvent(st, grp.out_free, 0));
-        if ((rc = back_group(g, d_out)) != BFIR_OK) return rc;
+        if ((rc = front_group(g, stage_in[k], &grp.in_free[k])) != BFIR_OK) return rc;
+        BFIR_CUDA(cudaStreamWaitEvent(st, grp.out_free[k], 0));
+        if ((rc = back_group(g, stage_out[k])) != BFIR_OK) return rc;
         BFIR_CUDA(cudaEventRecord(grp.out_ready, st));
         BFIR_CUDA(cudaStreamWaitEvent(grp.d2h, grp.out_ready, 0));
-        BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)d_out + ooff, obytes, cudaMemcpyDeviceToHost, grp.d2h));
-        BFIR_CUDA(cudaEventRecord(grp.out_free, grp.d2h));
+        BFIR_CUDA(cudaMemcpyAsync((char *)outbuf + ooff, (const char *)stage_out[k] + ooff, obytes, cudaMemcpyDeviceToHost, grp.d2h));
+        BFIR_CUDA(cudaEventRecord(grp.out_free[k], grp.d2h));
         if (ticket_ev[slot][g] == nullptr) BFIR_CUDA(cudaEventCreateWithFlags(&ticket_ev[slot][g], cudaEventDisableTiming));
         BFIR_CUDA(cudaEventRecord(ticket_ev[slot][g], grp.d2h));
     }
     finish_block();
     return next_ticket++;
+}
+
+// two consecutive blocks of host buffers per call (see pair_group); returns the ticket of the second block
+long long Engine::run_host_async_pair(const void *in0, const void *in1, void *out0, void *out1)
+{
+    int rc;
+    if (!pair_ok()) {
+        const long long t0 = run_host_async(in0, out0);
+        if (t0 < 0) return t0;
+        return run_host_async(in1, out1);
+    }
+    if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, (size_t)N * rs * Ct));
+    if ((rc = open_async_copies()) != BFIR_OK) return rc;
+    if (next_ticket + 1 - done_ticket >= kMaxInflight && (rc = wait_ticket(next_ticket + 1 - kMaxInflight)) != BFIR_OK) return rc;
+    const int slot0 = (int)(next_ticket % kMaxInflight), slot1 = (int)((next_ticket + 1) % kMaxInflight);
+    const int sc = stage_count >= 2 ? (stage_count & ~1) : 2;   // pairs need an even number of slots, at least two
+    const int k0 = (int)(stage_next % (unsigned long long)sc), k1 = (int)((stage_next + 1) % (unsigned long long)sc);
+    stage_next += 2;
+    for (int g = 0; g < n_groups; g++) {
+        Group &grp = groups[g];
+        const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
+        const size_t ioff = s0 * L * Ci * in_sf.bytes, ibytes = ns * L * Ci * in_sf.bytes;
+        const size_t ooff = s0 * L * Co * out_sf.bytes, obytes = ns * L * Co * out_sf.bytes;
+        cudaStream_t st = gstream(g);
+        BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, grp.in_free[k0], 0));
+        BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, grp.in_free[k1], 0));
+        BFIR_CUDA(cudaMemcpyAsync((char *)stage_in[k0] + ioff, (const char *)in0 + ioff, ibytes, cudaMemcpyHostToDevice, grp.h2d));
+        BFIR_CUDA(cudaMemcpyAsync((char *)stage_in[k1] + ioff, (const char *)in1 + ioff, ibytes, cudaMemcpyHostToDevice, grp.h2d));
+        BFIR_CUDA(cudaEventRecord(grp.in_ready, grp.h2d));
+        BFIR_CUDA(cudaStreamWaitEvent(st, grp.in_ready, 0));
+        BFIR_CUDA(cudaStreamWaitEvent(st, grp.out_free[k0], 0));   // (long done: these slots were drained kStage blocks ago)
+        if ((rc = pair_group(g, stage_in[k0], stage_in[k1], stage_out[k0], stage_out[k1], &grp.in_free[k1], &grp.out_free[k1])) != BFIR_OK) return rc;
+        BFIR_CUDA(cudaEventRecord(grp.in_free[k0], st));
+        BFIR_CUDA(cudaEventRecord(grp.out_ready, st));
+        BFIR_CUDA(cudaStreamWaitEvent(grp.d2h, grp.out_ready, 0));
+        BFIR_CUDA(cudaMemcpyAsync((char *)out0 + ooff, (const char *)stage_out[k0] + ooff, obytes, cudaMemcpyDeviceToHost, grp.d2h));
+        BFIR_CUDA(cudaEventRecord(grp.out_free[k0], grp.d2h));
+        BFIR_CUDA(cudaMemcpyAsync((char *)out1 + ooff, (const char *)stage_out[k1] + ooff, obytes, cudaMemcpyDeviceToHost, grp.d2h));
+        BFIR_CUDA(cudaEventRecord(grp.out_free[k1], grp.d2h));
+        for (int slot : { slot0, slot1 }) {
+            if (ticket_ev[slot][g] == nullptr) BFIR_CUDA(cudaEventCreateWithFlags(&ticket_ev[slot][g], cudaEventDisableTiming));
+            BFIR_CUDA(cudaEventRecord(ticket_ev[slot][g], grp.d2h));
+        }
+    }
+    finish_block();
+    finish_block();
+    next_ticket += 2;
+    return next_ticket - 1;
 }
 
 // returns when the step with ticket t (and every earlier one) has delivered its output block
@@ -1025,6 +1192,23 @@ int bfir_run_device_pipelined(bfir_engine *e, const void *d_inbuf, void *d_outbu
     if (rc != BFIR_OK) return rc;
     if (e->impl.peer.enabled) { bfir::set_error("bfir_run_device_pipelined is not available on a partition shard"); return BFIR_ERR_INVALID; }
     return e->impl.enqueue_block_pipelined(d_inbuf, d_outbuf);
+}
+
+int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, int pipelined)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_in0 == nullptr || d_in1 == nullptr || d_out0 == nullptr || d_out1 == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.enqueue_pair(d_in0, d_in1, d_out0, d_out1, pipelined != 0);
+}
+
+long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, void *out0, void *out1)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (in0 == nullptr || in1 == nullptr || out0 == nullptr || out1 == nullptr) return BFIR_ERR_INVALID;
+    if (e->impl.peer.enabled) { bfir::set_error("bfir_run_async_pair is not available on a partition shard"); return BFIR_ERR_INVALID; }
+    return e->impl.run_host_async_pair(in0, in1, out0, out1);
 }
 
 int bfir_join(bfir_engine *e)
@@ -1207,6 +1391,7 @@ int bfir_set_groups(bfir_engine *e, int n_groups)
 }
 
 int bfir_get_groups(bfir_engine *e) { return e ? e->impl.n_groups : BFIR_ERR_INVALID; }
+int bfir_get_mac_split(bfir_engine *e) { return e ? e->impl.mac_split : BFIR_ERR_INVALID; }
 
 int bfir_set_stream(bfir_engine *e, void *cuda_stream)
 {

@@ -21,13 +21,15 @@ struct MacArgs {
     void *acc;               // [channels][N]
     long long fdl_stride_ch, coeff_stride_ch; // elements
     int N;
-    int n_slots;             // filter_blocks of the engine
+    int n_slots;             // delay-line slots per channel (filter_blocks + 1 in the engine)
+    int n_parts;             // filter_blocks
     int part_begin, part_count; // partition shard convolved by this launch (whole filter: 0, n_slots)
     const int *coeff_blocks; // [channels] coefficient partitions actually loaded
     const int *procblocks;   // [channels] blocks seen so far, already counting the current one
     const EngineState *state;
     int block_offset;        // 0: blockcounter is the current block; used by tests
     int ch_base;             // first channel of this launch (channel-group pipelining)
+    void *acc_next;          // pair kernel: accumulated spectrum of block t+1, [channels][N]
     int procblocks_bias;     // 1: look-ahead launch for the NEXT block, whose forward transform has not counted itself yet
     PeerPush push;           // enabled: partial sums go to the owner rank's receive buffer (fused reduce)
 };
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
     const int ch = blockIdx.y + a.ch_base;
     const bool active = g * 8 < a.N;
     const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
-    const int peff = min(a.coeff_blocks[ch], min(a.procblocks[ch] + a.procblocks_bias, a.n_slots)); // brutefir.cpp:292, 265-268
+    const int peff = min(a.coeff_blocks[ch], min(a.procblocks[ch] + a.procblocks_bias, a.n_parts)); // brutefir.cpp:292, 265-268
     const int i_end = min(peff, a.part_begin + a.part_count);
     const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
     const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
@@ -142,7 +144,108 @@ __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
     }
 }
 
+// Two consecutive blocks t, t+1 in one pass (offline / pipelined callers that have the next block at hand; steady
+// state only: every channel has seen at least n_slots blocks, so P_eff = coeff_blocks). H[i] is read once for both
+// blocks, and X[t-i] serves block t at partition i and block t+1 at partition i+1, so a contiguous run of partitions
+// costs ONE coefficient and ONE delay-line load per partition: per channel (2 P_eff + SPLIT + 2) N rs bytes for two
+// blocks instead of 2 (2 P_eff + 1) N rs. Both forward transforms have run (block t+1 sits in slot (t+1) % P).
+// Slice s owns the contiguous partitions [s cs, (s+1) cs), cs = ceil(P_eff / SPLIT); slices are summed in order.
+template <class T, int SPLIT, int UNROLL>
+__global__ void __launch_bounds__(256) partition_mac_pair_kernel(const MacArgs a)
+{
+    constexpr int GPC = 256 / SPLIT;
+    const int slice = threadIdx.x / GPC, gl = threadIdx.x - slice * GPC;
+    const int g = blockIdx.x * GPC + gl;
+    const int ch = blockIdx.y + a.ch_base;
+    const bool active = g * 8 < a.N;
+    const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
+    const int peff = min(a.coeff_blocks[ch], a.n_parts);
+    const int cs = (peff + SPLIT - 1) / SPLIT;
+    const int i0 = slice * cs, i1 = min(peff, i0 + cs);
+    const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
+    const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
+    const unsigned int P = (unsigned int)a.n_slots;
+
+    T acc0[8], acc1[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { acc0[j] = (T)0; acc1[j] = (T)0; }
+    T dc0 = (T)0, ny0 = (T)0, dc1 = (T)0, ny1 = (T)0;
+
+    if (active && i0 < i1) {
+        T xa[8];                                                   // X[t+1-i]: block t+1's operand at partition i
+        ld8(fdl + (long long)((t + 1u - (unsigned int)i0) % P) * a.N, xa);
+        int i = i0;
+        for (; i + UNROLL <= i1; i += UNROLL) {
+            T xb[UNROLL][8], c[UNROLL][8];
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                ld8(fdl + (long long)((t - (unsigned int)(i + u)) % P) * a.N, xb[u]);   // X[t-i]: block t at i, block t+1 at i+1
+                ld8(cf + (long long)(i + u) * a.N, c[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                if (g == 0) {
+                    dc1 = fma(xa[0], c[u][0], dc1); ny1 = fma(xa[4], c[u][4], ny1);
+                    dc0 = fma(xb[u][0], c[u][0], dc0); ny0 = fma(xb[u][4], c[u][4], ny0);
+                }
+                mac8<T>(acc1, xa, c[u]);
+                mac8<T>(acc0, xb[u], c[u]);
+#pragma unroll
+                for (int j = 0; j < 8; j++) xa[j] = xb[u][j];
+            }
+        }
+        for (; i < i1; i++) {
+            T xb[8], c[8];
+            ld8(fdl + (long long)((t - (unsigned int)i) % P) * a.N, xb);
+            ld8(cf + (long long)i * a.N, c);
+            if (g == 0) {
+                dc1 = fma(xa[0], c[0], dc1); ny1 = fma(xa[4], c[4], ny1);
+                dc0 = fma(xb[0], c[0], dc0); ny0 = fma(xb[4], c[4], ny0);
+            }
+            mac8<T>(acc1, xa, c);
+            mac8<T>(acc0, xb, c);
+#pragma unroll
+            for (int j = 0; j < 8; j++) xa[j] = xb[j];
+        }
+        if (g == 0) { acc0[0] = dc0; acc0[4] = ny0; acc1[0] = dc1; acc1[4] = ny1; }
+    }
+    if (SPLIT > 1) {
+        __shared__ T red[SPLIT > 1 ? (SPLIT - 1) * GPC * 16 : 1];
+        if (slice > 0) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                red[((slice - 1) * 16 + j) * GPC + gl] = acc0[j];
+                red[((slice - 1) * 16 + 8 + j) * GPC + gl] = acc1[j];
+            }
+        }
+        __syncthreads();
+        if (slice > 0) return;
+#pragma unroll
+        for (int s = 1; s < SPLIT; s++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                acc0[j] += red[((s - 1) * 16 + j) * GPC + gl];
+                acc1[j] += red[((s - 1) * 16 + 8 + j) * GPC + gl];
+            }
+    }
+    if (active) {
+        st8((T *)a.acc + (long long)ch * a.N + (long long)g * 8, acc0);
+        st8((T *)a.acc_next + (long long)ch * a.N + (long long)g * 8, acc1);
+    }
+}
+
 typedef void (*mac_kernel_t)(const MacArgs);
+template <class T> inline mac_kernel_t mac_pair_kernel_for_split(int split)
+{
+    constexpr int U = sizeof(T) == 8 ? 2 : 4;
+    switch (split) {
+    case 1: return partition_mac_pair_kernel<T, 1, U>;
+    case 2: return partition_mac_pair_kernel<T, 2, U>;
+    case 4: return partition_mac_pair_kernel<T, 4, U>;
+    case 8: return partition_mac_pair_kernel<T, 8, 2>;
+    default: return partition_mac_pair_kernel<T, 16, 1>;
+    }
+}
 template <class T> inline mac_kernel_t mac_kernel_for_split(int split)
 {
     switch (split) {

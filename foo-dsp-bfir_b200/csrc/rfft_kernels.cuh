@@ -68,8 +68,10 @@ struct FwdArgs {
     int fmt, ch_per_stream, n_channels;
     int ch_base;             // first channel of this launch (channel-group pipelining): bx = blockIdx.x + ch_base
     unsigned int prev_parity; // blockcounter & 1, tracked by the host so that no load depends on the state word
-    const EngineState *state; // out slot = blockcounter % n_slots when state != NULL
-    int n_slots;
+    const EngineState *state; // out slot = (blockcounter + slot_offset) % n_slots when state != NULL
+    int n_slots;             // delay-line slots per channel (the engine keeps one more than partitions)
+    int n_parts;             // filter partitions: procblocks counts up to this (brutefir.cpp:265-268)
+    int slot_offset;         // 1: the second block of a pair, transformed before the first one has been counted
     int *procblocks;         // [channels], brutefir.cpp:265-268
     unsigned char *pb_inc;   // [channels], 1 when procblocks was incremented by this launch
     // IN_COEFF
@@ -221,10 +223,10 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], con
     }
     if (a.in_mode == IN_COEFF && bad) *a.nonfinite = 1;
     if (a.in_mode == IN_RAW_PREV && a.state != NULL && t == 0 && r == 0 && by == 0 && bx == a.ch_base)
-        const_cast<EngineState *>(a.state)->cur_slot = a.state->blockcounter % (unsigned int)a.n_slots;
+        const_cast<EngineState *>(a.state)->cur_slot = (a.state->blockcounter + (unsigned int)a.slot_offset) % (unsigned int)a.n_slots;
     if (a.in_mode == IN_RAW_PREV && t == 0 && r == 0 && a.procblocks != NULL) { // brutefir.cpp:265-268
         const int pb = a.procblocks[bx];
-        const bool inc = pb < a.n_slots;
+        const bool inc = pb < a.n_parts;
         if (inc) a.procblocks[bx] = pb + 1;
         a.pb_inc[bx] = inc ? 1 : 0;
     }
@@ -238,7 +240,7 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
     constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, M = MS * R0, N = 2 * M;
     typedef cpx<T> C;
     long long off = bx * a.out_stride_x + by * a.out_stride_y;
-    if (a.state != NULL) off += (long long)(a.state->blockcounter % (unsigned int)a.n_slots) * a.out_stride_y;
+    if (a.state != NULL) off += (long long)((a.state->blockcounter + (unsigned int)a.slot_offset) % (unsigned int)a.n_slots) * a.out_stride_y;
     T *out = (T *)a.out + off;
     const T sc = (T)a.scale_out;
     const C wbase = tw[(R0 * t + r) << tw_shift_n];   // W_N^k of i = 0; the thread's bins are N/(2E) apart

@@ -23,6 +23,7 @@ struct XbarArgs {
     int n_in, n_out, N, n_streams;
     const EngineState *state;  // slot = blockcounter % n_slots
     int n_slots;
+    int n_parts;               // filter partitions (procblocks cap)
     int *procblocks;           // [streams * n_out]: incremented here for the filter channels (brutefir.cpp:265-268)
     unsigned char *pb_inc;
     int stream_base;           // first stream of this launch (channel groups)
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
     if (a.procblocks != NULL && blockIdx.x == 0 && threadIdx.x < a.n_out) {
         const int ch = s * a.n_out + threadIdx.x;
         const int pb = a.procblocks[ch];
-        const bool inc = pb < a.n_slots;
+        const bool inc = pb < a.n_parts;
         if (inc) a.procblocks[ch] = pb + 1;
         a.pb_inc[ch] = inc ? 1 : 0;
     }

@@ -155,6 +155,17 @@ int bfir_wait(bfir_engine *e, long long ticket);
  * its slice of d_outbuf, in call order; the caller must not rewrite a buffer that a queued block still uses. */
 int bfir_run_device_pipelined(bfir_engine *e, const void *d_inbuf, void *d_outbuf);
 int bfir_join(bfir_engine *e);
+/* Two consecutive blocks per call, for callers that have the next block at hand (offline rendering, the
+ * pipelined paths above): both forward transforms, ONE partition-sum launch in which every coefficient spectrum
+ * is read once for both blocks and every delay-line spectrum serves block t at partition i and block t+1 at
+ * partition i+1 (per channel (2P + split + 2) N realsize bytes for two blocks instead of 2 (2P + 1) N realsize),
+ * both inverse transforms. Same results as two bfir_run_device / bfir_run_async calls up to the summation order
+ * of the partition sum. While that is not possible (fewer than filter_blocks blocks since the last reset, a
+ * crossbar, a partition shard, a pending filter swap, profiling) the call runs the two blocks one by one.
+ * bfir_run_device_pair: `pipelined` != 0 behaves like bfir_run_device_pipelined (no join), 0 like bfir_run_device.
+ * bfir_run_async_pair: pinned host buffers, returns the ticket of the SECOND block (waiting on it covers both). */
+int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, int pipelined);
+long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, void *out0, void *out1);
 
 /* brutefir::reset (brutefir.cpp:347-367): zeroes counters and overflow statistics, NOT the buffers */
 int bfir_reset(bfir_engine *e);
@@ -195,6 +206,8 @@ int bfir_peer_own_channels(bfir_engine *e, int *first, int *count);
 /* Change the number of channel groups (see bfir_config_t.n_groups); synchronises the engine. */
 int bfir_set_groups(bfir_engine *e, int n_groups);
 int bfir_get_groups(bfir_engine *e);
+/* partition slices per CTA the engine chose for its partition-sum kernels (reporting only) */
+int bfir_get_mac_split(bfir_engine *e);
 
 /* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the engine's own. */
 int bfir_set_stream(bfir_engine *e, void *cuda_stream);

@@ -129,7 +129,7 @@ template <class T, int LOG2MS, int R0, int LOG2E = 4> static int check_engine_mo
         a.in_mode = IN_RAW_PREV; a.out_layout = LAYOUT_ORD; a.in = raw_in.data(); a.in_stride_x = (long long)L * CH * ib;
         a.out = fdl.data(); a.out_stride_x = (long long)P * N; a.out_stride_y = N; a.scale_in = 1.0; a.scale_out = 0.5;
         a.prev = prev.data(); a.fmt = fmt_in; a.ch_per_stream = CH; a.n_channels = Ct; a.ch_base = 0; a.prev_parity = 0;
-        a.state = &st; a.n_slots = P; a.procblocks = procblocks.data(); a.pb_inc = pb_inc.data();
+        a.state = &st; a.n_slots = P; a.n_parts = P; a.procblocks = procblocks.data(); a.pb_inc = pb_inc.data();
         for (int r = 0; r < R0; r++) {
             for (int t = 0; t < NT; t++) fwd_load<T, LOG2MS, R0, LOG2E>(t, bx, 0, r, vs[t], tw.data(), 0, a);
             fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run_host(vs, smem.data(), tw.data(), sm);
