@@ -650,3 +650,32 @@ def test_block_pairs_equal_single_blocks(pkg, oracle, rs, groups, out_fmt, dithe
                     assert dd.mean() < 0.5
         if b < P and not dither:                         # the fall-back path is the single-block path itself
             assert np.array_equal(a, out_p[b].cpu().numpy()), b
+
+
+def test_cfg1_block_pairs_vs_oracle(pkg, oracle):
+    """BASELINE configs[1] geometry (8 ch, double, L 8192, P 32) through the two-block entry point, straight against
+    the oracle: the pair kernel must meet the same 1e-12 bar as the one-block path."""
+    import torch
+    L, P, C = 8192, 32, 8
+    g = pkg.Brutefir(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 48000, False)
+    o = oracle.Engine(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 48000, False)
+    h = [decay_filter(c, L * P) for c in range(C)]
+    assert g.set_coeff(h, P) == 0 and o.set_coeff(h, P) == 0
+    nblk = P + 6
+    x = white_noise(23, nblk * L, C)
+    d_out = [torch.zeros(L * C, dtype=torch.float64, device="cuda") for _ in range(2)]
+    for b in range(0, nblk, 2):
+        blk = [np.ascontiguousarray(x[(b + k) * L:(b + k + 1) * L]) for k in range(2)]
+        d_in = [torch.from_numpy(v.ravel()).cuda() for v in blk]
+        torch.cuda.synchronize()
+        g.run_device_pair(d_in[0], d_in[1], d_out[0], d_out[1])
+        assert g.sync() == 0
+        for k in range(2):
+            rc, ref = o.run(blk[k].view(np.uint8).ravel())
+            assert rc == 0
+            if b + k >= P - 2:                      # the last one-by-one blocks and every pair
+                got = d_out[k].cpu().numpy().reshape(L, C)
+                want = ref.view(np.float64).reshape(L, C)
+                for c in range(C):
+                    assert rel_rms(got[:, c], want[:, c]) < 1e-12, (b + k, c)
+    assert g.blockcounter() == o.blockcounter() == nblk
