@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--streams", type=int, default=16)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--pairs", action="store_true", help="two blocks per call (bfir_run_device_pair); times are per PAIR then")
     a = ap.parse_args()
     import torch
     pkg = importlib.import_module("foo-dsp-bfir_b200")
@@ -46,12 +47,21 @@ def main():
     for b in range(a.P + 5):
         eng.run_device(d_in[b % 4], d_out)
     assert eng.sync() == 0
-    eng.set_profiling(a.steps)
-    for b in range(a.steps):
-        eng.run_device(d_in[b % 4], d_out)
+    if a.pairs:
+        d_out2 = torch.empty_like(d_out)
+        eng.run_device_pair(d_in[0], d_in[1], d_out, d_out2)
+        assert eng.sync() == 0
+        eng.set_profiling(a.steps // 2)
+        for b in range(0, a.steps, 2):
+            eng.run_device_pair(d_in[b % 4], d_in[(b + 1) % 4], d_out, d_out2)
+    else:
+        eng.set_profiling(a.steps)
+        for b in range(a.steps):
+            eng.run_device(d_in[b % 4], d_out)
     assert eng.sync() == 0
     prof, n = eng.get_profile()
-    ms = {k: v / n for k, v in prof.items()}
+    per = 2 if a.pairs else 1                  # blocks per profiled entry
+    ms = {k: v / n / per for k, v in prof.items()}   # per block
     step = sum(ms.values())
     b_mac = (2 * a.P + 1) * 2 * a.L * a.realsize * Ct
     print(json.dumps({"tag": a.tag, "split_env": os.environ.get("BFIR_MAC_SPLIT"), "cfg": vars(a), "ms": ms,
