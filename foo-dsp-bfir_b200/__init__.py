@@ -66,6 +66,8 @@ API = [
     ("bfir_set_coeff_device", _ci, [_vp, _vp, ctypes.c_longlong, _ci, _ci, _ci, _cd, _ci]),
     ("bfir_set_crossbar", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(_cd)]),
     ("bfir_run", _ci, [_vp, _vp, _vp]),
+    ("bfir_host_alloc", _vp, [ctypes.c_size_t]),
+    ("bfir_host_free", None, [_vp]),
     ("bfir_run_device", _ci, [_vp, _vp, _vp]),
     ("bfir_run_async", ctypes.c_longlong, [_vp, _vp, _vp]),
     ("bfir_run_device_pipelined", _ci, [_vp, _vp, _vp]),

@@ -120,3 +120,16 @@ void DitherTables::destroy()
 }
 
 } // namespace bfir
+
+// pinned host memory for the raw blocks a caller hands to bfir_run (lets an integrator stay free of CUDA headers)
+extern "C" void *bfir_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void bfir_host_free(void *p)
+{
+    if (p != nullptr) cudaFreeHost(p);
+}

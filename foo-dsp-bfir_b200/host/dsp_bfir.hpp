@@ -10,8 +10,8 @@
 //       planar double arrays owned by the provider until the call returns
 //   chunk_sink(data, sample_count, channels, srate)  == insert_chunk + set_data_32 (:334-335)
 #pragma once
+#include <cstdlib>
 #include <cstring>
-#include <vector>
 #include "brutefir.hpp"
 
 #define BFIR_FILTER_LEN 1024 // FILTER_LEN, foo_dsp_bfir/common.h:17
@@ -27,9 +27,9 @@ public:
 
     dsp_bfir(filter_provider_t provider, chunk_sink_t sink, void *user, bool check_overflows = false)
         : m_provider(provider), m_sink(sink), m_user(user), m_check_overflows(check_overflows),
-          m_filter(NULL), m_channels(0), m_srate(0), m_buffer_count(0) {}
+          m_filter(NULL), m_channels(0), m_srate(0), m_buffer_count(0), m_inbuf(NULL), m_outbuf(NULL), m_pinned(false) {}
 
-    ~dsp_bfir() { delete m_filter; }
+    ~dsp_bfir() { delete m_filter; free_buffers(); }
 
     // foo_dsp_bfir.cpp:100-362. Returns true = "pass the original chunk through" (no filter),
     // false = "the chunk was consumed and replaced by the emitted ones".
@@ -50,8 +50,7 @@ public:
                 m_filter = new brutefir(BFIR_FILTER_LEN, blocks > 0 ? blocks : 1, BFIR_REALSIZE, (int)m_channels,
                                         BFIR_SAMPLE_FORMAT_FLOAT_LE, BFIR_SAMPLE_FORMAT_FLOAT_LE, (int)m_srate, false); // :279-286
                 m_filter->set_coeff(coeffs, n_coeffs, length, blocks > 0 ? blocks : 1, scale);                        // :289
-                m_inbuf.assign((size_t)BFIR_FILTER_LEN * m_channels, 0.f);                                            // :292-294
-                m_outbuf.assign((size_t)BFIR_FILTER_LEN * m_channels, 0.f);
+                alloc_buffers((size_t)BFIR_FILTER_LEN * m_channels);                                                  // :292-294
             }
         }
         if (m_filter == NULL) return true;                       // :352-357 pass-through
@@ -60,13 +59,13 @@ public:
         while (sample_count) {                                   // :311-349
             size_t todo = BFIR_FILTER_LEN - m_buffer_count;
             if (todo > sample_count) todo = sample_count;
-            memcpy(&m_inbuf[m_buffer_count * m_channels], src, todo * m_channels * sizeof(audio_sample));
+            memcpy(m_inbuf + m_buffer_count * m_channels, src, todo * m_channels * sizeof(audio_sample));
             src += todo * m_channels;
             sample_count -= todo;
             m_buffer_count += todo;
             if (m_buffer_count == BFIR_FILTER_LEN) {
-                if (m_filter->run(m_inbuf.data(), m_outbuf.data()) == 0) {
-                    if (m_sink != NULL) m_sink(m_user, m_outbuf.data(), m_buffer_count, m_channels, m_srate);
+                if (m_filter->run(m_inbuf, m_outbuf) == 0) {
+                    if (m_sink != NULL) m_sink(m_user, m_outbuf, m_buffer_count, m_channels, m_srate);
                     if (m_check_overflows) m_filter->check_overflows();
                 }                                                // else: "Filter processing error.", block dropped
                 m_buffer_count = 0;
@@ -92,5 +91,27 @@ private:
     brutefir *m_filter;
     unsigned m_channels, m_srate;
     size_t m_buffer_count;
-    std::vector<audio_sample> m_inbuf, m_outbuf;
+    // the block buffers are page-locked (bfir_host_alloc) so that bfir_run's copies go straight over the link;
+    // plain memory is the fall-back when that fails (bfir_run accepts it)
+    audio_sample *m_inbuf, *m_outbuf;
+    bool m_pinned;
+    void free_buffers()
+    {
+        if (m_pinned) { bfir_host_free(m_inbuf); bfir_host_free(m_outbuf); } else { free(m_inbuf); free(m_outbuf); }
+        m_inbuf = m_outbuf = NULL;
+    }
+    void alloc_buffers(size_t n)
+    {
+        free_buffers();
+        m_inbuf = (audio_sample *)bfir_host_alloc(n * sizeof(audio_sample));
+        m_outbuf = (audio_sample *)bfir_host_alloc(n * sizeof(audio_sample));
+        m_pinned = m_inbuf != NULL && m_outbuf != NULL;
+        if (!m_pinned) {
+            bfir_host_free(m_inbuf); bfir_host_free(m_outbuf);
+            m_inbuf = (audio_sample *)malloc(n * sizeof(audio_sample));
+            m_outbuf = (audio_sample *)malloc(n * sizeof(audio_sample));
+        }
+        memset(m_inbuf, 0, n * sizeof(audio_sample));
+        memset(m_outbuf, 0, n * sizeof(audio_sample));
+    }
 };

@@ -126,6 +126,13 @@ int bfir_set_coeff_device(bfir_engine *e, const void *d_coeffs, long long channe
  * HOST arrays of doubles, copied. The sample-format scales are applied on top, as in brutefir::run. */
 int bfir_set_crossbar(bfir_engine *e, const double *in_gains, const double *out_gains);
 
+/* Page-locked host memory for the raw blocks handed to bfir_run / bfir_run_async (the reference's
+ * _aligned_realloc of m_inbuf / m_outbuf, foo_dsp_bfir.cpp:292-294). bfir_run also accepts ordinary pageable
+ * memory (the driver then stages the copies itself, more slowly); bfir_run_async needs page-locked buffers.
+ * Returns NULL without a CUDA device or when the allocation fails. */
+void *bfir_host_alloc(size_t bytes);
+void bfir_host_free(void *p);
+
 /* brutefir::run (brutefir.cpp:245-343): inbuf/outbuf are HOST buffers holding exactly
  * n_streams * filter_length * channels interleaved samples in in_format / out_format. Synchronous:
  * returns when outbuf is filled. Returns 0, or BFIR_ERR_NONFINITE (-1) when output sample 0 of some
