@@ -304,7 +304,7 @@ def main():
     # output block. e2e.value: bfir_run_async_pair / bfir_wait (two blocks per call, DEPTH calls in flight, stream
     # groups with their own copy streams), median of 3 passes of K steps (the pass is half host work, and the hosts
     # of this pool are noisy). Beside it: one block per call (bfir_run_async) and the reference's synchronous run().
-    DEPTH = 2
+    DEPTH = 3
 
     def e2e_pass(engine, ins, outs, steps, sync_groups, async_groups):
         engine.set_groups(min(sync_groups, S))

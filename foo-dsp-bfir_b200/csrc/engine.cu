@@ -49,7 +49,7 @@ struct Engine {
         // bfir_run_async: the group's copies ride on their own streams so that they overlap its kernels too
         cudaStream_t h2d, d2h;
         cudaEvent_t in_ready, out_ready, copies_done;
-        cudaEvent_t in_free[4], out_free[4];   // per staging slot (kStage)
+        cudaEvent_t in_free[8], out_free[8];   // per staging slot (kStage)
     };
     Group groups[BFIR_MAX_GROUPS] = {};
     int n_groups = 1;
@@ -104,11 +104,13 @@ struct Engine {
     // launch that reads every coefficient spectrum once for both blocks, both inverse transforms
     void *acc_pair = nullptr;       // accumulated spectra of the second block, [Ct][N]
     // bfir_run_async: ring of staging buffers for the raw blocks (slot 0 = d_in / d_out), so that the input copies can
-    // run up to kStage - 1 blocks ahead of the transforms and the output copies behind them
-    static const int kStage = 4;
+    // run up to kStage - 1 blocks ahead of the transforms and the output copies behind them. A slot is busy from the
+    // start of its H2D to the end of its D2H (three pipeline stages), so fewer than three blocks (pairs) worth of
+    // slots leaves one of the stages idle: 8 slots = 4 pairs
+    static const int kStage = 8;
     void *stage_in[kStage] = {}, *stage_out[kStage] = {};
     unsigned long long stage_next = 0;
-    int stage_count = kStage;       // slots in use (BFIR_STAGE = 1 .. 4, measurement)
+    int stage_count = kStage;       // slots in use (BFIR_STAGE = 1 .. 8, measurement)
     int open_async_copies();
     int stage_alloc(int k);
     int fwd_block_offset = 0;       // front_group: 1 while the second block of a pair is transformed
