@@ -117,7 +117,7 @@ struct Engine {
     const void *acc_override = nullptr; // back_group: accumulated spectra to emit instead of acc
     bool pair_ok() const
     {
-        return !xbar && !peer.enabled && part_begin == 0 && part_count == P && P >= 2 && !xfade_pending &&
+        return !peer.enabled && part_begin == 0 && part_count == P && P >= 2 && !xfade_pending &&
                host_blockcounter >= (unsigned int)P;
     }
     int pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, cudaEvent_t *input_consumed, cudaEvent_t *output_free);
@@ -551,7 +551,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
         XbarArgs x = {};
         x.in = xin; x.in_stride = N; x.out = fdl; x.out_stride = (long long)Pslots * N; x.slot_stride = N;
         x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = ns; x.stream_base = s0;
-        x.state = state + g; x.n_slots = Pslots; x.n_parts = P; x.procblocks = procblocks; x.pb_inc = pb_inc;
+        x.state = state + g; x.n_slots = Pslots; x.n_parts = P; x.slot_offset = fwd_block_offset; x.procblocks = procblocks; x.pb_inc = pb_inc;
         xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
         xk<<<dim3((N + 255) / 256, ns), 256, (size_t)C * Ci * rs, st>>>(x);
         count_launch();
@@ -618,7 +618,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
     }
     if (xbar) { // filter outputs -> outputs (mixnscale OUTPUT, n_bufs = C)
         XbarArgs x = {};
-        x.in = acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
+        x.in = acc_override ? acc_override : acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
         x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = ns; x.stream_base = s0;
         x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.procblocks = nullptr; x.pb_inc = nullptr;
         xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
@@ -647,7 +647,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
         BFIR_CUDA(cudaGetLastError());
     }
     InvArgs v = {};
-    v.in_layout = LAYOUT_ORD; v.in = acc_override ? acc_override : (xbar ? yacc : acc); v.in_stride_x = N;
+    v.in_layout = LAYOUT_ORD; v.in = xbar ? yacc : (acc_override ? acc_override : acc); v.in_stride_x = N;
     v.scale_in = out_sf.scale;                                         // brutefir.cpp:303-307
     v.fmt = out_sf.format; v.ch_per_stream = Co; v.ovf_max = ovf_max; v.stats = stats; v.state = state + g; v.ch_base = c0; v.host_flag = d_flag;
     if (dither_on) { v.out_mode = OUT_REAL_L; v.out = ybuf; v.out_stride_x = L; }

@@ -21,8 +21,9 @@ struct XbarArgs {
     long long in_stride, out_stride, slot_stride;
     const void *gains;         // device, [n_out][n_in] of T, row-major
     int n_in, n_out, N, n_streams;
-    const EngineState *state;  // slot = blockcounter % n_slots
+    const EngineState *state;  // slot = (blockcounter + slot_offset) % n_slots
     int n_slots;
+    int slot_offset;           // 1: the second block of a pair
     int n_parts;               // filter partitions (procblocks cap)
     int *procblocks;           // [streams * n_out]: incremented here for the filter channels (brutefir.cpp:265-268)
     unsigned char *pb_inc;
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
 #pragma unroll
     for (int i = 0; i < MAXI; i++) x[i] = i < a.n_in ? in[(long long)i * a.in_stride] : (T)0;
     long long off = (long long)s * a.n_out * a.out_stride + j;
-    if (a.state != NULL) off += (long long)(a.state->blockcounter % (unsigned int)a.n_slots) * a.slot_stride;
+    if (a.state != NULL) off += (long long)((a.state->blockcounter + (unsigned int)a.slot_offset) % (unsigned int)a.n_slots) * a.slot_stride;
     T *out = (T *)a.out + off;
     for (int o = 0; o < a.n_out; o++) {
         const T *row = g + o * a.n_in;

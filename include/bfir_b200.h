@@ -168,7 +168,7 @@ int bfir_join(bfir_engine *e);
  * partition i+1 (per channel (2P + split + 2) N realsize bytes for two blocks instead of 2 (2P + 1) N realsize),
  * both inverse transforms. Same results as two bfir_run_device / bfir_run_async calls up to the summation order
  * of the partition sum. While that is not possible (fewer than filter_blocks blocks since the last reset, a
- * crossbar, a partition shard, a pending filter swap, profiling) the call runs the two blocks one by one.
+ * partition shard, a pending filter swap) the call runs the two blocks one by one.
  * bfir_run_device_pair: `pipelined` != 0 behaves like bfir_run_device_pipelined (no join), 0 like bfir_run_device.
  * bfir_run_async_pair: pinned host buffers, returns the ticket of the SECOND block (waiting on it covers both). */
 int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, int pipelined);

@@ -150,3 +150,42 @@ def test_cfg4_full_depth_one_gpu(pkg):
     Y = torch.cat(y, dim=0).double()
     err = torch.sqrt(torch.mean((Y - ref) ** 2) / torch.mean(ref ** 2)).item()
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("rs,L,P,n_in,n_f,n_out,S", [(4, 256, 3, 2, 3, 2, 1), (8, 128, 4, 5, 4, 3, 2), (4, 1024, 4, 32, 32, 32, 1)])
+def test_crossbar_block_pairs_equal_single_blocks(pkg, rs, L, P, n_in, n_f, n_out, S):
+    """two blocks per partition-sum launch with a crossbar around the filters (the cfg4 shape): same output as block
+    by block up to the summation order, through the device and the pinned-host entry points"""
+    import torch
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt, tdt = (np.float32, torch.float32) if rs == 4 else (np.float64, torch.float64)
+    rng = np.random.default_rng(5)
+    gin = rng.standard_normal((n_f, n_in)) / np.sqrt(n_in)
+    gout = rng.standard_normal((n_out, n_f)) / np.sqrt(n_f)
+    h = [decay_filter(f % 5, L * P) * (1 + 0.1 * f) for f in range(n_f * S)]
+    engines = [pkg.Brutefir(L, P, rs, n_f, fmt, fmt, 48000, False, n_streams=S, xbar_inputs=n_in, xbar_outputs=n_out) for _ in range(3)]
+    for e in engines:
+        assert e.set_coeff(h, P) == 0
+        e.set_crossbar(gin, gout)
+    single, pair_d, pair_h = engines
+    nblk = 2 * P + 6
+    blocks = [rng.uniform(-1, 1, S * L * n_in).astype(dt) for _ in range(nblk)]
+    d_in = [torch.from_numpy(b).cuda() for b in blocks]
+    pin_in = [torch.from_numpy(b).pin_memory() for b in blocks]
+    n_o = S * L * n_out
+    out_s = [torch.zeros(n_o, dtype=tdt, device="cuda") for _ in range(nblk)]
+    out_p = [torch.zeros(n_o, dtype=tdt, device="cuda") for _ in range(nblk)]
+    out_h = [torch.zeros(n_o, dtype=tdt).pin_memory() for _ in range(nblk)]
+    torch.cuda.synchronize()
+    for b in range(nblk):
+        single.run_device(d_in[b], out_s[b])
+    t = None
+    for b in range(0, nblk, 2):
+        pair_d.run_device_pair(d_in[b], d_in[b + 1], out_p[b], out_p[b + 1])
+        t = pair_h.run_async_pair(pin_in[b].numpy(), pin_in[b + 1].numpy(), out_h[b].numpy(), out_h[b + 1].numpy())
+    assert single.sync() == 0 and pair_d.sync() == 0 and pair_h.wait(t) == 0
+    tol = 2e-6 if rs == 4 else 1e-13
+    for b in range(nblk):
+        a = out_s[b].cpu().numpy()
+        assert rel_rms(out_p[b].cpu().numpy(), a) < tol, b
+        assert rel_rms(out_h[b].numpy(), a) < tol, b
