@@ -738,7 +738,7 @@ int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0
 }
 
 // two consecutive blocks on device buffers. Falls back to two single-block steps while the delay line is still
-// filling, with a crossbar / partition shard / pending filter swap / dither / profiling.
+// filling, on a partition shard and with a pending filter swap.
 int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined)
 {
     int rc;
