@@ -13,7 +13,8 @@ Workload (one "step" = one block of the block loop, brutefir::run, for every str
   runs its own S streams (channel/stream sharding, no collective): weak scaling.
 
 Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM, two blocks per call
-(bfir_run_device_pair: one partition-sum launch for both, every coefficient spectrum read once); e2e = the
+(bfir_run_device_pair: one partition-sum launch for both, every coefficient spectrum read once) through the engine's
+stage pipeline (transforms of the neighbouring pairs on side streams beside the pair sum); e2e = the
 same metric on pinned HOST buffers, the H2D of every input block and the D2H of every output block inside
 the timed region: e2e.value through bfir_run_async_pair/bfir_wait (two calls in flight), e2e.one_block_per_call
 through bfir_run_async, e2e.sync_run through the reference's synchronous run() = bfir_run (H2D + kernels + D2H +
@@ -246,10 +247,13 @@ def main():
     # ---- device-resident throughput: EXACTLY K steps between barrier+sync, CUDA events on the launch stream.
     # A throughput caller has the next block at hand, so the steps go through the two-block entry point: both forward
     # transforms, ONE partition-sum launch that reads every coefficient spectrum once for both blocks, both inverse
-    # transforms (one stream, kernels back to back, so each kernel's CUDA-event time is its own: the roofline's).
+    # transforms. "staged": the engine's stage pipeline (the pair sum stays on the engine's stream, where its CUDA-event
+    # time is taken; the transforms of the next / previous pair run beside it on two side streams). "serial": the same
+    # kernels back to back on one stream (each kernel's event time is its own: step shares). "single": one block per call.
     dev_out2 = torch.empty_like(dev_out)
 
-    def device_pass(single):
+    def device_pass(mode):
+        single = mode == "single"
         eng.set_profiling(K if single else K // 2)
         n0 = pkg.kernel_launch_count()
         barrier()
@@ -260,9 +264,10 @@ def main():
                 eng.run_device(dev_in[b % ring], dev_out)
         else:
             for b in range(0, K - 1, 2):
-                eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2)
+                eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2, pipelined=(mode == "staged"))
             if K % 2:
                 eng.run_device(dev_in[(K - 1) % ring], dev_out)
+            eng.join()                      # the engine's stream waits for the side streams (no host wait)
         e1.record(stream)
         assert eng.sync() == 0
         barrier()
@@ -271,17 +276,19 @@ def main():
         pr, npr = eng.get_profile()
         return ms, n, pr, npr
 
+    device_pass("staged")                   # warm-up of the stage pipeline (allocates its accumulators)
     sampler.busy.set()
-    ms_total, launches, prof, nprof = device_pass(single=False)
+    ms_total, launches, prof_staged, nprof_staged = device_pass("staged")
     sampler.busy.clear()
     value = n_gpus * Ct * L * K / (ms_total * 1e-3) / 1e6
+    ms_serial, _, prof, nprof = device_pass("serial")
     # the same K steps one block per call (what a real-time caller gets; the per-block partition sum of SURVEY 8d)
-    ms_single, _, prof_single, nprof_single = device_pass(single=True)
+    ms_single, _, prof_single, nprof_single = device_pass("single")
     mac_split = eng.get_mac_split()
 
     # the same device-resident work the way the end-to-end path runs it: 8 stream groups, no join between calls
     # (a group that is done with its blocks starts the next ones while others still convolve, so transforms run under
-    # the partition sums). Per-kernel event times overlap there, so the roofline stays on the serial pass above.
+    # the partition sums of other groups).
     eng.set_groups(min(8, S))
     for b in range(0, 4, 2):
         eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2, pipelined=True)
@@ -391,7 +398,8 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     b_mac = (2 * P + 1) * (2 * L) * rs * Ct            # algorithmic bytes per channel-block x channels
     npairs = max(nprof, 1)
-    mac_ms = prof["mac_ms"] / npairs                    # one pair launch = two blocks of every channel
+    mac_ms = prof_staged["mac_ms"] / max(nprof_staged, 1)   # one pair launch = two blocks of every channel; timed region of `value`
+    mac_serial_ms = prof["mac_ms"] / npairs
     algorithmic = 2 * b_mac
     actual = (2 * P + mac_split + 2) * (2 * L) * rs * Ct   # what the pair kernel has to move: H once, X once per slice run, two outputs
     achieved = algorithmic / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
@@ -409,6 +417,9 @@ def main():
                         "reads each coefficient spectrum once for both blocks, so it needs to move only bytes_needed_per_launch: frac > 1 is that reuse, "
                         "frac_of_bytes_needed is the kernel against the HBM roofline" % Ct,
                 "bytes_needed_per_launch": actual, "frac_of_bytes_needed": actual / (mac_ms * 1e-3) / 1e9 / peak if mac_ms > 0 else 0.0,
+                "serial_pass": {"note": "the same pair kernels back to back on one stream", "avg_launch_ms": mac_serial_ms,
+                                "frac": algorithmic / (mac_serial_ms * 1e-3) / 1e9 / peak if mac_serial_ms > 0 else 0.0,
+                                "value": n_gpus * Ct * L * K / (ms_serial * 1e-3) / 1e6, "ms_per_step": ms_serial / K},
                 "step_share": {k: v / npairs / 2 for k, v in prof.items()},
                 "one_block_per_launch": {"kernel": "partition_mac_kernel<double,SPLIT=%d,UNROLL=4>" % mac_split, "avg_launch_ms": mac1_ms,
                                          "algorithmic_bytes_per_launch": b_mac,

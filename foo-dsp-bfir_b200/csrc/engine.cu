@@ -114,6 +114,18 @@ struct Engine {
     int open_async_copies();
     int stage_alloc(int k);
     int fwd_block_offset = 0;       // front_group: 1 while the second block of a pair is transformed
+    // stage pipeline (one group, bfir_run_device_pair(pipelined)): forward transforms of pair k+1 on their own stream under
+    // the partition sum of pair k on the engine's stream, inverse transforms of pair k-1 on a third; the kernels get the
+    // block index from the host because the device counter (advanced by the inverse kernels) lags behind
+    cudaStream_t sp_fwd = nullptr, sp_inv = nullptr;
+    cudaEvent_t sp_fwd_done[2] = {}, sp_mac_done[2] = {}, sp_inv_done[2] = {};
+    void *sp_acc[2][2] = {};        // [pair parity][block in pair] accumulated spectra
+    unsigned long long sp_pairs = 0; // pairs queued since the pipeline was opened
+    bool sp_open = false;
+    bool staged_enabled = true;     // BFIR_STAGED=0 switches the stage pipeline off
+    bool use_abs = false;           // front_group / pair sum: pass host_blockcounter (+ offset) as the block index
+    int staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1);
+    int close_staged();
     const void *acc_override = nullptr; // back_group: accumulated spectra to emit instead of acc
     bool pair_ok() const
     {
@@ -170,7 +182,7 @@ int Engine::init(const bfir_config_t &c)
     if (P < 1 || C < 1) { set_error("No channels defined."); return BFIR_ERR_INVALID; }            // brutefir.cpp:745-749
     if ((long long)C * S > 0x7fffffffLL / 2) return BFIR_ERR_INVALID;
     Ct = C * S;
-    Pslots = P + 1;
+    Pslots = P + 3;
     xbar = c.xbar_inputs > 0 || c.xbar_outputs > 0;
     Ci = c.xbar_inputs > 0 ? c.xbar_inputs : C;
     Co = c.xbar_outputs > 0 ? c.xbar_outputs : C;
@@ -192,9 +204,9 @@ int Engine::init(const bfir_config_t &c)
     own_stream = true;
 
     const size_t cbuf = (size_t)N * rs;
-    // The reference's delay line has P slots, slot = blockcounter % P (brutefir.cpp:270,294). Here it has P + 1:
-    // the spectrum of block t+1 may then be written while block t's partition sum still needs X[t-P+1] (block
-    // pairs, look-ahead across blocks). Which slot a block lands in is not observable -- partition i is only
+    // The reference's delay line has P slots, slot = blockcounter % P (brutefir.cpp:270,294). Here it has P + 3:
+    // with P + 1 the spectrum of block t+1 can be written while block t's partition sum still needs X[t-P+1] (block
+    // pairs); the stage pipeline transforms the NEXT pair (t+2, t+3) while the sum of (t, t+1) runs, two more. Which slot a block lands in is not observable -- partition i is only
     // read once procblocks says the slot has been written since the last reset.
     BFIR_CUDA(cudaMalloc(&fdl, cbuf * Pslots * Ct));
     BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * Pslots * Ct, stream));                                      // brutefir.cpp:768-769
@@ -211,8 +223,13 @@ int Engine::init(const bfir_config_t &c)
     fft_r0 = rfft_choose_r0(rs, log2m, Ct);
     if (const char *env = getenv("BFIR_GRAPHS")) graphs_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_LOOKAHEAD")) lookahead_enabled = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_STAGED")) staged_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
+    BFIR_CUDA(cudaStreamCreateWithFlags(&sp_fwd, cudaStreamNonBlocking));
+    BFIR_CUDA(cudaStreamCreateWithFlags(&sp_inv, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++)
+        for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k] }) BFIR_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     BFIR_CUDA(cudaStreamCreateWithFlags(&tail_stream, cudaStreamNonBlocking));
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) BFIR_CUDA(cudaEventCreateWithFlags(&tail_done[g], cudaEventDisableTiming));
     BFIR_CUDA(cudaEventCreateWithFlags(&tail_join_ev, cudaEventDisableTiming));
@@ -313,6 +330,11 @@ void Engine::destroy()
     }
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
     if (out_done) { cudaEventDestroy(out_done); out_done = nullptr; }
+    for (cudaStream_t *st : { &sp_fwd, &sp_inv }) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
+    for (int k = 0; k < 2; k++) {
+        for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
+        for (int j = 0; j < 2; j++) if (sp_acc[k][j]) { cudaFree(sp_acc[k][j]); sp_acc[k][j] = nullptr; }
+    }
     if (tail_stream) { cudaStreamSynchronize(tail_stream); cudaStreamDestroy(tail_stream); tail_stream = nullptr; }
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) if (tail_done[g]) { cudaEventDestroy(tail_done[g]); tail_done[g] = nullptr; }
     if (tail_join_ev) { cudaEventDestroy(tail_join_ev); tail_join_ev = nullptr; }
@@ -539,6 +561,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
     f.in = d_inbuf; f.in_stride_x = (long long)L * Ci * in_sf.bytes;  // bytes per stream
     f.scale_in = 1.0; f.scale_out = in_sf.scale;                       // brutefir.cpp:273-277
     f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = Ci; f.n_channels = Cit; f.ch_base = s0 * Ci;
+    f.use_abs_block = use_abs ? 1 : 0; f.abs_block = host_blockcounter + (unsigned int)fwd_block_offset;
     f.state = state + g; f.n_slots = Pslots; f.n_parts = P; f.prev_parity = (host_blockcounter + (unsigned int)fwd_block_offset) & 1u; f.slot_offset = fwd_block_offset;
     if (!xbar) { f.out = fdl; f.out_stride_x = (long long)Pslots * N; f.out_stride_y = N; f.procblocks = procblocks; f.pb_inc = pb_inc; }
     else { f.out = xin; f.out_stride_x = N; f.out_stride_y = 0; f.procblocks = nullptr; f.pb_inc = nullptr; }
@@ -737,6 +760,82 @@ int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0
     return rc;
 }
 
+// One pair through the stage pipeline (one group). Pair k = blocks (t, t+1), t = host_blockcounter:
+//   forward stream:  after the pair sum k-2 (which still reads the slots these transforms overwrite): forward t, t+1
+//   engine's stream: after those transforms and after the inverse transforms of pair k-2 (same accumulators): pair sum
+//   inverse stream:  after the pair sum: inverse t, t+1 (these advance the device block counter)
+// The inputs must be complete when the call is made (nothing orders the forward stream after later work on the
+// engine's stream -- that is the point).
+int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1)
+{
+    int rc;
+    const size_t cbuf = (size_t)N * rs;
+    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) if (!sp_acc[k][j]) BFIR_CUDA(cudaMalloc(&sp_acc[k][j], cbuf * Ct));
+    if (!sp_open) {
+        if ((rc = close_async()) != BFIR_OK) return rc;
+        BFIR_CUDA(cudaEventRecord(fork_ev, stream));
+        BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, fork_ev, 0));
+        BFIR_CUDA(cudaStreamWaitEvent(sp_inv, fork_ev, 0));
+        for (int k = 0; k < 2; k++) { BFIR_CUDA(cudaEventRecord(sp_mac_done[k], stream)); BFIR_CUDA(cudaEventRecord(sp_inv_done[k], sp_inv)); }
+        sp_open = true;
+        sp_pairs = 0;
+    }
+    const int par = (int)(sp_pairs & 1ull);
+    cudaStream_t main_stream = stream;
+    tail_ready = false;
+    use_abs = true;
+    // forward transforms of both blocks on the forward stream (front_group launches on `stream`: redirect it)
+    BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, sp_mac_done[par], 0));
+    stream = sp_fwd;
+    prof_suppress = true;
+    rc = front_group(0, d_in0, nullptr, true);
+    fwd_block_offset = 1;
+    if (rc == BFIR_OK) rc = front_group(0, d_in1, nullptr, true);
+    fwd_block_offset = 0;
+    prof_suppress = false;
+    stream = main_stream;
+    if (rc != BFIR_OK) { use_abs = false; return rc; }
+    BFIR_CUDA(cudaEventRecord(sp_fwd_done[par], sp_fwd));
+    // pair sum on the engine's stream
+    BFIR_CUDA(cudaStreamWaitEvent(stream, sp_fwd_done[par], 0));
+    BFIR_CUDA(cudaStreamWaitEvent(stream, sp_inv_done[par], 0));
+    prof(0);
+    prof(1);   // profiling: only the pair sum's interval (1 -> 2) means anything in this mode
+    MacArgs m = {};
+    m.fdl = fdl; m.coeffs = coeffs; m.acc = sp_acc[par][0]; m.acc_next = sp_acc[par][1];
+    m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
+    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state; m.ch_base = 0;
+    m.use_abs_block = 1; m.abs_block = host_blockcounter;
+    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), Ct);
+    mac_kernel_t mk = rs == 4 ? mac_pair_kernel_for_split<float>(mac_split) : mac_pair_kernel_for_split<double>(mac_split);
+    mk<<<grid, 256, 0, stream>>>(m);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    prof(2);
+    prof(3);
+    if (pidx < pcap) pidx++;
+    BFIR_CUDA(cudaEventRecord(sp_mac_done[par], stream));
+    // inverse transforms on the inverse stream
+    BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
+    stream = sp_inv;
+    prof_suppress = true;
+    acc_override = sp_acc[par][0];
+    rc = back_group(0, d_out0);
+    acc_override = sp_acc[par][1];
+    if (rc == BFIR_OK) rc = back_group(0, d_out1);
+    acc_override = nullptr;
+    prof_suppress = false;
+    stream = main_stream;
+    use_abs = false;
+    if (rc != BFIR_OK) return rc;
+    BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
+    sp_pairs++;
+    finish_block();
+    finish_block();
+    return BFIR_OK;
+}
+
 // two consecutive blocks on device buffers. Falls back to two single-block steps while the delay line is still
 // filling, on a partition shard and with a pending filter swap.
 int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined)
@@ -747,7 +846,9 @@ int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, voi
         if (rc == BFIR_OK) rc = pipelined ? enqueue_block_pipelined(d_in1, d_out1) : enqueue_block(d_in1, d_out1);
         return rc;
     }
+    if (pipelined && n_groups == 1 && !xbar && staged_enabled) return staged_pair(d_in0, d_in1, d_out0, d_out1);
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, (size_t)N * rs * Ct));
+    if ((rc = close_staged()) != BFIR_OK) return rc;
     if (!pipelined) { if ((rc = close_async()) != BFIR_OK) return rc; }
     if (!async_open) {
         if ((rc = join_tail()) != BFIR_OK || (rc = fork()) != BFIR_OK) return rc;
@@ -796,7 +897,8 @@ int Engine::enqueue_block(const void *d_inbuf, void *d_outbuf)
 // block t starts block t+1 while others still work on t); close_async() joins
 int Engine::enqueue_block_pipelined(const void *d_inbuf, void *d_outbuf)
 {
-    int rc = BFIR_OK;
+    int rc = close_staged();
+    if (rc != BFIR_OK) return rc;
     if (!async_open) {
         if ((rc = join_tail()) != BFIR_OK || (rc = fork()) != BFIR_OK) return rc;
         async_open = n_groups > 1;
@@ -892,10 +994,23 @@ int Engine::join_tail()
     return BFIR_OK;
 }
 
+// the engine's stream is ordered after the side streams of the stage pipeline
+int Engine::close_staged()
+{
+    if (!sp_open) return BFIR_OK;
+    sp_open = false;
+    BFIR_CUDA(cudaEventRecord(sp_fwd_done[0], sp_fwd));
+    BFIR_CUDA(cudaStreamWaitEvent(stream, sp_fwd_done[0], 0));
+    BFIR_CUDA(cudaEventRecord(sp_inv_done[0], sp_inv));
+    BFIR_CUDA(cudaStreamWaitEvent(stream, sp_inv_done[0], 0));
+    return BFIR_OK;
+}
+
 int Engine::close_async()
 {
     int trc = join_tail();
     if (trc != BFIR_OK) return trc;
+    if ((trc = close_staged()) != BFIR_OK) return trc;
     if (!async_open) return BFIR_OK;
     async_open = false;
     if (async_copies) { // the output copies are the last link of every group's chain
@@ -1038,7 +1153,7 @@ int Engine::wait_ticket(long long t)
 
 int Engine::run_host(const void *inbuf, void *outbuf)
 {
-    if (async_open) { const int arc = close_async(); if (arc != BFIR_OK) return arc; }
+    if (async_open || sp_open) { const int arc = close_async(); if (arc != BFIR_OK) return arc; }
     const bool use_tail = tail_ready && lookahead_ok();   // acc already holds partitions 1 .. P-1 of this block
     const bool swap_block = xfade_pending;                // filters are being swapped: more swaps may follow, no look-ahead
     tail_ready = false;

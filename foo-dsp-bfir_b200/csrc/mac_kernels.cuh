@@ -30,6 +30,8 @@ struct MacArgs {
     int block_offset;        // 0: blockcounter is the current block; used by tests
     int ch_base;             // first channel of this launch (channel-group pipelining)
     void *acc_next;          // pair kernel: accumulated spectrum of block t+1, [channels][N]
+    int use_abs_block;       // 1: block index t = abs_block, given by the host (stage pipeline) instead of the device counter
+    unsigned int abs_block;
     int procblocks_bias;     // 1: look-ahead launch for the NEXT block, whose forward transform has not counted itself yet
     PeerPush push;           // enabled: partial sums go to the owner rank's receive buffer (fused reduce)
 };
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256) partition_mac_pair_kernel(const MacArgs a
     const int g = blockIdx.x * GPC + gl;
     const int ch = blockIdx.y + a.ch_base;
     const bool active = g * 8 < a.N;
-    const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
+    const unsigned int t = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.block_offset;
     const int peff = min(a.coeff_blocks[ch], a.n_parts);
     const int cs = (peff + SPLIT - 1) / SPLIT;
     const int i0 = slice * cs, i1 = min(peff, i0 + cs);

@@ -72,12 +72,20 @@ struct FwdArgs {
     int n_slots;             // delay-line slots per channel (the engine keeps one more than partitions)
     int n_parts;             // filter partitions: procblocks counts up to this (brutefir.cpp:265-268)
     int slot_offset;         // 1: the second block of a pair, transformed before the first one has been counted
+    int use_abs_block;       // 1: the block index is abs_block, given by the host (stage pipeline: the device counter lags behind)
+    unsigned int abs_block;
     int *procblocks;         // [channels], brutefir.cpp:265-268
     unsigned char *pb_inc;   // [channels], 1 when procblocks was incremented by this launch
     // IN_COEFF
     int coeff_len;           // valid coefficients per channel
     int *nonfinite;          // set to 1 when a scaled coefficient is NaN/Inf (fftw_convolver.cpp:493-497)
 };
+
+// index of the block a forward launch transforms
+template <class Dummy> BFIR_HD unsigned int fwd_block(const FwdArgs &a)
+{
+    return a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.slot_offset;
+}
 
 struct InvArgs {
     int in_layout, out_mode;
@@ -223,7 +231,7 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], con
     }
     if (a.in_mode == IN_COEFF && bad) *a.nonfinite = 1;
     if (a.in_mode == IN_RAW_PREV && a.state != NULL && t == 0 && r == 0 && by == 0 && bx == a.ch_base)
-        const_cast<EngineState *>(a.state)->cur_slot = (a.state->blockcounter + (unsigned int)a.slot_offset) % (unsigned int)a.n_slots;
+        const_cast<EngineState *>(a.state)->cur_slot = fwd_block<int>(a) % (unsigned int)a.n_slots;
     if (a.in_mode == IN_RAW_PREV && t == 0 && r == 0 && a.procblocks != NULL) { // brutefir.cpp:265-268
         const int pb = a.procblocks[bx];
         const bool inc = pb < a.n_parts;
@@ -240,7 +248,7 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
     constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, M = MS * R0, N = 2 * M;
     typedef cpx<T> C;
     long long off = bx * a.out_stride_x + by * a.out_stride_y;
-    if (a.state != NULL) off += (long long)((a.state->blockcounter + (unsigned int)a.slot_offset) % (unsigned int)a.n_slots) * a.out_stride_y;
+    if (a.state != NULL) off += (long long)(fwd_block<int>(a) % (unsigned int)a.n_slots) * a.out_stride_y;
     T *out = (T *)a.out + off;
     const T sc = (T)a.scale_out;
     const C wbase = tw[(R0 * t + r) << tw_shift_n];   // W_N^k of i = 0; the thread's bins are N/(2E) apart

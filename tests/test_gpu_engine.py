@@ -679,3 +679,54 @@ def test_cfg1_block_pairs_vs_oracle(pkg, oracle):
                 for c in range(C):
                     assert rel_rms(got[:, c], want[:, c]) < 1e-12, (b + k, c)
     assert g.blockcounter() == o.blockcounter() == nblk
+
+
+@pytest.mark.parametrize("rs,out_fmt,dither", [(8, 10, False), (4, 8, False), (4, 2, True)])
+def test_stage_pipeline_equals_single_blocks(pkg, rs, out_fmt, dither):
+    """bfir_run_device_pair(pipelined) on a one-group engine runs the stage pipeline (forward transforms of the next
+    pair under the pair sum, inverse transforms of the previous pair behind it, block index from the host): same
+    output as block by block, through mode changes (join, synchronous run, plain pair) in between."""
+    import torch
+    L, P, C, S = 512, 5, 2, 4
+    in_fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt = np.float32 if rs == 4 else np.float64
+    nb = pkg.FORMAT_BYTES[out_fmt]
+    h = [decay_filter(c, L * P) for c in range(C * S)]
+    single = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, dither, n_streams=S, n_groups=1)
+    staged = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, dither, n_streams=S, n_groups=1)
+    assert single.set_coeff(h, P) == 0 and staged.set_coeff(h, P) == 0
+    nblk = 40
+    x = white_noise(33, nblk * L, C * S).astype(dt)
+    blocks = [np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2)).ravel() for b in range(nblk)]
+    d_in = [torch.from_numpy(b).cuda() for b in blocks]
+    n_out = S * L * C * nb
+    out_s = [torch.zeros(n_out, dtype=torch.uint8, device="cuda") for _ in range(nblk)]
+    out_t = [torch.zeros(n_out, dtype=torch.uint8, device="cuda") for _ in range(nblk)]
+    torch.cuda.synchronize()
+    for b in range(nblk):
+        single.run_device(d_in[b], out_s[b])
+    b = 0
+    while b < nblk:
+        if b == 20:                                  # a plain pair and a synchronous block in the middle
+            staged.run_device_pair(d_in[b], d_in[b + 1], out_t[b], out_t[b + 1], pipelined=False)
+            b += 2
+            rc, o = staged.run(blocks[b].view(np.uint8))
+            assert rc == 0
+            out_t[b].copy_(torch.from_numpy(o))
+            b += 1
+            staged.run_device(d_in[b], out_t[b])
+            b += 1
+            continue
+        staged.run_device_pair(d_in[b], d_in[b + 1], out_t[b], out_t[b + 1], pipelined=True)
+        if b == 12:
+            staged.join()
+        b += 2
+    assert single.sync() == 0 and staged.sync() == 0
+    assert single.blockcounter() == staged.blockcounter() == nblk
+    for b in range(nblk):
+        a, t = out_s[b].cpu().numpy(), out_t[b].cpu().numpy()
+        if out_fmt in (8, 10):
+            assert rel_rms(t.view(dt), a.view(dt)) < (2e-6 if rs == 4 else 1e-13), b
+        else:
+            dd = np.abs(decode_raw(a, out_fmt, C).ravel().astype(np.float64) - decode_raw(t, out_fmt, C).ravel())
+            assert dd.max() <= 4 and dd.mean() < 0.5, (b, dd.max(), dd.mean())
