@@ -123,6 +123,7 @@ struct Engine {
     unsigned long long sp_pairs = 0; // pairs queued since the pipeline was opened
     bool sp_open = false;
     bool staged_enabled = true;     // BFIR_STAGED=0 switches the stage pipeline off
+    bool whole_copies = false;      // BFIR_WHOLE_COPIES=1: the pair host path moves whole blocks on one copy stream each way
     bool use_abs = false;           // front_group / pair sum: pass host_blockcounter (+ offset) as the block index
     int staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1);
     int close_staged();
@@ -224,6 +225,7 @@ int Engine::init(const bfir_config_t &c)
     if (const char *env = getenv("BFIR_GRAPHS")) graphs_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_LOOKAHEAD")) lookahead_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGED")) staged_enabled = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_WHOLE_COPIES")) whole_copies = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
     BFIR_CUDA(cudaStreamCreateWithFlags(&sp_fwd, cudaStreamNonBlocking));
@@ -1107,6 +1109,39 @@ long long Engine::run_host_async_pair(const void *in0, const void *in1, void *ou
     const int sc = stage_count >= 2 ? (stage_count & ~1) : 2;   // pairs need an even number of slots, at least two
     const int k0 = (int)(stage_next % (unsigned long long)sc), k1 = (int)((stage_next + 1) % (unsigned long long)sc);
     stage_next += 2;
+    if (whole_copies && n_groups > 1) { // one copy stream each way moves whole blocks; the groups only run kernels
+        cudaStream_t h2d = groups[0].h2d, d2h = groups[0].d2h;
+        for (int g = 0; g < n_groups; g++) {
+            BFIR_CUDA(cudaStreamWaitEvent(h2d, groups[g].in_free[k0], 0));
+            BFIR_CUDA(cudaStreamWaitEvent(h2d, groups[g].in_free[k1], 0));
+        }
+        BFIR_CUDA(cudaMemcpyAsync(stage_in[k0], in0, in_bytes, cudaMemcpyHostToDevice, h2d));
+        BFIR_CUDA(cudaMemcpyAsync(stage_in[k1], in1, in_bytes, cudaMemcpyHostToDevice, h2d));
+        BFIR_CUDA(cudaEventRecord(groups[0].in_ready, h2d));
+        for (int g = 0; g < n_groups; g++) {
+            Group &grp = groups[g];
+            cudaStream_t st = gstream(g);
+            BFIR_CUDA(cudaStreamWaitEvent(st, groups[0].in_ready, 0));
+            BFIR_CUDA(cudaStreamWaitEvent(st, groups[0].out_free[k0], 0));
+            if ((rc = pair_group(g, stage_in[k0], stage_in[k1], stage_out[k0], stage_out[k1], &grp.in_free[k1], &groups[0].out_free[k1])) != BFIR_OK) return rc;
+            BFIR_CUDA(cudaEventRecord(grp.in_free[k0], st));
+            BFIR_CUDA(cudaEventRecord(grp.out_ready, st));
+            BFIR_CUDA(cudaStreamWaitEvent(d2h, grp.out_ready, 0));
+        }
+        BFIR_CUDA(cudaMemcpyAsync(out0, stage_out[k0], out_bytes, cudaMemcpyDeviceToHost, d2h));
+        BFIR_CUDA(cudaEventRecord(groups[0].out_free[k0], d2h));
+        BFIR_CUDA(cudaMemcpyAsync(out1, stage_out[k1], out_bytes, cudaMemcpyDeviceToHost, d2h));
+        BFIR_CUDA(cudaEventRecord(groups[0].out_free[k1], d2h));
+        for (int slot : { slot0, slot1 }) {
+            if (ticket_ev[slot][0] == nullptr) BFIR_CUDA(cudaEventCreateWithFlags(&ticket_ev[slot][0], cudaEventDisableTiming));
+            BFIR_CUDA(cudaEventRecord(ticket_ev[slot][0], d2h));
+            for (int g = 1; g < n_groups; g++) if (ticket_ev[slot][g]) { cudaEventDestroy(ticket_ev[slot][g]); ticket_ev[slot][g] = nullptr; }
+        }
+        finish_block();
+        finish_block();
+        next_ticket += 2;
+        return next_ticket - 1;
+    }
     for (int g = 0; g < n_groups; g++) {
         Group &grp = groups[g];
         const size_t s0 = n_groups == 1 ? 0 : (size_t)grp.s0, ns = n_groups == 1 ? (size_t)S : (size_t)(grp.s1 - grp.s0);
