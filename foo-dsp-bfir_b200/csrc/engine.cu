@@ -92,7 +92,7 @@ struct Engine {
     // throughput variant of run (bfir_run_async / bfir_wait): block steps are queued on the group streams
     // without joining them, so the copies and kernels of consecutive blocks overlap; a ring of events
     // (one per group) marks the completion of each queued step
-    static const int kMaxInflight = 8;
+    static const int kMaxInflight = 16;
     cudaEvent_t ticket_ev[kMaxInflight][BFIR_MAX_GROUPS] = {};
     long long next_ticket = 0, done_ticket = 0;    // tickets < done_ticket are known to be complete
     bool async_open = false;                        // group streams hold work the engine's stream has not joined

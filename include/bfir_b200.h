@@ -148,7 +148,7 @@ int bfir_sync(bfir_engine *e);
  * synchronous, brutefir.cpp:245-343). Queues H2D -> block step -> D2H of one block on the stream groups and
  * returns a ticket (>= 0) without waiting, so the copies and kernels of consecutive blocks overlap.
  * inbuf/outbuf are PINNED host buffers laid out as for bfir_run; they must stay untouched until
- * bfir_wait(ticket) (or bfir_sync) has returned. At most 8 steps are in flight: a ninth call first waits
+ * bfir_wait(ticket) (or bfir_sync) has returned. At most 16 steps are in flight: a seventeenth call first waits
  * for the oldest. bfir_wait returns when the step with that ticket and all earlier ones have delivered
  * their output; BFIR_ERR_NONFINITE if a NaN/Inf probe fired in any block since the last wait/sync (all
  * queued work is drained first; unlike bfir_run the block counter is not rolled back). Any other call
