@@ -74,6 +74,7 @@ API = [
     ("bfir_join", _ci, [_vp]),
     ("bfir_run_device_pair", _ci, [_vp, _vp, _vp, _vp, _vp, _ci]),
     ("bfir_run_async_pair", ctypes.c_longlong, [_vp, _vp, _vp, _vp, _vp]),
+    ("bfir_run_device_quad", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -304,6 +305,12 @@ class Brutefir:
     def run_device_pair(self, d_in0, d_in1, d_out0, d_out1, pipelined=False):
         """Two consecutive blocks with one partition-sum launch (offline / pipelined callers)."""
         _check(self.lib.bfir_run_device_pair(self.h, _ptr(d_in0), _ptr(d_in1), _ptr(d_out0), _ptr(d_out1), int(bool(pipelined))))
+
+    def run_device_quad(self, d_ins, d_outs):
+        """Four consecutive blocks with one partition-sum launch (single-precision engines; others run two pairs)."""
+        a = (_vp * 4)(*[_ptr(x) for x in d_ins])
+        b = (_vp * 4)(*[_ptr(x) for x in d_outs])
+        _check(self.lib.bfir_run_device_quad(self.h, a, b))
 
     def run_async_pair(self, in0, in1, out0, out1):
         """Two consecutive blocks of PINNED host buffers; returns the ticket of the second block."""

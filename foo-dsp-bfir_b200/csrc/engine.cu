@@ -133,6 +133,9 @@ struct Engine {
         return !peer.enabled && part_begin == 0 && part_count == P && P >= 2 && !xfade_pending &&
                host_blockcounter >= (unsigned int)P;
     }
+    void *acc_quad[2] = {};         // accumulated spectra of blocks 3 and 4 of a quad (single precision)
+    int quad_group(int g, const void *const d_in[4], void *const d_out[4]);
+    int enqueue_quad(const void *const d_in[4], void *const d_out[4]);
     int pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, cudaEvent_t *input_consumed, cudaEvent_t *output_free);
     int enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined);
     long long run_host_async_pair(const void *in0, const void *in1, void *out0, void *out1);
@@ -348,9 +351,9 @@ void Engine::destroy()
     if (recv) { cudaFree(recv); recv = nullptr; }
     for (int k = 1; k < kStage; k++) { if (stage_in[k]) cudaFree(stage_in[k]); if (stage_out[k]) cudaFree(stage_out[k]); stage_in[k] = stage_out[k] = nullptr; }
     stage_in[0] = stage_out[0] = nullptr;
-    void *bufs[] = { acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
+    void *bufs[] = { acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
-    acc_pair = nullptr;
+    acc_pair = nullptr; acc_quad[0] = acc_quad[1] = nullptr;
     fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
     state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
@@ -836,6 +839,61 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
     finish_block();
     finish_block();
     return BFIR_OK;
+}
+
+// four consecutive blocks of one group with ONE partition-sum launch (single precision): see partition_mac_multi_kernel
+int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
+{
+    const Group &grp = groups[g];
+    const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
+    int rc = BFIR_OK;
+    if (g == 0) prof(0);
+    prof_suppress = true;
+    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(g, d_in[b], nullptr, true); }
+    fwd_block_offset = 0;
+    prof_suppress = false;
+    if (rc != BFIR_OK) return rc;
+    if (g == 0) prof(1);
+    tail_ready = false;
+    MacArgs m = {};
+    m.fdl = fdl; m.coeffs = coeffs;
+    m.acc_multi[0] = acc; m.acc_multi[1] = acc_pair; m.acc_multi[2] = acc_quad[0]; m.acc_multi[3] = acc_quad[1];
+    m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
+    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
+    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), ns * C);
+    mac_kernel_t mk = mac_quad_kernel_for_split(mac_split);
+    mk<<<grid, 256, 0, gstream(g)>>>(m);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    if (g == 0) prof(2);
+    prof_suppress = true;
+    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { acc_override = b == 0 ? nullptr : m.acc_multi[b]; rc = back_group(g, d_out[b]); }
+    acc_override = nullptr;
+    prof_suppress = false;
+    if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+    return rc;
+}
+
+// four consecutive blocks on device buffers (joined like bfir_run_device). Single precision, steady state, no crossbar;
+// otherwise two pair steps.
+int Engine::enqueue_quad(const void *const d_in[4], void *const d_out[4])
+{
+    int rc;
+    if (!pair_ok() || rs != 4 || xbar) {
+        rc = enqueue_pair(d_in[0], d_in[1], d_out[0], d_out[1], false);
+        if (rc == BFIR_OK) rc = enqueue_pair(d_in[2], d_in[3], d_out[2], d_out[3], false);
+        return rc;
+    }
+    const size_t cbuf = (size_t)N * rs;
+    if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
+    for (int k = 0; k < 2; k++) if (!acc_quad[k]) BFIR_CUDA(cudaMalloc(&acc_quad[k], cbuf * Ct));
+    if ((rc = close_async()) != BFIR_OK) return rc;
+    if ((rc = fork()) != BFIR_OK) return rc;
+    for (int g = 0; g < n_groups && rc == BFIR_OK; g++) rc = quad_group(g, d_in, d_out);
+    for (int b = 0; b < 4; b++) finish_block();
+    if (rc == BFIR_OK) rc = join();
+    return rc;
 }
 
 // two consecutive blocks on device buffers. Falls back to two single-block steps while the delay line is still
@@ -1352,6 +1410,15 @@ int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, v
     if (rc != BFIR_OK) return rc;
     if (d_in0 == nullptr || d_in1 == nullptr || d_out0 == nullptr || d_out1 == nullptr) return BFIR_ERR_INVALID;
     return e->impl.enqueue_pair(d_in0, d_in1, d_out0, d_out1, pipelined != 0);
+}
+
+int bfir_run_device_quad(bfir_engine *e, const void *const d_in[4], void *const d_out[4])
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_in == nullptr || d_out == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 4; b++) if (d_in[b] == nullptr || d_out[b] == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.enqueue_quad(d_in, d_out);
 }
 
 long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, void *out0, void *out1)

@@ -30,6 +30,7 @@ struct MacArgs {
     int block_offset;        // 0: blockcounter is the current block; used by tests
     int ch_base;             // first channel of this launch (channel-group pipelining)
     void *acc_next;          // pair kernel: accumulated spectrum of block t+1, [channels][N]
+    void *acc_multi[4];      // multi kernel: accumulated spectra of blocks t .. t+NB-1
     int use_abs_block;       // 1: block index t = abs_block, given by the host (stage pipeline) instead of the device counter
     unsigned int abs_block;
     int procblocks_bias;     // 1: look-ahead launch for the NEXT block, whose forward transform has not counted itself yet
@@ -236,7 +237,94 @@ __global__ void __launch_bounds__(256) partition_mac_pair_kernel(const MacArgs a
     }
 }
 
+// NB consecutive blocks t .. t+NB-1 in one pass (the pair kernel generalised; single precision has the registers
+// for NB = 4): a window of NB delay-line spectra slides over a contiguous run of partitions, so every partition
+// costs one coefficient and one delay-line load for NB multiply-accumulates: per channel
+// (2 P_eff + (NB-1) SPLIT + NB) N rs bytes for NB blocks instead of NB (2 P_eff + 1) N rs.
+// Block t+b uses X[t+b-i] at partition i; all NB forward transforms have run (needs P + NB - 1 delay-line slots).
+template <class T, int NB, int SPLIT>
+__global__ void __launch_bounds__(256) partition_mac_multi_kernel(const MacArgs a)
+{
+    constexpr int GPC = 256 / SPLIT;
+    const int slice = threadIdx.x / GPC, gl = threadIdx.x - slice * GPC;
+    const int g = blockIdx.x * GPC + gl;
+    const int ch = blockIdx.y + a.ch_base;
+    const bool active = g * 8 < a.N;
+    const unsigned int t = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.block_offset;
+    const int peff = min(a.coeff_blocks[ch], a.n_parts);
+    const int cs = (peff + SPLIT - 1) / SPLIT;
+    const int i0 = slice * cs, i1 = min(peff, i0 + cs);
+    const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
+    const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
+    const unsigned int P = (unsigned int)a.n_slots;
+
+    T acc[NB][8];
+    T dc[NB], ny[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        dc[b] = (T)0; ny[b] = (T)0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[b][j] = (T)0;
+    }
+    if (active && i0 < i1) {
+        T x[NB][8];                                                // x[b] = X[t+b-i]: block t+b's operand at partition i
+#pragma unroll
+        for (int b = 1; b < NB; b++) ld8(fdl + (long long)((t + (unsigned int)b - (unsigned int)i0) % P) * a.N, x[b]);
+#pragma unroll 2
+        for (int i = i0; i < i1; i++) {
+            T c[8];
+            ld8(fdl + (long long)((t - (unsigned int)i) % P) * a.N, x[0]);
+            ld8(cf + (long long)i * a.N, c);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                if (g == 0) { dc[b] = fma(x[b][0], c[0], dc[b]); ny[b] = fma(x[b][4], c[4], ny[b]); }
+                mac8<T>(acc[b], x[b], c);
+            }
+#pragma unroll
+            for (int b = NB - 1; b > 0; b--)                       // next partition: block t+b needs what block t+b-1 just used
+#pragma unroll
+                for (int j = 0; j < 8; j++) x[b][j] = x[b - 1][j];
+        }
+        if (g == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) { acc[b][0] = dc[b]; acc[b][4] = ny[b]; }
+        }
+    }
+    if (SPLIT > 1) {
+        __shared__ T red[SPLIT > 1 ? (SPLIT - 1) * GPC * 8 * NB : 1];
+        if (slice > 0) {
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) red[((slice - 1) * 8 * NB + b * 8 + j) * GPC + gl] = acc[b][j];
+        }
+        __syncthreads();
+        if (slice > 0) return;
+#pragma unroll
+        for (int s = 1; s < SPLIT; s++)
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[b][j] += red[((s - 1) * 8 * NB + b * 8 + j) * GPC + gl];
+    }
+    if (active) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) st8((T *)a.acc_multi[b] + (long long)ch * a.N + (long long)g * 8, acc[b]);
+    }
+}
+
 typedef void (*mac_kernel_t)(const MacArgs);
+// four blocks per launch, single precision (shared memory: (SPLIT-1) * 256/SPLIT * 32 floats <= 32 KB)
+inline mac_kernel_t mac_quad_kernel_for_split(int split)
+{
+    switch (split) {
+    case 1: return partition_mac_multi_kernel<float, 4, 1>;
+    case 2: return partition_mac_multi_kernel<float, 4, 2>;
+    case 4: return partition_mac_multi_kernel<float, 4, 4>;
+    case 8: return partition_mac_multi_kernel<float, 4, 8>;
+    default: return partition_mac_multi_kernel<float, 4, 16>;
+    }
+}
 template <class T> inline mac_kernel_t mac_pair_kernel_for_split(int split)
 {
     constexpr int U = sizeof(T) == 8 ? 2 : 4;

@@ -173,6 +173,10 @@ int bfir_join(bfir_engine *e);
  * bfir_run_async_pair: pinned host buffers, returns the ticket of the SECOND block (waiting on it covers both). */
 int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, int pipelined);
 long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, void *out0, void *out1);
+/* Four consecutive blocks with one partition-sum launch, single-precision engines (their kernels have the registers
+ * for four accumulators): per channel (2P + 3 split + 4) N realsize bytes for four blocks instead of 4 (2P + 1) N realsize.
+ * Device buffers, joined like bfir_run_device. Other engines, and the cases listed above, run two pairs. */
+int bfir_run_device_quad(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 
 /* brutefir::reset (brutefir.cpp:347-367): zeroes counters and overflow statistics, NOT the buffers */
 int bfir_reset(bfir_engine *e);

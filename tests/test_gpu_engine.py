@@ -730,3 +730,32 @@ def test_stage_pipeline_equals_single_blocks(pkg, rs, out_fmt, dither):
         else:
             dd = np.abs(decode_raw(a, out_fmt, C).ravel().astype(np.float64) - decode_raw(t, out_fmt, C).ravel())
             assert dd.max() <= 4 and dd.mean() < 0.5, (b, dd.max(), dd.mean())
+
+
+@pytest.mark.parametrize("rs,groups,P", [(4, 1, 6), (4, 3, 9), (8, 2, 5), (4, 2, 2)])
+def test_block_quads_equal_single_blocks(pkg, rs, groups, P):
+    """bfir_run_device_quad: four blocks per partition-sum launch on single-precision engines (double: two pairs);
+    same output as block by block up to the summation order, from the first block on (fall-back while filling)."""
+    import torch
+    L, C, S = 256, 2, 3
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt, tdt = (np.float32, torch.float32) if rs == 4 else (np.float64, torch.float64)
+    h = [decay_filter(c, L * P - 3) for c in range(C * S)]
+    single = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=1)
+    quad = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=groups)
+    assert single.set_coeff(h, P) == 0 and quad.set_coeff(h, P) == 0
+    nblk = 28
+    x = white_noise(61, nblk * L, C * S).astype(dt)
+    d_in = [torch.from_numpy(np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2)).ravel()).cuda() for b in range(nblk)]
+    n = S * L * C
+    out_s = [torch.zeros(n, dtype=tdt, device="cuda") for _ in range(nblk)]
+    out_q = [torch.zeros(n, dtype=tdt, device="cuda") for _ in range(nblk)]
+    torch.cuda.synchronize()
+    for b in range(nblk):
+        single.run_device(d_in[b], out_s[b])
+    for b in range(0, nblk, 4):
+        quad.run_device_quad(d_in[b:b + 4], out_q[b:b + 4])
+    assert single.sync() == 0 and quad.sync() == 0
+    assert single.blockcounter() == quad.blockcounter() == nblk
+    for b in range(nblk):
+        assert rel_rms(out_q[b].cpu().numpy(), out_s[b].cpu().numpy()) < (2e-6 if rs == 4 else 1e-13), b

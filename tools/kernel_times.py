@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--streams", type=int, default=16)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--quads", action="store_true", help="four blocks per call (bfir_run_device_quad, single precision)")
     ap.add_argument("--pairs", action="store_true", help="two blocks per call (bfir_run_device_pair); times are per PAIR then")
     a = ap.parse_args()
     import torch
@@ -47,7 +48,14 @@ def main():
     for b in range(a.P + 5):
         eng.run_device(d_in[b % 4], d_out)
     assert eng.sync() == 0
-    if a.pairs:
+    if a.quads:
+        outs = [d_out] + [torch.empty_like(d_out) for _ in range(3)]
+        eng.run_device_quad(d_in, outs)
+        assert eng.sync() == 0
+        eng.set_profiling(a.steps // 4)
+        for b in range(0, a.steps, 4):
+            eng.run_device_quad(d_in, outs)
+    elif a.pairs:
         d_out2 = torch.empty_like(d_out)
         eng.run_device_pair(d_in[0], d_in[1], d_out, d_out2)
         assert eng.sync() == 0
@@ -60,7 +68,7 @@ def main():
             eng.run_device(d_in[b % 4], d_out)
     assert eng.sync() == 0
     prof, n = eng.get_profile()
-    per = 2 if a.pairs else 1                  # blocks per profiled entry
+    per = 4 if a.quads else (2 if a.pairs else 1)   # blocks per profiled entry
     ms = {k: v / n / per for k, v in prof.items()}   # per block
     step = sum(ms.values())
     b_mac = (2 * a.P + 1) * 2 * a.L * a.realsize * Ct

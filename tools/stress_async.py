@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised schedule stress of the pipelined entry points against the one-block device path: for random
 geometries, every block goes through a randomly chosen call (bfir_run, bfir_run_device, bfir_run_device_pipelined,
-bfir_run_device_pair, bfir_run_async, bfir_run_async_pair) with random waits in between; outputs must match the
+bfir_run_device_pair, bfir_run_device_quad, bfir_run_async, bfir_run_async_pair) with random waits in between; outputs must match the
 reference engine (one stream, bfir_run_device) to rounding.   python tools/stress_async.py [seconds]"""
 import importlib, os, sys, time
 import numpy as np
@@ -40,9 +40,11 @@ while time.time() < t_end:
     assert ref.sync() == 0
     b, tickets, log = 0, [], []
     while b < nblk:
-        op = int(rng.integers(0, 6))
+        op = int(rng.integers(0, 7))
         if op in (3, 5) and b + 1 >= nblk:
             op = 0
+        if op == 6 and b + 3 >= nblk:
+            op = 1
         log.append(op)
         if op == 0:
             rc, out = eng.run(blocks[b].view(np.uint8), got_h[b].numpy().view(np.uint8)); assert rc == 0; where[b] = "h"; b += 1
@@ -52,6 +54,11 @@ while time.time() < t_end:
             eng.run_device_pipelined(d_in[b], got_d[b]); where[b] = "d"; b += 1
         elif op == 3:
             eng.run_device_pair(d_in[b], d_in[b + 1], got_d[b], got_d[b + 1], pipelined=bool(rng.integers(0, 2))); where[b] = where[b + 1] = "d"; b += 2
+        elif op == 6:
+            eng.run_device_quad(d_in[b:b + 4], got_d[b:b + 4])
+            for k in range(4):
+                where[b + k] = "d"
+            b += 4
         elif op == 4:
             tickets.append(eng.run_async(pin_in[b].numpy(), got_h[b].numpy())); where[b] = "h"; b += 1
         else:
