@@ -124,6 +124,7 @@ struct Engine {
     bool sp_open = false;
     bool staged_enabled = true;     // BFIR_STAGED=0 switches the stage pipeline off
     bool whole_copies = false;      // BFIR_WHOLE_COPIES=1: the pair host path moves whole blocks on one copy stream each way
+    cudaStream_t stage_stream = nullptr; // front_group / back_group launch here instead of the group's stream (stage pipeline)
     bool use_abs = false;           // front_group / pair sum: pass host_blockcounter (+ offset) as the block index
     int staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1);
     int close_staged();
@@ -560,7 +561,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
     const Group &grp = groups[g];
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
     const int nch = ns * C, c0 = s0 * C;
-    cudaStream_t st = gstream(g);
+    cudaStream_t st = stage_stream ? stage_stream : gstream(g);
     FwdArgs f = {};
     f.in_mode = IN_RAW_PREV; f.out_layout = LAYOUT_ORD;
     f.in = d_inbuf; f.in_stride_x = (long long)L * Ci * in_sf.bytes;  // bytes per stream
@@ -625,7 +626,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
     const Group &grp = groups[g];
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
     const int nch = ns * Co, c0 = s0 * Co;
-    cudaStream_t st = gstream(g);
+    cudaStream_t st = stage_stream ? stage_stream : gstream(g);
     if (peer.enabled) { // owner side: sum the source slots of the own channels, then the normal output stage on them
         void *dst = xbar ? yacc : acc;
         dim3 grid((N + 255) / 256, own_count);
@@ -786,19 +787,18 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
         sp_pairs = 0;
     }
     const int par = (int)(sp_pairs & 1ull);
-    cudaStream_t main_stream = stream;
     tail_ready = false;
     use_abs = true;
-    // forward transforms of both blocks on the forward stream (front_group launches on `stream`: redirect it)
+    // forward transforms of both blocks on the forward stream
     BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, sp_mac_done[par], 0));
-    stream = sp_fwd;
+    stage_stream = sp_fwd;
     prof_suppress = true;
     rc = front_group(0, d_in0, nullptr, true);
     fwd_block_offset = 1;
     if (rc == BFIR_OK) rc = front_group(0, d_in1, nullptr, true);
     fwd_block_offset = 0;
     prof_suppress = false;
-    stream = main_stream;
+    stage_stream = nullptr;
     if (rc != BFIR_OK) { use_abs = false; return rc; }
     BFIR_CUDA(cudaEventRecord(sp_fwd_done[par], sp_fwd));
     // pair sum on the engine's stream
@@ -823,7 +823,7 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
     BFIR_CUDA(cudaEventRecord(sp_mac_done[par], stream));
     // inverse transforms on the inverse stream
     BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
-    stream = sp_inv;
+    stage_stream = sp_inv;
     prof_suppress = true;
     acc_override = sp_acc[par][0];
     rc = back_group(0, d_out0);
@@ -831,7 +831,7 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
     if (rc == BFIR_OK) rc = back_group(0, d_out1);
     acc_override = nullptr;
     prof_suppress = false;
-    stream = main_stream;
+    stage_stream = nullptr;
     use_abs = false;
     if (rc != BFIR_OK) return rc;
     BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
