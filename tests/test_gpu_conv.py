@@ -5,7 +5,7 @@ north star states; the element-wise entry points are bit-exact."""
 import numpy as np
 import pytest
 
-from conftest import rel_rms, encode_raw, decode_raw
+from conftest import rel_rms, encode_raw, decode_raw, parity
 
 pytestmark = pytest.mark.gpu
 
@@ -102,7 +102,9 @@ def test_dirac_convolve(pkg, oracle, rs):
     g.convolver_mixnscale([bx2], xo, [1.0], pkg.MIXMODE_INPUT)
     g.convolver_convolve(xo, one, yo)
     g.convolver_mixnscale([yo], yh, [1.0], pkg.MIXMODE_OUTPUT)
-    assert rel_rms(g.get(yh), ref) < TOL[rs] * 10
+    # the same chain through the oracle; the (exact) dirac result is the truth both are measured against
+    via = o.mixnscale([o.convolve(o.mixnscale([x], [1.0], 1), o.coeffs2cbuf(np.array([1.0])))], [1.0], 3)
+    parity("dirac_vs_convolve_with_unit_coeff/rs%d" % rs, g.get(yh), via, TOL[rs], truth=ref)
 
 
 @pytest.mark.parametrize("L,rs", [(64, 4), (1024, 4), (1024, 8), (8192, 8), (16384, 4), (32768, 4), (16384, 8)])
@@ -138,10 +140,11 @@ def test_runtime_coeffs2cbuf(pkg, oracle, rs, L):
     assert rel_rms(got, o.coeffs2cbuf(h)) < TOL[rs]
 
 
-@pytest.mark.parametrize("rs,L", [(4, 1024), (8, 1024), (4, 32768), (8, 4096)])
+@pytest.mark.parametrize("rs,L", [(4, 1024), (8, 1024), (4, 4096), (4, 32768), (8, 4096)])
 def test_crossfade_inplace(pkg, oracle, rs, L):
     g = pkg.FftwConvolver(L, rs)
     o = oracle.Convolver(L, rs, kind="port" if rs == 8 else None)  # double: float-branch algorithm
+    o64 = oracle.Convolver(L, 8, kind="port")                      # float64 truth of the same chain
     rng = np.random.default_rng(11)
     x = rng.uniform(-1, 1, 2 * L).astype(g.dtype)
     new = o.convolve(o.mixnscale([o.time2freq(x)], [1.0], 1), o.coeffs2cbuf(rng.standard_normal(L)))
@@ -149,13 +152,17 @@ def test_crossfade_inplace(pkg, oracle, rs, L):
     bi, bx, bb = g.cbuf(new), g.cbuf(old), g.cbuf()
     g.convolver_crossfade_inplace(bi, bx, bb)
     ref = o.crossfade_inplace(new.copy(), old.copy(), o.cbuf())
-    assert rel_rms(g.get(bi), ref) < TOL[rs] * 2
+    truth = o64.crossfade_inplace(new.astype(np.float64), old.astype(np.float64), o64.cbuf()) if rs == 4 else None
+    parity("crossfade_inplace/rs%d/L%d" % (rs, L), g.get(bi), ref, TOL[rs], truth)
     # semantic check: IFFT of the result ramps old -> new over the first half
-    y = o.freq2time(o.mixnscale([g.get(bi)], [1.0], 3))[:L]
-    y_old = o.freq2time(o.mixnscale([old], [1.0], 3))[:L]
-    y_new = o.freq2time(o.mixnscale([new], [1.0], 3))[:L]
+    got64 = g.get(bi).astype(np.float64)
+    y = o64.freq2time(o64.mixnscale([got64], [1.0], 3))[:L]
+    y_old = o64.freq2time(o64.mixnscale([old.astype(np.float64)], [1.0], 3))[:L]
+    y_new = o64.freq2time(o64.mixnscale([new.astype(np.float64)], [1.0], 3))[:L]
     w = np.arange(L) / (L - 1)
-    assert rel_rms(y, y_old * (1 - w) + y_new * w) < 1e-4 if rs == 4 else 1e-10
+    ramp_err = rel_rms(y, y_old * (1 - w) + y_new * w)
+    print("crossfade ramp semantics rs%d L%d: %.3e" % (rs, L, ramp_err))
+    assert ramp_err < (1e-5 if rs == 4 else 1e-12)
 
 
 @pytest.mark.parametrize("rs", [4, 8])
@@ -171,8 +178,8 @@ def test_convolve_eval(pkg, oracle, rs):
         g.convolver_convolve_eval(bi, buf_g, bo)
         ref = o.convolve_eval(hc, buf_o)
         scale = 2 * L
-        assert rel_rms(g.get(bo) / scale, ref / scale) < TOL[rs] * 2
-        assert rel_rms(buf_g.download(g.dtype)[:L], buf_o[:L]) < TOL[rs] * 2
+        parity("convolve_eval/out/rs%d" % rs, g.get(bo) / scale, ref / scale, TOL[rs])
+        parity("convolve_eval/state/rs%d" % rs, buf_g.download(g.dtype)[:L], buf_o[:L], TOL[rs])
 
 
 FORMATS = list(range(1, 12))
@@ -296,12 +303,12 @@ def test_td_convolver(pkg, oracle, rs, n_coeffs):
         d = g.rawbuf(x)
         g.convolver_td_convolve(gt, d)
         ref = o.td_convolve(ot, x.copy())
-        assert rel_rms(d.download(g.dtype), ref) < TOL[rs] * 2
+        parity("td_convolve/rs%d/n%d" % (rs, n_coeffs), d.download(g.dtype), ref, TOL[rs])
         # and it is what it says: circular convolution of the block with the coefficients placed at blocklen
         hp = np.zeros(2 * bl)
         hp[bl:bl + n_coeffs] = h
         want = np.real(np.fft.ifft(np.fft.fft(x.astype(np.float64)) * np.fft.fft(hp)))
-        assert rel_rms(d.download(g.dtype), want) < TOL[rs] * 4
+        parity("td_convolve_vs_numpy/rs%d/n%d" % (rs, n_coeffs), d.download(g.dtype), want, TOL[rs])
     g.convolver_td_free(gt)
     o.td_free(ot)
 

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import rel_rms, white_noise
+from conftest import rel_rms, white_noise, parity, SwapChain
 
 pytestmark = pytest.mark.gpu
 BANDS = [20, 25, 31.5, 40, 50, 63, 80, 100, 125, 160, 200, 250, 315, 400, 500, 630, 800, 1000, 1250, 1600, 2000, 2500,
@@ -64,43 +64,50 @@ def test_fewer_bands_and_invalid_sizes(pkg, oracle):
         eq.generate(list(range(1, 33)), [0.0] * 32, [0.0] * 32)   # more than BAND_COUNT bands (:96-100)
 
 
-def test_cfg2_equalizer_crossfade_every_block(pkg, oracle):
-    """configs[2] at reduced size: a fresh equalizer curve every block, rendered on the device, handed to
-    the engine without leaving the GPU (bfir_set_coeff_device, stride 0 = same filter for every channel)
-    and cross-faded in; the oracle renders the same curves on the CPU and composes run() + crossfade."""
-    L, EQB, C, rs = 256, 16, 2, 4
-    taps = L * EQB                      # 4096 -> 2048 coefficients -> P = 8
+def _cfg2_flow(pkg, oracle, L, EQB, C, nb, tag):
+    """configs[2]: a fresh equalizer curve every block, rendered on the device, handed to the engine without leaving
+    the GPU (bfir_set_coeff_device, stride 0 = same filter for every channel) and cross-faded in on EVERY block; the
+    oracle renders the same curves on the CPU (the reference's render_f) and composes run() + crossfade_inplace
+    (conftest.SwapChain); the same chain in double, fed the reference's float coefficients, is the float64 truth."""
+    rs = 4
+    taps = L * EQB
     P = (taps // 2) // L
     eq = pkg.Equalizer(L, EQB, rs, 96000)
     g = pkg.Brutefir(L, P, rs, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 96000, False)
-    cv = oracle.Convolver(L, rs)
-    nb = 2 * P + 2
+    ref = SwapChain(oracle.Convolver(L, rs), L, P, C, np.float32)
+    tru = SwapChain(oracle.Convolver(L, 8, kind="port"), L, P, C, np.float64)
     mags = [gains(7 + b) for b in range(nb)]
     zero = np.zeros(31)
-    d0 = eq.generate_device(BANDS, mags[0], zero)
-    assert g.set_coeff_device(d0, 0, C, taps // 2, P) == 0
-    h_ref = [oracle.equalizer_render(L, EQB, rs, 96000, BANDS, m, zero) for m in mags]
-    H = [cv.preprocess_coeff(h, P) for h in h_ref]
-    fdl = np.zeros((C, P, 2 * L), dtype=np.float32)
-    prev = np.zeros((C, L), dtype=np.float32)
+    assert g.set_coeff_device(eq.generate_device(BANDS, mags[0], zero), 0, C, taps // 2, P) == 0
     x = white_noise(5, nb * L, C).astype(np.float32)
-
-    def psum(c, t, Hc):
-        acc = cv.convolve(fdl[c, t % P].copy(), Hc[0].copy())
-        for i in range(1, min(P, t + 1)):
-            cv.convolve_add(fdl[c, (t - i) % P].copy(), Hc[i].copy(), acc)
-        return acc
-
+    got, want, truth = [], [], []
+    H_prev = H64_prev = None
     for t in range(nb):
+        h_ref = oracle.equalizer_render(L, EQB, rs, 96000, BANDS, mags[t], zero)
+        H, H64 = ref.spectra([h_ref], same_for_all=True), tru.spectra([h_ref], same_for_all=True)
         if t >= 1:
             assert g.set_coeff_device(eq.generate_device(BANDS, mags[t], zero), 0, C, taps // 2, P, crossfade=True) == 0
         blk = np.ascontiguousarray(x[t * L:(t + 1) * L])
         rc, out = g.run(blk.view(np.uint8).ravel())
         assert rc == 0
-        y = out.view(np.float32).reshape(L, C)
-        for c in range(C):
-            fdl[c, t % P] = cv.mixnscale([cv.time2freq(np.concatenate([prev[c], blk[:, c]]))], [1.0], 1)
-            prev[c] = blk[:, c]
-            spec = psum(c, t, H[t]) if t == 0 else cv.crossfade_inplace(psum(c, t, H[t]), psum(c, t, H[t - 1]), cv.cbuf())
-            ref = cv.freq2time(cv.mixnscale([spec], [1.0], 3))[:L]
-            assert rel_rms(y[:, c], ref) < 3e-5, (t, c)
+        got.append(out.view(np.float32).reshape(L, C).copy())
+        want.append(ref.block(blk, H, H_prev))
+        truth.append(tru.block(blk, H64, H64_prev))
+        H_prev, H64_prev = H, H64
+    got, want, truth = np.concatenate(got), np.concatenate(want), np.concatenate(truth)
+    for c in range(C):
+        parity("%s/ch%d" % (tag, c), got[:, c], want[:, c], 1e-5, truth[:, c])
+        worst = max(rel_rms(got[b * L:(b + 1) * L, c], want[b * L:(b + 1) * L, c]) for b in range(nb))
+        print("%s ch%d worst single block vs oracle: %.3e" % (tag, c, worst))
+
+
+def test_cfg2_equalizer_crossfade_every_block(pkg, oracle):
+    """configs[2] at reduced size: 4096-tap equalizer -> 2048 coefficients -> P 8, L 256"""
+    _cfg2_flow(pkg, oracle, 256, 16, 2, 18, "cfg2_small")
+
+
+def test_cfg2_baseline_size_equalizer_crossfade_every_block(pkg, oracle):
+    """configs[2] at its BASELINE size: stereo 96 kHz float, L 4096, 262144-point equalizer render (four-step inverse
+    transform on the device) -> 131072 coefficients -> P 32, a crossfade swap on every one of 44 blocks (the last 12
+    with all 32 partitions live)"""
+    _cfg2_flow(pkg, oracle, 4096, 64, 2, 44, "cfg2_baseline_size")

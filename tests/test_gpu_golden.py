@@ -6,7 +6,7 @@ import zlib
 import numpy as np
 import pytest
 
-from conftest import rel_rms
+from conftest import rel_rms, parity
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
@@ -54,11 +54,11 @@ def test_convolver_entry_points(pkg, G, rs):
     if rs == 4:
         bi, bx, bb = g.cbuf(G[k + "convolve"]), g.cbuf(G[k + "xfade_old"]), g.cbuf()
         g.convolver_crossfade_inplace(bi, bx, bb)
-        assert rel_rms(g.get(bi), G[k + "crossfade"]) < 2e-5
+        parity("golden/crossfade_inplace/f32", g.get(bi), G[k + "crossfade"], TOL[rs])
     buf = g.cbuf(n_cbufs=1.5)
     for i, name in enumerate(("x", "x2", "x3")):
         g.convolver_convolve_eval(hcs[i], buf, out)
-        assert rel_rms(g.get(out), G[k + "convolve_eval"][i]) < TOL[rs] * 2
+        parity("golden/convolve_eval/%s/%d" % (tag, i), g.get(out), G[k + "convolve_eval"][i], TOL[rs])
 
 
 @pytest.mark.parametrize("rs", [4, 8])
@@ -69,7 +69,7 @@ def test_td_convolver(pkg, G, rs):
     assert rel_rms(g.convolver_td_coeffs(t), G[k + "td_coeffs"]) < TOL[rs]
     d = g.rawbuf(G[k + "td_x"])
     g.convolver_td_convolve(t, d)
-    assert rel_rms(d.download(g.dtype), G[k + "td_convolve"]) < TOL[rs] * 2
+    parity("golden/td_convolve/%s" % TAGS[rs], d.download(g.dtype), G[k + "td_convolve"], TOL[rs])
     g.convolver_td_free(t)
 
 

@@ -152,6 +152,60 @@ def test_cfg4_full_depth_one_gpu(pkg):
     assert err < 1e-5, err
 
 
+def test_cfg4_steady_state_all_512_partitions(pkg):
+    """BASELINE configs[4] at FULL size in STEADY STATE: 518 blocks, so that from block 511 on all 512 partitions of
+    every filter are live (procblocks == P; delay-line slots taken modulo P + 3 over more than a full turn). Filter f
+    carries 16 scaled impulses, one in each of the partitions f, f + 32, ..., f + 480 -- over the 32 filters every
+    partition index is hit -- so the exact output is a sum of delayed crossbar mixes (float64 on the GPU). Checked on
+    the last six blocks: two one-block steps, then two two-block (pair-kernel) steps."""
+    import torch
+    L, P, n = 32768, 512, 32
+    rng = np.random.default_rng(21)
+    taps = L * P
+    nb = P + 6
+    delays = np.array([[(f + 32 * j) * L + int(rng.integers(0, L)) for j in range(16)] for f in range(n)])
+    amps = rng.uniform(0.3, 1.0, (n, 16)).astype(np.float32)
+    coeffs = []
+    for f in range(n):
+        v = np.zeros(taps, dtype=np.float32)
+        v[delays[f]] = amps[f]
+        coeffs.append(v)
+    gin = rng.standard_normal((n, n)) / np.sqrt(n)
+    gout = rng.standard_normal((n, n)) / np.sqrt(n)
+    g = pkg.Brutefir(L, P, 4, n, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, xbar_inputs=n, xbar_outputs=n)
+    assert g.set_coeff(coeffs, P) == 0
+    del coeffs
+    g.set_crossbar(gin, gout)
+    gen = torch.Generator(device="cuda").manual_seed(10)
+    X = torch.rand(nb * L, n, dtype=torch.float32, device="cuda", generator=gen) * 2 - 1
+    Y = torch.empty(6 * L, n, dtype=torch.float32, device="cuda")
+    scratch = torch.empty(L, n, dtype=torch.float32, device="cuda")
+    first = nb - 6
+    for b in range(first + 2):
+        g.run_device(X[b * L:(b + 1) * L], Y[(b - first) * L:(b - first + 1) * L] if b >= first else scratch)
+    for b in range(first + 2, nb, 2):
+        k = b - first
+        g.run_device_pair(X[b * L:(b + 1) * L], X[(b + 1) * L:(b + 2) * L], Y[k * L:(k + 1) * L], Y[(k + 1) * L:(k + 2) * L])
+    assert g.sync() == 0
+    assert g.blockcounter() == nb
+    Gi = torch.from_numpy(gin.astype(np.float32)).double().cuda()
+    Go = torch.from_numpy(gout.astype(np.float32)).double().cuda()
+    m0, m1 = first * L, nb * L
+    fout = torch.zeros(m1 - m0, n, dtype=torch.float64, device="cuda")
+    for f in range(n):
+        for d, a in zip(delays[f], amps[f]):
+            d = int(d)
+            lo = max(m0 - d, 0)                                     # samples before the start of the run are zero
+            seg = X[lo:m1 - d].double() @ Gi[f]                      # filter input f over the shifted window
+            fout[(lo + d) - m0:, f] += seg * float(a)
+    ref = fout @ Go.T
+    for k in range(6):
+        a, b = Y[k * L:(k + 1) * L].double(), ref[k * L:(k + 1) * L]
+        err = torch.sqrt(torch.mean((a - b) ** 2) / torch.mean(b ** 2)).item()
+        print("cfg4 steady state, block %d (%s): rel rms vs float64 truth %.3e" % (first + k, "single" if k < 2 else "pair", err))
+        assert err < 1e-5, (k, err)
+
+
 @pytest.mark.parametrize("rs,L,P,n_in,n_f,n_out,S", [(4, 256, 3, 2, 3, 2, 1), (8, 128, 4, 5, 4, 3, 2), (4, 1024, 4, 32, 32, 32, 1)])
 def test_crossbar_block_pairs_equal_single_blocks(pkg, rs, L, P, n_in, n_f, n_out, S):
     """two blocks per partition-sum launch with a crossbar around the filters (the cfg4 shape): same output as block
