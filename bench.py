@@ -21,7 +21,12 @@ through bfir_run_async, e2e.sync_run through the reference's synchronous run() =
 sync per call); roofline = partition-sum kernel, algorithmic bytes (2P+1)*N*realsize per channel-block over its CUDA-event
 time; cpu_baseline = the reference's own sources (oracle/_ref, FFT provider named) on the host cores;
 latency = host-visible bfir_run latency of ONE 7.1 stream (p50/p99).
-`--impl reference` times only the CPU reference (rank 0), same metric/config.
+`--impl reference` times only the CPU reference (rank 0), same metric/config, --steps / --warmup honoured (each step a
+bounded sample: one block of one stream per host thread).
+`configs` (unless --no-configs): the other BASELINE.json configurations -- cfg0 / cfg2 block latency and the dither
+kernel (rank 0, one GPU), cfg3 (4096 stereo streams, stream-sharded over the ranks, quad kernel + its roofline),
+`partition_sharded`: cfg4 (16 Mi taps, 32x32 crossbar) with its partitions sharded over the ranks and the spectrum
+reduce (NCCL and fused), against the unsharded engine on rank 0 (tools/bench_configs.py).
 """
 import argparse
 import importlib
@@ -111,10 +116,12 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------ CPU reference
 def cpu_reference(n_threads, blocks, steps, warmup):
-    """The reference's own brutefir::run (oracle/_ref = unmodified sources; else the port) on the host
-    cores: one engine instance (= one 7.1 stream, single-threaded like the reference) per thread."""
+    """The reference's own brutefir::run (oracle/_ref = unmodified sources, on the fastest FFT provider this image
+    has: MKL DFTI when libtorch_cpu.so loads, else oracle/fft_r2r; else the port) on the host cores: one engine
+    instance (= one 7.1 stream, single-threaded like the reference) per thread. One step = `blocks` block(s) of every
+    thread's stream; W untimed steps, then exactly `steps` timed ones."""
     import oracle
-    kind = oracle.best_kind()
+    kind = oracle.best_timing_kind()
     C, L, P, rs, fmt, rate = CFG["channels"], CFG["L"], CFG["P"], CFG["realsize"], CFG["fmt"], CFG["rate"]
     engines, inputs = [], []
     for t in range(n_threads):
@@ -146,9 +153,9 @@ def cpu_reference(n_threads, blocks, steps, warmup):
     samples = n_threads * C * L * blocks * steps
     return {
         "value": samples / total / 1e6, "unit": "Msamples/s", "cores": n_threads,
-        "kind": "reference" if kind == "ref" else "port",
-        "sample": "%d thread(s) x 1 stream (8 ch) each, %d timed block(s) of 8192 frames per step x %d steps after a %d-block prefill; "
-                  "FFT provider: %s" % (n_threads, blocks, steps, P, oracle.lib(kind).fft_provider().decode()),
+        "kind": "port" if kind == "port" else "reference",
+        "sample": "%d thread(s) x 1 stream (8 ch) each, %d timed block(s) of 8192 frames per step x %d steps after a %d-block prefill "
+                  "and %d warm-up step(s); FFT provider: %s" % (n_threads, blocks, steps, P, warmup, oracle.lib(kind).fft_provider().decode()),
         "ms_per_step": 1e3 * total / steps, "samples_per_step": n_threads * C * L * blocks,
     }
 
@@ -170,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg0 / cfg2 / cfg3 / cfg4 blocks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -182,13 +190,14 @@ def main():
         if rank != 0:
             return 0
         cores = host_cores()
-        r = cpu_reference(cores, blocks=2, steps=max(1, min(K, 8)), warmup=min(W, 1))
+        # the timed sample per step is ONE block of one 7.1 stream per host thread (the GPU arm's step is one block of
+        # 16 streams per GPU); value is samples per second, so the two arms compare directly. K and W are honoured.
+        r = cpu_reference(cores, blocks=1, steps=max(1, K), warmup=W)
         line = {
             "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Msamples/s", "n_gpus": n_gpus,
-            "steps": max(1, min(K, 8)), "warmup": min(W, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "steps": max(1, K), "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(S, n_gpus), samples_per_step=r["samples_per_step"],
-                           note="CPU reference: each step is a bounded sample (see cpu_baseline.sample); steps capped at 8"),
+            "config": workload_config(S, n_gpus),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -264,7 +273,7 @@ def main():
                 eng.run_device(dev_in[b % ring], dev_out)
         else:
             for b in range(0, K - 1, 2):
-                eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2, pipelined=(mode == "staged"))
+                eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2, pipelined=("staged" if mode == "staged" else False))
             if K % 2:
                 eng.run_device(dev_in[(K - 1) % ring], dev_out)
             eng.join()                      # the engine's stream waits for the side streams (no host wait)
@@ -276,11 +285,41 @@ def main():
         pr, npr = eng.get_profile()
         return ms, n, pr, npr
 
+    def output_check():
+        """The timed passes never look at their output: afterwards, run the SAME two blocks through the stage pipeline
+        on this engine and block by block on a second engine in the same state, and compare."""
+        chk = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=S, device=local_rank, n_groups=1)
+        chk.set_stream(stream.cuda_stream)
+        assert chk.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
+        e2 = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=S, device=local_rank, n_groups=1)
+        e2.set_stream(stream.cuda_stream)
+        assert e2.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
+        o = [torch.empty_like(dev_out) for _ in range(4)]
+        for b in range(P + 2):
+            chk.run_device(dev_in[b % ring], o[0])
+            e2.run_device(dev_in[b % ring], o[2])
+        torch.cuda.synchronize()
+        b = P + 2
+        chk.run_device(dev_in[b % ring], o[0])
+        chk.run_device(dev_in[(b + 1) % ring], o[1])
+        e2.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], o[2], o[3], pipelined="staged")
+        e2.join()
+        assert chk.sync() == 0 and e2.sync() == 0
+        errs = []
+        for k in range(2):
+            d = (o[2 + k] - o[k]).double()
+            errs.append(float(torch.sqrt(torch.mean(d * d) / torch.mean(o[k].double() ** 2))))
+        chk.close()
+        e2.close()
+        return {"rel_rms_staged_pair_vs_single_blocks": errs, "ok": max(errs) < 1e-12,
+                "note": "same two blocks through bfir_run_device_pair(BFIR_PAIR_STAGED) and through two bfir_run_device calls"}
+
     device_pass("staged")                   # warm-up of the stage pipeline (allocates its accumulators)
     sampler.busy.set()
     ms_total, launches, prof_staged, nprof_staged = device_pass("staged")
     sampler.busy.clear()
     value = n_gpus * Ct * L * K / (ms_total * 1e-3) / 1e6
+    out_check = output_check()
     ms_serial, _, prof, nprof = device_pass("serial")
     # the same K steps one block per call (what a real-time caller gets; the per-block partition sum of SURVEY 8d)
     ms_single, _, prof_single, nprof_single = device_pass("single")
@@ -356,7 +395,7 @@ def main():
         t_single = async_pass(False)
         return max_over_ranks(t_sync), t_pairs, t_single, groups
 
-    e2e_steps = K
+    e2e_steps = max(K, 200) - max(K, 200) % 2   # fill and drain of the copy pipeline are a fixed cost: time at least 200 steps
     n_host = 2 * (DEPTH + 1)
     host_ins = host_in + [torch.from_numpy(noise_block(1000 * rank + 50 + b, S, L, C)).contiguous().pin_memory() for b in range(n_host - ring)]
     host_outs = [host_out] + [torch.empty(S * L * C, dtype=torch.float64).pin_memory() for _ in range(n_host - 1)]
@@ -396,34 +435,48 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    b_mac = (2 * P + 1) * (2 * L) * rs * Ct            # algorithmic bytes per channel-block x channels
+    # Bytes per launch. SURVEY 8d counts one channel-block of the partition sum as B_mac = (2P+1) N rs: P coefficient
+    # spectra + P delay-line spectra in, one accumulated spectrum out. A launch of the PAIR kernel convolves two
+    # consecutive blocks of every channel; both use the same P coefficient spectra and, of the delay line, the P + 1
+    # spectra X[t+1] .. X[t-P+1] between them, so the bytes that MUST move are (P + (P+1) + 2) N rs = (2P+3) N rs per
+    # channel -- that is what `achieved` / `frac` are taken on (roofline fraction <= ~1). The kernel moves a little
+    # more ((2P + SPLIT + 2) N rs: each of the SPLIT partition runs re-reads one boundary spectrum); ncu's DRAM bytes
+    # per launch are `traffic`. 2 x B_mac, what two one-block launches (and the reference's access pattern) would
+    # move, is kept under `vs_reference_access_pattern`.
+    b_mac = (2 * P + 1) * (2 * L) * rs * Ct
     npairs = max(nprof, 1)
     mac_ms = prof_staged["mac_ms"] / max(nprof_staged, 1)   # one pair launch = two blocks of every channel; timed region of `value`
     mac_serial_ms = prof["mac_ms"] / npairs
-    algorithmic = 2 * b_mac
-    actual = (2 * P + mac_split + 2) * (2 * L) * rs * Ct   # what the pair kernel has to move: H once, X once per slice run, two outputs
-    achieved = algorithmic / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
+    must_move = (2 * P + 3) * (2 * L) * rs * Ct
+    kernel_moves = (2 * P + mac_split + 2) * (2 * L) * rs * Ct
+    achieved = must_move / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
     traffic, traffic_src = None, None       # DRAM read+write bytes per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
     if os.path.exists(tpath) and S == 16:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
     mac1_ms = prof_single["mac_ms"] / max(nprof_single, 1)
+
+    def gbs(nbytes, ms):
+        return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "partition_mac_pair_kernel<double,SPLIT=%d,UNROLL=2>" % mac_split, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algorithmic, "avg_launch_ms": mac_ms,
-                "note": "algorithmic bytes = SURVEY 8d's (2P+1)*N*realsize per channel-block x 2 blocks x %d channels per launch; the pair kernel "
-                        "reads each coefficient spectrum once for both blocks, so it needs to move only bytes_needed_per_launch: frac > 1 is that reuse, "
-                        "frac_of_bytes_needed is the kernel against the HBM roofline" % Ct,
-                "bytes_needed_per_launch": actual, "frac_of_bytes_needed": actual / (mac_ms * 1e-3) / 1e9 / peak if mac_ms > 0 else 0.0,
-                "serial_pass": {"note": "the same pair kernels back to back on one stream", "avg_launch_ms": mac_serial_ms,
-                                "frac": algorithmic / (mac_serial_ms * 1e-3) / 1e9 / peak if mac_serial_ms > 0 else 0.0,
+                "algorithmic_bytes_per_launch": must_move, "avg_launch_ms": mac_ms,
+                "note": "one launch = the partition sums of TWO consecutive blocks of %d channels; algorithmic bytes = what must move for that: "
+                        "(2P+3) N realsize per channel (P coefficient + P+1 delay-line spectra in, 2 accumulated spectra out). Timed with CUDA events on "
+                        "the engine's stream inside the timed region of `value`, i.e. WITH the transforms of the neighbouring pairs running beside it" % Ct,
+                "kernel_moves_bytes_per_launch": kernel_moves,
+                "vs_reference_access_pattern": {"bytes_per_launch": 2 * b_mac, "frac": gbs(2 * b_mac, mac_ms) / peak,
+                                                "note": "2 x SURVEY 8d's B_mac = (2P+1) N realsize per channel-block: what two one-block partition sums move; "
+                                                        "above 1 because the pair kernel reads every coefficient spectrum once for both blocks"},
+                "serial_pass": {"note": "the same pair kernels back to back on one stream (nothing beside them)", "avg_launch_ms": mac_serial_ms,
+                                "frac": gbs(must_move, mac_serial_ms) / peak,
                                 "value": n_gpus * Ct * L * K / (ms_serial * 1e-3) / 1e6, "ms_per_step": ms_serial / K},
                 "step_share": {k: v / npairs / 2 for k, v in prof.items()},
                 "one_block_per_launch": {"kernel": "partition_mac_kernel<double,SPLIT=%d,UNROLL=4>" % mac_split, "avg_launch_ms": mac1_ms,
-                                         "algorithmic_bytes_per_launch": b_mac,
-                                         "frac": b_mac / (mac1_ms * 1e-3) / 1e9 / peak if mac1_ms > 0 else 0.0,
+                                         "algorithmic_bytes_per_launch": b_mac, "note": "SURVEY 8d's B_mac x channels: here it IS the minimum",
+                                         "frac": gbs(b_mac, mac1_ms) / peak,
                                          "value": n_gpus * Ct * L * K / (ms_single * 1e-3) / 1e6, "ms_per_step": ms_single / K,
                                          "step_share": {k: v / max(nprof_single, 1) for k, v in prof_single.items()}}}
 
@@ -466,9 +519,30 @@ def main():
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
+    # ---- the other BASELINE configurations (tools/bench_configs.py)
+    configs, sharded = None, None
+    if not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs as bc
+        sh = importlib.import_module("foo-dsp-bfir_b200.sharding")
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        configs = {}
+        if rank == 0 and world == 1:
+            configs["cfg0"] = bc.latency_plain(pkg, torch, "cfg0: stereo 44.1 kHz float, 65536 taps, L 4096, P 16 (bfir_run, pinned host buffers)",
+                                               4096, 16, 4, 2, 44100, calls=3000)
+            configs["cfg0_s16_dither"] = bc.latency_plain(pkg, torch, "cfg0 with S16_LE output and dither on", 4096, 16, 4, 2, 44100, calls=1500,
+                                                          out_fmt=pkg.S16_LE, dither=True)
+            configs["cfg2"] = bc.latency_cfg2(pkg, torch, calls=1000)
+            configs["dither_kernel"] = bc.dither_timing(pkg, torch, streams=1)
+            configs["dither_kernel_64_streams"] = bc.dither_timing(pkg, torch, streams=64)
+        configs["cfg3"] = bc.throughput_cfg3(pkg, torch, peak, total_streams=4096, world=world, rank=rank, steps=40,
+                                             max_over_ranks=max_over_ranks, barrier=barrier)
+        sharded = bc.partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20)
+        torch.cuda.set_stream(stream)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        r = cpu_reference(host_cores(), blocks=2, steps=3, warmup=0)
+        r = cpu_reference(host_cores(), blocks=1, steps=8, warmup=1)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -487,6 +561,7 @@ def main():
                     "checksum": checksum},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
             "e2e_product_io": e2e_f32, "value_pipelined": value_grouped,
+            "output_check": out_check, "configs": configs, "partition_sharded": sharded,
             "clocks": sampler.summary(),
         }
         print(json.dumps(line))

@@ -189,6 +189,22 @@ def _ptr(a):
     return a
 
 
+def _buf(a, nbytes, what):
+    """_ptr() for a block buffer: numpy arrays and torch tensors must be contiguous and hold at least `nbytes`
+    (the library copies / transforms exactly that many bytes from the bare pointer); raw addresses pass through."""
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("%s: numpy buffer is not C-contiguous" % what)
+        if a.nbytes < nbytes:
+            raise ValueError("%s: buffer holds %d bytes, the block needs %d" % (what, a.nbytes, nbytes))
+    elif hasattr(a, "data_ptr") and hasattr(a, "is_contiguous"):
+        if not a.is_contiguous():
+            raise ValueError("%s: tensor is not contiguous" % what)
+        if a.numel() * a.element_size() < nbytes:
+            raise ValueError("%s: tensor holds %d bytes, the block needs %d" % (what, a.numel() * a.element_size(), nbytes))
+    return _ptr(a)
+
+
 def real_dtype(realsize):
     return np.float32 if realsize == 4 else np.float64
 
@@ -249,10 +265,19 @@ class Brutefir:
     def is_initialized(self):
         return bool(self.lib.bfir_is_initialized(self.h))
 
+    @staticmethod
+    def _check_lengths(arrs, length):
+        # the library reads `length` elements from EVERY array (brutefir::set_coeff takes one length for all,
+        # brutefir.hpp:31-35): a shorter array would be read past its end
+        for n, a in enumerate(arrs):
+            if len(a) < length:
+                raise ValueError("coefficient array %d has %d elements, length is %d" % (n, len(a), length))
+
     def set_coeff(self, coeffs, coeff_blocks, scale=1.0, length=None):
         """set_coeff(void **coeffs, n_coeffs, length, coeff_blocks, scale): returns 0 or -2."""
-        arrs = [np.ascontiguousarray(c, dtype=self.dtype) for c in coeffs]
+        arrs = [np.ascontiguousarray(c, dtype=self.dtype).ravel() for c in coeffs]
         length = (len(arrs[0]) if arrs else 0) if length is None else length
+        self._check_lengths(arrs, length)
         ptrs = (ctypes.c_void_p * max(len(arrs), 1))(*[a.ctypes.data for a in arrs])
         rc = self.lib.bfir_set_coeff(self.h, ptrs, len(arrs), length, coeff_blocks, float(scale))
         if rc not in (OK, ERR_COEFF):
@@ -261,8 +286,9 @@ class Brutefir:
 
     def set_coeff_crossfade(self, coeffs, coeff_blocks, scale=1.0, length=None):
         """stage a new coefficient set; the next run() cross-fades old -> new (crossfade_inplace ramp)"""
-        arrs = [np.ascontiguousarray(c, dtype=self.dtype) for c in coeffs]
+        arrs = [np.ascontiguousarray(c, dtype=self.dtype).ravel() for c in coeffs]
         length = len(arrs[0]) if length is None else length
+        self._check_lengths(arrs, length)
         ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         rc = self.lib.bfir_set_coeff_crossfade(self.h, ptrs, len(arrs), length, coeff_blocks, float(scale))
         if rc not in (OK, ERR_COEFF):
@@ -288,40 +314,45 @@ class Brutefir:
         """run(void *inbuf, void *outbuf) -> (rc, outbuf); rc is 0 or -1 like the reference."""
         if outbuf is None:
             outbuf = np.empty(self.out_bytes, dtype=np.uint8)
-        rc = self.lib.bfir_run(self.h, _ptr(inbuf), _ptr(outbuf))
+        rc = self.lib.bfir_run(self.h, _buf(inbuf, self.in_bytes, "inbuf"), _buf(outbuf, self.out_bytes, "outbuf"))
         if rc not in (OK, ERR_NONFINITE):
             raise BfirError(rc, last_error())
         return rc, outbuf
 
     def run_device(self, d_in, d_out):
-        _check(self.lib.bfir_run_device(self.h, _ptr(d_in), _ptr(d_out)))
+        _check(self.lib.bfir_run_device(self.h, _buf(d_in, self.in_bytes, "d_in"), _buf(d_out, self.out_bytes, "d_out")))
 
     def run_device_pipelined(self, d_in, d_out):
-        _check(self.lib.bfir_run_device_pipelined(self.h, _ptr(d_in), _ptr(d_out)))
+        _check(self.lib.bfir_run_device_pipelined(self.h, _buf(d_in, self.in_bytes, "d_in"), _buf(d_out, self.out_bytes, "d_out")))
 
     def join(self):
         _check(self.lib.bfir_join(self.h))
 
     def run_device_pair(self, d_in0, d_in1, d_out0, d_out1, pipelined=False):
-        """Two consecutive blocks with one partition-sum launch (offline / pipelined callers)."""
-        _check(self.lib.bfir_run_device_pair(self.h, _ptr(d_in0), _ptr(d_in1), _ptr(d_out0), _ptr(d_out1), int(bool(pipelined))))
+        """Two consecutive blocks with one partition-sum launch (offline / pipelined callers). `pipelined`: False/0 joined,
+        True/1 no join between calls (stream-ordered with one group), "staged"/2 the engine's stage pipeline -- inputs
+        must be complete at call time, outputs are visible after join() / sync() (include/bfir_b200.h)."""
+        pipelined = 2 if pipelined == "staged" else int(pipelined)
+        _check(self.lib.bfir_run_device_pair(self.h, _buf(d_in0, self.in_bytes, "d_in0"), _buf(d_in1, self.in_bytes, "d_in1"),
+                                             _buf(d_out0, self.out_bytes, "d_out0"), _buf(d_out1, self.out_bytes, "d_out1"), pipelined))
 
     def run_device_quad(self, d_ins, d_outs):
         """Four consecutive blocks with one partition-sum launch (single-precision engines; others run two pairs)."""
-        a = (_vp * 4)(*[_ptr(x) for x in d_ins])
-        b = (_vp * 4)(*[_ptr(x) for x in d_outs])
+        a = (_vp * 4)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
+        b = (_vp * 4)(*[_buf(x, self.out_bytes, "d_out") for x in d_outs])
         _check(self.lib.bfir_run_device_quad(self.h, a, b))
 
     def run_async_pair(self, in0, in1, out0, out1):
         """Two consecutive blocks of PINNED host buffers; returns the ticket of the second block."""
-        t = self.lib.bfir_run_async_pair(self.h, _ptr(in0), _ptr(in1), _ptr(out0), _ptr(out1))
+        t = self.lib.bfir_run_async_pair(self.h, _buf(in0, self.in_bytes, "in0"), _buf(in1, self.in_bytes, "in1"),
+                                         _buf(out0, self.out_bytes, "out0"), _buf(out1, self.out_bytes, "out1"))
         if t < 0:
             raise BfirError(int(t), last_error())
         return t
 
     def run_async(self, inbuf, outbuf):
         """Queue one block on PINNED host buffers; returns a ticket for wait(). Buffers stay untouched until then."""
-        t = self.lib.bfir_run_async(self.h, _ptr(inbuf), _ptr(outbuf))
+        t = self.lib.bfir_run_async(self.h, _buf(inbuf, self.in_bytes, "inbuf"), _buf(outbuf, self.out_bytes, "outbuf"))
         if t < 0:
             raise BfirError(int(t), last_error())
         return t
@@ -334,7 +365,7 @@ class Brutefir:
         return rc
 
     def run_partial_device(self, d_in):
-        _check(self.lib.bfir_run_partial_device(self.h, _ptr(d_in)))
+        _check(self.lib.bfir_run_partial_device(self.h, _buf(d_in, self.in_bytes, "d_in")))
 
     def run_finish_device(self, d_out):
         _check(self.lib.bfir_run_finish_device(self.h, _ptr(d_out)))

@@ -138,7 +138,7 @@ struct Engine {
     int quad_group(int g, const void *const d_in[4], void *const d_out[4]);
     int enqueue_quad(const void *const d_in[4], void *const d_out[4]);
     int pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, cudaEvent_t *input_consumed, cudaEvent_t *output_free);
-    int enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined);
+    int enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined, bool staged = false);
     long long run_host_async_pair(const void *in0, const void *in1, void *out0, void *out1);
     int mac_split = 1;              // partition slices per CTA of the MAC kernel
     int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
@@ -898,7 +898,7 @@ int Engine::enqueue_quad(const void *const d_in[4], void *const d_out[4])
 
 // two consecutive blocks on device buffers. Falls back to two single-block steps while the delay line is still
 // filling, on a partition shard and with a pending filter swap.
-int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined)
+int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined, bool staged)
 {
     int rc;
     if (!pair_ok()) {
@@ -906,7 +906,7 @@ int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, voi
         if (rc == BFIR_OK) rc = pipelined ? enqueue_block_pipelined(d_in1, d_out1) : enqueue_block(d_in1, d_out1);
         return rc;
     }
-    if (pipelined && n_groups == 1 && !xbar && staged_enabled) return staged_pair(d_in0, d_in1, d_out0, d_out1);
+    if (staged && n_groups == 1 && !xbar && staged_enabled) return staged_pair(d_in0, d_in1, d_out0, d_out1);
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, (size_t)N * rs * Ct));
     if ((rc = close_staged()) != BFIR_OK) return rc;
     if (!pipelined) { if ((rc = close_async()) != BFIR_OK) return rc; }
@@ -998,7 +998,10 @@ int Engine::sync_and_probe(bool allow_rollback, cudaEvent_t wait_for)
         const int threads = 256, blocks = (Ct + threads - 1) / threads;
         if (n == 1 && allow_rollback) { // exact reference semantics: the aborted block does not advance the counters
             host_blockcounter--;
-            engine_abort_fixup_kernel<<<blocks, threads, 0, stream>>>(state, n_groups, procblocks, pb_inc, Ct, bad);
+            // without a crossbar channel n's input and output stages belong together and the reference never ran
+            // the channels after `bad`; with one, `bad` is an OUTPUT index and every filter channel has already
+            // counted the block on its input side: all of them are rolled back, as if the block had not happened
+            engine_abort_fixup_kernel<<<blocks, threads, 0, stream>>>(state, n_groups, procblocks, pb_inc, Ct, xbar ? -1 : bad);
             count_launch();
         } else {
             for (int g = 0; g < n_groups; g++) h_state[g].first_bad_channel = 0x7fffffff;
@@ -1385,6 +1388,7 @@ int bfir_run(bfir_engine *e, const void *inbuf, void *outbuf)
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     if (inbuf == nullptr || outbuf == nullptr) return BFIR_ERR_INVALID;
+    if (e->impl.peer.enabled) { bfir::set_error("bfir_run is not available on a peer-connected partition shard (run_partial / barrier / run_finish)"); return BFIR_ERR_INVALID; }
     return e->impl.run_host(inbuf, outbuf);
 }
 
@@ -1393,6 +1397,7 @@ int bfir_run_device(bfir_engine *e, const void *d_inbuf, void *d_outbuf)
     if (e != nullptr) e->impl.close_async();
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
+    if (e->impl.peer.enabled) { bfir::set_error("bfir_run_device is not available on a peer-connected partition shard (run_partial / barrier / run_finish)"); return BFIR_ERR_INVALID; }
     return e->impl.enqueue_block(d_inbuf, d_outbuf);
 }
 
@@ -1409,7 +1414,7 @@ int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, v
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     if (d_in0 == nullptr || d_in1 == nullptr || d_out0 == nullptr || d_out1 == nullptr) return BFIR_ERR_INVALID;
-    return e->impl.enqueue_pair(d_in0, d_in1, d_out0, d_out1, pipelined != 0);
+    return e->impl.enqueue_pair(d_in0, d_in1, d_out0, d_out1, pipelined != 0, pipelined == BFIR_PAIR_STAGED);
 }
 
 int bfir_run_device_quad(bfir_engine *e, const void *const d_in[4], void *const d_out[4])
@@ -1617,9 +1622,13 @@ int bfir_set_stream(bfir_engine *e, void *cuda_stream)
     if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     Engine &g = e->impl;
-    if (g.stream && g.own_stream) { cudaStreamSynchronize(g.stream); cudaStreamDestroy(g.stream); }
+    // nothing queued on the previous stream (the engine's own or a caller's) may still be pending when work starts on
+    // the new one: close_async() above ordered the side streams behind it, this drains it
+    if (g.stream) BFIR_CUDA(cudaStreamSynchronize(g.stream));
+    if (g.stream && g.own_stream) cudaStreamDestroy(g.stream);
     g.stream = (cudaStream_t)cuda_stream;
     g.own_stream = false;
+    g.tail_ready = false;           // a look-ahead partition sum left on the old stream is not reused
     g.invalidate_graphs();
     return BFIR_OK;
 }

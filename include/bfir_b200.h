@@ -75,7 +75,8 @@ typedef struct bfir_eq bfir_eq;
  * (brutefir/brutefir.hpp:18-25); the rest have no reference counterpart and default to
  * {1, -1, 0, 0, 0, 0, 0} through bfir_create. */
 typedef struct bfir_config_t {
-    int filter_length;   /* block length L, power of two, 16..16384 (realsize 4) / 16..8192 (realsize 8) */
+    int filter_length;   /* block length L, power of two, 16..32768 (realsize 4) / 16..16384 (realsize 8); the largest
+                            size of each precision runs as a transform split over two CTAs */
     int filter_blocks;   /* partitions P >= 1 */
     int realsize;        /* 4 or 8 */
     int channels;        /* channels per stream; no BF_MAXCHANNELS limit (global.h:21) */
@@ -169,8 +170,20 @@ int bfir_join(bfir_engine *e);
  * both inverse transforms. Same results as two bfir_run_device / bfir_run_async calls up to the summation order
  * of the partition sum. While that is not possible (fewer than filter_blocks blocks since the last reset, a
  * partition shard, a pending filter swap) the call runs the two blocks one by one.
- * bfir_run_device_pair: `pipelined` != 0 behaves like bfir_run_device_pipelined (no join), 0 like bfir_run_device.
+ * bfir_run_device_pair, `pipelined`:
+ *   BFIR_PAIR_JOINED (0)    like bfir_run_device: stream-ordered on the engine's stream, joined at the end of the call.
+ *   BFIR_PAIR_PIPELINED (1) like bfir_run_device_pipelined: no join between calls; with one stream group everything
+ *                           stays stream-ordered on the engine's stream (inputs may be produced on that stream).
+ *   BFIR_PAIR_STAGED (2)    the engine's STAGE PIPELINE (one stream group, no crossbar; otherwise as 1): the forward
+ *                           transforms of pair k+1 and the inverse transforms of pair k-1 run on two side streams beside
+ *                           the partition sum of pair k. CONTRACT: the side streams are NOT ordered after later work on
+ *                           the engine's stream, so d_in0 / d_in1 must be COMPLETE (their producers finished, e.g. a
+ *                           stream/event synchronisation by the caller) when the call is made, and d_out0 / d_out1 are
+ *                           visible to the engine's stream only after bfir_join, to the host after bfir_sync.
  * bfir_run_async_pair: pinned host buffers, returns the ticket of the SECOND block (waiting on it covers both). */
+#define BFIR_PAIR_JOINED 0
+#define BFIR_PAIR_PIPELINED 1
+#define BFIR_PAIR_STAGED 2
 int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, int pipelined);
 long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, void *out0, void *out1);
 /* Four consecutive blocks with one partition-sum launch, single-precision engines (their kernels have the registers

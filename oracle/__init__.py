@@ -2,6 +2,8 @@
 
     kind="ref"  -> oracle/_ref/libbfir_ref.so     the UNMODIFIED reference sources (compiled from
                    /root/reference/brutefir through oracle/ref_shim; see oracle/Makefile)
+    kind="ref_mkl" -> oracle/_ref/libbfir_ref_mkl.so the same reference objects with MKL DFTI (PyTorch's
+                   libtorch_cpu.so) behind the FFTW calls: the tuned CPU FFT for BASELINE TIMINGS only
     kind="port" -> oracle/_build/libbfir_oracle.so the restatement in oracle/bfir_oracle.cpp
 
 Both export the same entry points (prefix ``ref_`` / ``orc_``), so every test can be run against
@@ -16,7 +18,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libbfir_ref.so")
+REF_MKL_SO = os.path.join(HERE, "_ref", "libbfir_ref_mkl.so")
 PORT_SO = os.path.join(HERE, "_build", "libbfir_oracle.so")
+_PATHS = {"ref": REF_SO, "ref_mkl": REF_MKL_SO, "port": PORT_SO}
 
 # sample formats, reference brutefir/global.h:24-37
 S8, S16_LE, S16_BE, S24_LE, S24_BE, S32_LE, S32_BE, FLOAT_LE, FLOAT_BE, FLOAT64_LE, FLOAT64_BE = range(1, 12)
@@ -43,7 +47,29 @@ def build(kind="all", quiet=True):
 
 
 def available(kind):
-    return os.path.exists(REF_SO if kind == "ref" else PORT_SO)
+    return os.path.exists(_PATHS[kind])
+
+
+def _mkl_library():
+    """PyTorch's libtorch_cpu.so (exports MKL's Dfti* entry points), located without importing torch"""
+    import importlib.util
+    spec = importlib.util.find_spec("torch")
+    if spec is None or not spec.origin:
+        return None
+    path = os.path.join(os.path.dirname(spec.origin), "lib", "libtorch_cpu.so")
+    return path if os.path.exists(path) else None
+
+
+def best_timing_kind():
+    """The fastest honest CPU arm for baseline timings: the reference sources on MKL's FFT when that library loads
+    and its provider reports itself, else best_kind()."""
+    if available("ref_mkl") and _mkl_library() is not None:
+        try:
+            if lib("ref_mkl").fft_provider():
+                return "ref_mkl"
+        except OSError:
+            pass
+    return best_kind()
 
 
 def best_kind():
@@ -61,13 +87,15 @@ def _ptr(a):
 def lib(kind):
     if kind in _libs:
         return _libs[kind]
-    path = REF_SO if kind == "ref" else PORT_SO
+    path = _PATHS[kind]
     if not os.path.exists(path):
-        build("ref" if kind == "ref" else "port")
+        build("port" if kind == "port" else "ref")
     if not os.path.exists(path):
         raise FileNotFoundError(path)
+    if kind == "ref_mkl":
+        os.environ.setdefault("BFIR_MKL_LIB", _mkl_library() or "")
     L = ctypes.CDLL(path)
-    p = "ref_" if kind == "ref" else "orc_"
+    p = "orc_" if kind == "port" else "ref_"
     vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
 
     def sig(name, res, *args):
@@ -119,7 +147,7 @@ def lib(kind):
                               ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(cd), vp, ci)
     ns.fft_provider = sig("fft_provider", ctypes.c_char_p)
     _libs[kind] = ns
-    if kind == "ref":
+    if kind in ("ref", "ref_mkl"):
         # Reference quirk (fftw_convolver.cpp:543-549): convolver_runtime_coeffs2cbuf keeps a
         # function-static scratch sized by its FIRST caller and shared by every later instance, so a
         # larger convolver overruns it. Prime it once with the largest cbuf any caller here uses.

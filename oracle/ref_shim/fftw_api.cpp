@@ -20,6 +20,8 @@ struct fftwf_plan_s : plan_impl<float> { using plan_impl<float>::plan_impl; };
 
 extern "C" {
 
+const char *oracle_fft_provider_name(void) { return "oracle/fft_r2r (own Stockham radix-4, native precision; NOT FFTW)"; }
+
 fftw_plan fftw_plan_r2r_1d(int n, double *, double *, fftw_r2r_kind kind, unsigned)
 {
     if (n < 1 || (n & (n - 1)) != 0 || (kind != FFTW_R2HC && kind != FFTW_HC2R)) return NULL;

@@ -235,6 +235,7 @@ int ref_equalizer_render(int block_length, int n_blocks, int realsize, int n_cha
     return frames;
 }
 
-const char *ref_fft_provider(void) { return "oracle/fft_r2r (own Stockham radix-4, native precision; NOT FFTW)"; }
+extern "C" const char *oracle_fft_provider_name(void);   // fftw_api.cpp / fftw_api_mkl.cpp
+const char *ref_fft_provider(void) { return oracle_fft_provider_name(); }
 
 }

@@ -341,6 +341,7 @@ def test_dense_filter_steady_state_512_partitions(pkg, oracle):
     # the same blocks two per call on device buffers (pairs engage once P blocks have been seen)
     d_x = torch.from_numpy(x).cuda()
     d_y = torch.empty_like(d_x)
+    torch.cuda.synchronize()
     for b in range(0, nb, 2):
         g2.run_device_pair(d_x[b * L:(b + 1) * L], d_x[(b + 1) * L:(b + 2) * L], d_y[b * L:(b + 1) * L], d_y[(b + 1) * L:(b + 2) * L])
     assert g2.sync() == 0
@@ -386,6 +387,7 @@ def test_cfg3_full_size_properties(pkg, oracle):
     gen = torch.Generator(device="cuda").manual_seed(5)
     x = [torch.rand(S, L, C, dtype=torch.float32, device="cuda", generator=gen) * 2 - 1 for _ in range(nb)]
     y = [torch.empty(S, L, C, dtype=torch.float32, device="cuda") for _ in range(nb)]
+    torch.cuda.synchronize()                           # the engine runs on its own stream
     for b in range(nb):
         g.run_device(x[b], y[b])
     assert g.sync() == 0
@@ -736,7 +738,7 @@ def test_cfg1_block_pairs_vs_oracle(pkg, oracle):
 
 @pytest.mark.parametrize("rs,out_fmt,dither", [(8, 10, False), (4, 8, False), (4, 2, True)])
 def test_stage_pipeline_equals_single_blocks(pkg, rs, out_fmt, dither):
-    """bfir_run_device_pair(pipelined) on a one-group engine runs the stage pipeline (forward transforms of the next
+    """bfir_run_device_pair(BFIR_PAIR_STAGED) on a one-group engine runs the stage pipeline (forward transforms of the next
     pair under the pair sum, inverse transforms of the previous pair behind it, block index from the host): same
     output as block by block, through mode changes (join, synchronous run, plain pair) in between."""
     import torch
@@ -770,7 +772,7 @@ def test_stage_pipeline_equals_single_blocks(pkg, rs, out_fmt, dither):
             staged.run_device(d_in[b], out_t[b])
             b += 1
             continue
-        staged.run_device_pair(d_in[b], d_in[b + 1], out_t[b], out_t[b + 1], pipelined=True)
+        staged.run_device_pair(d_in[b], d_in[b + 1], out_t[b], out_t[b + 1], pipelined="staged" if b != 30 else True)
         if b == 12:
             staged.join()
         b += 2

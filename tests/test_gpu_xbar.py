@@ -134,6 +134,7 @@ def test_cfg4_full_depth_one_gpu(pkg):
     gen = torch.Generator(device="cuda").manual_seed(9)
     x = [torch.rand(L, n, dtype=torch.float32, device="cuda", generator=gen) * 2 - 1 for _ in range(nb)]
     y = [torch.empty(L, n, dtype=torch.float32, device="cuda") for _ in range(nb)]
+    torch.cuda.synchronize()                           # the engine runs on its own stream
     for b in range(nb):
         g.run_device(x[b], y[b])
     assert g.sync() == 0
@@ -180,6 +181,7 @@ def test_cfg4_steady_state_all_512_partitions(pkg):
     X = torch.rand(nb * L, n, dtype=torch.float32, device="cuda", generator=gen) * 2 - 1
     Y = torch.empty(6 * L, n, dtype=torch.float32, device="cuda")
     scratch = torch.empty(L, n, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()                           # the engine runs on its own stream: X must be complete first
     first = nb - 6
     for b in range(first + 2):
         g.run_device(X[b * L:(b + 1) * L], Y[(b - first) * L:(b - first + 1) * L] if b >= first else scratch)

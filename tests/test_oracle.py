@@ -281,3 +281,33 @@ def test_td_convolver_is_a_circular_convolution(oracle, kind, rs):
         want = np.real(np.fft.ifft(np.fft.fft(x.astype(np.float64)) * np.fft.fft(hp)))
         assert rel_rms(cv.td_convolve(tdc, x.copy()), want) < (2e-6 if rs == 4 else 1e-14)
         cv.td_free(tdc)
+
+
+def test_mkl_fft_provider_for_the_cpu_baseline(oracle):
+    """The baseline-timing build of the reference (oracle/_ref/libbfir_ref_mkl.so: the same unmodified sources, MKL
+    DFTI out of libtorch_cpu.so behind the FFTW calls, SURVEY.md 8c provider 2) computes the same thing as the
+    build the parity tests use: transforms against numpy, a whole run() against the first provider."""
+    if not (oracle.available("ref_mkl") and oracle.best_timing_kind() == "ref_mkl"):
+        pytest.skip("oracle/_ref/libbfir_ref_mkl.so or libtorch_cpu.so not present")
+    from oracle import oracle_np as onp
+    assert b"MKL" in oracle.lib("ref_mkl").fft_provider()
+    for rs in (4, 8):
+        for L in (16, 512, 8192):
+            cv = oracle.Convolver(L, rs, kind="ref_mkl")
+            x = np.random.default_rng(L).uniform(-1, 1, 2 * L).astype(cv.dtype)
+            hc = cv.time2freq(x.copy())
+            assert rel_rms(hc, onp.r2hc(x)) < TOL[rs]
+            assert rel_rms(cv.freq2time(hc.copy()), 2 * L * x.astype(np.float64)) < TOL[rs]
+            buf = x.copy()                       # in place, as the reference calls it (fftw_convolver.cpp:193-200)
+            cv.time2freq(buf, buf)
+            assert np.array_equal(buf, hc)
+    L, P, C = 256, 6, 3
+    a = oracle.Engine(L, P, 8, C, oracle.FLOAT64_LE, oracle.FLOAT64_LE, 48000, False, kind="ref")
+    b = oracle.Engine(L, P, 8, C, oracle.FLOAT64_LE, oracle.FLOAT64_LE, 48000, False, kind="ref_mkl")
+    h = [decay_filter(c, L * P) for c in range(C)]
+    assert a.set_coeff(h, P) == 0 and b.set_coeff(h, P) == 0
+    x = white_noise(4, 10 * L, C)
+    for blk in range(10):
+        raw = np.ascontiguousarray(x[blk * L:(blk + 1) * L]).view(np.uint8).ravel()
+        ya, yb = a.run(raw)[1].view(np.float64), b.run(raw)[1].view(np.float64)
+        assert rel_rms(yb, ya) < 1e-13

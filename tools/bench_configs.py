@@ -1,0 +1,294 @@
+"""Measurements of the BASELINE.json configurations other than the headline one, shared by bench.py (which puts them
+into its JSON line) and the stand-alone tools:
+
+    cfg0 / cfg2   single-stream block latency, p50 / p99 of the host-visible call sequence (latency_plain, latency_cfg2)
+    cfg0 + dither the requantiser kernel's time on S16_LE output (dither_timing)
+    cfg3          4096 independent stereo float streams x 65536 taps, stream-sharded over the ranks, four blocks per
+                  partition-sum launch (throughput_cfg3)
+    cfg4          16 Mi-tap reverb, 32x32 crossbar, partitions sharded over the ranks with the spectrum reduce -- NCCL
+                  all-reduce and the fused peer-store reduce -- against the unsharded engine (partition_sharded)
+
+Everything runs through the package's ctypes mirror of the C ABI (foo-dsp-bfir_b200/__init__.py). Synthetic data as
+BASELINE.md section 2 describes it; filters that would take seconds to draw on the host are generated on the device
+and handed over with bfir_set_coeff_device.
+"""
+import time
+
+import numpy as np
+
+BANDS = [20, 25, 31.5, 40, 50, 63, 80, 100, 125, 160, 200, 250, 315, 400, 500, 630, 800, 1000, 1250, 1600, 2000, 2500,
+         3150, 4000, 5000, 6300, 8000, 10000, 12500, 16000, 20000]
+
+
+def _stats(lat, period_ms):
+    lat = np.sort(np.array(lat)) * 1e3
+    p99 = float(lat[int(len(lat) * 0.99)])
+    return {"p50_ms": float(lat[len(lat) // 2]), "p99_ms": p99, "max_ms": float(lat[-1]), "calls": len(lat),
+            "block_period_ms": period_ms, "real_time_margin_x": period_ms / p99}
+
+
+def host_filter(ch, taps):
+    g = np.random.default_rng(1000 + ch).standard_normal(taps) * np.exp(-6.9 * np.arange(taps) / taps)
+    return g / np.sqrt(np.sum(g * g))
+
+
+def device_filters(torch, n, taps, seed, dtype):
+    """[n][taps] decaying Gaussian filters of unit L2 norm, drawn on the device (distinct per row)"""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    env = torch.exp(-6.9 * torch.arange(taps, device="cuda", dtype=torch.float32) / taps)
+    h = torch.randn(n, taps, device="cuda", dtype=torch.float32, generator=gen) * env
+    h /= torch.sqrt(torch.sum(h.double() ** 2, dim=1, keepdim=True)).float()
+    return h.to(dtype).contiguous()
+
+
+def latency_plain(pkg, torch, name, L, P, rs, C, rate, calls=3000, out_fmt=None, dither=False):
+    """p50 / p99 of bfir_run on pinned host buffers, paced (300 us between calls: the look-ahead partition sum of the
+    next block finishes, as it would between real blocks) and back to back"""
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    out_fmt = fmt if out_fmt is None else out_fmt
+    dt = torch.float32 if rs == 4 else torch.float64
+    e = pkg.Brutefir(L, P, rs, C, fmt, out_fmt, rate, dither)
+    assert e.set_coeff([host_filter(c, L * P) for c in range(C)], P) == 0
+    x = [(torch.rand(L * C, dtype=dt) * 2 - 1).pin_memory() for _ in range(4)]
+    y = torch.empty(e.out_bytes, dtype=torch.uint8).pin_memory()
+    xs, yn = [t.numpy() for t in x], y.numpy()
+    for b in range(P + 50):
+        e.run(xs[b % 4], yn)
+    out = {}
+    for mode, gap in (("paced", 300e-6), ("back_to_back", 0.0)):
+        lat = []
+        for b in range(calls if gap else max(calls // 3, 300)):
+            if gap:
+                t1 = time.perf_counter() + gap
+                while time.perf_counter() < t1:
+                    pass
+            t0 = time.perf_counter()
+            e.run(xs[b % 4], yn)
+            lat.append(time.perf_counter() - t0)
+        out[mode] = _stats(lat, 1e3 * L / rate)
+    e.set_profiling(500)
+    for b in range(500):
+        e.run(xs[b % 4], yn)
+    prof, n = e.get_profile()
+    e.close()
+    return dict(out["paced"], back_to_back={k: out["back_to_back"][k] for k in ("p50_ms", "p99_ms", "max_ms")}, pacing_gap_ms=0.3,
+                device_kernels_ms={k: v / max(n, 1) for k, v in prof.items()}, config=name)
+
+
+def latency_cfg2(pkg, torch, calls=1500):
+    """cfg2: every block = bfir_eq_render_device (262144-point four-step inverse FFT) + bfir_set_coeff_device(crossfade)
+    (32 partition FFTs) + bfir_run (two partition sums, two inverse FFTs, ramp)"""
+    L, EQB, C, rs, rate = 4096, 64, 2, 4, 96000
+    taps = L * EQB
+    P = (taps // 2) // L
+    eq = pkg.Equalizer(L, EQB, rs, rate)
+    e = pkg.Brutefir(L, P, rs, C, pkg.FLOAT_LE, pkg.FLOAT_LE, rate, False)
+    rng = np.random.default_rng(7)
+    zero = [0.0] * 31
+    assert e.set_coeff_device(eq.generate_device(BANDS, list(rng.integers(-120, 121, 31) / 10.0), zero), 0, C, taps // 2, P) == 0
+    gains = [list(rng.integers(-120, 121, 31) / 10.0) for _ in range(16)]
+    x = [(torch.rand(L * C) * 2 - 1).pin_memory() for _ in range(4)]
+    y = torch.empty(L * C).pin_memory()
+    xs, yn = [t.numpy() for t in x], y.numpy()
+    lat = []
+    for b in range(P + 50 + calls):
+        t0 = time.perf_counter()
+        d = eq.generate_device(BANDS, gains[b % 16], zero)
+        assert e.set_coeff_device(d, 0, C, taps // 2, P, crossfade=True) == 0
+        e.run(xs[b % 4], yn)
+        if b >= P + 50:
+            lat.append(time.perf_counter() - t0)
+    e.close()
+    eq.close()
+    return dict(_stats(lat, 1e3 * L / rate), config="cfg2: stereo 96 kHz float, 131072 taps from the equalizer (262144-point render), "
+                "crossfade swap on EVERY block: bfir_eq_render_device + bfir_set_coeff_device(crossfade) + bfir_run")
+
+
+def dither_timing(pkg, torch, streams=1, blocks=400):
+    """cfg0 geometry (stereo float engine, L 4096, P 16) with S16_LE output: the output stage with dither on (inverse
+    transform to planar reals + the serial requantiser kernel) against dither off (fused into the inverse kernel);
+    CUDA events around the output stage on the engine's stream. The difference is what the requantiser costs."""
+    L, P, C = 4096, 16, 2
+    res = {}
+    for dither in (False, True):
+        e = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.S16_LE, 44100, dither, n_streams=streams, n_groups=1)
+        assert e.set_coeff([host_filter(c % 8, L * P) for c in range(C * streams)], P) == 0
+        d_in = [torch.rand(streams * L * C, dtype=torch.float32, device="cuda") - 0.5 for _ in range(4)]
+        d_out = torch.empty(e.out_bytes, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        for b in range(P + 8):
+            e.run_device(d_in[b % 4], d_out)
+        assert e.sync() == 0
+        e.set_profiling(blocks)
+        for b in range(blocks):
+            e.run_device(d_in[b % 4], d_out)
+        assert e.sync() == 0
+        prof, n = e.get_profile()
+        res["dither_on" if dither else "dither_off"] = {k: v / max(n, 1) for k, v in prof.items()}
+        e.close()
+    return {"config": "cfg0 geometry, S16_LE out, %d stream(s) = %d dither channels" % (streams, streams * C),
+            "output_stage_ms": {k: v["inv_ms"] for k, v in res.items()},
+            "dither_kernel_ms": res["dither_on"]["inv_ms"] - res["dither_off"]["inv_ms"],
+            "block_step_ms": {k: sum(v.values()) for k, v in res.items()}}
+
+
+def throughput_cfg3(pkg, torch, peak_gbs, total_streams=4096, world=1, rank=0, steps=40, max_over_ranks=None, barrier=None):
+    """cfg3: `total_streams` independent stereo float streams x 65536 taps (L 4096, P 16, distinct filter per channel),
+    stream-sharded over the ranks (no collective); four blocks per partition-sum launch (bfir_run_device_quad).
+    Returns whole-job Msamples/s (all ranks) and the roofline of the quad partition-sum kernel."""
+    L, P, C = 4096, 16, 2
+    base, extra = divmod(total_streams, world)
+    S = base + (1 if rank < extra else 0)
+    Ct = S * C
+    e = pkg.Brutefir(L, P, 4, C, pkg.FLOAT_LE, pkg.FLOAT_LE, 44100, False, n_streams=S, n_groups=1)
+    h = device_filters(torch, Ct, L * P, 300 + rank, torch.float32)
+    torch.cuda.synchronize()
+    assert e.set_coeff_device(h, L * P, Ct, L * P, P) == 0
+    del h
+    d_in = [torch.rand(S * L * C, dtype=torch.float32, device="cuda") * 2 - 1 for _ in range(4)]
+    d_out = [torch.empty(S * L * C, dtype=torch.float32, device="cuda") for _ in range(4)]
+    torch.cuda.synchronize()
+    for b in range(P):
+        e.run_device(d_in[b % 4], d_out[0])
+    e.run_device_quad(d_in, d_out)
+    assert e.sync() == 0
+    steps -= steps % 4
+    e.set_profiling(steps // 4)
+    if barrier:
+        barrier()
+    t0 = time.perf_counter()
+    for b in range(0, steps, 4):
+        e.run_device_quad(d_in, d_out)
+    assert e.sync() == 0
+    dt = time.perf_counter() - t0
+    if barrier:
+        barrier()
+    if max_over_ranks:
+        dt = max_over_ranks(dt)
+    prof, n = e.get_profile()
+    split = e.get_mac_split()
+    e.close()
+    mac_ms = prof["mac_ms"] / max(n, 1)                     # one launch = four blocks of every channel
+    N, rs = 2 * L, 4
+    needed = (2 * P + 7) * N * rs * Ct                      # P coefficient + (P + 3) delay-line spectra in, 4 out
+    algorithmic_8d = 4 * (2 * P + 1) * N * rs * Ct          # four one-block partition sums
+    return {"workload": "cfg3: %d independent stereo float streams x 65536 taps (L 4096, P 16), distinct filters, stream-sharded over %d GPU(s)" % (total_streams, world),
+            "streams_this_rank": S, "value": total_streams * C * L * steps / dt / 1e6, "unit": "Msamples/s (all ranks)",
+            "ms_per_step": 1e3 * dt / steps, "steps": steps, "api": "bfir_run_device_quad (four blocks per partition-sum launch), wall clock around %d blocks incl. sync" % steps,
+            "step_share_ms_per_block": {k: v / max(n, 1) / 4 for k, v in prof.items()},
+            "roofline": {"kernel": "partition_mac_multi_kernel<float,4,SPLIT=%d>" % split, "bound": "hbm", "avg_launch_ms": mac_ms,
+                         "bytes_needed_per_launch": needed, "achieved": needed / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,
+                         "peak": peak_gbs, "unit": "GB/s", "frac": needed / (mac_ms * 1e-3) / 1e9 / peak_gbs if mac_ms > 0 else 0.0,
+                         "vs_reference_access_pattern": {"bytes_per_launch": algorithmic_8d,
+                                                         "frac": algorithmic_8d / (mac_ms * 1e-3) / 1e9 / peak_gbs if mac_ms > 0 else 0.0}}}
+
+
+def partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20, L=32768, P=512, n=32):
+    """cfg4: n x n crossbar around n filters of L * P taps; the partitions of every filter are dealt to the ranks, each
+    rank computes partial output spectra, and they are summed (a) by ONE NCCL all-reduce per block, (b) by the fused
+    peer-store reduce. Timed after a P-block prefill (every partition live), CUDA events on the engine's stream, max
+    over ranks. Rank 0 also runs the UNSHARDED engine on the same inputs: its time (the one-GPU point of the strong-
+    scaling curve, measured on this box) and the relative RMS of the sharded output against it."""
+    taps = L * P
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    h = device_filters(torch, n, taps, 500, torch.float32)
+    rng = np.random.default_rng(5)
+    gin = rng.standard_normal((n, n)) / np.sqrt(n)
+    gout = rng.standard_normal((n, n)) / np.sqrt(n)
+    gen = torch.Generator(device="cuda").manual_seed(0xB200)
+    d_in = [torch.rand(L * n, dtype=torch.float32, device="cuda", generator=gen) * 2 - 1 for _ in range(4)]
+    torch.cuda.synchronize()
+
+    def make(part_begin, part_count):
+        e = pkg.Brutefir(L, P, 4, n, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, device=local_rank, part_begin=part_begin,
+                         part_count=part_count, n_groups=1, xbar_inputs=n, xbar_outputs=n)
+        e.set_crossbar(gin, gout)
+        e.set_stream(stream.cuda_stream)
+        assert e.set_coeff_device(h, taps, n, taps, P) == 0
+        return e
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step, sync, n_blocks, first):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for b in range(n_blocks):
+            step(first + b)
+        ev1.record(stream)
+        assert sync() == 0
+        torch.cuda.synchronize()
+        return maxr(ev0.elapsed_time(ev1) / n_blocks)
+
+    out = {"workload": "cfg4: 16 Mi-tap reverb (L %d x P %d), %dx%d mixnscale crossbar around %d filters, float" % (L, P, n, n, n),
+           "world": world, "blocks_timed": blocks, "prefill_blocks": P, "reduce_bytes_per_block": n * 2 * L * 4}
+    # ---- the unsharded engine on rank 0 (every rank at world 1)
+    y_ref = None
+    if rank == 0:
+        full = make(0, 0)
+        d_ref = torch.empty(L * n, dtype=torch.float32, device="cuda")
+        for b in range(P):
+            full.run_device(d_in[b % 4], d_ref)
+        assert full.sync() == 0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for b in range(blocks):
+            full.run_device(d_in[(P + b) % 4], d_ref)
+        ev1.record(stream)
+        assert full.sync() == 0
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / blocks
+        out["unsharded_one_gpu"] = {"ms_per_block": ms, "Msamples_s": n * L / (ms * 1e-3) / 1e6, "api": "bfir_run_device"}
+        y_ref = d_ref.double().reshape(L, n).clone()            # output of block P + blocks - 1
+        full.close()
+        del full
+    if world == 1:
+        return out
+    begin, count = sh.partition_shard(P, world, rank)
+    last = P + blocks - 1
+    # ---- (a) NCCL all-reduce of the partial spectra
+    eng = make(begin, count)
+    ptr, nbytes = eng.acc_device_ptr()
+    drv = sh.PartitionShardedEngine(eng, pkg.as_torch(ptr, nbytes // 4, "<f4"))
+    d_out = torch.empty(L * n, dtype=torch.float32, device="cuda")
+    for b in range(P):
+        drv.run_device(d_in[b % 4], d_out)
+    assert drv.sync() == 0
+    ms = timed(lambda b: drv.run_device(d_in[b % 4], d_out), drv.sync, blocks, P)
+    err = None
+    if rank == 0:
+        y = d_out.double().reshape(L, n)
+        err = float(torch.sqrt(torch.mean((y - y_ref) ** 2) / torch.mean(y_ref ** 2)))
+    out["nccl_all_reduce"] = {"ms_per_block": ms, "Msamples_s": n * L / (ms * 1e-3) / 1e6, "partitions_per_rank": count,
+                              "rel_rms_vs_unsharded": err}
+    eng.close()
+    del drv, eng
+    # ---- (b) fused reduce: partial spectra stored straight into the owner rank's receive buffer over NVLink
+    eng = make(begin, count)
+    fz = sh.FusedPartitionShardedEngine(eng)
+    d_own = torch.empty(L * fz.own_count, dtype=torch.float32, device="cuda")
+    for b in range(P):
+        fz.run_device(d_in[b % 4], d_own)
+    assert fz.sync() == 0
+    ms = timed(lambda b: fz.run_device(d_in[b % 4], d_own), fz.sync, blocks, P)
+    err = None
+    if rank == 0:
+        y = d_own.double().reshape(L, fz.own_count)
+        r = y_ref[:, fz.own_first:fz.own_first + fz.own_count]
+        err = float(torch.sqrt(torch.mean((y - r) ** 2) / torch.mean(r ** 2)))
+    out["fused_peer_reduce"] = {"ms_per_block": ms, "Msamples_s": n * L / (ms * 1e-3) / 1e6, "partitions_per_rank": count,
+                                "rel_rms_vs_unsharded": err, "output": "every rank emits its own %d output channels" % fz.own_count}
+    eng.close()
+    if rank == 0:
+        best = min(out["nccl_all_reduce"]["ms_per_block"], out["fused_peer_reduce"]["ms_per_block"])
+        out["speedup_vs_unsharded_same_box"] = out["unsharded_one_gpu"]["ms_per_block"] / best
+        out["strong_scaling_efficiency"] = out["speedup_vs_unsharded_same_box"] / world
+    return out

@@ -32,7 +32,7 @@ for name in ("single", "pair"):
         if name == "single":
             e.run_device_pipelined(d_in[b % 4], d_out[0]); e.run_device_pipelined(d_in[(b + 1) % 4], d_out[1])
         else:
-            e.run_device_pair(d_in[b % 4], d_in[(b + 1) % 4], d_out[0], d_out[1], pipelined=True)
+            e.run_device_pair(d_in[b % 4], d_in[(b + 1) % 4], d_out[0], d_out[1], pipelined="staged")
     e.join()
     ev1.record(st)
     assert e.sync() == 0

@@ -53,7 +53,7 @@ while time.time() < t_end:
         elif op == 2:
             eng.run_device_pipelined(d_in[b], got_d[b]); where[b] = "d"; b += 1
         elif op == 3:
-            eng.run_device_pair(d_in[b], d_in[b + 1], got_d[b], got_d[b + 1], pipelined=bool(rng.integers(0, 2))); where[b] = where[b + 1] = "d"; b += 2
+            eng.run_device_pair(d_in[b], d_in[b + 1], got_d[b], got_d[b + 1], pipelined=int(rng.integers(0, 3))); where[b] = where[b + 1] = "d"; b += 2
         elif op == 6:
             eng.run_device_quad(d_in[b:b + 4], got_d[b:b + 4])
             for k in range(4):
