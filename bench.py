@@ -12,15 +12,16 @@ Workload (one "step" = one block of the block loop, brutefir::run, for every str
   line = S x 64 MiB) exceeds the 126 MB L2 -- no L2 flush is needed between steps. N GPUs: every rank
   runs its own S streams (channel/stream sharding, no collective): weak scaling.
 
-Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM, two blocks per call
-(bfir_run_device_pair: one partition-sum launch for both, every coefficient spectrum read once) through the engine's
-stage pipeline (transforms of the neighbouring pairs on side streams beside the pair sum); e2e = the
+Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM, four blocks per call
+(bfir_run_device_quad_staged: ONE partition-sum launch for the four, every coefficient spectrum read once) through the
+engine's stage pipeline (transforms of the neighbouring calls on side streams beside the partition sum); e2e = the
 same metric on pinned HOST buffers, the H2D of every input block and the D2H of every output block inside
-the timed region: e2e.value through bfir_run_async_pair/bfir_wait (two calls in flight), e2e.one_block_per_call
+the timed region: e2e.value through bfir_run_async_pair/bfir_wait (three calls in flight), e2e.one_block_per_call
 through bfir_run_async, e2e.sync_run through the reference's synchronous run() = bfir_run (H2D + kernels + D2H +
-sync per call); roofline = partition-sum kernel, algorithmic bytes (2P+1)*N*realsize per channel-block over its CUDA-event
-time; cpu_baseline = the reference's own sources (oracle/_ref, FFT provider named) on the host cores;
-latency = host-visible bfir_run latency of ONE 7.1 stream (p50/p99).
+sync per call); roofline = the four-block partition-sum kernel, bytes that must move ((2P+7) N realsize per channel
+and launch) over its CUDA-event time, with the two-block and one-block kernels beside it; cpu_baseline = the
+reference's own sources (oracle/_ref, FFT provider named) on the host cores; latency = host-visible bfir_run latency
+of ONE 7.1 stream (p50/p99).
 `--impl reference` times only the CPU reference (rank 0), same metric/config, --steps / --warmup honoured (each step a
 bounded sample: one block of one stream per host thread).
 `configs` (unless --no-configs): the other BASELINE.json configurations -- cfg0 / cfg2 block latency and the dither
@@ -56,8 +57,9 @@ def workload_config(streams, n_gpus):
         "l2": "streamed set per step (%d MiB coefficient + delay-line spectra per GPU) exceeds the 126 MB L2; no flush"
               % (streams * CFG["channels"] * 2 * CFG["P"] * 2 * CFG["L"] * CFG["realsize"] // (1 << 20)),
         "prefill_blocks": CFG["P"],
-        "step": "one block (8192 frames) of every stream; throughput passes call the two-block entry points (bfir_run_device_pair / "
-                "bfir_run_async_pair), i.e. two steps per call with one partition-sum launch; the one-block-per-call numbers ride beside them",
+        "step": "one block (8192 frames) of every stream; `value` calls the four-block entry point (bfir_run_device_quad_staged: four steps per call "
+                "with ONE partition-sum launch), e2e the two-block one on pinned host buffers (bfir_run_async_pair); the two- and one-block-per-call "
+                "device numbers ride beside them under `roofline`",
     }
 
 
@@ -251,7 +253,10 @@ def main():
     warm_out2 = torch.empty_like(dev_out)
     for b in range(0, max(W, 2), 2):       # warm-up through the two-block entry point (its buffers are allocated here)
         eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, warm_out2)
+    warm_outs = [dev_out, warm_out2, torch.empty_like(dev_out), torch.empty_like(dev_out)]
+    eng.run_device_quad(dev_in, warm_outs)  # and the four-block one
     assert eng.sync() == 0
+    del warm_outs
 
     # ---- device-resident throughput: EXACTLY K steps between barrier+sync, CUDA events on the launch stream.
     # A throughput caller has the next block at hand, so the steps go through the two-block entry point: both forward
@@ -260,23 +265,31 @@ def main():
     # time is taken; the transforms of the next / previous pair run beside it on two side streams). "serial": the same
     # kernels back to back on one stream (each kernel's event time is its own: step shares). "single": one block per call.
     dev_out2 = torch.empty_like(dev_out)
+    dev_outs = [dev_out, dev_out2] + [torch.empty_like(dev_out) for _ in range(2)]
 
     def device_pass(mode):
-        single = mode == "single"
-        eng.set_profiling(K if single else K // 2)
+        """K steps: 'staged_quad' / 'serial_quad' four blocks per call, 'staged' / 'serial' two, 'single' one."""
+        per = 4 if mode.endswith("quad") else (1 if mode == "single" else 2)
+        staged = mode.startswith("staged")
+        eng.set_profiling(max(K // per, 1))
         n0 = pkg.kernel_launch_count()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        if single:
-            for b in range(K):
-                eng.run_device(dev_in[b % ring], dev_out)
-        else:
-            for b in range(0, K - 1, 2):
-                eng.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], dev_out, dev_out2, pipelined=("staged" if mode == "staged" else False))
+        b = 0
+        if per == 4:
+            for b in range(0, K - 3, 4):
+                eng.run_device_quad(dev_in, dev_outs, staged=staged)
+            b = K - K % 4
+        if per >= 2:
+            for b2 in range(b, K - 1, 2):
+                eng.run_device_pair(dev_in[b2 % ring], dev_in[(b2 + 1) % ring], dev_out, dev_out2, pipelined=("staged" if staged else False))
             if K % 2:
                 eng.run_device(dev_in[(K - 1) % ring], dev_out)
             eng.join()                      # the engine's stream waits for the side streams (no host wait)
+        else:
+            for b in range(K):
+                eng.run_device(dev_in[b % ring], dev_out)
         e1.record(stream)
         assert eng.sync() == 0
         barrier()
@@ -286,44 +299,49 @@ def main():
         return ms, n, pr, npr
 
     def output_check():
-        """The timed passes never look at their output: afterwards, run the SAME two blocks through the stage pipeline
-        on this engine and block by block on a second engine in the same state, and compare."""
+        """The timed passes never look at their output: afterwards, run the SAME four blocks through the stage pipeline
+        (one four-block call) on one engine and block by block on a second engine in the same state, and compare."""
         chk = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=S, device=local_rank, n_groups=1)
         chk.set_stream(stream.cuda_stream)
         assert chk.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
         e2 = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=S, device=local_rank, n_groups=1)
         e2.set_stream(stream.cuda_stream)
         assert e2.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
-        o = [torch.empty_like(dev_out) for _ in range(4)]
+        o = [torch.empty_like(dev_out) for _ in range(8)]
         for b in range(P + 2):
             chk.run_device(dev_in[b % ring], o[0])
-            e2.run_device(dev_in[b % ring], o[2])
+            e2.run_device(dev_in[b % ring], o[4])
         torch.cuda.synchronize()
         b = P + 2
-        chk.run_device(dev_in[b % ring], o[0])
-        chk.run_device(dev_in[(b + 1) % ring], o[1])
-        e2.run_device_pair(dev_in[b % ring], dev_in[(b + 1) % ring], o[2], o[3], pipelined="staged")
+        for k in range(4):
+            chk.run_device(dev_in[(b + k) % ring], o[k])
+        e2.run_device_quad([dev_in[(b + k) % ring] for k in range(4)], o[4:8], staged=True)
         e2.join()
         assert chk.sync() == 0 and e2.sync() == 0
         errs = []
-        for k in range(2):
-            d = (o[2 + k] - o[k]).double()
+        for k in range(4):
+            d = (o[4 + k] - o[k]).double()
             errs.append(float(torch.sqrt(torch.mean(d * d) / torch.mean(o[k].double() ** 2))))
         chk.close()
         e2.close()
-        return {"rel_rms_staged_pair_vs_single_blocks": errs, "ok": max(errs) < 1e-12,
-                "note": "same two blocks through bfir_run_device_pair(BFIR_PAIR_STAGED) and through two bfir_run_device calls"}
+        return {"rel_rms_staged_quad_vs_single_blocks": errs, "ok": max(errs) < 1e-12,
+                "note": "same four blocks through bfir_run_device_quad_staged and through four bfir_run_device calls"}
 
-    device_pass("staged")                   # warm-up of the stage pipeline (allocates its accumulators)
+    device_pass("staged_quad")              # warm-up of the stage pipeline (allocates its accumulators)
     sampler.busy.set()
-    ms_total, launches, prof_staged, nprof_staged = device_pass("staged")
+    ms_total, launches, prof_staged, nprof_staged = device_pass("staged_quad")
     sampler.busy.clear()
     value = n_gpus * Ct * L * K / (ms_total * 1e-3) / 1e6
     out_check = output_check()
-    ms_serial, _, prof, nprof = device_pass("serial")
-    # the same K steps one block per call (what a real-time caller gets; the per-block partition sum of SURVEY 8d)
+    ms_serial, _, prof, nprof = device_pass("serial_quad")
+    # two blocks per call (staged and back to back), and one block per call (what a real-time caller gets; the
+    # per-block partition sum of SURVEY 8d)
+    device_pass("staged")
+    ms_pair_staged, _, prof_pair_staged, nprof_pair_staged = device_pass("staged")
+    ms_pair_serial, _, prof_pair, nprof_pair = device_pass("serial")
     ms_single, _, prof_single, nprof_single = device_pass("single")
     mac_split = eng.get_mac_split()
+    quad_split = eng.get_quad_split()
 
     # the same device-resident work the way the end-to-end path runs it: 8 stream groups, no join between calls
     # (a group that is done with its blocks starts the next ones while others still convolve, so transforms run under
@@ -436,44 +454,55 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # Bytes per launch. SURVEY 8d counts one channel-block of the partition sum as B_mac = (2P+1) N rs: P coefficient
-    # spectra + P delay-line spectra in, one accumulated spectrum out. A launch of the PAIR kernel convolves two
-    # consecutive blocks of every channel; both use the same P coefficient spectra and, of the delay line, the P + 1
-    # spectra X[t+1] .. X[t-P+1] between them, so the bytes that MUST move are (P + (P+1) + 2) N rs = (2P+3) N rs per
-    # channel -- that is what `achieved` / `frac` are taken on (roofline fraction <= ~1). The kernel moves a little
-    # more ((2P + SPLIT + 2) N rs: each of the SPLIT partition runs re-reads one boundary spectrum); ncu's DRAM bytes
-    # per launch are `traffic`. 2 x B_mac, what two one-block launches (and the reference's access pattern) would
-    # move, is kept under `vs_reference_access_pattern`.
+    # spectra + P delay-line spectra in, one accumulated spectrum out. A launch of the FOUR-BLOCK kernel convolves four
+    # consecutive blocks of every channel; all four use the same P coefficient spectra and, of the delay line, the
+    # P + 3 spectra X[t+3] .. X[t-P+1] between them, so the bytes that MUST move are (P + (P+3) + 4) N rs = (2P+7) N rs
+    # per channel -- that is what `achieved` / `frac` are taken on (roofline fraction <= ~1). The kernel moves
+    # (2P + 3 SPLIT + 4) N rs (each of the SPLIT partition runs re-reads three boundary spectra; SPLIT = 1 here), ncu's
+    # DRAM bytes per launch are `traffic`. 4 x B_mac, what four one-block launches (and the reference's access
+    # pattern) would move, is kept under `vs_reference_access_pattern`.
     b_mac = (2 * P + 1) * (2 * L) * rs * Ct
-    npairs = max(nprof, 1)
-    mac_ms = prof_staged["mac_ms"] / max(nprof_staged, 1)   # one pair launch = two blocks of every channel; timed region of `value`
-    mac_serial_ms = prof["mac_ms"] / npairs
-    must_move = (2 * P + 3) * (2 * L) * rs * Ct
-    kernel_moves = (2 * P + mac_split + 2) * (2 * L) * rs * Ct
+    nquads = max(nprof, 1)
+    mac_ms = prof_staged["mac_ms"] / max(nprof_staged, 1)   # one launch = four blocks of every channel; timed region of `value`
+    mac_serial_ms = prof["mac_ms"] / nquads
+    must_move = (2 * P + 7) * (2 * L) * rs * Ct
+    kernel_moves = (2 * P + 3 * quad_split + 4) * (2 * L) * rs * Ct
     achieved = must_move / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
     traffic, traffic_src = None, None       # DRAM read+write bytes per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
     if os.path.exists(tpath) and S == 16:
         tj = json.load(open(tpath))
-        traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+        if tj.get("kernel", "").startswith("partition_mac_multi_kernel<double"):
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
     mac1_ms = prof_single["mac_ms"] / max(nprof_single, 1)
+    mac2_ms = prof_pair_staged["mac_ms"] / max(nprof_pair_staged, 1)
+    mac2_serial_ms = prof_pair["mac_ms"] / max(nprof_pair, 1)
+    must_move2 = (2 * P + 3) * (2 * L) * rs * Ct
 
     def gbs(nbytes, ms):
         return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "partition_mac_pair_kernel<double,SPLIT=%d,UNROLL=2>" % mac_split, "peak_source": peak_src,
+                "kernel": "partition_mac_multi_kernel<double,NB=4,SPLIT=%d>" % quad_split, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": must_move, "avg_launch_ms": mac_ms,
-                "note": "one launch = the partition sums of TWO consecutive blocks of %d channels; algorithmic bytes = what must move for that: "
-                        "(2P+3) N realsize per channel (P coefficient + P+1 delay-line spectra in, 2 accumulated spectra out). Timed with CUDA events on "
-                        "the engine's stream inside the timed region of `value`, i.e. WITH the transforms of the neighbouring pairs running beside it" % Ct,
+                "note": "one launch = the partition sums of FOUR consecutive blocks of %d channels; algorithmic bytes = what must move for that: "
+                        "(2P+7) N realsize per channel (P coefficient + P+3 delay-line spectra in, 4 accumulated spectra out). Timed with CUDA events on "
+                        "the engine's stream inside the timed region of `value`, i.e. WITH the transforms of the neighbouring calls running beside it" % Ct,
                 "kernel_moves_bytes_per_launch": kernel_moves,
-                "vs_reference_access_pattern": {"bytes_per_launch": 2 * b_mac, "frac": gbs(2 * b_mac, mac_ms) / peak,
-                                                "note": "2 x SURVEY 8d's B_mac = (2P+1) N realsize per channel-block: what two one-block partition sums move; "
-                                                        "above 1 because the pair kernel reads every coefficient spectrum once for both blocks"},
-                "serial_pass": {"note": "the same pair kernels back to back on one stream (nothing beside them)", "avg_launch_ms": mac_serial_ms,
+                "vs_reference_access_pattern": {"bytes_per_launch": 4 * b_mac, "frac": gbs(4 * b_mac, mac_ms) / peak,
+                                                "note": "4 x SURVEY 8d's B_mac = (2P+1) N realsize per channel-block: what four one-block partition sums move; "
+                                                        "above 1 because the four-block kernel reads every coefficient spectrum once for all four blocks"},
+                "serial_pass": {"note": "the same four-block calls with their kernels back to back on one stream (nothing beside them)", "avg_launch_ms": mac_serial_ms,
                                 "frac": gbs(must_move, mac_serial_ms) / peak,
                                 "value": n_gpus * Ct * L * K / (ms_serial * 1e-3) / 1e6, "ms_per_step": ms_serial / K},
-                "step_share": {k: v / npairs / 2 for k, v in prof.items()},
+                "step_share": {k: v / nquads / 4 for k, v in prof.items()},
+                "two_blocks_per_launch": {"kernel": "partition_mac_pair_kernel<double,SPLIT=%d,UNROLL=2>" % mac_split,
+                                          "algorithmic_bytes_per_launch": must_move2, "note": "(2P+3) N realsize per channel for two blocks",
+                                          "staged": {"avg_launch_ms": mac2_ms, "frac": gbs(must_move2, mac2_ms) / peak,
+                                                     "value": n_gpus * Ct * L * K / (ms_pair_staged * 1e-3) / 1e6, "ms_per_step": ms_pair_staged / K},
+                                          "serial": {"avg_launch_ms": mac2_serial_ms, "frac": gbs(must_move2, mac2_serial_ms) / peak,
+                                                     "value": n_gpus * Ct * L * K / (ms_pair_serial * 1e-3) / 1e6, "ms_per_step": ms_pair_serial / K,
+                                                     "step_share": {k: v / max(nprof_pair, 1) / 2 for k, v in prof_pair.items()}}},
                 "one_block_per_launch": {"kernel": "partition_mac_kernel<double,SPLIT=%d,UNROLL=4>" % mac_split, "avg_launch_ms": mac1_ms,
                                          "algorithmic_bytes_per_launch": b_mac, "note": "SURVEY 8d's B_mac x channels: here it IS the minimum",
                                          "frac": gbs(b_mac, mac1_ms) / peak,

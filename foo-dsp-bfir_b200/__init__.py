@@ -75,6 +75,7 @@ API = [
     ("bfir_run_device_pair", _ci, [_vp, _vp, _vp, _vp, _vp, _ci]),
     ("bfir_run_async_pair", ctypes.c_longlong, [_vp, _vp, _vp, _vp, _vp]),
     ("bfir_run_device_quad", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    ("bfir_run_device_quad_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -94,6 +95,7 @@ API = [
     ("bfir_set_groups", _ci, [_vp, _ci]),
     ("bfir_get_groups", _ci, [_vp]),
     ("bfir_get_mac_split", _ci, [_vp]),
+    ("bfir_get_quad_split", _ci, [_vp]),
     ("bfir_set_stream", _ci, [_vp, _vp]),
     ("bfir_set_profiling", _ci, [_vp, _ci]),
     ("bfir_get_profile", _ci, [_vp, ctypes.POINTER(_cd), ctypes.POINTER(ctypes.c_ulonglong), _ci]),
@@ -336,11 +338,12 @@ class Brutefir:
         _check(self.lib.bfir_run_device_pair(self.h, _buf(d_in0, self.in_bytes, "d_in0"), _buf(d_in1, self.in_bytes, "d_in1"),
                                              _buf(d_out0, self.out_bytes, "d_out0"), _buf(d_out1, self.out_bytes, "d_out1"), pipelined))
 
-    def run_device_quad(self, d_ins, d_outs):
-        """Four consecutive blocks with one partition-sum launch (single-precision engines; others run two pairs)."""
+    def run_device_quad(self, d_ins, d_outs, staged=False):
+        """Four consecutive blocks with one partition-sum launch; staged=True: through the stage pipeline (inputs
+        complete at call time, outputs visible after join() / sync())."""
         a = (_vp * 4)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
         b = (_vp * 4)(*[_buf(x, self.out_bytes, "d_out") for x in d_outs])
-        _check(self.lib.bfir_run_device_quad(self.h, a, b))
+        _check((self.lib.bfir_run_device_quad_staged if staged else self.lib.bfir_run_device_quad)(self.h, a, b))
 
     def run_async_pair(self, in0, in1, out0, out1):
         """Two consecutive blocks of PINNED host buffers; returns the ticket of the second block."""
@@ -412,6 +415,9 @@ class Brutefir:
 
     def get_mac_split(self):
         return _check(self.lib.bfir_get_mac_split(self.h))
+
+    def get_quad_split(self):
+        return _check(self.lib.bfir_get_quad_split(self.h))
 
     def set_stream(self, cuda_stream):
         _check(self.lib.bfir_set_stream(self.h, ctypes.c_void_p(cuda_stream)))

@@ -385,8 +385,8 @@ int bfir_conv_cbuf2raw(bfir_conv *c, const void *cbuf, void *d_outbuf, int forma
         d.fmt = format; d.ch_per_stream = sample_spacing; d.L = g.L; d.n_channels = 1;
         d.randtab = g.dither.d_tab; d.randtab_size = g.dither.size; d.randmap = g.dither.d_map;
         d.dstate = g.dither.d_state; d.stats = g.d_stats - dither_channel; d.single_channel = dither_channel;
-        if (g.rs == 4) dither_kernel<float><<<1, 32, 0, g.stream>>>(d);
-        else dither_kernel<double><<<1, 32, 0, g.stream>>>(d);
+        if (g.rs == 4) dither_kernel<float><<<1, 128, 0, g.stream>>>(d, 1);
+        else dither_kernel<double><<<1, 128, 0, g.stream>>>(d, 1);
         count_launch();
         BFIR_CUDA(cudaGetLastError());
     } else {

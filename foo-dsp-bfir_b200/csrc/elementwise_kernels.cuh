@@ -226,59 +226,163 @@ __global__ void real2raw_kernel(const T *real, uint8_t *raw, int fmt, int spacin
     if (acc.largest > 0.0) atomicMax(&stats->largest_bits, (unsigned long long)__double_as_longlong(acc.largest));
 }
 
-// real2raw*_hp_tpdf -> dither*_real2int_hp_tpdf (real2raw.cpp:39-315 / :645-920, dither.cpp:127-212 /
-// :276-347): first-order high-pass error feedback + TPDF dither. The recurrence is serial in n, so
-// one thread walks one channel; channels run in parallel (one thread per channel).
+// quantise() of codec.cuh for the dither walker, without a branch: every branch of the original sits on the walker's
+// dependent chain (one warp, nothing else to issue). The value the error feedback subtracts, (T)s, is computed in
+// floating point -- trunc, minus one for negative values, clamped to the format's range: the correctly rounded image
+// of the same integer, so it equals (T)s bit for bit (also where T cannot hold s exactly: 32-bit samples in single
+// precision) -- while the integer s itself, which only the output needs, is formed beside the chain with selects,
+// like the statistics. Same results as quantise() for every finite input.
 template <class T>
-__global__ void dither_kernel(const DitherArgs a)
+__device__ __forceinline__ T quantise_walk(T d, T stat, T rmin, T rmax, int32_t imin, int32_t imax, int32_t &s_out, OverflowAcc &acc)
 {
-    int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a.single_channel >= 0) { if (ch != 0) return; ch = a.single_channel; }
-    else { if (ch >= a.n_channels) return; ch += a.ch_base; }
-    const int data_ch = a.single_channel >= 0 ? 0 : ch;
-    DitherState st = a.dstate[ch];
-    // dither_preloop_real2int_hp_tpdf, dither.cpp:127-139
-    if (st.randtab_ptr + a.L >= a.randtab_size) {
-        st.tab0 = a.randtab[st.randtab_ptr - 1];
-        st.randtab_ptr = 1;
-    }
-    const int base = st.randtab_ptr;
-    st.randtab_ptr += a.L;
+    const bool neg = d < (T)0;
+    const T tr = sizeof(T) == 4 ? (T)truncf((float)d) : (T)trunc((double)d);
+    const T sf = fmin(fmax(add_rn<T>(tr, neg ? (T)-1 : (T)0), rmin), rmax);   // + 0 also turns -0 into the +0 of (T)int
+    const bool ovn = neg && d <= rmin, ovp = !neg && d > rmax;
+    int32_t s = real_to_int_rz<T>(d) - (neg ? 1 : 0);
+    s = ovn ? imin : (ovp ? imax : s);
+    acc.n_overflows += (ovn || ovp) ? 1u : 0u;
+    const double ds = (double)stat, dd = (double)d;
+    const bool ln = ovn && ds < -acc.largest, lp = ovp && ds > acc.largest;
+    acc.largest = ln ? -dd : (lp ? dd : acc.largest);
+    const bool in = neg && !ovn && s < -acc.intlargest, ip = !neg && !ovp && s > acc.intlargest;
+    acc.intlargest = in ? -s : (ip ? s : acc.intlargest);
+    s_out = s;
+    return sf;
+}
 
-    const T *real = (const T *)a.real + (long long)data_ch * a.real_stride;
+// real2raw*_hp_tpdf -> dither*_real2int_hp_tpdf (real2raw.cpp:39-315 / :645-920, dither.cpp:127-212 /
+// :276-347): first-order high-pass error feedback + TPDF dither. The recurrence
+//     x[n] = real[n] + (e[n-1] - e[n-2]);  s[n] = Q(x[n] + dv[n]);  e[n] = x[n] - s[n]
+// is serial in n (Q rounds and clamps), so ONE lane walks a channel -- but nothing else has to be serial. A CTA of
+// four warps takes G channels (G = 1 .. 32, a power of two chosen by the launch so that few-channel engines get
+// one channel per CTA and many-channel ones fill the lanes of the walker warp) and moves through the block in
+// chunks of DITHER_STAGE / G samples, double buffered in shared memory:
+//     warps 1-3: stage chunk k+1 -- real[] (coalesced) and the dither values dv[n] = map[tab[base+n] - tab[base+n-1]],
+//                which do not depend on the recurrence -- and write chunk k-1's samples out in the raw format
+//                (lanes along the interleaved channels)
+//     warp 0:    lane g walks channel g through chunk k reading and writing shared memory only
+// so the walker's dependent chain is sub, add, add, trunc, add, min, max, sub (quantise_walk: no branch, no integer
+// round trip) and no global-memory latency sits on it
+// (round 1: one thread per channel with every operand fetched from global memory inside the loop, 230 ns per sample).
+#define DITHER_STAGE 1024
+template <class T>
+__global__ void __launch_bounds__(128) dither_kernel(const DitherArgs a, const int G)
+{
+    constexpr int PAD = DITHER_STAGE + DITHER_STAGE / 32;       // odd channel pitch G | 1 needs up to 1/32 more
+    __shared__ T real_s[2][PAD], dv_s[2][PAD];
+    __shared__ int32_t out_s[2][PAD];
+    __shared__ int base_s[32], tab0_s[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g0 = blockIdx.x * G;                              // first channel of this CTA, relative to the launch
+    const int ng = min(G, a.n_channels - g0);
+    const int GP = G | 1;                                       // shared-memory pitch between consecutive samples
+    const int CH = DITHER_STAGE / G;                            // samples per chunk and channel
+    const int nchunks = (a.L + CH - 1) / CH;
     const T *map = (const T *)a.randmap + 256;
-    const int stream = data_ch / a.ch_per_stream, c = data_ch - stream * a.ch_per_stream;
-    const int bytes = fmt_bytes(a.fmt);
-    uint8_t *raw = (uint8_t *)a.raw + (long long)stream * a.raw_stream_stride + (long long)c * bytes;
-    const long long step = (long long)a.ch_per_stream * bytes;
+    // channel g of this CTA: state / statistics index, data index (planar reals, raw position)
+    const int single = a.single_channel;
+    // walker registers (warp 0, lane < ng)
+    DitherState st = {};
+    OverflowAcc acc;
+    acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
+    T e0 = (T)0, e1 = (T)0;
+    const int my_ch = single >= 0 ? single : a.ch_base + g0 + lane;
+    if (warp == 0 && lane < ng) {
+        st = a.dstate[my_ch];
+        // dither_preloop_real2int_hp_tpdf, dither.cpp:127-139
+        if (st.randtab_ptr + a.L >= a.randtab_size) {
+            st.tab0 = a.randtab[st.randtab_ptr - 1];
+            st.randtab_ptr = 1;
+        }
+        base_s[lane] = st.randtab_ptr;
+        tab0_s[lane] = st.tab0;
+        st.randtab_ptr += a.L;
+        const OverflowStats os = a.stats[my_ch];     // sequential, so seed with the running values (dither.cpp:170-205)
+        acc.intlargest = os.intlargest;
+        acc.largest = __longlong_as_double((long long)os.largest_bits);
+        e0 = (T)st.err[0]; e1 = (T)st.err[1];
+    }
+    __syncthreads();
+
+    auto stage = [&](int k, int first, int nthreads) {
+        const int n0 = k * CH, len = min(CH, a.L - n0);
+        T *rs = real_s[k & 1], *ds = dv_s[k & 1];
+        for (int idx = first; idx < ng * len; idx += nthreads) {
+            const int g = idx / len, n = idx - g * len;
+            const int data_ch = single >= 0 ? 0 : a.ch_base + g0 + g;
+            const int ti = base_s[g] + n0 + n;
+            const int cur = (int)a.randtab[ti];
+            const int prev = ti - 1 == 0 ? tab0_s[g] : (int)a.randtab[ti - 1];
+            rs[n * GP + g] = ((const T *)a.real)[(long long)data_ch * a.real_stride + n0 + n];
+            ds[n * GP + g] = map[cur - prev];
+        }
+    };
+    auto emit = [&](int k, int first, int nthreads) {
+        const int n0 = k * CH, len = min(CH, a.L - n0);
+        const int32_t *os = out_s[k & 1];
+        const int bytes = fmt_bytes(a.fmt);
+        for (int idx = first; idx < ng * len; idx += nthreads) {
+            const int n = idx / ng, g = idx - n * ng;
+            const int data_ch = single >= 0 ? 0 : a.ch_base + g0 + g;
+            const int stream = data_ch / a.ch_per_stream, c = data_ch - stream * a.ch_per_stream;
+            uint8_t *p = (uint8_t *)a.raw + (long long)stream * a.raw_stream_stride + ((long long)(n0 + n) * a.ch_per_stream + c) * bytes;
+            store_raw_int(p, a.fmt, os[n * GP + g]);
+        }
+    };
+
     int32_t imin, imax;
     int_limits(a.fmt, imin, imax);
     const T rmin = (T)imin, rmax = (T)imax;
-
-    OverflowStats *os = &a.stats[ch];
-    OverflowAcc acc; // sequential here, so seed with the running values (dither.cpp:170-205 compares against them)
-    acc.n_overflows = 0;
-    acc.intlargest = os->intlargest;
-    acc.largest = __longlong_as_double((long long)os->largest_bits);
-    T e0 = (T)st.err[0], e1 = (T)st.err[1];
-    int prev = base - 1 == 0 ? st.tab0 : (int)a.randtab[base - 1];
-    for (int n = 0; n < a.L; n++) {
-        const int cur = (int)a.randtab[base + n];
-        const T dv = map[cur - prev];
-        prev = cur;
-        T x = add_rn<T>(real[n], sub_rn<T>(e0, e1));          // error feedback {1, -1}
-        e1 = e0;
-        const T d = add_rn<T>(x, dv);
-        const int32_t s = quantise<T>(d, x, rmin, rmax, imin, imax, acc);
-        e0 = sub_rn<T>(x, (T)s);
-        store_raw_int(raw + (long long)n * step, a.fmt, s);
+    stage(0, tid, 128);
+    __syncthreads();
+    for (int k = 0; k < nchunks; k++) {
+        if (warp == 0) {
+            if (lane < ng) {
+                const int len = min(CH, a.L - k * CH);
+                const T *rs = real_s[k & 1] + lane, *ds = dv_s[k & 1] + lane;
+                int32_t *os = out_s[k & 1] + lane;
+                for (int n = 0; n < len; n += 8) {              // L and CH are powers of two >= 16
+                    T r[8], dv[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { r[j] = rs[(n + j) * GP]; dv[j] = ds[(n + j) * GP]; }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const T x = add_rn<T>(r[j], sub_rn<T>(e0, e1));      // error feedback {1, -1}
+                        e1 = e0;
+                        const T d = add_rn<T>(x, dv[j]);
+                        int32_t s;
+                        const T sf = quantise_walk<T>(d, x, rmin, rmax, imin, imax, s, acc);
+                        e0 = sub_rn<T>(x, sf);
+                        os[(n + j) * GP] = s;
+                    }
+                }
+            }
+        } else {
+            if (k + 1 < nchunks) stage(k + 1, tid - 32, 96);
+            if (k > 0) emit(k - 1, tid - 32, 96);
+        }
+        __syncthreads();
     }
-    st.err[0] = (double)e0;
-    st.err[1] = (double)e1;
-    a.dstate[ch] = st;
-    os->n_overflows += acc.n_overflows;
-    os->intlargest = acc.intlargest;
-    os->largest_bits = (unsigned long long)__double_as_longlong(acc.largest);
+    emit(nchunks - 1, tid, 128);
+    if (warp == 0 && lane < ng) {
+        st.err[0] = (double)e0;
+        st.err[1] = (double)e1;
+        a.dstate[my_ch] = st;
+        OverflowStats *os = &a.stats[my_ch];
+        os->n_overflows += acc.n_overflows;
+        os->intlargest = acc.intlargest;
+        os->largest_bits = (unsigned long long)__double_as_longlong(acc.largest);
+    }
+}
+
+// channels per CTA of the dither kernel: one while that still gives at most two CTAs per SM's worth of walkers,
+// then powers of two up to a full walker warp
+static inline int dither_channels_per_cta(int n_channels)
+{
+    int g = 1;
+    while (g < 32 && (n_channels + g - 1) / g > 296) g *= 2;
+    return g;
 }
 
 // engine housekeeping

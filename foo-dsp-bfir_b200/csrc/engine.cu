@@ -16,7 +16,7 @@ namespace bfir {
 struct Engine {
     bfir_config_t cfg;
     int L = 0, N = 0, P = 0, C = 0, S = 0, Ct = 0, rs = 0, log2m = 0;
-    int Pslots = 0;                 // delay-line slots per channel, P + 1 (see init)
+    int Pslots = 0;                 // delay-line slots per channel, P + 7 (see init)
     // crossbar: Ci inputs and Co outputs per stream around the C filters (== C without a crossbar)
     int Ci = 0, Co = 0, Cit = 0, Cot = 0;
     bool xbar = false, xbar_set = false;
@@ -119,7 +119,7 @@ struct Engine {
     // block index from the host because the device counter (advanced by the inverse kernels) lags behind
     cudaStream_t sp_fwd = nullptr, sp_inv = nullptr;
     cudaEvent_t sp_fwd_done[2] = {}, sp_mac_done[2] = {}, sp_inv_done[2] = {};
-    void *sp_acc[2][2] = {};        // [pair parity][block in pair] accumulated spectra
+    void *sp_acc[2][4] = {};        // [call parity][block in call] accumulated spectra (two or four blocks per call)
     unsigned long long sp_pairs = 0; // pairs queued since the pipeline was opened
     bool sp_open = false;
     bool staged_enabled = true;     // BFIR_STAGED=0 switches the stage pipeline off
@@ -136,11 +136,13 @@ struct Engine {
     }
     void *acc_quad[2] = {};         // accumulated spectra of blocks 3 and 4 of a quad (single precision)
     int quad_group(int g, const void *const d_in[4], void *const d_out[4]);
-    int enqueue_quad(const void *const d_in[4], void *const d_out[4]);
+    int enqueue_quad(const void *const d_in[4], void *const d_out[4], bool staged = false);
+    int staged_blocks(int nb, const void *const *d_in, void *const *d_out);
     int pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, cudaEvent_t *input_consumed, cudaEvent_t *output_free);
     int enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined, bool staged = false);
     long long run_host_async_pair(const void *in0, const void *in1, void *out0, void *out1);
     int mac_split = 1;              // partition slices per CTA of the MAC kernel
+    int quad_split = 1;             // the same for the four-block kernel (one CTA per SM in double precision: fewer slices)
     int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
     // optional per-kernel timing (bfir_set_profiling)
     std::vector<cudaEvent_t> pev;
@@ -187,7 +189,7 @@ int Engine::init(const bfir_config_t &c)
     if (P < 1 || C < 1) { set_error("No channels defined."); return BFIR_ERR_INVALID; }            // brutefir.cpp:745-749
     if ((long long)C * S > 0x7fffffffLL / 2) return BFIR_ERR_INVALID;
     Ct = C * S;
-    Pslots = P + 3;
+    Pslots = P + 7;
     xbar = c.xbar_inputs > 0 || c.xbar_outputs > 0;
     Ci = c.xbar_inputs > 0 ? c.xbar_inputs : C;
     Co = c.xbar_outputs > 0 ? c.xbar_outputs : C;
@@ -209,10 +211,11 @@ int Engine::init(const bfir_config_t &c)
     own_stream = true;
 
     const size_t cbuf = (size_t)N * rs;
-    // The reference's delay line has P slots, slot = blockcounter % P (brutefir.cpp:270,294). Here it has P + 3:
+    // The reference's delay line has P slots, slot = blockcounter % P (brutefir.cpp:270,294). Here it has P + 7:
     // with P + 1 the spectrum of block t+1 can be written while block t's partition sum still needs X[t-P+1] (block
-    // pairs); the stage pipeline transforms the NEXT pair (t+2, t+3) while the sum of (t, t+1) runs, two more. Which slot a block lands in is not observable -- partition i is only
-    // read once procblocks says the slot has been written since the last reset.
+    // pairs), P + 3 covers four blocks per launch, and the stage pipeline transforms the NEXT call's (up to four)
+    // blocks while the sum of this one runs, four more. Which slot a block lands in is not observable -- partition i
+    // is only read once procblocks says the slot has been written since the last reset.
     BFIR_CUDA(cudaMalloc(&fdl, cbuf * Pslots * Ct));
     BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * Pslots * Ct, stream));                                      // brutefir.cpp:768-769
     BFIR_CUDA(cudaMalloc(&acc, cbuf * Ct));
@@ -286,6 +289,15 @@ int Engine::init(const bfir_config_t &c)
             const int v = atoi(env);
             if ((v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) && v <= P) mac_split = v;
         }
+        // four-block kernel: 214 registers in double precision (one CTA of 256 threads per SM), 128 in single (two);
+        // slices only until there are ~4 waves of CTAs (measured, cfg1 x 16: 209 / 230 / 256 us at 1 / 2 / 4 slices)
+        const long long resident = 148LL * (rs == 8 ? 1 : 2);
+        quad_split = 1;
+        while (quad_split < (rs == 8 ? 4 : 16) && quad_split * 2 <= P && group_threads * quad_split / 256 < 4 * resident) quad_split *= 2;
+        if (const char *env = getenv("BFIR_QUAD_SPLIT")) {
+            const int v = atoi(env);
+            if ((v == 1 || v == 2 || v == 4 || (rs == 4 && (v == 8 || v == 16))) && v <= P) quad_split = v;
+        }
     }
     last_overflow.assign(Cot, bfir_overflow_t{0, 0, 0.0, ovf_max});
     {
@@ -339,7 +351,7 @@ void Engine::destroy()
     for (cudaStream_t *st : { &sp_fwd, &sp_inv }) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
     for (int k = 0; k < 2; k++) {
         for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
-        for (int j = 0; j < 2; j++) if (sp_acc[k][j]) { cudaFree(sp_acc[k][j]); sp_acc[k][j] = nullptr; }
+        for (int j = 0; j < 4; j++) if (sp_acc[k][j]) { cudaFree(sp_acc[k][j]); sp_acc[k][j] = nullptr; }
     }
     if (tail_stream) { cudaStreamSynchronize(tail_stream); cudaStreamDestroy(tail_stream); tail_stream = nullptr; }
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) if (tail_done[g]) { cudaEventDestroy(tail_done[g]); tail_done[g] = nullptr; }
@@ -697,9 +709,9 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
         d.fmt = out_sf.format; d.ch_per_stream = Co; d.L = L; d.n_channels = nch; d.ch_base = c0;
         d.randtab = dither.d_tab; d.randtab_size = dither.size; d.randmap = dither.d_map;
         d.dstate = dither.d_state; d.stats = stats; d.single_channel = -1;
-        const int threads = 32, blocks = (nch + threads - 1) / threads;
-        if (rs == 4) dither_kernel<float><<<blocks, threads, 0, st>>>(d);
-        else dither_kernel<double><<<blocks, threads, 0, st>>>(d);
+        const int G = dither_channels_per_cta(nch), blocks = (nch + G - 1) / G;
+        if (rs == 4) dither_kernel<float><<<blocks, 128, 0, st>>>(d, G);
+        else dither_kernel<double><<<blocks, 128, 0, st>>>(d, G);
         count_launch();
         BFIR_CUDA(cudaGetLastError());
     }
@@ -766,17 +778,21 @@ int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0
     return rc;
 }
 
-// One pair through the stage pipeline (one group). Pair k = blocks (t, t+1), t = host_blockcounter:
-//   forward stream:  after the pair sum k-2 (which still reads the slots these transforms overwrite): forward t, t+1
-//   engine's stream: after those transforms and after the inverse transforms of pair k-2 (same accumulators): pair sum
-//   inverse stream:  after the pair sum: inverse t, t+1 (these advance the device block counter)
+// One call of NB = 2 or 4 consecutive blocks through the stage pipeline (one group). Call k = blocks t .. t+NB-1,
+// t = host_blockcounter:
+//   forward stream:  after the partition sum of call k-2 (which still reads the slots these transforms overwrite;
+//                    call k-1's sum reaches back to block t-P-3 at most, and the delay line has P+7 slots, so the
+//                    slots of blocks t .. t+3 are not among its operands): forward t .. t+NB-1
+//   engine's stream: after those transforms and after the inverse transforms of call k-2 (same accumulators): ONE
+//                    partition-sum launch for the NB blocks (pair / multi kernel)
+//   inverse stream:  after the sum: inverse t .. t+NB-1 (these advance the device block counter)
 // The inputs must be complete when the call is made (nothing orders the forward stream after later work on the
 // engine's stream -- that is the point).
-int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1)
+int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out)
 {
     int rc;
     const size_t cbuf = (size_t)N * rs;
-    for (int k = 0; k < 2; k++) for (int j = 0; j < 2; j++) if (!sp_acc[k][j]) BFIR_CUDA(cudaMalloc(&sp_acc[k][j], cbuf * Ct));
+    for (int k = 0; k < 2; k++) for (int j = 0; j < nb; j++) if (!sp_acc[k][j]) BFIR_CUDA(cudaMalloc(&sp_acc[k][j], cbuf * Ct));
     if (!sp_open) {
         if ((rc = close_async()) != BFIR_OK) return rc;
         BFIR_CUDA(cudaEventRecord(fork_ev, stream));
@@ -789,31 +805,34 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
     const int par = (int)(sp_pairs & 1ull);
     tail_ready = false;
     use_abs = true;
-    // forward transforms of both blocks on the forward stream
+    // forward transforms of all blocks on the forward stream
     BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, sp_mac_done[par], 0));
     stage_stream = sp_fwd;
     prof_suppress = true;
-    rc = front_group(0, d_in0, nullptr, true);
-    fwd_block_offset = 1;
-    if (rc == BFIR_OK) rc = front_group(0, d_in1, nullptr, true);
+    rc = BFIR_OK;
+    for (int b = 0; b < nb && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
     fwd_block_offset = 0;
     prof_suppress = false;
     stage_stream = nullptr;
     if (rc != BFIR_OK) { use_abs = false; return rc; }
     BFIR_CUDA(cudaEventRecord(sp_fwd_done[par], sp_fwd));
-    // pair sum on the engine's stream
+    // partition sum on the engine's stream
     BFIR_CUDA(cudaStreamWaitEvent(stream, sp_fwd_done[par], 0));
     BFIR_CUDA(cudaStreamWaitEvent(stream, sp_inv_done[par], 0));
     prof(0);
-    prof(1);   // profiling: only the pair sum's interval (1 -> 2) means anything in this mode
+    prof(1);   // profiling: only the partition sum's interval (1 -> 2) means anything in this mode
     MacArgs m = {};
     m.fdl = fdl; m.coeffs = coeffs; m.acc = sp_acc[par][0]; m.acc_next = sp_acc[par][1];
+    for (int b = 0; b < nb; b++) m.acc_multi[b] = sp_acc[par][b];
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state; m.ch_base = 0;
     m.use_abs_block = 1; m.abs_block = host_blockcounter;
-    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), Ct);
-    mac_kernel_t mk = rs == 4 ? mac_pair_kernel_for_split<float>(mac_split) : mac_pair_kernel_for_split<double>(mac_split);
+    const int split = nb == 4 ? quad_split : mac_split;
+    dim3 grid((N / 8 + 256 / split - 1) / (256 / split), Ct);
+    mac_kernel_t mk;
+    if (nb == 4) mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split);
+    else mk = rs == 4 ? mac_pair_kernel_for_split<float>(split) : mac_pair_kernel_for_split<double>(split);
     mk<<<grid, 256, 0, stream>>>(m);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
@@ -825,10 +844,7 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
     BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
     stage_stream = sp_inv;
     prof_suppress = true;
-    acc_override = sp_acc[par][0];
-    rc = back_group(0, d_out0);
-    acc_override = sp_acc[par][1];
-    if (rc == BFIR_OK) rc = back_group(0, d_out1);
+    for (int b = 0; b < nb && rc == BFIR_OK; b++) { acc_override = sp_acc[par][b]; rc = back_group(0, d_out[b]); }
     acc_override = nullptr;
     prof_suppress = false;
     stage_stream = nullptr;
@@ -836,9 +852,15 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
     if (rc != BFIR_OK) return rc;
     BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
     sp_pairs++;
-    finish_block();
-    finish_block();
+    for (int b = 0; b < nb; b++) finish_block();
     return BFIR_OK;
+}
+
+int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1)
+{
+    const void *in[2] = { d_in0, d_in1 };
+    void *out[2] = { d_out0, d_out1 };
+    return staged_blocks(2, in, out);
 }
 
 // four consecutive blocks of one group with ONE partition-sum launch (single precision): see partition_mac_multi_kernel
@@ -861,8 +883,9 @@ int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
-    dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), ns * C);
-    mac_kernel_t mk = mac_quad_kernel_for_split(mac_split);
+    const int qsplit = quad_split;
+    dim3 grid((N / 8 + 256 / qsplit - 1) / (256 / qsplit), ns * C);
+    mac_kernel_t mk = rs == 4 ? mac_quad_kernel_for_split<float>(qsplit) : mac_quad_kernel_for_split<double>(qsplit);
     mk<<<grid, 256, 0, gstream(g)>>>(m);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
@@ -877,14 +900,16 @@ int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
 
 // four consecutive blocks on device buffers (joined like bfir_run_device). Single precision, steady state, no crossbar;
 // otherwise two pair steps.
-int Engine::enqueue_quad(const void *const d_in[4], void *const d_out[4])
+int Engine::enqueue_quad(const void *const d_in[4], void *const d_out[4], bool staged)
 {
     int rc;
-    if (!pair_ok() || rs != 4 || xbar) {
-        rc = enqueue_pair(d_in[0], d_in[1], d_out[0], d_out[1], false);
-        if (rc == BFIR_OK) rc = enqueue_pair(d_in[2], d_in[3], d_out[2], d_out[3], false);
+    if (!pair_ok() || xbar) {
+        rc = enqueue_pair(d_in[0], d_in[1], d_out[0], d_out[1], staged, staged);
+        if (rc == BFIR_OK) rc = enqueue_pair(d_in[2], d_in[3], d_out[2], d_out[3], staged, staged);
         return rc;
     }
+    if (staged && n_groups == 1 && staged_enabled) return staged_blocks(4, d_in, d_out);
+    if ((rc = close_staged()) != BFIR_OK) return rc;
     const size_t cbuf = (size_t)N * rs;
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
     for (int k = 0; k < 2; k++) if (!acc_quad[k]) BFIR_CUDA(cudaMalloc(&acc_quad[k], cbuf * Ct));
@@ -1426,6 +1451,15 @@ int bfir_run_device_quad(bfir_engine *e, const void *const d_in[4], void *const 
     return e->impl.enqueue_quad(d_in, d_out);
 }
 
+int bfir_run_device_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4])
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_in == nullptr || d_out == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 4; b++) if (d_in[b] == nullptr || d_out[b] == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.enqueue_quad(d_in, d_out, true);
+}
+
 long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, void *out0, void *out1)
 {
     int rc = check_ready(e);
@@ -1616,6 +1650,7 @@ int bfir_set_groups(bfir_engine *e, int n_groups)
 
 int bfir_get_groups(bfir_engine *e) { return e ? e->impl.n_groups : BFIR_ERR_INVALID; }
 int bfir_get_mac_split(bfir_engine *e) { return e ? e->impl.mac_split : BFIR_ERR_INVALID; }
+int bfir_get_quad_split(bfir_engine *e) { return e ? e->impl.quad_split : BFIR_ERR_INVALID; }
 
 int bfir_set_stream(bfir_engine *e, void *cuda_stream)
 {

@@ -314,9 +314,17 @@ __global__ void __launch_bounds__(256) partition_mac_multi_kernel(const MacArgs 
 }
 
 typedef void (*mac_kernel_t)(const MacArgs);
-// four blocks per launch, single precision (shared memory: (SPLIT-1) * 256/SPLIT * 32 floats <= 32 KB)
-inline mac_kernel_t mac_quad_kernel_for_split(int split)
+// four blocks per launch. Shared memory of the slice reduction: (SPLIT-1) * 256/SPLIT * 32 reals, i.e. <= 32 KB in
+// single precision and 48 KB at SPLIT 4 in double precision (the static limit), so double stops at SPLIT 4
+template <class T> inline mac_kernel_t mac_quad_kernel_for_split(int split)
 {
+    if (sizeof(T) == 8) {
+        switch (split) {
+        case 1: return partition_mac_multi_kernel<T, 4, 1>;
+        case 2: return partition_mac_multi_kernel<T, 4, 2>;
+        default: return partition_mac_multi_kernel<T, 4, 4>;
+        }
+    }
     switch (split) {
     case 1: return partition_mac_multi_kernel<float, 4, 1>;
     case 2: return partition_mac_multi_kernel<float, 4, 2>;
@@ -325,6 +333,7 @@ inline mac_kernel_t mac_quad_kernel_for_split(int split)
     default: return partition_mac_multi_kernel<float, 4, 16>;
     }
 }
+inline int mac_quad_split(int realsize, int split) { return realsize == 8 && split > 4 ? 4 : split; }
 template <class T> inline mac_kernel_t mac_pair_kernel_for_split(int split)
 {
     constexpr int U = sizeof(T) == 8 ? 2 : 4;

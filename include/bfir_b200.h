@@ -186,10 +186,15 @@ int bfir_join(bfir_engine *e);
 #define BFIR_PAIR_STAGED 2
 int bfir_run_device_pair(bfir_engine *e, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, int pipelined);
 long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, void *out0, void *out1);
-/* Four consecutive blocks with one partition-sum launch, single-precision engines (their kernels have the registers
- * for four accumulators): per channel (2P + 3 split + 4) N realsize bytes for four blocks instead of 4 (2P + 1) N realsize.
- * Device buffers, joined like bfir_run_device. Other engines, and the cases listed above, run two pairs. */
+/* Four consecutive blocks with one partition-sum launch: a window of four delay-line spectra slides over the
+ * partitions, so per channel (2P + 3 split + 4) N realsize bytes move for four blocks instead of 4 (2P + 1) N realsize
+ * (split = partition slices per CTA, 1 for large batches). Both precisions (double: 214 registers, one CTA per SM).
+ * Device buffers. bfir_run_device_quad is joined like bfir_run_device; bfir_run_device_quad_staged runs the four blocks
+ * through the stage pipeline under the contract of BFIR_PAIR_STAGED (inputs complete at call time, outputs visible
+ * after bfir_join / bfir_sync). With a crossbar, on a partition shard, with a pending filter swap and while the delay
+ * line is still filling the call runs two pairs (or four single blocks). */
 int bfir_run_device_quad(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
+int bfir_run_device_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 
 /* brutefir::reset (brutefir.cpp:347-367): zeroes counters and overflow statistics, NOT the buffers */
 int bfir_reset(bfir_engine *e);
@@ -232,6 +237,7 @@ int bfir_set_groups(bfir_engine *e, int n_groups);
 int bfir_get_groups(bfir_engine *e);
 /* partition slices per CTA the engine chose for its partition-sum kernels (reporting only) */
 int bfir_get_mac_split(bfir_engine *e);
+int bfir_get_quad_split(bfir_engine *e);   /* the same for the four-block kernel */
 
 /* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the engine's own. */
 int bfir_set_stream(bfir_engine *e, void *cuda_stream);

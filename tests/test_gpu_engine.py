@@ -787,9 +787,63 @@ def test_stage_pipeline_equals_single_blocks(pkg, rs, out_fmt, dither):
             assert dd.max() <= 4 and dd.mean() < 0.5, (b, dd.max(), dd.mean())
 
 
+@pytest.mark.parametrize("rs,out_fmt,P", [(8, 10, 5), (4, 8, 5), (8, 10, 2), (4, 4, 7)])
+def test_stage_pipeline_quads_equal_single_blocks(pkg, rs, out_fmt, P):
+    """bfir_run_device_quad_staged: four blocks per call through the stage pipeline (four forward transforms on the
+    forward stream under the previous call's partition sum, ONE four-block partition-sum launch -- both precisions
+    -- and four inverse transforms behind it), mixed with staged pairs, a join, a plain quad and single blocks: same
+    output as block by block. The delay line has P + 7 slots so that the next call's transforms never touch a slot
+    the running sum still reads; P = 2 makes every slot turn over within two calls."""
+    import torch
+    L, C, S = 512, 2, 4
+    in_fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt = np.float32 if rs == 4 else np.float64
+    nb = pkg.FORMAT_BYTES[out_fmt]
+    h = [decay_filter(c, L * P) for c in range(C * S)]
+    single = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, False, n_streams=S, n_groups=1)
+    staged = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, False, n_streams=S, n_groups=1)
+    assert single.set_coeff(h, P) == 0 and staged.set_coeff(h, P) == 0
+    nblk = 64
+    x = white_noise(35, nblk * L, C * S).astype(dt)
+    blocks = [np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2)).ravel() for b in range(nblk)]
+    d_in = [torch.from_numpy(b).cuda() for b in blocks]
+    n_out = S * L * C * nb
+    out_s = [torch.zeros(n_out, dtype=torch.uint8, device="cuda") for _ in range(nblk)]
+    out_t = [torch.zeros(n_out, dtype=torch.uint8, device="cuda") for _ in range(nblk)]
+    torch.cuda.synchronize()
+    for b in range(nblk):
+        single.run_device(d_in[b], out_s[b])
+    b = 0
+    while b < nblk:
+        if b in (24, 26):                            # staged pairs between staged quads
+            staged.run_device_pair(d_in[b], d_in[b + 1], out_t[b], out_t[b + 1], pipelined="staged")
+            b += 2
+            continue
+        if b == 40:                                  # a plain (joined) quad, then single blocks
+            staged.run_device_quad(d_in[b:b + 4], out_t[b:b + 4])
+            b += 4
+            for _ in range(4):
+                staged.run_device(d_in[b], out_t[b])
+                b += 1
+            continue
+        staged.run_device_quad(d_in[b:b + 4], out_t[b:b + 4], staged=True)
+        if b == 12:
+            staged.join()
+        b += 4
+    assert single.sync() == 0 and staged.sync() == 0
+    assert single.blockcounter() == staged.blockcounter() == nblk
+    for b in range(nblk):
+        a, t = out_s[b].cpu().numpy(), out_t[b].cpu().numpy()
+        if out_fmt in (8, 10):
+            assert rel_rms(t.view(dt), a.view(dt)) < (2e-6 if rs == 4 else 1e-13), b
+        else:
+            dd = np.abs(decode_raw(a, out_fmt, C).ravel().astype(np.float64) - decode_raw(t, out_fmt, C).ravel())
+            assert dd.max() <= 1, (b, dd.max())
+
+
 @pytest.mark.parametrize("rs,groups,P", [(4, 1, 6), (4, 3, 9), (8, 2, 5), (4, 2, 2)])
 def test_block_quads_equal_single_blocks(pkg, rs, groups, P):
-    """bfir_run_device_quad: four blocks per partition-sum launch on single-precision engines (double: two pairs);
+    """bfir_run_device_quad: four blocks per partition-sum launch (both precisions);
     same output as block by block up to the summation order, from the first block on (fall-back while filling)."""
     import torch
     L, C, S = 256, 2, 3

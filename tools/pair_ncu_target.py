@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""A few two-block steps of cfg1 x 16 streams on one stream, for ncu (profiles/README.md):
-ncu --set full --clock-control none -k regex:partition_mac_pair -s 2 -c 2 python tools/pair_ncu_target.py"""
+"""A few two-block steps (or, with --quads, four-block steps) of cfg1 x 16 streams on one stream, for ncu
+(profiles/README.md):
+ncu --set full --clock-control none -k regex:partition_mac_pair -s 2 -c 2 python tools/pair_ncu_target.py
+ncu --set full --clock-control none -k regex:partition_mac_multi -s 2 -c 2 python tools/pair_ncu_target.py --quads"""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,10 +14,14 @@ base = np.random.default_rng(0).standard_normal(L * P) * np.exp(-6.9 * np.arange
 assert e.set_coeff([np.roll(base, c) for c in range(S * C)], P) == 0
 n = S * L * C
 d_in = [torch.rand(n, dtype=torch.float64, device="cuda") for _ in range(4)]
-d_out = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(2)]
+d_out = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(4)]
 for b in range(P + 2):
     e.run_device(d_in[b % 4], d_out[0])
-for b in range(0, 12, 2):
-    e.run_device_pair(d_in[b % 4], d_in[(b + 1) % 4], d_out[0], d_out[1])
+if "--quads" in sys.argv:
+    for b in range(0, 24, 4):
+        e.run_device_quad(d_in, d_out)
+else:
+    for b in range(0, 12, 2):
+        e.run_device_pair(d_in[b % 4], d_in[(b + 1) % 4], d_out[0], d_out[1])
 assert e.sync() == 0
 print("ok")
