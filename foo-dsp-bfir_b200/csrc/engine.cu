@@ -142,6 +142,7 @@ struct Engine {
     int enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined, bool staged = false);
     long long run_host_async_pair(const void *in0, const void *in1, void *out0, void *out1);
     int mac_split = 1;              // partition slices per CTA of the MAC kernel
+    int quad_threads = 128;         // threads per CTA of the double-precision four-block kernel (BFIR_QUAD_THREADS = 128 | 256; measured 1.5 % apart)
     int quad_split = 1;             // the same for the four-block kernel (one CTA per SM in double precision: fewer slices)
     int fft_r0 = 1;                 // CTAs per transform (rfft_choose_r0)
     // optional per-kernel timing (bfir_set_profiling)
@@ -294,6 +295,7 @@ int Engine::init(const bfir_config_t &c)
         const long long resident = 148LL * (rs == 8 ? 1 : 2);
         quad_split = 1;
         while (quad_split < (rs == 8 ? 4 : 16) && quad_split * 2 <= P && group_threads * quad_split / 256 < 4 * resident) quad_split *= 2;
+        if (const char *env = getenv("BFIR_QUAD_THREADS")) { const int v = atoi(env); if (v == 128 || v == 256) quad_threads = v; }
         if (const char *env = getenv("BFIR_QUAD_SPLIT")) {
             const int v = atoi(env);
             if ((v == 1 || v == 2 || v == 4 || (rs == 4 && (v == 8 || v == 16))) && v <= P) quad_split = v;
@@ -829,11 +831,12 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out)
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state; m.ch_base = 0;
     m.use_abs_block = 1; m.abs_block = host_blockcounter;
     const int split = nb == 4 ? quad_split : mac_split;
-    dim3 grid((N / 8 + 256 / split - 1) / (256 / split), Ct);
+    const int mthreads = nb == 4 && rs == 8 ? quad_threads : 256;
+    dim3 grid((N / 8 + mthreads / split - 1) / (mthreads / split), Ct);
     mac_kernel_t mk;
-    if (nb == 4) mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split);
+    if (nb == 4) mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split, mthreads);
     else mk = rs == 4 ? mac_pair_kernel_for_split<float>(split) : mac_pair_kernel_for_split<double>(split);
-    mk<<<grid, 256, 0, stream>>>(m);
+    mk<<<grid, mthreads, 0, stream>>>(m);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     prof(2);
@@ -883,10 +886,10 @@ int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
     m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
-    const int qsplit = quad_split;
-    dim3 grid((N / 8 + 256 / qsplit - 1) / (256 / qsplit), ns * C);
-    mac_kernel_t mk = rs == 4 ? mac_quad_kernel_for_split<float>(qsplit) : mac_quad_kernel_for_split<double>(qsplit);
-    mk<<<grid, 256, 0, gstream(g)>>>(m);
+    const int qsplit = quad_split, mthreads = rs == 8 ? quad_threads : 256;
+    dim3 grid((N / 8 + mthreads / qsplit - 1) / (mthreads / qsplit), ns * C);
+    mac_kernel_t mk = rs == 4 ? mac_quad_kernel_for_split<float>(qsplit) : mac_quad_kernel_for_split<double>(qsplit, mthreads);
+    mk<<<grid, mthreads, 0, gstream(g)>>>(m);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     if (g == 0) prof(2);

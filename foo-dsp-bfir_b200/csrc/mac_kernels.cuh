@@ -242,10 +242,10 @@ __global__ void __launch_bounds__(256) partition_mac_pair_kernel(const MacArgs a
 // costs one coefficient and one delay-line load for NB multiply-accumulates: per channel
 // (2 P_eff + (NB-1) SPLIT + NB) N rs bytes for NB blocks instead of NB (2 P_eff + 1) N rs.
 // Block t+b uses X[t+b-i] at partition i; all NB forward transforms have run (needs P + NB - 1 delay-line slots).
-template <class T, int NB, int SPLIT>
-__global__ void __launch_bounds__(256) partition_mac_multi_kernel(const MacArgs a)
+template <class T, int NB, int SPLIT, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS) partition_mac_multi_kernel(const MacArgs a)
 {
-    constexpr int GPC = 256 / SPLIT;
+    constexpr int GPC = THREADS / SPLIT;
     const int slice = threadIdx.x / GPC, gl = threadIdx.x - slice * GPC;
     const int g = blockIdx.x * GPC + gl;
     const int ch = blockIdx.y + a.ch_base;
@@ -316,9 +316,18 @@ __global__ void __launch_bounds__(256) partition_mac_multi_kernel(const MacArgs 
 typedef void (*mac_kernel_t)(const MacArgs);
 // four blocks per launch. Shared memory of the slice reduction: (SPLIT-1) * 256/SPLIT * 32 reals, i.e. <= 32 KB in
 // single precision and 48 KB at SPLIT 4 in double precision (the static limit), so double stops at SPLIT 4
-template <class T> inline mac_kernel_t mac_quad_kernel_for_split(int split)
+template <class T> inline mac_kernel_t mac_quad_kernel_for_split(int split, int threads = 256)
 {
     if (sizeof(T) == 8) {
+        // 128 threads: 214 registers x 128 = 27 K registers per CTA, so that a transform CTA (256 threads x 128
+        // registers, 70 KB) fits beside it on the SM when both run at once (stage pipeline)
+        if (threads == 128) {
+            switch (split) {
+            case 1: return partition_mac_multi_kernel<T, 4, 1, 128>;
+            case 2: return partition_mac_multi_kernel<T, 4, 2, 128>;
+            default: return partition_mac_multi_kernel<T, 4, 4, 128>;
+            }
+        }
         switch (split) {
         case 1: return partition_mac_multi_kernel<T, 4, 1>;
         case 2: return partition_mac_multi_kernel<T, 4, 2>;

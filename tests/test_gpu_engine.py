@@ -787,7 +787,7 @@ def test_stage_pipeline_equals_single_blocks(pkg, rs, out_fmt, dither):
             assert dd.max() <= 4 and dd.mean() < 0.5, (b, dd.max(), dd.mean())
 
 
-@pytest.mark.parametrize("rs,out_fmt,P", [(8, 10, 5), (4, 8, 5), (8, 10, 2), (4, 4, 7)])
+@pytest.mark.parametrize("rs,out_fmt,P", [(8, 10, 5), (4, 8, 5), (8, 10, 2), (4, 2, 7), (8, 4, 3)])
 def test_stage_pipeline_quads_equal_single_blocks(pkg, rs, out_fmt, P):
     """bfir_run_device_quad_staged: four blocks per call through the stage pipeline (four forward transforms on the
     forward stream under the previous call's partition sum, ONE four-block partition-sum launch -- both precisions
@@ -838,7 +838,7 @@ def test_stage_pipeline_quads_equal_single_blocks(pkg, rs, out_fmt, P):
             assert rel_rms(t.view(dt), a.view(dt)) < (2e-6 if rs == 4 else 1e-13), b
         else:
             dd = np.abs(decode_raw(a, out_fmt, C).ravel().astype(np.float64) - decode_raw(t, out_fmt, C).ravel())
-            assert dd.max() <= 4 and dd.mean() < 0.5, (b, dd.max(), dd.mean())   # 24-bit samples: 1 LSB = float32 resolution; summation order differs
+            assert dd.max() <= 1, (b, dd.max())      # S16 from the float engine, S24 from the double one: within 1 LSB
 
 
 @pytest.mark.parametrize("rs,groups,P", [(4, 1, 6), (4, 3, 9), (8, 2, 5), (4, 2, 2)])
