@@ -158,6 +158,32 @@ template <class T> BFIR_HD int32_t quantise(T x, T stat, T rmin, T rmax, int32_t
     return s;
 }
 
+// Branch-free forms of the two statistics updates above for the unrolled store loops of the transform kernels
+// (there every branch costs its resolve latency sixteen times per thread, and `largest` as a double costs a
+// conversion and an FP64 compare per sample in single-precision engines): the per-thread maximum is kept in T --
+// exact, |x| converts to double without rounding and max does not round -- and merged into OverflowAcc once.
+// Same counters as store_raw_float / quantise for every input, NaN included (all comparisons false).
+template <class T> BFIR_HD void float_stats_nb(T x, T rmax, T &largest, unsigned int &n_overflows)
+{
+    const T ax = x < (T)0 ? -x : x;
+    n_overflows += ax > rmax ? 1u : 0u;
+    largest = ax > largest ? ax : largest;
+}
+
+template <class T> BFIR_HD int32_t quantise_nb(T x, T rmin, T rmax, int32_t imin, int32_t imax, T &largest, unsigned int &n_overflows, int32_t &intlargest)
+{
+    const bool neg = x < (T)0;
+    const bool ovn = neg && x <= rmin, ovp = !neg && x > rmax, ov = ovn || ovp;
+    int32_t s = real_to_int_rz<T>(x) - (neg ? 1 : 0);
+    s = ovn ? imin : (ovp ? imax : s);
+    const T ax = neg ? -x : x;
+    n_overflows += ov ? 1u : 0u;
+    largest = (ov && ax > largest) ? ax : largest;
+    const int32_t as = neg ? (int32_t)(0u - (uint32_t)s) : s;
+    intlargest = (!ov && as > intlargest) ? as : intlargest;
+    return s;
+}
+
 BFIR_HD void store_raw_int(uint8_t *p, int fmt, int32_t s)
 {
     const uint32_t u = (uint32_t)s;
@@ -177,6 +203,25 @@ BFIR_HD void int_limits(int fmt, int32_t &imin, int32_t &imax)
     const int bits = fmt_bytes(fmt) << 3;
     imin = (int32_t)(0u - (1u << (bits - 1)));
     imax = (int32_t)((1u << (bits - 1)) - 1u);
+}
+
+// x + 0.5 without contraction (the no-dither requantiser's rounding offset)
+template <class T> BFIR_HD T half_up(T x)
+{
+#ifdef __CUDA_ARCH__
+    return sizeof(T) == 4 ? (T)__fadd_rn((float)x, 0.5f) : (T)__dadd_rn((double)x, 0.5);
+#else
+    return x + (T)0.5;
+#endif
+}
+
+// float / double sample in the raw format FMT (compile-time), no statistics
+template <class T, int FMT> BFIR_HD void store_raw_real(uint8_t *p, T x)
+{
+    if (FMT == FMT_FLOAT_LE) *(float *)p = (float)x;
+    else if (FMT == FMT_FLOAT_BE) *(uint32_t *)p = bswap32(float_as_u32((float)x));
+    else if (FMT == FMT_FLOAT64_LE) *(double *)p = (double)x;
+    else *(uint64_t *)p = bswap64(double_as_u64((double)x));
 }
 
 // integer output without dither: real2raw*_no_dither -> dither*_real2int_no_dither

@@ -1,6 +1,7 @@
 // Dispatch table over the per-size FFT translation units (fft_inst.cu).
 #include "fft_dispatch.hpp"
 #include <cstdlib>
+#include <cstdint>
 
 namespace bfir {
 
@@ -94,21 +95,34 @@ cudaError_t launch_cfft_inverse(int realsize, int log2m, int batch, cudaStream_t
     return (realsize == 4 ? kCfftF32 : kCfftF64)[log2m - kMinLog2M](batch, stream, a);
 }
 
-cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw)
+// bulk-copy staging of the contiguous operands (rfft_kernels.cuh): needs 16-byte aligned sources and at least 16 bytes
+static bool tma_enabled()
+{
+    static const bool on = [] { const char *env = getenv("BFIR_FFT_TMA"); return env ? atoi(env) != 0 : true; }();
+    return on;
+}
+
+cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a0, const void *tw)
 {
     if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
     const int sub = log2m - (r0 == 2 ? 1 : 0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
+    FwdArgs a = a0;
+    a.tma = (tma_enabled() && r0 == 1 && a.in_mode == IN_RAW_PREV && a.prev != nullptr && ((uintptr_t)a.prev & 15) == 0
+             && (((size_t)realsize << log2m) & 15) == 0) ? 1 : 0;
     // table length N = 2 * 2^log2m: shift for the sub-transform twiddles, 0 for the W_N^k of the split step
     if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, true)) return (realsize == 4 ? kFwdF32E8 : kFwdF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
     return (realsize == 4 ? kFwdF32 : kFwdF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }
 
-cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw)
+cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const InvArgs &a0, const void *tw)
 {
     if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
     const int sub = log2m - (r0 == 2 ? 1 : 0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
+    InvArgs a = a0;
+    a.tma = (tma_enabled() && r0 == 1 && a.head_x == nullptr && ((uintptr_t)a.in & 15) == 0
+             && (((size_t)a.in_stride_x * realsize) & 15) == 0) ? 1 : 0;
     if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return (realsize == 4 ? kInvF32E8 : kInvF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
     return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
 }

@@ -79,6 +79,7 @@ struct FwdArgs {
     // IN_COEFF
     int coeff_len;           // valid coefficients per channel
     int *nonfinite;          // set to 1 when a scaled coefficient is NaN/Inf (fftw_convolver.cpp:493-497)
+    int tma;                 // 1: IN_RAW_PREV, one CTA per transform: the previous block arrives by bulk copy (set by launch_rfft_forward)
 };
 
 // index of the block a forward launch transforms
@@ -107,6 +108,7 @@ struct InvArgs {
     const void *head_h;      // coefficients [channels][..][N], partition 0 at the start of each channel
     long long head_x_stride, head_h_stride; // elements per channel
     const int *head_blocks;  // [channels] coefficient partitions loaded (0: the channel has no filter)
+    int tma;                 // 1: one CTA per transform, no head term: the input spectrum arrives by bulk copy (set by launch_rfft_inverse)
 };
 
 template <class T> BFIR_HD T tw_re(const cpx<T> &w) { return w.x; }
@@ -204,6 +206,50 @@ BFIR_HD cpx<T> fwd_elem(int m, int by, int r, const FwdArgs &a, const FwdCtx<T> 
     }
 }
 
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// Bulk-asynchronous staging (TMA, cp.async.bulk + mbarrier) of the CONTIGUOUS operands of a transform into the CTA's
+// shared-memory buffer, which is idle until the first pass stores into it: the inverse kernel's input spectrum
+// (N reals of one channel) and the forward kernel's previous block (L reals). One elected thread arms the barrier
+// with the byte count and issues the copies; the TMA unit streams the lines while the threads compute their twiddles
+// and issue the loads that cannot be bulk copies (the interleaved raw block); everybody then waits on the barrier's
+// phase. Replaces 16-32 LDG.128 per thread that each had to be tracked by the LSU.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "BFIR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra BFIR_DONE;\n"
+                 "bra BFIR_WAIT;\n"
+                 "BFIR_DONE:\n"
+                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: `bytes` (a multiple of 16) from global to shared memory in pieces of at most 32 KB
+__device__ __forceinline__ void bulk_stage(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    mbar_expect_tx(bar, bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u)
+        bulk_g2s((char *)dst + off, (const char *)src + off, min(32768u, bytes - off), bar);
+}
+
+#endif
+
 // The sample format is a run-time engine parameter but must be a compile-time constant inside the unrolled load /
 // store loops: with the switch inside load_raw() every sample's load sat behind its own branch, and the loads of
 // one thread were issued one by one, each waiting out a full memory latency (ncu source page, round 1: 40 % of the
@@ -221,13 +267,30 @@ BFIR_HD cpx<T> fwd_elem(int m, int by, int r, const FwdArgs &a, const FwdCtx<T> 
 // engine input (IN_RAW_PREV) for one thread, sample format known at compile time: the raw samples of the current
 // block (complex index n = t + j NTs of the block, i.e. frames 2n and 2n+1) and the previous block from its planar
 // ping-pong buffer; all loads are independent and issued back to back
-template <class T, int LOG2MS, int R0, int LOG2E, int FMT>
-BFIR_HD void fwd_load_raw_prev(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> wpre, const FwdCtx<T> &c)
+template <class T, int LOG2MS, int R0, int LOG2E, int FMT, bool STAGED = false>
+BFIR_HD void fwd_load_raw_prev(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> wpre, const FwdCtx<T> &c, const cpx<T> *staged_prev = NULL, void *bar = NULL)
 {
     constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E;
     constexpr int NH = R0 == 1 ? E / 2 : E;       // complex points of the current block per thread
     constexpr int CH = R0 == 2 ? 4 : NH;          // complex loads in flight per batch and source (R0 = 2: register budget)
     typedef cpx<T> C;
+    if constexpr (STAGED) {
+        // R0 = 1: the raw samples first (their loads are in flight while the bulk copy of the previous block lands),
+        // then the previous block out of shared memory
+        C hi[NH];
+#pragma unroll
+        for (int j = 0; j < NH; j++) {
+            const uint8_t *p = c.raw + (long long)(2 * (t + j * NT)) * c.step;
+            hi[j] = mk<T>(load_raw<T>(p, FMT), load_raw<T>(p + c.step, FMT));
+        }
+#ifdef __CUDA_ARCH__
+        mbar_wait((uint64_t *)bar, 0);
+#endif
+#pragma unroll
+        for (int j = 0; j < NH; j++) v[j] = staged_prev[t + j * NT];
+#pragma unroll
+        for (int j = 0; j < NH; j++) { c.prev_wr[t + j * NT] = hi[j]; v[j + NH] = hi[j]; }
+    } else {
 #pragma unroll
     for (int j0 = 0; j0 < NH; j0 += CH) {
         C lo[CH], hi[CH];
@@ -253,11 +316,13 @@ BFIR_HD void fwd_load_raw_prev(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<
             }
         }
     }
+    }
 }
 
 // forward, phase 0: thread t builds s_r[n], n = t + i*NTs
-template <class T, int LOG2MS, int R0, int LOG2E = 4>
-BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
+template <class T, int LOG2MS, int R0, int LOG2E = 4, bool STAGED = false>
+BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a,
+                      const cpx<T> *staged_prev = NULL, void *bar = NULL)
 {
     constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, LOG2M = LOG2MS + (R0 == 2 ? 1 : 0);
     typedef cpx<T> C;
@@ -266,7 +331,7 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], con
     if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];     // W_M^t = W_N^(2t); W_M^(t + i NTs) = W_M^t * root32(i)
     const FwdCtx<T> ctx = fwd_ctx<T, LOG2M>(bx, by, a);
     if (a.in_mode == IN_RAW_PREV) {
-        BFIR_FMT_SWITCH(a.fmt, (fwd_load_raw_prev<T, LOG2MS, R0, LOG2E, FMT>(t, r, v, wpre, ctx)))
+        BFIR_FMT_SWITCH(a.fmt, (fwd_load_raw_prev<T, LOG2MS, R0, LOG2E, FMT, STAGED>(t, r, v, wpre, ctx, staged_prev, bar)))
     } else if (R0 == 1) {
 #pragma unroll
         for (int i = 0; i < E / 2; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, by, r, a, ctx, bad);
@@ -413,24 +478,32 @@ template <class T, int LOG2MS, int R0, int LOG2E, int FMT>
 BFIR_HD void inv_store_raw(int t, int r, const cpx<T> (&v)[1 << LOG2E], uint8_t *raw, long long step, T ovf_max, OverflowAcc &acc)
 {
     constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E;
+    T lg = (T)0;
+    unsigned int novf = 0;
     if constexpr (FMT >= FMT_FLOAT_LE) {
 #pragma unroll
         for (int i = 0; i < E / 2; i++) {
             uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
-            store_raw_float<T>(p, FMT, v[i].x, ovf_max, acc);
-            store_raw_float<T>(p + step, FMT, v[i].y, ovf_max, acc);
+            float_stats_nb<T>(v[i].x, ovf_max, lg, novf);
+            float_stats_nb<T>(v[i].y, ovf_max, lg, novf);
+            store_raw_real<T, FMT>(p, v[i].x);
+            store_raw_real<T, FMT>(p + step, v[i].y);
         }
     } else {
         int32_t imin, imax;
         int_limits(FMT, imin, imax);
         const T rmin = (T)imin, rmax = (T)imax;
+        int32_t il = 0;
 #pragma unroll
         for (int i = 0; i < E / 2; i++) {
             uint8_t *p = raw + (long long)(2 * (R0 * (t + i * NT) + r)) * step;
-            store_raw_quantised<T>(p, FMT, v[i].x, rmin, rmax, imin, imax, acc);
-            store_raw_quantised<T>(p + step, FMT, v[i].y, rmin, rmax, imin, imax, acc);
+            store_raw_int(p, FMT, quantise_nb<T>(half_up<T>(v[i].x), rmin, rmax, imin, imax, lg, novf, il));
+            store_raw_int(p + step, FMT, quantise_nb<T>(half_up<T>(v[i].y), rmin, rmax, imin, imax, lg, novf, il));
         }
+        if (il > acc.intlargest) acc.intlargest = il;
     }
+    acc.n_overflows += novf;
+    if ((double)lg > acc.largest) acc.largest = (double)lg;
 }
 
 // inverse, phase 1: v[i] = z[R0 n + r], n = t + i*NTs;  x[2m] = Re z[m], x[2m+1] = Im z[m]
@@ -505,7 +578,19 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
     const int t = threadIdx.x, bx = blockIdx.x + a.ch_base, by = blockIdx.y, r = blockIdx.z;
     cpx<T> v[1 << LOG2E];
-    fwd_load<T, LOG2MS, R0, LOG2E>(t, bx, by, r, v, tw, tw_shift_n, a);
+    bool staged = false;
+    if constexpr (R0 == 1) staged = a.tma != 0;
+    if constexpr (R0 == 1) if (staged) {
+        // previous block: L reals, contiguous in the planar ping-pong buffer -> head of the (still idle) FFT buffer
+        __shared__ __align__(8) uint64_t bar;
+        constexpr int L = 1 << LOG2MS;
+        if (t == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (t == 0) bulk_stage(smem_raw, (const T *)a.prev + ((long long)(a.prev_parity & 1u) * a.n_channels + bx) * L, (uint32_t)(L * sizeof(T)), &bar);
+        fwd_load<T, LOG2MS, R0, LOG2E, true>(t, bx, by, r, v, tw, tw_shift_n, a, smem, &bar);
+        __syncthreads();                               // every thread has read its part of the staged block
+    }
+    if (!staged) fwd_load<T, LOG2MS, R0, LOG2E>(t, bx, by, r, v, tw, tw_shift_n, a);
     fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run(t, v, smem, tw, tw_shift_m);
     BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, v, smem);
     __syncthreads();
@@ -519,7 +604,20 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
     cpx<T> *smem = reinterpret_cast<cpx<T> *>(smem_raw);
     const int t = threadIdx.x, bx = blockIdx.x + a.ch_base, r = blockIdx.z;
     cpx<T> v[1 << LOG2E];
-    inv_load<T, LOG2MS, R0, LOG2E>(t, bx, r, v, tw, tw_shift_n, a);
+    bool staged = false;
+    if constexpr (R0 == 1) staged = a.tma != 0;
+    if constexpr (R0 == 1) if (staged) {
+        // input spectrum: N reals of this channel, contiguous -> the (still idle) FFT buffer, read back bin by bin
+        __shared__ __align__(8) uint64_t bar;
+        constexpr int N = 2 << LOG2MS;
+        if (t == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (t == 0) bulk_stage(smem_raw, (const T *)a.in + bx * a.in_stride_x, (uint32_t)(N * sizeof(T)), &bar);
+        mbar_wait(&bar, 0);
+        inv_load_impl<T, LOG2MS, R0, false, LOG2E>(t, r, v, tw, tw_shift_n, reinterpret_cast<const T *>(smem_raw), a.in_layout, (T)a.scale_in, NULL, NULL);
+        __syncthreads();                               // every thread has read its bins before the passes overwrite them
+    }
+    if (!staged) inv_load<T, LOG2MS, R0, LOG2E>(t, bx, r, v, tw, tw_shift_n, a);
     fft_passes<T, LOG2MS, true, 0, 0, LOG2E>::run(t, v, smem, tw, tw_shift_m);
     OverflowAcc acc;
     acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
