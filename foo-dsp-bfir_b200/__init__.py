@@ -94,6 +94,7 @@ API = [
     ("bfir_peer_own_channels", _ci, [_vp, ctypes.POINTER(_ci), ctypes.POINTER(_ci)]),
     ("bfir_set_groups", _ci, [_vp, _ci]),
     ("bfir_get_groups", _ci, [_vp]),
+    ("bfir_set_coeff_map", _ci, [_vp, ctypes.POINTER(ctypes.c_int), _ci]),
     ("bfir_get_mac_split", _ci, [_vp]),
     ("bfir_get_quad_split", _ci, [_vp]),
     ("bfir_set_stream", _ci, [_vp, _vp]),
@@ -412,6 +413,13 @@ class Brutefir:
 
     def get_groups(self):
         return _check(self.lib.bfir_get_groups(self.h))
+
+    def set_coeff_map(self, mapping):
+        """filter channel c uses coefficient set mapping[c]; None restores the identity (bfir_set_coeff_map)"""
+        if mapping is None:
+            return _check(self.lib.bfir_set_coeff_map(self.h, None, 0))
+        m = [int(x) for x in mapping]
+        return _check(self.lib.bfir_set_coeff_map(self.h, (ctypes.c_int * len(m))(*m), len(m)))
 
     def get_mac_split(self):
         return _check(self.lib.bfir_get_mac_split(self.h))

@@ -55,6 +55,7 @@ struct Engine {
     int n_groups = 1;
     cudaEvent_t fork_ev = nullptr;
     int *procblocks = nullptr, *coeff_blocks = nullptr, *nonfinite = nullptr;
+    int *coeff_map = nullptr;       // [Ct] coefficient set per filter channel; nullptr = identity (bfir_set_coeff_map)
     unsigned char *pb_inc = nullptr;
     OverflowStats *stats = nullptr;
     EngineState *h_state = nullptr; // pinned, [BFIR_MAX_GROUPS]
@@ -366,11 +367,11 @@ void Engine::destroy()
     if (recv) { cudaFree(recv); recv = nullptr; }
     for (int k = 1; k < kStage; k++) { if (stage_in[k]) cudaFree(stage_in[k]); if (stage_out[k]) cudaFree(stage_out[k]); stage_in[k] = stage_out[k] = nullptr; }
     stage_in[0] = stage_out[0] = nullptr;
-    void *bufs[] = { acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
+    void *bufs[] = { coeff_map, acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
     acc_pair = nullptr; acc_quad[0] = acc_quad[1] = nullptr;
     fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
-    state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; pb_inc = nullptr; stats = nullptr;
+    state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; coeff_map = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
     h_state = nullptr;
     if (h_flag) cudaFreeHost(h_flag);
@@ -608,7 +609,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
     m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = part_begin; m.part_count = part_count;
-    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = c0;
+    m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = c0;
     if (peer.enabled && !xbar) m.push = peer;
     dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), nch);
     mac_kernel_t mk = rs == 4 ? mac_kernel_for_split<float>(mac_split) : mac_kernel_for_split<double>(mac_split);
@@ -698,7 +699,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
     if (head) {
         v.head_x = fdl; v.head_x_stride = (long long)Pslots * N;
         v.head_h = coeffs; v.head_h_stride = (long long)coeff_alloc * N;
-        v.head_blocks = coeff_blocks;
+        v.head_blocks = coeff_blocks; v.head_map = coeff_map;
     }
     if (!xfade_pending) {
         cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(nch, 1), st, v, tw);
@@ -731,7 +732,7 @@ int Engine::tail_group(int g, cudaStream_t st)
     m.fdl = fdl; m.coeffs = coeffs; m.acc = acc;
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 1; m.part_count = P - 1;
-    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
+    m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
     m.procblocks_bias = 1;
     dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), ns * C);
     mac_kernel_t mk = rs == 4 ? mac_kernel_for_split<float>(mac_split) : mac_kernel_for_split<double>(mac_split);
@@ -762,7 +763,7 @@ int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0
     m.fdl = fdl; m.coeffs = coeffs; m.acc = acc; m.acc_next = acc_pair;
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
-    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
+    m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
     dim3 grid((N / 8 + 256 / mac_split - 1) / (256 / mac_split), ns * C);
     mac_kernel_t mk = rs == 4 ? mac_pair_kernel_for_split<float>(mac_split) : mac_pair_kernel_for_split<double>(mac_split);
     mk<<<grid, 256, 0, gstream(g)>>>(m);
@@ -828,7 +829,7 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out)
     for (int b = 0; b < nb; b++) m.acc_multi[b] = sp_acc[par][b];
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
-    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state; m.ch_base = 0;
+    m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state; m.ch_base = 0;
     m.use_abs_block = 1; m.abs_block = host_blockcounter;
     const int split = nb == 4 ? quad_split : mac_split;
     const int mthreads = nb == 4 && rs == 8 ? quad_threads : 256;
@@ -885,7 +886,7 @@ int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
     m.acc_multi[0] = acc; m.acc_multi[1] = acc_pair; m.acc_multi[2] = acc_quad[0]; m.acc_multi[3] = acc_quad[1];
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = 0; m.part_count = P;
-    m.coeff_blocks = coeff_blocks; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
+    m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state + g; m.block_offset = 0; m.ch_base = s0 * C;
     const int qsplit = quad_split, mthreads = rs == 8 ? quad_threads : 256;
     dim3 grid((N / 8 + mthreads / qsplit - 1) / (mthreads / qsplit), ns * C);
     mac_kernel_t mk = rs == 4 ? mac_quad_kernel_for_split<float>(qsplit) : mac_quad_kernel_for_split<double>(qsplit, mthreads);
@@ -1383,6 +1384,25 @@ int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int 
     if (e != nullptr) e->impl.close_async();
     if (e == nullptr) return BFIR_ERR_INVALID;
     return e->impl.set_coeff(coeffs, n_coeffs, length, coeff_blocks, scale);
+}
+
+int bfir_set_coeff_map(bfir_engine *e, const int *map, int n)
+{
+    if (e != nullptr) e->impl.close_async();
+    if (e == nullptr) return BFIR_ERR_INVALID;
+    Engine &g = e->impl;
+    if (map != nullptr && n != g.Ct) { bfir::set_error("bfir_set_coeff_map: %d entries for %d filter channels", n, g.Ct); return BFIR_ERR_INVALID; }
+    BFIR_CUDA(cudaStreamSynchronize(g.stream));
+    if (map == nullptr) {
+        if (g.coeff_map) { cudaFree(g.coeff_map); g.coeff_map = nullptr; }
+    } else {
+        for (int c = 0; c < n; c++) if (map[c] < 0 || map[c] >= g.Ct) { bfir::set_error("bfir_set_coeff_map: entry %d = %d out of range", c, map[c]); return BFIR_ERR_INVALID; }
+        if (!g.coeff_map) BFIR_CUDA(cudaMalloc((void **)&g.coeff_map, sizeof(int) * g.Ct));
+        BFIR_CUDA(cudaMemcpy(g.coeff_map, map, sizeof(int) * g.Ct, cudaMemcpyHostToDevice));
+    }
+    g.tail_ready = false;           // a look-ahead partition sum computed with the old map is not reused
+    g.invalidate_graphs();
+    return BFIR_OK;
 }
 
 int bfir_set_coeff_crossfade(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale)

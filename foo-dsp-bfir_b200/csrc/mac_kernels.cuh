@@ -25,6 +25,7 @@ struct MacArgs {
     int n_parts;             // filter_blocks
     int part_begin, part_count; // partition shard convolved by this launch (whole filter: 0, n_slots)
     const int *coeff_blocks; // [channels] coefficient partitions actually loaded
+    const int *coeff_map;    // [channels] coefficient set each filter channel convolves with; NULL = its own (bfir_set_coeff_map)
     const int *procblocks;   // [channels] blocks seen so far, already counting the current one
     const EngineState *state;
     int block_offset;        // 0: blockcounter is the current block; used by tests
@@ -91,10 +92,11 @@ __global__ void __launch_bounds__(256) partition_mac_kernel(const MacArgs a)
     const int ch = blockIdx.y + a.ch_base;
     const bool active = g * 8 < a.N;
     const unsigned int t = a.state->blockcounter + (unsigned int)a.block_offset;
-    const int peff = min(a.coeff_blocks[ch], min(a.procblocks[ch] + a.procblocks_bias, a.n_parts)); // brutefir.cpp:292, 265-268
+    const int cs_ = a.coeff_map ? a.coeff_map[ch] : ch;
+    const int peff = min(a.coeff_blocks[cs_], min(a.procblocks[ch] + a.procblocks_bias, a.n_parts)); // brutefir.cpp:292, 265-268
     const int i_end = min(peff, a.part_begin + a.part_count);
     const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
-    const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
+    const T *cf = (const T *)a.coeffs + cs_ * a.coeff_stride_ch + (long long)g * 8;
     const unsigned int P = (unsigned int)a.n_slots;
 
     T acc[8];
@@ -162,11 +164,12 @@ __global__ void __launch_bounds__(256) partition_mac_pair_kernel(const MacArgs a
     const int ch = blockIdx.y + a.ch_base;
     const bool active = g * 8 < a.N;
     const unsigned int t = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.block_offset;
-    const int peff = min(a.coeff_blocks[ch], a.n_parts);
+    const int cs_ = a.coeff_map ? a.coeff_map[ch] : ch;
+    const int peff = min(a.coeff_blocks[cs_], a.n_parts);
     const int cs = (peff + SPLIT - 1) / SPLIT;
     const int i0 = slice * cs, i1 = min(peff, i0 + cs);
     const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
-    const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
+    const T *cf = (const T *)a.coeffs + cs_ * a.coeff_stride_ch + (long long)g * 8;
     const unsigned int P = (unsigned int)a.n_slots;
 
     T acc0[8], acc1[8];
@@ -251,11 +254,12 @@ __global__ void __launch_bounds__(THREADS) partition_mac_multi_kernel(const MacA
     const int ch = blockIdx.y + a.ch_base;
     const bool active = g * 8 < a.N;
     const unsigned int t = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.block_offset;
-    const int peff = min(a.coeff_blocks[ch], a.n_parts);
+    const int cs_ = a.coeff_map ? a.coeff_map[ch] : ch;
+    const int peff = min(a.coeff_blocks[cs_], a.n_parts);
     const int cs = (peff + SPLIT - 1) / SPLIT;
     const int i0 = slice * cs, i1 = min(peff, i0 + cs);
     const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
-    const T *cf = (const T *)a.coeffs + ch * a.coeff_stride_ch + (long long)g * 8;
+    const T *cf = (const T *)a.coeffs + cs_ * a.coeff_stride_ch + (long long)g * 8;
     const unsigned int P = (unsigned int)a.n_slots;
 
     T acc[NB][8];

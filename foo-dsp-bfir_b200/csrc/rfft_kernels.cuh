@@ -108,6 +108,7 @@ struct InvArgs {
     const void *head_h;      // coefficients [channels][..][N], partition 0 at the start of each channel
     long long head_x_stride, head_h_stride; // elements per channel
     const int *head_blocks;  // [channels] coefficient partitions loaded (0: the channel has no filter)
+    const int *head_map;     // [channels] coefficient set of each channel, NULL = its own (bfir_set_coeff_map)
     int tma;                 // 1: one CTA per transform, no head term: the input spectrum arrives by bulk copy (set by launch_rfft_inverse)
 };
 
@@ -464,9 +465,10 @@ BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T
     constexpr int M = (1 << LOG2MS) * R0;
     const T *in = (const T *)a.in + bx * a.in_stride_x;
     const T sc = (T)a.scale_in;
-    if (a.head_x != NULL && a.head_blocks[bx] > 0) {   // uniform per CTA
+    const int cset = (a.head_x != NULL && a.head_map != NULL) ? a.head_map[bx] : bx;
+    if (a.head_x != NULL && a.head_blocks[cset] > 0) {   // uniform per CTA
         const T *hx = (const T *)a.head_x + bx * a.head_x_stride + (long long)a.state->cur_slot * (2 * M);
-        const T *hh = (const T *)a.head_h + bx * a.head_h_stride;
+        const T *hh = (const T *)a.head_h + cset * a.head_h_stride;
         inv_load_impl<T, LOG2MS, R0, true, LOG2E>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, hx, hh);
     } else {
         inv_load_impl<T, LOG2MS, R0, false, LOG2E>(t, r, v, tw, tw_shift_n, in, a.in_layout, sc, NULL, NULL);

@@ -69,9 +69,11 @@ namespace preprocessor
     // reference seeds its generator from time() (buffer.hpp:19); here the seed is a parameter. The peak
     // is read from the engine's overflow statistics (bfoverflow_t.largest, reduced on the device)
     // instead of scanning the output on the host.
+    // `noise` (optional): filter_length*filter_blocks*channels interleaved samples to use instead of the seeded
+    // generator (what buffer::load_white_noise returned in a run that is being reproduced).
     template <class T>
     inline bool calculate_attenuation(const std::vector<std::vector<T> > &response, int filter_length, int sampling_rate,
-                                      double *attenuation, unsigned seed = 0xB200u, bool first_block_only = true)
+                                      double *attenuation, unsigned seed = 0xB200u, bool first_block_only = true, const T *noise = nullptr)
     {
         *attenuation = 0;
         const int realsize = (int)sizeof(T), channels = (int)response.size();
@@ -88,7 +90,8 @@ namespace preprocessor
         std::uniform_real_distribution<double> uni(-1.0, 1.0);                                                // buffer.cpp:455-493
         std::vector<T> inbuf((size_t)filter_length * channels), outbuf((size_t)filter_length * channels);
         for (int n = 0; n < filter_blocks; n++) {                                                             // :329-356
-            for (size_t i = 0; i < inbuf.size(); i++) inbuf[i] = (T)uni(gen);
+            if (noise != nullptr) memcpy(inbuf.data(), noise + (size_t)n * inbuf.size(), sizeof(T) * inbuf.size());
+            else for (size_t i = 0; i < inbuf.size(); i++) inbuf[i] = (T)uni(gen);
             if (filter.run(inbuf.data(), outbuf.data()) != 0) return false;
         }
         double peak = 0;

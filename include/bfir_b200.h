@@ -111,6 +111,13 @@ int bfir_is_initialized(const bfir_engine *e);
  * Returns 0 or BFIR_ERR_COEFF (-2) when a scaled coefficient is NaN/Inf. */
 int bfir_set_coeff(bfir_engine *e, const void *const *coeffs, int n_coeffs, int length, int coeff_blocks, double scale);
 
+/* Coefficient-set routing: filter channel c convolves with coefficient set map[c] (0 <= map[c] < channels * n_streams,
+ * n = that count; map = NULL restores the identity). The original BruteFIR's struct bfcoeff_t carries the list of
+ * channels a coefficient set serves (global.h:71-78); the reference always fills it with the identity
+ * (brutefir.cpp:213-216) and never reads it, so this is the general form it left out: one room-correction filter
+ * shared by several channels is loaded (and kept in HBM) once. Takes effect with the next block. */
+int bfir_set_coeff_map(bfir_engine *e, const int *map, int n);
+
 /* Runtime filter swap (BASELINE configs[2]; the reference has convolver_crossfade_inplace,
  * fftw_convolver.cpp:276-321, but no caller): stages a new coefficient set of the SAME geometry; the
  * next block is computed with the old and the new set and cross-faded old->new with the linear ramp of

@@ -146,6 +146,14 @@ def lib(kind):
     ns.equalizer_render = sig("equalizer_render", ci, ci, ci, ci, ci, ci, ci,
                               ctypes.POINTER(cd), ctypes.POINTER(cd), ctypes.POINTER(cd), vp, ci)
     ns.fft_provider = sig("fft_provider", ctypes.c_char_p)
+    if kind != "port":   # the reference's own offline drivers (brutefir/preprocessor.cpp), in-memory sound files
+        wp = ctypes.c_wchar_p
+        ns.vfile_register = sig("vfile_register", None, wp, ci, ci, ci, vp)
+        ns.vfile_clear = sig("vfile_clear", None)
+        ns.set_noise = sig("set_noise", None, vp, ctypes.c_longlong)
+        ns.convolve_impulses = sig("convolve_impulses", ci, ctypes.POINTER(wp), vp, ci, ci, ci, vp, ctypes.c_longlong, ctypes.POINTER(ci))
+        ns.calculate_attenuation = sig("calculate_attenuation", ci, wp, ci, ci, ctypes.POINTER(cd), ctypes.POINTER(ci),
+                                       ctypes.POINTER(ci), ctypes.POINTER(ci))
     _libs[kind] = ns
     if kind in ("ref", "ref_mkl"):
         # Reference quirk (fftw_convolver.cpp:543-549): convolver_runtime_coeffs2cbuf keeps a
@@ -372,3 +380,39 @@ def equalizer_render(block_length, n_blocks, realsize, sampling_rate, freq, mag,
     if rc < 0:
         raise ValueError("equalizer_render failed")
     return out
+
+
+def ref_convolve_impulses(responses, scales, filter_length, realsize, rate=44100, kind="ref"):
+    """preprocessor::convolve_impulses of the reference itself (brutefir/preprocessor.cpp:34-233) on in-memory sound
+    files: responses = list of [frames, channels] arrays. Returns [g_frames, channels] in the engine's precision."""
+    ns = lib(kind)
+    ns.vfile_clear()
+    names = []
+    for i, r in enumerate(responses):
+        a = np.ascontiguousarray(np.asarray(r, dtype=np.float64))
+        ns.vfile_register("impulse%d.wav" % i, a.shape[1], a.shape[0], rate, _ptr(a))
+        names.append("impulse%d.wav" % i)
+    C = np.asarray(responses[0]).shape[1]
+    frames = max(np.asarray(r).shape[0] for r in responses)
+    out = np.zeros((frames + filter_length) * C, dtype=real_dtype(realsize))
+    sc = np.ascontiguousarray(np.asarray(scales, dtype=np.float64))
+    ch = ctypes.c_int(0)
+    n = ns.convolve_impulses((ctypes.c_wchar_p * len(names))(*names), _ptr(sc), len(names), filter_length, realsize, _ptr(out),
+                             out.nbytes, ctypes.byref(ch))
+    if n <= 0:
+        raise ValueError("reference convolve_impulses failed")
+    return out[:n * ch.value].reshape(n, ch.value)
+
+
+def ref_calculate_attenuation(response, filter_length, realsize, noise, rate=44100, kind="ref"):
+    """preprocessor::calculate_attenuation of the reference itself (brutefir/preprocessor.cpp:250-412); `noise` is what
+    its buffer::load_white_noise returns (interleaved, filter_length * blocks * channels samples). Returns dB."""
+    ns = lib(kind)
+    a = np.ascontiguousarray(np.asarray(response, dtype=np.float64))
+    ns.vfile_register("response.wav", a.shape[1], a.shape[0], rate, _ptr(a))
+    nz = np.ascontiguousarray(np.asarray(noise, dtype=np.float64).ravel())
+    ns.set_noise(_ptr(nz), nz.size)
+    att, c, f, r = ctypes.c_double(0), ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    if not ns.calculate_attenuation("response.wav", filter_length, realsize, ctypes.byref(att), ctypes.byref(c), ctypes.byref(f), ctypes.byref(r)):
+        raise ValueError("reference calculate_attenuation failed")
+    return att.value

@@ -12,11 +12,15 @@
 #include "equalizer.hpp"
 #include "raw2real.hpp"
 #include "real2raw.hpp"
+#include "preprocessor.hpp"
 #undef private
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
 
+void stub_vfile_register(const wchar_t *name, int channels, int frames, int rate, const double *data);
+void stub_vfile_clear();
+void stub_set_noise(const double *data, size_t n);
 extern std::vector<unsigned char> g_last_saved;
 extern int g_last_saved_channels, g_last_saved_frames, g_last_saved_realsize;
 
@@ -237,5 +241,43 @@ int ref_equalizer_render(int block_length, int n_blocks, int realsize, int n_cha
 
 extern "C" const char *oracle_fft_provider_name(void);   // fftw_api.cpp / fftw_api_mkl.cpp
 const char *ref_fft_provider(void) { return oracle_fft_provider_name(); }
+
+}
+
+
+// ------------------------------------------------------------------ preprocessor (offline drivers of the block loop)
+// The UNMODIFIED brutefir/preprocessor.cpp, fed from in-memory "sound files" (stubs.cpp) instead of libsndfile.
+extern "C" {
+
+void ref_vfile_register(const wchar_t *name, int channels, int frames, int rate, const double *interleaved)
+{
+    stub_vfile_register(name, channels, frames, rate, interleaved);
+}
+void ref_vfile_clear(void) { stub_vfile_clear(); }
+void ref_set_noise(const double *samples, long long n) { stub_set_noise(samples, (size_t)n); }
+
+// preprocessor::convolve_impulses (preprocessor.cpp:34-233). The result "file" is what the function hands to
+// save_to_snd_file: g_frames frames x channels, interleaved, in the engine's precision. Returns the number of
+// frames (0 on error) and copies at most `capacity` bytes to `out`.
+int ref_convolve_impulses(const wchar_t *const *names, const double *scales, int n, int filter_length, int realsize,
+                          void *out, long long capacity, int *channels)
+{
+    std::vector<struct impulse_info> info(n);
+    for (int i = 0; i < n; i++) { info[i].filename = names[i]; info[i].scale = scales[i]; }
+    g_last_saved.clear();
+    g_last_saved_frames = 0;
+    std::wstring name = preprocessor::convolve_impulses(info, filter_length, realsize);
+    if (name.empty() || g_last_saved.empty()) return 0;
+    if (channels) *channels = g_last_saved_channels;
+    memcpy(out, g_last_saved.data(), (size_t)capacity < g_last_saved.size() ? (size_t)capacity : g_last_saved.size());
+    return g_last_saved_frames;
+}
+
+// preprocessor::calculate_attenuation (preprocessor.cpp:250-412); noise from ref_set_noise
+int ref_calculate_attenuation(const wchar_t *name, int filter_length, int realsize, double *attenuation, int *n_channels,
+                              int *n_frames, int *sampling_rate)
+{
+    return preprocessor::calculate_attenuation(name, filter_length, realsize, attenuation, n_channels, n_frames, sampling_rate) ? 1 : 0;
+}
 
 }

@@ -868,3 +868,61 @@ def test_block_quads_equal_single_blocks(pkg, rs, groups, P):
     assert single.blockcounter() == quad.blockcounter() == nblk
     for b in range(nblk):
         assert rel_rms(out_q[b].cpu().numpy(), out_s[b].cpu().numpy()) < (2e-6 if rs == 4 else 1e-13), b
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_coefficient_set_routing(pkg, rs):
+    """bfir_set_coeff_map (N4: the channels[] list of struct bfcoeff_t, global.h:71-78, which the reference always
+    leaves at the identity): an engine whose filter channels share coefficient sets through a map produces the same
+    bytes as an engine loaded with the explicitly duplicated filters -- one block per call (look-ahead head term),
+    two and four blocks per call, staged calls and the synchronous host path; None restores the identity."""
+    import torch
+    L, P, C, S = 256, 4, 4, 2
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt, tdt = (np.float32, torch.float32) if rs == 4 else (np.float64, torch.float64)
+    Ct = C * S
+    h = [decay_filter(c, L * P - 5) for c in range(Ct)]
+    mapping = [2, 2, 0, 1, 7, 5, 5, 4]
+    mapped = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=1)
+    plain = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=1)
+    assert mapped.set_coeff(h, P) == 0 and plain.set_coeff([h[m] for m in mapping], P) == 0
+    assert mapped.set_coeff_map(mapping) == 0
+    with pytest.raises(pkg.BfirError):
+        mapped.set_coeff_map(mapping[:-1])
+    with pytest.raises(pkg.BfirError):
+        mapped.set_coeff_map([Ct] * Ct)
+    nblk = 30
+    x = white_noise(71, nblk * L, Ct).astype(dt)
+    blocks = [np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2)).ravel() for b in range(nblk)]
+    d_in = [torch.from_numpy(b).cuda() for b in blocks]
+    n = S * L * C
+    out = {k: [torch.zeros(n, dtype=tdt, device="cuda") for _ in range(nblk)] for k in ("m", "p")}
+    torch.cuda.synchronize()
+    for name, e in (("m", mapped), ("p", plain)):
+        o = out[name]
+        b = 0
+        for _ in range(6):
+            e.run_device(d_in[b], o[b]); b += 1
+        rc, y = e.run(blocks[b].view(np.uint8))                      # synchronous host path (look-ahead head term)
+        assert rc == 0
+        o[b].copy_(torch.from_numpy(y.view(dt))); b += 1
+        rc, y = e.run(blocks[b].view(np.uint8))
+        assert rc == 0
+        o[b].copy_(torch.from_numpy(y.view(dt))); b += 1
+        e.run_device_pair(d_in[b], d_in[b + 1], o[b], o[b + 1]); b += 2
+        e.run_device_quad(d_in[b:b + 4], o[b:b + 4]); b += 4
+        e.run_device_quad(d_in[b:b + 4], o[b:b + 4], staged=True); b += 4
+        e.run_device_pair(d_in[b], d_in[b + 1], o[b], o[b + 1], pipelined="staged"); b += 2
+        e.join()
+        while b < nblk:
+            e.run_device(d_in[b], o[b]); b += 1
+        assert e.sync() == 0
+    for b in range(nblk):
+        assert torch.equal(out["m"][b], out["p"][b]), b
+    # back to the identity: now the two engines differ (different filters per channel)
+    assert mapped.set_coeff_map(None) == 0
+    ym, yp = torch.zeros(n, dtype=tdt, device="cuda"), torch.zeros(n, dtype=tdt, device="cuda")
+    mapped.run_device(d_in[0], ym)
+    plain.run_device(d_in[0], yp)
+    assert mapped.sync() == 0 and plain.sync() == 0
+    assert not torch.equal(ym, yp)

@@ -48,3 +48,20 @@ def test_plugin_adapter_and_offline_tools(tmp_path):
     """next rows N2 (dsp_impl_base framing) and N3 (convolve_impulses, calculate_attenuation) on the GPU engine"""
     r = subprocess.run([build(tmp_path, SRC_TOOLS), "gpu"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_offline_tools_match_reference_preprocessor(tmp_path):
+    """N3: host/preprocessor.hpp on the GPU engine against the reference's own preprocessor.cpp (oracle/_ref, fed the
+    same dense responses from in-memory sound files): convolve_impulses 1e-5 / 1e-12, calculate_attenuation in dB"""
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(refdir, "libbfir_ref.so")):
+        pytest.skip("oracle/_ref/libbfir_ref.so not built")
+    src = os.path.join(ROOT, "tests", "host_cpp", "preprocessor_parity_test.cpp")
+    exe = str(tmp_path / "preprocessor_parity_test")
+    r = subprocess.run(["g++", "-std=c++11", "-O1", src, "-o", exe, "-L" + LIBDIR, "-lbfir_b200", "-L" + refdir, "-lbfir_ref",
+                        "-Wl,-rpath," + LIBDIR, "-Wl,-rpath," + refdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr

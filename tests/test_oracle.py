@@ -311,3 +311,41 @@ def test_mkl_fft_provider_for_the_cpu_baseline(oracle):
         raw = np.ascontiguousarray(x[blk * L:(blk + 1) * L]).view(np.uint8).ravel()
         ya, yb = a.run(raw)[1].view(np.float64), b.run(raw)[1].view(np.float64)
         assert rel_rms(yb, ya) < 1e-13
+
+
+@pytest.mark.parametrize("rs", [4, 8])
+def test_reference_offline_drivers_in_the_oracle(oracle, rs):
+    """brutefir/preprocessor.cpp compiled into oracle/_ref (in-memory sound files instead of libsndfile) behaves as
+    its source reads: the cascade keeps only the FIRST block of each intermediate result as the next coefficient set
+    (set_coeff is handed filter_length as the coefficient length, preprocessor.cpp:176), scaled by the file's scale;
+    the attenuation probe is -20 log10 of the peak of noise * first block of the response."""
+    if not oracle.available("ref"):
+        pytest.skip("oracle/_ref not built")
+    L, C = 64, 2
+    rng = np.random.default_rng(3)
+    dt = np.float32 if rs == 4 else np.float64
+    irs = [(rng.standard_normal((f, C)) * np.exp(-np.arange(f) / 50.0)[:, None] * 0.3).astype(dt) for f in (150, 200, 90)]
+    scales = [1.0, 0.5, 2.0]
+    y = oracle.ref_convolve_impulses(irs, scales, L, rs)
+    assert y.shape == (200, C)
+    T = L * ((200 + L - 1) // L)
+    want = np.zeros((T, C))
+    for c in range(C):
+        h = np.zeros(L)
+        h[0] = 1.0
+        carry = np.zeros(0)
+        for k, ir in enumerate(irs):
+            x = np.zeros(T)
+            x[:ir.shape[0]] = ir[:, c]
+            stream = np.concatenate([carry, x])                   # the engine is never reset: the delay line carries on
+            out = np.convolve(stream, h)[len(carry):len(carry) + T]
+            carry = stream
+            h = out[:L] * scales[k]
+        want[:, c] = out
+    assert rel_rms(y, want[:200]) < (2e-6 if rs == 4 else 1e-13)
+    resp = irs[1] * 10
+    noise = rng.uniform(-1, 1, T * C).astype(dt)
+    att = oracle.ref_calculate_attenuation(resp, L, rs, noise)
+    nz = noise.reshape(T, C).astype(np.float64)
+    peak = max(np.abs(np.convolve(nz[:, c], resp[:L, c].astype(np.float64))[:T]).max() for c in range(C))
+    assert peak > 1 and abs(att + 20 * np.log10(peak)) < (1e-4 if rs == 4 else 1e-9)
