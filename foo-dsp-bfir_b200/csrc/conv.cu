@@ -32,7 +32,7 @@ struct Conv {
     {
         int r0 = fft_r0;
         void *final_out = nullptr;
-        if (r0 == 2 && overlaps(a.in, a.out)) {
+        if (r0 >= 2 && overlaps(a.in, a.out)) {   // several CTAs per transform cannot work in place
             if (rfft_choose_r0(rs, log2m, 1LL << 40) == 1) r0 = 1;
             else { final_out = a.out; a.out = scratch; }
         }
@@ -46,7 +46,7 @@ struct Conv {
     {
         int r0 = fft_r0;
         void *final_out = nullptr;
-        if (r0 == 2 && overlaps(a.in, a.out)) {
+        if (r0 >= 2 && overlaps(a.in, a.out)) {   // several CTAs per transform cannot work in place
             if (rfft_choose_r0(rs, log2m, 1LL << 40) == 1) r0 = 1;
             else { final_out = a.out; a.out = scratch; }
         }

@@ -50,6 +50,7 @@ static const inv_launcher_t kInvF32E8[] = { BFIR_FOR_F32E8(BFIR_INV_ENTRY) };
 // BFIR_FFT_E = 8 | 16 forces the answer where both exist.
 static bool use_e8(int realsize, int sub, int r0, long long n_buffers, bool forward)
 {
+    if (r0 == 4) return false;
     if (sub < kMinLog2M_e8 || sub > (realsize == 8 ? kMaxLog2M_e8 : kMaxLog2M_e8_f32)) return false;
     static const int forced = [] { const char *env = getenv("BFIR_FFT_E"); return env ? atoi(env) : 0; }();
     if (forced == 8) return true;
@@ -68,11 +69,15 @@ static int max_sub(int realsize) { return realsize == 4 ? kMaxLog2M_f32 : kMaxLo
 bool rfft_supported(int realsize, int log2m)
 {
     if (realsize != 4 && realsize != 8) return false;
-    return log2m >= kMinLog2M && log2m <= max_sub(realsize) + 1;
+    // one, two or (double precision, the largest size) four CTAs per transform
+    return log2m >= kMinLog2M && log2m <= max_sub(realsize) + (realsize == 8 ? 2 : 1);
 }
+
+static int ilog2_r0(int r0) { return r0 == 4 ? 2 : (r0 == 2 ? 1 : 0); }
 
 int rfft_choose_r0(int realsize, int log2m, long long n_buffers)
 {
+    if (log2m > max_sub(realsize) + 1) return 4;
     if (log2m > max_sub(realsize)) return 2;
     if (log2m - 1 < kMinLog2M) return 1;
     if (const char *env = getenv("BFIR_FFT_R0")) {
@@ -104,27 +109,27 @@ static bool tma_enabled()
 
 cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a0, const void *tw)
 {
-    if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
-    const int sub = log2m - (r0 == 2 ? 1 : 0);
+    if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2 && r0 != 4)) return cudaErrorInvalidValue;
+    const int sub = log2m - ilog2_r0(r0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
     FwdArgs a = a0;
     a.tma = (tma_enabled() && r0 == 1 && a.in_mode == IN_RAW_PREV && a.prev != nullptr && ((uintptr_t)a.prev & 15) == 0
              && (((size_t)realsize << log2m) & 15) == 0) ? 1 : 0;
     // table length N = 2 * 2^log2m: shift for the sub-transform twiddles, 0 for the W_N^k of the split step
-    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, true)) return (realsize == 4 ? kFwdF32E8 : kFwdF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
-    return (realsize == 4 ? kFwdF32 : kFwdF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
+    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, true)) return (realsize == 4 ? kFwdF32E8 : kFwdF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
+    return (realsize == 4 ? kFwdF32 : kFwdF64)[sub - kMinLog2M](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
 }
 
 cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const InvArgs &a0, const void *tw)
 {
-    if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2)) return cudaErrorInvalidValue;
-    const int sub = log2m - (r0 == 2 ? 1 : 0);
+    if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2 && r0 != 4)) return cudaErrorInvalidValue;
+    const int sub = log2m - ilog2_r0(r0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
     InvArgs a = a0;
     a.tma = (tma_enabled() && r0 == 1 && a.head_x == nullptr && ((uintptr_t)a.in & 15) == 0
              && (((size_t)a.in_stride_x * realsize) & 15) == 0) ? 1 : 0;
-    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return (realsize == 4 ? kInvF32E8 : kInvF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
-    return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, r0 == 2 ? 2 : 1, 0);
+    if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return (realsize == 4 ? kInvF32E8 : kInvF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
+    return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
 }
 
 } // namespace bfir

@@ -7,11 +7,12 @@
 
 namespace bfir {
 
-// block length L = M = 2^log2m. One transform is computed by r0 = 1 or 2 CTAs (rfft_kernels.cuh); each
+// block length L = M = 2^log2m. One transform is computed by r0 = 1, 2 or 4 CTAs (rfft_kernels.cuh); each
 // CTA holds M/r0 complex values (+1/16 padding) in shared memory (<= 227 KB), which bounds the
-// per-CTA size at 2^14 (float) / 2^13 (double). Supported: 16 <= L <= 32768 (float), 16 <= L <= 16384 (double).
+// per-CTA size at 2^14 (float) / 2^13 (double). Supported: 16 <= L <= 32768 in both precisions (double at L = 32768:
+// four CTAs, the forward kernel as a thread-block cluster).
 bool rfft_supported(int realsize, int log2m);
-// 1 or 2 CTAs per transform: 2 when the size needs it, or when there are too few buffers to fill the GPU
+// 1, 2 or 4 CTAs per transform: 2 / 4 when the size needs it, 2 also when there are too few buffers to fill the GPU
 int rfft_choose_r0(int realsize, int log2m, long long n_buffers);
 
 // grid = (buffers/channels, partitions); block size, grid.z and shared memory are implied by size and r0.

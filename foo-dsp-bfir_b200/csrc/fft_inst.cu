@@ -30,12 +30,11 @@ static cudaError_t launch_fwd(dim3 grid, cudaStream_t stream, const FwdArgs &a, 
         configured = true;
     }
     grid.z = R0;
-    static const int cl = [] { const char *e = getenv("BFIR_FFT_CLUSTER"); return e ? atoi(e) : 0; }();
-    if (cl > 1 && grid.x % cl == 0) {   // experiment: cluster launch of the unchanged kernel (scheduling cost only)
+    if (R0 == 4) {   // four CTAs per transform: one thread-block cluster along z (DSMEM exchange in the split step)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid; cfg.blockDim = dim3(kM >> kLog2E); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
         cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 4;
         cfg.attrs = at; cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kernel, a, (const cpx<real_t> *)tw, sm, sn);
     }
@@ -54,27 +53,26 @@ static cudaError_t launch_inv(dim3 grid, cudaStream_t stream, const InvArgs &a, 
         configured = true;
     }
     grid.z = R0;
-    static const int cl = [] { const char *e = getenv("BFIR_FFT_CLUSTER"); return e ? atoi(e) : 0; }();
-    if (cl > 1 && grid.x % cl == 0) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid; cfg.blockDim = dim3(kM >> kLog2E); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, kernel, a, (const cpx<real_t> *)tw, sm, sn);
-    }
     kernel<<<grid, kM >> kLog2E, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
     return cudaGetLastError();
 }
 
 // kLog2M is the per-CTA sub-transform size; r0 CTAs cooperate on one buffer of 2^kLog2M * r0 points
+// four CTAs per transform only where the size needs it: the largest double-precision sub-transform (2^13 points per
+// CTA, 16 points per thread) -> 65536-point real transforms
+static constexpr bool kHasR04 = sizeof(real_t) == 8 && kLog2M == 13 && kLog2E == 4;
+
 cudaError_t BFIR_CAT(launch_fwd_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw, int sm, int sn)
 {
+    if constexpr (kHasR04) { if (r0 == 4) return launch_fwd<4>(grid, stream, a, tw, sm, sn); }
+    if (r0 == 4) return cudaErrorInvalidValue;
     return r0 == 2 ? launch_fwd<2>(grid, stream, a, tw, sm, sn) : launch_fwd<1>(grid, stream, a, tw, sm, sn);
 }
 
 cudaError_t BFIR_CAT(launch_inv_, BFIR_FFT_TAG, m, BFIR_FFT_LOG2M)(int r0, dim3 grid, cudaStream_t stream, const InvArgs &a, const void *tw, int sm, int sn)
 {
+    if constexpr (kHasR04) { if (r0 == 4) return launch_inv<4>(grid, stream, a, tw, sm, sn); }
+    if (r0 == 4) return cudaErrorInvalidValue;
     return r0 == 2 ? launch_inv<2>(grid, stream, a, tw, sm, sn) : launch_inv<1>(grid, stream, a, tw, sm, sn);
 }
 

@@ -15,6 +15,9 @@
 #pragma once
 #include "fft_core.cuh"
 #include "codec.cuh"
+#ifdef __CUDACC__
+#include <cooperative_groups.h>
+#endif
 
 namespace bfir {
 
@@ -141,6 +144,30 @@ template <class T> BFIR_HD cpx<T> spec_load(const T *s, int layout, int k, int M
 // For R0 = 2 the real-FFT split partner of bin k = 2k'+r is M-k = 2(Ms-k')  (r = 0) or 2(Ms-1-k')+1
 // (r = 1): the same CTA, so no exchange between the two CTAs is ever needed. R0 = 2 doubles the
 // largest block length (L = 32768 float, 16384 double) and halves the per-CTA latency of big transforms.
+
+// R0 = 4 (four CTAs per transform, double-precision 65536-point real transforms: 32768 complex points do not fit
+// two CTAs' shared memory): the radix-4 decimation-in-frequency pre-pass of residue r on four points Ms apart,
+//     forward: y_r = z0 + z1 W4^r + z2 W4^2r + z3 W4^3r, W4 = -i;   inverse: the conjugate roots.
+// The real-FFT split partner of bin k = 4k'+r is M-k = 4(Ms-k') (r = 0) or 4(Ms-1-k') + (4-r): residues 1 and 3
+// pair ACROSS CTAs, so the forward kernel's four CTAs form a thread-block cluster and read the partner's
+// sub-transform through distributed shared memory.
+template <bool INV, class C> BFIR_HD C dif4_residue(int r, C z0, C z1, C z2, C z3)
+{
+    if (r == 0) return cadd(cadd(z0, z2), cadd(z1, z3));
+    if (r == 2) return csub(cadd(z0, z2), cadd(z1, z3));
+    const C d = mul_mi<INV>(csub(z1, z3));            // forward: -i (z1 - z3); inverse: +i (z1 - z3)
+    return r == 1 ? cadd(csub(z0, z2), d) : csub(csub(z0, z2), d);
+}
+// w^r for r = 0..3
+template <class C> BFIR_HD C cpow_small(C w, int r)
+{
+    C one; one.x = 1; one.y = 0;
+    if (r == 0) return one;
+    if (r == 1) return w;
+    const C w2 = cmul(w, w);
+    return r == 2 ? w2 : cmul(w2, w);
+}
+template <int R0> struct log2_r0 { static constexpr int value = R0 == 4 ? 2 : (R0 == 2 ? 1 : 0); };
 
 // per-thread constants of the input access, computed once (the state word must not be re-read per element:
 // the stores into the previous-block buffer would force the compiler to reload it every time)
@@ -291,6 +318,30 @@ BFIR_HD void fwd_load_raw_prev(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<
         for (int j = 0; j < NH; j++) v[j] = staged_prev[t + j * NT];
 #pragma unroll
         for (int j = 0; j < NH; j++) { c.prev_wr[t + j * NT] = hi[j]; v[j + NH] = hi[j]; }
+    } else if constexpr (R0 == 4) {
+        // n = t + j NT in [0, Ms): previous block at complex indices n and n + Ms, current block likewise (M/2 = 2 Ms)
+#pragma unroll
+        for (int j0 = 0; j0 < E; j0 += 2) {
+            C lo0[2], lo1[2], hi0[2], hi1[2];
+#pragma unroll
+            for (int j = 0; j < 2; j++) { lo0[j] = c.prev_rd[t + (j0 + j) * NT]; lo1[j] = c.prev_rd[t + (j0 + j) * NT + MS]; }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const uint8_t *p = c.raw + (long long)(2 * (t + (j0 + j) * NT)) * c.step;
+                const uint8_t *q = c.raw + (long long)(2 * (t + (j0 + j) * NT + MS)) * c.step;
+                hi0[j] = mk<T>(load_raw<T>(p, FMT), load_raw<T>(p + c.step, FMT));
+                hi1[j] = mk<T>(load_raw<T>(q, FMT), load_raw<T>(q + c.step, FMT));
+            }
+            if (r == 0) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) { c.prev_wr[t + (j0 + j) * NT] = hi0[j]; c.prev_wr[t + (j0 + j) * NT + MS] = hi1[j]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const C y = dif4_residue<false>(r, lo0[j], lo1[j], hi0[j], hi1[j]);
+                v[j0 + j] = r == 0 ? y : cmul(y, cpow_small(cmul(wpre, thread_root<T, 4 * E>(j0 + j)), r));
+            }
+        }
     } else {
 #pragma unroll
     for (int j0 = 0; j0 < NH; j0 += CH) {
@@ -325,11 +376,12 @@ template <class T, int LOG2MS, int R0, int LOG2E = 4, bool STAGED = false>
 BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a,
                       const cpx<T> *staged_prev = NULL, void *bar = NULL)
 {
-    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, LOG2M = LOG2MS + (R0 == 2 ? 1 : 0);
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, LOG2M = LOG2MS + log2_r0<R0>::value;
     typedef cpx<T> C;
     bool bad = false;
     cpx<T> wpre = mk<T>((T)1, (T)0);
     if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];     // W_M^t = W_N^(2t); W_M^(t + i NTs) = W_M^t * root32(i)
+    if (R0 == 4 && r != 0) wpre = tw[(2 * t) << tw_shift_n];     // W_M^t; W_M^(t + i NTs) = W_M^t * root64(i), then the r-th power
     const FwdCtx<T> ctx = fwd_ctx<T, LOG2M>(bx, by, a);
     if (a.in_mode == IN_RAW_PREV) {
         BFIR_FMT_SWITCH(a.fmt, (fwd_load_raw_prev<T, LOG2MS, R0, LOG2E, FMT, STAGED>(t, r, v, wpre, ctx, staged_prev, bar)))
@@ -338,6 +390,17 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], con
         for (int i = 0; i < E / 2; i++) v[i] = fwd_elem<T, LOG2M, false>(t + i * NT, by, r, a, ctx, bad);
 #pragma unroll
         for (int i = E / 2; i < E; i++) v[i] = fwd_elem<T, LOG2M, true>(t + i * NT, by, r, a, ctx, bad);
+    } else if (R0 == 4) {
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+            const int n = t + i * NT;
+            const C z0 = fwd_elem<T, LOG2M, false>(n, by, r, a, ctx, bad);
+            const C z1 = fwd_elem<T, LOG2M, false>(n + MS, by, r, a, ctx, bad);
+            const C z2 = fwd_elem<T, LOG2M, true>(n + 2 * MS, by, r, a, ctx, bad);
+            const C z3 = fwd_elem<T, LOG2M, true>(n + 3 * MS, by, r, a, ctx, bad);
+            const C y = dif4_residue<false>(r, z0, z1, z2, z3);
+            v[i] = r == 0 ? y : cmul(y, cpow_small(cmul(wpre, thread_root<T, 4 * E>(i)), r));
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < E; i++) {
@@ -361,9 +424,12 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], con
 
 // forward, phase 2: sub-transform result (natural order, padded smem) -> X_k, k = R0 k' + r, scaled,
 // stored in ORD or HC layout
+// `partner`: where Z_{M-k} lives -- this CTA's own buffer except for R0 = 4, r = 1 / 3 (the other one's, through DSMEM)
 template <class T, int LOG2MS, int R0, int LOG2E = 4>
-BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a)
+BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a,
+                             const cpx<T> *partner = NULL)
 {
+    if (partner == NULL) partner = smem;
     constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, M = MS * R0, N = 2 * M;
     typedef cpx<T> C;
     long long off = bx * a.out_stride_x + by * a.out_stride_y;
@@ -381,7 +447,7 @@ BFIR_HD void fwd_split_store(int t, int bx, int by, int r, const cpx<T> *smem, c
             out[0] = dc;
             if (a.out_layout == LAYOUT_ORD) out[4] = ny; else out[M] = ny;
         } else {
-            const C zm = smem[fft_pad(r == 0 ? MS - kp : MS - 1 - kp)];   // Z_{M-k}
+            const C zm = partner[fft_pad(r == 0 ? MS - kp : MS - 1 - kp)];   // Z_{M-k}
             // E = (Z_k + conj Z_{M-k})/2, O = (Z_k - conj Z_{M-k})/(2i), X_k = E + W_N^k O
             const T er = (T)0.5 * (zk.x + zm.x), ei = (T)0.5 * (zk.y - zm.y);
             const T dr = (T)0.5 * (zk.x - zm.x), di = (T)0.5 * (zk.y + zm.y);
@@ -443,6 +509,28 @@ BFIR_HD void inv_load_impl(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *
     const C wbase = tw[t << tw_shift_n];                                   // W_N^t
     C wpre = mk<T>((T)1, (T)0);
     if (R0 == 2 && r == 1) wpre = tw[(2 * t) << tw_shift_n];               // W_M^t
+    if constexpr (R0 == 4) {
+        // Z' at k + j Ms, j = 0..3: W_N^(k + j Ms) = W_N^k W_8^j; then the inverse radix-4 pre-pass and W_M^(-k r)
+        const T h = (T)0.70710678118654752440;
+#pragma unroll
+        for (int i = 0; i < E; i++) {
+            const int k = t + i * NT;
+            const C wk = tw[k << tw_shift_n];                                  // the bins are N/(8E) apart: one look-up each
+            const C w1 = mk<T>((wk.x + wk.y) * h, (wk.y - wk.x) * h);          // W_N^k (1 - i)/sqrt2
+            const C w2 = mk<T>(wk.y, -wk.x);                                   // -i W_N^k
+            const C w3 = mk<T>((wk.y - wk.x) * h, (-wk.x - wk.y) * h);         // W_N^k (-1 - i)/sqrt2
+            C z0, z1, z2, z3;
+            if (HEAD) {
+                z0 = inv_elem<T>(in, layout, k, M, sc, wk, hx, hh); z1 = inv_elem<T>(in, layout, k + MS, M, sc, w1, hx, hh);
+                z2 = inv_elem<T>(in, layout, k + 2 * MS, M, sc, w2, hx, hh); z3 = inv_elem<T>(in, layout, k + 3 * MS, M, sc, w3, hx, hh);
+            } else {
+                z0 = inv_elem<T>(in, layout, k, M, sc, wk); z1 = inv_elem<T>(in, layout, k + MS, M, sc, w1);
+                z2 = inv_elem<T>(in, layout, k + 2 * MS, M, sc, w2); z3 = inv_elem<T>(in, layout, k + 3 * MS, M, sc, w3);
+            }
+            const C y = dif4_residue<true>(r, z0, z1, z2, z3);
+            v[i] = r == 0 ? y : cmul(y, cconj(cpow_small(cmul(wk, wk), r)));  // W_M^k = W_N^(2k)
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < E; i++) {
         const int k = t + i * NT;
@@ -456,6 +544,7 @@ BFIR_HD void inv_load_impl(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *
             if (r == 0) v[i] = cadd(lo, hi);
             else v[i] = cmul(csub(lo, hi), cconj(cmul(wpre, thread_root<T, 2 * E>(i))));   // W_M^(-k)
         }
+    }
     }
 }
 
@@ -596,7 +685,17 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
     fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run(t, v, smem, tw, tw_shift_m);
     BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, v, smem);
     __syncthreads();
-    fwd_split_store<T, LOG2MS, R0, LOG2E>(t, bx, by, r, smem, tw, tw_shift_n, a);
+    if constexpr (R0 == 4) {
+        // launched as clusters of four CTAs along z (rank = r): residues 1 and 3 read each other's sub-transform
+        namespace cg = cooperative_groups;
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();                                 // all four sub-transforms are in shared memory
+        const cpx<T> *partner = (r == 1 || r == 3) ? cluster.map_shared_rank(smem, 4 - r) : smem;
+        fwd_split_store<T, LOG2MS, R0, LOG2E>(t, bx, by, r, smem, tw, tw_shift_n, a, partner);
+        cluster.sync();                                 // nobody leaves while a partner still reads its buffer
+    } else {
+        fwd_split_store<T, LOG2MS, R0, LOG2E>(t, bx, by, r, smem, tw, tw_shift_n, a);
+    }
 }
 
 template <class T, int LOG2MS, int R0, int LOG2E = 4>

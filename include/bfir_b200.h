@@ -75,8 +75,9 @@ typedef struct bfir_eq bfir_eq;
  * (brutefir/brutefir.hpp:18-25); the rest have no reference counterpart and default to
  * {1, -1, 0, 0, 0, 0, 0} through bfir_create. */
 typedef struct bfir_config_t {
-    int filter_length;   /* block length L, power of two, 16..32768 (realsize 4) / 16..16384 (realsize 8); the largest
-                            size of each precision runs as a transform split over two CTAs */
+    int filter_length;   /* block length L, power of two, 16..32768 in both precisions (transforms of 32..65536 points);
+                            the largest sizes run as transforms split over two CTAs (L 32768 float, 16384 double) or
+                            over a cluster of four (L 32768 double) */
     int filter_blocks;   /* partitions P >= 1 */
     int realsize;        /* 4 or 8 */
     int channels;        /* channels per stream; no BF_MAXCHANNELS limit (global.h:21) */

@@ -10,7 +10,7 @@ from conftest import rel_rms, encode_raw, decode_raw, parity
 pytestmark = pytest.mark.gpu
 
 TOL = {4: 1e-5, 8: 1e-12}
-SIZES = [(16, 4), (64, 4), (512, 4), (1024, 8), (4096, 4), (8192, 8), (16384, 4), (32, 8), (2048, 8), (32768, 4), (16384, 8)]
+SIZES = [(16, 4), (64, 4), (512, 4), (1024, 8), (4096, 4), (8192, 8), (16384, 4), (32, 8), (2048, 8), (32768, 4), (16384, 8), (32768, 8)]
 
 
 def make(pkg, oracle, L, rs):
@@ -107,7 +107,7 @@ def test_dirac_convolve(pkg, oracle, rs):
     parity("dirac_vs_convolve_with_unit_coeff/rs%d" % rs, g.get(yh), via, TOL[rs], truth=ref)
 
 
-@pytest.mark.parametrize("L,rs", [(64, 4), (1024, 4), (1024, 8), (8192, 8), (16384, 4), (32768, 4), (16384, 8)])
+@pytest.mark.parametrize("L,rs", [(64, 4), (1024, 4), (1024, 8), (8192, 8), (16384, 4), (32768, 4), (16384, 8), (32768, 8)])
 def test_coeffs2cbuf(pkg, oracle, L, rs):
     g, o = make(pkg, oracle, L, rs)
     rng = np.random.default_rng(L)

@@ -69,9 +69,11 @@ def test_cfg1_double_vs_oracle_and_direct(pkg, oracle):
         assert rel_rms(yg[:, c], oracle_np.direct_convolution(x[:, c], h[c], len(x))) < 1e-12
 
 
-@pytest.mark.parametrize("L,rs", [(32768, 4), (16384, 8), (16384, 4), (8192, 8)])
+@pytest.mark.parametrize("L,rs", [(32768, 4), (16384, 8), (16384, 4), (8192, 8), (32768, 8)])
 def test_largest_block_lengths_two_cta_transform(pkg, oracle, L, rs):
-    """L = 32768 (float) / 16384 (double) only exist as two-CTA transforms; cfg4 uses L = 32768"""
+    """L = 32768 (float) / 16384 (double) only exist as two-CTA transforms (cfg4 uses L = 32768); L = 32768 in double
+    precision (65536-point transforms) runs on FOUR CTAs per transform, the forward side as a thread-block cluster
+    whose CTAs 1 and 3 exchange their sub-transforms through distributed shared memory"""
     fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
     g, o, x, h, yg, yo = run_both(pkg, oracle, L, 3, rs, 2, fmt, fmt, 5)
     assert rel_rms(yg, yo) < TOL[rs]
