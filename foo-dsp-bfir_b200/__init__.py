@@ -76,6 +76,8 @@ API = [
     ("bfir_run_async_pair", ctypes.c_longlong, [_vp, _vp, _vp, _vp, _vp]),
     ("bfir_run_device_quad", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_run_device_quad_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    ("bfir_run_partial_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
+    ("bfir_run_finish_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -345,6 +347,17 @@ class Brutefir:
         a = (_vp * 4)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
         b = (_vp * 4)(*[_buf(x, self.out_bytes, "d_out") for x in d_outs])
         _check((self.lib.bfir_run_device_quad_staged if staged else self.lib.bfir_run_device_quad)(self.h, a, b))
+
+    def run_partial_quad_device(self, d_ins):
+        """partition shard with the fused reduce, four blocks: transforms, one four-block partition sum over the own
+        partitions, pushes to the owners, arrival flag (bfir_run_partial_quad_device)"""
+        a = (_vp * 4)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
+        _check(self.lib.bfir_run_partial_quad_device(self.h, a))
+
+    def run_finish_quad_device(self, d_outs):
+        """wait for every source rank's arrival flag on the device, then sum and emit the own channels of the four blocks"""
+        b = (_vp * 4)(*[_ptr(x) for x in d_outs])
+        _check(self.lib.bfir_run_finish_quad_device(self.h, b))
 
     def run_async_pair(self, in0, in1, out0, out1):
         """Two consecutive blocks of PINNED host buffers; returns the ticket of the second block."""

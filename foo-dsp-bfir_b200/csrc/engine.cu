@@ -29,6 +29,12 @@ struct Engine {
     void *recv = nullptr;
     void *peer_opened[BFIR_MAX_PEERS] = {};
     int own_first = 0, own_count = 0;
+    int peer_phase = -1;            // receive-buffer phase back_group sums (-1: block parity, one-block calls)
+    unsigned int peer_epoch = 0;    // four-block calls made (arrival-flag value)
+    bool peer_quad_pending = false; // run_partial_quad has been queued, run_finish_quad has not
+    int *d_peer_timeout = nullptr;  // set by peer_wait_kernel when a source rank never arrived
+    int run_partial_quad(const void *const d_in[4]);
+    int run_finish_quad(void *const d_out[4]);
     int peer_setup(int rank, int world);
     int peer_ready() const { if (!peer.enabled) return 1; for (int q = 0; q < peer.world; q++) if (!peer.recv[q]) return 0; return 1; }
     int part_begin = 0, part_count = 0;
@@ -367,11 +373,11 @@ void Engine::destroy()
     if (recv) { cudaFree(recv); recv = nullptr; }
     for (int k = 1; k < kStage; k++) { if (stage_in[k]) cudaFree(stage_in[k]); if (stage_out[k]) cudaFree(stage_out[k]); stage_in[k] = stage_out[k] = nullptr; }
     stage_in[0] = stage_out[0] = nullptr;
-    void *bufs[] = { coeff_map, acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
+    void *bufs[] = { d_peer_timeout, coeff_map, acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
     acc_pair = nullptr; acc_quad[0] = acc_quad[1] = nullptr;
     fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
-    state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; coeff_map = nullptr; pb_inc = nullptr; stats = nullptr;
+    state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; coeff_map = nullptr; d_peer_timeout = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
     h_state = nullptr;
     if (h_flag) cudaFreeHost(h_flag);
@@ -511,9 +517,13 @@ int Engine::peer_setup(int rank, int world)
     own_count = own_first >= n_red ? 0 : (n_red - own_first < peer.cpr ? n_red - own_first : peer.cpr);
     if (own_count < 1) { set_error("rank %d owns no channel", rank); return BFIR_ERR_INVALID; }
     if (recv) { cudaFree(recv); recv = nullptr; }
-    const size_t bytes = (size_t)2 * world * peer.cpr * N * rs;
+    const size_t data_bytes = (size_t)BFIR_PEER_PHASES * world * peer.cpr * N * rs;
+    const size_t bytes = data_bytes + 256;                 // + arrival flags
+    peer.flag_offset = (long long)data_bytes;
     BFIR_CUDA(cudaMalloc(&recv, bytes));
     BFIR_CUDA(cudaMemset(recv, 0, bytes));
+    if (!d_peer_timeout) { BFIR_CUDA(cudaMalloc((void **)&d_peer_timeout, sizeof(int))); BFIR_CUDA(cudaMemset(d_peer_timeout, 0, sizeof(int))); }
+    peer_epoch = 0; peer_quad_pending = false;
     peer.recv[rank] = recv;
     peer.enabled = 1;
     invalidate_graphs();
@@ -626,7 +636,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
         XbarArgs x = {};
         x.in = acc; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
         x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = ns; x.stream_base = s0;
-        x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.push = peer; x.push_state = state + g;
+        x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.push = peer; x.push_state = state + g; x.push_phase = -1;
         xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
         xk<<<dim3((N + 255) / 256, ns), 256, (size_t)Co * C * rs, st>>>(x);
         count_launch();
@@ -645,8 +655,8 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
     if (peer.enabled) { // owner side: sum the source slots of the own channels, then the normal output stage on them
         void *dst = xbar ? yacc : acc;
         dim3 grid((N + 255) / 256, own_count);
-        if (rs == 4) peer_sum_kernel<float><<<grid, 256, 0, st>>>((const float *)recv, (float *)dst, state + g, peer.world, peer.cpr, N, own_first, own_count);
-        else peer_sum_kernel<double><<<grid, 256, 0, st>>>((const double *)recv, (double *)dst, state + g, peer.world, peer.cpr, N, own_first, own_count);
+        if (rs == 4) peer_sum_kernel<float><<<grid, 256, 0, st>>>((const float *)recv, (float *)dst, state + g, peer.world, peer.cpr, N, own_first, own_count, peer_phase);
+        else peer_sum_kernel<double><<<grid, 256, 0, st>>>((const double *)recv, (double *)dst, state + g, peer.world, peer.cpr, N, own_first, own_count, peer_phase);
         count_launch();
         BFIR_CUDA(cudaGetLastError());
         InvArgs v = {};
@@ -867,6 +877,86 @@ int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void
     return staged_blocks(2, in, out);
 }
 
+// Partition shard with the fused reduce, FOUR blocks per call (steady state: every partition live). run_partial_quad:
+// four forward transforms (+ input crossbar), ONE four-block partition sum over this rank's partitions (a shard of
+// P/G partitions costs (2P/G + 7) spectra per channel for four blocks instead of 4 (2P/G + 1)), the four partial
+// results pushed to their owners (straight from the partition-sum kernel, or from the output crossbar), then the
+// arrival flag. run_finish_quad: wait for every source rank's flag, then per block sum the own channels' slots and
+// run the output stage on them. No collective and no host synchronisation between the two.
+int Engine::run_partial_quad(const void *const d_in[4])
+{
+    if (!peer.enabled || !peer_ready()) { set_error("run_partial_quad needs a connected peer shard"); return BFIR_ERR_INVALID; }
+    if (peer_quad_pending) { set_error("run_partial_quad called twice without run_finish_quad"); return BFIR_ERR_INVALID; }
+    if (host_blockcounter < (unsigned int)P || xfade_pending || n_groups != 1) { set_error("four-block shard calls need the delay line filled (%d blocks) and no pending filter swap", P); return BFIR_ERR_NOT_READY; }
+    const size_t cbuf = (size_t)N * rs;
+    if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
+    for (int k = 0; k < 2; k++) if (!acc_quad[k]) BFIR_CUDA(cudaMalloc(&acc_quad[k], cbuf * Ct));
+    int rc = BFIR_OK;
+    prof(0);
+    prof_suppress = true;
+    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
+    fwd_block_offset = 0;
+    prof_suppress = false;
+    if (rc != BFIR_OK) return rc;
+    prof(1);
+    tail_ready = false;
+    const int base = 2 + (int)(peer_epoch & 1u) * 4;
+    MacArgs m = {};
+    m.fdl = fdl; m.coeffs = coeffs;
+    m.acc_multi[0] = acc; m.acc_multi[1] = acc_pair; m.acc_multi[2] = acc_quad[0]; m.acc_multi[3] = acc_quad[1];
+    m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = part_begin; m.part_count = part_count;
+    m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state; m.block_offset = 0; m.ch_base = 0;
+    if (!xbar) { m.push = peer; m.push_phase = base; }
+    const int mthreads = rs == 8 ? quad_threads : 256;
+    // slices: a shard has few partitions per channel, so split less than the whole-filter heuristic would
+    int split = quad_split;
+    while (split > 1 && split * 4 > part_count) split >>= 1;
+    dim3 grid((N / 8 + mthreads / split - 1) / (mthreads / split), Ct);
+    mac_kernel_t mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split, mthreads);
+    mk<<<grid, mthreads, 0, stream>>>(m);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    prof(2);
+    if (xbar) {
+        for (int b = 0; b < 4; b++) {   // partial out-mix of block b, rows pushed to their owners
+            XbarArgs x = {};
+            x.in = m.acc_multi[b]; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
+            x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = S; x.stream_base = 0;
+            x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.push = peer; x.push_state = state; x.push_phase = base + b;
+            xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
+            xk<<<dim3((N + 255) / 256, S), 256, (size_t)Co * C * rs, stream>>>(x);
+            count_launch();
+        }
+        BFIR_CUDA(cudaGetLastError());
+    }
+    peer_epoch++;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    peer_quad_pending = true;
+    return BFIR_OK;
+}
+
+int Engine::run_finish_quad(void *const d_out[4])
+{
+    if (!peer_quad_pending) { set_error("run_finish_quad without run_partial_quad"); return BFIR_ERR_INVALID; }
+    peer_quad_pending = false;
+    peer_wait_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch, d_peer_timeout);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    const int base = 2 + (int)((peer_epoch - 1u) & 1u) * 4;
+    int rc = BFIR_OK;
+    prof_suppress = true;
+    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { peer_phase = base + b; rc = back_group(0, d_out[b]); }
+    peer_phase = -1;
+    prof_suppress = false;
+    prof(3);
+    if (pidx < pcap) pidx++;
+    for (int b = 0; b < 4; b++) finish_block();
+    return rc;
+}
+
 // four consecutive blocks of one group with ONE partition-sum launch (single precision): see partition_mac_multi_kernel
 int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
 {
@@ -907,12 +997,12 @@ int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
 int Engine::enqueue_quad(const void *const d_in[4], void *const d_out[4], bool staged)
 {
     int rc;
-    if (!pair_ok() || xbar) {
+    if (!pair_ok()) {
         rc = enqueue_pair(d_in[0], d_in[1], d_out[0], d_out[1], staged, staged);
         if (rc == BFIR_OK) rc = enqueue_pair(d_in[2], d_in[3], d_out[2], d_out[3], staged, staged);
         return rc;
     }
-    if (staged && n_groups == 1 && staged_enabled) return staged_blocks(4, d_in, d_out);
+    if (staged && n_groups == 1 && !xbar && staged_enabled) return staged_blocks(4, d_in, d_out);
     if ((rc = close_staged()) != BFIR_OK) return rc;
     const size_t cbuf = (size_t)N * rs;
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
@@ -1012,6 +1102,15 @@ int Engine::sync_and_probe(bool allow_rollback, cudaEvent_t wait_for)
     }
     done_ticket = next_ticket;
     prof_collect();
+    if (peer.enabled && d_peer_timeout != nullptr && peer_epoch > 0) {   // four-block shard calls: did every source rank arrive?
+        int timed_out = 0;
+        BFIR_CUDA(cudaMemcpy(&timed_out, d_peer_timeout, sizeof(int), cudaMemcpyDeviceToHost));
+        if (timed_out) {
+            cudaMemset(d_peer_timeout, 0, sizeof(int));
+            set_error("partition shard: a peer rank never signalled its partial sums (time-out in the arrival wait)");
+            return BFIR_ERR_CUDA;
+        }
+    }
     const unsigned long long n = blocks_since_sync;
     blocks_since_sync = 0;
     if (*(volatile int *)h_flag == 0) return BFIR_OK;          // nothing raised the flag: no copy needed
@@ -1527,6 +1626,25 @@ int bfir_run_finish_device(bfir_engine *e, void *d_outbuf)
     int rc = check_ready(e);
     if (rc != BFIR_OK) return rc;
     return e->impl.enqueue_back(d_outbuf);
+}
+
+int bfir_run_partial_quad_device(bfir_engine *e, const void *const d_in[4])
+{
+    if (e != nullptr) e->impl.close_async();
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_in == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 4; b++) if (d_in[b] == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.run_partial_quad(d_in);
+}
+
+int bfir_run_finish_quad_device(bfir_engine *e, void *const d_out[4])
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_out == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 4; b++) if (d_out[b] == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.run_finish_quad(d_out);
 }
 
 int bfir_peer_setup(bfir_engine *e, int rank, int world)

@@ -36,6 +36,7 @@ struct MacArgs {
     unsigned int abs_block;
     int procblocks_bias;     // 1: look-ahead launch for the NEXT block, whose forward transform has not counted itself yet
     PeerPush push;           // enabled: partial sums go to the owner rank's receive buffer (fused reduce)
+    int push_phase;          // multi kernel: receive-buffer phase of block t (block t+b: push_phase + b)
 };
 
 template <class T> struct vec8 { T v[8]; };
@@ -256,8 +257,10 @@ __global__ void __launch_bounds__(THREADS) partition_mac_multi_kernel(const MacA
     const unsigned int t = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.block_offset;
     const int cs_ = a.coeff_map ? a.coeff_map[ch] : ch;
     const int peff = min(a.coeff_blocks[cs_], a.n_parts);
-    const int cs = (peff + SPLIT - 1) / SPLIT;
-    const int i0 = slice * cs, i1 = min(peff, i0 + cs);
+    // partition shard [part_begin, part_begin + part_count) (the whole filter: 0, n_parts), dealt to the slices
+    const int p_end = min(peff, a.part_begin + a.part_count);
+    const int cs = (max(p_end - a.part_begin, 0) + SPLIT - 1) / SPLIT;
+    const int i0 = a.part_begin + slice * cs, i1 = min(p_end, i0 + cs);
     const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + (long long)g * 8;
     const T *cf = (const T *)a.coeffs + cs_ * a.coeff_stride_ch + (long long)g * 8;
     const unsigned int P = (unsigned int)a.n_slots;
@@ -313,7 +316,10 @@ __global__ void __launch_bounds__(THREADS) partition_mac_multi_kernel(const MacA
     }
     if (active) {
 #pragma unroll
-        for (int b = 0; b < NB; b++) st8((T *)a.acc_multi[b] + (long long)ch * a.N + (long long)g * 8, acc[b]);
+        for (int b = 0; b < NB; b++) {
+            T *dst = a.push.enabled ? peer_dst<T>(a.push, ch, a.N, (unsigned int)(a.push_phase + b)) : (T *)a.acc_multi[b] + (long long)ch * a.N;
+            st8(dst + (long long)g * 8, acc[b]);
+        }
     }
 }
 

@@ -38,16 +38,19 @@ enum {
 // of reduced channel `ch` to local memory for a later NCCL reduce, the producing kernel stores it
 // straight into the receive buffer of the rank that owns `ch` -- a peer-mapped pointer, i.e. plain
 // st.global over NVLink -- so the transfer overlaps the partition sum tile by tile. Receive buffer
-// of rank q: [2 (block parity)][world (source rank)][cpr (owned channels)][N].
+// of rank q: [BFIR_PEER_PHASES][world (source rank)][cpr (owned channels)][N], then one arrival flag per source
+// rank. Phases 0 / 1: block parity of the one-block calls; phases 2 .. 9: (call parity, block) of the four-block calls.
 #define BFIR_MAX_PEERS 8
+#define BFIR_PEER_PHASES 10
 struct PeerPush {
     void *recv[BFIR_MAX_PEERS];
     int world, self, cpr, enabled;
+    long long flag_offset;      // bytes from the start of a receive buffer to its unsigned int flags[world]
 };
-template <class T> BFIR_HD T *peer_dst(const PeerPush &p, int ch, int N, unsigned int parity)
+template <class T> BFIR_HD T *peer_dst(const PeerPush &p, int ch, int N, unsigned int phase)
 {
     const int q = ch / p.cpr, local = ch - q * p.cpr;
-    return (T *)p.recv[q] + (((long long)parity * p.world + p.self) * p.cpr + local) * N;
+    return (T *)p.recv[q] + (((long long)phase * p.world + p.self) * p.cpr + local) * N;
 }
 
 // device-resident engine state: lets one CUDA graph be replayed for every block

@@ -29,7 +29,8 @@ struct XbarArgs {
     unsigned char *pb_inc;
     int stream_base;           // first stream of this launch (channel groups)
     PeerPush push;             // enabled: output rows go to the owner rank's receive buffer (fused reduce)
-    const EngineState *push_state; // block parity of the receive buffer
+    const EngineState *push_state; // block parity of the receive buffer (one-block calls)
+    int push_phase;            // >= 0: explicit receive-buffer phase (four-block calls), else the parity of push_state
 };
 
 #ifdef __CUDACC__
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
         T acc = (T)0;
 #pragma unroll
         for (int i = 0; i < MAXI; i++) if (i < a.n_in) acc = fma(row[i], x[i], acc);
-        if (a.push.enabled) peer_dst<T>(a.push, s * a.n_out + o, a.N, a.push_state->blockcounter & 1u)[j] = acc;
+        if (a.push.enabled) peer_dst<T>(a.push, s * a.n_out + o, a.N, a.push_phase >= 0 ? (unsigned int)a.push_phase : (a.push_state->blockcounter & 1u))[j] = acc;
         else out[(long long)o * a.out_stride] = acc;
     }
 }
@@ -71,15 +72,42 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
 // owner side of the fused reduce: sum the `world` source slots of each owned channel in rank order
 // (deterministic) into the local spectrum buffer at the channel's absolute position
 template <class T>
-__global__ void __launch_bounds__(256) peer_sum_kernel(const T *recv, T *dst, const EngineState *state, int world, int cpr, int N, int ch_first, int n_own)
+__global__ void __launch_bounds__(256) peer_sum_kernel(const T *recv, T *dst, const EngineState *state, int world, int cpr, int N, int ch_first, int n_own, int phase)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int local = blockIdx.y;
     if (j >= N || local >= n_own) return;
-    const unsigned int parity = state->blockcounter & 1u;
+    const unsigned int parity = phase >= 0 ? (unsigned int)phase : (state->blockcounter & 1u);
     T acc = (T)0;
     for (int s = 0; s < world; s++) acc += recv[(((long long)parity * world + s) * cpr + local) * N + j];
     dst[(long long)(ch_first + local) * N + j] = acc;
+}
+
+// Cross-rank ordering of the four-block calls without a collective: after its pushes (earlier kernels on the same
+// stream) a rank raises its arrival flag in every peer's receive buffer -- fence, then a system-scope store over
+// NVLink -- and the owner's output stage starts with a kernel that waits until every source rank's flag has reached
+// the call's epoch. Replaces the one-element NCCL all-reduce of the one-block calls (tens of microseconds at 8 ranks).
+// A rank that never arrives trips the time-out (about two seconds) and is reported by bfir_sync, not by a hang.
+static __global__ void peer_signal_kernel(const PeerPush p, unsigned int epoch)
+{
+    const int q = threadIdx.x;
+    if (q >= p.world) return;
+    __threadfence_system();
+    volatile unsigned int *f = (volatile unsigned int *)((char *)p.recv[q] + p.flag_offset) + p.self;
+    *f = epoch;
+    __threadfence_system();
+}
+static __global__ void peer_wait_kernel(const PeerPush p, unsigned int epoch, int *timed_out)
+{
+    const int s = threadIdx.x;
+    if (s >= p.world) return;
+    volatile unsigned int *f = (volatile unsigned int *)((char *)p.recv[p.self] + p.flag_offset) + s;
+    const long long t0 = clock64();
+    while ((int)(*f - epoch) < 0) {
+        if (clock64() - t0 > 4000000000LL) { *timed_out = 1; break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
 }
 
 typedef void (*xbar_kernel_t)(const XbarArgs);

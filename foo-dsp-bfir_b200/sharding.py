@@ -118,6 +118,12 @@ class FusedPartitionShardedEngine:
         self.dist.all_reduce(self.flag, op=self.dist.ReduceOp.SUM, group=self.group)   # cross-rank barrier on the stream
         self.engine.run_finish_device(d_out_own)                              # sum own slots + output stage
 
+    def run_device_quad(self, d_ins, d_outs_own):
+        """Four blocks per call (steady state, i.e. after filter_blocks one-block calls): one four-block partition
+        sum per rank, pushes, and a device-side arrival flag instead of the collective -- no NCCL call at all."""
+        self.engine.run_partial_quad_device(d_ins)
+        self.engine.run_finish_quad_device(d_outs_own)
+
     def gather(self, d_out_own, d_all):
         """d_all [world][L * cpr] <- every rank's own block (only needed when one rank wants all channels)"""
         self.dist.all_gather_into_tensor(d_all, d_out_own, group=self.group)

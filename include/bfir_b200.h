@@ -222,6 +222,15 @@ int bfir_get_blockcounter(bfir_engine *e, unsigned int *out);
  * has summed the shards' buffers (NCCL reduce / all-reduce), run_finish_device does the output stage. */
 int bfir_run_partial_device(bfir_engine *e, const void *d_inbuf);
 int bfir_run_finish_device(bfir_engine *e, void *d_outbuf);
+/* The same with FOUR consecutive blocks per call and no collective in between (fused reduce only, i.e. after
+ * bfir_peer_setup / import; steady state: at least filter_blocks blocks since the last reset, else BFIR_ERR_NOT_READY
+ * and the caller keeps using the one-block pair above): bfir_run_partial_quad_device transforms the four blocks, runs
+ * ONE four-block partition sum over this rank's partitions, pushes the four partial results to their owners and
+ * raises this rank's arrival flag in every peer's receive buffer; bfir_run_finish_quad_device waits (on the device)
+ * until every source rank's flag has arrived, then sums and emits the own channels of the four blocks. Call them
+ * back to back on every rank; a rank that never arrives is reported by bfir_sync after a time-out. */
+int bfir_run_partial_quad_device(bfir_engine *e, const void *const d_in[4]);
+int bfir_run_finish_quad_device(bfir_engine *e, void *const d_out[4]);
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
 
 /* Fused partition-shard reduce (no reference counterpart; SURVEY 8e "fused variant"). After

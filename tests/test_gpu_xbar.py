@@ -245,3 +245,14 @@ def test_crossbar_block_pairs_equal_single_blocks(pkg, rs, L, P, n_in, n_f, n_ou
         a = out_s[b].cpu().numpy()
         assert rel_rms(out_p[b].cpu().numpy(), a) < tol, b
         assert rel_rms(out_h[b].numpy(), a) < tol, b
+    # four blocks per partition-sum launch with the crossbar (bfir_run_device_quad)
+    quad = pkg.Brutefir(L, P, rs, n_f, fmt, fmt, 48000, False, n_streams=S, xbar_inputs=n_in, xbar_outputs=n_out)
+    assert quad.set_coeff(h, P) == 0
+    quad.set_crossbar(gin, gout)
+    out_q = [torch.zeros(n_o, dtype=tdt, device="cuda") for _ in range(nblk)]
+    nq = nblk - nblk % 4
+    for b in range(0, nq, 4):
+        quad.run_device_quad(d_in[b:b + 4], out_q[b:b + 4])
+    assert quad.sync() == 0 and quad.blockcounter() == nq
+    for b in range(nq):
+        assert rel_rms(out_q[b].cpu().numpy(), out_s[b].cpu().numpy()) < tol, b

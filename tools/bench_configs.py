@@ -248,6 +248,24 @@ def partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20, 
         ms = ev0.elapsed_time(ev1) / blocks
         out["unsharded_one_gpu"] = {"ms_per_block": ms, "Msamples_s": n * L / (ms * 1e-3) / 1e6, "api": "bfir_run_device"}
         y_ref = d_ref.double().reshape(L, n).clone()            # output of block P + blocks - 1
+        # the same engine four blocks per call (one four-block partition sum): the fair one-GPU point for the
+        # four-block shard calls below
+        d_q = [d_ref] + [torch.empty_like(d_ref) for _ in range(3)]
+        qin = [d_in[(P + blocks + k) % 4] for k in range(4)]
+        full.run_device_quad(qin, d_q)
+        assert full.sync() == 0
+        nq = max(blocks // 4, 1)
+        ev0.record(stream)
+        for k in range(nq):
+            full.run_device_quad(qin, d_q)
+        ev1.record(stream)
+        assert full.sync() == 0
+        torch.cuda.synchronize()
+        msq = ev0.elapsed_time(ev1) / (4 * nq)
+        out["unsharded_one_gpu_four_blocks_per_call"] = {"ms_per_block": msq, "Msamples_s": n * L / (msq * 1e-3) / 1e6, "api": "bfir_run_device_quad"}
+        # reference output for the four-block shard calls: blocks P+blocks+4*(1+nq) .. +3 have just been emitted; the
+        # shards below replay the same input sequence, so keep the last call's four outputs
+        y_ref_q = [t.double().reshape(L, n).clone() for t in d_q]
         full.close()
         del full
     if world == 1:
@@ -286,8 +304,27 @@ def partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20, 
         err = float(torch.sqrt(torch.mean((y - r) ** 2) / torch.mean(r ** 2)))
     out["fused_peer_reduce"] = {"ms_per_block": ms, "Msamples_s": n * L / (ms * 1e-3) / 1e6, "partitions_per_rank": count,
                                 "rel_rms_vs_unsharded": err, "output": "every rank emits its own %d output channels" % fz.own_count}
+    # ---- (c) fused reduce, four blocks per call: one four-block partition sum per rank, arrival flags, no collective
+    nq = max(blocks // 4, 1)
+    qin = [d_in[(P + blocks + k) % 4] for k in range(4)]
+    d_own4 = [d_own] + [torch.empty_like(d_own) for _ in range(3)]
+    fz.run_device_quad(qin, d_own4)
+    assert fz.sync() == 0
+    ms = timed(lambda b: fz.run_device_quad(qin, d_own4), fz.sync, nq, 0) / 4
+    err = None
+    if rank == 0:
+        errs = []
+        for k in range(4):
+            y = d_own4[k].double().reshape(L, fz.own_count)
+            r = y_ref_q[k][:, fz.own_first:fz.own_first + fz.own_count]
+            errs.append(float(torch.sqrt(torch.mean((y - r) ** 2) / torch.mean(r ** 2))))
+        err = max(errs)
+    out["fused_peer_reduce_four_blocks_per_call"] = {"ms_per_block": ms, "Msamples_s": n * L / (ms * 1e-3) / 1e6, "partitions_per_rank": count,
+                                                     "rel_rms_vs_unsharded": err, "api": "bfir_run_partial_quad_device + bfir_run_finish_quad_device (device-side arrival flags, no collective)"}
     eng.close()
     if rank == 0:
+        out["four_blocks_speedup_vs_unsharded_four_blocks"] = out["unsharded_one_gpu_four_blocks_per_call"]["ms_per_block"] / ms
+        out["four_blocks_strong_scaling_efficiency"] = out["four_blocks_speedup_vs_unsharded_four_blocks"] / world
         best = min(out["nccl_all_reduce"]["ms_per_block"], out["fused_peer_reduce"]["ms_per_block"])
         out["speedup_vs_unsharded_same_box"] = out["unsharded_one_gpu"]["ms_per_block"] / best
         out["strong_scaling_efficiency"] = out["speedup_vs_unsharded_same_box"] / world
