@@ -184,7 +184,7 @@ def test_set_coeff_errors_and_replacement(pkg, oracle):
 def test_invalid_parameters(pkg):
     for args in [(100, 2, 4, 2, 8, 8, 44100, False), (64, 2, 5, 2, 8, 8, 44100, False), (64, 0, 4, 2, 8, 8, 44100, False),
                  (64, 2, 4, 0, 8, 8, 44100, False), (64, 2, 4, 2, 0, 8, 44100, False), (64, 2, 4, 2, 8, 12, 44100, False),
-                 (65536, 2, 4, 2, 8, 8, 44100, False), (32768, 2, 8, 2, 8, 8, 44100, False)]:
+                 (65536, 2, 4, 2, 8, 8, 44100, False), (65536, 2, 8, 2, 8, 8, 44100, False)]:
         with pytest.raises(pkg.BfirError) as e:
             pkg.Brutefir(*args)
         assert e.value.code == pkg.ERR_INVALID
