@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbfir_b200.so")
+LIB_PATH = os.environ.get("BFIR_LIB") or os.path.join(HERE, "libbfir_b200.so")   # BFIR_LIB: A/B builds of the library (tools)
 
 OK, ERR_NONFINITE, ERR_COEFF, ERR_NOT_READY, ERR_INVALID, ERR_CUDA = 0, -1, -2, -3, -4, -5
 
@@ -78,6 +78,7 @@ API = [
     ("bfir_run_device_quad_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_run_partial_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
     ("bfir_run_finish_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
+    ("bfir_run_shard_quad_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -358,6 +359,13 @@ class Brutefir:
         """wait for every source rank's arrival flag on the device, then sum and emit the own channels of the four blocks"""
         b = (_vp * 4)(*[_ptr(x) for x in d_outs])
         _check(self.lib.bfir_run_finish_quad_device(self.h, b))
+
+    def run_shard_quad_staged(self, d_ins, d_outs):
+        """both halves of the four-block shard call through the stage pipeline (bfir_run_shard_quad_staged): inputs
+        complete at call time, own-channel outputs visible after join() / sync()"""
+        a = (_vp * 4)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
+        b = (_vp * 4)(*[_ptr(x) for x in d_outs])
+        _check(self.lib.bfir_run_shard_quad_staged(self.h, a, b))
 
     def run_async_pair(self, in0, in1, out0, out1):
         """Two consecutive blocks of PINNED host buffers; returns the ticket of the second block."""

@@ -35,6 +35,8 @@ struct Engine {
     int *d_peer_timeout = nullptr;  // set by peer_wait_kernel when a source rank never arrived
     int run_partial_quad(const void *const d_in[4]);
     int run_finish_quad(void *const d_out[4]);
+    int shard_quad_staged(const void *const d_in[4], void *const d_out[4]);
+    cudaEvent_t sp_arrived[2] = {};  // staged shard calls: every source rank's flag of call k has been seen (inverse stream)
     int peer_setup(int rank, int world);
     int peer_ready() const { if (!peer.enabled) return 1; for (int q = 0; q < peer.world; q++) if (!peer.recv[q]) return 0; return 1; }
     int part_begin = 0, part_count = 0;
@@ -246,7 +248,7 @@ int Engine::init(const bfir_config_t &c)
     BFIR_CUDA(cudaStreamCreateWithFlags(&sp_fwd, cudaStreamNonBlocking));
     BFIR_CUDA(cudaStreamCreateWithFlags(&sp_inv, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++)
-        for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k] }) BFIR_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k], &sp_arrived[k] }) BFIR_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     BFIR_CUDA(cudaStreamCreateWithFlags(&tail_stream, cudaStreamNonBlocking));
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) BFIR_CUDA(cudaEventCreateWithFlags(&tail_done[g], cudaEventDisableTiming));
     BFIR_CUDA(cudaEventCreateWithFlags(&tail_join_ev, cudaEventDisableTiming));
@@ -359,7 +361,7 @@ void Engine::destroy()
     if (out_done) { cudaEventDestroy(out_done); out_done = nullptr; }
     for (cudaStream_t *st : { &sp_fwd, &sp_inv }) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
     for (int k = 0; k < 2; k++) {
-        for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
+        for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k], &sp_arrived[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
         for (int j = 0; j < 4; j++) if (sp_acc[k][j]) { cudaFree(sp_acc[k][j]); sp_acc[k][j] = nullptr; }
     }
     if (tail_stream) { cudaStreamSynchronize(tail_stream); cudaStreamDestroy(tail_stream); tail_stream = nullptr; }
@@ -606,6 +608,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
         x.in = xin; x.in_stride = N; x.out = fdl; x.out_stride = (long long)Pslots * N; x.slot_stride = N;
         x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = ns; x.stream_base = s0;
         x.state = state + g; x.n_slots = Pslots; x.n_parts = P; x.slot_offset = fwd_block_offset; x.procblocks = procblocks; x.pb_inc = pb_inc;
+        x.use_abs_block = use_abs ? 1 : 0; x.abs_block = host_blockcounter + (unsigned int)fwd_block_offset;
         xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
         xk<<<dim3((N + 255) / 256, ns), 256, (size_t)C * Ci * rs, st>>>(x);
         count_launch();
@@ -957,6 +960,117 @@ int Engine::run_finish_quad(void *const d_out[4])
     return rc;
 }
 
+// The four-block shard call through the stage pipeline: call k = blocks t .. t+3 of a peer-connected partition shard.
+//   forward stream:  after the partition sum of call k-2 (slot reuse, as in staged_blocks): four forward transforms
+//                    (+ input crossbar)
+//   engine's stream: after those and after this rank has SEEN every peer's flag of call k-1: ONE four-block partition
+//                    sum over the rank's partitions, the pushes (from the sum or from the output crossbar); then,
+//                    after this rank's own output stage of call k-1 has finished, the arrival flag of call k
+//   inverse stream:  after the flag went out: wait for every source rank's flag of call k, then per block sum the
+//                    own channels' slots and run the output stage
+// Receive-buffer phases are reused every second call. A peer overwrites this rank's phase set of call k-2 with its
+// pushes of call k only after it has seen this rank's flag of call k-1, and that flag is raised only after this
+// rank's output stage of call k-2 has read the set: no collective, no host synchronisation, and the three stages of
+// neighbouring calls overlap on every rank.
+int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
+{
+    if (!peer.enabled || !peer_ready()) { set_error("shard_quad_staged needs a connected peer shard"); return BFIR_ERR_INVALID; }
+    if (peer_quad_pending) { set_error("run_partial_quad is pending: finish it first"); return BFIR_ERR_INVALID; }
+    if (host_blockcounter < (unsigned int)P || xfade_pending || n_groups != 1) { set_error("four-block shard calls need the delay line filled (%d blocks) and no pending filter swap", P); return BFIR_ERR_NOT_READY; }
+    const size_t cbuf = (size_t)N * rs;
+    if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
+    for (int k = 0; k < 2; k++) if (!acc_quad[k]) BFIR_CUDA(cudaMalloc(&acc_quad[k], cbuf * Ct));
+    int rc;
+    if (!sp_open) {
+        if ((rc = close_async()) != BFIR_OK) return rc;
+        BFIR_CUDA(cudaEventRecord(fork_ev, stream));
+        BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, fork_ev, 0));
+        BFIR_CUDA(cudaStreamWaitEvent(sp_inv, fork_ev, 0));
+        for (int k = 0; k < 2; k++) {
+            BFIR_CUDA(cudaEventRecord(sp_mac_done[k], stream));
+            BFIR_CUDA(cudaEventRecord(sp_inv_done[k], sp_inv));
+            BFIR_CUDA(cudaEventRecord(sp_arrived[k], sp_inv));
+        }
+        sp_open = true;
+        sp_pairs = 0;
+    }
+    const int par = (int)(sp_pairs & 1ull);
+    tail_ready = false;
+    use_abs = true;
+    // forward stage
+    BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, sp_mac_done[par], 0));
+    stage_stream = sp_fwd;
+    prof_suppress = true;
+    rc = BFIR_OK;
+    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
+    fwd_block_offset = 0;
+    prof_suppress = false;
+    stage_stream = nullptr;
+    if (rc != BFIR_OK) { use_abs = false; return rc; }
+    BFIR_CUDA(cudaEventRecord(sp_fwd_done[par], sp_fwd));
+    // partition sum + pushes on the engine's stream
+    BFIR_CUDA(cudaStreamWaitEvent(stream, sp_fwd_done[par], 0));
+    BFIR_CUDA(cudaStreamWaitEvent(stream, sp_arrived[par ^ 1], 0));
+    prof(0);
+    prof(1);
+    const int base = 2 + (int)(peer_epoch & 1u) * 4;
+    MacArgs m = {};
+    m.fdl = fdl; m.coeffs = coeffs;
+    m.acc_multi[0] = acc; m.acc_multi[1] = acc_pair; m.acc_multi[2] = acc_quad[0]; m.acc_multi[3] = acc_quad[1];
+    m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
+    m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = part_begin; m.part_count = part_count;
+    m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state; m.block_offset = 0; m.ch_base = 0;
+    m.use_abs_block = 1; m.abs_block = host_blockcounter;
+    if (!xbar) { m.push = peer; m.push_phase = base; }
+    const int mthreads = rs == 8 ? quad_threads : 256;
+    int split = quad_split;
+    while (split > 1 && split * 4 > part_count) split >>= 1;
+    dim3 grid((N / 8 + mthreads / split - 1) / (mthreads / split), Ct);
+    mac_kernel_t mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split, mthreads);
+    mk<<<grid, mthreads, 0, stream>>>(m);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    prof(2);
+    if (xbar) {
+        for (int b = 0; b < 4; b++) {
+            XbarArgs x = {};
+            x.in = m.acc_multi[b]; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
+            x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = S; x.stream_base = 0;
+            x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.push = peer; x.push_state = state; x.push_phase = base + b;
+            xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
+            xk<<<dim3((N + 255) / 256, S), 256, (size_t)Co * C * rs, stream>>>(x);
+            count_launch();
+        }
+        BFIR_CUDA(cudaGetLastError());
+    }
+    prof(3);
+    if (pidx < pcap) pidx++;
+    BFIR_CUDA(cudaStreamWaitEvent(stream, sp_inv_done[par ^ 1], 0));   // own output stage of call k-1 has read its phase set
+    peer_epoch++;
+    peer_signal_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    BFIR_CUDA(cudaEventRecord(sp_mac_done[par], stream));
+    // output stage on the inverse stream
+    BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
+    peer_wait_kernel<<<1, 32, 0, sp_inv>>>(peer, peer_epoch, d_peer_timeout);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    BFIR_CUDA(cudaEventRecord(sp_arrived[par], sp_inv));
+    stage_stream = sp_inv;
+    prof_suppress = true;
+    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { peer_phase = base + b; rc = back_group(0, d_out[b]); }
+    peer_phase = -1;
+    prof_suppress = false;
+    stage_stream = nullptr;
+    use_abs = false;
+    if (rc != BFIR_OK) return rc;
+    BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
+    sp_pairs++;
+    for (int b = 0; b < 4; b++) finish_block();
+    return BFIR_OK;
+}
+
 // four consecutive blocks of one group with ONE partition-sum launch (single precision): see partition_mac_multi_kernel
 int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
 {
@@ -1002,7 +1116,7 @@ int Engine::enqueue_quad(const void *const d_in[4], void *const d_out[4], bool s
         if (rc == BFIR_OK) rc = enqueue_pair(d_in[2], d_in[3], d_out[2], d_out[3], staged, staged);
         return rc;
     }
-    if (staged && n_groups == 1 && !xbar && staged_enabled) return staged_blocks(4, d_in, d_out);
+    if (staged && n_groups == 1 && staged_enabled) return staged_blocks(4, d_in, d_out);
     if ((rc = close_staged()) != BFIR_OK) return rc;
     const size_t cbuf = (size_t)N * rs;
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
@@ -1025,7 +1139,7 @@ int Engine::enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, voi
         if (rc == BFIR_OK) rc = pipelined ? enqueue_block_pipelined(d_in1, d_out1) : enqueue_block(d_in1, d_out1);
         return rc;
     }
-    if (staged && n_groups == 1 && !xbar && staged_enabled) return staged_pair(d_in0, d_in1, d_out0, d_out1);
+    if (staged && n_groups == 1 && staged_enabled) return staged_pair(d_in0, d_in1, d_out0, d_out1);
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, (size_t)N * rs * Ct));
     if ((rc = close_staged()) != BFIR_OK) return rc;
     if (!pipelined) { if ((rc = close_async()) != BFIR_OK) return rc; }
@@ -1645,6 +1759,15 @@ int bfir_run_finish_quad_device(bfir_engine *e, void *const d_out[4])
     if (d_out == nullptr) return BFIR_ERR_INVALID;
     for (int b = 0; b < 4; b++) if (d_out[b] == nullptr) return BFIR_ERR_INVALID;
     return e->impl.run_finish_quad(d_out);
+}
+
+int bfir_run_shard_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4])
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_in == nullptr || d_out == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 4; b++) if (d_in[b] == nullptr || d_out[b] == nullptr) return BFIR_ERR_INVALID;
+    return e->impl.shard_quad_staged(d_in, d_out);
 }
 
 int bfir_peer_setup(bfir_engine *e, int rank, int world)

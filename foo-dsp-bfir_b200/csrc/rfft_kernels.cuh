@@ -286,6 +286,13 @@ __device__ __forceinline__ void bulk_stage(void *dst, const void *src, uint32_t 
 // one thread were issued one by one, each waiting out a full memory latency (ncu source page, round 1: 40 % of the
 // forward kernel's stall samples). BFIR_FMT_SWITCH hoists the switch around the whole loop.
 #define BFIR_FMT_CASE(f, ...) case f: { constexpr int FMT = f; __VA_ARGS__; } break;
+#ifdef BFIR_LEAN_FORMATS   // experiment: only the two little-endian float formats (code size of the transform kernels)
+#define BFIR_FMT_SWITCH(fmt, ...)                                                                        \
+    switch (fmt) {                                                                                       \
+        BFIR_FMT_CASE(FMT_FLOAT_LE, __VA_ARGS__) BFIR_FMT_CASE(FMT_FLOAT64_LE, __VA_ARGS__)               \
+        default: break;                                                                                  \
+    }
+#else
 #define BFIR_FMT_SWITCH(fmt, ...)                                                                        \
     switch (fmt) {                                                                                       \
         BFIR_FMT_CASE(FMT_S8, __VA_ARGS__) BFIR_FMT_CASE(FMT_S16_LE, __VA_ARGS__) BFIR_FMT_CASE(FMT_S16_BE, __VA_ARGS__) \
@@ -294,6 +301,7 @@ __device__ __forceinline__ void bulk_stage(void *dst, const void *src, uint32_t 
         BFIR_FMT_CASE(FMT_FLOAT64_LE, __VA_ARGS__) BFIR_FMT_CASE(FMT_FLOAT64_BE, __VA_ARGS__)               \
         default: break;                                                                                  \
     }
+#endif
 
 // engine input (IN_RAW_PREV) for one thread, sample format known at compile time: the raw samples of the current
 // block (complex index n = t + j NTs of the block, i.e. frames 2n and 2n+1) and the previous block from its planar

@@ -24,6 +24,8 @@ struct XbarArgs {
     const EngineState *state;  // slot = (blockcounter + slot_offset) % n_slots
     int n_slots;
     int slot_offset;           // 1: the second block of a pair
+    int use_abs_block;         // 1: the block index is abs_block, given by the host (stage pipeline: the device counter lags behind)
+    unsigned int abs_block;
     int n_parts;               // filter partitions (procblocks cap)
     int *procblocks;           // [streams * n_out]: incremented here for the filter channels (brutefir.cpp:265-268)
     unsigned char *pb_inc;
@@ -57,7 +59,10 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
 #pragma unroll
     for (int i = 0; i < MAXI; i++) x[i] = i < a.n_in ? in[(long long)i * a.in_stride] : (T)0;
     long long off = (long long)s * a.n_out * a.out_stride + j;
-    if (a.state != NULL) off += (long long)((a.state->blockcounter + (unsigned int)a.slot_offset) % (unsigned int)a.n_slots) * a.slot_stride;
+    if (a.state != NULL) {
+        const unsigned int blk = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.slot_offset;
+        off += (long long)(blk % (unsigned int)a.n_slots) * a.slot_stride;
+    }
     T *out = (T *)a.out + off;
     for (int o = 0; o < a.n_out; o++) {
         const T *row = g + o * a.n_in;

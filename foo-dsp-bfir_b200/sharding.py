@@ -124,6 +124,16 @@ class FusedPartitionShardedEngine:
         self.engine.run_partial_quad_device(d_ins)
         self.engine.run_finish_quad_device(d_outs_own)
 
+    def run_device_quad_staged(self, d_ins, d_outs_own):
+        """The same through the engine's stage pipeline (bfir_run_shard_quad_staged): forward transforms of the next
+        call and the wait + sum + output stage of the previous one run beside the partition sum on side streams.
+        The inputs must be complete when the call is made; call join() (stream-ordered) or sync() before reading
+        the outputs."""
+        self.engine.run_shard_quad_staged(d_ins, d_outs_own)
+
+    def join(self):
+        return self.engine.join()
+
     def gather(self, d_out_own, d_all):
         """d_all [world][L * cpr] <- every rank's own block (only needed when one rank wants all channels)"""
         self.dist.all_gather_into_tensor(d_all, d_out_own, group=self.group)

@@ -182,7 +182,7 @@ int bfir_join(bfir_engine *e);
  *   BFIR_PAIR_JOINED (0)    like bfir_run_device: stream-ordered on the engine's stream, joined at the end of the call.
  *   BFIR_PAIR_PIPELINED (1) like bfir_run_device_pipelined: no join between calls; with one stream group everything
  *                           stays stream-ordered on the engine's stream (inputs may be produced on that stream).
- *   BFIR_PAIR_STAGED (2)    the engine's STAGE PIPELINE (one stream group, no crossbar; otherwise as 1): the forward
+ *   BFIR_PAIR_STAGED (2)    the engine's STAGE PIPELINE (one stream group; otherwise as 1): the forward
  *                           transforms of pair k+1 and the inverse transforms of pair k-1 run on two side streams beside
  *                           the partition sum of pair k. CONTRACT: the side streams are NOT ordered after later work on
  *                           the engine's stream, so d_in0 / d_in1 must be COMPLETE (their producers finished, e.g. a
@@ -199,8 +199,8 @@ long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, 
  * (split = partition slices per CTA, 1 for large batches). Both precisions (double: 214 registers, one CTA per SM).
  * Device buffers. bfir_run_device_quad is joined like bfir_run_device; bfir_run_device_quad_staged runs the four blocks
  * through the stage pipeline under the contract of BFIR_PAIR_STAGED (inputs complete at call time, outputs visible
- * after bfir_join / bfir_sync). With a crossbar, on a partition shard, with a pending filter swap and while the delay
- * line is still filling the call runs two pairs (or four single blocks). */
+ * after bfir_join / bfir_sync). On a partition shard, with a pending filter swap and while the delay line is still
+ * filling the call runs two pairs (or four single blocks); a crossbar (bfir_set_crossbar) is part of the stages. */
 int bfir_run_device_quad(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 int bfir_run_device_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 
@@ -231,6 +231,14 @@ int bfir_run_finish_device(bfir_engine *e, void *d_outbuf);
  * back to back on every rank; a rank that never arrives is reported by bfir_sync after a time-out. */
 int bfir_run_partial_quad_device(bfir_engine *e, const void *const d_in[4]);
 int bfir_run_finish_quad_device(bfir_engine *e, void *const d_out[4]);
+/* Both halves in ONE call through the engine's stage pipeline (same preconditions): the forward transforms of call
+ * k+1 run on a side stream beside the four-block partition sum of call k on the engine's stream, and the arrival wait
+ * + sum + output stage of call k-1 on a third. The cross-rank protocol stays collective-free: a rank pushes call k only
+ * after it has seen every peer's flag of call k-1, and raises its flag of call k only after its own output stage of
+ * call k-1 has read the receive-buffer phases that call k+1 will overwrite. CONTRACT as BFIR_PAIR_STAGED: the four
+ * input blocks are complete when the call is made; the compact own-channel output blocks are visible to the engine's
+ * stream after bfir_join, to the host after bfir_sync. Every rank makes the same sequence of calls. */
+int bfir_run_shard_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
 
 /* Fused partition-shard reduce (no reference counterpart; SURVEY 8e "fused variant"). After

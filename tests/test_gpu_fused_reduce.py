@@ -141,6 +141,81 @@ def test_two_emulated_ranks_four_blocks_per_call(pkg, rs, L, P, C, xb):
     assert [e.blockcounter() for e in ranks] == [nb, nb]
 
 
+@pytest.mark.parametrize("rs,L,P,C,xb", [(4, 512, 6, 4, (0, 0)), (8, 256, 4, 5, (0, 0)), (4, 1024, 8, 4, (3, 5)), (4, 2048, 16, 8, (8, 8))])
+def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb):
+    """bfir_run_shard_quad_staged: the four-block shard call through the stage pipeline (forward transforms, partition
+    sum + pushes, arrival wait + output stage of neighbouring calls on three streams per rank; receive-buffer phases
+    handed over by the arrival flags alone). Seven staged calls with a one-block call and a split (partial / finish)
+    four-block call in between: same output as the unsharded engine for every block."""
+    import torch
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt, tdt = (np.float32, torch.float32) if rs == 4 else (np.float64, torch.float64)
+    n_in = xb[0] or C
+    n_out = xb[1] or C
+    rng = np.random.default_rng(C + 1)
+    gains = (rng.standard_normal((C, n_in)) / np.sqrt(n_in), rng.standard_normal((n_out, C)) / np.sqrt(C))
+    h = [decay_filter(c, L * P) for c in range(C)]
+    full = build(pkg, L, P, rs, C, fmt, xb, h, gains)
+    world = 2
+    ranks = []
+    for r in range(world):
+        begin = r * (P // world)
+        count = P // world if r < world - 1 else P - begin
+        e = build(pkg, L, P, rs, C, fmt, xb, h, gains, part_begin=begin, part_count=count)
+        e.peer_setup(r, world)
+        ranks.append(e)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    for e in ranks + [full]:
+        e.set_stream(stream.cuda_stream)
+    for r, e in enumerate(ranks):
+        for q, other in enumerate(ranks):
+            if q != r:
+                e.peer_set_ptr(q, other.peer_recv_ptr())
+    own = [e.peer_own_channels() for e in ranks]
+    nb = P + 4 * 8 + 1
+    x = white_noise(3, nb * L, n_in).astype(dt)
+    d_in = [torch.from_numpy(np.ascontiguousarray(x[b * L:(b + 1) * L]).ravel()).cuda() for b in range(nb)]
+    d_ref = [torch.empty(L * n_out, dtype=tdt, device="cuda") for _ in range(nb)]
+    d_own = [[torch.empty(L * c, dtype=tdt, device="cuda") for _ in range(nb)] for _, c in own]
+    torch.cuda.synchronize()
+    for b in range(nb):
+        full.run_device(d_in[b], d_ref[b])
+
+    def single(b):
+        for e in ranks:
+            e.run_partial_device(d_in[b])
+        for e, o in zip(ranks, d_own):
+            e.run_finish_device(o[b])
+
+    b = 0
+    while b < P:
+        single(b)
+        b += 1
+    torch.cuda.synchronize()                                  # staged contract: inputs complete (they are), prefill done
+    for call in range(8):
+        if call == 3:                                         # a one-block call closes the pipeline, the next call reopens it
+            single(b)
+            b += 1
+        if call == 5:                                         # the split four-block call between staged ones
+            for e in ranks:
+                e.run_partial_quad_device(d_in[b:b + 4])
+            for e, o in zip(ranks, d_own):
+                e.run_finish_quad_device(o[b:b + 4])
+        else:
+            for e, o in zip(ranks, d_own):
+                e.run_shard_quad_staged(d_in[b:b + 4], o[b:b + 4])
+        b += 4
+    assert b == nb
+    for e in ranks + [full]:
+        assert e.sync() == 0
+    for b in range(nb):
+        ref = d_ref[b].cpu().numpy().reshape(L, n_out)
+        got = np.concatenate([o[b].cpu().numpy().reshape(L, c) for o, (_, c) in zip(d_own, own)], axis=1)
+        assert rel_rms(got, ref) < (2e-6 if rs == 4 else 1e-13), b
+    assert [e.blockcounter() for e in ranks] == [nb, nb]
+
+
 def test_unconnected_peer_is_refused(pkg):
     e = pkg.Brutefir(256, 4, 4, 4, pkg.FLOAT_LE, pkg.FLOAT_LE, 48000, False, part_begin=0, part_count=2)
     e.set_coeff([decay_filter(c, 1024) for c in range(4)], 4)

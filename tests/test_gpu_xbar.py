@@ -256,3 +256,23 @@ def test_crossbar_block_pairs_equal_single_blocks(pkg, rs, L, P, n_in, n_f, n_ou
     assert quad.sync() == 0 and quad.blockcounter() == nq
     for b in range(nq):
         assert rel_rms(out_q[b].cpu().numpy(), out_s[b].cpu().numpy()) < tol, b
+    # the same through the stage pipeline (crossbar kernels on the side streams, block index from the host): staged
+    # quads, a staged pair in between, a join
+    stg = pkg.Brutefir(L, P, rs, n_f, fmt, fmt, 48000, False, n_streams=S, xbar_inputs=n_in, xbar_outputs=n_out, n_groups=1)
+    assert stg.set_coeff(h, P) == 0
+    stg.set_crossbar(gin, gout)
+    out_t = [torch.zeros(n_o, dtype=tdt, device="cuda") for _ in range(nblk)]
+    torch.cuda.synchronize()
+    b = 0
+    while b < nblk:
+        if b + 4 <= nblk and b != 8:
+            stg.run_device_quad(d_in[b:b + 4], out_t[b:b + 4], staged=True)
+            b += 4
+        else:
+            stg.run_device_pair(d_in[b], d_in[b + 1], out_t[b], out_t[b + 1], pipelined="staged")
+            b += 2
+        if b == 12:
+            stg.join()
+    assert stg.sync() == 0 and stg.blockcounter() == nblk
+    for b in range(nblk):
+        assert rel_rms(out_t[b].cpu().numpy(), out_s[b].cpu().numpy()) < tol, b
