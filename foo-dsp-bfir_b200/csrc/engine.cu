@@ -245,8 +245,15 @@ int Engine::init(const bfir_config_t &c)
     if (const char *env = getenv("BFIR_WHOLE_COPIES")) whole_copies = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
-    BFIR_CUDA(cudaStreamCreateWithFlags(&sp_fwd, cudaStreamNonBlocking));
-    BFIR_CUDA(cudaStreamCreateWithFlags(&sp_inv, cudaStreamNonBlocking));
+    {   // the stage pipeline's side streams; BFIR_STAGE_PRIO=1: at the highest priority, so that the block scheduler places
+        // the (whole-SM) transform CTAs of the neighbouring calls before further CTAs of the running partition sum
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        const char *env = getenv("BFIR_STAGE_PRIO");
+        const int prio = (env && atoi(env) != 0) ? prio_hi : 0;
+        BFIR_CUDA(cudaStreamCreateWithPriority(&sp_fwd, cudaStreamNonBlocking, prio));
+        BFIR_CUDA(cudaStreamCreateWithPriority(&sp_inv, cudaStreamNonBlocking, prio));
+    }
     for (int k = 0; k < 2; k++)
         for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k], &sp_arrived[k] }) BFIR_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     BFIR_CUDA(cudaStreamCreateWithFlags(&tail_stream, cudaStreamNonBlocking));

@@ -107,6 +107,37 @@ static bool tma_enabled()
     return on;
 }
 
+// De-interleaving through a thread-block cluster (rfft_kernels.cuh): Cc = the largest power of two <= 8 that divides the
+// channels per stream, provided a 16-byte chunk of the (frame, channel)-ordered tile never straddles a frame (16 / bytes
+// samples <= Cc) or the tile is the whole frame (Cc == C); launches whose channel range is not a whole number of
+// clusters, sample sizes 1 and 3 and unaligned buffers keep the strided path. BFIR_FFT_CLUSTER=0 switches it off.
+static int cluster_channels(int log2m, int r0, int fmt, int ch_per_stream, unsigned int grid_x, int ch_first, const void *raw, long long raw_stride_bytes)
+{
+    static const bool on = [] { const char *env = getenv("BFIR_FFT_CLUSTER"); return env ? atoi(env) != 0 : true; }();
+    if (!on || r0 != 1 || log2m < 8 || raw == nullptr) return 0;
+    const int bytes = fmt_bytes(fmt);
+    if (bytes != 2 && bytes != 4 && bytes != 8) return 0;
+    const int C = ch_per_stream, S = 16 / bytes;
+    if (C < 2) return 0;
+    // clusters of at most FOUR: 8-CTA clusters of one-CTA-per-SM kernels do not pack (measured: the 16 clusters of
+    // cfg1 x 16 took two waves, 23 -> 35 us), 4-CTA clusters leave at most 16 of 148 SMs unused
+    int cc = 4;
+    while (cc > 1 && C % cc != 0) cc >>= 1;
+    if (cc < 2) return 0;
+    if (!(S <= cc || cc == C)) return 0;
+    // worth it only where the strided path wastes at least three quarters of every sector it touches and the
+    // cluster path gets four times more out of them (measured: stereo float, 50 % -> 100 %, is slower)
+    {
+        const int frame = C * bytes, run = cc * bytes;
+        const double strided = (double)bytes / (frame < 32 ? frame : 32), tiled = (double)(run < 32 ? run : 32) / (frame < 32 ? frame : 32);
+        if (tiled < 4.0 * strided) return 0;
+    }
+    if (cc != C && ((long long)C * bytes) % 16 != 0) return 0;      // frames of a partial tile must start on 16 bytes
+    if (grid_x % (unsigned)cc != 0 || ch_first % cc != 0) return 0;
+    if (((uintptr_t)raw & 15) != 0 || (raw_stride_bytes & 15) != 0) return 0;
+    return cc;
+}
+
 cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cudaStream_t stream, const FwdArgs &a0, const void *tw)
 {
     if (!rfft_supported(realsize, log2m) || (r0 != 1 && r0 != 2 && r0 != 4)) return cudaErrorInvalidValue;
@@ -115,6 +146,9 @@ cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cuda
     FwdArgs a = a0;
     a.tma = (tma_enabled() && r0 == 1 && a.in_mode == IN_RAW_PREV && a.prev != nullptr && ((uintptr_t)a.prev & 15) == 0
              && (((size_t)realsize << log2m) & 15) == 0) ? 1 : 0;
+    a.cluster = 0;
+    if (a.in_mode == IN_RAW_PREV && a.prev != nullptr && grid.y == 1)
+        a.cluster = cluster_channels(log2m, r0, a.fmt, a.ch_per_stream, grid.x, a.ch_base % a.ch_per_stream, a.in, a.in_stride_x);
     // table length N = 2 * 2^log2m: shift for the sub-transform twiddles, 0 for the W_N^k of the split step
     if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, true)) return (realsize == 4 ? kFwdF32E8 : kFwdF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
     return (realsize == 4 ? kFwdF32 : kFwdF64)[sub - kMinLog2M](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
@@ -128,6 +162,9 @@ cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cuda
     InvArgs a = a0;
     a.tma = (tma_enabled() && r0 == 1 && a.head_x == nullptr && ((uintptr_t)a.in & 15) == 0
              && (((size_t)a.in_stride_x * realsize) & 15) == 0) ? 1 : 0;
+    a.cluster = 0;
+    if (a.out_mode == OUT_RAW && grid.y == 1)
+        a.cluster = cluster_channels(log2m, r0, a.fmt, a.ch_per_stream, grid.x, (a.ch_base - a.raw_ch_base) % a.ch_per_stream, a.out, a.out_stride_x);
     if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return (realsize == 4 ? kInvF32E8 : kInvF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
     return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
 }

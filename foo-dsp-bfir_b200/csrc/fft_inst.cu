@@ -18,6 +18,20 @@ static constexpr int kLog2E = BFIR_FFT_LOG2E;
 static constexpr int kLog2M = BFIR_FFT_LOG2M;
 static constexpr int kM = 1 << kLog2M;
 static constexpr size_t kSmem = (size_t)fft_smem_elems<kM>::value * sizeof(cpx<real_t>);
+// the cluster variants of the one-CTA kernels exist from 256 points per CTA (fft_dispatch.cu: cluster_channels)
+static constexpr bool kHasCluster = kLog2M >= 8;
+
+// the CTAs of `cx` neighbouring channels as one thread-block cluster along x (de-interleaving through the cluster)
+template <class K, class A>
+static cudaError_t launch_clustered(K kernel, dim3 grid, int cx, cudaStream_t stream, const A &a, const void *tw, int sm, int sn)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kM >> kLog2E); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cx; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, a, (const cpx<real_t> *)tw, sm, sn);
+}
 
 template <int R0>
 static cudaError_t launch_fwd(dim3 grid, cudaStream_t stream, const FwdArgs &a, const void *tw, int sm, int sn)
@@ -38,6 +52,18 @@ static cudaError_t launch_fwd(dim3 grid, cudaStream_t stream, const FwdArgs &a, 
         cfg.attrs = at; cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, kernel, a, (const cpx<real_t> *)tw, sm, sn);
     }
+    if constexpr (R0 == 1 && kHasCluster) {
+        if (a.cluster > 1) {
+            static bool configured_cl = false;
+            auto kcl = rfft_forward_kernel<real_t, kLog2M, 1, kLog2E, true>;
+            if (!configured_cl) {
+                cudaError_t e = cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+                if (e != cudaSuccess) return e;
+                configured_cl = true;
+            }
+            return launch_clustered(kcl, grid, a.cluster, stream, a, tw, sm, sn);
+        }
+    }
     kernel<<<grid, kM >> kLog2E, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
     return cudaGetLastError();
 }
@@ -53,6 +79,18 @@ static cudaError_t launch_inv(dim3 grid, cudaStream_t stream, const InvArgs &a, 
         configured = true;
     }
     grid.z = R0;
+    if constexpr (R0 == 1 && kHasCluster) {
+        if (a.cluster > 1) {
+            static bool configured_cl = false;
+            auto kcl = rfft_inverse_kernel<real_t, kLog2M, 1, kLog2E, true>;
+            if (!configured_cl) {
+                cudaError_t e = cudaFuncSetAttribute(kcl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+                if (e != cudaSuccess) return e;
+                configured_cl = true;
+            }
+            return launch_clustered(kcl, grid, a.cluster, stream, a, tw, sm, sn);
+        }
+    }
     kernel<<<grid, kM >> kLog2E, kSmem, stream>>>(a, (const cpx<real_t> *)tw, sm, sn);
     return cudaGetLastError();
 }

@@ -86,6 +86,8 @@ struct FwdArgs {
     int coeff_len;           // valid coefficients per channel
     int *nonfinite;          // set to 1 when a scaled coefficient is NaN/Inf (fftw_convolver.cpp:493-497)
     int tma;                 // 1: IN_RAW_PREV, one CTA per transform: the previous block arrives by bulk copy (set by launch_rfft_forward)
+    int cluster;             // > 1: IN_RAW_PREV, the CTAs of `cluster` neighbouring channels of a stream form a thread-block cluster
+                             // and de-interleave the raw block together (set by launch_rfft_forward; see fwd_load_cluster)
 };
 
 // index of the block a forward launch transforms
@@ -116,6 +118,8 @@ struct InvArgs {
     const int *head_blocks;  // [channels] coefficient partitions loaded (0: the channel has no filter)
     const int *head_map;     // [channels] coefficient set of each channel, NULL = its own (bfir_set_coeff_map)
     int tma;                 // 1: one CTA per transform, no head term: the input spectrum arrives by bulk copy (set by launch_rfft_inverse)
+    int cluster;             // > 1: OUT_RAW, the CTAs of `cluster` neighbouring channels of a stream form a thread-block cluster and
+                             // interleave their output together (set by launch_rfft_inverse; see inv_store_cluster)
 };
 
 template <class T> BFIR_HD T tw_re(const cpx<T> &w) { return w.x; }
@@ -382,6 +386,19 @@ BFIR_HD void fwd_load_raw_prev(int t, int r, cpx<T> (&v)[1 << LOG2E], const cpx<
     }
 }
 
+// engine bookkeeping of a forward launch: the slot of the block in flight, procblocks (brutefir.cpp:265-268)
+template <class Dummy> BFIR_HD void fwd_bookkeeping(int t, int bx, int by, int r, const FwdArgs &a)
+{
+    if (a.in_mode == IN_RAW_PREV && a.state != NULL && t == 0 && r == 0 && by == 0 && bx == a.ch_base)
+        const_cast<EngineState *>(a.state)->cur_slot = fwd_block<int>(a) % (unsigned int)a.n_slots;
+    if (a.in_mode == IN_RAW_PREV && t == 0 && r == 0 && a.procblocks != NULL) {
+        const int pb = a.procblocks[bx];
+        const bool inc = pb < a.n_parts;
+        if (inc) a.procblocks[bx] = pb + 1;
+        a.pb_inc[bx] = inc ? 1 : 0;
+    }
+}
+
 // forward, phase 0: thread t builds s_r[n], n = t + i*NTs
 template <class T, int LOG2MS, int R0, int LOG2E = 4, bool STAGED = false>
 BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const FwdArgs &a,
@@ -423,14 +440,7 @@ BFIR_HD void fwd_load(int t, int bx, int by, int r, cpx<T> (&v)[1 << LOG2E], con
         }
     }
     if (a.in_mode == IN_COEFF && bad) *a.nonfinite = 1;
-    if (a.in_mode == IN_RAW_PREV && a.state != NULL && t == 0 && r == 0 && by == 0 && bx == a.ch_base)
-        const_cast<EngineState *>(a.state)->cur_slot = fwd_block<int>(a) % (unsigned int)a.n_slots;
-    if (a.in_mode == IN_RAW_PREV && t == 0 && r == 0 && a.procblocks != NULL) { // brutefir.cpp:265-268
-        const int pb = a.procblocks[bx];
-        const bool inc = pb < a.n_parts;
-        if (inc) a.procblocks[bx] = pb + 1;
-        a.pb_inc[bx] = inc ? 1 : 0;
-    }
+    fwd_bookkeeping<int>(t, bx, by, r, a);
 }
 
 // forward, phase 2: sub-transform result (natural order, padded smem) -> X_k, k = R0 k' + r, scaled,
@@ -648,6 +658,168 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[1 << LOG2E], cons
 }
 
 #ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// De-interleaving through a thread-block cluster and distributed shared memory. One CTA owns one channel, but the
+// raw blocks are interleaved [frame][channel]: a CTA that reads (writes) its own samples touches `bytes` of every
+// C * bytes frame -- for 7.1 double 8 of every 64 bytes, 32 sectors per warp instruction at 25 % efficiency, and the
+// load / store unit spends 28 % (forward) / 39 % (inverse) of the kernel on them
+// (profiles/r02n_fft_f64_13_stall_profile.txt). Here the CTAs of Cc <= 4 neighbouring channels of one stream form a
+// cluster (launch attribute), and every CTA moves 1/Cc of the FRAMES of all Cc channels with 16-byte global accesses
+// that tile memory exactly:
+//   forward: CTA r loads frames [r F, (r+1) F), F = L/Cc, of the Cc channels, decodes them and scatters them into the
+//            channels' PLANAR previous-block rows; cluster barrier; every CTA reads its own row back (fwd_load_cluster).
+//   inverse: every CTA stores its encoded samples planar into its FFT buffer (free after the last pass); cluster
+//            barrier; CTA r gathers frames [r F, (r+1) F) of the Cc channels through distributed shared memory into
+//            16-byte chunks and writes them to the interleaved block; cluster barrier before anybody exits.
+// Both exchanges were measured both ways (cfg1 x 16, per launch): forward through L2 20.1 us / through DSMEM 23.2 /
+// strided 22.7; inverse through L2 23.5 / through DSMEM 21.8 / strided 23.8 -- each side keeps its faster variant.
+// A 16-byte chunk holds S = 16 / bytes consecutive samples of the (frame, channel)-ordered tile; launch_rfft_* only
+// enables the path when a chunk never straddles a frame (S <= Cc) or the tile is the whole frame (Cc == C).
+template <int B> struct raw_word;
+template <> struct raw_word<2> { typedef unsigned short type; };
+template <> struct raw_word<4> { typedef unsigned int type; };
+template <> struct raw_word<8> { typedef unsigned long long type; };
+
+__device__ __forceinline__ int cluster_log2(int c) { return c >= 4 ? 2 : 1; }
+#define BFIR_MAX_CLUSTER 4
+
+// the same shared-memory address in every CTA of the cluster
+template <class P> __device__ __forceinline__ void cluster_peers(P *own, int Cc, P *(&peer)[BFIR_MAX_CLUSTER])
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+#pragma unroll
+    for (int k = 0; k < BFIR_MAX_CLUSTER; k++) peer[k] = k < Cc ? cl.map_shared_rank(own, k) : own;
+}
+template <class P> __device__ __forceinline__ P *cluster_pick(P *const (&peer)[BFIR_MAX_CLUSTER], int k)
+{
+    P *p = peer[0];
+    if (k == 1) p = peer[1];
+    if (k == 2) p = peer[2];
+    if (k == 3) p = peer[3];
+    return p;
+}
+
+// inverse side, after the planar rows are complete: gather one slab of frames through DSMEM and write it interleaved
+template <int B>
+__device__ __forceinline__ void cluster_gather_store(int t, int nt, const uint8_t *const (&rows)[BFIR_MAX_CLUSTER], uint8_t *out_stream,
+                                                     int C, int Cc, int cg0, int f0, int nchunks)
+{
+    constexpr int S = 16 / B;
+    typedef typename raw_word<B>::type W;
+    const int lc = cluster_log2(Cc);
+    for (int q = t; q < nchunks; q += nt) {
+        const int s = q * S;
+        union { uint4 u; W w[S]; } pack;
+#pragma unroll
+        for (int j = 0; j < S; j++) {
+            const int idx = s + j, fl = idx >> lc, c = idx & (Cc - 1);
+            pack.w[j] = ((const W *)cluster_pick(rows, c))[f0 + fl];
+        }
+        uint8_t *dst = out_stream + ((long long)(f0 + (s >> lc)) * C + cg0 + (s & (Cc - 1))) * B;
+        *(uint4 *)dst = pack.u;
+    }
+}
+
+// forward side: one slab of frames -> decoded samples scattered into the channels' planar rows (global memory)
+template <class T, int FMT>
+__device__ __forceinline__ void cluster_scatter_load(int t, int nt, const uint8_t *in_stream, T *rows, long long row_stride,
+                                                     int C, int Cc, int cg0, int f0, int nchunks)
+{
+    constexpr int B = FMT == FMT_S8 ? 1 : (FMT <= FMT_S16_BE ? 2 : (FMT <= FMT_S24_BE ? 3 : (FMT <= FMT_FLOAT_BE ? 4 : 8)));
+    if constexpr (B == 2 || B == 4 || B == 8) {
+        constexpr int S = 16 / B;
+        const int lc = cluster_log2(Cc);
+        for (int q = t; q < nchunks; q += nt) {
+            const int s = q * S;
+            union { uint4 u; uint8_t b[16]; } pack;
+            pack.u = __ldg((const uint4 *)(in_stream + ((long long)(f0 + (s >> lc)) * C + cg0 + (s & (Cc - 1))) * B));
+#pragma unroll
+            for (int j = 0; j < S; j++) {
+                const int idx = s + j, fl = idx >> lc, c = idx & (Cc - 1);
+                rows[(long long)c * row_stride + (f0 + fl)] = load_raw<T>(pack.b + j * B, FMT);
+            }
+        }
+    }
+}
+
+// forward load phase in cluster mode (R0 = 1, IN_RAW_PREV). The exchange goes through the channels' planar
+// previous-block rows, i.e. L2 (measured against the DSMEM variant of the same phase: 20.1 against 23.2 us for
+// cfg1 x 16; DSMEM delivers ~20 B/clk per SM, B300_MICROARCH.md): CTA r scatters its slab of frames into the Cc
+// rows -- which the kernel has to write anyway for the next block --, cluster barrier (release / acquire at cluster
+// scope), every CTA reads its own row back with L2 loads. `staged_prev` != NULL: the previous block is arriving in
+// shared memory by bulk copy (barrier `bar`), else it is read from its planar row.
+template <class T, int LOG2MS, int LOG2E>
+__device__ __forceinline__ void fwd_load_cluster(int t, int bx, int by, cpx<T> (&v)[1 << LOG2E], const FwdArgs &a,
+                                                 const cpx<T> *staged_prev, uint64_t *bar)
+{
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, NH = E / 2, L = MS;
+    typedef cpx<T> C2;
+    namespace cg = cooperative_groups;
+    const int Cc = a.cluster, C = a.ch_per_stream;
+    const int stream = bx / C, ch = bx - stream * C;
+    const int r = ch & (Cc - 1), cg0 = ch - r;           // r = rank in the cluster (launch_rfft_forward aligns the grid)
+    const int bytes = fmt_bytes(a.fmt);
+    const unsigned int par = a.prev_parity & 1u;
+    T *rows = (T *)a.prev + ((long long)(par ^ 1u) * a.n_channels + (bx - r)) * L;      // planar rows of the cluster's channels (written)
+    const uint8_t *in_stream = (const uint8_t *)a.in + (long long)stream * a.in_stride_x;
+    const int F = L >> cluster_log2(Cc);
+    BFIR_FMT_SWITCH(a.fmt, (cluster_scatter_load<T, FMT>(t, NT, in_stream, rows, (long long)L, C, Cc, cg0, r * F, (L * bytes) >> 4)))
+    cg::this_cluster().sync();                          // every channel's current block is in its planar row
+    const C2 *cur = (const C2 *)(rows + (long long)r * L);
+    C2 hi[NH];
+#pragma unroll
+    for (int j = 0; j < NH; j++) {
+        if constexpr (sizeof(T) == 8) { const double2 d = __ldcg((const double2 *)cur + (t + j * NT)); hi[j].x = d.x; hi[j].y = d.y; }
+        else { const float2 f = __ldcg((const float2 *)cur + (t + j * NT)); hi[j].x = f.x; hi[j].y = f.y; }
+    }
+    if (staged_prev != NULL) {
+        mbar_wait(bar, 0);
+#pragma unroll
+        for (int j = 0; j < NH; j++) v[j] = staged_prev[t + j * NT];
+    } else {
+        const C2 *prev_rd = (const C2 *)((const T *)a.prev + ((long long)par * a.n_channels + bx) * L);
+#pragma unroll
+        for (int j = 0; j < NH; j++) v[j] = prev_rd[t + j * NT];
+    }
+#pragma unroll
+    for (int j = 0; j < NH; j++) v[j + NH] = hi[j];
+    fwd_bookkeeping<int>(t, bx, by, 0, a);
+}
+
+// inverse store phase in cluster mode (R0 = 1, OUT_RAW); smem_raw: the CTA's FFT buffer, free after the last pass
+template <class T, int LOG2MS, int LOG2E>
+__device__ __forceinline__ void inv_store_cluster(int t, int bx, const cpx<T> (&v)[1 << LOG2E], const InvArgs &a, OverflowAcc &acc,
+                                                  unsigned char *smem_raw)
+{
+    constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, L = MS;
+    namespace cg = cooperative_groups;
+    if (t == 0 && a.state != NULL) {                    // brutefir.cpp:316-321
+        const T y0 = v[0].x;
+        if (!(y0 - y0 == (T)0)) {
+            atomicMin(&a.state->first_bad_channel, bx);
+            if (a.host_flag != NULL) *(volatile int *)a.host_flag = 1;
+        }
+    }
+    const int bytes = fmt_bytes(a.fmt);
+    __syncthreads();                                    // every thread is past its last read of the FFT buffer
+    BFIR_FMT_SWITCH(a.fmt, (inv_store_raw<T, LOG2MS, 1, LOG2E, FMT>(t, 0, v, (uint8_t *)smem_raw, (long long)bytes, (T)a.ovf_max, acc)))
+    cg::this_cluster().sync();                          // the planar rows of all Cc channels are complete
+    const int Cc = a.cluster, C = a.ch_per_stream;
+    const int rb = bx - a.raw_ch_base;
+    const int stream = rb / C, ch = rb - stream * C;
+    const int r = ch & (Cc - 1), cg0 = ch - r;
+    const int F = L >> cluster_log2(Cc);
+    uint8_t *out_stream = (uint8_t *)a.out + (long long)stream * a.out_stride_x;
+    const uint8_t *rows[BFIR_MAX_CLUSTER];
+    cluster_peers<const uint8_t>((const uint8_t *)smem_raw, Cc, rows);
+    const int nchunks = (L * bytes) >> 4;
+    if (bytes == 8) cluster_gather_store<8>(t, NT, rows, out_stream, C, Cc, cg0, r * F, nchunks);
+    else if (bytes == 4) cluster_gather_store<4>(t, NT, rows, out_stream, C, Cc, cg0, r * F, nchunks);
+    else cluster_gather_store<2>(t, NT, rows, out_stream, C, Cc, cg0, r * F, nchunks);
+    cg::this_cluster().sync();                          // nobody leaves while a peer still reads its rows
+}
+
 // merge per-thread statistics into the channel's counters: max / sum are order independent, so the
 // result equals the reference's serial update (real2raw.cpp:17-32, dither.cpp:226-271)
 __device__ __forceinline__ void overflow_commit(OverflowStats *dst, OverflowAcc acc)
@@ -673,7 +845,9 @@ __device__ __forceinline__ void overflow_commit(OverflowStats *dst, OverflowAcc 
 #define BFIR_E8_MINB(log2e, log2ms) (((log2e) == 3 && (log2ms) == 12) ? 2 : 0)
 #endif
 // grid = (buffers, partitions, R0); tw_shift_m = log2(table length / Ms), tw_shift_n = log2(table length / N)
-template <class T, int LOG2MS, int R0, int LOG2E = 4>
+// CL: the cluster variant (de-interleaving through a thread-block cluster, R0 = 1 only) is its own instantiation, so that
+// the plain kernels keep their register allocation
+template <class T, int LOG2MS, int R0, int LOG2E = 4, bool CL = false>
 __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LOG2MS)) rfft_forward_kernel(const FwdArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -682,6 +856,7 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
     cpx<T> v[1 << LOG2E];
     bool staged = false;
     if constexpr (R0 == 1) staged = a.tma != 0;
+    constexpr bool clustered = CL && R0 == 1;
     if constexpr (R0 == 1) if (staged) {
         // previous block: L reals, contiguous in the planar ping-pong buffer -> head of the (still idle) FFT buffer
         __shared__ __align__(8) uint64_t bar;
@@ -689,10 +864,12 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
         if (t == 0) mbar_init(&bar, 1);
         __syncthreads();
         if (t == 0) bulk_stage(smem_raw, (const T *)a.prev + ((long long)(a.prev_parity & 1u) * a.n_channels + bx) * L, (uint32_t)(L * sizeof(T)), &bar);
-        fwd_load<T, LOG2MS, R0, LOG2E, true>(t, bx, by, r, v, tw, tw_shift_n, a, smem, &bar);
+        if constexpr (clustered) fwd_load_cluster<T, LOG2MS, LOG2E>(t, bx, by, v, a, smem, &bar);
+        else fwd_load<T, LOG2MS, R0, LOG2E, true>(t, bx, by, r, v, tw, tw_shift_n, a, smem, &bar);
         __syncthreads();                               // every thread has read its part of the staged block
     }
-    if (!staged) fwd_load<T, LOG2MS, R0, LOG2E>(t, bx, by, r, v, tw, tw_shift_n, a);
+    if constexpr (clustered) { if (!staged) fwd_load_cluster<T, LOG2MS, LOG2E>(t, bx, by, v, a, NULL, NULL); }
+    else { if (!staged) fwd_load<T, LOG2MS, R0, LOG2E>(t, bx, by, r, v, tw, tw_shift_n, a); }
     fft_passes<T, LOG2MS, false, 0, 0, LOG2E>::run(t, v, smem, tw, tw_shift_m);
     BlockFFT<T, LOG2MS, false, LOG2E>::store_natural(t, v, smem);
     __syncthreads();
@@ -709,7 +886,7 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
     }
 }
 
-template <class T, int LOG2MS, int R0, int LOG2E = 4>
+template <class T, int LOG2MS, int R0, int LOG2E = 4, bool CL = false>
 __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LOG2MS)) rfft_inverse_kernel(const InvArgs a, const cpx<T> *__restrict__ tw, int tw_shift_m, int tw_shift_n)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -733,7 +910,8 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
     fft_passes<T, LOG2MS, true, 0, 0, LOG2E>::run(t, v, smem, tw, tw_shift_m);
     OverflowAcc acc;
     acc.n_overflows = 0; acc.intlargest = 0; acc.largest = 0.0;
-    inv_store<T, LOG2MS, R0, LOG2E>(t, bx, r, v, a, acc);
+    if constexpr (CL && R0 == 1) inv_store_cluster<T, LOG2MS, LOG2E>(t, bx, v, a, acc, smem_raw);
+    else inv_store<T, LOG2MS, R0, LOG2E>(t, bx, r, v, a, acc);
     if (a.out_mode == OUT_RAW && a.stats != NULL) overflow_commit(&a.stats[bx], acc);
     if (a.state != NULL && blockIdx.x == 0 && t == 0 && r == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
 }
