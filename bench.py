@@ -369,6 +369,7 @@ def main():
     # groups with their own copy streams), median of 3 passes of K steps (the pass is half host work, and the hosts
     # of this pool are noisy). Beside it: one block per call (bfir_run_async) and the reference's synchronous run().
     DEPTH = 3
+    QDEPTH = 2
 
     def e2e_pass(engine, ins, outs, steps, sync_groups, async_groups):
         engine.set_groups(min(sync_groups, S))
@@ -411,21 +412,65 @@ def main():
         async_pass(True)                                             # warm-up (allocates the staging ring)
         t_pairs = sorted(async_pass(True) for _ in range(3))
         t_single = async_pass(False)
-        return max_over_ranks(t_sync), t_pairs, t_single, groups
+
+        # four blocks per call through the stage pipeline (bfir_run_async_quad): ONE stream group -- whole-block copies
+        # on one copy stream each way, five streams in all --, QDEPTH calls in flight
+        def quad_pass():
+            barrier()
+            tickets = []
+            t0 = time.perf_counter()
+            for k in range(steps // 4):
+                b = 4 * k
+                tickets.append(engine.run_async_quad([ins[(b + j) % ni] for j in range(4)], [outs[(b + j) % no] for j in range(4)]))
+                if k >= QDEPTH:
+                    assert engine.wait(tickets[k - QDEPTH]) == 0
+            for b in range(steps - steps % 4, steps):
+                tickets.append(engine.run_async(ins[b % ni], outs[b % no]))
+            assert engine.wait(tickets[-1]) == 0
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            return max_over_ranks(dt)
+        engine.set_groups(1)
+        quad_pass()
+        t_quads = sorted(quad_pass() for _ in range(3))
+        return max_over_ranks(t_sync), t_pairs, t_single, groups, t_quads
 
     e2e_steps = max(K, 200) - max(K, 200) % 2   # fill and drain of the copy pipeline are a fixed cost: time at least 200 steps
-    n_host = 2 * (DEPTH + 1)
+    n_host = max(2 * (DEPTH + 1), 4 * (QDEPTH + 1))
     host_ins = host_in + [torch.from_numpy(noise_block(1000 * rank + 50 + b, S, L, C)).contiguous().pin_memory() for b in range(n_host - ring)]
     host_outs = [host_out] + [torch.empty(S * L * C, dtype=torch.float64).pin_memory() for _ in range(n_host - 1)]
     np_in, np_outs = [h.numpy() for h in host_ins], [h.numpy() for h in host_outs]
     sampler.busy.set()
-    t_sync, t_pairs, t_single, e2e_groups = e2e_pass(eng, np_in, np_outs, e2e_steps, 4, 4)
+    t_sync, t_pairs, t_single, e2e_groups, t_quads = e2e_pass(eng, np_in, np_outs, e2e_steps, 4, 4)
     sampler.busy.clear()
-    t_e2e = t_pairs[1]
+    e2e_quads = t_quads[1] <= t_pairs[1]     # the headline is the faster of the two pipelined host paths (medians of 3 passes)
+    t_e2e = t_quads[1] if e2e_quads else t_pairs[1]
     e2e_value = n_gpus * Ct * L * e2e_steps / t_e2e / 1e6
     e2e_sync_value = n_gpus * Ct * L * e2e_steps / t_sync / 1e6
     e2e_single_value = n_gpus * Ct * L * e2e_steps / t_single / 1e6
     checksum = float(host_out.numpy()[:1024].sum())
+
+    # the link alone, same buffers, same process: every step's 8 MiB in and 8 MiB out as plain copies on two streams with
+    # no kernel between them -- the floor of any end-to-end step on this box (PCIe duplex rate with this buffer ring)
+    def link_only(steps):
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        d_i = [torch.empty_like(dev_in[0]) for _ in range(2)]
+        d_o = [torch.empty_like(dev_out) for _ in range(2)]
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for b in range(steps):
+            with torch.cuda.stream(s_in):
+                d_i[b & 1].copy_(host_ins[b % n_host], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                host_outs[b % n_host].copy_(d_o[b & 1], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(dt)
+    link_only(20)
+    t_link = sorted(link_only(e2e_steps) for _ in range(3))[1]
 
     # ---- the same end-to-end step with the product's I/O format: foo_dsp_bfir constructs the engine with REALSIZE 8
     # and FLOAT_LE in/out (foo_dsp_bfir.cpp:279-286), which halves the PCIe bytes of the FLOAT64_LE headline run
@@ -439,8 +484,10 @@ def main():
         no32 = [torch.empty(S * L * C, dtype=torch.float32).pin_memory().numpy() for _ in range(n_host)]
         for b in range(P):
             e32.run(n32[b % ring], no32[0])
-        ts32, tp32, t1_32, _ = e2e_pass(e32, n32, no32, e2e_steps, 4, 4)
-        e2e_f32 = {"value": Ct * L * e2e_steps / tp32[1] / 1e6, "unit": "Msamples/s (this rank only)", "ms_per_step": 1e3 * tp32[1] / e2e_steps,
+        ts32, tp32, t1_32, _, tq32 = e2e_pass(e32, n32, no32, e2e_steps, 4, 4)
+        tb32 = min(tp32[1], tq32[1])
+        e2e_f32 = {"value": Ct * L * e2e_steps / tb32 / 1e6, "unit": "Msamples/s (this rank only)", "ms_per_step": 1e3 * tb32 / e2e_steps,
+                   "two_blocks_per_call_ms_per_step": 1e3 * tp32[1] / e2e_steps, "four_blocks_per_call_ms_per_step": 1e3 * tq32[1] / e2e_steps,
                    "one_block_per_call": {"value": Ct * L * e2e_steps / t1_32 / 1e6, "ms_per_step": 1e3 * t1_32 / e2e_steps},
                    "sync_run": {"value": Ct * L * e2e_steps / ts32 / 1e6, "ms_per_step": 1e3 * ts32 / e2e_steps},
                    "h2d_bytes_per_step": S * L * C * 4, "d2h_bytes_per_step": S * L * C * 4,
@@ -581,13 +628,22 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": workload_config(S, n_gpus),
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * L * C * 8,
                     "d2h_bytes_per_step": S * L * C * 8, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "bfir_run_async_pair(pinned host in x2, pinned host out x2) + bfir_wait: H2D + kernels + D2H of every block, "
-                           "%d calls in flight, %d stream groups with their own copy streams; median of 3 passes" % (DEPTH, e2e_groups),
-                    "passes_ms_per_step": [1e3 * t / e2e_steps for t in t_pairs],
+                    "api": ("bfir_run_async_quad(4 pinned host in, 4 pinned host out) + bfir_wait: H2D + kernels + D2H of every block through the stage "
+                            "pipeline (one stream group, five streams), %d calls in flight; median of 3 passes" % (QDEPTH + 1)) if e2e_quads else
+                           ("bfir_run_async_pair(pinned host in x2, pinned host out x2) + bfir_wait: H2D + kernels + D2H of every block, "
+                            "%d calls in flight, %d stream groups with their own copy streams; median of 3 passes" % (DEPTH, e2e_groups)),
+                    "passes_ms_per_step": [1e3 * t / e2e_steps for t in (t_quads if e2e_quads else t_pairs)],
+                    "four_blocks_per_call": {"value": n_gpus * Ct * L * e2e_steps / t_quads[1] / 1e6, "passes_ms_per_step": [1e3 * t / e2e_steps for t in t_quads],
+                                             "api": "bfir_run_async_quad + bfir_wait, one stream group"},
+                    "two_blocks_per_call": {"value": n_gpus * Ct * L * e2e_steps / t_pairs[1] / 1e6, "passes_ms_per_step": [1e3 * t / e2e_steps for t in t_pairs],
+                                            "api": "bfir_run_async_pair + bfir_wait, %d stream groups" % e2e_groups},
                     "one_block_per_call": {"value": e2e_single_value, "ms_per_step": 1e3 * t_single / e2e_steps, "api": "bfir_run_async + bfir_wait"},
                     "sync_run": {"value": e2e_sync_value, "ms_per_step": 1e3 * t_sync / e2e_steps,
                                  "api": "bfir_run(host in, host out): the reference's synchronous run(), 4 stream groups"},
-                    "checksum": checksum},
+                    "checksum": checksum,
+                    "link_only": {"ms_per_step": 1e3 * t_link / e2e_steps, "frac_of_link": t_link / t_e2e,
+                                  "note": "the same host buffers moved H2D and D2H concurrently on two streams with no kernels (median of 3 passes): "
+                                          "the floor of an end-to-end step on this box; frac_of_link = link-only time / e2e time"}},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
             "e2e_product_io": e2e_f32, "value_pipelined": value_grouped,
             "output_check": out_check, "configs": configs, "partition_sharded": sharded,

@@ -79,6 +79,7 @@ API = [
     ("bfir_run_partial_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
     ("bfir_run_finish_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
     ("bfir_run_shard_quad_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    ("bfir_run_async_quad", ctypes.c_longlong, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -366,6 +367,15 @@ class Brutefir:
         a = (_vp * 4)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
         b = (_vp * 4)(*[_ptr(x) for x in d_outs])
         _check(self.lib.bfir_run_shard_quad_staged(self.h, a, b))
+
+    def run_async_quad(self, ins, outs):
+        """Four consecutive blocks of PINNED host buffers through the stage pipeline; returns the ticket of the fourth."""
+        a = (_vp * 4)(*[_buf(x, self.in_bytes, "in") for x in ins])
+        b = (_vp * 4)(*[_buf(x, self.out_bytes, "out") for x in outs])
+        t = self.lib.bfir_run_async_quad(self.h, a, b)
+        if t < 0:
+            raise BfirError(int(t), last_error())
+        return t
 
     def run_async_pair(self, in0, in1, out0, out1):
         """Two consecutive blocks of PINNED host buffers; returns the ticket of the second block."""

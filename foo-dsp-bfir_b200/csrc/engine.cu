@@ -57,7 +57,7 @@ struct Engine {
         // bfir_run_async: the group's copies ride on their own streams so that they overlap its kernels too
         cudaStream_t h2d, d2h;
         cudaEvent_t in_ready, out_ready, copies_done;
-        cudaEvent_t in_free[8], out_free[8];   // per staging slot (kStage)
+        cudaEvent_t in_free[12], out_free[12]; // per staging slot (kStage)
     };
     Group groups[BFIR_MAX_GROUPS] = {};
     int n_groups = 1;
@@ -116,10 +116,10 @@ struct Engine {
     // run up to kStage - 1 blocks ahead of the transforms and the output copies behind them. A slot is busy from the
     // start of its H2D to the end of its D2H (three pipeline stages), so fewer than three blocks (pairs) worth of
     // slots leaves one of the stages idle: 8 slots = 4 pairs
-    static const int kStage = 8;
+    static const int kStage = 12;   // three four-block calls (or six pairs) in flight
     void *stage_in[kStage] = {}, *stage_out[kStage] = {};
     unsigned long long stage_next = 0;
-    int stage_count = kStage;       // slots in use (BFIR_STAGE = 1 .. 8, measurement)
+    int stage_count = 8;            // slots the one- and two-block host calls cycle through (BFIR_STAGE = 1 .. 12, measurement)
     int open_async_copies();
     int stage_alloc(int k);
     int fwd_block_offset = 0;       // front_group: 1 while the second block of a pair is transformed
@@ -146,7 +146,14 @@ struct Engine {
     void *acc_quad[2] = {};         // accumulated spectra of blocks 3 and 4 of a quad (single precision)
     int quad_group(int g, const void *const d_in[4], void *const d_out[4]);
     int enqueue_quad(const void *const d_in[4], void *const d_out[4], bool staged = false);
-    int staged_blocks(int nb, const void *const *d_in, void *const *d_out);
+    int staged_blocks(int nb, const void *const *d_in, void *const *d_out, const void *const *h_in = nullptr, void *const *h_out = nullptr);
+    long long run_host_async_quad(const void *const in[4], void *const out[4]);
+    cudaEvent_t q_in_ready[4] = {}, q_out_ready[4] = {};   // four-block host calls: block b has arrived / has been emitted
+    // BFIR_COPY_TIMING=1 (diagnosis): CUDA-event brackets around every copy of the four-block host path, summarised on stderr by destroy()
+    bool copy_timing = false;
+    std::vector<cudaEvent_t> ct_h2d, ct_d2h;
+    void copy_mark(std::vector<cudaEvent_t> &v, cudaStream_t st) { if (!copy_timing || v.size() >= 8192) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); v.push_back(e); }
+    void copy_report();
     int pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, cudaEvent_t *input_consumed, cudaEvent_t *output_free);
     int enqueue_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1, bool pipelined, bool staged = false);
     long long run_host_async_pair(const void *in0, const void *in1, void *out0, void *out1);
@@ -242,6 +249,7 @@ int Engine::init(const bfir_config_t &c)
     if (const char *env = getenv("BFIR_GRAPHS")) graphs_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_LOOKAHEAD")) lookahead_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGED")) staged_enabled = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_COPY_TIMING")) copy_timing = atoi(env) != 0;
     if (const char *env = getenv("BFIR_WHOLE_COPIES")) whole_copies = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
@@ -254,6 +262,7 @@ int Engine::init(const bfir_config_t &c)
         BFIR_CUDA(cudaStreamCreateWithPriority(&sp_fwd, cudaStreamNonBlocking, prio));
         BFIR_CUDA(cudaStreamCreateWithPriority(&sp_inv, cudaStreamNonBlocking, prio));
     }
+    for (int k = 0; k < 4; k++) { BFIR_CUDA(cudaEventCreateWithFlags(&q_in_ready[k], cudaEventDisableTiming)); BFIR_CUDA(cudaEventCreateWithFlags(&q_out_ready[k], cudaEventDisableTiming)); }
     for (int k = 0; k < 2; k++)
         for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k], &sp_arrived[k] }) BFIR_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     BFIR_CUDA(cudaStreamCreateWithFlags(&tail_stream, cudaStreamNonBlocking));
@@ -350,8 +359,28 @@ void Engine::prof_collect()
     pidx = 0;
 }
 
+void Engine::copy_report()
+{
+    for (int dir = 0; dir < 2; dir++) {
+        std::vector<cudaEvent_t> &v = dir == 0 ? ct_h2d : ct_d2h;
+        const size_t n = v.size() / 2;
+        if (n >= 8) {
+            cudaEventSynchronize(v.back());
+            const size_t first = n / 2;                       // second half: steady state
+            double busy = 0.0; float ms = 0.f, span = 0.f;
+            for (size_t k = first; k < n; k++) { cudaEventElapsedTime(&ms, v[2 * k], v[2 * k + 1]); busy += ms; }
+            cudaEventElapsedTime(&span, v[2 * first], v[2 * n - 1]);
+            fprintf(stderr, "[bfir copy timing] %s: %zu copies, mean copy %.4f ms, span per copy %.4f ms, busy fraction %.3f\n",
+                    dir == 0 ? "H2D" : "D2H", n - first, busy / (n - first), span / (n - first), busy / span);
+        }
+        for (auto e : v) cudaEventDestroy(e);
+        v.clear();
+    }
+}
+
 void Engine::destroy()
 {
+    if (copy_timing) copy_report();
     prof_free();
     if (stream) cudaStreamSynchronize(stream);
     invalidate_graphs();
@@ -367,6 +396,7 @@ void Engine::destroy()
     if (fork_ev) { cudaEventDestroy(fork_ev); fork_ev = nullptr; }
     if (out_done) { cudaEventDestroy(out_done); out_done = nullptr; }
     for (cudaStream_t *st : { &sp_fwd, &sp_inv }) if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); *st = nullptr; }
+    for (int k = 0; k < 4; k++) for (cudaEvent_t *ev : { &q_in_ready[k], &q_out_ready[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
     for (int k = 0; k < 2; k++) {
         for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k], &sp_arrived[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
         for (int j = 0; j < 4; j++) if (sp_acc[k][j]) { cudaFree(sp_acc[k][j]); sp_acc[k][j] = nullptr; }
@@ -811,21 +841,51 @@ int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0
 //   inverse stream:  after the sum: inverse t .. t+NB-1 (these advance the device block counter)
 // The inputs must be complete when the call is made (nothing orders the forward stream after later work on the
 // engine's stream -- that is the point).
-int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out)
+// With host buffers (h_in / h_out, pinned; bfir_run_async_quad) the raw blocks travel through the ring of staging slots on
+// the group's two copy streams: H2D of block b after the forward transform that last read its slot, forward b after its
+// H2D (per-block events, so the first transform starts when the first block has arrived), inverse b after the D2H that
+// last drained its slot, D2H b after inverse b; the ticket events ride on the output-copy stream.
+int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, const void *const *h_in, void *const *h_out)
 {
     int rc;
+    const bool host = h_in != nullptr;
     const size_t cbuf = (size_t)N * rs;
     for (int k = 0; k < 2; k++) for (int j = 0; j < nb; j++) if (!sp_acc[k][j]) BFIR_CUDA(cudaMalloc(&sp_acc[k][j], cbuf * Ct));
-    if (!sp_open) {
+    Group &grp = groups[0];
+    if (!sp_open || (host && !async_copies)) {
         if ((rc = close_async()) != BFIR_OK) return rc;
         BFIR_CUDA(cudaEventRecord(fork_ev, stream));
         BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, fork_ev, 0));
         BFIR_CUDA(cudaStreamWaitEvent(sp_inv, fork_ev, 0));
         for (int k = 0; k < 2; k++) { BFIR_CUDA(cudaEventRecord(sp_mac_done[k], stream)); BFIR_CUDA(cudaEventRecord(sp_inv_done[k], sp_inv)); }
+        if (host) {
+            for (int k = 0; k < kStage; k++) if ((rc = stage_alloc(k)) != BFIR_OK) return rc;
+            BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, fork_ev, 0));
+            BFIR_CUDA(cudaStreamWaitEvent(grp.d2h, fork_ev, 0));
+            for (int k = 0; k < kStage; k++) { BFIR_CUDA(cudaEventRecord(grp.in_free[k], sp_fwd)); BFIR_CUDA(cudaEventRecord(grp.out_free[k], grp.d2h)); }
+            async_open = async_copies = true;
+        }
         sp_open = true;
         sp_pairs = 0;
     }
     const int par = (int)(sp_pairs & 1ull);
+    int slot[4] = { 0, 0, 0, 0 };
+    const void *dev_in[4] = { nullptr, nullptr, nullptr, nullptr };
+    void *dev_out[4] = { nullptr, nullptr, nullptr, nullptr };
+    if (host) {   // input copies first: they are what the call's first kernels wait for
+        const int sc = kStage - kStage % nb;
+        for (int b = 0; b < nb; b++) {
+            slot[b] = (int)((stage_next + (unsigned long long)b) % (unsigned long long)sc);
+            dev_in[b] = stage_in[slot[b]]; dev_out[b] = stage_out[slot[b]];
+            BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, grp.in_free[slot[b]], 0));
+            copy_mark(ct_h2d, grp.h2d);
+            BFIR_CUDA(cudaMemcpyAsync(stage_in[slot[b]], h_in[b], in_bytes, cudaMemcpyHostToDevice, grp.h2d));
+            copy_mark(ct_h2d, grp.h2d);
+            BFIR_CUDA(cudaEventRecord(q_in_ready[b], grp.h2d));
+        }
+        stage_next += (unsigned long long)nb;
+        d_in = dev_in; d_out = dev_out;
+    }
     tail_ready = false;
     use_abs = true;
     // forward transforms of all blocks on the forward stream
@@ -833,7 +893,11 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out)
     stage_stream = sp_fwd;
     prof_suppress = true;
     rc = BFIR_OK;
-    for (int b = 0; b < nb && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
+    for (int b = 0; b < nb && rc == BFIR_OK; b++) {
+        fwd_block_offset = b;
+        if (host) BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, q_in_ready[b], 0));
+        rc = front_group(0, d_in[b], host ? &grp.in_free[slot[b]] : nullptr, true);
+    }
     fwd_block_offset = 0;
     prof_suppress = false;
     stage_stream = nullptr;
@@ -868,16 +932,49 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out)
     BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
     stage_stream = sp_inv;
     prof_suppress = true;
-    for (int b = 0; b < nb && rc == BFIR_OK; b++) { acc_override = sp_acc[par][b]; rc = back_group(0, d_out[b]); }
+    for (int b = 0; b < nb && rc == BFIR_OK; b++) {
+        acc_override = sp_acc[par][b];
+        if (host) BFIR_CUDA(cudaStreamWaitEvent(sp_inv, grp.out_free[slot[b]], 0));
+        rc = back_group(0, d_out[b]);
+        if (host) BFIR_CUDA(cudaEventRecord(q_out_ready[b], sp_inv));
+    }
     acc_override = nullptr;
     prof_suppress = false;
     stage_stream = nullptr;
     use_abs = false;
     if (rc != BFIR_OK) return rc;
     BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
+    if (host) {
+        for (int b = 0; b < nb; b++) {
+            BFIR_CUDA(cudaStreamWaitEvent(grp.d2h, q_out_ready[b], 0));
+            copy_mark(ct_d2h, grp.d2h);
+            BFIR_CUDA(cudaMemcpyAsync(h_out[b], stage_out[slot[b]], out_bytes, cudaMemcpyDeviceToHost, grp.d2h));
+            copy_mark(ct_d2h, grp.d2h);
+            BFIR_CUDA(cudaEventRecord(grp.out_free[slot[b]], grp.d2h));
+            const int tslot = (int)((next_ticket + b) % kMaxInflight);
+            if (ticket_ev[tslot][0] == nullptr) BFIR_CUDA(cudaEventCreateWithFlags(&ticket_ev[tslot][0], cudaEventDisableTiming));
+            BFIR_CUDA(cudaEventRecord(ticket_ev[tslot][0], grp.d2h));
+        }
+    }
     sp_pairs++;
     for (int b = 0; b < nb; b++) finish_block();
     return BFIR_OK;
+}
+
+// four consecutive blocks of pinned host buffers through the stage pipeline; returns the ticket of the fourth block.
+// Needs one stream group and the steady state; otherwise two two-block calls.
+long long Engine::run_host_async_quad(const void *const in[4], void *const out[4])
+{
+    int rc;
+    if (!pair_ok() || n_groups != 1 || !staged_enabled) {
+        const long long t0 = run_host_async_pair(in[0], in[1], out[0], out[1]);
+        if (t0 < 0) return t0;
+        return run_host_async_pair(in[2], in[3], out[2], out[3]);
+    }
+    if (next_ticket + 3 - done_ticket >= kMaxInflight && (rc = wait_ticket(next_ticket + 3 - kMaxInflight)) != BFIR_OK) return rc;
+    if ((rc = staged_blocks(4, nullptr, nullptr, in, out)) != BFIR_OK) return rc;
+    next_ticket += 4;
+    return next_ticket - 1;
 }
 
 int Engine::staged_pair(const void *d_in0, const void *d_in1, void *d_out0, void *d_out1)
@@ -1349,7 +1446,7 @@ int Engine::stage_alloc(int k)
 // all streams of the pipelined host path start after everything queued on the engine's stream so far
 int Engine::open_async_copies()
 {
-    if (async_open && async_copies) return BFIR_OK;
+    if (async_open && async_copies && !sp_open) return BFIR_OK;
     int rc = close_async();
     if (rc != BFIR_OK) return rc;
     for (int k = 0; k < kStage; k++) if ((rc = stage_alloc(k)) != BFIR_OK) return rc;
@@ -1710,6 +1807,16 @@ long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, 
     if (in0 == nullptr || in1 == nullptr || out0 == nullptr || out1 == nullptr) return BFIR_ERR_INVALID;
     if (e->impl.peer.enabled) { bfir::set_error("bfir_run_async_pair is not available on a partition shard"); return BFIR_ERR_INVALID; }
     return e->impl.run_host_async_pair(in0, in1, out0, out1);
+}
+
+long long bfir_run_async_quad(bfir_engine *e, const void *const in[4], void *const out[4])
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (in == nullptr || out == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 4; b++) if (in[b] == nullptr || out[b] == nullptr) return BFIR_ERR_INVALID;
+    if (e->impl.peer.enabled) { bfir::set_error("bfir_run_async_quad is not available on a partition shard"); return BFIR_ERR_INVALID; }
+    return e->impl.run_host_async_quad(in, out);
 }
 
 int bfir_join(bfir_engine *e)

@@ -843,6 +843,57 @@ def test_stage_pipeline_quads_equal_single_blocks(pkg, rs, out_fmt, P):
             assert dd.max() <= 1, (b, dd.max())      # S16 from the float engine, S24 from the double one: within 1 LSB
 
 
+@pytest.mark.parametrize("rs,groups,P", [(8, 1, 5), (4, 1, 2), (4, 1, 7), (8, 3, 4)])
+def test_host_quads_equal_single_blocks(pkg, rs, groups, P):
+    """bfir_run_async_quad: four blocks of pinned host buffers per call through the stage pipeline (input copies, forward
+    transforms, ONE four-block partition sum, inverse transforms, output copies on five streams over a ring of 12 staging
+    slots), more calls in flight than the ring holds, mixed with two-block and one-block host calls and a device call;
+    with several stream groups the call falls back to two pair calls. Same output as the synchronous bfir_run."""
+    import torch
+    L, C, S = 512, 2, 3
+    fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt, tdt = (np.float32, torch.float32) if rs == 4 else (np.float64, torch.float64)
+    h = [decay_filter(c, L * P) for c in range(C * S)]
+    single = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=1)
+    quad = pkg.Brutefir(L, P, rs, C, fmt, fmt, 2000, False, n_streams=S, n_groups=groups)
+    assert single.set_coeff(h, P) == 0 and quad.set_coeff(h, P) == 0
+    nblk = P + 4 * 9 + 2 + 1 + 4
+    x = white_noise(77, nblk * L, C * S).astype(dt)
+    blocks = [np.ascontiguousarray(x[b * L:(b + 1) * L].reshape(L, S, C).transpose(1, 0, 2)).ravel() for b in range(nblk)]
+    pin_in = [torch.from_numpy(b).pin_memory() for b in blocks]
+    pin_out = [torch.zeros(S * L * C, dtype=tdt).pin_memory() for _ in range(nblk)]
+    ref = []
+    for b in range(nblk):
+        rc, o = single.run(blocks[b].view(np.uint8))
+        assert rc == 0
+        ref.append(o.view(dt).copy())
+    b, t = 0, None
+    while b < P:                                     # fill the delay line block by block
+        t = quad.run_async(pin_in[b].numpy(), pin_out[b].numpy())
+        b += 1
+    for call in range(9):
+        if call == 4:                                # a two-block and a one-block host call between the four-block ones
+            t = quad.run_async_pair(pin_in[b].numpy(), pin_in[b + 1].numpy(), pin_out[b].numpy(), pin_out[b + 1].numpy())
+            b += 2
+            t = quad.run_async(pin_in[b].numpy(), pin_out[b].numpy())
+            b += 1
+        t = quad.run_async_quad([p.numpy() for p in pin_in[b:b + 4]], [p.numpy() for p in pin_out[b:b + 4]])
+        b += 4
+        if call == 6:
+            assert quad.wait(t) == 0
+    d_in = [torch.from_numpy(blocks[k]).cuda() for k in range(b, b + 4)]
+    d_out = [torch.zeros(S * L * C, dtype=tdt, device="cuda") for _ in range(4)]
+    torch.cuda.synchronize()
+    quad.run_device_quad(d_in, d_out, staged=True)   # a device call on the same pipeline
+    assert quad.wait(t) == 0 and quad.sync() == 0
+    for k in range(4):
+        pin_out[b + k].copy_(d_out[k].cpu())
+    b += 4
+    assert b == nblk and quad.blockcounter() == nblk
+    for k in range(nblk):
+        assert rel_rms(pin_out[k].numpy(), ref[k]) < (2e-6 if rs == 4 else 1e-13), k
+
+
 @pytest.mark.parametrize("rs,groups,P", [(4, 1, 6), (4, 3, 9), (8, 2, 5), (4, 2, 2)])
 def test_block_quads_equal_single_blocks(pkg, rs, groups, P):
     """bfir_run_device_quad: four blocks per partition-sum launch (both precisions);
