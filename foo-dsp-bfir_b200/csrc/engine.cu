@@ -31,6 +31,14 @@ struct Engine {
     int own_first = 0, own_count = 0;
     int peer_phase = -1;            // receive-buffer phase back_group sums (-1: block parity, one-block calls)
     unsigned int peer_epoch = 0;    // four-block calls made (arrival-flag value)
+    unsigned int peer_in_epoch = 0; // staged four-block calls with the sharded input stage (input-flag value)
+    int own_in_first = 0, own_in_count = 0;   // inputs this rank transforms in the sharded input stage
+    bool shard_inputs = false;      // BFIR_SHARD_INPUTS=1: sharded input stage (measured slower: 0.129 against 0.112 ms per block on 8 GPUs)
+    // BFIR_SHARD_TIMING=1 (diagnosis): CUDA-event marks at the stage boundaries of every staged shard call, summarised on stderr by destroy()
+    bool shard_timing = false;
+    std::vector<cudaEvent_t> st_marks;   // 8 per call: fwd begin, fwd end, sum begin, sum end, pushes end, flag out, flags in, output stage end
+    void st_mark(cudaStream_t st) { if (!shard_timing || st_marks.size() >= 8 * 512) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); st_marks.push_back(e); }
+    void shard_report();
     bool peer_quad_pending = false; // run_partial_quad has been queued, run_finish_quad has not
     int *d_peer_timeout = nullptr;  // set by peer_wait_kernel when a source rank never arrived
     int run_partial_quad(const void *const d_in[4]);
@@ -250,6 +258,7 @@ int Engine::init(const bfir_config_t &c)
     if (const char *env = getenv("BFIR_LOOKAHEAD")) lookahead_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGED")) staged_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_COPY_TIMING")) copy_timing = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_SHARD_TIMING")) shard_timing = atoi(env) != 0;
     if (const char *env = getenv("BFIR_WHOLE_COPIES")) whole_copies = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
@@ -359,6 +368,27 @@ void Engine::prof_collect()
     pidx = 0;
 }
 
+void Engine::shard_report()
+{
+    const size_t n = st_marks.size() / 8;
+    if (n >= 6) {
+        cudaEventSynchronize(st_marks.back());
+        static const char *names[8] = { "forward begin", "forward end", "sum begin", "sum end", "pushes end", "flag out", "flags in", "output stage end" };
+        double off[8] = { 0 }, period = 0.0;
+        float ms = 0.f;
+        const size_t first = n / 3;
+        for (size_t k = first; k < n; k++) {
+            for (int j = 0; j < 8; j++) { cudaEventElapsedTime(&ms, st_marks[8 * k + 2], st_marks[8 * k + j]); off[j] += ms; }
+            if (k > first) { cudaEventElapsedTime(&ms, st_marks[8 * (k - 1) + 2], st_marks[8 * k + 2]); period += ms; }
+        }
+        fprintf(stderr, "[bfir shard timing] rank %d, %zu calls, period %.4f ms per call; offsets from the partition sum's start:", peer.self, n - first, period / (n - first - 1));
+        for (int j = 0; j < 8; j++) fprintf(stderr, " %s %+.4f;", names[j], off[j] / (n - first));
+        fprintf(stderr, "\n");
+    }
+    for (auto e : st_marks) cudaEventDestroy(e);
+    st_marks.clear();
+}
+
 void Engine::copy_report()
 {
     for (int dir = 0; dir < 2; dir++) {
@@ -381,6 +411,7 @@ void Engine::copy_report()
 void Engine::destroy()
 {
     if (copy_timing) copy_report();
+    if (shard_timing) shard_report();
     prof_free();
     if (stream) cudaStreamSynchronize(stream);
     invalidate_graphs();
@@ -557,12 +588,21 @@ int Engine::peer_setup(int rank, int world)
     if (own_count < 1) { set_error("rank %d owns no channel", rank); return BFIR_ERR_INVALID; }
     if (recv) { cudaFree(recv); recv = nullptr; }
     const size_t data_bytes = (size_t)BFIR_PEER_PHASES * world * peer.cpr * N * rs;
-    const size_t bytes = data_bytes + 256;                 // + arrival flags
+    size_t bytes = data_bytes + 256;                       // + arrival flags (outputs at +0, inputs at +128)
     peer.flag_offset = (long long)data_bytes;
+    peer.flag_in_offset = (long long)data_bytes + 128;
+    if (const char *env = getenv("BFIR_SHARD_INPUTS")) shard_inputs = atoi(env) != 0;
+    peer.xin_offset = 0; peer.n_inputs = Cit; peer.in_cpr = (Cit + world - 1) / world;
+    own_in_first = rank * peer.in_cpr;
+    own_in_count = own_in_first >= Cit ? 0 : (Cit - own_in_first < peer.in_cpr ? Cit - own_in_first : peer.in_cpr);
+    if (xbar && shard_inputs) {                            // input region: [2 call parities * 4 blocks][Cit][N]
+        peer.xin_offset = (long long)bytes;
+        bytes += (size_t)8 * Cit * N * rs;
+    }
     BFIR_CUDA(cudaMalloc(&recv, bytes));
     BFIR_CUDA(cudaMemset(recv, 0, bytes));
     if (!d_peer_timeout) { BFIR_CUDA(cudaMalloc((void **)&d_peer_timeout, sizeof(int))); BFIR_CUDA(cudaMemset(d_peer_timeout, 0, sizeof(int))); }
-    peer_epoch = 0; peer_quad_pending = false;
+    peer_epoch = 0; peer_in_epoch = 0; peer_quad_pending = false;
     peer.recv[rank] = recv;
     peer.enabled = 1;
     invalidate_graphs();
@@ -1038,7 +1078,7 @@ int Engine::run_partial_quad(const void *const d_in[4])
         BFIR_CUDA(cudaGetLastError());
     }
     peer_epoch++;
-    peer_signal_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch);
+    peer_signal_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch, peer.flag_offset);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     peer_quad_pending = true;
@@ -1049,7 +1089,7 @@ int Engine::run_finish_quad(void *const d_out[4])
 {
     if (!peer_quad_pending) { set_error("run_finish_quad without run_partial_quad"); return BFIR_ERR_INVALID; }
     peer_quad_pending = false;
-    peer_wait_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch, d_peer_timeout);
+    peer_wait_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch, d_peer_timeout, peer.flag_offset);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     const int base = 2 + (int)((peer_epoch - 1u) & 1u) * 4;
@@ -1103,18 +1143,72 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     use_abs = true;
     // forward stage
     BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, sp_mac_done[par], 0));
-    stage_stream = sp_fwd;
-    prof_suppress = true;
+    st_mark(sp_fwd);
     rc = BFIR_OK;
-    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
-    fwd_block_offset = 0;
-    prof_suppress = false;
-    stage_stream = nullptr;
+    if (xbar && peer.xin_offset != 0) {
+        // SHARDED input stage: this rank transforms only its own inputs (own_in_count CTAs instead of Ci), stores the
+        // spectra into every peer's input region -- phase (call parity, block) -- and raises its input flag; once every
+        // rank's flag of this call is in, the whole input crossbar runs on the gathered spectra. All on the forward
+        // stream, so a rank's input flag of call k+1 also says that its crossbar of call k has read phase set k & 1,
+        // which its peers overwrite with call k+2 only after they have seen that flag.
+        const int ibase = (int)(peer_in_epoch & 1u) * 4;
+        char *xin_all = (char *)recv + peer.xin_offset;
+        const long long row_bytes = (long long)N * rs;
+        for (int b = 0; b < 4; b++) {
+            if (own_in_count > 0) {
+                FwdArgs f = {};
+                f.in_mode = IN_RAW_PREV; f.out_layout = LAYOUT_ORD;
+                f.in = d_in[b]; f.in_stride_x = (long long)L * Ci * in_sf.bytes;
+                f.scale_in = 1.0; f.scale_out = in_sf.scale;
+                f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = Ci; f.n_channels = Cit; f.ch_base = own_in_first;
+                f.use_abs_block = 1; f.abs_block = host_blockcounter + (unsigned int)b;
+                f.state = nullptr; f.n_slots = Pslots; f.n_parts = P; f.prev_parity = (host_blockcounter + (unsigned int)b) & 1u; f.slot_offset = b;
+                f.out = xin_all + (long long)(ibase + b) * Cit * row_bytes; f.out_stride_x = N; f.out_stride_y = 0;
+                cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(own_in_count, 1), sp_fwd, f, tw);
+                count_launch();
+                if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); use_abs = false; return BFIR_ERR_CUDA; }
+                peer_bcast_kernel<<<dim3((unsigned)((row_bytes / 16 + 255) / 256), own_in_count, peer.world - 1), 256, 0, sp_fwd>>>(peer, ibase + b, own_in_first, row_bytes);
+                count_launch();
+            }
+        }
+        {   // the previous-block rows of the inputs other ranks transform: keep them valid (last block of the call)
+            const unsigned int last = host_blockcounter + 3u;
+            void *rows = (char *)prev + ((size_t)((last & 1u) ^ 1u) * Cit) * L * rs;
+            const dim3 g((L + 255) / 256, Cit);
+            if (rs == 4) raw_to_prev_kernel<float><<<g, 256, 0, sp_fwd>>>((const uint8_t *)d_in[3], (float *)rows, L, Cit, in_sf.format, own_in_first, own_in_count);
+            else raw_to_prev_kernel<double><<<g, 256, 0, sp_fwd>>>((const uint8_t *)d_in[3], (double *)rows, L, Cit, in_sf.format, own_in_first, own_in_count);
+            count_launch();
+        }
+        peer_in_epoch++;
+        peer_signal_kernel<<<1, 32, 0, sp_fwd>>>(peer, peer_in_epoch, peer.flag_in_offset);
+        peer_wait_kernel<<<1, 32, 0, sp_fwd>>>(peer, peer_in_epoch, d_peer_timeout, peer.flag_in_offset);
+        count_launch(2);
+        for (int b = 0; b < 4; b++) {
+            XbarArgs x = {};
+            x.in = xin_all + (long long)(ibase + b) * Cit * row_bytes; x.in_stride = N; x.out = fdl; x.out_stride = (long long)Pslots * N; x.slot_stride = N;
+            x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = S; x.stream_base = 0;
+            x.state = state; x.n_slots = Pslots; x.n_parts = P; x.slot_offset = b; x.procblocks = procblocks; x.pb_inc = pb_inc;
+            x.use_abs_block = 1; x.abs_block = host_blockcounter + (unsigned int)b;
+            xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
+            xk<<<dim3((N + 255) / 256, S), 256, (size_t)C * Ci * rs, sp_fwd>>>(x);
+            count_launch();
+        }
+        BFIR_CUDA(cudaGetLastError());
+    } else {
+        stage_stream = sp_fwd;
+        prof_suppress = true;
+        for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
+        fwd_block_offset = 0;
+        prof_suppress = false;
+        stage_stream = nullptr;
+    }
     if (rc != BFIR_OK) { use_abs = false; return rc; }
+    st_mark(sp_fwd);
     BFIR_CUDA(cudaEventRecord(sp_fwd_done[par], sp_fwd));
     // partition sum + pushes on the engine's stream
     BFIR_CUDA(cudaStreamWaitEvent(stream, sp_fwd_done[par], 0));
     BFIR_CUDA(cudaStreamWaitEvent(stream, sp_arrived[par ^ 1], 0));
+    st_mark(stream);
     prof(0);
     prof(1);
     const int base = 2 + (int)(peer_epoch & 1u) * 4;
@@ -1135,6 +1229,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     prof(2);
+    st_mark(stream);
     if (xbar) {
         for (int b = 0; b < 4; b++) {
             XbarArgs x = {};
@@ -1149,17 +1244,20 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     }
     prof(3);
     if (pidx < pcap) pidx++;
+    st_mark(stream);
     BFIR_CUDA(cudaStreamWaitEvent(stream, sp_inv_done[par ^ 1], 0));   // own output stage of call k-1 has read its phase set
     peer_epoch++;
-    peer_signal_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch);
+    peer_signal_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch, peer.flag_offset);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
+    st_mark(stream);
     BFIR_CUDA(cudaEventRecord(sp_mac_done[par], stream));
     // output stage on the inverse stream
     BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
-    peer_wait_kernel<<<1, 32, 0, sp_inv>>>(peer, peer_epoch, d_peer_timeout);
+    peer_wait_kernel<<<1, 32, 0, sp_inv>>>(peer, peer_epoch, d_peer_timeout, peer.flag_offset);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
+    st_mark(sp_inv);
     BFIR_CUDA(cudaEventRecord(sp_arrived[par], sp_inv));
     stage_stream = sp_inv;
     prof_suppress = true;
@@ -1169,6 +1267,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     stage_stream = nullptr;
     use_abs = false;
     if (rc != BFIR_OK) return rc;
+    st_mark(sp_inv);
     BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
     sp_pairs++;
     for (int b = 0; b < 4; b++) finish_block();

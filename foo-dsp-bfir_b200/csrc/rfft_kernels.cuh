@@ -46,6 +46,11 @@ struct PeerPush {
     void *recv[BFIR_MAX_PEERS];
     int world, self, cpr, enabled;
     long long flag_offset;      // bytes from the start of a receive buffer to its unsigned int flags[world]
+    // sharded input stage (crossbar engines, four-block staged calls): every rank transforms its own in_cpr inputs and
+    // stores the spectra into every peer's input region [2 call parities * 4 blocks][n_inputs][N]; second flag array
+    long long xin_offset;       // bytes from the start of a receive buffer to that region (0: not allocated)
+    long long flag_in_offset;   // ... and to unsigned int flags_in[world]
+    int in_cpr, n_inputs;
 };
 template <class T> BFIR_HD T *peer_dst(const PeerPush &p, int ch, int N, unsigned int phase)
 {

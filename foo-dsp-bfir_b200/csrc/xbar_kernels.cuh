@@ -93,26 +93,52 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(const T *recv, T *dst, co
 // NVLink -- and the owner's output stage starts with a kernel that waits until every source rank's flag has reached
 // the call's epoch. Replaces the one-element NCCL all-reduce of the one-block calls (tens of microseconds at 8 ranks).
 // A rank that never arrives trips the time-out (about two seconds) and is reported by bfir_sync, not by a hang.
-static __global__ void peer_signal_kernel(const PeerPush p, unsigned int epoch)
+// flag_off: p.flag_offset (partial output spectra) or p.flag_in_offset (input spectra of the sharded input stage)
+static __global__ void peer_signal_kernel(const PeerPush p, unsigned int epoch, long long flag_off)
 {
     const int q = threadIdx.x;
     if (q >= p.world) return;
     __threadfence_system();
-    volatile unsigned int *f = (volatile unsigned int *)((char *)p.recv[q] + p.flag_offset) + p.self;
+    volatile unsigned int *f = (volatile unsigned int *)((char *)p.recv[q] + flag_off) + p.self;
     *f = epoch;
     __threadfence_system();
 }
-static __global__ void peer_wait_kernel(const PeerPush p, unsigned int epoch, int *timed_out)
+static __global__ void peer_wait_kernel(const PeerPush p, unsigned int epoch, int *timed_out, long long flag_off)
 {
     const int s = threadIdx.x;
     if (s >= p.world) return;
-    volatile unsigned int *f = (volatile unsigned int *)((char *)p.recv[p.self] + p.flag_offset) + s;
+    volatile unsigned int *f = (volatile unsigned int *)((char *)p.recv[p.self] + flag_off) + s;
     const long long t0 = clock64();
     while ((int)(*f - epoch) < 0) {
         if (clock64() - t0 > 4000000000LL) { *timed_out = 1; break; }
         __nanosleep(100);
     }
     __threadfence_system();
+}
+
+// Sharded input stage: this rank's input spectra (rows [row0, row0 + nrows) of phase `phase`, N reals each, already in
+// the local input region) -> the same rows of every peer's input region, 16-byte stores over NVLink.
+// grid (ceil(row_bytes / 16 / 256), nrows, world - 1)
+static __global__ void __launch_bounds__(256) peer_bcast_kernel(const PeerPush p, int phase, int row0, long long row_bytes)
+{
+    int q = blockIdx.z;
+    if (q >= p.self) q++;                               // the z-th OTHER rank
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * 16 >= row_bytes) return;
+    const long long off = p.xin_offset + ((long long)phase * p.n_inputs + row0 + blockIdx.y) * row_bytes;
+    const uint4 v = ((const uint4 *)((const char *)p.recv[p.self] + off))[i];
+    ((uint4 *)((char *)p.recv[q] + off))[i] = v;
+}
+
+// one raw interleaved block -> planar rows of the previous-block buffer, for the channels this rank does NOT transform
+// itself in the sharded input stage (keeps every entry point's view of the previous block valid). grid (ceil(L/256), channels)
+template <class T>
+static __global__ void __launch_bounds__(256) raw_to_prev_kernel(const uint8_t *raw, T *prev_rows, int L, int n_ch, int fmt, int skip_first, int skip_count)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (f >= L || (c >= skip_first && c < skip_first + skip_count)) return;
+    const int bytes = fmt_bytes(fmt);
+    prev_rows[(long long)c * L + f] = load_raw<T>(raw + ((long long)f * n_ch + c) * bytes, fmt);
 }
 
 typedef void (*xbar_kernel_t)(const XbarArgs);

@@ -243,7 +243,11 @@ int bfir_run_finish_quad_device(bfir_engine *e, void *const d_out[4]);
  * after it has seen every peer's flag of call k-1, and raises its flag of call k only after its own output stage of
  * call k-1 has read the receive-buffer phases that call k+1 will overwrite. CONTRACT as BFIR_PAIR_STAGED: the four
  * input blocks are complete when the call is made; the compact own-channel output blocks are visible to the engine's
- * stream after bfir_join, to the host after bfir_sync. Every rank makes the same sequence of calls. */
+ * stream after bfir_join, to the host after bfir_sync. Every rank makes the same sequence of calls.
+ * BFIR_SHARD_INPUTS=1 (read by bfir_peer_setup; crossbar engines): the input stage is sharded as well -- a rank
+ * transforms only its own ceil(inputs / world) input channels and stores the spectra into every peer's input region
+ * (a second flag array orders it), then applies the whole input crossbar. Off by default: measured slower than the
+ * redundant input stage on 2 and on 8 GPUs. */
 int bfir_run_shard_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
 

@@ -141,13 +141,19 @@ def test_two_emulated_ranks_four_blocks_per_call(pkg, rs, L, P, C, xb):
     assert [e.blockcounter() for e in ranks] == [nb, nb]
 
 
-@pytest.mark.parametrize("rs,L,P,C,xb", [(4, 512, 6, 4, (0, 0)), (8, 256, 4, 5, (0, 0)), (4, 1024, 8, 4, (3, 5)), (4, 2048, 16, 8, (8, 8))])
-def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb):
+@pytest.mark.parametrize("rs,L,P,C,xb,shard_inputs", [(4, 512, 6, 4, (0, 0), 0), (8, 256, 4, 5, (0, 0), 0), (4, 1024, 8, 4, (3, 5), 0),
+                                                      (4, 2048, 16, 8, (8, 8), 0), (4, 1024, 8, 4, (3, 5), 1), (4, 2048, 16, 8, (8, 8), 1),
+                                                      (8, 512, 5, 6, (4, 4), 1)])
+def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb, shard_inputs, monkeypatch):
     """bfir_run_shard_quad_staged: the four-block shard call through the stage pipeline (forward transforms, partition
     sum + pushes, arrival wait + output stage of neighbouring calls on three streams per rank; receive-buffer phases
     handed over by the arrival flags alone). Seven staged calls with a one-block call and a split (partial / finish)
-    four-block call in between: same output as the unsharded engine for every block."""
+    four-block call in between: same output as the unsharded engine for every block. shard_inputs = 1: with a crossbar
+    every rank transforms only its own inputs and stores the spectra into its peers' input regions (second flag array;
+    BFIR_SHARD_INPUTS=1, off by default because it measured slower), including the hand-back of the previous-block rows
+    to the one-block calls in between."""
     import torch
+    monkeypatch.setenv("BFIR_SHARD_INPUTS", str(shard_inputs))
     fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
     dt, tdt = (np.float32, torch.float32) if rs == 4 else (np.float64, torch.float64)
     n_in = xb[0] or C
@@ -164,10 +170,8 @@ def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb):
         e = build(pkg, L, P, rs, C, fmt, xb, h, gains, part_begin=begin, part_count=count)
         e.peer_setup(r, world)
         ranks.append(e)
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    for e in ranks + [full]:
-        e.set_stream(stream.cuda_stream)
+    # every emulated rank keeps its OWN streams, as separate processes would: with the sharded input stage a rank's
+    # forward stream waits for its peers' input flags, which must not sit behind this rank's work on a shared stream
     for r, e in enumerate(ranks):
         for q, other in enumerate(ranks):
             if q != r:
@@ -185,8 +189,10 @@ def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb):
     def single(b):
         for e in ranks:
             e.run_partial_device(d_in[b])
+        torch.cuda.synchronize()                              # the cross-rank barrier of the one-block calls
         for e, o in zip(ranks, d_own):
             e.run_finish_device(o[b])
+        torch.cuda.synchronize()
 
     b = 0
     while b < P:
