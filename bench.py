@@ -12,14 +12,14 @@ Workload (one "step" = one block of the block loop, brutefir::run, for every str
   line = S x 64 MiB) exceeds the 126 MB L2 -- no L2 flush is needed between steps. N GPUs: every rank
   runs its own S streams (channel/stream sharding, no collective): weak scaling.
 
-Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM, four blocks per call
-(bfir_run_device_quad_staged: ONE partition-sum launch for the four, every coefficient spectrum read once) through the
+Printed JSON (one line, rank 0): value = whole-job Msamples/s with inputs resident in HBM, eight blocks per call
+(bfir_run_device_oct, staged: ONE partition-sum launch for the eight, every coefficient spectrum read once) through the
 engine's stage pipeline (transforms of the neighbouring calls on side streams beside the partition sum); e2e = the
 same metric on pinned HOST buffers, the H2D of every input block and the D2H of every output block inside
 the timed region: e2e.value through bfir_run_async_pair/bfir_wait (three calls in flight), e2e.one_block_per_call
 through bfir_run_async, e2e.sync_run through the reference's synchronous run() = bfir_run (H2D + kernels + D2H +
-sync per call); roofline = the four-block partition-sum kernel, bytes that must move ((2P+7) N realsize per channel
-and launch) over its CUDA-event time, with the two-block and one-block kernels beside it; cpu_baseline = the
+sync per call); roofline = the eight-block partition-sum kernel, bytes that must move ((2P+15) N realsize per channel
+and launch) over its CUDA-event time, with the four-, two- and one-block kernels beside it; cpu_baseline = the
 reference's own sources (oracle/_ref, FFT provider named) on the host cores; latency = host-visible bfir_run latency
 of ONE 7.1 stream (p50/p99).
 `--impl reference` times only the CPU reference (rank 0), same metric/config, --steps / --warmup honoured (each step a
@@ -57,8 +57,8 @@ def workload_config(streams, n_gpus):
         "l2": "streamed set per step (%d MiB coefficient + delay-line spectra per GPU) exceeds the 126 MB L2; no flush"
               % (streams * CFG["channels"] * 2 * CFG["P"] * 2 * CFG["L"] * CFG["realsize"] // (1 << 20)),
         "prefill_blocks": CFG["P"],
-        "step": "one block (8192 frames) of every stream; `value` calls the four-block entry point (bfir_run_device_quad_staged: four steps per call "
-                "with ONE partition-sum launch), e2e the two-block one on pinned host buffers (bfir_run_async_pair); the two- and one-block-per-call "
+        "step": "one block (8192 frames) of every stream; `value` calls the eight-block entry point (bfir_run_device_oct, staged: eight steps per call "
+                "with ONE partition-sum launch), e2e the two-block one on pinned host buffers (bfir_run_async_pair); the four-, two- and one-block-per-call "
                 "device numbers ride beside them under `roofline`",
     }
 
@@ -266,19 +266,25 @@ def main():
     # kernels back to back on one stream (each kernel's event time is its own: step shares). "single": one block per call.
     dev_out2 = torch.empty_like(dev_out)
     dev_outs = [dev_out, dev_out2] + [torch.empty_like(dev_out) for _ in range(2)]
+    dev_outs8 = dev_outs + [torch.empty_like(dev_out) for _ in range(4)]
 
     def device_pass(mode):
-        """K steps: 'staged_quad' / 'serial_quad' four blocks per call, 'staged' / 'serial' two, 'single' one."""
-        per = 4 if mode.endswith("quad") else (1 if mode == "single" else 2)
+        """K steps: 'staged_oct' / 'serial_oct' eight blocks per call, 'staged_quad' / 'serial_quad' four, 'staged' / 'serial'
+        two, 'single' one; what does not fill a call goes through the next smaller one."""
+        per = 8 if mode.endswith("oct") else (4 if mode.endswith("quad") else (1 if mode == "single" else 2))
         staged = mode.startswith("staged")
-        eng.set_profiling(max(K // per, 1))
+        eng.set_profiling(max(K // per, 1) + 2)
         n0 = pkg.kernel_launch_count()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         b = 0
-        if per == 4:
-            for b in range(0, K - 3, 4):
+        if per == 8:
+            for b in range(0, K - 7, 8):
+                eng.run_device_oct(dev_in + dev_in, dev_outs8, staged=staged)
+            b = K - K % 8
+        if per >= 4:
+            for b in range(b, K - 3, 4):
                 eng.run_device_quad(dev_in, dev_outs, staged=staged)
             b = K - K % 4
         if per >= 2:
@@ -299,40 +305,48 @@ def main():
         return ms, n, pr, npr
 
     def output_check():
-        """The timed passes never look at their output: afterwards, run the SAME four blocks through the stage pipeline
-        (one four-block call) on one engine and block by block on a second engine in the same state, and compare."""
+        """The timed passes never look at their output: afterwards, run the SAME eight blocks through the stage pipeline
+        (one eight-block call) on one engine and block by block on a second engine in the same state, and compare."""
         chk = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=S, device=local_rank, n_groups=1)
         chk.set_stream(stream.cuda_stream)
         assert chk.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
         e2 = pkg.Brutefir(L, P, rs, C, fmt, fmt, rate, False, n_streams=S, device=local_rank, n_groups=1)
         e2.set_stream(stream.cuda_stream)
         assert e2.set_coeff(make_filters(Ct, L * P, first=rank * Ct), P) == 0
-        o = [torch.empty_like(dev_out) for _ in range(8)]
+        o = [torch.empty_like(dev_out) for _ in range(16)]
         for b in range(P + 2):
             chk.run_device(dev_in[b % ring], o[0])
-            e2.run_device(dev_in[b % ring], o[4])
+            e2.run_device(dev_in[b % ring], o[8])
         torch.cuda.synchronize()
         b = P + 2
-        for k in range(4):
+        for k in range(8):
             chk.run_device(dev_in[(b + k) % ring], o[k])
-        e2.run_device_quad([dev_in[(b + k) % ring] for k in range(4)], o[4:8], staged=True)
+        e2.run_device_oct([dev_in[(b + k) % ring] for k in range(8)], o[8:16], staged=True)
         e2.join()
         assert chk.sync() == 0 and e2.sync() == 0
         errs = []
-        for k in range(4):
-            d = (o[4 + k] - o[k]).double()
+        for k in range(8):
+            d = (o[8 + k] - o[k]).double()
             errs.append(float(torch.sqrt(torch.mean(d * d) / torch.mean(o[k].double() ** 2))))
         chk.close()
         e2.close()
-        return {"rel_rms_staged_quad_vs_single_blocks": errs, "ok": max(errs) < 1e-12,
-                "note": "same four blocks through bfir_run_device_quad_staged and through four bfir_run_device calls"}
+        return {"rel_rms_staged_oct_vs_single_blocks": errs, "ok": max(errs) < 1e-12,
+                "note": "same eight blocks through bfir_run_device_oct (staged) and through eight bfir_run_device calls"}
 
-    device_pass("staged_quad")              # warm-up of the stage pipeline (allocates its accumulators)
+    device_pass("staged_oct")               # warm-up of the stage pipeline (allocates its accumulators)
+    for nb in (1, 2, 4, 8):
+        eng.get_mac_profile(nb)
     sampler.busy.set()
-    ms_total, launches, prof_staged, nprof_staged = device_pass("staged_quad")
+    ms_total, launches, _, _ = device_pass("staged_oct")
     sampler.busy.clear()
     value = n_gpus * Ct * L * K / (ms_total * 1e-3) / 1e6
+    mac8_sum, mac8_n = eng.get_mac_profile(8)            # the eight-block launches inside the timed region of `value`
+    mac4_in_value = eng.get_mac_profile(4)               # (K % 8 >= 4: one four-block launch rides along)
     out_check = output_check()
+    ms_serial8, _, _, _ = device_pass("serial_oct")
+    mac8s_sum, mac8s_n = eng.get_mac_profile(8)
+    device_pass("staged_quad")
+    ms_quad_staged, _, prof_staged, nprof_staged = device_pass("staged_quad")
     ms_serial, _, prof, nprof = device_pass("serial_quad")
     # two blocks per call (staged and back to back), and one block per call (what a real-time caller gets; the
     # per-block partition sum of SURVEY 8d)
@@ -510,17 +524,19 @@ def main():
     # pattern) would move, is kept under `vs_reference_access_pattern`.
     b_mac = (2 * P + 1) * (2 * L) * rs * Ct
     nquads = max(nprof, 1)
-    mac_ms = prof_staged["mac_ms"] / max(nprof_staged, 1)   # one launch = four blocks of every channel; timed region of `value`
-    mac_serial_ms = prof["mac_ms"] / nquads
-    must_move = (2 * P + 7) * (2 * L) * rs * Ct
-    kernel_moves = (2 * P + 3 * quad_split + 4) * (2 * L) * rs * Ct
+    mac_ms = mac8_sum / max(mac8_n, 1)                      # one launch = EIGHT blocks of every channel; timed region of `value`
+    mac8_serial_ms = mac8s_sum / max(mac8s_n, 1)
+    must_move = (2 * P + 15) * (2 * L) * rs * Ct
     achieved = must_move / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0
     traffic, traffic_src = None, None       # DRAM read+write bytes per launch from the committed ncu --set full capture
     tpath = os.path.join(ROOT, "profiles", "mac_traffic.json")
     if os.path.exists(tpath) and S == 16:
         tj = json.load(open(tpath))
-        if tj.get("kernel", "").startswith("partition_mac_multi_kernel<double"):
+        if tj.get("kernel", "").startswith("partition_mac_oct_kernel<double"):
             traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+    mac4_ms = prof_staged["mac_ms"] / max(nprof_staged, 1)
+    mac4_serial_ms = prof["mac_ms"] / nquads
+    must_move4 = (2 * P + 7) * (2 * L) * rs * Ct
     mac1_ms = prof_single["mac_ms"] / max(nprof_single, 1)
     mac2_ms = prof_pair_staged["mac_ms"] / max(nprof_pair_staged, 1)
     mac2_serial_ms = prof_pair["mac_ms"] / max(nprof_pair, 1)
@@ -530,18 +546,25 @@ def main():
         return nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "partition_mac_multi_kernel<double,NB=4,SPLIT=%d>" % quad_split, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": must_move, "avg_launch_ms": mac_ms,
-                "note": "one launch = the partition sums of FOUR consecutive blocks of %d channels; algorithmic bytes = what must move for that: "
-                        "(2P+7) N realsize per channel (P coefficient + P+3 delay-line spectra in, 4 accumulated spectra out). Timed with CUDA events on "
-                        "the engine's stream inside the timed region of `value`, i.e. WITH the transforms of the neighbouring calls running beside it" % Ct,
-                "kernel_moves_bytes_per_launch": kernel_moves,
-                "vs_reference_access_pattern": {"bytes_per_launch": 4 * b_mac, "frac": gbs(4 * b_mac, mac_ms) / peak,
-                                                "note": "4 x SURVEY 8d's B_mac = (2P+1) N realsize per channel-block: what four one-block partition sums move; "
-                                                        "above 1 because the four-block kernel reads every coefficient spectrum once for all four blocks"},
-                "serial_pass": {"note": "the same four-block calls with their kernels back to back on one stream (nothing beside them)", "avg_launch_ms": mac_serial_ms,
-                                "frac": gbs(must_move, mac_serial_ms) / peak,
-                                "value": n_gpus * Ct * L * K / (ms_serial * 1e-3) / 1e6, "ms_per_step": ms_serial / K},
+                "kernel": "partition_mac_oct_kernel<double,W=4,128>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": must_move, "avg_launch_ms": mac_ms, "launches_timed": mac8_n,
+                "note": "one launch = the partition sums of EIGHT consecutive blocks of %d channels; algorithmic bytes = what must move for that: "
+                        "(2P+15) N realsize per channel (P coefficient + P+7 delay-line spectra in, 8 accumulated spectra out). Timed with CUDA events on "
+                        "the engine's stream inside the timed region of `value`, i.e. WITH the transforms of the neighbouring calls running beside it"
+                        "%s" % (Ct, "; the %d steps that do not fill an eight-block call went through one four-block launch (%.4f ms)" % (K % 8, mac4_in_value[0] / max(mac4_in_value[1], 1)) if mac4_in_value[1] else ""),
+                "vs_reference_access_pattern": {"bytes_per_launch": 8 * b_mac, "frac": gbs(8 * b_mac, mac_ms) / peak,
+                                                "note": "8 x SURVEY 8d's B_mac = (2P+1) N realsize per channel-block: what eight one-block partition sums move; "
+                                                        "above 1 because the eight-block kernel reads every coefficient spectrum once for all eight blocks"},
+                "serial_pass": {"note": "the same eight-block calls joined after every call (nothing beside the sum)", "avg_launch_ms": mac8_serial_ms,
+                                "frac": gbs(must_move, mac8_serial_ms) / peak,
+                                "value": n_gpus * Ct * L * K / (ms_serial8 * 1e-3) / 1e6, "ms_per_step": ms_serial8 / K},
+                "four_blocks_per_launch": {"kernel": "partition_mac_multi_kernel<double,NB=4,SPLIT=%d>" % quad_split,
+                                           "algorithmic_bytes_per_launch": must_move4, "note": "(2P+7) N realsize per channel for four blocks",
+                                           "staged": {"avg_launch_ms": mac4_ms, "frac": gbs(must_move4, mac4_ms) / peak,
+                                                      "value": n_gpus * Ct * L * K / (ms_quad_staged * 1e-3) / 1e6, "ms_per_step": ms_quad_staged / K},
+                                           "serial": {"avg_launch_ms": mac4_serial_ms, "frac": gbs(must_move4, mac4_serial_ms) / peak,
+                                                      "value": n_gpus * Ct * L * K / (ms_serial * 1e-3) / 1e6, "ms_per_step": ms_serial / K,
+                                                      "step_share": {k: v / nquads / 4 for k, v in prof.items()}}},
                 "step_share": {k: v / nquads / 4 for k, v in prof.items()},
                 "two_blocks_per_launch": {"kernel": "partition_mac_pair_kernel<double,SPLIT=%d,UNROLL=2>" % mac_split,
                                           "algorithmic_bytes_per_launch": must_move2, "note": "(2P+3) N realsize per channel for two blocks",

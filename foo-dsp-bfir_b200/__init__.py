@@ -80,6 +80,8 @@ API = [
     ("bfir_run_finish_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
     ("bfir_run_shard_quad_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_run_async_quad", ctypes.c_longlong, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    ("bfir_run_device_oct", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _ci]),
+    ("bfir_get_mac_profile", _ci, [_vp, _ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong), _ci]),
     ("bfir_wait", _ci, [_vp, ctypes.c_longlong]),
     ("bfir_sync", _ci, [_vp]),
     ("bfir_reset", _ci, [_vp]),
@@ -350,6 +352,13 @@ class Brutefir:
         b = (_vp * 4)(*[_buf(x, self.out_bytes, "d_out") for x in d_outs])
         _check((self.lib.bfir_run_device_quad_staged if staged else self.lib.bfir_run_device_quad)(self.h, a, b))
 
+    def run_device_oct(self, d_ins, d_outs, staged=False):
+        """Eight consecutive blocks with one partition-sum launch, through the stage pipeline; staged=False joins at the
+        end of the call, staged=True leaves the pipeline open (inputs complete at call time, outputs after join() / sync())."""
+        a = (_vp * 8)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
+        b = (_vp * 8)(*[_buf(x, self.out_bytes, "d_out") for x in d_outs])
+        _check(self.lib.bfir_run_device_oct(self.h, a, b, 1 if staged else 0))
+
     def run_partial_quad_device(self, d_ins):
         """partition shard with the fused reduce, four blocks: transforms, one four-block partition sum over the own
         partitions, pushes to the owners, arrival flag (bfir_run_partial_quad_device)"""
@@ -473,6 +482,12 @@ class Brutefir:
         n = ctypes.c_ulonglong()
         _check(self.lib.bfir_get_profile(self.h, ms, ctypes.byref(n), int(reset)))
         return {"fwd_ms": ms[0], "mac_ms": ms[1], "inv_ms": ms[2]}, int(n.value)
+
+    def get_mac_profile(self, blocks_per_launch, reset=True):
+        """-> (summed ms, launches) of the profiled partition sums that covered `blocks_per_launch` blocks"""
+        ms, n = ctypes.c_double(), ctypes.c_ulonglong()
+        _check(self.lib.bfir_get_mac_profile(self.h, int(blocks_per_launch), ctypes.byref(ms), ctypes.byref(n), int(reset)))
+        return float(ms.value), int(n.value)
 
     def check_overflows(self):
         return _check(self.lib.bfir_check_overflows(self.h))

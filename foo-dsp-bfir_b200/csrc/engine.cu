@@ -16,7 +16,7 @@ namespace bfir {
 struct Engine {
     bfir_config_t cfg;
     int L = 0, N = 0, P = 0, C = 0, S = 0, Ct = 0, rs = 0, log2m = 0;
-    int Pslots = 0;                 // delay-line slots per channel, P + 7 (see init)
+    int Pslots = 0;                 // delay-line slots per channel, P + 15 (see init)
     // crossbar: Ci inputs and Co outputs per stream around the C filters (== C without a crossbar)
     int Ci = 0, Co = 0, Cit = 0, Cot = 0;
     bool xbar = false, xbar_set = false;
@@ -136,7 +136,7 @@ struct Engine {
     // block index from the host because the device counter (advanced by the inverse kernels) lags behind
     cudaStream_t sp_fwd = nullptr, sp_inv = nullptr;
     cudaEvent_t sp_fwd_done[2] = {}, sp_mac_done[2] = {}, sp_inv_done[2] = {};
-    void *sp_acc[2][4] = {};        // [call parity][block in call] accumulated spectra (two or four blocks per call)
+    void *sp_acc[2][8] = {};        // [call parity][block in call] accumulated spectra (two, four or eight blocks per call)
     unsigned long long sp_pairs = 0; // pairs queued since the pipeline was opened
     bool sp_open = false;
     bool staged_enabled = true;     // BFIR_STAGED=0 switches the stage pipeline off
@@ -154,6 +154,7 @@ struct Engine {
     void *acc_quad[2] = {};         // accumulated spectra of blocks 3 and 4 of a quad (single precision)
     int quad_group(int g, const void *const d_in[4], void *const d_out[4]);
     int enqueue_quad(const void *const d_in[4], void *const d_out[4], bool staged = false);
+    int enqueue_oct(const void *const d_in[8], void *const d_out[8], bool staged);
     int staged_blocks(int nb, const void *const *d_in, void *const *d_out, const void *const *h_in = nullptr, void *const *h_out = nullptr);
     long long run_host_async_quad(const void *const in[4], void *const out[4]);
     cudaEvent_t q_in_ready[4] = {}, q_out_ready[4] = {};   // four-block host calls: block b has arrived / has been emitted
@@ -176,6 +177,12 @@ struct Engine {
     unsigned long long pblocks = 0;
     bool prof_suppress = false;     // pair_group times the pair as a whole and silences the per-block marks inside it
     void prof(int k) { if (pidx < pcap && !prof_suppress) cudaEventRecord(pev[4 * pidx + k], stream); }
+    // blocks per profiled entry (1, 2, 4, 8): lets the partition-sum time be reported per kernel family
+    int prof_nb = 1;
+    std::vector<int> pnb;
+    double pmac_by_nb[9] = {0};
+    unsigned long long pcount_by_nb[9] = {0};
+    void prof_next() { if (pidx < pcap) { if (pnb.size() <= pidx) pnb.resize(pidx + 1); pnb[pidx] = prof_nb; pidx++; } }
     void prof_collect();
     void prof_free() { for (auto ev : pev) cudaEventDestroy(ev); pev.clear(); pcap = pidx = 0; }
 
@@ -214,7 +221,7 @@ int Engine::init(const bfir_config_t &c)
     if (P < 1 || C < 1) { set_error("No channels defined."); return BFIR_ERR_INVALID; }            // brutefir.cpp:745-749
     if ((long long)C * S > 0x7fffffffLL / 2) return BFIR_ERR_INVALID;
     Ct = C * S;
-    Pslots = P + 7;
+    Pslots = P + 15;
     xbar = c.xbar_inputs > 0 || c.xbar_outputs > 0;
     Ci = c.xbar_inputs > 0 ? c.xbar_inputs : C;
     Co = c.xbar_outputs > 0 ? c.xbar_outputs : C;
@@ -236,11 +243,11 @@ int Engine::init(const bfir_config_t &c)
     own_stream = true;
 
     const size_t cbuf = (size_t)N * rs;
-    // The reference's delay line has P slots, slot = blockcounter % P (brutefir.cpp:270,294). Here it has P + 7:
+    // The reference's delay line has P slots, slot = blockcounter % P (brutefir.cpp:270,294). Here it has P + 15:
     // with P + 1 the spectrum of block t+1 can be written while block t's partition sum still needs X[t-P+1] (block
-    // pairs), P + 3 covers four blocks per launch, and the stage pipeline transforms the NEXT call's (up to four)
-    // blocks while the sum of this one runs, four more. Which slot a block lands in is not observable -- partition i
-    // is only read once procblocks says the slot has been written since the last reset.
+    // pairs), P + 3 covers four blocks per launch, P + 7 eight, and the stage pipeline transforms the NEXT call's (up
+    // to eight) blocks while the sum of this one runs, eight more. Which slot a block lands in is not observable --
+    // partition i is only read once procblocks says the slot has been written since the last reset.
     BFIR_CUDA(cudaMalloc(&fdl, cbuf * Pslots * Ct));
     BFIR_CUDA(cudaMemsetAsync(fdl, 0, cbuf * Pslots * Ct, stream));                                      // brutefir.cpp:768-769
     BFIR_CUDA(cudaMalloc(&acc, cbuf * Ct));
@@ -360,11 +367,14 @@ void Engine::prof_collect()
     for (size_t i = 0; i < pidx; i++) {
         for (int k = 0; k < 3; k++) {
             float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, pev[4 * i + k], pev[4 * i + k + 1]) == cudaSuccess) pms[k] += ms;
+            if (cudaEventElapsedTime(&ms, pev[4 * i + k], pev[4 * i + k + 1]) == cudaSuccess) {
+                pms[k] += ms;
+                if (k == 1 && i < pnb.size() && pnb[i] >= 1 && pnb[i] <= 8) { pmac_by_nb[pnb[i]] += ms; pcount_by_nb[pnb[i]]++; }
+            }
         }
         pblocks++;
     }
-    if (pidx > 0) { pcap -= pidx; pev.erase(pev.begin(), pev.begin() + 4 * pidx); }
+    if (pidx > 0) { pcap -= pidx; pev.erase(pev.begin(), pev.begin() + 4 * pidx); pnb.erase(pnb.begin(), pnb.begin() + (pnb.size() < pidx ? pnb.size() : pidx)); }
     pidx = 0;
 }
 
@@ -430,7 +440,7 @@ void Engine::destroy()
     for (int k = 0; k < 4; k++) for (cudaEvent_t *ev : { &q_in_ready[k], &q_out_ready[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
     for (int k = 0; k < 2; k++) {
         for (cudaEvent_t *ev : { &sp_fwd_done[k], &sp_mac_done[k], &sp_inv_done[k], &sp_arrived[k] }) if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
-        for (int j = 0; j < 4; j++) if (sp_acc[k][j]) { cudaFree(sp_acc[k][j]); sp_acc[k][j] = nullptr; }
+        for (int j = 0; j < 8; j++) if (sp_acc[k][j]) { cudaFree(sp_acc[k][j]); sp_acc[k][j] = nullptr; }
     }
     if (tail_stream) { cudaStreamSynchronize(tail_stream); cudaStreamDestroy(tail_stream); tail_stream = nullptr; }
     for (int g = 0; g < BFIR_MAX_GROUPS; g++) if (tail_done[g]) { cudaEventDestroy(tail_done[g]); tail_done[g] = nullptr; }
@@ -675,6 +685,7 @@ int Engine::front_group(int g, const void *d_inbuf, cudaEvent_t *input_consumed,
     f.state = state + g; f.n_slots = Pslots; f.n_parts = P; f.prev_parity = (host_blockcounter + (unsigned int)fwd_block_offset) & 1u; f.slot_offset = fwd_block_offset;
     if (!xbar) { f.out = fdl; f.out_stride_x = (long long)Pslots * N; f.out_stride_y = N; f.procblocks = procblocks; f.pb_inc = pb_inc; }
     else { f.out = xin; f.out_stride_x = N; f.out_stride_y = 0; f.procblocks = nullptr; f.pb_inc = nullptr; }
+    if (g == 0 && !prof_suppress) prof_nb = 1;
     if (g == 0) prof(0);
     cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(ns * Ci, 1), st, f, tw);
     count_launch();
@@ -747,7 +758,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
         cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(own_count, 1), st, v, tw);
         count_launch();
         if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
-        if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+        if (g == 0) { prof(3); prof_next(); }
         return BFIR_OK;
     }
     if (xbar) { // filter outputs -> outputs (mixnscale OUTPUT, n_bufs = C)
@@ -808,7 +819,7 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
         count_launch();
         BFIR_CUDA(cudaGetLastError());
     }
-    if (g == 0 && !prof_suppress) { prof(3); if (pidx < pcap) pidx++; }
+    if (g == 0 && !prof_suppress) { prof(3); prof_next(); }
     return BFIR_OK;
 }
 
@@ -839,6 +850,7 @@ int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0
     const Group &grp = groups[g];
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
     // profiling (bfir_set_profiling): one entry per PAIR -- both forward transforms, the pair sum, both inverse transforms
+    if (g == 0) prof_nb = 2;
     if (g == 0) prof(0);
     prof_suppress = true;
     int rc = front_group(g, d_in0, nullptr, true);
@@ -867,7 +879,7 @@ int Engine::pair_group(int g, const void *d_in0, const void *d_in1, void *d_out0
     if (rc == BFIR_OK) rc = back_group(g, d_out1);
     acc_override = nullptr;
     prof_suppress = false;
-    if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+    if (g == 0) { prof(3); prof_next(); }
     return rc;
 }
 
@@ -909,9 +921,11 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
         sp_pairs = 0;
     }
     const int par = (int)(sp_pairs & 1ull);
+    prof_nb = nb;
     int slot[4] = { 0, 0, 0, 0 };
     const void *dev_in[4] = { nullptr, nullptr, nullptr, nullptr };
     void *dev_out[4] = { nullptr, nullptr, nullptr, nullptr };
+    if (host && nb > 4) { set_error("the pinned-host stage pipeline takes at most four blocks per call"); return BFIR_ERR_INVALID; }
     if (host) {   // input copies first: they are what the call's first kernels wait for
         const int sc = kStage - kStage % nb;
         for (int b = 0; b < nb; b++) {
@@ -956,17 +970,22 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
     m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state; m.ch_base = 0;
     m.use_abs_block = 1; m.abs_block = host_blockcounter;
     const int split = nb == 4 ? quad_split : mac_split;
-    const int mthreads = nb == 4 && rs == 8 ? quad_threads : 256;
+    int mthreads = nb == 4 && rs == 8 ? quad_threads : 256;
     dim3 grid((N / 8 + mthreads / split - 1) / (mthreads / split), Ct);
     mac_kernel_t mk;
-    if (nb == 4) mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split, mthreads);
+    if (nb == 8) {   // eight blocks: a thread owns 4 (double) or 8 (float) reals of a group, one slice
+        mthreads = 128;
+        const int w = rs == 4 ? mac_oct_reals_per_thread<float>() : mac_oct_reals_per_thread<double>();
+        grid = dim3((N / w + mthreads - 1) / mthreads, Ct);
+        mk = rs == 4 ? mac_oct_kernel<float>() : mac_oct_kernel<double>();
+    } else if (nb == 4) mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split, mthreads);
     else mk = rs == 4 ? mac_pair_kernel_for_split<float>(split) : mac_pair_kernel_for_split<double>(split);
     mk<<<grid, mthreads, 0, stream>>>(m);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     prof(2);
     prof(3);
-    if (pidx < pcap) pidx++;
+    prof_next();
     BFIR_CUDA(cudaEventRecord(sp_mac_done[par], stream));
     // inverse transforms on the inverse stream
     BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
@@ -1039,6 +1058,7 @@ int Engine::run_partial_quad(const void *const d_in[4])
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
     for (int k = 0; k < 2; k++) if (!acc_quad[k]) BFIR_CUDA(cudaMalloc(&acc_quad[k], cbuf * Ct));
     int rc = BFIR_OK;
+    prof_nb = 4;
     prof(0);
     prof_suppress = true;
     for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
@@ -1099,7 +1119,7 @@ int Engine::run_finish_quad(void *const d_out[4])
     peer_phase = -1;
     prof_suppress = false;
     prof(3);
-    if (pidx < pcap) pidx++;
+    prof_next();
     for (int b = 0; b < 4; b++) finish_block();
     return rc;
 }
@@ -1139,6 +1159,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
         sp_pairs = 0;
     }
     const int par = (int)(sp_pairs & 1ull);
+    prof_nb = 4;
     tail_ready = false;
     use_abs = true;
     // forward stage
@@ -1243,7 +1264,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
         BFIR_CUDA(cudaGetLastError());
     }
     prof(3);
-    if (pidx < pcap) pidx++;
+    prof_next();
     st_mark(stream);
     BFIR_CUDA(cudaStreamWaitEvent(stream, sp_inv_done[par ^ 1], 0));   // own output stage of call k-1 has read its phase set
     peer_epoch++;
@@ -1280,6 +1301,7 @@ int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
     const Group &grp = groups[g];
     const int s0 = n_groups == 1 ? 0 : grp.s0, ns = n_groups == 1 ? S : grp.s1 - grp.s0;
     int rc = BFIR_OK;
+    if (g == 0) prof_nb = 4;
     if (g == 0) prof(0);
     prof_suppress = true;
     for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(g, d_in[b], nullptr, true); }
@@ -1305,7 +1327,7 @@ int Engine::quad_group(int g, const void *const d_in[4], void *const d_out[4])
     for (int b = 0; b < 4 && rc == BFIR_OK; b++) { acc_override = b == 0 ? nullptr : m.acc_multi[b]; rc = back_group(g, d_out[b]); }
     acc_override = nullptr;
     prof_suppress = false;
-    if (g == 0) { prof(3); if (pidx < pcap) pidx++; }
+    if (g == 0) { prof(3); prof_next(); }
     return rc;
 }
 
@@ -1329,6 +1351,23 @@ int Engine::enqueue_quad(const void *const d_in[4], void *const d_out[4], bool s
     for (int g = 0; g < n_groups && rc == BFIR_OK; g++) rc = quad_group(g, d_in, d_out);
     for (int b = 0; b < 4; b++) finish_block();
     if (rc == BFIR_OK) rc = join();
+    return rc;
+}
+
+// eight consecutive blocks on device buffers through the stage pipeline (joined at the end unless `staged`): ONE
+// eight-block partition-sum launch. One stream group, steady state, enough work for a one-slice kernel; otherwise two
+// four-block calls.
+int Engine::enqueue_oct(const void *const d_in[8], void *const d_out[8], bool staged)
+{
+    int rc;
+    const long long threads_needed = (long long)Ct * (N / (rs == 4 ? 8 : 4));
+    if (!pair_ok() || n_groups != 1 || !staged_enabled || threads_needed < 148LL * 128 * 4) {
+        rc = enqueue_quad(d_in, d_out, staged);
+        if (rc == BFIR_OK) rc = enqueue_quad(d_in + 4, d_out + 4, staged);
+        return rc;
+    }
+    rc = staged_blocks(8, d_in, d_out);
+    if (rc == BFIR_OK && !staged) rc = close_async();
     return rc;
 }
 
@@ -1908,6 +1947,16 @@ long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, 
     return e->impl.run_host_async_pair(in0, in1, out0, out1);
 }
 
+int bfir_run_device_oct(bfir_engine *e, const void *const d_in[8], void *const d_out[8], int staged)
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_in == nullptr || d_out == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 8; b++) if (d_in[b] == nullptr || d_out[b] == nullptr) return BFIR_ERR_INVALID;
+    if (e->impl.peer.enabled) { bfir::set_error("bfir_run_device_oct is not available on a partition shard"); return BFIR_ERR_INVALID; }
+    return e->impl.enqueue_oct(d_in, d_out, staged != 0);
+}
+
 long long bfir_run_async_quad(bfir_engine *e, const void *const in[4], void *const out[4])
 {
     int rc = check_ready(e);
@@ -2155,6 +2204,16 @@ int bfir_set_profiling(bfir_engine *e, int max_blocks)
     g.pev.resize((size_t)max_blocks * 4);
     for (auto &ev : g.pev) BFIR_CUDA(cudaEventCreate(&ev));
     g.pcap = (size_t)max_blocks;
+    return BFIR_OK;
+}
+
+int bfir_get_mac_profile(bfir_engine *e, int blocks_per_launch, double *ms_sum, unsigned long long *launches, int reset)
+{
+    if (e == nullptr || ms_sum == nullptr || launches == nullptr || blocks_per_launch < 1 || blocks_per_launch > 8) return BFIR_ERR_INVALID;
+    Engine &g = e->impl;
+    *ms_sum = g.pmac_by_nb[blocks_per_launch];
+    *launches = g.pcount_by_nb[blocks_per_launch];
+    if (reset) { g.pmac_by_nb[blocks_per_launch] = 0.0; g.pcount_by_nb[blocks_per_launch] = 0; }
     return BFIR_OK;
 }
 

@@ -31,7 +31,7 @@ struct MacArgs {
     int block_offset;        // 0: blockcounter is the current block; used by tests
     int ch_base;             // first channel of this launch (channel-group pipelining)
     void *acc_next;          // pair kernel: accumulated spectrum of block t+1, [channels][N]
-    void *acc_multi[4];      // multi kernel: accumulated spectra of blocks t .. t+NB-1
+    void *acc_multi[8];      // multi / wide kernel: accumulated spectra of blocks t .. t+NB-1
     int use_abs_block;       // 1: block index t = abs_block, given by the host (stage pipeline) instead of the device counter
     unsigned int abs_block;
     int procblocks_bias;     // 1: look-ahead launch for the NEXT block, whose forward transform has not counted itself yet
@@ -323,7 +323,150 @@ __global__ void __launch_bounds__(THREADS) partition_mac_multi_kernel(const MacA
     }
 }
 
+// EIGHT consecutive blocks per launch (bfir_run_device_oct): per channel (2 P_eff + 15) N rs bytes for eight blocks, i.e.
+// 9.9 spectra per block at P = 32 where four blocks per launch move 17.75 and one block per launch 65. Eight accumulators
+// and an eight-deep window of delay-line spectra do not fit the registers of a thread that owns a whole ORD group in
+// double precision, so a thread owns W reals of a group: W = 4 in single precision (bins 2h, 2h+1 of the group =
+// [Re, Re | Im, Im]: two 8-byte loads per spectrum), W = 2 in double precision (one bin: two 8-byte loads; 148 registers,
+// three CTAs of 128 threads per SM, the eight partitions of a loop body requested before the first is used). Wider
+// threads were measured and are slower (fewer CTAs per SM, fewer loads in flight). The window is a circular buffer indexed at
+// compile time: the body handles eight partitions, partition i+u loading X[t-i-u] into slot (-u) & 7 -- the slot whose
+// spectrum X[t-i+8-u] no later step needs -- and block b reading slot (b-u) & 7, so nothing is ever moved.
+// One slice per group (large batches); grid (ceil(N/W / THREADS), channels).
+template <class T, int W> __device__ __forceinline__ void ldw(const T *p, T (&r)[W])
+{
+    if constexpr (W == 8) { ld8(p, r); }
+    else if constexpr (W == 2) { r[0] = __ldg(p); r[1] = __ldg(p + 4); }
+    else if constexpr (sizeof(T) == 8) {
+        const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p + 4));
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+    } else {
+        const float2 a = __ldg(reinterpret_cast<const float2 *>(p)), b = __ldg(reinterpret_cast<const float2 *>(p + 4));
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+    }
+}
+template <class T, int W> __device__ __forceinline__ void stw(T *p, const T (&r)[W])
+{
+    if constexpr (W == 8) { st8(p, r); }
+    else if constexpr (W == 2) { p[0] = r[0]; p[4] = r[1]; }
+    else if constexpr (sizeof(T) == 8) {
+        *reinterpret_cast<double2 *>(p) = make_double2(r[0], r[1]); *reinterpret_cast<double2 *>(p + 4) = make_double2(r[2], r[3]);
+    } else {
+        *reinterpret_cast<float2 *>(p) = make_float2(r[0], r[1]); *reinterpret_cast<float2 *>(p + 4) = make_float2(r[2], r[3]);
+    }
+}
+template <class T, int W> __device__ __forceinline__ void macw(T (&acc)[W], const T (&b)[W], const T (&c)[W])
+{
+    constexpr int H = W / 2;
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+        acc[j] = fma(b[j], c[j], acc[j]);
+        acc[j] = fma(-b[j + H], c[j + H], acc[j]);
+        acc[j + H] = fma(b[j], c[j + H], acc[j + H]);
+        acc[j + H] = fma(b[j + H], c[j], acc[j + H]);
+    }
+}
+
+template <class T, int W, int THREADS, int AHEAD>
+__global__ void __launch_bounds__(THREADS) partition_mac_oct_kernel(const MacArgs a)
+{
+    constexpr int NB = 8, HALVES = 8 / W, H = W / 2;
+    const int q = blockIdx.x * THREADS + threadIdx.x;
+    const int g = q / HALVES, h = q - g * HALVES;
+    const int ch = blockIdx.y + a.ch_base;
+    if (g * 8 >= a.N) return;
+    const unsigned int t = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.block_offset;
+    const int cs_ = a.coeff_map ? a.coeff_map[ch] : ch;
+    const int peff = min(a.coeff_blocks[cs_], a.n_parts);
+    const int i0 = a.part_begin, i1 = min(peff, a.part_begin + a.part_count);
+    const long long off = (long long)g * 8 + h * H;                 // W = 4: reals [2h, 2h+1] and [4+2h, 4+2h+1] of the group
+    const T *fdl = (const T *)a.fdl + ch * a.fdl_stride_ch + off;
+    const T *cf = (const T *)a.coeffs + cs_ * a.coeff_stride_ch + off;
+    const unsigned int P = (unsigned int)a.n_slots;
+
+    T acc[NB][W], xs[NB][W];
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+#pragma unroll
+        for (int j = 0; j < W; j++) acc[b][j] = (T)0;
+    if (i0 < i1) {
+#pragma unroll
+        for (int d = 1; d < NB; d++) ldw<T, W>(fdl + (long long)((t + (unsigned int)d - (unsigned int)i0) % P) * a.N, xs[d]);
+        for (int i = i0; i < i1; i += NB) {
+#pragma unroll
+            for (int grp = 0; grp < NB / AHEAD; grp++) {
+                // AHEAD partitions' operands are requested before the first of them is used: with two CTAs of 128 threads
+                // per SM that is 64 KB in flight per SM, what the four-block kernel keeps in flight too
+                T xn[AHEAD][W], cn[AHEAD][W];
+#pragma unroll
+                for (int k = 0; k < AHEAD; k++) {
+                    const int u = grp * AHEAD + k;
+                    if (i + u < i1) {
+                        ldw<T, W>(fdl + (long long)((t - (unsigned int)(i + u)) % P) * a.N, xn[k]);
+                        ldw<T, W>(cf + (long long)(i + u) * a.N, cn[k]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < AHEAD; k++) {
+                    const int u = grp * AHEAD + k;
+                    if (i + u < i1) {
+#pragma unroll
+                        for (int j = 0; j < W; j++) xs[(NB - u) & (NB - 1)][j] = xn[k][j];
+#pragma unroll
+                        for (int b = 0; b < NB; b++) macw<T, W>(acc[b], xs[(b - u + NB) & (NB - 1)], cn[k]);
+                    }
+                }
+            }
+        }
+    }
+    T *dst[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        dst[b] = a.push.enabled ? peer_dst<T>(a.push, ch, a.N, (unsigned int)(a.push_phase + b)) : (T *)a.acc_multi[b] + (long long)ch * a.N;
+        stw<T, W>(dst[b] + off, acc[b]);
+    }
+    // The real DC and Nyquist bins (slots 0 and 4 of group 0) are products of reals (fftw_convolver.cpp:1507-1508), not
+    // the complex product the thread above has just stored for "bin 0": the one thread that owns them walks the
+    // partitions once more with scalars and overwrites the two slots (same accumulation order as the other kernels).
+    if (g == 0 && h == 0 && i0 < i1) {
+        T d0[NB], d4[NB], w0[NB], w4[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) { d0[b] = (T)0; d4[b] = (T)0; w0[b] = (T)0; w4[b] = (T)0; }
+#pragma unroll
+        for (int d = 1; d < NB; d++) {
+            const T *x = fdl + (long long)((t + (unsigned int)d - (unsigned int)i0) % P) * a.N;
+            w0[d] = __ldg(x); w4[d] = __ldg(x + 4);
+        }
+        for (int i = i0; i < i1; i++) {
+            const T *x = fdl + (long long)((t - (unsigned int)i) % P) * a.N, *c = cf + (long long)i * a.N;
+            w0[0] = __ldg(x); w4[0] = __ldg(x + 4);
+            const T c0 = __ldg(c), c4 = __ldg(c + 4);
+#pragma unroll
+            for (int b = 0; b < NB; b++) { d0[b] = fma(w0[b], c0, d0[b]); d4[b] = fma(w4[b], c4, d4[b]); }
+#pragma unroll
+            for (int b = NB - 1; b > 0; b--) { w0[b] = w0[b - 1]; w4[b] = w4[b - 1]; }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) { dst[b][0] = d0[b]; dst[b][4] = d4[b]; }
+    }
+}
+
 typedef void (*mac_kernel_t)(const MacArgs);
+// reals per thread: BFIR_OCT_W overrides (measurement)
+template <class T> inline int mac_oct_reals_per_thread()
+{
+    static const int forced = [] { const char *env = getenv("BFIR_OCT_W"); return env ? atoi(env) : 0; }();
+    // measured (tools/kernel_times.py --octs): double cfg1 x 16 W = 2 0.229 ms per launch (0.88 of the HBM peak on the bytes
+    // that must move), W = 4 0.326 (224 registers, two CTAs per SM); float cfg3 shape W = 4 0.575 ms (0.84), W = 8 0.766
+    if (sizeof(T) == 8) return forced == 4 ? 4 : 2;
+    return forced == 8 ? 8 : 4;
+}
+template <class T> inline mac_kernel_t mac_oct_kernel()
+{
+    const int w = mac_oct_reals_per_thread<T>();
+    if constexpr (sizeof(T) == 8) { if (w == 2) return partition_mac_oct_kernel<T, 2, 128, 8>; return partition_mac_oct_kernel<T, 4, 128, 4>; }
+    else { if (w == 4) return partition_mac_oct_kernel<T, 4, 128, 8>; return partition_mac_oct_kernel<T, 8, 128, 4>; }
+}
 // four blocks per launch. Shared memory of the slice reduction: (SPLIT-1) * 256/SPLIT * 32 reals, i.e. <= 32 KB in
 // single precision and 48 KB at SPLIT 4 in double precision (the static limit), so double stops at SPLIT 4
 template <class T> inline mac_kernel_t mac_quad_kernel_for_split(int split, int threads = 256)

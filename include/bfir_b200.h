@@ -203,6 +203,12 @@ long long bfir_run_async_pair(bfir_engine *e, const void *in0, const void *in1, 
  * filling the call runs two pairs (or four single blocks); a crossbar (bfir_set_crossbar) is part of the stages. */
 int bfir_run_device_quad(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 int bfir_run_device_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
+/* EIGHT consecutive blocks with one partition-sum launch (both precisions): per channel (2P + 15) N realsize bytes for
+ * eight blocks -- 9.9 spectra per block at P = 32 against 17.75 with four blocks per launch and 65 with one. Always
+ * through the stage pipeline; `staged` = 0 joins at the end of the call (like bfir_run_device), `staged` != 0 leaves the
+ * pipeline open under the contract of BFIR_PAIR_STAGED. One stream group, steady state and at least ~75 000 threads of
+ * work; otherwise the call runs two four-block calls. The delay line keeps filter_blocks + 15 slots for it. */
+int bfir_run_device_oct(bfir_engine *e, const void *const d_in[8], void *const d_out[8], int staged);
 /* Four consecutive blocks of PINNED host buffers through the stage pipeline (one stream group; otherwise, and outside
  * the steady state, two bfir_run_async_pair calls): the input copies of block b, its forward transform, the four-block
  * partition sum, the inverse transforms and the output copies run on five streams chained by events over a ring of 12
@@ -283,6 +289,9 @@ int bfir_set_stream(bfir_engine *e, void *cuda_stream);
  * as of the last bfir_sync / bfir_run, optionally clearing the sums. */
 int bfir_set_profiling(bfir_engine *e, int max_blocks);
 int bfir_get_profile(bfir_engine *e, double ms_out[3], unsigned long long *blocks, int reset);
+/* the partition-sum part of the profile, per kernel family: summed launch time and number of profiled launches of the
+ * partition sums that covered `blocks_per_launch` (1, 2, 4 or 8) blocks */
+int bfir_get_mac_profile(bfir_engine *e, int blocks_per_launch, double *ms_sum, unsigned long long *launches, int reset);
 
 /* pinfo / set_print_callback (brutefir/pinfo.h:17-18) */
 void bfir_set_print_callback(void (*cb)(const char *message));

@@ -843,6 +843,70 @@ def test_stage_pipeline_quads_equal_single_blocks(pkg, rs, out_fmt, P):
             assert dd.max() <= 1, (b, dd.max())      # S16 from the float engine, S24 from the double one: within 1 LSB
 
 
+@pytest.mark.parametrize("rs,out_fmt,P,S,C,xb", [(8, 10, 5, 20, 4, 0), (4, 8, 5, 40, 4, 0), (8, 10, 2, 20, 4, 0), (4, 2, 9, 40, 4, 0),
+                                                 (8, 4, 3, 24, 4, 0), (4, 8, 4, 8, 32, 32), (4, 8, 6, 2, 2, 0)])
+def test_eight_blocks_per_call_equal_single_blocks(pkg, rs, out_fmt, P, S, C, xb):
+    """bfir_run_device_oct: eight blocks per call with ONE partition-sum launch (partition_mac_oct_kernel: a thread owns
+    8 reals of an ORD group in single precision, 4 in double precision, circular window of eight delay-line spectra),
+    joined and staged, mixed with four- and two-block calls and single blocks, with a crossbar, with integer output;
+    the last case is too small for the one-slice kernel and falls back to two four-block calls. P = 2 turns every delay-line
+    slot over within one call (P + 15 slots). Same output as block by block."""
+    import torch
+    L = 2048
+    in_fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
+    dt = np.float32 if rs == 4 else np.float64
+    nb = pkg.FORMAT_BYTES[out_fmt]
+    n_in = xb or C
+    n_out = xb or C
+    h = [decay_filter(c % 7, L * P) * (1 + 0.01 * c) for c in range(C * S)]
+    kw = dict(n_streams=S, n_groups=1)
+    if xb:
+        kw.update(xbar_inputs=xb, xbar_outputs=xb)
+    single = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, False, **kw)
+    octs = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, False, **kw)
+    assert single.set_coeff(h, P) == 0 and octs.set_coeff(h, P) == 0
+    if xb:
+        rng = np.random.default_rng(3)
+        gin, gout = rng.standard_normal((C, xb)) / np.sqrt(xb), rng.standard_normal((xb, C)) / np.sqrt(C)
+        single.set_crossbar(gin, gout)
+        octs.set_crossbar(gin, gout)
+    nblk = 8 * 6 + 4 + 2 + 2
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    tdt = torch.float32 if rs == 4 else torch.float64
+    d_in = [torch.rand(S * L * n_in, dtype=tdt, device="cuda", generator=gen) * 2 - 1 for _ in range(nblk)]
+    n_o = S * L * n_out * nb
+    out_s = [torch.zeros(n_o, dtype=torch.uint8, device="cuda") for _ in range(nblk)]
+    out_t = [torch.zeros(n_o, dtype=torch.uint8, device="cuda") for _ in range(nblk)]
+    torch.cuda.synchronize()
+    for b in range(nblk):
+        single.run_device(d_in[b], out_s[b])
+    b = 0
+    for call in range(6):
+        if call == 2:                                # a staged four-block and a staged two-block call in between
+            octs.run_device_quad(d_in[b:b + 4], out_t[b:b + 4], staged=True)
+            b += 4
+            octs.run_device_pair(d_in[b], d_in[b + 1], out_t[b], out_t[b + 1], pipelined="staged")
+            b += 2
+        if call == 4:                                # single blocks (close the pipeline), then a JOINED eight-block call
+            for _ in range(2):
+                octs.run_device(d_in[b], out_t[b])
+                b += 1
+        octs.run_device_oct(d_in[b:b + 8], out_t[b:b + 8], staged=(call != 4))
+        b += 8
+        if call == 1:
+            octs.join()
+    assert b == nblk
+    assert single.sync() == 0 and octs.sync() == 0
+    assert single.blockcounter() == octs.blockcounter() == nblk
+    for b in range(nblk):
+        a, t = out_s[b].cpu().numpy(), out_t[b].cpu().numpy()
+        if out_fmt in (8, 10):
+            assert rel_rms(t.view(dt), a.view(dt)) < (2e-6 if rs == 4 else 1e-13), b
+        else:
+            dd = np.abs(decode_raw(a, out_fmt, n_out).ravel().astype(np.float64) - decode_raw(t, out_fmt, n_out).ravel())
+            assert dd.max() <= 1, (b, dd.max())
+
+
 @pytest.mark.parametrize("rs,groups,P", [(8, 1, 5), (4, 1, 2), (4, 1, 7), (8, 3, 4)])
 def test_host_quads_equal_single_blocks(pkg, rs, groups, P):
     """bfir_run_async_quad: four blocks of pinned host buffers per call through the stage pipeline (input copies, forward

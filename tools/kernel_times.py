@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--tag", default="")
     ap.add_argument("--quads", action="store_true", help="four blocks per call (bfir_run_device_quad, single precision)")
+    ap.add_argument("--octs", action="store_true", help="eight blocks per call (bfir_run_device_oct, joined): only the partition-sum time is meaningful")
     ap.add_argument("--pairs", action="store_true", help="two blocks per call (bfir_run_device_pair); times are per PAIR then")
     a = ap.parse_args()
     import torch
@@ -48,6 +49,21 @@ def main():
     for b in range(a.P + 5):
         eng.run_device(d_in[b % 4], d_out)
     assert eng.sync() == 0
+    if a.octs:
+        outs = [d_out] + [torch.empty_like(d_out) for _ in range(7)]
+        eng.run_device_oct(d_in + d_in, outs)
+        assert eng.sync() == 0
+        eng.get_mac_profile(8)
+        eng.set_profiling(a.steps // 8)
+        for b in range(0, a.steps, 8):
+            eng.run_device_oct(d_in + d_in, outs)
+        assert eng.sync() == 0
+        ms8, n8 = eng.get_mac_profile(8)
+        Ct_, N_ = a.streams * a.channels, 2 * a.L
+        need = (2 * a.P + 15) * N_ * a.realsize * Ct_
+        print(json.dumps({"tag": a.tag, "oct_w": os.environ.get("BFIR_OCT_W"), "mac_ms_per_launch": ms8 / max(n8, 1), "mac_ms_per_block": ms8 / max(n8, 1) / 8,
+                          "launches": n8, "frac_of_6545_on_bytes_needed": need / (ms8 / max(n8, 1) * 1e-3) / 1e9 / 6545.3}))
+        return
     if a.quads:
         outs = [d_out] + [torch.empty_like(d_out) for _ in range(3)]
         eng.run_device_quad(d_in, outs)
