@@ -79,6 +79,7 @@ API = [
     ("bfir_run_partial_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
     ("bfir_run_finish_quad_device", _ci, [_vp, ctypes.POINTER(_vp)]),
     ("bfir_run_shard_quad_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    ("bfir_run_shard_oct_staged", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_run_async_quad", ctypes.c_longlong, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     ("bfir_run_device_oct", _ci, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _ci]),
     ("bfir_get_mac_profile", _ci, [_vp, _ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_ulonglong), _ci]),
@@ -376,6 +377,12 @@ class Brutefir:
         a = (_vp * 4)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
         b = (_vp * 4)(*[_ptr(x) for x in d_outs])
         _check(self.lib.bfir_run_shard_quad_staged(self.h, a, b))
+
+    def run_shard_oct_staged(self, d_ins, d_outs):
+        """the eight-block shard call through the stage pipeline (bfir_run_shard_oct_staged)"""
+        a = (_vp * 8)(*[_buf(x, self.in_bytes, "d_in") for x in d_ins])
+        b = (_vp * 8)(*[_ptr(x) for x in d_outs])
+        _check(self.lib.bfir_run_shard_oct_staged(self.h, a, b))
 
     def run_async_quad(self, ins, outs):
         """Four consecutive blocks of PINNED host buffers through the stage pipeline; returns the ticket of the fourth."""

@@ -43,7 +43,8 @@ struct Engine {
     int *d_peer_timeout = nullptr;  // set by peer_wait_kernel when a source rank never arrived
     int run_partial_quad(const void *const d_in[4]);
     int run_finish_quad(void *const d_out[4]);
-    int shard_quad_staged(const void *const d_in[4], void *const d_out[4]);
+    int shard_blocks_staged(int nb, const void *const *d_in, void *const *d_out);
+    void *acc_oct[4] = {};          // accumulated spectra of blocks 5 .. 8 of an eight-block shard call
     cudaEvent_t sp_arrived[2] = {};  // staged shard calls: every source rank's flag of call k has been seen (inverse stream)
     int peer_setup(int rank, int world);
     int peer_ready() const { if (!peer.enabled) return 1; for (int q = 0; q < peer.world; q++) if (!peer.recv[q]) return 0; return 1; }
@@ -453,9 +454,9 @@ void Engine::destroy()
     if (recv) { cudaFree(recv); recv = nullptr; }
     for (int k = 1; k < kStage; k++) { if (stage_in[k]) cudaFree(stage_in[k]); if (stage_out[k]) cudaFree(stage_out[k]); stage_in[k] = stage_out[k] = nullptr; }
     stage_in[0] = stage_out[0] = nullptr;
-    void *bufs[] = { d_peer_timeout, coeff_map, acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
+    void *bufs[] = { acc_oct[0], acc_oct[1], acc_oct[2], acc_oct[3], d_peer_timeout, coeff_map, acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
-    acc_pair = nullptr; acc_quad[0] = acc_quad[1] = nullptr;
+    acc_pair = nullptr; acc_quad[0] = acc_quad[1] = nullptr; acc_oct[0] = acc_oct[1] = acc_oct[2] = acc_oct[3] = nullptr;
     fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
     state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; coeff_map = nullptr; d_peer_timeout = nullptr; pb_inc = nullptr; stats = nullptr;
     if (h_state) cudaFreeHost(h_state);
@@ -1067,7 +1068,7 @@ int Engine::run_partial_quad(const void *const d_in[4])
     if (rc != BFIR_OK) return rc;
     prof(1);
     tail_ready = false;
-    const int base = 2 + (int)(peer_epoch & 1u) * 4;
+    const int base = 2 + (int)(peer_epoch & 1u) * 8;
     MacArgs m = {};
     m.fdl = fdl; m.coeffs = coeffs;
     m.acc_multi[0] = acc; m.acc_multi[1] = acc_pair; m.acc_multi[2] = acc_quad[0]; m.acc_multi[3] = acc_quad[1];
@@ -1112,7 +1113,7 @@ int Engine::run_finish_quad(void *const d_out[4])
     peer_wait_kernel<<<1, 32, 0, stream>>>(peer, peer_epoch, d_peer_timeout, peer.flag_offset);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
-    const int base = 2 + (int)((peer_epoch - 1u) & 1u) * 4;
+    const int base = 2 + (int)((peer_epoch - 1u) & 1u) * 8;
     int rc = BFIR_OK;
     prof_suppress = true;
     for (int b = 0; b < 4 && rc == BFIR_OK; b++) { peer_phase = base + b; rc = back_group(0, d_out[b]); }
@@ -1136,7 +1137,7 @@ int Engine::run_finish_quad(void *const d_out[4])
 // pushes of call k only after it has seen this rank's flag of call k-1, and that flag is raised only after this
 // rank's output stage of call k-2 has read the set: no collective, no host synchronisation, and the three stages of
 // neighbouring calls overlap on every rank.
-int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
+int Engine::shard_blocks_staged(int nb, const void *const *d_in, void *const *d_out)
 {
     if (!peer.enabled || !peer_ready()) { set_error("shard_quad_staged needs a connected peer shard"); return BFIR_ERR_INVALID; }
     if (peer_quad_pending) { set_error("run_partial_quad is pending: finish it first"); return BFIR_ERR_INVALID; }
@@ -1144,6 +1145,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     const size_t cbuf = (size_t)N * rs;
     if (!acc_pair) BFIR_CUDA(cudaMalloc(&acc_pair, cbuf * Ct));
     for (int k = 0; k < 2; k++) if (!acc_quad[k]) BFIR_CUDA(cudaMalloc(&acc_quad[k], cbuf * Ct));
+    if (nb == 8) for (int k = 0; k < 4; k++) if (!acc_oct[k]) BFIR_CUDA(cudaMalloc(&acc_oct[k], cbuf * Ct));
     int rc;
     if (!sp_open) {
         if ((rc = close_async()) != BFIR_OK) return rc;
@@ -1159,20 +1161,20 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
         sp_pairs = 0;
     }
     const int par = (int)(sp_pairs & 1ull);
-    prof_nb = 4;
+    prof_nb = nb;
     tail_ready = false;
     use_abs = true;
     // forward stage
     BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, sp_mac_done[par], 0));
     st_mark(sp_fwd);
     rc = BFIR_OK;
-    if (xbar && peer.xin_offset != 0) {
+    if (xbar && peer.xin_offset != 0 && nb == 4) {
         // SHARDED input stage: this rank transforms only its own inputs (own_in_count CTAs instead of Ci), stores the
         // spectra into every peer's input region -- phase (call parity, block) -- and raises its input flag; once every
         // rank's flag of this call is in, the whole input crossbar runs on the gathered spectra. All on the forward
         // stream, so a rank's input flag of call k+1 also says that its crossbar of call k has read phase set k & 1,
         // which its peers overwrite with call k+2 only after they have seen that flag.
-        const int ibase = (int)(peer_in_epoch & 1u) * 4;
+        const int ibase = (int)(peer_in_epoch & 1u) * 4;   // (sharded inputs: four-block calls only, see bfir_run_shard_oct_staged)
         char *xin_all = (char *)recv + peer.xin_offset;
         const long long row_bytes = (long long)N * rs;
         for (int b = 0; b < 4; b++) {
@@ -1218,7 +1220,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     } else {
         stage_stream = sp_fwd;
         prof_suppress = true;
-        for (int b = 0; b < 4 && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
+        for (int b = 0; b < nb && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
         fwd_block_offset = 0;
         prof_suppress = false;
         stage_stream = nullptr;
@@ -1232,27 +1234,34 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     st_mark(stream);
     prof(0);
     prof(1);
-    const int base = 2 + (int)(peer_epoch & 1u) * 4;
+    const int base = 2 + (int)(peer_epoch & 1u) * 8;
     MacArgs m = {};
     m.fdl = fdl; m.coeffs = coeffs;
     m.acc_multi[0] = acc; m.acc_multi[1] = acc_pair; m.acc_multi[2] = acc_quad[0]; m.acc_multi[3] = acc_quad[1];
+    for (int k = 0; k < 4; k++) m.acc_multi[4 + k] = acc_oct[k];
     m.fdl_stride_ch = (long long)Pslots * N; m.coeff_stride_ch = (long long)coeff_alloc * N;
     m.N = N; m.n_slots = Pslots; m.n_parts = P; m.part_begin = part_begin; m.part_count = part_count;
     m.coeff_blocks = coeff_blocks; m.coeff_map = coeff_map; m.procblocks = procblocks; m.state = state; m.block_offset = 0; m.ch_base = 0;
     m.use_abs_block = 1; m.abs_block = host_blockcounter;
     if (!xbar) { m.push = peer; m.push_phase = base; }
-    const int mthreads = rs == 8 ? quad_threads : 256;
+    int mthreads = rs == 8 ? quad_threads : 256;
     int split = quad_split;
     while (split > 1 && split * 4 > part_count) split >>= 1;
     dim3 grid((N / 8 + mthreads / split - 1) / (mthreads / split), Ct);
     mac_kernel_t mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split, mthreads);
+    if (nb == 8) {
+        mthreads = 128;
+        const int w = rs == 4 ? mac_oct_reals_per_thread<float>() : mac_oct_reals_per_thread<double>();
+        grid = dim3((N / w + mthreads - 1) / mthreads, Ct);
+        mk = rs == 4 ? mac_oct_kernel<float>() : mac_oct_kernel<double>();
+    }
     mk<<<grid, mthreads, 0, stream>>>(m);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     prof(2);
     st_mark(stream);
     if (xbar) {
-        for (int b = 0; b < 4; b++) {
+        for (int b = 0; b < nb; b++) {
             XbarArgs x = {};
             x.in = m.acc_multi[b]; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
             x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = S; x.stream_base = 0;
@@ -1282,7 +1291,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     BFIR_CUDA(cudaEventRecord(sp_arrived[par], sp_inv));
     stage_stream = sp_inv;
     prof_suppress = true;
-    for (int b = 0; b < 4 && rc == BFIR_OK; b++) { peer_phase = base + b; rc = back_group(0, d_out[b]); }
+    for (int b = 0; b < nb && rc == BFIR_OK; b++) { peer_phase = base + b; rc = back_group(0, d_out[b]); }
     peer_phase = -1;
     prof_suppress = false;
     stage_stream = nullptr;
@@ -1291,7 +1300,7 @@ int Engine::shard_quad_staged(const void *const d_in[4], void *const d_out[4])
     st_mark(sp_inv);
     BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
     sp_pairs++;
-    for (int b = 0; b < 4; b++) finish_block();
+    for (int b = 0; b < nb; b++) finish_block();
     return BFIR_OK;
 }
 
@@ -2029,7 +2038,20 @@ int bfir_run_shard_quad_staged(bfir_engine *e, const void *const d_in[4], void *
     if (rc != BFIR_OK) return rc;
     if (d_in == nullptr || d_out == nullptr) return BFIR_ERR_INVALID;
     for (int b = 0; b < 4; b++) if (d_in[b] == nullptr || d_out[b] == nullptr) return BFIR_ERR_INVALID;
-    return e->impl.shard_quad_staged(d_in, d_out);
+    return e->impl.shard_blocks_staged(4, d_in, d_out);
+}
+
+int bfir_run_shard_oct_staged(bfir_engine *e, const void *const d_in[8], void *const d_out[8])
+{
+    int rc = check_ready(e);
+    if (rc != BFIR_OK) return rc;
+    if (d_in == nullptr || d_out == nullptr) return BFIR_ERR_INVALID;
+    for (int b = 0; b < 8; b++) if (d_in[b] == nullptr || d_out[b] == nullptr) return BFIR_ERR_INVALID;
+    if ((long long)e->impl.Ct * (e->impl.N / (e->impl.rs == 4 ? 4 : 2)) < 148LL * 128 * 4) {   // too small for the one-slice kernel
+        rc = e->impl.shard_blocks_staged(4, d_in, d_out);
+        return rc == BFIR_OK ? e->impl.shard_blocks_staged(4, d_in + 4, d_out + 4) : rc;
+    }
+    return e->impl.shard_blocks_staged(8, d_in, d_out);
 }
 
 int bfir_peer_setup(bfir_engine *e, int rank, int world)

@@ -39,9 +39,10 @@ enum {
 // straight into the receive buffer of the rank that owns `ch` -- a peer-mapped pointer, i.e. plain
 // st.global over NVLink -- so the transfer overlaps the partition sum tile by tile. Receive buffer
 // of rank q: [BFIR_PEER_PHASES][world (source rank)][cpr (owned channels)][N], then one arrival flag per source
-// rank. Phases 0 / 1: block parity of the one-block calls; phases 2 .. 9: (call parity, block) of the four-block calls.
+// rank. Phases 0 / 1: block parity of the one-block calls; phases 2 .. 17: (call parity, block) of the four- and eight-block calls
+// (phase 2 + 8 parity + b; consecutive calls differ in parity).
 #define BFIR_MAX_PEERS 8
-#define BFIR_PEER_PHASES 10
+#define BFIR_PEER_PHASES 18
 struct PeerPush {
     void *recv[BFIR_MAX_PEERS];
     int world, self, cpr, enabled;

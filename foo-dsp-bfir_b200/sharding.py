@@ -131,6 +131,10 @@ class FusedPartitionShardedEngine:
         the outputs."""
         self.engine.run_shard_quad_staged(d_ins, d_outs_own)
 
+    def run_device_oct_staged(self, d_ins, d_outs_own):
+        """Eight blocks per call through the stage pipeline (bfir_run_shard_oct_staged)."""
+        self.engine.run_shard_oct_staged(d_ins, d_outs_own)
+
     def join(self):
         return self.engine.join()
 

@@ -255,6 +255,9 @@ int bfir_run_finish_quad_device(bfir_engine *e, void *const d_out[4]);
  * (a second flag array orders it), then applies the whole input crossbar. Off by default: measured slower than the
  * redundant input stage on 2 and on 8 GPUs. */
 int bfir_run_shard_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
+/* The same with EIGHT blocks per call (one eight-block partition sum over the rank's partitions; shards too small for
+ * that kernel run two four-block calls). The input stage is never sharded here. */
+int bfir_run_shard_oct_staged(bfir_engine *e, const void *const d_in[8], void *const d_out[8]);
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
 
 /* Fused partition-shard reduce (no reference counterpart; SURVEY 8e "fused variant"). After

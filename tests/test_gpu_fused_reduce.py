@@ -143,7 +143,7 @@ def test_two_emulated_ranks_four_blocks_per_call(pkg, rs, L, P, C, xb):
 
 @pytest.mark.parametrize("rs,L,P,C,xb,shard_inputs", [(4, 512, 6, 4, (0, 0), 0), (8, 256, 4, 5, (0, 0), 0), (4, 1024, 8, 4, (3, 5), 0),
                                                       (4, 2048, 16, 8, (8, 8), 0), (4, 1024, 8, 4, (3, 5), 1), (4, 2048, 16, 8, (8, 8), 1),
-                                                      (8, 512, 5, 6, (4, 4), 1)])
+                                                      (8, 512, 5, 6, (4, 4), 1), (4, 16384, 4, 12, (0, 0), 0), (8, 8192, 3, 12, (6, 6), 0)])
 def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb, shard_inputs, monkeypatch):
     """bfir_run_shard_quad_staged: the four-block shard call through the stage pipeline (forward transforms, partition
     sum + pushes, arrival wait + output stage of neighbouring calls on three streams per rank; receive-buffer phases
@@ -177,7 +177,7 @@ def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb, shard_input
             if q != r:
                 e.peer_set_ptr(q, other.peer_recv_ptr())
     own = [e.peer_own_channels() for e in ranks]
-    nb = P + 4 * 8 + 1
+    nb = P + 4 * 8 + 1 + 8 * 3
     x = white_noise(3, nb * L, n_in).astype(dt)
     d_in = [torch.from_numpy(np.ascontiguousarray(x[b * L:(b + 1) * L]).ravel()).cuda() for b in range(nb)]
     d_ref = [torch.empty(L * n_out, dtype=tdt, device="cuda") for _ in range(nb)]
@@ -212,6 +212,10 @@ def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb, shard_input
             for e, o in zip(ranks, d_own):
                 e.run_shard_quad_staged(d_in[b:b + 4], o[b:b + 4])
         b += 4
+    for call in range(3):                                     # eight blocks per call (two four-block calls where the shard is too small)
+        for e, o in zip(ranks, d_own):
+            e.run_shard_oct_staged(d_in[b:b + 8], o[b:b + 8])
+        b += 8
     assert b == nb
     for e in ranks + [full]:
         assert e.sync() == 0

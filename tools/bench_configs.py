@@ -134,8 +134,8 @@ def dither_timing(pkg, torch, streams=1, blocks=400):
 
 def throughput_cfg3(pkg, torch, peak_gbs, total_streams=4096, world=1, rank=0, steps=40, max_over_ranks=None, barrier=None):
     """cfg3: `total_streams` independent stereo float streams x 65536 taps (L 4096, P 16, distinct filter per channel),
-    stream-sharded over the ranks (no collective); four blocks per partition-sum launch (bfir_run_device_quad).
-    Returns whole-job Msamples/s (all ranks) and the roofline of the quad partition-sum kernel."""
+    stream-sharded over the ranks (no collective); EIGHT blocks per partition-sum launch through the stage pipeline
+    (bfir_run_device_oct, staged). Returns whole-job Msamples/s (all ranks) and the roofline of the eight-block kernel."""
     L, P, C = 4096, 16, 2
     base, extra = divmod(total_streams, world)
     S = base + (1 if rank < extra else 0)
@@ -146,37 +146,45 @@ def throughput_cfg3(pkg, torch, peak_gbs, total_streams=4096, world=1, rank=0, s
     assert e.set_coeff_device(h, L * P, Ct, L * P, P) == 0
     del h
     d_in = [torch.rand(S * L * C, dtype=torch.float32, device="cuda") * 2 - 1 for _ in range(4)]
-    d_out = [torch.empty(S * L * C, dtype=torch.float32, device="cuda") for _ in range(4)]
+    d_out = [torch.empty(S * L * C, dtype=torch.float32, device="cuda") for _ in range(8)]
     torch.cuda.synchronize()
     for b in range(P):
         e.run_device(d_in[b % 4], d_out[0])
-    e.run_device_quad(d_in, d_out)
+    e.run_device_oct(d_in + d_in, d_out, staged=True)
+    e.join()
     assert e.sync() == 0
-    steps -= steps % 4
-    e.set_profiling(steps // 4)
+    steps -= steps % 8
+    e.get_mac_profile(8)
+    e.set_profiling(steps // 8)
     if barrier:
         barrier()
     t0 = time.perf_counter()
-    for b in range(0, steps, 4):
-        e.run_device_quad(d_in, d_out)
+    for b in range(0, steps, 8):
+        e.run_device_oct(d_in + d_in, d_out, staged=True)
+    e.join()
     assert e.sync() == 0
     dt = time.perf_counter() - t0
     if barrier:
         barrier()
     if max_over_ranks:
         dt = max_over_ranks(dt)
+    ms8, n8 = e.get_mac_profile(8)
+    # the transforms' share: the same calls with four blocks per launch, joined (per-kernel event times are separable there)
+    e.set_profiling(2)
+    for k in range(2):
+        e.run_device_quad(d_in, d_out[:4])
+    assert e.sync() == 0
     prof, n = e.get_profile()
-    split = e.get_mac_split()
     e.close()
-    mac_ms = prof["mac_ms"] / max(n, 1)                     # one launch = four blocks of every channel
+    mac_ms = ms8 / max(n8, 1)                              # one launch = eight blocks of every channel
     N, rs = 2 * L, 4
-    needed = (2 * P + 7) * N * rs * Ct                      # P coefficient + (P + 3) delay-line spectra in, 4 out
-    algorithmic_8d = 4 * (2 * P + 1) * N * rs * Ct          # four one-block partition sums
+    needed = (2 * P + 15) * N * rs * Ct                     # P coefficient + (P + 7) delay-line spectra in, 8 out
+    algorithmic_8d = 8 * (2 * P + 1) * N * rs * Ct          # eight one-block partition sums
     return {"workload": "cfg3: %d independent stereo float streams x 65536 taps (L 4096, P 16), distinct filters, stream-sharded over %d GPU(s)" % (total_streams, world),
             "streams_this_rank": S, "value": total_streams * C * L * steps / dt / 1e6, "unit": "Msamples/s (all ranks)",
-            "ms_per_step": 1e3 * dt / steps, "steps": steps, "api": "bfir_run_device_quad (four blocks per partition-sum launch), wall clock around %d blocks incl. sync" % steps,
-            "step_share_ms_per_block": {k: v / max(n, 1) / 4 for k, v in prof.items()},
-            "roofline": {"kernel": "partition_mac_multi_kernel<float,4,SPLIT=%d>" % split, "bound": "hbm", "avg_launch_ms": mac_ms,
+            "ms_per_step": 1e3 * dt / steps, "steps": steps, "api": "bfir_run_device_oct, staged (eight blocks per partition-sum launch) + bfir_join, wall clock around %d blocks incl. sync" % steps,
+            "four_block_calls_joined_ms_per_block": {k: v / max(n, 1) / 4 for k, v in prof.items()},
+            "roofline": {"kernel": "partition_mac_oct_kernel<float,W=4,128>", "bound": "hbm", "avg_launch_ms": mac_ms,
                          "bytes_needed_per_launch": needed, "achieved": needed / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0,
                          "peak": peak_gbs, "unit": "GB/s", "frac": needed / (mac_ms * 1e-3) / 1e9 / peak_gbs if mac_ms > 0 else 0.0,
                          "vs_reference_access_pattern": {"bytes_per_launch": algorithmic_8d,
@@ -279,6 +287,21 @@ def partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20, 
         torch.cuda.synchronize()
         mss = ev0.elapsed_time(ev1) / (4 * nqs)
         out["unsharded_one_gpu_four_blocks_staged"] = {"ms_per_block": mss, "Msamples_s": n * L / (mss * 1e-3) / 1e6, "api": "bfir_run_device_quad_staged + bfir_join"}
+        # ... and eight blocks per call (one eight-block partition sum)
+        d_q8 = d_q + [torch.empty_like(d_ref) for _ in range(4)]
+        full.run_device_oct(qin + qin, d_q8, staged=True)
+        full.join()
+        assert full.sync() == 0
+        nq8 = max(nqs // 2, 6)
+        ev0.record(stream)
+        for k in range(nq8):
+            full.run_device_oct(qin + qin, d_q8, staged=True)
+        full.join()
+        ev1.record(stream)
+        assert full.sync() == 0
+        torch.cuda.synchronize()
+        ms8 = ev0.elapsed_time(ev1) / (8 * nq8)
+        out["unsharded_one_gpu_eight_blocks_staged"] = {"ms_per_block": ms8, "Msamples_s": n * L / (ms8 * 1e-3) / 1e6, "api": "bfir_run_device_oct (staged) + bfir_join"}
         # reference output for the four-block shard calls: blocks P+blocks+4*(1+nq) .. +3 have just been emitted; the
         # shards below replay the same input sequence, so keep the last call's four outputs
         y_ref_q = [t.double().reshape(L, n).clone() for t in d_q]
@@ -360,8 +383,34 @@ def partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20, 
         err_st = max(errs)
     out["fused_peer_reduce_four_blocks_staged"] = {"ms_per_block": ms_st, "Msamples_s": n * L / (ms_st * 1e-3) / 1e6, "partitions_per_rank": count,
                                                    "rel_rms_vs_unsharded": err_st, "calls_timed": nqs, "api": "bfir_run_shard_quad_staged + bfir_join (three streams per rank, arrival flags, no collective)"}
+    # ---- (e) eight blocks per call through the stage pipeline
+    d_own8 = d_own4 + [torch.empty_like(d_own) for _ in range(4)]
+    fz.run_device_oct_staged(qin + qin, d_own8)
+    fz.join()
+    assert fz.sync() == 0
+    nq8 = max(nqs // 2, 6)
+
+    def oct_pass(b):
+        for k in range(nq8):
+            fz.run_device_oct_staged(qin + qin, d_own8)
+        fz.join()
+    ms_8 = timed(oct_pass, fz.sync, 1, 0) / (8 * nq8)
+    err_8 = None
+    if rank == 0:
+        errs = []
+        for k in range(8):
+            y = d_own8[k].double().reshape(L, fz.own_count)
+            r = y_ref_q[k % 4][:, fz.own_first:fz.own_first + fz.own_count]
+            errs.append(float(torch.sqrt(torch.mean((y - r) ** 2) / torch.mean(r ** 2))))
+        err_8 = max(errs)
+    out["fused_peer_reduce_eight_blocks_staged"] = {"ms_per_block": ms_8, "Msamples_s": n * L / (ms_8 * 1e-3) / 1e6, "partitions_per_rank": count,
+                                                    "rel_rms_vs_unsharded": err_8, "calls_timed": nq8, "api": "bfir_run_shard_oct_staged + bfir_join"}
     eng.close()
     if rank == 0:
+        best1 = min(out["unsharded_one_gpu_four_blocks_staged"]["ms_per_block"], out["unsharded_one_gpu_eight_blocks_staged"]["ms_per_block"])
+        bestn = min(ms_st, ms_8)
+        out["best_speedup_vs_best_one_gpu"] = best1 / bestn
+        out["best_strong_scaling_efficiency"] = best1 / bestn / world
         out["four_blocks_speedup_vs_unsharded_four_blocks"] = out["unsharded_one_gpu_four_blocks_per_call"]["ms_per_block"] / ms
         out["four_blocks_strong_scaling_efficiency"] = out["four_blocks_speedup_vs_unsharded_four_blocks"] / world
         base1 = out["unsharded_one_gpu_four_blocks_staged"]["ms_per_block"]
