@@ -2,7 +2,8 @@
 """A few two-block steps (or, with --quads, four-block steps) of cfg1 x 16 streams on one stream, for ncu
 (profiles/README.md):
 ncu --set full --clock-control none -k regex:partition_mac_pair -s 2 -c 2 python tools/pair_ncu_target.py
-ncu --set full --clock-control none -k regex:partition_mac_multi -s 2 -c 2 python tools/pair_ncu_target.py --quads"""
+ncu --set full --clock-control none -k regex:partition_mac_multi -s 2 -c 2 python tools/pair_ncu_target.py --quads
+ncu --set full --clock-control none -k regex:partition_mac_oct -s 2 -c 2 python tools/pair_ncu_target.py --octs"""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,7 +18,11 @@ d_in = [torch.rand(n, dtype=torch.float64, device="cuda") for _ in range(4)]
 d_out = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(4)]
 for b in range(P + 2):
     e.run_device(d_in[b % 4], d_out[0])
-if "--quads" in sys.argv:
+if "--octs" in sys.argv:
+    d_out8 = d_out + [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(4)]
+    for b in range(0, 48, 8):
+        e.run_device_oct(d_in + d_in, d_out8)
+elif "--quads" in sys.argv:
     for b in range(0, 24, 4):
         e.run_device_quad(d_in, d_out)
 else:
