@@ -44,6 +44,13 @@ struct Engine {
     int run_partial_quad(const void *const d_in[4]);
     int run_finish_quad(void *const d_out[4]);
     int shard_blocks_staged(int nb, const void *const *d_in, void *const *d_out);
+    // multi-block launches of the stage pipeline's output stage (BFIR_BATCH_STAGES=0: one launch per block as before)
+    bool batch_stages = true;
+    void *out8 = nullptr;           // [8][max(Cot, Ct)][N]: per-block spectra between the output crossbar / slot sum and the inverse transforms
+    size_t out8_stride = 0;         // bytes per block
+    int back_blocks(int nb, void *const *acc_in, void *const *d_out, cudaStream_t st);
+    void *plan8 = nullptr, *xin8 = nullptr;   // [8][Cit][L] planar raw blocks, [8][Cit][N] input spectra (crossbar engines, front_blocks)
+    int front_blocks(int nb, const void *const *d_in, cudaStream_t st);
     void *acc_oct[4] = {};          // accumulated spectra of blocks 5 .. 8 of an eight-block shard call
     cudaEvent_t sp_arrived[2] = {};  // staged shard calls: every source rank's flag of call k has been seen (inverse stream)
     int peer_setup(int rank, int world);
@@ -267,6 +274,7 @@ int Engine::init(const bfir_config_t &c)
     if (const char *env = getenv("BFIR_STAGED")) staged_enabled = atoi(env) != 0;
     if (const char *env = getenv("BFIR_COPY_TIMING")) copy_timing = atoi(env) != 0;
     if (const char *env = getenv("BFIR_SHARD_TIMING")) shard_timing = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_BATCH_STAGES")) batch_stages = atoi(env) != 0;
     if (const char *env = getenv("BFIR_WHOLE_COPIES")) whole_copies = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
@@ -454,8 +462,9 @@ void Engine::destroy()
     if (recv) { cudaFree(recv); recv = nullptr; }
     for (int k = 1; k < kStage; k++) { if (stage_in[k]) cudaFree(stage_in[k]); if (stage_out[k]) cudaFree(stage_out[k]); stage_in[k] = stage_out[k] = nullptr; }
     stage_in[0] = stage_out[0] = nullptr;
-    void *bufs[] = { acc_oct[0], acc_oct[1], acc_oct[2], acc_oct[3], d_peer_timeout, coeff_map, acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
+    void *bufs[] = { plan8, xin8, out8, acc_oct[0], acc_oct[1], acc_oct[2], acc_oct[3], d_peer_timeout, coeff_map, acc_quad[0], acc_quad[1], acc_pair, fdl, coeffs, acc, prev, ybuf, tw, d_in, d_out, state, procblocks, coeff_blocks, pb_inc, nonfinite, stats, xin, yacc, gains_in, gains_out, coeffs_next, acc2, tbuf };
     for (void *b : bufs) if (b) cudaFree(b);
+    out8 = plan8 = xin8 = nullptr;
     acc_pair = nullptr; acc_quad[0] = acc_quad[1] = nullptr; acc_oct[0] = acc_oct[1] = acc_oct[2] = acc_oct[3] = nullptr;
     fdl = coeffs = acc = prev = ybuf = tw = d_in = d_out = xin = yacc = gains_in = gains_out = coeffs_next = acc2 = tbuf = nullptr;
     state = nullptr; procblocks = coeff_blocks = nonfinite = nullptr; coeff_map = nullptr; d_peer_timeout = nullptr; pb_inc = nullptr; stats = nullptr;
@@ -824,6 +833,132 @@ int Engine::back_group(int g, void *d_outbuf, bool head)
     return BFIR_OK;
 }
 
+// Input stage of nb consecutive blocks (one group, stage pipeline, host-given block index) of a CROSSBAR engine in three
+// launches: the raw blocks de-interleaved into planar rows (which makes the blocks independent of each other: block b's
+// previous block is plan[b-1], block 0's the engine's previous-block row), ONE forward-transform launch over all inputs of
+// all blocks (grid.y = block), ONE input-mix launch (grid.z = block) into the delay-line slots. Without a crossbar (128
+// transforms per block already fill the GPU, and one launch per block leaves SMs to the partition sum running beside them)
+// and for fewer than two blocks: block by block.
+int Engine::front_blocks(int nb, const void *const *d_in, cudaStream_t st)
+{
+    if (!batch_stages || !xbar || nb < 2 || nb > 8 || S != 1) {
+        int rc = BFIR_OK;
+        cudaStream_t keep = stage_stream;
+        stage_stream = st;
+        for (int b = 0; b < nb && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
+        fwd_block_offset = 0;
+        stage_stream = keep;
+        return rc;
+    }
+    if (!plan8) BFIR_CUDA(cudaMalloc(&plan8, (size_t)8 * Cit * L * rs));
+    if (!xin8) BFIR_CUDA(cudaMalloc(&xin8, (size_t)8 * Cit * N * rs));
+    const unsigned int t0 = host_blockcounter;
+    PlanarArgs pa = {};
+    for (int b = 0; b < nb; b++) pa.raw[b] = d_in[b];
+    pa.plan = plan8; pa.L = L; pa.n_ch = Cit; pa.fmt = in_sf.format; pa.nb = nb;
+    if (rs == 4) raw_to_planar_kernel<float><<<dim3((L + 255) / 256, Cit, nb), 256, 0, st>>>(pa);
+    else raw_to_planar_kernel<double><<<dim3((L + 255) / 256, Cit, nb), 256, 0, st>>>(pa);
+    count_launch();
+    FwdArgs f = {};
+    f.in_mode = IN_PLANAR2; f.out_layout = LAYOUT_ORD;
+    f.scale_in = 1.0; f.scale_out = in_sf.scale;
+    f.out = xin8; f.out_stride_x = N; f.out_stride_y = (long long)Cit * N;
+    f.n_channels = Cit; f.ch_per_stream = Ci; f.fmt = in_sf.format;
+    for (int b = 0; b < nb; b++) {
+        f.hi_multi[b] = (char *)plan8 + (size_t)b * Cit * L * rs;
+        f.lo_multi[b] = b == 0 ? (const void *)((char *)prev + ((size_t)(t0 & 1u) * Cit) * L * rs) : (const void *)((char *)plan8 + (size_t)(b - 1) * Cit * L * rs);
+    }
+    cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(Cit, nb), st, f, tw);
+    count_launch();
+    if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    // the last block of the call goes where every other entry point expects the previous block -- AFTER the transforms: for an
+    // even number of blocks that is the very row block 0 has just read as ITS previous block
+    BFIR_CUDA(cudaMemcpyAsync((char *)prev + ((size_t)(((t0 + (unsigned int)nb - 1u) & 1u) ^ 1u) * Cit) * L * rs,
+                              (char *)plan8 + (size_t)(nb - 1) * Cit * L * rs, (size_t)Cit * L * rs, cudaMemcpyDeviceToDevice, st));
+    XbarArgs x = {};
+    x.in_stride = N; x.out = fdl; x.out_stride = (long long)Pslots * N; x.slot_stride = N;
+    x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = S; x.stream_base = 0;
+    x.state = state; x.n_slots = Pslots; x.n_parts = P; x.slot_offset = 0; x.procblocks = procblocks; x.pb_inc = pb_inc;
+    x.use_abs_block = 1; x.abs_block = t0;
+    x.n_multi = nb;
+    for (int b = 0; b < nb; b++) { x.in_multi[b] = (char *)xin8 + (size_t)b * Cit * N * rs; x.out_multi[b] = nullptr; }
+    xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
+    xk<<<dim3((N + 255) / 256, S, nb), 256, (size_t)C * Ci * rs, st>>>(x);
+    count_launch();
+    BFIR_CUDA(cudaGetLastError());
+    return BFIR_OK;
+}
+
+// Output stage of nb consecutive blocks (one group, stage pipeline) in as few launches as possible: on a partition shard ONE
+// slot-sum launch (grid.z = block), with a crossbar ONE output-mix launch, then ONE inverse-transform launch (grid.y =
+// block) -- instead of nb times (sum / mix + transform) of latency-bound kernels with at most Co CTAs each. acc_in[b]:
+// accumulated filter-output spectra of block b (ignored on a shard, where the receive-buffer phases peer_phase + b are
+// summed). Dither and a pending filter swap take the block-by-block path.
+int Engine::back_blocks(int nb, void *const *acc_in, void *const *d_out, cudaStream_t st)
+{
+    // (without a crossbar or shard a block's transforms nearly fill the GPU; one launch per block then leaves the remaining SMs
+    //  to the partition sum running beside them, and batching measured 3 % slower on cfg1 x 16)
+    if (!batch_stages || dither_on || xfade_pending || nb < 2 || nb > 8 || !(xbar || peer.enabled)) {
+        int rc = BFIR_OK;
+        cudaStream_t keep = stage_stream;
+        stage_stream = st;
+        const int base = peer_phase;
+        for (int b = 0; b < nb && rc == BFIR_OK; b++) {
+            if (peer.enabled) peer_phase = base + b; else acc_override = acc_in[b];
+            rc = back_group(0, d_out[b]);
+        }
+        acc_override = nullptr;
+        peer_phase = base;
+        stage_stream = keep;
+        return rc;
+    }
+    const size_t cbuf = (size_t)N * rs;
+    const int nred = xbar ? Cot : Ct;
+    if (xbar || peer.enabled) {
+        const size_t need = cbuf * (size_t)(Cot > Ct ? Cot : Ct);
+        if (!out8) { BFIR_CUDA(cudaMalloc(&out8, need * 8)); out8_stride = need; }
+    }
+    InvArgs v = {};
+    v.in_layout = LAYOUT_ORD; v.in_stride_x = N; v.scale_in = out_sf.scale;
+    v.fmt = out_sf.format; v.ovf_max = ovf_max; v.stats = stats; v.state = state; v.host_flag = d_flag;
+    v.out_mode = OUT_RAW; v.n_multi = nb;
+    int n_launch_ch;
+    if (peer.enabled) {   // owner side: sum the source slots of the own channels of all nb blocks
+        dim3 grid((N + 255) / 256, own_count, nb);
+        const long long bstride = (long long)(out8_stride / rs);
+        if (rs == 4) peer_sum_kernel<float><<<grid, 256, 0, st>>>((const float *)recv, (float *)out8, state, peer.world, peer.cpr, N, own_first, own_count, peer_phase, bstride);
+        else peer_sum_kernel<double><<<grid, 256, 0, st>>>((const double *)recv, (double *)out8, state, peer.world, peer.cpr, N, own_first, own_count, peer_phase, bstride);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+        for (int b = 0; b < nb; b++) { v.in_multi[b] = (char *)out8 + (size_t)b * out8_stride; v.out_multi[b] = d_out[b]; }
+        v.ch_per_stream = own_count; v.ch_base = own_first; v.raw_ch_base = own_first;
+        v.out_stride_x = (long long)L * own_count * out_sf.bytes;
+        n_launch_ch = own_count;
+    } else {
+        if (xbar) {       // filter outputs -> outputs of all nb blocks (mixnscale OUTPUT, n_bufs = C)
+            XbarArgs x = {};
+            x.in_stride = N; x.out = out8; x.out_stride = N; x.slot_stride = 0;
+            x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = S; x.stream_base = 0;
+            x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.procblocks = nullptr; x.pb_inc = nullptr;
+            x.n_multi = nb;
+            for (int b = 0; b < nb; b++) { x.in_multi[b] = acc_in[b]; x.out_multi[b] = (char *)out8 + (size_t)b * out8_stride; }
+            xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
+            xk<<<dim3((N + 255) / 256, S, nb), 256, (size_t)Co * C * rs, st>>>(x);
+            count_launch();
+            BFIR_CUDA(cudaGetLastError());
+        }
+        for (int b = 0; b < nb; b++) { v.in_multi[b] = xbar ? (void *)((char *)out8 + (size_t)b * out8_stride) : acc_in[b]; v.out_multi[b] = d_out[b]; }
+        v.ch_per_stream = Co; v.ch_base = 0; v.raw_ch_base = 0;
+        v.out_stride_x = (long long)L * Co * out_sf.bytes;
+        n_launch_ch = S * Co;
+    }
+    (void)nred;
+    cudaError_t e = launch_rfft_inverse(rs, log2m, fft_r0, dim3(n_launch_ch, 1), st, v, tw);
+    count_launch();
+    if (e != cudaSuccess) { set_error("inverse launch failed: %s", cudaGetErrorString(e)); return BFIR_ERR_CUDA; }
+    return BFIR_OK;
+}
+
 // look-ahead: partitions 1 .. P-1 of the NEXT block for the channels of one group (blockcounter has been advanced
 // by the inverse kernel of the block that just went out; the next forward transform has not counted itself yet)
 int Engine::tail_group(int g, cudaStream_t st)
@@ -948,10 +1083,14 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
     stage_stream = sp_fwd;
     prof_suppress = true;
     rc = BFIR_OK;
-    for (int b = 0; b < nb && rc == BFIR_OK; b++) {
-        fwd_block_offset = b;
-        if (host) BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, q_in_ready[b], 0));
-        rc = front_group(0, d_in[b], host ? &grp.in_free[slot[b]] : nullptr, true);
+    if (!host) {
+        rc = front_blocks(nb, d_in, sp_fwd);
+    } else {
+        for (int b = 0; b < nb && rc == BFIR_OK; b++) {
+            fwd_block_offset = b;
+            BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, q_in_ready[b], 0));
+            rc = front_group(0, d_in[b], &grp.in_free[slot[b]], true);
+        }
     }
     fwd_block_offset = 0;
     prof_suppress = false;
@@ -992,11 +1131,15 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
     BFIR_CUDA(cudaStreamWaitEvent(sp_inv, sp_mac_done[par], 0));
     stage_stream = sp_inv;
     prof_suppress = true;
-    for (int b = 0; b < nb && rc == BFIR_OK; b++) {
-        acc_override = sp_acc[par][b];
-        if (host) BFIR_CUDA(cudaStreamWaitEvent(sp_inv, grp.out_free[slot[b]], 0));
-        rc = back_group(0, d_out[b]);
-        if (host) BFIR_CUDA(cudaEventRecord(q_out_ready[b], sp_inv));
+    if (!host) {
+        rc = back_blocks(nb, sp_acc[par], d_out, sp_inv);
+    } else {
+        for (int b = 0; b < nb && rc == BFIR_OK; b++) {
+            acc_override = sp_acc[par][b];
+            BFIR_CUDA(cudaStreamWaitEvent(sp_inv, grp.out_free[slot[b]], 0));
+            rc = back_group(0, d_out[b]);
+            BFIR_CUDA(cudaEventRecord(q_out_ready[b], sp_inv));
+        }
     }
     acc_override = nullptr;
     prof_suppress = false;
@@ -1218,12 +1361,9 @@ int Engine::shard_blocks_staged(int nb, const void *const *d_in, void *const *d_
         }
         BFIR_CUDA(cudaGetLastError());
     } else {
-        stage_stream = sp_fwd;
         prof_suppress = true;
-        for (int b = 0; b < nb && rc == BFIR_OK; b++) { fwd_block_offset = b; rc = front_group(0, d_in[b], nullptr, true); }
-        fwd_block_offset = 0;
+        rc = front_blocks(nb, d_in, sp_fwd);
         prof_suppress = false;
-        stage_stream = nullptr;
     }
     if (rc != BFIR_OK) { use_abs = false; return rc; }
     st_mark(sp_fwd);
@@ -1260,7 +1400,18 @@ int Engine::shard_blocks_staged(int nb, const void *const *d_in, void *const *d_
     BFIR_CUDA(cudaGetLastError());
     prof(2);
     st_mark(stream);
-    if (xbar) {
+    if (xbar && batch_stages) {   // partial out-mix of all nb blocks in one launch, rows pushed to their owners
+        XbarArgs x = {};
+        x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
+        x.gains = gains_out; x.n_in = C; x.n_out = Co; x.N = N; x.n_streams = S; x.stream_base = 0;
+        x.state = nullptr; x.n_slots = Pslots; x.n_parts = P; x.push = peer; x.push_state = state; x.push_phase = base;
+        x.n_multi = nb;
+        for (int b = 0; b < nb; b++) { x.in_multi[b] = m.acc_multi[b]; x.out_multi[b] = nullptr; }
+        xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(C) : xbar_kernel_for<double>(C);
+        xk<<<dim3((N + 255) / 256, S, nb), 256, (size_t)Co * C * rs, stream>>>(x);
+        count_launch();
+        BFIR_CUDA(cudaGetLastError());
+    } else if (xbar) {
         for (int b = 0; b < nb; b++) {
             XbarArgs x = {};
             x.in = m.acc_multi[b]; x.in_stride = N; x.out = yacc; x.out_stride = N; x.slot_stride = 0;
@@ -1289,12 +1440,11 @@ int Engine::shard_blocks_staged(int nb, const void *const *d_in, void *const *d_
     BFIR_CUDA(cudaGetLastError());
     st_mark(sp_inv);
     BFIR_CUDA(cudaEventRecord(sp_arrived[par], sp_inv));
-    stage_stream = sp_inv;
     prof_suppress = true;
-    for (int b = 0; b < nb && rc == BFIR_OK; b++) { peer_phase = base + b; rc = back_group(0, d_out[b]); }
+    peer_phase = base;
+    rc = back_blocks(nb, nullptr, d_out, sp_inv);
     peer_phase = -1;
     prof_suppress = false;
-    stage_stream = nullptr;
     use_abs = false;
     if (rc != BFIR_OK) return rc;
     st_mark(sp_inv);

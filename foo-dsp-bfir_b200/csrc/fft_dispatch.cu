@@ -144,6 +144,7 @@ cudaError_t launch_rfft_forward(int realsize, int log2m, int r0, dim3 grid, cuda
     const int sub = log2m - ilog2_r0(r0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
     FwdArgs a = a0;
+    if (a.in_mode == IN_PLANAR2 && (grid.y < 1 || grid.y > 8)) return cudaErrorInvalidValue;
     a.tma = (tma_enabled() && r0 == 1 && a.in_mode == IN_RAW_PREV && a.prev != nullptr && ((uintptr_t)a.prev & 15) == 0
              && (((size_t)realsize << log2m) & 15) == 0) ? 1 : 0;
     a.cluster = 0;
@@ -160,11 +161,17 @@ cudaError_t launch_rfft_inverse(int realsize, int log2m, int r0, dim3 grid, cuda
     const int sub = log2m - ilog2_r0(r0);
     if (sub < kMinLog2M || sub > max_sub(realsize)) return cudaErrorInvalidValue;
     InvArgs a = a0;
-    a.tma = (tma_enabled() && r0 == 1 && a.head_x == nullptr && ((uintptr_t)a.in & 15) == 0
+    if (a.n_multi > 0) {   // several blocks in one launch: grid.y = blocks
+        if (a.n_multi > 8 || a.head_x != nullptr) return cudaErrorInvalidValue;
+        grid.y = (unsigned)a.n_multi;
+    }
+    uintptr_t in_bits = (uintptr_t)a.in, out_bits = (uintptr_t)a.out;
+    if (a.n_multi > 0) { in_bits = out_bits = 0; for (int k = 0; k < a.n_multi; k++) { in_bits |= (uintptr_t)a.in_multi[k]; out_bits |= (uintptr_t)a.out_multi[k]; } }
+    a.tma = (tma_enabled() && r0 == 1 && a.head_x == nullptr && (in_bits & 15) == 0
              && (((size_t)a.in_stride_x * realsize) & 15) == 0) ? 1 : 0;
     a.cluster = 0;
-    if (a.out_mode == OUT_RAW && grid.y == 1)
-        a.cluster = cluster_channels(log2m, r0, a.fmt, a.ch_per_stream, grid.x, (a.ch_base - a.raw_ch_base) % a.ch_per_stream, a.out, a.out_stride_x);
+    if (a.out_mode == OUT_RAW && (grid.y == 1 || a.n_multi > 0))
+        a.cluster = cluster_channels(log2m, r0, a.fmt, a.ch_per_stream, grid.x, (a.ch_base - a.raw_ch_base) % a.ch_per_stream, (const void *)out_bits, a.out_stride_x);
     if (use_e8(realsize, sub, r0, (long long)grid.x * grid.y, false)) return (realsize == 4 ? kInvF32E8 : kInvF64E8)[sub - kMinLog2M_e8](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
     return (realsize == 4 ? kInvF32 : kInvF64)[sub - kMinLog2M](r0, grid, stream, a, tw, 1 + ilog2_r0(r0), 0);
 }

@@ -26,7 +26,9 @@ enum {
     IN_TIME = 0,     // N reals, T layout (time2freq)
     IN_RAW_PREV = 1, // engine: interleaved raw block + per-channel previous block
     IN_COEFF = 2,    // planar coefficients, partition blockIdx.y: [0_L | h[y*L .. ) * scale] (coeffs2cbuf)
-    IN_UPPER = 3     // [0_L | src[0..L)] (runtime_coeffs2cbuf)
+    IN_UPPER = 3,    // [0_L | src[0..L)] (runtime_coeffs2cbuf)
+    IN_PLANAR2 = 4   // engine, several blocks per launch (blockIdx.y = block): [planar previous block | planar current block] of
+                     // channel bx, rows lo_multi[y] + bx L and hi_multi[y] + bx L (de-interleaved beforehand by raw_to_planar_kernel)
 };
 enum {
     OUT_TIME = 0,    // all N reals (freq2time)
@@ -94,6 +96,7 @@ struct FwdArgs {
     int tma;                 // 1: IN_RAW_PREV, one CTA per transform: the previous block arrives by bulk copy (set by launch_rfft_forward)
     int cluster;             // > 1: IN_RAW_PREV, the CTAs of `cluster` neighbouring channels of a stream form a thread-block cluster
                              // and de-interleave the raw block together (set by launch_rfft_forward; see fwd_load_cluster)
+    const void *lo_multi[8], *hi_multi[8];   // IN_PLANAR2: planar [channels][L] rows of the previous / current block of block y
 };
 
 // index of the block a forward launch transforms
@@ -126,7 +129,28 @@ struct InvArgs {
     int tma;                 // 1: one CTA per transform, no head term: the input spectrum arrives by bulk copy (set by launch_rfft_inverse)
     int cluster;             // > 1: OUT_RAW, the CTAs of `cluster` neighbouring channels of a stream form a thread-block cluster and
                              // interleave their output together (set by launch_rfft_inverse; see inv_store_cluster)
+    // several consecutive blocks in ONE launch (grid.y = n_multi, the stage pipeline's output stage): block y reads
+    // in_multi[y] and writes out_multi[y]; `in` / `out` are ignored then
+    int n_multi;
+    const void *in_multi[8];
+    void *out_multi[8];
 };
+
+// input / output of the block a CTA works on (blockIdx.y selects it in a multi-block launch)
+BFIR_HD const void *inv_in(const InvArgs &a)
+{
+#ifdef __CUDA_ARCH__
+    if (a.n_multi > 0) return a.in_multi[blockIdx.y];
+#endif
+    return a.in;
+}
+BFIR_HD void *inv_out(const InvArgs &a)
+{
+#ifdef __CUDA_ARCH__
+    if (a.n_multi > 0) return a.out_multi[blockIdx.y];
+#endif
+    return a.out;
+}
 
 template <class T> BFIR_HD T tw_re(const cpx<T> &w) { return w.x; }
 
@@ -204,6 +228,10 @@ BFIR_HD FwdCtx<T> fwd_ctx(int bx, int by, const FwdArgs &a)
     c.coeff = (const T *)a.in + bx * a.in_stride_x;
     c.sc = (T)a.scale_in;
     c.prev_rd = NULL; c.prev_wr = NULL; c.raw = NULL; c.step = 0;
+    if (a.in_mode == IN_PLANAR2) {
+        c.prev_rd = (const C *)((const T *)a.lo_multi[by] + (long long)bx * L);
+        c.plain = (const C *)((const T *)a.hi_multi[by] + (long long)bx * L);
+    }
     if (a.in_mode == IN_RAW_PREV) {
         // [previous block | current block], previous kept in a ping-pong pair that follows the reference's
         // input_timecbuf[n][curbuf] (brutefir.cpp:255-260, 337)
@@ -226,6 +254,9 @@ BFIR_HD cpx<T> fwd_elem(int m, int by, int r, const FwdArgs &a, const FwdCtx<T> 
     typedef cpx<T> C;
     if (a.in_mode == IN_TIME) {
         return c.plain[m];
+    } else if (a.in_mode == IN_PLANAR2) {
+        if (!UPPER) return c.prev_rd[m];
+        return c.plain[m - M / 2];
     } else if (a.in_mode == IN_UPPER) {
         if (!UPPER) return mk<T>((T)0, (T)0);
         return c.plain[m - M / 2];
@@ -579,7 +610,7 @@ template <class T, int LOG2MS, int R0, int LOG2E = 4>
 BFIR_HD void inv_load(int t, int bx, int r, cpx<T> (&v)[1 << LOG2E], const cpx<T> *__restrict__ tw, int tw_shift_n, const InvArgs &a)
 {
     constexpr int M = (1 << LOG2MS) * R0;
-    const T *in = (const T *)a.in + bx * a.in_stride_x;
+    const T *in = (const T *)inv_in(a) + bx * a.in_stride_x;
     const T sc = (T)a.scale_in;
     const int cset = (a.head_x != NULL && a.head_map != NULL) ? a.head_map[bx] : bx;
     if (a.head_x != NULL && a.head_blocks[cset] > 0) {   // uniform per CTA
@@ -631,7 +662,7 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[1 << LOG2E], cons
     constexpr int E = 1 << LOG2E, MS = 1 << LOG2MS, NT = MS / E, M = MS * R0, L = M;
     typedef cpx<T> C;
     if (a.out_mode == OUT_TIME) {
-        C *out = (C *)((T *)a.out + bx * a.out_stride_x);
+        C *out = (C *)((T *)inv_out(a) + bx * a.out_stride_x);
 #pragma unroll
         for (int i = 0; i < E; i++) out[R0 * (t + i * NT) + r] = v[i];
         return;
@@ -649,7 +680,7 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[1 << LOG2E], cons
     }
     // only the first L samples are consumed (fftw_convolver.cpp:425-430): z index < M/2 <=> i < E/2
     if (a.out_mode == OUT_REAL_L) {
-        C *out = (C *)((T *)a.out + (long long)bx * L);
+        C *out = (C *)((T *)inv_out(a) + (long long)bx * L);
 #pragma unroll
         for (int i = 0; i < E / 2; i++) out[R0 * (t + i * NT) + r] = v[i];
         return;
@@ -658,7 +689,7 @@ BFIR_HD void inv_store(int t, int bx, int r, const cpx<T> (&v)[1 << LOG2E], cons
     const int rb = bx - a.raw_ch_base;
     const int stream = rb / a.ch_per_stream, ch = rb - stream * a.ch_per_stream;
     const int bytes = fmt_bytes(a.fmt);
-    uint8_t *raw = (uint8_t *)a.out + (long long)stream * a.out_stride_x + (long long)ch * bytes;
+    uint8_t *raw = (uint8_t *)inv_out(a) + (long long)stream * a.out_stride_x + (long long)ch * bytes;
     const long long step = (long long)a.ch_per_stream * bytes;
     BFIR_FMT_SWITCH(a.fmt, (inv_store_raw<T, LOG2MS, R0, LOG2E, FMT>(t, r, v, raw, step, (T)a.ovf_max, acc)))
 }
@@ -816,7 +847,7 @@ __device__ __forceinline__ void inv_store_cluster(int t, int bx, const cpx<T> (&
     const int stream = rb / C, ch = rb - stream * C;
     const int r = ch & (Cc - 1), cg0 = ch - r;
     const int F = L >> cluster_log2(Cc);
-    uint8_t *out_stream = (uint8_t *)a.out + (long long)stream * a.out_stride_x;
+    uint8_t *out_stream = (uint8_t *)inv_out(a) + (long long)stream * a.out_stride_x;
     const uint8_t *rows[BFIR_MAX_CLUSTER];
     cluster_peers<const uint8_t>((const uint8_t *)smem_raw, Cc, rows);
     const int nchunks = (L * bytes) >> 4;
@@ -907,7 +938,7 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
         constexpr int N = 2 << LOG2MS;
         if (t == 0) mbar_init(&bar, 1);
         __syncthreads();
-        if (t == 0) bulk_stage(smem_raw, (const T *)a.in + bx * a.in_stride_x, (uint32_t)(N * sizeof(T)), &bar);
+        if (t == 0) bulk_stage(smem_raw, (const T *)inv_in(a) + bx * a.in_stride_x, (uint32_t)(N * sizeof(T)), &bar);
         mbar_wait(&bar, 0);
         inv_load_impl<T, LOG2MS, R0, false, LOG2E>(t, r, v, tw, tw_shift_n, reinterpret_cast<const T *>(smem_raw), a.in_layout, (T)a.scale_in, NULL, NULL);
         __syncthreads();                               // every thread has read its bins before the passes overwrite them
@@ -919,7 +950,7 @@ __global__ void __launch_bounds__((1 << LOG2MS) >> LOG2E, BFIR_E8_MINB(LOG2E, LO
     if constexpr (CL && R0 == 1) inv_store_cluster<T, LOG2MS, LOG2E>(t, bx, v, a, acc, smem_raw);
     else inv_store<T, LOG2MS, R0, LOG2E>(t, bx, r, v, a, acc);
     if (a.out_mode == OUT_RAW && a.stats != NULL) overflow_commit(&a.stats[bx], acc);
-    if (a.state != NULL && blockIdx.x == 0 && t == 0 && r == 0) a.state->blockcounter += 1u; // brutefir.cpp:337-340
+    if (a.state != NULL && blockIdx.x == 0 && blockIdx.y == 0 && t == 0 && r == 0) a.state->blockcounter += a.n_multi > 0 ? (unsigned int)a.n_multi : 1u; // brutefir.cpp:337-340
 }
 #endif
 

@@ -33,6 +33,11 @@ struct XbarArgs {
     PeerPush push;             // enabled: output rows go to the owner rank's receive buffer (fused reduce)
     const EngineState *push_state; // block parity of the receive buffer (one-block calls)
     int push_phase;            // >= 0: explicit receive-buffer phase (four-block calls), else the parity of push_state
+    // several consecutive blocks in ONE launch (grid.z = n_multi): block z reads in_multi[z], writes out_multi[z] (NULL: `out`,
+    // e.g. the delay line, where the slot follows from abs_block + z), pushes into phase push_phase + z
+    int n_multi;
+    const void *in_multi[8];
+    void *out_multi[8];
 };
 
 #ifdef __CUDACC__
@@ -46,43 +51,48 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
     __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.y + a.stream_base;
-    if (a.procblocks != NULL && blockIdx.x == 0 && threadIdx.x < a.n_out) {
+    if (a.procblocks != NULL && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x < a.n_out) {
         const int ch = s * a.n_out + threadIdx.x;
         const int pb = a.procblocks[ch];
-        const bool inc = pb < a.n_parts;
-        if (inc) a.procblocks[ch] = pb + 1;
-        a.pb_inc[ch] = inc ? 1 : 0;
+        const int want = a.n_multi > 0 ? a.n_multi : 1;            // (multi-block launches run in the steady state: no increment left)
+        const int add = min(want, max(a.n_parts - pb, 0));
+        if (add > 0) a.procblocks[ch] = pb + add;
+        a.pb_inc[ch] = add > 0 ? 1 : 0;
     }
     if (j >= a.N) return;
-    const T *in = (const T *)a.in + (long long)s * a.n_in * a.in_stride + j;
+    const int z = a.n_multi > 0 ? (int)blockIdx.z : 0;
+    const T *in = (const T *)(a.n_multi > 0 ? a.in_multi[z] : a.in) + (long long)s * a.n_in * a.in_stride + j;
     T x[MAXI];
 #pragma unroll
     for (int i = 0; i < MAXI; i++) x[i] = i < a.n_in ? in[(long long)i * a.in_stride] : (T)0;
     long long off = (long long)s * a.n_out * a.out_stride + j;
     if (a.state != NULL) {
-        const unsigned int blk = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.slot_offset;
+        const unsigned int blk = (a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.slot_offset) + (unsigned int)z;
         off += (long long)(blk % (unsigned int)a.n_slots) * a.slot_stride;
     }
-    T *out = (T *)a.out + off;
+    T *out = (T *)((a.n_multi > 0 && a.out_multi[z] != NULL) ? a.out_multi[z] : a.out) + off;
     for (int o = 0; o < a.n_out; o++) {
         const T *row = g + o * a.n_in;
         T acc = (T)0;
 #pragma unroll
         for (int i = 0; i < MAXI; i++) if (i < a.n_in) acc = fma(row[i], x[i], acc);
-        if (a.push.enabled) peer_dst<T>(a.push, s * a.n_out + o, a.N, a.push_phase >= 0 ? (unsigned int)a.push_phase : (a.push_state->blockcounter & 1u))[j] = acc;
+        if (a.push.enabled) peer_dst<T>(a.push, s * a.n_out + o, a.N, a.push_phase >= 0 ? (unsigned int)(a.push_phase + z) : (a.push_state->blockcounter & 1u))[j] = acc;
         else out[(long long)o * a.out_stride] = acc;
     }
 }
 
 // owner side of the fused reduce: sum the `world` source slots of each owned channel in rank order
 // (deterministic) into the local spectrum buffer at the channel's absolute position
+// grid.z > 1: consecutive blocks of a multi-block call, block z from phase + z into dst + z * dst_block_stride
 template <class T>
-__global__ void __launch_bounds__(256) peer_sum_kernel(const T *recv, T *dst, const EngineState *state, int world, int cpr, int N, int ch_first, int n_own, int phase)
+__global__ void __launch_bounds__(256) peer_sum_kernel(const T *recv, T *dst, const EngineState *state, int world, int cpr, int N, int ch_first, int n_own, int phase,
+                                                       long long dst_block_stride = 0)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int local = blockIdx.y;
     if (j >= N || local >= n_own) return;
-    const unsigned int parity = phase >= 0 ? (unsigned int)phase : (state->blockcounter & 1u);
+    dst += (long long)blockIdx.z * dst_block_stride;
+    const unsigned int parity = phase >= 0 ? (unsigned int)phase + blockIdx.z : (state->blockcounter & 1u);
     T acc = (T)0;
     for (int s = 0; s < world; s++) acc += recv[(((long long)parity * world + s) * cpr + local) * N + j];
     dst[(long long)(ch_first + local) * N + j] = acc;
@@ -139,6 +149,24 @@ static __global__ void __launch_bounds__(256) raw_to_prev_kernel(const uint8_t *
     if (f >= L || (c >= skip_first && c < skip_first + skip_count)) return;
     const int bytes = fmt_bytes(fmt);
     prev_rows[(long long)c * L + f] = load_raw<T>(raw + ((long long)f * n_ch + c) * bytes, fmt);
+}
+
+// nb raw interleaved blocks -> planar rows plan[z][channel][L] (the several-blocks-per-launch forward transforms read
+// those instead of the interleaved block, which makes the blocks of a call independent of each other).
+// grid (ceil(L/256), channels, nb)
+struct PlanarArgs {
+    const void *raw[8];
+    void *plan;              // [nb][n_ch][L] reals
+    int L, n_ch, fmt, nb;
+};
+template <class T>
+static __global__ void __launch_bounds__(256) raw_to_planar_kernel(const PlanarArgs a)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y, z = blockIdx.z;
+    if (f >= a.L) return;
+    const int bytes = fmt_bytes(a.fmt);
+    const T x = load_raw<T>((const uint8_t *)a.raw[z] + ((long long)f * a.n_ch + c) * bytes, a.fmt);
+    ((T *)a.plan)[((long long)z * a.n_ch + c) * a.L + f] = x;
 }
 
 typedef void (*xbar_kernel_t)(const XbarArgs);

@@ -390,9 +390,13 @@ def partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20, 
     assert fz.sync() == 0
     nq8 = max(nqs // 2, 6)
 
+    host_enqueue = {}
+
     def oct_pass(b):
+        t0 = time.perf_counter()
         for k in range(nq8):
             fz.run_device_oct_staged(qin + qin, d_own8)
+        host_enqueue["ms_per_call"] = 1e3 * (time.perf_counter() - t0) / nq8   # host time to queue one call (no waiting in it)
         fz.join()
     ms_8 = timed(oct_pass, fz.sync, 1, 0) / (8 * nq8)
     err_8 = None
@@ -404,7 +408,8 @@ def partition_sharded(pkg, sh, torch, dist, rank, world, local_rank, blocks=20, 
             errs.append(float(torch.sqrt(torch.mean((y - r) ** 2) / torch.mean(r ** 2))))
         err_8 = max(errs)
     out["fused_peer_reduce_eight_blocks_staged"] = {"ms_per_block": ms_8, "Msamples_s": n * L / (ms_8 * 1e-3) / 1e6, "partitions_per_rank": count,
-                                                    "rel_rms_vs_unsharded": err_8, "calls_timed": nq8, "api": "bfir_run_shard_oct_staged + bfir_join"}
+                                                    "rel_rms_vs_unsharded": err_8, "calls_timed": nq8, "host_enqueue_ms_per_call": host_enqueue.get("ms_per_call"),
+                                                    "api": "bfir_run_shard_oct_staged + bfir_join"}
     eng.close()
     if rank == 0:
         best1 = min(out["unsharded_one_gpu_four_blocks_staged"]["ms_per_block"], out["unsharded_one_gpu_eight_blocks_staged"]["ms_per_block"])
