@@ -71,11 +71,30 @@ __global__ void __launch_bounds__(256) xbar_mix_kernel(const XbarArgs a)
         off += (long long)(blk % (unsigned int)a.n_slots) * a.slot_stride;
     }
     T *out = (T *)((a.n_multi > 0 && a.out_multi[z] != NULL) ? a.out_multi[z] : a.out) + off;
+    // the gains are read from shared memory by every thread of the warp at once (broadcast): one wavefront per load, so the
+    // loop is bound by the number of loads -- 16-byte loads (4 float / 2 double gains) when the rows allow it
+    const bool vec = (a.n_in & 3) == 0;
     for (int o = 0; o < a.n_out; o++) {
         const T *row = g + o * a.n_in;
         T acc = (T)0;
+        if (vec) {
+            if constexpr (sizeof(T) == 4) {
 #pragma unroll
-        for (int i = 0; i < MAXI; i++) if (i < a.n_in) acc = fma(row[i], x[i], acc);
+                for (int i = 0; i < MAXI; i += 4) if (i < a.n_in) {
+                    const float4 w = *reinterpret_cast<const float4 *>(row + i);
+                    acc = fma(w.x, x[i], acc); acc = fma(w.y, x[i + 1], acc); acc = fma(w.z, x[i + 2], acc); acc = fma(w.w, x[i + 3], acc);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < MAXI; i += 2) if (i < a.n_in) {
+                    const double2 w = *reinterpret_cast<const double2 *>(row + i);
+                    acc = fma(w.x, x[i], acc); acc = fma(w.y, x[i + 1], acc);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < MAXI; i++) if (i < a.n_in) acc = fma(row[i], x[i], acc);
+        }
         if (a.push.enabled) peer_dst<T>(a.push, s * a.n_out + o, a.N, a.push_phase >= 0 ? (unsigned int)(a.push_phase + z) : (a.push_state->blockcounter & 1u))[j] = acc;
         else out[(long long)o * a.out_stride] = acc;
     }
