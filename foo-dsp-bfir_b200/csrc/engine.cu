@@ -45,6 +45,7 @@ struct Engine {
     int run_finish_quad(void *const d_out[4]);
     int shard_blocks_staged(int nb, const void *const *d_in, void *const *d_out);
     // multi-block launches of the stage pipeline's output stage (BFIR_BATCH_STAGES=0: one launch per block as before)
+    int mac_persist_sms = 0;        // BFIR_MAC_SMS: > 0 = the eight-block partition sum as a persistent grid alone on that many SMs
     bool batch_stages = true;
     void *out8 = nullptr;           // [8][max(Cot, Ct)][N]: per-block spectra between the output crossbar / slot sum and the inverse transforms
     size_t out8_stride = 0;         // bytes per block
@@ -275,6 +276,7 @@ int Engine::init(const bfir_config_t &c)
     if (const char *env = getenv("BFIR_COPY_TIMING")) copy_timing = atoi(env) != 0;
     if (const char *env = getenv("BFIR_SHARD_TIMING")) shard_timing = atoi(env) != 0;
     if (const char *env = getenv("BFIR_BATCH_STAGES")) batch_stages = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_MAC_SMS")) { const int v = atoi(env); if (v >= 1 && v <= 1024) mac_persist_sms = v; }
     if (const char *env = getenv("BFIR_WHOLE_COPIES")) whole_copies = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
     BFIR_CUDA(cudaEventCreateWithFlags(&out_done, cudaEventDisableTiming));
@@ -1113,14 +1115,24 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
     int mthreads = nb == 4 && rs == 8 ? quad_threads : 256;
     dim3 grid((N / 8 + mthreads / split - 1) / (mthreads / split), Ct);
     mac_kernel_t mk;
-    if (nb == 8) {   // eight blocks: a thread owns 4 (double) or 8 (float) reals of a group, one slice
+    size_t msmem = 0;
+    if (nb == 8) {   // eight blocks: a thread owns 2 (double) or 4 (float) reals of a group, one slice
         mthreads = 128;
         const int w = rs == 4 ? mac_oct_reals_per_thread<float>() : mac_oct_reals_per_thread<double>();
         grid = dim3((N / w + mthreads - 1) / mthreads, Ct);
         mk = rs == 4 ? mac_oct_kernel<float>() : mac_oct_kernel<double>();
+        if (mac_persist_sms > 0) {   // BFIR_MAC_SMS=n: persistent CTAs alone on n SMs, the rest of the GPU left to the transforms
+            mthreads = 256;
+            m.tiles_x = (N / w + mthreads - 1) / mthreads; m.n_ch_launch = Ct;
+            grid = dim3(mac_persist_sms, 1);
+            mk = rs == 4 ? mac_oct_persistent_kernel<float>() : mac_oct_persistent_kernel<double>();
+            msmem = 160 * 1024;
+            static bool configured[2] = { false, false };
+            if (!configured[rs == 8]) { BFIR_CUDA(cudaFuncSetAttribute((const void *)mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem)); configured[rs == 8] = true; }
+        }
     } else if (nb == 4) mk = rs == 4 ? mac_quad_kernel_for_split<float>(split) : mac_quad_kernel_for_split<double>(split, mthreads);
     else mk = rs == 4 ? mac_pair_kernel_for_split<float>(split) : mac_pair_kernel_for_split<double>(split);
-    mk<<<grid, mthreads, 0, stream>>>(m);
+    mk<<<grid, mthreads, msmem, stream>>>(m);
     count_launch();
     BFIR_CUDA(cudaGetLastError());
     prof(2);

@@ -37,6 +37,7 @@ struct MacArgs {
     int procblocks_bias;     // 1: look-ahead launch for the NEXT block, whose forward transform has not counted itself yet
     PeerPush push;           // enabled: partial sums go to the owner rank's receive buffer (fused reduce)
     int push_phase;          // multi kernel: receive-buffer phase of block t (block t+b: push_phase + b)
+    int tiles_x, n_ch_launch; // persistent eight-block kernel: tiles per channel, channels of the launch
 };
 
 template <class T> struct vec8 { T v[8]; };
@@ -367,13 +368,11 @@ template <class T, int W> __device__ __forceinline__ void macw(T (&acc)[W], cons
     }
 }
 
-template <class T, int W, int THREADS, int AHEAD>
-__global__ void __launch_bounds__(THREADS) partition_mac_oct_kernel(const MacArgs a)
+template <class T, int W, int AHEAD>
+__device__ __forceinline__ void mac_oct_tile(const MacArgs &a, int q, int ch)
 {
     constexpr int NB = 8, HALVES = 8 / W, H = W / 2;
-    const int q = blockIdx.x * THREADS + threadIdx.x;
     const int g = q / HALVES, h = q - g * HALVES;
-    const int ch = blockIdx.y + a.ch_base;
     if (g * 8 >= a.N) return;
     const unsigned int t = a.use_abs_block ? a.abs_block : a.state->blockcounter + (unsigned int)a.block_offset;
     const int cs_ = a.coeff_map ? a.coeff_map[ch] : ch;
@@ -451,6 +450,26 @@ __global__ void __launch_bounds__(THREADS) partition_mac_oct_kernel(const MacArg
     }
 }
 
+template <class T, int W, int THREADS, int AHEAD>
+__global__ void __launch_bounds__(THREADS) partition_mac_oct_kernel(const MacArgs a)
+{
+    mac_oct_tile<T, W, AHEAD>(a, blockIdx.x * THREADS + threadIdx.x, blockIdx.y + a.ch_base);
+}
+
+// The same as a PERSISTENT grid of a.persist_ctas CTAs, each alone on its SM (the launch asks for most of the shared
+// memory), walking the (channel, tile) list: the partition sum is bound by bytes in flight, not by SM cycles, and ~64 KB in
+// flight on each of a THIRD of the SMs already saturates HBM -- so it can leave the other SMs to the transform kernels of
+// the neighbouring calls (whole-SM CTAs, which otherwise wait until a sum's CTAs have drained from an SM).
+template <class T, int W, int THREADS, int AHEAD>
+__global__ void __launch_bounds__(THREADS) partition_mac_oct_persistent_kernel(const MacArgs a)
+{
+    const int n_tiles = a.tiles_x * a.n_ch_launch;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int c = tile / a.tiles_x, xb = tile - c * a.tiles_x;
+        mac_oct_tile<T, W, AHEAD>(a, xb * THREADS + threadIdx.x, c + a.ch_base);
+    }
+}
+
 typedef void (*mac_kernel_t)(const MacArgs);
 // reals per thread: BFIR_OCT_W overrides (measurement)
 template <class T> inline int mac_oct_reals_per_thread()
@@ -460,6 +479,12 @@ template <class T> inline int mac_oct_reals_per_thread()
     // that must move), W = 4 0.326 (224 registers, two CTAs per SM); float cfg3 shape W = 4 0.575 ms (0.84), W = 8 0.766
     if (sizeof(T) == 8) return forced == 4 ? 4 : 2;
     return forced == 8 ? 8 : 4;
+}
+template <class T> inline mac_kernel_t mac_oct_persistent_kernel()
+{
+    const int w = mac_oct_reals_per_thread<T>();
+    if constexpr (sizeof(T) == 8) { if (w == 2) return partition_mac_oct_persistent_kernel<T, 2, 256, 8>; return partition_mac_oct_persistent_kernel<T, 4, 256, 4>; }
+    else { if (w == 4) return partition_mac_oct_persistent_kernel<T, 4, 256, 8>; return partition_mac_oct_persistent_kernel<T, 8, 256, 4>; }
 }
 template <class T> inline mac_kernel_t mac_oct_kernel()
 {
