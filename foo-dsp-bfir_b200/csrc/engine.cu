@@ -617,9 +617,9 @@ int Engine::peer_setup(int rank, int world)
     peer.xin_offset = 0; peer.n_inputs = Cit; peer.in_cpr = (Cit + world - 1) / world;
     own_in_first = rank * peer.in_cpr;
     own_in_count = own_in_first >= Cit ? 0 : (Cit - own_in_first < peer.in_cpr ? Cit - own_in_first : peer.in_cpr);
-    if (xbar && shard_inputs) {                            // input region: [2 call parities * 4 blocks][Cit][N]
+    if (xbar && shard_inputs && S == 1) {                  // input region: [2 call parities * 8 blocks][Cit][N]
         peer.xin_offset = (long long)bytes;
-        bytes += (size_t)8 * Cit * N * rs;
+        bytes += (size_t)16 * Cit * N * rs;
     }
     BFIR_CUDA(cudaMalloc(&recv, bytes));
     BFIR_CUDA(cudaMemset(recv, 0, bytes));
@@ -1323,54 +1323,57 @@ int Engine::shard_blocks_staged(int nb, const void *const *d_in, void *const *d_
     BFIR_CUDA(cudaStreamWaitEvent(sp_fwd, sp_mac_done[par], 0));
     st_mark(sp_fwd);
     rc = BFIR_OK;
-    if (xbar && peer.xin_offset != 0 && nb == 4) {
-        // SHARDED input stage: this rank transforms only its own inputs (own_in_count CTAs instead of Ci), stores the
-        // spectra into every peer's input region -- phase (call parity, block) -- and raises its input flag; once every
-        // rank's flag of this call is in, the whole input crossbar runs on the gathered spectra. All on the forward
-        // stream, so a rank's input flag of call k+1 also says that its crossbar of call k has read phase set k & 1,
-        // which its peers overwrite with call k+2 only after they have seen that flag.
-        const int ibase = (int)(peer_in_epoch & 1u) * 4;   // (sharded inputs: four-block calls only, see bfir_run_shard_oct_staged)
+    if (xbar && peer.xin_offset != 0) {
+        // SHARDED input stage (BFIR_SHARD_INPUTS=1): this rank transforms only its own inputs (own_in_count x nb CTAs
+        // instead of Ci x nb), stores the spectra into every peer's input region -- phase (call parity, block) -- and
+        // raises its input flag; once every rank's flag of this call is in, the whole input crossbar runs on the
+        // gathered spectra. All on the forward stream, so a rank's input flag of call k+1 also says that its crossbar of
+        // call k has read phase set k & 1, which its peers overwrite with call k+2 only after they have seen that flag.
+        const int ibase = (int)(peer_in_epoch & 1u) * 8;
         char *xin_all = (char *)recv + peer.xin_offset;
         const long long row_bytes = (long long)N * rs;
-        for (int b = 0; b < 4; b++) {
-            if (own_in_count > 0) {
-                FwdArgs f = {};
-                f.in_mode = IN_RAW_PREV; f.out_layout = LAYOUT_ORD;
-                f.in = d_in[b]; f.in_stride_x = (long long)L * Ci * in_sf.bytes;
-                f.scale_in = 1.0; f.scale_out = in_sf.scale;
-                f.prev = prev; f.fmt = in_sf.format; f.ch_per_stream = Ci; f.n_channels = Cit; f.ch_base = own_in_first;
-                f.use_abs_block = 1; f.abs_block = host_blockcounter + (unsigned int)b;
-                f.state = nullptr; f.n_slots = Pslots; f.n_parts = P; f.prev_parity = (host_blockcounter + (unsigned int)b) & 1u; f.slot_offset = b;
-                f.out = xin_all + (long long)(ibase + b) * Cit * row_bytes; f.out_stride_x = N; f.out_stride_y = 0;
-                cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(own_in_count, 1), sp_fwd, f, tw);
-                count_launch();
-                if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); use_abs = false; return BFIR_ERR_CUDA; }
-                peer_bcast_kernel<<<dim3((unsigned)((row_bytes / 16 + 255) / 256), own_in_count, peer.world - 1), 256, 0, sp_fwd>>>(peer, ibase + b, own_in_first, row_bytes);
-                count_launch();
+        const unsigned int t0 = host_blockcounter;
+        if (!plan8) BFIR_CUDA(cudaMalloc(&plan8, (size_t)8 * Cit * L * rs));
+        PlanarArgs pa = {};
+        for (int bb = 0; bb < nb; bb++) pa.raw[bb] = d_in[bb];
+        pa.plan = plan8; pa.L = L; pa.n_ch = Cit; pa.fmt = in_sf.format; pa.nb = nb;
+        if (rs == 4) raw_to_planar_kernel<float><<<dim3((L + 255) / 256, Cit, nb), 256, 0, sp_fwd>>>(pa);
+        else raw_to_planar_kernel<double><<<dim3((L + 255) / 256, Cit, nb), 256, 0, sp_fwd>>>(pa);
+        count_launch();
+        if (own_in_count > 0) {
+            FwdArgs f = {};
+            f.in_mode = IN_PLANAR2; f.out_layout = LAYOUT_ORD;
+            f.scale_in = 1.0; f.scale_out = in_sf.scale;
+            f.out = xin_all + (long long)ibase * Cit * row_bytes; f.out_stride_x = N; f.out_stride_y = (long long)Cit * N;
+            f.n_channels = Cit; f.ch_per_stream = Ci; f.fmt = in_sf.format; f.ch_base = own_in_first;
+            for (int bb = 0; bb < nb; bb++) {
+                f.hi_multi[bb] = (char *)plan8 + (size_t)bb * Cit * L * rs;
+                f.lo_multi[bb] = bb == 0 ? (const void *)((char *)prev + ((size_t)(t0 & 1u) * Cit) * L * rs) : (const void *)((char *)plan8 + (size_t)(bb - 1) * Cit * L * rs);
             }
+            cudaError_t e = launch_rfft_forward(rs, log2m, fft_r0, dim3(own_in_count, nb), sp_fwd, f, tw);
+            count_launch();
+            if (e != cudaSuccess) { set_error("forward launch failed: %s", cudaGetErrorString(e)); use_abs = false; return BFIR_ERR_CUDA; }
         }
-        {   // the previous-block rows of the inputs other ranks transform: keep them valid (last block of the call)
-            const unsigned int last = host_blockcounter + 3u;
-            void *rows = (char *)prev + ((size_t)((last & 1u) ^ 1u) * Cit) * L * rs;
-            const dim3 g((L + 255) / 256, Cit);
-            if (rs == 4) raw_to_prev_kernel<float><<<g, 256, 0, sp_fwd>>>((const uint8_t *)d_in[3], (float *)rows, L, Cit, in_sf.format, own_in_first, own_in_count);
-            else raw_to_prev_kernel<double><<<g, 256, 0, sp_fwd>>>((const uint8_t *)d_in[3], (double *)rows, L, Cit, in_sf.format, own_in_first, own_in_count);
+        BFIR_CUDA(cudaMemcpyAsync((char *)prev + ((size_t)(((t0 + (unsigned int)nb - 1u) & 1u) ^ 1u) * Cit) * L * rs,
+                                  (char *)plan8 + (size_t)(nb - 1) * Cit * L * rs, (size_t)Cit * L * rs, cudaMemcpyDeviceToDevice, sp_fwd));
+        if (own_in_count > 0) {
+            peer_bcast_kernel<<<dim3((unsigned)((row_bytes / 16 + 255) / 256), own_in_count * nb, peer.world - 1), 256, 0, sp_fwd>>>(peer, ibase, own_in_first, row_bytes, own_in_count);
             count_launch();
         }
         peer_in_epoch++;
         peer_signal_kernel<<<1, 32, 0, sp_fwd>>>(peer, peer_in_epoch, peer.flag_in_offset);
         peer_wait_kernel<<<1, 32, 0, sp_fwd>>>(peer, peer_in_epoch, d_peer_timeout, peer.flag_in_offset);
         count_launch(2);
-        for (int b = 0; b < 4; b++) {
-            XbarArgs x = {};
-            x.in = xin_all + (long long)(ibase + b) * Cit * row_bytes; x.in_stride = N; x.out = fdl; x.out_stride = (long long)Pslots * N; x.slot_stride = N;
-            x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = S; x.stream_base = 0;
-            x.state = state; x.n_slots = Pslots; x.n_parts = P; x.slot_offset = b; x.procblocks = procblocks; x.pb_inc = pb_inc;
-            x.use_abs_block = 1; x.abs_block = host_blockcounter + (unsigned int)b;
-            xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
-            xk<<<dim3((N + 255) / 256, S), 256, (size_t)C * Ci * rs, sp_fwd>>>(x);
-            count_launch();
-        }
+        XbarArgs x = {};
+        x.in_stride = N; x.out = fdl; x.out_stride = (long long)Pslots * N; x.slot_stride = N;
+        x.gains = gains_in; x.n_in = Ci; x.n_out = C; x.N = N; x.n_streams = S; x.stream_base = 0;
+        x.state = state; x.n_slots = Pslots; x.n_parts = P; x.slot_offset = 0; x.procblocks = procblocks; x.pb_inc = pb_inc;
+        x.use_abs_block = 1; x.abs_block = t0;
+        x.n_multi = nb;
+        for (int bb = 0; bb < nb; bb++) { x.in_multi[bb] = xin_all + (long long)(ibase + bb) * Cit * row_bytes; x.out_multi[bb] = nullptr; }
+        xbar_kernel_t xk = rs == 4 ? xbar_kernel_for<float>(Ci) : xbar_kernel_for<double>(Ci);
+        xk<<<dim3((N + 255) / 256, S, nb), 256, (size_t)C * Ci * rs, sp_fwd>>>(x);
+        count_launch();
         BFIR_CUDA(cudaGetLastError());
     } else {
         prof_suppress = true;

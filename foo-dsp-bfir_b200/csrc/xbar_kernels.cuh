@@ -147,27 +147,17 @@ static __global__ void peer_wait_kernel(const PeerPush p, unsigned int epoch, in
 
 // Sharded input stage: this rank's input spectra (rows [row0, row0 + nrows) of phase `phase`, N reals each, already in
 // the local input region) -> the same rows of every peer's input region, 16-byte stores over NVLink.
-// grid (ceil(row_bytes / 16 / 256), nrows, world - 1)
-static __global__ void __launch_bounds__(256) peer_bcast_kernel(const PeerPush p, int phase, int row0, long long row_bytes)
+// grid (ceil(row_bytes / 16 / 256), nrows * blocks, world - 1): blockIdx.y = block * nrows + row, block b in phase phase + b
+static __global__ void __launch_bounds__(256) peer_bcast_kernel(const PeerPush p, int phase, int row0, long long row_bytes, int nrows)
 {
     int q = blockIdx.z;
     if (q >= p.self) q++;                               // the z-th OTHER rank
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i * 16 >= row_bytes) return;
-    const long long off = p.xin_offset + ((long long)phase * p.n_inputs + row0 + blockIdx.y) * row_bytes;
+    const int b = blockIdx.y / nrows, k = blockIdx.y - b * nrows;
+    const long long off = p.xin_offset + ((long long)(phase + b) * p.n_inputs + row0 + k) * row_bytes;
     const uint4 v = ((const uint4 *)((const char *)p.recv[p.self] + off))[i];
     ((uint4 *)((char *)p.recv[q] + off))[i] = v;
-}
-
-// one raw interleaved block -> planar rows of the previous-block buffer, for the channels this rank does NOT transform
-// itself in the sharded input stage (keeps every entry point's view of the previous block valid). grid (ceil(L/256), channels)
-template <class T>
-static __global__ void __launch_bounds__(256) raw_to_prev_kernel(const uint8_t *raw, T *prev_rows, int L, int n_ch, int fmt, int skip_first, int skip_count)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-    if (f >= L || (c >= skip_first && c < skip_first + skip_count)) return;
-    const int bytes = fmt_bytes(fmt);
-    prev_rows[(long long)c * L + f] = load_raw<T>(raw + ((long long)f * n_ch + c) * bytes, fmt);
 }
 
 // nb raw interleaved blocks -> planar rows plan[z][channel][L] (the several-blocks-per-launch forward transforms read

@@ -253,10 +253,10 @@ int bfir_run_finish_quad_device(bfir_engine *e, void *const d_out[4]);
  * BFIR_SHARD_INPUTS=1 (read by bfir_peer_setup; crossbar engines): the input stage is sharded as well -- a rank
  * transforms only its own ceil(inputs / world) input channels and stores the spectra into every peer's input region
  * (a second flag array orders it), then applies the whole input crossbar. Off by default: measured slower than the
- * redundant input stage on 2 and on 8 GPUs. */
+ * redundant input stage on 2 and on 8 GPUs, with one launch per block and with multi-block launches. */
 int bfir_run_shard_quad_staged(bfir_engine *e, const void *const d_in[4], void *const d_out[4]);
 /* The same with EIGHT blocks per call (one eight-block partition sum over the rank's partitions; shards too small for
- * that kernel run two four-block calls). The input stage is never sharded here. */
+ * that kernel run two four-block calls). */
 int bfir_run_shard_oct_staged(bfir_engine *e, const void *const d_in[8], void *const d_out[8]);
 void *bfir_acc_device_ptr(bfir_engine *e, size_t *bytes);
 

@@ -143,7 +143,7 @@ def test_two_emulated_ranks_four_blocks_per_call(pkg, rs, L, P, C, xb):
 
 @pytest.mark.parametrize("rs,L,P,C,xb,shard_inputs", [(4, 512, 6, 4, (0, 0), 0), (8, 256, 4, 5, (0, 0), 0), (4, 1024, 8, 4, (3, 5), 0),
                                                       (4, 2048, 16, 8, (8, 8), 0), (4, 1024, 8, 4, (3, 5), 1), (4, 2048, 16, 8, (8, 8), 1),
-                                                      (8, 512, 5, 6, (4, 4), 1), (4, 16384, 4, 12, (0, 0), 0), (8, 8192, 3, 12, (6, 6), 0)])
+                                                      (8, 512, 5, 6, (4, 4), 1), (4, 16384, 4, 12, (0, 0), 0), (8, 8192, 3, 12, (6, 6), 0), (8, 8192, 3, 12, (6, 6), 1)])
 def test_two_emulated_ranks_four_blocks_staged(pkg, rs, L, P, C, xb, shard_inputs, monkeypatch):
     """bfir_run_shard_quad_staged: the four-block shard call through the stage pipeline (forward transforms, partition
     sum + pushes, arrival wait + output stage of neighbouring calls on three streams per rank; receive-buffer phases
