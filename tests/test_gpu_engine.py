@@ -907,6 +907,34 @@ def test_eight_blocks_per_call_equal_single_blocks(pkg, rs, out_fmt, P, S, C, xb
             assert dd.max() <= 1, (b, dd.max())
 
 
+def test_mac_profile_tells_the_launch_kinds_apart(pkg):
+    """bfir_get_mac_profile: the partition-sum launches of a profiled run, by blocks per launch (8 / 4 / 2 / 1)."""
+    import torch
+    L, P, C, S = 2048, 3, 4, 24
+    e = pkg.Brutefir(L, P, 8, C, pkg.FLOAT64_LE, pkg.FLOAT64_LE, 2000, False, n_streams=S, n_groups=1)
+    assert e.set_coeff([decay_filter(c % 5, L * P) for c in range(C * S)], P) == 0
+    d_in = [torch.rand(S * L * C, dtype=torch.float64, device="cuda") for _ in range(8)]
+    d_out = [torch.empty(S * L * C, dtype=torch.float64, device="cuda") for _ in range(8)]
+    torch.cuda.synchronize()
+    for b in range(P):
+        e.run_device(d_in[b], d_out[0])
+    assert e.sync() == 0
+    e.set_profiling(16)
+    for nb in (1, 2, 4, 8):
+        e.get_mac_profile(nb)
+    e.run_device_oct(d_in, d_out)
+    e.run_device_oct(d_in, d_out, staged=True)
+    e.run_device_quad(d_in[:4], d_out[:4])
+    e.run_device_pair(d_in[0], d_in[1], d_out[0], d_out[1])
+    e.run_device(d_in[2], d_out[2])
+    assert e.sync() == 0
+    counts = {nb: e.get_mac_profile(nb) for nb in (8, 4, 2, 1)}
+    assert [counts[nb][1] for nb in (8, 4, 2, 1)] == [2, 1, 1, 1], counts
+    assert all(ms > 0 for ms, n in counts.values())
+    assert e.get_mac_profile(8) == (0.0, 0)              # reset by the read above
+    assert e.blockcounter() == P + 8 + 8 + 4 + 2 + 1
+
+
 @pytest.mark.parametrize("rs,groups,P", [(8, 1, 5), (4, 1, 2), (4, 1, 7), (8, 3, 4)])
 def test_host_quads_equal_single_blocks(pkg, rs, groups, P):
     """bfir_run_async_quad: four blocks of pinned host buffers per call through the stage pipeline (input copies, forward
