@@ -843,14 +843,16 @@ def test_stage_pipeline_quads_equal_single_blocks(pkg, rs, out_fmt, P):
             assert dd.max() <= 1, (b, dd.max())      # S16 from the float engine, S24 from the double one: within 1 LSB
 
 
-@pytest.mark.parametrize("rs,out_fmt,P,S,C,xb", [(8, 10, 5, 20, 4, 0), (4, 8, 5, 40, 4, 0), (8, 10, 2, 20, 4, 0), (4, 2, 9, 40, 4, 0),
-                                                 (8, 4, 3, 24, 4, 0), (4, 8, 4, 8, 32, 32), (4, 8, 6, 2, 2, 0)])
-def test_eight_blocks_per_call_equal_single_blocks(pkg, rs, out_fmt, P, S, C, xb):
+@pytest.mark.parametrize("rs,out_fmt,P,S,C,xb,cb", [(8, 10, 5, 20, 4, 0, 5), (4, 8, 5, 40, 4, 0, 5), (8, 10, 2, 20, 4, 0, 2), (4, 2, 9, 40, 4, 0, 9),
+                                                    (8, 4, 3, 24, 4, 0, 3), (4, 8, 4, 8, 32, 32, 4), (4, 8, 6, 2, 2, 0, 6),
+                                                    (8, 10, 9, 20, 4, 0, 6), (4, 8, 11, 40, 4, 0, 1)])
+def test_eight_blocks_per_call_equal_single_blocks(pkg, rs, out_fmt, P, S, C, xb, cb):
     """bfir_run_device_oct: eight blocks per call with ONE partition-sum launch (partition_mac_oct_kernel: a thread owns
     8 reals of an ORD group in single precision, 4 in double precision, circular window of eight delay-line spectra),
     joined and staged, mixed with four- and two-block calls and single blocks, with a crossbar, with integer output;
-    the last case is too small for the one-slice kernel and falls back to two four-block calls. P = 2 turns every delay-line
-    slot over within one call (P + 15 slots). Same output as block by block."""
+    one case is too small for the one-slice kernel and falls back to two four-block calls. P = 2 turns every delay-line
+    slot over within one call (P + 15 slots); cb < P: filters with fewer coefficient partitions than the engine has
+    (brutefir.cpp:292). Same output as block by block."""
     import torch
     L = 2048
     in_fmt = pkg.FLOAT_LE if rs == 4 else pkg.FLOAT64_LE
@@ -858,13 +860,13 @@ def test_eight_blocks_per_call_equal_single_blocks(pkg, rs, out_fmt, P, S, C, xb
     nb = pkg.FORMAT_BYTES[out_fmt]
     n_in = xb or C
     n_out = xb or C
-    h = [decay_filter(c % 7, L * P) * (1 + 0.01 * c) for c in range(C * S)]
+    h = [decay_filter(c % 7, L * cb) * (1 + 0.01 * c) for c in range(C * S)]
     kw = dict(n_streams=S, n_groups=1)
     if xb:
         kw.update(xbar_inputs=xb, xbar_outputs=xb)
     single = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, False, **kw)
     octs = pkg.Brutefir(L, P, rs, C, in_fmt, out_fmt, 2000, False, **kw)
-    assert single.set_coeff(h, P) == 0 and octs.set_coeff(h, P) == 0
+    assert single.set_coeff(h, cb) == 0 and octs.set_coeff(h, cb) == 0
     if xb:
         rng = np.random.default_rng(3)
         gin, gout = rng.standard_normal((C, xb)) / np.sqrt(xb), rng.standard_normal((xb, C)) / np.sqrt(C)
