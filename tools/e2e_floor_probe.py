@@ -10,7 +10,7 @@ import torch
 pkg = importlib.import_module("foo-dsp-bfir_b200")
 L, C, S, steps = 8192, 8, 16, 400
 Ps = [int(x) for x in sys.argv[1:]] or [32, 2]
-n_host = 12
+n_host = 16
 host_in = [torch.rand(S * L * C, dtype=torch.float64).pin_memory() for _ in range(n_host)]
 host_out = [torch.empty(S * L * C, dtype=torch.float64).pin_memory() for _ in range(n_host)]
 ins, outs = [h.numpy() for h in host_in], [h.numpy() for h in host_out]
@@ -21,7 +21,7 @@ for P in Ps:
     for b in range(P + 2):
         e.run(ins[b % n_host], outs[0])
     res = {"P": P}
-    for mode, groups, depth in (("quad", 1, 2), ("quad", 1, 1), ("pair", 4, 3), ("pair", 1, 3)):
+    for mode, groups, depth in (("quad", 1, 3), ("quad", 1, 2), ("quad", 1, 1), ("pair", 4, 3), ("pair", 4, 5)):
         e.set_groups(groups)
         per = 4 if mode == "quad" else 2
         times = []
