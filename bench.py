@@ -383,7 +383,7 @@ def main():
     # groups with their own copy streams), median of 3 passes of K steps (the pass is half host work, and the hosts
     # of this pool are noisy). Beside it: one block per call (bfir_run_async) and the reference's synchronous run().
     DEPTH = 3
-    QDEPTH = 2
+    QDEPTH = 3      # four-block calls in flight before the host waits for the oldest (measured: 2 leaves the copy streams starving now and then)
 
     def e2e_pass(engine, ins, outs, steps, sync_groups, async_groups):
         engine.set_groups(min(sync_groups, S))
@@ -428,7 +428,7 @@ def main():
         t_single = async_pass(False)
 
         # four blocks per call through the stage pipeline (bfir_run_async_quad): ONE stream group -- whole-block copies
-        # on one copy stream each way, five streams in all --, QDEPTH calls in flight
+        # alternating between two copy streams each way, seven streams in all --, QDEPTH + 1 calls in flight
         def quad_pass():
             barrier()
             tickets = []
@@ -450,7 +450,7 @@ def main():
         t_quads = sorted(quad_pass() for _ in range(3))
         return max_over_ranks(t_sync), t_pairs, t_single, groups, t_quads
 
-    e2e_steps = max(K, 200) - max(K, 200) % 2   # fill and drain of the copy pipeline are a fixed cost: time at least 200 steps
+    e2e_steps = max(K, 400) - max(K, 400) % 4   # fill and drain of the copy pipeline are a fixed cost: time at least 400 steps
     n_host = max(2 * (DEPTH + 1), 4 * (QDEPTH + 1))
     host_ins = host_in + [torch.from_numpy(noise_block(1000 * rank + 50 + b, S, L, C)).contiguous().pin_memory() for b in range(n_host - ring)]
     host_outs = [host_out] + [torch.empty(S * L * C, dtype=torch.float64).pin_memory() for _ in range(n_host - 1)]
@@ -652,7 +652,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": S * L * C * 8,
                     "d2h_bytes_per_step": S * L * C * 8, "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
                     "api": ("bfir_run_async_quad(4 pinned host in, 4 pinned host out) + bfir_wait: H2D + kernels + D2H of every block through the stage "
-                            "pipeline (one stream group, five streams), %d calls in flight; median of 3 passes" % (QDEPTH + 1)) if e2e_quads else
+                            "pipeline (one stream group, two copy streams each way), %d calls in flight; median of 3 passes" % (QDEPTH + 1)) if e2e_quads else
                            ("bfir_run_async_pair(pinned host in x2, pinned host out x2) + bfir_wait: H2D + kernels + D2H of every block, "
                             "%d calls in flight, %d stream groups with their own copy streams; median of 3 passes" % (DEPTH, e2e_groups)),
                     "passes_ms_per_step": [1e3 * t / e2e_steps for t in (t_quads if e2e_quads else t_pairs)],

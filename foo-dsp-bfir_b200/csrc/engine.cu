@@ -167,6 +167,8 @@ struct Engine {
     int staged_blocks(int nb, const void *const *d_in, void *const *d_out, const void *const *h_in = nullptr, void *const *h_out = nullptr);
     long long run_host_async_quad(const void *const in[4], void *const out[4]);
     cudaEvent_t q_in_ready[4] = {}, q_out_ready[4] = {};   // four-block host calls: block b has arrived / has been emitted
+    int host_copy_streams = 2;      // copy streams each way of the four-block host calls (BFIR_HOST_COPY_STREAMS = 1 .. 4)
+    bool host_staged_open = false;  // those streams hold copies the engine's stream has not joined
     // BFIR_COPY_TIMING=1 (diagnosis): CUDA-event brackets around every copy of the four-block host path, summarised on stderr by destroy()
     bool copy_timing = false;
     std::vector<cudaEvent_t> ct_h2d, ct_d2h;
@@ -276,6 +278,7 @@ int Engine::init(const bfir_config_t &c)
     if (const char *env = getenv("BFIR_COPY_TIMING")) copy_timing = atoi(env) != 0;
     if (const char *env = getenv("BFIR_SHARD_TIMING")) shard_timing = atoi(env) != 0;
     if (const char *env = getenv("BFIR_BATCH_STAGES")) batch_stages = atoi(env) != 0;
+    if (const char *env = getenv("BFIR_HOST_COPY_STREAMS")) { const int v = atoi(env); if (v >= 1 && v <= 4) host_copy_streams = v; }
     if (const char *env = getenv("BFIR_MAC_SMS")) { const int v = atoi(env); if (v >= 1 && v <= 1024) mac_persist_sms = v; }
     if (const char *env = getenv("BFIR_WHOLE_COPIES")) whole_copies = atoi(env) != 0;
     if (const char *env = getenv("BFIR_STAGE")) { const int v = atoi(env); if (v >= 1 && v <= kStage) stage_count = v; }
@@ -1050,10 +1053,13 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
         for (int k = 0; k < 2; k++) { BFIR_CUDA(cudaEventRecord(sp_mac_done[k], stream)); BFIR_CUDA(cudaEventRecord(sp_inv_done[k], sp_inv)); }
         if (host) {
             for (int k = 0; k < kStage; k++) if ((rc = stage_alloc(k)) != BFIR_OK) return rc;
-            BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, fork_ev, 0));
-            BFIR_CUDA(cudaStreamWaitEvent(grp.d2h, fork_ev, 0));
+            for (int c = 0; c < host_copy_streams; c++) {
+                BFIR_CUDA(cudaStreamWaitEvent(groups[c].h2d, fork_ev, 0));
+                BFIR_CUDA(cudaStreamWaitEvent(groups[c].d2h, fork_ev, 0));
+            }
             for (int k = 0; k < kStage; k++) { BFIR_CUDA(cudaEventRecord(grp.in_free[k], sp_fwd)); BFIR_CUDA(cudaEventRecord(grp.out_free[k], grp.d2h)); }
             async_open = async_copies = true;
+            host_staged_open = true;
         }
         sp_open = true;
         sp_pairs = 0;
@@ -1069,11 +1075,14 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
         for (int b = 0; b < nb; b++) {
             slot[b] = (int)((stage_next + (unsigned long long)b) % (unsigned long long)sc);
             dev_in[b] = stage_in[slot[b]]; dev_out[b] = stage_out[slot[b]];
-            BFIR_CUDA(cudaStreamWaitEvent(grp.h2d, grp.in_free[slot[b]], 0));
-            copy_mark(ct_h2d, grp.h2d);
-            BFIR_CUDA(cudaMemcpyAsync(stage_in[slot[b]], h_in[b], in_bytes, cudaMemcpyHostToDevice, grp.h2d));
-            copy_mark(ct_h2d, grp.h2d);
-            BFIR_CUDA(cudaEventRecord(q_in_ready[b], grp.h2d));
+            // consecutive blocks alternate between the copy streams of the first host_copy_streams groups: a copy that still
+            // waits for its slot does not hold up the next one, and the copy engine always finds a runnable copy queued
+            cudaStream_t h2d = groups[b % host_copy_streams].h2d;
+            BFIR_CUDA(cudaStreamWaitEvent(h2d, grp.in_free[slot[b]], 0));
+            copy_mark(ct_h2d, h2d);
+            BFIR_CUDA(cudaMemcpyAsync(stage_in[slot[b]], h_in[b], in_bytes, cudaMemcpyHostToDevice, h2d));
+            copy_mark(ct_h2d, h2d);
+            BFIR_CUDA(cudaEventRecord(q_in_ready[b], h2d));
         }
         stage_next += (unsigned long long)nb;
         d_in = dev_in; d_out = dev_out;
@@ -1161,14 +1170,15 @@ int Engine::staged_blocks(int nb, const void *const *d_in, void *const *d_out, c
     BFIR_CUDA(cudaEventRecord(sp_inv_done[par], sp_inv));
     if (host) {
         for (int b = 0; b < nb; b++) {
-            BFIR_CUDA(cudaStreamWaitEvent(grp.d2h, q_out_ready[b], 0));
-            copy_mark(ct_d2h, grp.d2h);
-            BFIR_CUDA(cudaMemcpyAsync(h_out[b], stage_out[slot[b]], out_bytes, cudaMemcpyDeviceToHost, grp.d2h));
-            copy_mark(ct_d2h, grp.d2h);
-            BFIR_CUDA(cudaEventRecord(grp.out_free[slot[b]], grp.d2h));
+            cudaStream_t d2h = groups[b % host_copy_streams].d2h;
+            BFIR_CUDA(cudaStreamWaitEvent(d2h, q_out_ready[b], 0));
+            copy_mark(ct_d2h, d2h);
+            BFIR_CUDA(cudaMemcpyAsync(h_out[b], stage_out[slot[b]], out_bytes, cudaMemcpyDeviceToHost, d2h));
+            copy_mark(ct_d2h, d2h);
+            BFIR_CUDA(cudaEventRecord(grp.out_free[slot[b]], d2h));
             const int tslot = (int)((next_ticket + b) % kMaxInflight);
             if (ticket_ev[tslot][0] == nullptr) BFIR_CUDA(cudaEventCreateWithFlags(&ticket_ev[tslot][0], cudaEventDisableTiming));
-            BFIR_CUDA(cudaEventRecord(ticket_ev[tslot][0], grp.d2h));
+            BFIR_CUDA(cudaEventRecord(ticket_ev[tslot][0], d2h));
         }
     }
     sp_pairs++;
@@ -1736,7 +1746,9 @@ int Engine::close_async()
     async_open = false;
     if (async_copies) { // the output copies are the last link of every group's chain
         async_copies = false;
-        for (int g = 0; g < n_groups; g++) {
+        const int ncopy = host_staged_open && host_copy_streams > n_groups ? host_copy_streams : n_groups;
+        host_staged_open = false;
+        for (int g = 0; g < ncopy; g++) {
             BFIR_CUDA(cudaEventRecord(groups[g].copies_done, groups[g].d2h));
             BFIR_CUDA(cudaStreamWaitEvent(stream, groups[g].copies_done, 0));
             BFIR_CUDA(cudaEventRecord(groups[g].copies_done, groups[g].h2d));

@@ -211,9 +211,11 @@ int bfir_run_device_quad_staged(bfir_engine *e, const void *const d_in[4], void 
 int bfir_run_device_oct(bfir_engine *e, const void *const d_in[8], void *const d_out[8], int staged);
 /* Four consecutive blocks of PINNED host buffers through the stage pipeline (one stream group; otherwise, and outside
  * the steady state, two bfir_run_async_pair calls): the input copies of block b, its forward transform, the four-block
- * partition sum, the inverse transforms and the output copies run on five streams chained by events over a ring of 12
- * staging slots, so the copies of neighbouring calls overlap the kernels of this one. Returns the ticket of the FOURTH
- * block (bfir_wait on it covers all four). Up to three calls can be in flight before a call waits for the oldest. */
+ * partition sum, the inverse transforms and the output copies run on seven streams chained by events over a ring of 12
+ * staging slots (consecutive blocks alternate between two copy streams each way, so that a copy which still waits for
+ * its slot never holds up the next one), and the copies of neighbouring calls overlap the kernels of this one. Returns
+ * the ticket of the FOURTH block (bfir_wait on it covers all four). Keep four calls in flight to hold the link's rate
+ * (16 tickets may be outstanding before a call waits for the oldest). */
 long long bfir_run_async_quad(bfir_engine *e, const void *const in[4], void *const out[4]);
 
 /* brutefir::reset (brutefir.cpp:347-367): zeroes counters and overflow statistics, NOT the buffers */

@@ -21,11 +21,11 @@ for P in Ps:
     for b in range(P + 2):
         e.run(ins[b % n_host], outs[0])
     res = {"P": P}
-    for mode, groups, depth in (("quad", 1, 3), ("quad", 1, 2), ("quad", 1, 1), ("pair", 4, 3), ("pair", 4, 5)):
+    for mode, groups, depth in (("quad", 1, 2), ("pair", 4, 3), ("quad", 1, 2), ("quad", 1, 3)):
         e.set_groups(groups)
         per = 4 if mode == "quad" else 2
         times = []
-        for rep in range(4):
+        for rep in range(7):
             tickets = []
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -41,5 +41,6 @@ for P in Ps:
             torch.cuda.synchronize()
             times.append((time.perf_counter() - t0) / steps * 1e3)
         res["%s_g%d_d%d" % (mode, groups, depth)] = sorted(times[1:])[1]
+        res["%s_g%d_d%d_all" % (mode, groups, depth)] = [round(x, 4) for x in times]
     e.close()
     print(json.dumps(res))
